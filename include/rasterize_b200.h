@@ -1,0 +1,177 @@
+/* rasterize_b200 — C ABI of the B200-native fill pipeline (flatten -> signed-difference raster ->
+ * paint/composite).  This is the drop-in boundary a Rust `GpuRasterizer: Rasterizer` binds over FFI
+ * (see INTEGRATION.md for the `extern "C"` block and build.rs).  Plain pointers and sizes only.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the reference
+ * crate aslpavel/rasterize v0.6.7).  All functions return RGPU_OK (0) or a negative status; the text
+ * of the last error is available from rgpu_last_error().  The Rust shim turns a non-zero status
+ * into `panic!`, which is the reference's behaviour on bad input (src/path.rs:765-767).
+ *
+ * There is NO CPU fallback: if no CUDA device is usable rgpu_create fails with RGPU_ERR_CUDA.
+ *
+ * Threading: a context may be used from one thread at a time (the reference rasterizers are
+ * stateless `&self` objects, src/rasterize.rs:279-296; the shim wraps the context in a Mutex).
+ */
+#ifndef RASTERIZE_B200_H
+#define RASTERIZE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGPU_OK 0
+#define RGPU_ERR_INVALID (-1)   /* bad argument (null pointer, flatness <= 0, bad kind ...) */
+#define RGPU_ERR_CUDA (-2)      /* CUDA runtime error, text in rgpu_last_error */
+#define RGPU_ERR_NAN (-3)       /* a control point is NaN: reference panics "cannot flatten segment with NaN" */
+#define RGPU_ERR_DEPTH (-4)     /* subdivision deeper than the device stack (reference would recurse without bound) */
+#define RGPU_ERR_CAPACITY (-5)  /* output buffer supplied by the caller is too small */
+
+typedef struct rgpu_ctx rgpu_ctx;
+typedef struct rgpu_dpath rgpu_dpath; /* device-resident path */
+
+/* FillRule, src/path.rs:21-29 */
+enum { RGPU_NONZERO = 0, RGPU_EVENODD = 1 };
+
+/* Flat re-encoding of `Path { segments, subpaths, closed }` (src/path.rs:227-233; `Segment` is a Rust
+ * enum and not FFI-stable, src/curve.rs:905-909).  Segment i owns `kinds[i]` consecutive points
+ * (2 = Line, 3 = Quad, 4 = Cubic; src/curve.rs:163,349,614), segments are stored back to back in `points`.
+ * Subpath s is segments [subpath_offsets[s], subpath_offsets[s+1]). */
+typedef struct {
+    const double* points;            /* 2 * n_points, (x, y) pairs */
+    const uint8_t* kinds;            /* n_segments */
+    const uint32_t* subpath_offsets; /* n_subpaths + 1 (may be NULL when n_subpaths == 0) */
+    const uint8_t* closed;           /* n_subpaths */
+    uint32_t n_points, n_segments, n_subpaths;
+} rgpu_path;
+
+/* `Shape`, src/image.rs:6-17 (element strides, not bytes) */
+typedef struct {
+    size_t start, width, height, row_stride, col_stride;
+} rgpu_shape;
+
+/* `Pixel`, src/rasterize.rs (x, y, alpha) as yielded by `Rasterizer::mask_iter` */
+typedef struct {
+    size_t x, y;
+    double alpha;
+} rgpu_pixel;
+
+/* Paint description: `impl Paint for LinColor` (src/color.rs:357-374), `GradLinear` (src/grad.rs:150-160),
+ * `GradRadial` (src/grad.rs:307-317).  Stop colours are in the space the gradient STORES them, i.e. after
+ * `convert_to_srgb` when `linear_colors == 0` (src/grad.rs:165-191). */
+enum { RGPU_PAINT_SOLID = 0, RGPU_PAINT_LINEAR = 1, RGPU_PAINT_RADIAL = 2 };
+enum { RGPU_UNITS_USER_SPACE = 0, RGPU_UNITS_BOUNDING_BOX = 1 }; /* `Units`, src/rasterize.rs:171-176 */
+enum { RGPU_SPREAD_PAD = 0, RGPU_SPREAD_REPEAT = 1, RGPU_SPREAD_REFLECT = 2 }; /* `GradSpread`, src/grad.rs:13-20 */
+#define RGPU_MAX_STOPS 32
+typedef struct {
+    int32_t kind, units, linear_colors, spread;
+    double tr[6];    /* `Paint::transform` */
+    double p0[2];    /* linear: start ; radial: center */
+    double p1[2];    /* linear: end   ; radial: fcenter */
+    double r0, r1;   /* radial: radius, fradius */
+    float solid[4];  /* solid: premultiplied linear RGBA */
+    uint32_t n_stops;
+    const double* stop_pos;   /* n_stops */
+    const float* stop_colors; /* 4 * n_stops, premultiplied, stored space */
+} rgpu_paint;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+/* `SignedDifferenceRasterizer::new(flatness)` (src/rasterize.rs:284-296) on CUDA device `device`. */
+int rgpu_create(int device, double flatness, rgpu_ctx** out);
+void rgpu_destroy(rgpu_ctx* ctx);
+/* `Rasterizer::name` (src/rasterize.rs:46, 357-359) */
+const char* rgpu_name(void);
+const char* rgpu_last_error(const rgpu_ctx* ctx); /* ctx may be NULL: error of the last failed rgpu_create */
+int rgpu_device_count(void);
+
+/* ---- trait-level entry points: HOST buffers in, HOST buffers out --------------------------------- */
+/* `Path::flatten(tr, flatness, close)` (src/path.rs:418-425, 744-795): lines_out receives 4 doubles per line
+ * (x0,y0,x1,y1) in the reference's order; *n_out is always the full count (RGPU_ERR_CAPACITY if > cap). */
+int rgpu_flatten(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int close, double* lines_out, size_t cap,
+                 size_t* n_out);
+/* `Rasterizer::mask` (src/rasterize.rs:50-56, 299-311): img is a strided f64 host image, assumed zero on
+ * entry (src/path.rs:511-512) and overwritten with coverage; its last column is the anti-alias overflow
+ * column exactly as in the reference (src/rasterize.rs:372). */
+int rgpu_mask(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill_rule, double* img, rgpu_shape shape);
+/* Same semantics, dense row-major f32 host image (the device-native format). */
+int rgpu_mask_f32(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill_rule, float* img, size_t width,
+                  size_t height);
+/* `Rasterizer::mask_iter` (src/rasterize.rs:61-67, 313-355): pixels with abs(alpha) >= 1e-6 in row-major
+ * order; internal (width+1) canvas, overflow column dropped. *n_out is the full count. */
+int rgpu_mask_iter(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], size_t width, size_t height, int fill_rule,
+                   rgpu_pixel* out, size_t cap, size_t* n_out);
+/* Dense form of mask_iter: coverage[y*width + x] (0 where the iterator yields nothing). */
+int rgpu_coverage_f32(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill_rule, float* out, size_t width,
+                      size_t height);
+/* Default `Rasterizer::fill` (src/rasterize.rs:70-115): blend `paint` through the coverage of `path` over the
+ * strided LinColor (f32 x 4, premultiplied linear) host image.  path_bbox = `path.bbox(identity)` as
+ * (minx,miny,maxx,maxy), needed only for RGPU_UNITS_BOUNDING_BOX (NULL there => no-op, src/rasterize.rs:87-90).
+ * A singular paint transform is a silent no-op (src/rasterize.rs:92). */
+int rgpu_fill(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill_rule, const rgpu_paint* paint,
+              const double* path_bbox, float* img, rgpu_shape shape);
+
+/* ---- device-resident entry points (inputs and outputs stay in HBM) -------------------------------- */
+int rgpu_path_upload(rgpu_ctx* ctx, const rgpu_path* path, rgpu_dpath** out);
+void rgpu_path_free(rgpu_ctx* ctx, rgpu_dpath* p);
+
+/* One fill job of a batch.  `canvas` is a DEVICE pointer; the job covers the `width` x `height` window whose
+ * top-left element is canvas[origin] with `row_stride` elements between rows (elements = f32 for masks,
+ * 4 x f32 for colour).  This is the device form of `Path::fill` on a `view_mut` sub-image
+ * (src/scene.rs:412-429) and of `Path::mask`. */
+enum {
+    RGPU_JOB_MASK = 0,     /* Rasterizer::mask semantics  -> f32 coverage, last column = overflow column */
+    RGPU_JOB_COVERAGE = 1, /* mask_iter semantics         -> f32 coverage, (width+1) internal columns */
+    RGPU_JOB_FILL = 2      /* Rasterizer::fill semantics  -> blend paint over LinColor canvas */
+};
+typedef struct {
+    const rgpu_dpath* path;
+    double tr[6];
+    int32_t fill_rule;
+    int32_t mode;
+    const rgpu_paint* paint;  /* RGPU_JOB_FILL only (host pointer, copied at submission) */
+    const double* path_bbox;  /* RGPU_JOB_FILL with bounding-box units */
+    void* canvas;             /* device pointer */
+    size_t origin, row_stride; /* in elements */
+    uint32_t width, height;
+} rgpu_job;
+
+/* Batch flags */
+#define RGPU_BATCH_ORDERED 0u     /* jobs may overlap; composited in submission order (Scene::render Fill arm) */
+#define RGPU_BATCH_INDEPENDENT 1u /* caller guarantees disjoint outputs: one raster launch for all jobs */
+
+/* Flatten + bin + rasterize `n_jobs` jobs on the context's stream (asynchronous; call rgpu_sync or
+ * rgpu_batch_status afterwards).  Replaces the per-node loop of `Pipeline::render_rec` (src/scene.rs:397-435)
+ * for Fill nodes and a batch of `Path::mask` calls. */
+int rgpu_render_batch(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags);
+/* Waits for the stream and reports device-side errors of the last batch (NaN, depth, internal capacity —
+ * the latter is retried transparently by the host-buffer entry points and by rgpu_render_batch_sync). */
+int rgpu_batch_status(rgpu_ctx* ctx);
+/* rgpu_render_batch + rgpu_batch_status with transparent scratch growth and re-run on internal overflow. */
+int rgpu_render_batch_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags);
+/* Lines produced by the flatten stage of the last completed batch, and kernels launched since create. */
+int rgpu_last_counts(rgpu_ctx* ctx, uint64_t* n_lines, uint64_t* n_line_refs, uint64_t* n_launches);
+
+/* LinColor (f32x4) device image -> RGBA8 device image: `From<LinColor> for RGBA` (src/color.rs:164-175) with the
+ * x86 `l2s` polynomial (src/simd/x86.rs:197-214). n = pixels. */
+int rgpu_to_rgba8_dev(rgpu_ctx* ctx, const float* lin_dev, uint8_t* rgba_dev, size_t n_pixels);
+/* fill a LinColor device image with a constant (Layer::new with bg, src/scene.rs:483-501) */
+int rgpu_fill_color_dev(rgpu_ctx* ctx, float* lin_dev, size_t n_pixels, const float color[4]);
+
+/* ---- plumbing ----------------------------------------------------------------------------------- */
+void* rgpu_stream(rgpu_ctx* ctx);  /* cudaStream_t the context launches on */
+int rgpu_sync(rgpu_ctx* ctx);
+int rgpu_device_alloc(rgpu_ctx* ctx, size_t bytes, void** out);
+int rgpu_device_free(rgpu_ctx* ctx, void* p);
+int rgpu_device_zero(rgpu_ctx* ctx, void* p, size_t bytes);
+int rgpu_memcpy_h2d(rgpu_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int rgpu_memcpy_d2h(rgpu_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+/* pinned host memory for images handed to the host-buffer entry points (they also accept pageable memory) */
+int rgpu_host_alloc(rgpu_ctx* ctx, size_t bytes, void** out);
+int rgpu_host_free(rgpu_ctx* ctx, void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RASTERIZE_B200_H */

@@ -1,0 +1,586 @@
+"""Host-side mirror of the reference's interface for the fill path, on top of the C ABI.
+
+Names, argument meaning and error behaviour follow aslpavel/rasterize v0.6.7 (paths relative to the reference):
+`Path` / `PathBuilder` (src/path.rs:227-233, 800-1056), `Transform` (src/geometry.rs:317-539), `FillRule`
+(src/path.rs:21-29), `Size`, `Rasterizer::{name, mask, mask_iter, fill}` (src/rasterize.rs:44-101), `Units`,
+`LinColor` / `GradLinear` / `GradRadial` paints (src/color.rs:357-374, src/grad.rs:150-226, 307-426).
+
+Everything that computes goes through librasterize_b200.so; nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import math
+from dataclasses import dataclass
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import ffi
+from .ffi import RgpuError
+
+DEFAULT_FLATNESS = 0.05  # src/path.rs:16
+EPSILON = float(np.finfo(np.float64).eps)
+
+
+class FillRule(enum.IntEnum):
+    NonZero = 0
+    EvenOdd = 1
+
+
+class Units(enum.IntEnum):
+    UserSpaceOnUse = 0
+    BoundingBox = 1
+
+
+class GradSpread(enum.IntEnum):
+    Pad = 0
+    Repeat = 1
+    Reflect = 2
+
+
+@dataclass(frozen=True)
+class Size:
+    width: int
+    height: int
+
+
+class Transform:
+    """2x3 affine `[m00, m01, m02, m10, m11, m12]` (src/geometry.rs:317)."""
+
+    __slots__ = ("m",)
+
+    def __init__(self, m00=1.0, m01=0.0, m02=0.0, m10=0.0, m11=1.0, m12=0.0):
+        self.m = (float(m00), float(m01), float(m02), float(m10), float(m11), float(m12))
+
+    @staticmethod
+    def identity() -> "Transform":
+        return Transform()
+
+    @staticmethod
+    def from_array(a) -> "Transform":
+        return Transform(*[float(v) for v in np.asarray(a).reshape(6)])
+
+    @staticmethod
+    def new_translate(tx, ty) -> "Transform":
+        return Transform(1.0, 0.0, tx, 0.0, 1.0, ty)
+
+    @staticmethod
+    def new_scale(sx, sy) -> "Transform":
+        return Transform(sx, 0.0, 0.0, 0.0, sy, 0.0)
+
+    @staticmethod
+    def new_rotate(a) -> "Transform":
+        s, c = math.sin(a), math.cos(a)
+        return Transform(c, -s, 0.0, s, c, 0.0)
+
+    def __mul__(self, o: "Transform") -> "Transform":  # src/geometry.rs:519-539
+        s, t = self.m, o.m
+        return Transform(s[0] * t[0] + s[1] * t[3], s[0] * t[1] + s[1] * t[4], s[0] * t[2] + s[1] * t[5] + s[2],
+                         s[3] * t[0] + s[4] * t[3], s[3] * t[1] + s[4] * t[4], s[3] * t[2] + s[4] * t[5] + s[5])
+
+    def pre_translate(self, tx, ty) -> "Transform":
+        return self * Transform.new_translate(tx, ty)
+
+    def pre_scale(self, sx, sy) -> "Transform":
+        return self * Transform.new_scale(sx, sy)
+
+    def pre_rotate(self, a) -> "Transform":
+        return self * Transform.new_rotate(a)
+
+    def apply(self, p):  # src/geometry.rs:363-367
+        m = self.m
+        x, y = p
+        return (x * m[0] + y * m[1] + m[2], x * m[3] + y * m[4] + m[5])
+
+    def array(self) -> np.ndarray:
+        return np.array(self.m, dtype=np.float64)
+
+    def __repr__(self):
+        return "Transform(%r, %r, %r, %r, %r, %r)" % self.m
+
+
+def _as_tr(tr) -> np.ndarray:
+    if isinstance(tr, Transform):
+        return tr.array()
+    return np.ascontiguousarray(np.asarray(tr, dtype=np.float64).reshape(6))
+
+
+class Path:
+    """Flat `Path { segments, subpaths, closed }` (src/path.rs:227-233): the encoding that crosses the FFI."""
+
+    def __init__(self, points, kinds, subpath_offsets, closed):
+        self.points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 2)
+        self.kinds = np.ascontiguousarray(kinds, dtype=np.uint8)
+        self.closed = np.ascontiguousarray(closed, dtype=np.uint8)
+        so = np.ascontiguousarray(subpath_offsets, dtype=np.uint32)
+        if len(self.closed) == 0:
+            so = np.zeros(0, dtype=np.uint32)
+        self.subpath_offsets = so
+
+    @staticmethod
+    def empty() -> "Path":
+        return Path(np.zeros((0, 2)), [], [], [])
+
+    @staticmethod
+    def builder() -> "PathBuilder":
+        return PathBuilder()
+
+    @staticmethod
+    def load_npz(file) -> "Path":
+        z = np.load(file)
+        return Path(z["points"], z["kinds"], z["subpath_offsets"], z["closed"])
+
+    def save_npz(self, file) -> None:
+        np.savez_compressed(file, points=self.points, kinds=self.kinds, subpath_offsets=self.subpath_offsets, closed=self.closed)
+
+    def segments_count(self) -> int:  # src/path.rs:366-368
+        return int(len(self.kinds))
+
+    def is_empty(self) -> bool:
+        return len(self.closed) == 0
+
+    def transform(self, tr) -> "Path":
+        """`Path::transform` (src/path.rs:359-363) — returns a new path"""
+        m = _as_tr(tr)
+        x, y = self.points[:, 0], self.points[:, 1]
+        pts = np.stack([x * m[0] + y * m[1] + m[2], x * m[3] + y * m[4] + m[5]], axis=1)
+        return Path(pts, self.kinds, self.subpath_offsets, self.closed)
+
+    def input_bytes(self) -> int:
+        """Algorithmic input bytes: 16 B per control point."""
+        return int(self.points.shape[0]) * 16
+
+    def _c(self) -> ffi.CPath:
+        c = ffi.CPath()
+        c.points = self.points.ctypes.data_as(C.POINTER(C.c_double))
+        c.kinds = self.kinds.ctypes.data_as(C.POINTER(C.c_uint8))
+        c.subpath_offsets = self.subpath_offsets.ctypes.data_as(C.POINTER(C.c_uint32))
+        c.closed = self.closed.ctypes.data_as(C.POINTER(C.c_uint8))
+        c.n_points = self.points.shape[0]
+        c.n_segments = len(self.kinds)
+        c.n_subpaths = len(self.closed)
+        return c
+
+    # reference convenience methods: `Path::flatten/mask/fill` delegate to the rasterizer
+    def flatten(self, rasterizer: "GpuRasterizer", tr=Transform(), close: bool = True) -> np.ndarray:
+        return rasterizer.flatten(self, tr, close)
+
+    def mask(self, rasterizer: "GpuRasterizer", tr, fill_rule: FillRule, img: np.ndarray) -> np.ndarray:
+        rasterizer.mask(self, tr, img, fill_rule)
+        return img
+
+    def fill(self, rasterizer: "GpuRasterizer", tr, fill_rule: FillRule, paint, img: np.ndarray, bbox=None) -> np.ndarray:
+        rasterizer.fill(self, tr, fill_rule, paint, img, bbox=bbox)
+        return img
+
+
+class PathBuilder:
+    """`PathBuilder` (src/path.rs:800-1056) without arcs (arc -> cubic conversion stays on the Rust host side)."""
+
+    def __init__(self):
+        self.position = (0.0, 0.0)
+        self._pts: list = []
+        self._kinds: list = []
+        self._sub: list = []
+        self._closed: list = []
+
+    def _finish(self, close: bool):  # src/path.rs:849-868
+        n = len(self._kinds)
+        if n == 0 or (self._sub and self._sub[-1] == n):
+            return
+        if not self._sub:
+            self._sub.append(0)
+        if close:
+            first = self._sub[-1]
+            off = sum(self._kinds[:first])
+            self.position = self._pts[off]
+        self._sub.append(n)
+        self._closed.append(1 if close else 0)
+
+    def move_to(self, p) -> "PathBuilder":
+        self._finish(False)
+        self.position = (float(p[0]), float(p[1]))
+        return self
+
+    def close(self) -> "PathBuilder":
+        self._finish(True)
+        return self
+
+    def line_to(self, p) -> "PathBuilder":  # src/path.rs:895-903
+        p = (float(p[0]), float(p[1]))
+        if not (abs(self.position[0] - p[0]) < EPSILON and abs(self.position[1] - p[1]) < EPSILON):
+            self._pts += [self.position, p]
+            self._kinds.append(2)
+            self.position = p
+        return self
+
+    def quad_to(self, p1, p2) -> "PathBuilder":
+        p1, p2 = (float(p1[0]), float(p1[1])), (float(p2[0]), float(p2[1]))
+        self._pts += [self.position, p1, p2]
+        self._kinds.append(3)
+        self.position = p2
+        return self
+
+    def cubic_to(self, p1, p2, p3) -> "PathBuilder":
+        p1, p2, p3 = (float(p1[0]), float(p1[1])), (float(p2[0]), float(p2[1])), (float(p3[0]), float(p3[1]))
+        self._pts += [self.position, p1, p2, p3]
+        self._kinds.append(4)
+        self.position = p3
+        return self
+
+    def build(self) -> Path:
+        self._finish(False)
+        p = Path(np.array(self._pts, dtype=np.float64).reshape(-1, 2), self._kinds, self._sub, self._closed)
+        self.__init__()
+        return p
+
+
+# ---- paints -------------------------------------------------------------------------------------------
+class LinColor:
+    """Premultiplied linear RGBA f32x4; as a paint: `impl Paint for LinColor` (src/color.rs:357-374)."""
+
+    def __init__(self, r, g, b, a):
+        self.c = np.array([r, g, b, a], dtype=np.float32)
+
+    def _c(self, keep: list) -> ffi.CPaint:
+        p = ffi.CPaint()
+        p.kind = 0
+        p.tr[:] = (1.0, 0.0, 0.0, 0.0, 1.0, 0.0)
+        p.solid[:] = [float(v) for v in self.c]
+        return p
+
+
+@dataclass
+class GradStop:
+    position: float
+    color: Sequence[float]  # stored-space premultiplied f32x4
+
+
+class _Grad:
+    kind = 1
+
+    def __init__(self, stops, units, linear_colors, spread, tr):
+        self.stop_pos = np.ascontiguousarray([s.position if isinstance(s, GradStop) else s[0] for s in stops], dtype=np.float64)
+        self.stop_colors = np.ascontiguousarray([s.color if isinstance(s, GradStop) else s[1] for s in stops],
+                                                dtype=np.float32).reshape(-1, 4)
+        self.units = Units(units)
+        self.linear_colors = bool(linear_colors)
+        self.spread = GradSpread(spread)
+        self.tr = _as_tr(tr)
+
+    def _base(self, keep: list) -> ffi.CPaint:
+        p = ffi.CPaint()
+        p.kind = self.kind
+        p.units = int(self.units)
+        p.linear_colors = int(self.linear_colors)
+        p.spread = int(self.spread)
+        p.tr[:] = [float(v) for v in self.tr]
+        p.n_stops = len(self.stop_pos)
+        p.stop_pos = self.stop_pos.ctypes.data_as(C.POINTER(C.c_double))
+        p.stop_colors = self.stop_colors.ctypes.data_as(C.POINTER(C.c_float))
+        keep.append(self)
+        return p
+
+
+class GradLinear(_Grad):
+    """`GradLinear` (src/grad.rs:150-226).  `stops` carry the colours in the space the reference stores them
+    (after `convert_to_srgb` when `linear_colors` is false)."""
+    kind = 1
+
+    def __init__(self, stops, units, linear_colors, spread, tr, start, end):
+        super().__init__(stops, units, linear_colors, spread, tr)
+        self.start = (float(start[0]), float(start[1]))
+        self.end = (float(end[0]), float(end[1]))
+
+    def _c(self, keep: list) -> ffi.CPaint:
+        p = self._base(keep)
+        p.p0[:] = self.start
+        p.p1[:] = self.end
+        return p
+
+
+class GradRadial(_Grad):
+    """`GradRadial` (src/grad.rs:307-426)."""
+    kind = 2
+
+    def __init__(self, stops, units, linear_colors, spread, tr, center, radius, fcenter=None, fradius=0.0):
+        super().__init__(stops, units, linear_colors, spread, tr)
+        self.center = (float(center[0]), float(center[1]))
+        self.fcenter = self.center if fcenter is None else (float(fcenter[0]), float(fcenter[1]))
+        self.radius, self.fradius = float(radius), float(fradius)
+
+    def _c(self, keep: list) -> ffi.CPaint:
+        p = self._base(keep)
+        p.p0[:] = self.center
+        p.p1[:] = self.fcenter
+        p.r0, p.r1 = self.radius, self.fradius
+        return p
+
+
+def paint_from_desc(d: dict):
+    """Paint from the flat description used by the golden fixtures (kind, units, ..., stop_pos, stop_colors)."""
+    kind = int(d["kind"])
+    if kind == 0:
+        return LinColor(*[float(v) for v in d["solid"]])
+    stops = list(zip([float(v) for v in d["stop_pos"]], np.asarray(d["stop_colors"], dtype=np.float32).reshape(-1, 4)))
+    if kind == 1:
+        return GradLinear(stops, int(d["units"]), bool(d["linear_colors"]), int(d["spread"]), d["tr"], d["p0"], d["p1"])
+    return GradRadial(stops, int(d["units"]), bool(d["linear_colors"]), int(d["spread"]), d["tr"], d["p0"], float(d["r0"]),
+                      d["p1"], float(d["r1"]))
+
+
+# ---- device objects -------------------------------------------------------------------------------------
+class DevicePath:
+    """Device-resident path (`rgpu_dpath`)."""
+
+    def __init__(self, rast: "GpuRasterizer", path: Path):
+        self.rast = rast
+        self.path = path
+        h = C.c_void_p()
+        c = path._c()
+        rast._check(ffi.lib().rgpu_path_upload(rast.ctx, C.byref(c), C.byref(h)))
+        self.h = h
+
+    def free(self):
+        if self.h:
+            ffi.lib().rgpu_path_free(self.rast.ctx, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+@dataclass
+class Job:
+    """One entry of `GpuRasterizer.render_batch` (`rgpu_job`)."""
+    path: DevicePath
+    tr: object
+    fill_rule: FillRule
+    mode: int           # ffi.JOB_MASK / JOB_COVERAGE / JOB_FILL
+    canvas: int         # device pointer
+    width: int
+    height: int
+    row_stride: int
+    origin: int = 0
+    paint: object = None
+    path_bbox: object = None
+
+
+class GpuRasterizer:
+    """`impl Rasterizer` on a B200 (`GpuRasterizer` of the north star); one CUDA context/stream per instance."""
+
+    def __init__(self, flatness: float = DEFAULT_FLATNESS, device: int = 0):
+        self.ctx = None
+        L = ffi.lib()
+        h = C.c_void_p()
+        rc = L.rgpu_create(device, float(flatness), C.byref(h))
+        if rc != 0:
+            raise RgpuError(rc, L.rgpu_last_error(None).decode())
+        self.ctx = h
+        self.flatness = float(flatness)
+        self.device = device
+
+    def close(self):
+        if self.ctx:
+            ffi.lib().rgpu_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise RgpuError(rc, ffi.lib().rgpu_last_error(self.ctx).decode())
+
+    # -- Rasterizer trait ------------------------------------------------------------------------------
+    def name(self) -> str:
+        return ffi.lib().rgpu_name().decode()
+
+    def flatten(self, path: Path, tr=Transform(), close: bool = True) -> np.ndarray:
+        """`Path::flatten(tr, flatness, close)` -> [n,4] f64 lines (x0,y0,x1,y1) in the reference's order."""
+        L = ffi.lib()
+        c = path._c()
+        t = _as_tr(tr)
+        n = C.c_size_t()
+        cap = max(64, path.segments_count() * 32)
+        while True:
+            out = np.empty((cap, 4), dtype=np.float64)
+            rc = L.rgpu_flatten(self.ctx, C.byref(c), t.ctypes.data_as(C.POINTER(C.c_double)), int(close),
+                                out.ctypes.data_as(C.POINTER(C.c_double)), cap, C.byref(n))
+            if rc == ffi.ERR_CAPACITY and n.value > cap:
+                cap = n.value
+                continue
+            self._check(rc)
+            return out[: n.value].copy()
+
+    @staticmethod
+    def _shape_of(img: np.ndarray, elem: int):
+        """(base array pointer, CShape) of a 2-D (or [H,W,4]) possibly strided numpy view."""
+        h, w = img.shape[0], img.shape[1]
+        item = img.itemsize * elem
+        rs, cs = img.strides[0], img.strides[1]
+        if rs % item or cs % item or rs < 0 or cs < 0:
+            raise ValueError("image strides must be non-negative multiples of the pixel size")
+        if elem == 4 and (img.shape[2] != 4 or img.strides[2] != img.itemsize):
+            raise ValueError("LinColor images must be [H,W,4] with contiguous channels")
+        return CShapeOf(0, w, h, rs // item, cs // item)
+
+    def mask(self, path: Path, tr, img: np.ndarray, fill_rule: FillRule) -> None:
+        """`Rasterizer::mask`: img is an f64 (trait-faithful) or f32 (device-native) 2-D host image, zero on entry."""
+        L = ffi.lib()
+        c = path._c()
+        t = _as_tr(tr)
+        tp = t.ctypes.data_as(C.POINTER(C.c_double))
+        if img.dtype == np.float64:
+            shape = self._shape_of(img, 1)
+            self._check(L.rgpu_mask(self.ctx, C.byref(c), tp, int(fill_rule), img.ctypes.data, shape))
+        elif img.dtype == np.float32:
+            if not img.flags.c_contiguous:
+                raise ValueError("f32 masks must be dense row-major")
+            self._check(L.rgpu_mask_f32(self.ctx, C.byref(c), tp, int(fill_rule), img.ctypes.data, img.shape[1], img.shape[0]))
+        else:
+            raise TypeError("mask image must be float64 or float32")
+
+    def mask_iter(self, path: Path, tr, size: Size, fill_rule: FillRule):
+        """`Rasterizer::mask_iter`: list of (x, y, alpha) with abs(alpha) >= 1e-6, row-major order."""
+        L = ffi.lib()
+        c = path._c()
+        t = _as_tr(tr)
+        n = C.c_size_t()
+        cap = max(1, size.width * size.height)
+        buf = (ffi.CPixel * cap)()
+        self._check(L.rgpu_mask_iter(self.ctx, C.byref(c), t.ctypes.data_as(C.POINTER(C.c_double)), size.width, size.height,
+                                     int(fill_rule), buf, cap, C.byref(n)))
+        return [(buf[i].x, buf[i].y, buf[i].alpha) for i in range(n.value)]
+
+    def coverage(self, path: Path, tr, size: Size, fill_rule: FillRule) -> np.ndarray:
+        """Dense form of mask_iter: f32 [H,W]."""
+        L = ffi.lib()
+        c = path._c()
+        t = _as_tr(tr)
+        out = np.zeros((size.height, size.width), dtype=np.float32)
+        self._check(L.rgpu_coverage_f32(self.ctx, C.byref(c), t.ctypes.data_as(C.POINTER(C.c_double)), int(fill_rule),
+                                        out.ctypes.data, size.width, size.height))
+        return out
+
+    def fill(self, path: Path, tr, fill_rule: FillRule, paint, img: np.ndarray, bbox=None) -> None:
+        """Default `Rasterizer::fill`: blend `paint` over the f32 [H,W,4] LinColor host image in place.
+        `bbox` = `path.bbox(identity)` (minx,miny,maxx,maxy) for bounding-box units."""
+        if img.dtype != np.float32 or img.ndim != 3:
+            raise TypeError("fill image must be float32 [H,W,4]")
+        L = ffi.lib()
+        c = path._c()
+        t = _as_tr(tr)
+        keep: list = []
+        p = paint._c(keep)
+        bb = None
+        bbp = None
+        if bbox is not None:
+            bb = np.ascontiguousarray(bbox, dtype=np.float64)
+            bbp = bb.ctypes.data_as(C.POINTER(C.c_double))
+        shape = self._shape_of(img, 4)
+        self._check(L.rgpu_fill(self.ctx, C.byref(c), t.ctypes.data_as(C.POINTER(C.c_double)), int(fill_rule), C.byref(p), bbp,
+                                img.ctypes.data, shape))
+
+    # -- device-resident API ---------------------------------------------------------------------------
+    def upload(self, path: Path) -> DevicePath:
+        return DevicePath(self, path)
+
+    def _cjobs(self, jobs: Iterable[Job]):
+        jobs = list(jobs)
+        arr = (ffi.CJob * max(len(jobs), 1))()
+        keep: list = []
+        for i, j in enumerate(jobs):
+            cj = arr[i]
+            cj.path = j.path.h
+            cj.tr[:] = [float(v) for v in _as_tr(j.tr)]
+            cj.fill_rule = int(j.fill_rule)
+            cj.mode = int(j.mode)
+            if j.paint is not None:
+                cp = j.paint._c(keep)
+                keep.append(cp)
+                cj.paint = C.pointer(cp)
+            if j.path_bbox is not None:
+                bb = np.ascontiguousarray(j.path_bbox, dtype=np.float64)
+                keep.append(bb)
+                cj.path_bbox = bb.ctypes.data_as(C.POINTER(C.c_double))
+            cj.canvas = int(j.canvas)
+            cj.origin = int(j.origin)
+            cj.row_stride = int(j.row_stride)
+            cj.width = int(j.width)
+            cj.height = int(j.height)
+        return arr, len(jobs), keep
+
+    def prepare_batch(self, jobs: Iterable[Job]):
+        """Marshal a job list once; the result can be submitted repeatedly with `submit_prepared`."""
+        return self._cjobs(jobs)
+
+    def submit_prepared(self, prepared, independent: bool = False, sync: bool = True) -> None:
+        arr, n, _ = prepared
+        flags = ffi.BATCH_INDEPENDENT if independent else ffi.BATCH_ORDERED
+        fn = ffi.lib().rgpu_render_batch_sync if sync else ffi.lib().rgpu_render_batch
+        self._check(fn(self.ctx, arr, n, flags))
+
+    def render_batch(self, jobs: Iterable[Job], independent: bool = False, sync: bool = True) -> None:
+        self.submit_prepared(self._cjobs(jobs), independent, sync)
+
+    def batch_status(self) -> None:
+        self._check(ffi.lib().rgpu_batch_status(self.ctx))
+
+    def last_counts(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        ffi.lib().rgpu_last_counts(self.ctx, C.byref(a), C.byref(b), C.byref(c))
+        return dict(lines=a.value, line_refs=b.value, launches=c.value)
+
+    def stream(self) -> int:
+        return int(ffi.lib().rgpu_stream(self.ctx) or 0)
+
+    def sync(self) -> None:
+        self._check(ffi.lib().rgpu_sync(self.ctx))
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(ffi.lib().rgpu_device_alloc(self.ctx, nbytes, C.byref(p)))
+        return int(p.value)
+
+    def device_free(self, ptr: int) -> None:
+        self._check(ffi.lib().rgpu_device_free(self.ctx, C.c_void_p(ptr)))
+
+    def device_zero(self, ptr: int, nbytes: int) -> None:
+        self._check(ffi.lib().rgpu_device_zero(self.ctx, C.c_void_p(ptr), nbytes))
+
+    def to_host(self, ptr: int, shape, dtype) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        self._check(ffi.lib().rgpu_memcpy_d2h(self.ctx, out.ctypes.data, C.c_void_p(ptr), out.nbytes))
+        return out
+
+    def to_device(self, ptr: int, arr: np.ndarray) -> None:
+        a = np.ascontiguousarray(arr)
+        self._check(ffi.lib().rgpu_memcpy_h2d(self.ctx, C.c_void_p(ptr), a.ctypes.data, a.nbytes))
+
+    def to_rgba8(self, lin_ptr: int, rgba_ptr: int, n_pixels: int) -> None:
+        self._check(ffi.lib().rgpu_to_rgba8_dev(self.ctx, C.c_void_p(lin_ptr), C.c_void_p(rgba_ptr), n_pixels))
+
+    def fill_color(self, lin_ptr: int, n_pixels: int, color) -> None:
+        c = np.asarray(color, dtype=np.float32)
+        self._check(ffi.lib().rgpu_fill_color_dev(self.ctx, C.c_void_p(lin_ptr), n_pixels, c.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def host_alloc(self, shape, dtype) -> np.ndarray:
+        """Pinned host array (freed with the process; small helper for benchmarks)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._check(ffi.lib().rgpu_host_alloc(self.ctx, n, C.byref(p)))
+        buf = (C.c_byte * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def CShapeOf(start, width, height, row_stride, col_stride) -> ffi.CShape:
+    return ffi.CShape(start, width, height, row_stride, col_stride)

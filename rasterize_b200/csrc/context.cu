@@ -1,0 +1,830 @@
+// C ABI of rasterize_b200 (include/rasterize_b200.h): context, scratch management, job submission and the
+// host-buffer (trait-level) entry points.  No CPU fallback lives here: every entry point either launches the
+// CUDA kernels or fails.
+#include "../../include/rasterize_b200.h"
+#include "rgpu_internal.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace rgpu;
+
+struct rgpu_dpath {
+    double2* pts = nullptr;
+    uint2* items = nullptr;
+    uint32_t n_points = 0, n_items = 0, n_curves = 0;
+};
+
+namespace {
+
+thread_local std::string g_create_err;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct HostXf {  // 2x3 affine, reference src/geometry.rs:317-384, 519-539 (host-side paint set-up only)
+    double m[6];
+    static HostXf from(const double* t) { HostXf r; std::memcpy(r.m, t, sizeof(r.m)); return r; }
+    HostXf mul(const HostXf& o) const {
+        HostXf r;
+        r.m[0] = m[0] * o.m[0] + m[1] * o.m[3];
+        r.m[1] = m[0] * o.m[1] + m[1] * o.m[4];
+        r.m[2] = m[0] * o.m[2] + m[1] * o.m[5] + m[2];
+        r.m[3] = m[3] * o.m[0] + m[4] * o.m[3];
+        r.m[4] = m[3] * o.m[1] + m[4] * o.m[4];
+        r.m[5] = m[3] * o.m[2] + m[4] * o.m[5] + m[5];
+        return r;
+    }
+    bool invert(HostXf& out) const {
+        double det = m[0] * m[4] - m[3] * m[1];
+        if (std::fabs(det) <= 2.220446049250313e-16) return false;
+        double o00 = m[4] / det, o01 = -m[1] / det, o10 = -m[3] / det, o11 = m[0] / det;
+        out.m[0] = o00; out.m[1] = o01; out.m[2] = -o00 * m[2] - o01 * m[5];
+        out.m[3] = o10; out.m[4] = o11; out.m[5] = -o10 * m[2] - o11 * m[5];
+        return true;
+    }
+};
+
+}  // namespace
+
+struct rgpu_ctx {
+    int device = 0;
+    double flatness = 0.05;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // device scratch (grow-only)
+    DevBuf jobs, paints, slot_counts, slot_offs, lines, band_counts, band_offs, band_cursor, refs, scan_temp, status;
+    DevBuf img_f32, img_f64, img_lin;  // staging canvases of the host-buffer entry points
+    size_t lines_cap = 0, refs_cap = 0;
+    // pinned host
+    Status* h_status = nullptr;
+    void* h_stage = nullptr;
+    size_t h_stage_cap = 0;
+    JobDev* h_jobs = nullptr;
+    size_t h_jobs_cap = 0;
+    PaintDev* h_paints = nullptr;
+    size_t h_paints_cap = 0;
+    // stats
+    uint64_t n_launches = 0, last_lines = 0, last_refs = 0;
+    // last submission (for status / retry)
+    uint64_t need_lines = 0, need_refs = 0;
+    uint32_t last_total_slots = 0;
+};
+
+namespace {
+
+#define CK(ctx, call)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess) {                                                                            \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                \
+            return RGPU_ERR_CUDA;                                                                           \
+        }                                                                                                   \
+    } while (0)
+
+int fail(rgpu_ctx* ctx, int code, const char* msg) {
+    ctx->err = msg;
+    return code;
+}
+
+int ensure_dev(rgpu_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return RGPU_OK;
+    size_t want = std::max(bytes, b.cap + b.cap / 2);
+    want = (want + 255) & ~(size_t)255;
+    if (b.p) {
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        CK(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    CK(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return RGPU_OK;
+}
+
+template <class T>
+int ensure_pinned(rgpu_ctx* ctx, T*& p, size_t& cap, size_t count) {
+    if (count <= cap) return RGPU_OK;
+    size_t want = std::max(count, cap + cap / 2);
+    if (p) {
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        CK(ctx, cudaFreeHost(p));
+        p = nullptr;
+        cap = 0;
+    }
+    CK(ctx, cudaMallocHost(reinterpret_cast<void**>(&p), want * sizeof(T)));
+    cap = want;
+    return RGPU_OK;
+}
+
+int ensure_stage(rgpu_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->h_stage_cap) return RGPU_OK;
+    if (ctx->h_stage) {
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        CK(ctx, cudaFreeHost(ctx->h_stage));
+        ctx->h_stage = nullptr;
+        ctx->h_stage_cap = 0;
+    }
+    CK(ctx, cudaMallocHost(&ctx->h_stage, bytes));
+    ctx->h_stage_cap = bytes;
+    return RGPU_OK;
+}
+
+int validate_path(rgpu_ctx* ctx, const rgpu_path* p) {
+    if (!p) return fail(ctx, RGPU_ERR_INVALID, "path is NULL");
+    if (p->n_segments && (!p->points || !p->kinds)) return fail(ctx, RGPU_ERR_INVALID, "path arrays are NULL");
+    if (p->n_subpaths && (!p->subpath_offsets || !p->closed)) return fail(ctx, RGPU_ERR_INVALID, "subpath arrays are NULL");
+    size_t np = 0;
+    for (uint32_t i = 0; i < p->n_segments; i++) {
+        uint8_t k = p->kinds[i];
+        if (k < 2 || k > 4) return fail(ctx, RGPU_ERR_INVALID, "segment kind must be 2 (line), 3 (quad) or 4 (cubic)");
+        np += k;
+    }
+    if (np != p->n_points) return fail(ctx, RGPU_ERR_INVALID, "n_points does not match the sum of kinds");
+    if (p->n_points > kItemIndexMask) return fail(ctx, RGPU_ERR_INVALID, "path too large");
+    uint32_t prev = 0;
+    for (uint32_t s = 0; s < p->n_subpaths; s++) {
+        uint32_t a = p->subpath_offsets[s], b = p->subpath_offsets[s + 1];
+        if (a != prev || b <= a || b > p->n_segments) return fail(ctx, RGPU_ERR_INVALID, "bad subpath offsets");
+        prev = b;
+    }
+    return RGPU_OK;
+}
+
+// Build the device item list: the segments of each subpath followed by its closing item
+// (reference order of PathFlattenIter, src/path.rs:761-795).
+void build_items(const rgpu_path* p, std::vector<uint2>& items, uint32_t& n_curves) {
+    std::vector<uint32_t> pt_off(p->n_segments + 1);
+    uint32_t acc = 0;
+    n_curves = 0;
+    for (uint32_t i = 0; i < p->n_segments; i++) {
+        pt_off[i] = acc;
+        acc += p->kinds[i];
+        if (p->kinds[i] != 2) n_curves++;
+    }
+    pt_off[p->n_segments] = acc;
+    items.clear();
+    items.reserve(p->n_segments + p->n_subpaths);
+    for (uint32_t s = 0; s < p->n_subpaths; s++) {
+        uint32_t a = p->subpath_offsets[s], b = p->subpath_offsets[s + 1];
+        for (uint32_t i = a; i < b; i++) items.push_back(make_uint2(pt_off[i], p->kinds[i]));
+        uint32_t end_pt = pt_off[b] - 1;  // subpath.end()
+        uint32_t start_pt = pt_off[a];    // subpath.start()
+        items.push_back(make_uint2(end_pt, kItemClosing | (p->closed[s] ? kItemExplicitClosed : 0u) | start_pt));
+    }
+}
+
+int upload_path(rgpu_ctx* ctx, const rgpu_path* path, rgpu_dpath* dp) {
+    std::vector<uint2> items;
+    build_items(path, items, dp->n_curves);
+    dp->n_points = path->n_points;
+    dp->n_items = (uint32_t)items.size();
+    if (dp->n_points) {
+        CK(ctx, cudaMalloc(reinterpret_cast<void**>(&dp->pts), sizeof(double2) * dp->n_points));
+        CK(ctx, cudaMemcpyAsync(dp->pts, path->points, sizeof(double2) * dp->n_points, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (dp->n_items) {
+        CK(ctx, cudaMalloc(reinterpret_cast<void**>(&dp->items), sizeof(uint2) * dp->n_items));
+        CK(ctx, cudaMemcpyAsync(dp->items, items.data(), sizeof(uint2) * dp->n_items, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // `items` is pageable: the async copy is staged by the driver before returning, but be explicit
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RGPU_OK;
+}
+
+void free_path(rgpu_dpath* dp) {
+    if (dp->pts) cudaFree(dp->pts);
+    if (dp->items) cudaFree(dp->items);
+    dp->pts = nullptr;
+    dp->items = nullptr;
+}
+
+// Resolve the paint of a FILL job into the device form; returns false when the fill is a silent no-op
+// (singular transform, bounding-box units without a bbox: reference src/rasterize.rs:87-92).
+bool build_paint(const rgpu_job& job, PaintDev& out) {
+    const rgpu_paint* p = job.paint;
+    std::memset(&out, 0, sizeof(out));
+    out.kind = p->kind;
+    out.linear_colors = p->linear_colors;
+    out.spread = p->spread;
+    std::memcpy(out.solid, p->solid, sizeof(out.solid));
+    if (p->kind == RGPU_PAINT_SOLID) return true;
+    HostXf tr = HostXf::from(job.tr);
+    HostXf units_tr;
+    if (p->units == RGPU_UNITS_USER_SPACE) {
+        units_tr = tr.mul(HostXf::from(p->tr));
+    } else {
+        if (!job.path_bbox) return false;
+        const double* bb = job.path_bbox;
+        // BBox::unit_transform: translate(x, y).pre_scale(width, height), src/geometry.rs:662-664
+        const double tm[6] = {1.0, 0.0, bb[0], 0.0, 1.0, bb[1]};
+        const double sm[6] = {bb[2] - bb[0], 0.0, 0.0, 0.0, bb[3] - bb[1], 0.0};
+        HostXf t = HostXf::from(tm);
+        HostXf s = HostXf::from(sm);
+        units_tr = tr.mul(t.mul(s)).mul(HostXf::from(p->tr));
+    }
+    HostXf inv;
+    if (!units_tr.invert(inv)) return false;
+    std::memcpy(out.pixel_tr, inv.m, sizeof(inv.m));
+    out.p0x = p->p0[0]; out.p0y = p->p0[1]; out.p1x = p->p1[0]; out.p1y = p->p1[1];
+    out.r0 = p->r0; out.r1 = p->r1;
+    if (p->kind == RGPU_PAINT_LINEAR) {
+        // dir = (end - start) / |end - start|^2, src/grad.rs:180-190
+        double dx = p->p1[0] - p->p0[0], dy = p->p1[1] - p->p0[1];
+        double dd = dx * dx + dy * dy;
+        out.dirx = dx / dd;
+        out.diry = dy / dd;
+    }
+    out.n_stops = (int)std::min<uint32_t>(p->n_stops, kMaxStops);
+    for (int i = 0; i < out.n_stops; i++) {
+        out.stop_pos[i] = p->stop_pos[i];
+        std::memcpy(out.stop_col[i], p->stop_colors + 4 * i, 16);
+    }
+    if (out.n_stops == 0) {  // GradStops::new: empty list -> one opaque black stop, src/grad.rs:92-97
+        out.n_stops = 1;
+        out.stop_pos[0] = 0.0;
+        out.stop_col[0][0] = out.stop_col[0][1] = out.stop_col[0][2] = 0.f;
+        out.stop_col[0][3] = 1.f;
+    }
+    return true;
+}
+
+int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, int close_flag) {
+    if (n_jobs == 0) return RGPU_OK;
+    if (!jobs) return fail(ctx, RGPU_ERR_INVALID, "jobs is NULL");
+    if (!(ctx->flatness > 0.0)) return fail(ctx, RGPU_ERR_INVALID, "flatness must be > 0 (the reference loops forever on 0)");
+    int rc;
+    if ((rc = ensure_pinned(ctx, ctx->h_jobs, ctx->h_jobs_cap, n_jobs))) return rc;
+    if ((rc = ensure_pinned(ctx, ctx->h_paints, ctx->h_paints_cap, n_jobs))) return rc;
+
+    // tile variant: small canvases get a (128 x 64) tile, everything else (1024 x 8)
+    uint32_t max_w = 0;
+    for (size_t j = 0; j < n_jobs; j++) max_w = std::max(max_w, jobs[j].width);
+    int variant = (max_w <= 128) ? 1 : 0;
+    TileShape ts = raster_tile_shape(variant);
+
+    uint32_t item_acc = 0, band_acc = 0, tile_acc = 0, n_paints = 0;
+    uint64_t est_lines = 0;
+    const rgpu_paint* last_paint = nullptr;
+    int last_paint_index = -1;
+    const rgpu_job* last_paint_job = nullptr;
+    uint32_t n_live = 0;
+    for (size_t j = 0; j < n_jobs; j++) {
+        const rgpu_job& in = jobs[j];
+        if (!in.path) return fail(ctx, RGPU_ERR_INVALID, "job.path is NULL");
+        if (in.width == 0 || in.height == 0) continue;  // reference: empty iterator / nothing to write
+        if (!in.canvas) return fail(ctx, RGPU_ERR_INVALID, "job.canvas is NULL");
+        if (in.mode == RGPU_JOB_MASK && in.width < 1) continue;
+        JobDev d;
+        std::memset(&d, 0, sizeof(d));
+        d.paint_index = -1;
+        if (in.mode == RGPU_JOB_FILL) {
+            if (!in.paint) return fail(ctx, RGPU_ERR_INVALID, "fill job without a paint");
+            bool same = last_paint == in.paint && last_paint_job && in.paint->kind == RGPU_PAINT_SOLID;
+            if (same) {
+                d.paint_index = last_paint_index;
+            } else {
+                if (!build_paint(in, ctx->h_paints[n_paints])) continue;  // silent no-op fill
+                d.paint_index = (int)n_paints;
+                last_paint = in.paint;
+                last_paint_index = d.paint_index;
+                last_paint_job = &in;
+                n_paints++;
+            }
+        }
+        std::memcpy(d.tr, in.tr, sizeof(d.tr));
+        d.pts = in.path->pts;
+        d.items = in.path->items;
+        d.item_begin = item_acc;
+        d.n_items = in.path->n_items;
+        d.width_out = (int32_t)in.width;
+        d.height = (int32_t)in.height;
+        // reference `width`: img.width - 1 (mask: the image's own last column; mask_iter: (w+1) - 1)
+        d.clamp_w = (in.mode == RGPU_JOB_MASK) ? (double)in.width - 1.0 : (double)in.width;
+        d.rule = in.fill_rule;
+        d.mode = in.mode;
+        d.close = close_flag;
+        d.canvas = in.canvas;
+        d.origin = in.origin;
+        d.row_stride = in.row_stride;
+        d.band_begin = band_acc;
+        d.n_bands = (in.height + ts.th - 1) / ts.th;
+        d.n_chunks = (in.width + ts.cw - 1) / ts.cw;
+        d.tile_begin = tile_acc;
+        item_acc += d.n_items;
+        band_acc += d.n_bands;
+        tile_acc += d.n_bands * d.n_chunks;
+        est_lines += (uint64_t)in.path->n_curves * 24 + (in.path->n_items - in.path->n_curves) + 16;
+        ctx->h_jobs[n_live++] = d;
+    }
+    ctx->need_lines = ctx->need_refs = 0;
+    if (n_live == 0) {
+        std::memset(ctx->h_status, 0, sizeof(Status));
+        return RGPU_OK;
+    }
+    uint64_t total_slots64 = (uint64_t)item_acc * kSlotsPerItem + 1;
+    if (total_slots64 > 0x7fffffffull) return fail(ctx, RGPU_ERR_INVALID, "batch too large (more than 2^28 path items)");
+    uint32_t total_slots = item_acc * kSlotsPerItem;
+    ctx->last_total_slots = total_slots;
+
+    // scratch sizing (optimistic; grown and re-run on overflow by *_sync)
+    size_t want_lines = std::max<uint64_t>(ctx->lines_cap, est_lines);
+    size_t want_refs = std::max<uint64_t>(ctx->refs_cap, want_lines * 2);
+    if ((rc = ensure_dev(ctx, ctx->jobs, sizeof(JobDev) * n_live))) return rc;
+    if ((rc = ensure_dev(ctx, ctx->paints, sizeof(PaintDev) * std::max<uint32_t>(n_paints, 1)))) return rc;
+    if ((rc = ensure_dev(ctx, ctx->slot_counts, sizeof(uint32_t) * (total_slots + 1)))) return rc;
+    if ((rc = ensure_dev(ctx, ctx->slot_offs, sizeof(uint32_t) * (total_slots + 1)))) return rc;
+    if ((rc = ensure_dev(ctx, ctx->lines, sizeof(double4) * want_lines))) return rc;
+    ctx->lines_cap = std::min<size_t>(ctx->lines.cap / sizeof(double4), 0xfffffff0u);
+    if ((rc = ensure_dev(ctx, ctx->refs, sizeof(uint32_t) * want_refs))) return rc;
+    ctx->refs_cap = std::min<size_t>(ctx->refs.cap / sizeof(uint32_t), 0xfffffff0u);
+    if ((rc = ensure_dev(ctx, ctx->band_counts, sizeof(uint32_t) * (band_acc + 1)))) return rc;
+    if ((rc = ensure_dev(ctx, ctx->band_offs, sizeof(uint32_t) * (band_acc + 1)))) return rc;
+    if ((rc = ensure_dev(ctx, ctx->band_cursor, sizeof(uint32_t) * (band_acc + 1)))) return rc;
+    size_t tb = std::max(scan_temp_bytes(total_slots + 1), scan_temp_bytes(band_acc + 1));
+    if ((rc = ensure_dev(ctx, ctx->scan_temp, tb))) return rc;
+
+    cudaStream_t s = ctx->stream;
+    JobDev* d_jobs = static_cast<JobDev*>(ctx->jobs.p);
+    PaintDev* d_paints = static_cast<PaintDev*>(ctx->paints.p);
+    Status* d_status = static_cast<Status*>(ctx->status.p);
+    uint32_t* d_counts = static_cast<uint32_t*>(ctx->slot_counts.p);
+    uint32_t* d_offs = static_cast<uint32_t*>(ctx->slot_offs.p);
+    double4* d_lines = static_cast<double4*>(ctx->lines.p);
+    uint32_t* d_bc = static_cast<uint32_t*>(ctx->band_counts.p);
+    uint32_t* d_bo = static_cast<uint32_t*>(ctx->band_offs.p);
+    uint32_t* d_cur = static_cast<uint32_t*>(ctx->band_cursor.p);
+    uint32_t* d_refs = static_cast<uint32_t*>(ctx->refs.p);
+
+    CK(ctx, cudaMemcpyAsync(d_jobs, ctx->h_jobs, sizeof(JobDev) * n_live, cudaMemcpyHostToDevice, s));
+    if (n_paints) CK(ctx, cudaMemcpyAsync(d_paints, ctx->h_paints, sizeof(PaintDev) * n_paints, cudaMemcpyHostToDevice, s));
+    CK(ctx, cudaMemsetAsync(d_status, 0, sizeof(Status), s));
+    CK(ctx, cudaMemsetAsync(d_bc, 0, sizeof(uint32_t) * (band_acc + 1), s));
+    CK(ctx, cudaMemsetAsync(d_cur, 0, sizeof(uint32_t) * (band_acc + 1), s));
+
+    double thr = 16.0 * ctx->flatness * ctx->flatness;  // PathFlattenIter::new, src/path.rs:749
+    launch_flatten_count(d_jobs, n_live, item_acc, thr, d_counts, d_status, s);
+    launch_exclusive_scan(d_counts, d_offs, total_slots + 1, ctx->scan_temp.p, ctx->scan_temp.cap, s);
+    launch_flatten_emit(d_jobs, n_live, item_acc, thr, d_offs, d_lines, (uint32_t)ctx->lines_cap, d_status, s);
+    launch_bin_count(d_jobs, n_live, d_offs, total_slots, d_lines, d_bc, ts.th, d_status, s);
+    launch_exclusive_scan(d_bc, d_bo, band_acc + 1, ctx->scan_temp.p, ctx->scan_temp.cap, s);
+    launch_bin_fill(d_jobs, n_live, d_offs, total_slots, d_lines, d_bo, band_acc, d_cur, d_refs, (uint32_t)ctx->refs_cap, ts.th,
+                    d_status, s);
+    ctx->n_launches += 6;
+    if (flags & RGPU_BATCH_INDEPENDENT) {
+        launch_raster(variant, d_jobs, n_live, 0, 0, tile_acc, d_paints, d_lines, d_bo, d_refs, d_status, s);
+        ctx->n_launches += 1;
+    } else {
+        for (uint32_t j = 0; j < n_live; j++) {
+            const JobDev& d = ctx->h_jobs[j];
+            launch_raster(variant, d_jobs, 1, j, d.tile_begin, d.n_bands * d.n_chunks, d_paints, d_lines, d_bo, d_refs, d_status, s);
+            ctx->n_launches += 1;
+        }
+    }
+    CK(ctx, cudaMemcpyAsync(ctx->h_status, d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
+    CK(ctx, cudaGetLastError());
+    return RGPU_OK;
+}
+
+int check_status(rgpu_ctx* ctx) {
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    const Status& st = *ctx->h_status;
+    if (st.nan_flag) return fail(ctx, RGPU_ERR_NAN, "cannot flatten segment with NaN");
+    if (st.depth_flag) return fail(ctx, RGPU_ERR_DEPTH, "curve subdivision exceeded the device stack depth");
+    ctx->need_lines = st.n_lines;
+    ctx->need_refs = st.n_refs;
+    if (st.lines_overflow || st.refs_overflow) return fail(ctx, RGPU_ERR_CAPACITY, "internal scratch overflow (retry grows it)");
+    ctx->last_lines = st.n_lines;
+    ctx->last_refs = st.n_refs;
+    return RGPU_OK;
+}
+
+int submit_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, int close_flag) {
+    for (int attempt = 0; attempt < 4; attempt++) {
+        int rc = submit(ctx, jobs, n_jobs, flags, close_flag);
+        if (rc) return rc;
+        rc = check_status(ctx);
+        if (rc != RGPU_ERR_CAPACITY) return rc;
+        // grow: line count is exact once the emit pass overflowed (it comes from the scan); the reference
+        // count is only known when the lines fitted, so over-provision it from the line count.
+        const Status& st = *ctx->h_status;
+        size_t nl = std::max<size_t>(st.n_lines, ctx->lines_cap);
+        if (st.lines_overflow) {
+            // n_lines is written by bin_count, which is skipped on overflow: read the scan total instead
+            uint32_t total = 0;
+            uint32_t* d_offs = static_cast<uint32_t*>(ctx->slot_offs.p);
+            CK(ctx, cudaMemcpy(&total, d_offs + ctx->last_total_slots, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            nl = (size_t)total + total / 16 + 64;
+        }
+        size_t nr = st.refs_overflow ? (size_t)st.n_refs + st.n_refs / 16 + 64 : std::max<size_t>(ctx->refs_cap, nl * 2);
+        int rc2;
+        if ((rc2 = ensure_dev(ctx, ctx->lines, sizeof(double4) * nl))) return rc2;
+        ctx->lines_cap = ctx->lines.cap / sizeof(double4);
+        if ((rc2 = ensure_dev(ctx, ctx->refs, sizeof(uint32_t) * nr))) return rc2;
+        ctx->refs_cap = ctx->refs.cap / sizeof(uint32_t);
+    }
+    return fail(ctx, RGPU_ERR_CAPACITY, "internal scratch overflow persisted after 4 attempts");
+}
+
+}  // namespace
+
+extern "C" {
+
+int rgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* rgpu_name(void) { return "gpu-signed-difference"; }
+
+int rgpu_create(int device, double flatness, rgpu_ctx** out) {
+    if (!out) return RGPU_ERR_INVALID;
+    *out = nullptr;
+    if (!(flatness > 0.0)) {
+        g_create_err = "flatness must be > 0";
+        return RGPU_ERR_INVALID;
+    }
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        g_create_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e) + " (rasterize_b200 has no CPU fallback)";
+        return RGPU_ERR_CUDA;
+    }
+    auto* ctx = new rgpu_ctx();
+    ctx->device = device;
+    ctx->flatness = flatness;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_status), sizeof(Status));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->status.p, 256);
+    if (e != cudaSuccess) {
+        g_create_err = std::string("rgpu_create: ") + cudaGetErrorString(e);
+        delete ctx;
+        return RGPU_ERR_CUDA;
+    }
+    ctx->status.cap = 256;
+    std::memset(ctx->h_status, 0, sizeof(Status));
+    *out = ctx;
+    return RGPU_OK;
+}
+
+void rgpu_destroy(rgpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->jobs, &ctx->paints, &ctx->slot_counts, &ctx->slot_offs, &ctx->lines, &ctx->band_counts, &ctx->band_offs,
+                      &ctx->band_cursor, &ctx->refs, &ctx->scan_temp, &ctx->status, &ctx->img_f32, &ctx->img_f64, &ctx->img_lin};
+    for (DevBuf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->h_jobs) cudaFreeHost(ctx->h_jobs);
+    if (ctx->h_paints) cudaFreeHost(ctx->h_paints);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* rgpu_last_error(const rgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+void* rgpu_stream(rgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int rgpu_sync(rgpu_ctx* ctx) {
+    if (!ctx) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RGPU_OK;
+}
+
+int rgpu_device_alloc(rgpu_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMalloc(out, bytes ? bytes : 1));
+    return RGPU_OK;
+}
+int rgpu_device_free(rgpu_ctx* ctx, void* p) {
+    if (!ctx) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaFree(p));
+    return RGPU_OK;
+}
+int rgpu_device_zero(rgpu_ctx* ctx, void* p, size_t bytes) {
+    if (!ctx) return RGPU_ERR_INVALID;
+    CK(ctx, cudaMemsetAsync(p, 0, bytes, ctx->stream));
+    return RGPU_OK;
+}
+int rgpu_memcpy_h2d(rgpu_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return RGPU_ERR_INVALID;
+    CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RGPU_OK;
+}
+int rgpu_memcpy_d2h(rgpu_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return RGPU_ERR_INVALID;
+    CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RGPU_OK;
+}
+int rgpu_host_alloc(rgpu_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMallocHost(out, bytes ? bytes : 1));
+    return RGPU_OK;
+}
+int rgpu_host_free(rgpu_ctx* ctx, void* p) {
+    if (!ctx) return RGPU_ERR_INVALID;
+    CK(ctx, cudaFreeHost(p));
+    return RGPU_OK;
+}
+
+int rgpu_path_upload(rgpu_ctx* ctx, const rgpu_path* path, rgpu_dpath** out) {
+    if (!ctx || !out) return RGPU_ERR_INVALID;
+    *out = nullptr;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = validate_path(ctx, path);
+    if (rc) return rc;
+    auto* dp = new rgpu_dpath();
+    rc = upload_path(ctx, path, dp);
+    if (rc) {
+        free_path(dp);
+        delete dp;
+        return rc;
+    }
+    *out = dp;
+    return RGPU_OK;
+}
+
+void rgpu_path_free(rgpu_ctx* ctx, rgpu_dpath* p) {
+    if (!p) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    free_path(p);
+    delete p;
+}
+
+int rgpu_render_batch(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags) {
+    if (!ctx) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return submit(ctx, jobs, n_jobs, flags, 1);
+}
+
+int rgpu_batch_status(rgpu_ctx* ctx) {
+    if (!ctx) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return check_status(ctx);
+}
+
+int rgpu_render_batch_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags) {
+    if (!ctx) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    return submit_sync(ctx, jobs, n_jobs, flags, 1);
+}
+
+int rgpu_last_counts(rgpu_ctx* ctx, uint64_t* n_lines, uint64_t* n_line_refs, uint64_t* n_launches) {
+    if (!ctx) return RGPU_ERR_INVALID;
+    if (n_lines) *n_lines = ctx->last_lines;
+    if (n_line_refs) *n_line_refs = ctx->last_refs;
+    if (n_launches) *n_launches = ctx->n_launches;
+    return RGPU_OK;
+}
+
+int rgpu_to_rgba8_dev(rgpu_ctx* ctx, const float* lin_dev, uint8_t* rgba_dev, size_t n_pixels) {
+    if (!ctx) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    launch_to_rgba8(reinterpret_cast<const float4*>(lin_dev), reinterpret_cast<uchar4*>(rgba_dev), n_pixels, ctx->stream);
+    ctx->n_launches++;
+    CK(ctx, cudaGetLastError());
+    return RGPU_OK;
+}
+
+int rgpu_fill_color_dev(rgpu_ctx* ctx, float* lin_dev, size_t n_pixels, const float color[4]) {
+    if (!ctx || !color) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    launch_fill_color(reinterpret_cast<float4*>(lin_dev), n_pixels, make_float4(color[0], color[1], color[2], color[3]), ctx->stream);
+    ctx->n_launches++;
+    CK(ctx, cudaGetLastError());
+    return RGPU_OK;
+}
+
+// ---- trait-level entry points ------------------------------------------------------------------------
+
+int rgpu_flatten(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int close, double* lines_out, size_t cap, size_t* n_out) {
+    if (!ctx || !tr || !n_out) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = validate_path(ctx, path);
+    if (rc) return rc;
+    *n_out = 0;
+    if (path->n_segments == 0 || path->n_subpaths == 0) return RGPU_OK;
+    rgpu_dpath dp;
+    rc = upload_path(ctx, path, &dp);
+    if (rc) { free_path(&dp); return rc; }
+    // flatten only: run count + scan + emit through a throw-away 1x1 mask job so that one code path serves both
+    float* d_dummy = nullptr;
+    if ((rc = ensure_dev(ctx, ctx->img_f32, 64))) { free_path(&dp); return rc; }
+    d_dummy = static_cast<float*>(ctx->img_f32.p);
+    rgpu_job job;
+    std::memset(&job, 0, sizeof(job));
+    job.path = &dp;
+    std::memcpy(job.tr, tr, sizeof(job.tr));
+    job.mode = RGPU_JOB_COVERAGE;
+    job.canvas = d_dummy;
+    job.row_stride = 1;
+    job.width = 1;
+    job.height = 1;
+    rc = submit_sync(ctx, &job, 1, RGPU_BATCH_INDEPENDENT, close ? 1 : 0);
+    if (rc == RGPU_OK) {
+        size_t n = ctx->last_lines;
+        *n_out = n;
+        if (n > cap || (n && !lines_out)) {
+            rc = fail(ctx, RGPU_ERR_CAPACITY, "lines_out too small");
+        } else if (n) {
+            cudaError_t e = cudaMemcpyAsync(lines_out, ctx->lines.p, n * sizeof(double4), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = RGPU_ERR_CUDA; }
+        }
+    }
+    free_path(&dp);
+    return rc;
+}
+
+static int mask_to_device(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill_rule, int mode, size_t width, size_t height,
+                          float** d_out) {
+    int rc = validate_path(ctx, path);
+    if (rc) return rc;
+    if (fill_rule != RGPU_NONZERO && fill_rule != RGPU_EVENODD) return fail(ctx, RGPU_ERR_INVALID, "bad fill rule");
+    if (width > 0x7ffffff0u || height > 0x7ffffff0u) return fail(ctx, RGPU_ERR_INVALID, "image too large");
+    if ((rc = ensure_dev(ctx, ctx->img_f32, sizeof(float) * width * height))) return rc;
+    float* d_img = static_cast<float*>(ctx->img_f32.p);
+    *d_out = d_img;
+    rgpu_dpath dp;
+    if (path->n_segments == 0 || path->n_subpaths == 0) {
+        CK(ctx, cudaMemsetAsync(d_img, 0, sizeof(float) * width * height, ctx->stream));
+        return RGPU_OK;
+    }
+    rc = upload_path(ctx, path, &dp);
+    if (rc) { free_path(&dp); return rc; }
+    rgpu_job job;
+    std::memset(&job, 0, sizeof(job));
+    job.path = &dp;
+    std::memcpy(job.tr, tr, sizeof(job.tr));
+    job.fill_rule = fill_rule;
+    job.mode = mode;
+    job.canvas = d_img;
+    job.row_stride = width;
+    job.width = (uint32_t)width;
+    job.height = (uint32_t)height;
+    rc = submit_sync(ctx, &job, 1, RGPU_BATCH_INDEPENDENT, 1);
+    free_path(&dp);
+    return rc;
+}
+
+int rgpu_mask_f32(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill_rule, float* img, size_t width, size_t height) {
+    if (!ctx || !tr || (!img && width * height)) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (width == 0 || height == 0) return RGPU_OK;
+    float* d = nullptr;
+    int rc = mask_to_device(ctx, path, tr, fill_rule, RGPU_JOB_MASK, width, height, &d);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpyAsync(img, d, sizeof(float) * width * height, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RGPU_OK;
+}
+
+int rgpu_coverage_f32(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill_rule, float* out, size_t width, size_t height) {
+    if (!ctx || !tr || (!out && width * height)) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (width == 0 || height == 0) return RGPU_OK;  // src/rasterize.rs:320-322
+    float* d = nullptr;
+    int rc = mask_to_device(ctx, path, tr, fill_rule, RGPU_JOB_COVERAGE, width, height, &d);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpyAsync(out, d, sizeof(float) * width * height, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RGPU_OK;
+}
+
+int rgpu_mask(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill_rule, double* img, rgpu_shape shape) {
+    if (!ctx || !tr) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    size_t w = shape.width, h = shape.height;
+    if (w == 0 || h == 0) return RGPU_OK;
+    if (!img) return RGPU_ERR_INVALID;
+    float* d = nullptr;
+    int rc = mask_to_device(ctx, path, tr, fill_rule, RGPU_JOB_MASK, w, h, &d);
+    if (rc) return rc;
+    // widen on the device, then one strided D2H straight into the caller's image
+    if ((rc = ensure_dev(ctx, ctx->img_f64, sizeof(double) * w * h))) return rc;
+    double* d64 = static_cast<double*>(ctx->img_f64.p);
+    launch_f32_to_f64(d, d64, w * h, ctx->stream);
+    ctx->n_launches++;
+    double* dst = img + shape.start;
+    if (shape.col_stride == 1) {
+        CK(ctx, cudaMemcpy2DAsync(dst, shape.row_stride * sizeof(double), d64, w * sizeof(double), w * sizeof(double), h,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        if ((rc = ensure_stage(ctx, sizeof(double) * w * h))) return rc;
+        CK(ctx, cudaMemcpyAsync(ctx->h_stage, d64, sizeof(double) * w * h, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        const double* src = static_cast<const double*>(ctx->h_stage);
+        for (size_t y = 0; y < h; y++)
+            for (size_t x = 0; x < w; x++) dst[y * shape.row_stride + x * shape.col_stride] = src[y * w + x];
+    }
+    return RGPU_OK;
+}
+
+int rgpu_mask_iter(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], size_t width, size_t height, int fill_rule,
+                   rgpu_pixel* out, size_t cap, size_t* n_out) {
+    if (!ctx || !tr || !n_out) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    *n_out = 0;
+    if (width == 0 || height == 0) return RGPU_OK;
+    float* d = nullptr;
+    int rc = mask_to_device(ctx, path, tr, fill_rule, RGPU_JOB_COVERAGE, width, height, &d);
+    if (rc) return rc;
+    if ((rc = ensure_stage(ctx, sizeof(float) * width * height))) return rc;
+    CK(ctx, cudaMemcpyAsync(ctx->h_stage, d, sizeof(float) * width * height, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    const float* cov = static_cast<const float*>(ctx->h_stage);
+    size_t n = 0;
+    for (size_t y = 0; y < height; y++)
+        for (size_t x = 0; x < width; x++) {
+            float a = cov[y * width + x];
+            if (a != 0.0f) {
+                if (n < cap && out) { out[n].x = x; out[n].y = y; out[n].alpha = (double)a; }
+                n++;
+            }
+        }
+    *n_out = n;
+    if (n > cap) return fail(ctx, RGPU_ERR_CAPACITY, "pixel buffer too small");
+    return RGPU_OK;
+}
+
+int rgpu_fill(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill_rule, const rgpu_paint* paint,
+              const double* path_bbox, float* img, rgpu_shape shape) {
+    if (!ctx || !tr || !paint) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    size_t w = shape.width, h = shape.height;
+    if (w == 0 || h == 0) return RGPU_OK;
+    if (!img) return RGPU_ERR_INVALID;
+    int rc = validate_path(ctx, path);
+    if (rc) return rc;
+    if (path->n_segments == 0 || path->n_subpaths == 0) return RGPU_OK;
+    if (paint->n_stops > RGPU_MAX_STOPS) return fail(ctx, RGPU_ERR_INVALID, "too many gradient stops");
+    if ((rc = ensure_dev(ctx, ctx->img_lin, sizeof(float4) * w * h))) return rc;
+    float4* d_img = static_cast<float4*>(ctx->img_lin.p);
+    float* dst = img + 4 * shape.start;
+    bool dense_rows = shape.col_stride == 1;
+    // host image -> device canvas
+    if (dense_rows) {
+        CK(ctx, cudaMemcpy2DAsync(d_img, w * sizeof(float4), dst, shape.row_stride * sizeof(float4), w * sizeof(float4), h,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        if ((rc = ensure_stage(ctx, sizeof(float4) * w * h))) return rc;
+        float4* st = static_cast<float4*>(ctx->h_stage);
+        for (size_t y = 0; y < h; y++)
+            for (size_t x = 0; x < w; x++) std::memcpy(&st[y * w + x], dst + 4 * (y * shape.row_stride + x * shape.col_stride), 16);
+        CK(ctx, cudaMemcpyAsync(d_img, st, sizeof(float4) * w * h, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rgpu_dpath dp;
+    rc = upload_path(ctx, path, &dp);
+    if (rc) { free_path(&dp); return rc; }
+    rgpu_job job;
+    std::memset(&job, 0, sizeof(job));
+    job.path = &dp;
+    std::memcpy(job.tr, tr, sizeof(job.tr));
+    job.fill_rule = fill_rule;
+    job.mode = RGPU_JOB_FILL;
+    job.paint = paint;
+    job.path_bbox = path_bbox;
+    job.canvas = d_img;
+    job.row_stride = w;
+    job.width = (uint32_t)w;
+    job.height = (uint32_t)h;
+    rc = submit_sync(ctx, &job, 1, RGPU_BATCH_ORDERED, 1);
+    free_path(&dp);
+    if (rc) return rc;
+    if (dense_rows) {
+        CK(ctx, cudaMemcpy2DAsync(dst, shape.row_stride * sizeof(float4), d_img, w * sizeof(float4), w * sizeof(float4), h,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        float4* st = static_cast<float4*>(ctx->h_stage);
+        CK(ctx, cudaMemcpyAsync(st, d_img, sizeof(float4) * w * h, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        for (size_t y = 0; y < h; y++)
+            for (size_t x = 0; x < w; x++) std::memcpy(dst + 4 * (y * shape.row_stride + x * shape.col_stride), &st[y * w + x], 16);
+    }
+    return RGPU_OK;
+}
+
+}  // extern "C"

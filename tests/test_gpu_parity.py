@@ -1,0 +1,211 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Run on a B200: pytest -m gpu.
+
+Bars (BASELINE.json north_star): flattened line counts identical (we require bit-identical lines), f32
+coverage within 1e-4 absolute per pixel, 8-bit RGBA within 1 LSB.
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+import rasterize_b200 as rb
+from rasterize_b200 import assets, ffi
+
+pytestmark = pytest.mark.gpu
+
+COV_TOL = 1e-4   # north_star: f32 coverage within 1e-4 absolute per pixel
+ASSETS = ["squirrel", "tv", "rust", "material", "ava", "huyak", "tv_stroked", "squirrel_stroked"]
+
+
+@pytest.fixture(scope="module")
+def rast():
+    r = rb.GpuRasterizer()
+    yield r
+    r.close()
+
+
+def opath(p: rb.Path) -> O.OraclePath:
+    return O.OraclePath.from_flat(p.points, p.kinds, p.subpath_offsets, p.closed)
+
+
+@pytest.mark.parametrize("name", ASSETS)
+def test_flatten_identical(rast, name):
+    p = assets.load_path(name)
+    e = assets.expected()["paths"][name]
+    tr = np.array(e["size_tr"])
+    got = rast.flatten(p, tr, True)
+    ref = opath(p).flatten(tr)
+    assert len(got) == len(ref) == e["lines_at_size"]
+    assert np.array_equal(got, ref)  # bit-identical endpoints, reference order
+    got_open = rast.flatten(p, tr, False)
+    ref_open = opath(p).flatten(tr, close=False)
+    assert np.array_equal(got_open, ref_open)
+
+
+def test_flatten_rotated_and_configs(rast):
+    """src/path.rs:1192-1211 test_flatten transform + the BASELINE config transforms"""
+    import math
+    p = assets.load_path("squirrel")
+    tr = O.transform_mul(O.rotate(math.pi / 3.0), O.translate(-10.0, -20.0))
+    assert np.array_equal(rast.flatten(p, tr), opath(p).flatten(tr))
+    ex = assets.expected()["paths"]
+    for name, key in (("squirrel", "c1"), ("material", "c2"), ("tv_stroked", "c5")):
+        p = assets.load_path(name)
+        tr = np.array(ex[name][key]["tr"])
+        got = rast.flatten(p, tr)
+        assert len(got) == ex[name][key]["lines"]
+        assert np.array_equal(got, opath(p).flatten(tr))
+
+
+def test_flatten_quads_and_flatness(rast):
+    b = rb.Path.builder()
+    b.move_to((1, 1)).quad_to((40, 3), (50, 60)).quad_to((60, 120), (5, 90)).line_to((3, 3)).close()
+    b.move_to((10, 10)).cubic_to((300, 20), (-200, 200), (90, 90))
+    p = b.build()
+    for fl in (0.05, 0.5, 1e-3):
+        r = rb.GpuRasterizer(flatness=fl)
+        for close in (True, False):
+            got = r.flatten(p, rb.Transform.new_scale(3.0, 2.0), close)
+            ref = opath(p).flatten(rb.Transform.new_scale(3.0, 2.0).array(), fl, close)
+            assert np.array_equal(got, ref), (fl, close, len(got), len(ref))
+        r.close()
+
+
+def test_nan_is_an_error(rast):
+    """reference panics: "cannot flatten segment with NaN" (src/path.rs:765-767)"""
+    p = rb.Path([[0, 0], [float("nan"), 1], [2, 2]], [3], [0, 1], [0])
+    with pytest.raises(rb.RgpuError) as e:
+        rast.flatten(p)
+    assert e.value.code == ffi.ERR_NAN
+    # the context stays usable
+    assert len(rast.flatten(assets.load_path("squirrel"))) > 0
+
+
+@pytest.mark.parametrize("name", ["squirrel", "tv", "rust", "ava", "huyak", "material", "squirrel_stroked"])
+@pytest.mark.parametrize("rule", [rb.FillRule.NonZero, rb.FillRule.EvenOdd])
+def test_mask_matches_oracle(rast, name, rule):
+    """`Rasterizer::mask` on the `Path::size` canvas (the reference bench's workload, benches/rasterize_bench.rs:99-108)"""
+    p = assets.load_path(name)
+    e = assets.expected()["paths"][name]
+    w, h = e["size"]
+    tr = np.array(e["size_tr"])
+    img = np.zeros((h, w))
+    rast.mask(p, tr, img, rule)
+    ref = np.zeros((h, w))
+    opath(p).mask(tr, int(rule), ref)
+    assert np.abs(img - ref).max() <= COV_TOL
+    key = "mask_sum_nonzero" if rule == rb.FillRule.NonZero else "mask_sum_evenodd"
+    assert abs(img.sum() - e[key]) <= 1e-4 * w * h
+    # f32 entry point agrees with the f64 one
+    img32 = np.zeros((h, w), dtype=np.float32)
+    rast.mask(p, tr, img32, rule)
+    assert np.array_equal(img32.astype(np.float64), img)
+
+
+def test_reference_kats_through_gpu(rast):
+    """src/rasterize.rs:1065-1161 test_rasterizer + test_fill_rule with the GpuRasterizer in the loop"""
+    b = rb.Path.builder()
+    b.move_to((1, 0)).line_to((1, 1)).line_to((2, 2)).line_to((4, 3)).line_to((5, 3)).line_to((7, 2)).line_to((8, 1)).line_to((8, 0)).close()
+    img = np.zeros((4, 9))
+    b.build().mask(rast, rb.Transform.identity(), rb.FillRule.EvenOdd, img)
+    expected = np.array([
+        0.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.0,
+        0.0, 0.5, 1.0, 1.0, 1.0, 1.0, 1.0, 0.5, 0.0,
+        0.0, 0.0, 0.25, 0.75, 1.0, 0.75, 0.25, 0.0, 0.0,
+        0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]).reshape(4, 9)
+    assert np.abs(img - expected).max() <= 1e-6
+    # star + boxes
+    op = O.OraclePath.parse("M50,0 21,90 98,35 2,35 79,90z M110,0 h90 v90 h-90z M130,20 h50 v50 h-50 z M210,0  h90 v90 h-90 z M230,20 v50 h50 v-50 z")
+    p = rb.Path(*op.export())
+    (w, h), tr, _ = op.size()
+    img = np.zeros((h, w))
+    p.mask(rast, tr, rb.FillRule.EvenOdd, img)
+    assert abs(img[50, 50]) < 1e-6 and abs(img[50, 150]) < 1e-6 and abs(img[50, 250]) < 1e-6
+    assert abs(img.sum() - 13130.0) < 1.0
+    img[:] = 0
+    p.mask(rast, tr, rb.FillRule.NonZero, img)
+    assert abs(img[50, 50] - 1) < 1e-6 and abs(img[50, 150] - 1) < 1e-6 and abs(img[50, 250]) < 1e-6
+    assert abs(img.sum() - 16492.5) < 1.0
+
+
+def test_mask_edges_and_clipping(rast):
+    """H8 edge semantics: x<0 fold, right-edge clamp, y clipping, overflow column, ragged sizes"""
+    p = assets.load_path("squirrel")
+    op = opath(p)
+    for (w, h, tr) in [(37, 23, O.translate(-30.0, -20.0)), (130, 9, O.translate(5.0, -40.0)), (1, 50, O.IDENTITY),
+                       (1030, 70, O.transform_mul(O.translate(-40.0, -300.0), O.scale(12.0, 5.0))), (64, 64, O.scale(0.2, 0.2)),
+                       (3, 3, O.translate(-50.0, -50.0))]:
+        for rule in (rb.FillRule.NonZero, rb.FillRule.EvenOdd):
+            img = np.zeros((h, w))
+            rast.mask(p, tr, img, rule)
+            ref = np.zeros((h, w))
+            op.mask(tr, int(rule), ref)
+            assert np.abs(img - ref).max() <= COV_TOL, (w, h, rule)
+
+
+def test_mask_strided_view(rast):
+    p = assets.load_path("tv")
+    e = assets.expected()["paths"]["tv"]
+    w, h = e["size"]
+    tr = np.array(e["size_tr"])
+    big = np.zeros((h + 4, 2 * (w + 3)))
+    view = big[2:2 + h, 1:1 + 2 * w:2]  # row and column strides
+    rast.mask(p, tr, view, rb.FillRule.NonZero)
+    ref = np.zeros((h, w))
+    opath(p).mask(tr, O.NONZERO, ref)
+    assert np.abs(view - ref).max() <= COV_TOL
+    mask = np.ones_like(big, dtype=bool)
+    mask[2:2 + h, 1:1 + 2 * w:2] = False
+    assert (big[mask] == 0).all()
+
+
+def test_mask_iter_matches_oracle(rast):
+    p = assets.load_path("rust")
+    e = assets.expected()["paths"]["rust"]
+    w, h = e["size"]
+    tr = np.array(e["size_tr"])
+    got = rast.mask_iter(p, tr, rb.Size(w, h), rb.FillRule.NonZero)
+    ref = opath(p).mask_iter(tr, w, h, O.NONZERO)
+    gd = {(x, y): a for x, y, a in got}
+    rd = {(x, y): a for x, y, a in ref}
+    # pixels may differ only where alpha is at the 1e-6 drop threshold
+    for k in set(gd) | set(rd):
+        assert abs(gd.get(k, 0.0) - rd.get(k, 0.0)) <= COV_TOL
+    assert got == sorted(got, key=lambda t: (t[1], t[0]))
+    assert rast.mask_iter(p, tr, rb.Size(0, 10), rb.FillRule.NonZero) == []
+
+
+def test_empty_path_and_zero_size(rast):
+    img = np.zeros((5, 7))
+    rast.mask(rb.Path.empty(), rb.Transform.identity(), img, rb.FillRule.NonZero)
+    assert (img == 0).all()
+    assert len(rast.flatten(rb.Path.empty())) == 0
+    rast.mask(assets.load_path("squirrel"), rb.Transform.identity(), np.zeros((0, 0)), rb.FillRule.NonZero)
+
+
+def test_deterministic(rast):
+    p = assets.load_path("ava")
+    e = assets.expected()["paths"]["ava"]
+    w, h = e["size"]
+    tr = np.array(e["size_tr"])
+    a = np.zeros((h, w), dtype=np.float32)
+    b = np.zeros((h, w), dtype=np.float32)
+    rast.mask(p, tr, a, rb.FillRule.NonZero)
+    for _ in range(3):
+        rast.mask(p, tr, b, rb.FillRule.NonZero)
+        assert np.array_equal(a, b)  # bit-identical across runs (fixed-point atomics)
+
+
+def test_c2_material_4096(rast):
+    """BASELINE config 2: material.path fitted to 4096x4096, nonzero and even-odd"""
+    p = assets.load_path("material")
+    c2 = assets.expected()["paths"]["material"]["c2"]
+    tr = np.array(c2["tr"])
+    w, h = c2["size"]
+    op = opath(p)
+    for rule in (rb.FillRule.NonZero, rb.FillRule.EvenOdd):
+        img = np.zeros((h, w), dtype=np.float32)
+        rast.mask(p, tr, img, rule)
+        ref = np.zeros((h, w))
+        op.mask_threads(tr, int(rule), ref, threads=8)
+        assert np.abs(img - ref).max() <= COV_TOL
+    assert rast.last_counts()["lines"] == c2["lines"]
