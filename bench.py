@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""Benchmark of the fill hot path (BASELINE.json: Mpix/s, flattened lines/s, nonzero fill) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4|c5]
+
+A step is one pass of the hot path (flatten -> bin -> signed-difference raster) over one batch:
+  c2 (default, BASELINE configs[1]): data/material.path fitted to 4096x4096, `Rasterizer::mask`, non-zero.
+  c4: a batch of synthetic random-cubic glyphs at 64x64 (SURVEY §8d generator), mask per glyph.
+  c5: tv.path stroked on a 32768-wide canvas, this rank's band of rows (band sharding).
+N > 1 (under torchrun): every rank runs the same per-GPU workload on its own device with no data-path collective
+(independent paths of a batch / bands of a canvas) => weak scaling; value = units of all ranks / max-over-ranks time.
+
+Timing: CUDA events on the rasterizer's own stream around every step, L2 flushed (256 MiB memset) between steps
+outside the event pairs; torch is used for device buffers, events, the barrier and the max-over-ranks reduction only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(workload: str):
+    """dram bytes per raster launch from the committed ncu --set full capture, if one exists for this workload."""
+    p = os.path.join(ROOT, "profiles", "raster_traffic.json")
+    try:
+        return float(json.load(open(p))[workload]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr:
+            self._stop.set()
+            self._thr.join()
+        return {"sm_mhz": (statistics.median(self.samples) if self.samples else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---- workloads -------------------------------------------------------------------------------------------
+def glyph_path(rb, seed: int):
+    """Synthetic glyph of SURVEY §8d (LCG of the reference's benches/scene_bench.rs:53-88): 3 closed contours of
+    6 cubics, every coordinate uniform()*56+4."""
+    state = seed & 0xffffffff
+
+    def step():
+        nonlocal state
+        state = (state * 214013 + 2531011) & 0x7fffffff
+        return state >> 16
+
+    def u32():
+        hi = step() & 0xffff
+        lo = step() & 0xffff
+        return (hi << 16) | lo
+
+    def uniform():
+        hi = u32()
+        lo = u32()
+        return (((hi << 32) | lo) >> 10) * 2.0 ** -53
+
+    def pt():
+        x = uniform() * 56.0 + 4.0
+        y = uniform() * 56.0 + 4.0
+        return (x, y)
+
+    b = rb.Path.builder()
+    for _ in range(3):
+        b.move_to(pt())
+        for _ in range(6):
+            q1 = pt(); q2 = pt(); q3 = pt()
+            b.cubic_to(q1, q2, q3)
+        b.close()
+    return b.build()
+
+
+def build_workload(name: str, rb, rast, rank: int, world: int, torch):
+    from rasterize_b200 import assets, ffi
+    ex = assets.expected()["paths"]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if name == "c2":
+        path = assets.load_path("material")
+        c2 = ex["material"]["c2"]
+        w, h = c2["size"]
+        tr = np.array(c2["tr"])
+        canvases = [torch.empty((h, w), dtype=torch.float32, device=dev)]
+        dp = rast.upload(path)
+        jobs = [rb.Job(dp, tr, rb.FillRule.NonZero, ffi.JOB_MASK, canvases[0].data_ptr(), w, h, w)]
+        info = dict(workload="c2: data/material.path (21106 segments) fitted to 4096x4096, Rasterizer::mask, nonzero",
+                    canvas=[w, h], items_per_gpu=1, pixels_per_step=w * h, in_bytes=path.input_bytes(), out_bytes=4 * w * h,
+                    host_path=path, host_tr=tr, host_size=(w, h), keep=[dp, canvases])
+        return jobs, True, info
+    if name == "c4":
+        n = int(os.environ.get("RB_GLYPHS", "20000"))
+        first = rank * n
+        paths = [glyph_path(rb, first + i + 1) for i in range(n)]
+        slab = torch.empty((n, 64, 64), dtype=torch.float32, device=dev)
+        dps = [rast.upload(p) for p in paths]
+        ident = np.array([1.0, 0, 0, 0, 1.0, 0])
+        jobs = [rb.Job(dps[i], ident, rb.FillRule.NonZero, ffi.JOB_MASK, slab.data_ptr(), 64, 64, 64, origin=i * 4096) for i in range(n)]
+        info = dict(workload=f"c4: {n} synthetic random-cubic glyphs per GPU at 64x64, mask per glyph, nonzero", canvas=[64, 64],
+                    items_per_gpu=n, pixels_per_step=n * 4096, in_bytes=sum(p.input_bytes() for p in paths), out_bytes=4 * n * 4096,
+                    keep=[dps, slab])
+        return jobs, True, info
+    if name == "c5":
+        path = assets.load_path("tv_stroked")
+        c5 = ex["tv_stroked"]["c5"]
+        w, hfull = c5["size"]
+        bands = int(os.environ.get("RB_BANDS", "8"))
+        band = rank % bands
+        y0, y1 = hfull * band // bands, hfull * (band + 1) // bands
+        h = y1 - y0
+        tr = np.array(c5["tr"]).copy()
+        tr[5] -= y0  # band-local translate(0, -y0): the y<0 / y>=H clipping crops exactly
+        canvas = torch.empty((h, w), dtype=torch.float32, device=dev)
+        dp = rast.upload(path)
+        jobs = [rb.Job(dp, tr, rb.FillRule.NonZero, ffi.JOB_MASK, canvas.data_ptr(), w, h, w)]
+        info = dict(workload=f"c5: tv.path stroked (w=0.5 round/round) on a {w}x{hfull} canvas, band {band} of {bands} ({h} rows), mask, nonzero",
+                    canvas=[w, h], items_per_gpu=1, pixels_per_step=w * h, in_bytes=path.input_bytes(), out_bytes=4 * w * h,
+                    keep=[dp, canvas])
+        return jobs, True, info
+    raise SystemExit(f"unknown workload {name}")
+
+
+def run_ours(args):
+    import torch
+
+    import rasterize_b200 as rb
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (rasterize_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rast = rb.GpuRasterizer(device=local_rank)
+    jobs, independent, info = build_workload(args.workload, rb, rast, rank, world, torch)
+    prepared = rast.prepare_batch(jobs)
+    stream = torch.cuda.ExternalStream(rast.stream(), device=torch.device("cuda", local_rank))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def step(sync=False):
+        rast.submit_prepared(prepared, independent=independent, sync=sync)
+
+    # first call sizes the scratch buffers (and re-runs on overflow); then untimed warm-up
+    step(sync=True)
+    counts0 = rast.last_counts()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    rast.batch_status()
+    rast.set_profiling(True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    sampler.start()
+    l0 = rast.last_counts()["launches"]
+    with torch.cuda.stream(stream):
+        for i in range(args.steps):
+            flush.zero_()  # L2 flush between timed iterations, outside the event pair
+            starts[i].record(stream)
+            step()
+            stops[i].record(stream)
+            if (i & 31) == 31 or i == args.steps - 1:
+                rast.batch_status()  # surfaces device-side errors; also bounds the launch queue depth
+    barrier()
+    clocks = sampler.stop()
+    launches = rast.last_counts()["launches"] - l0
+    per_step = np.array([a.elapsed_time(b) for a, b in zip(starts, stops)])
+    total_ms = float(per_step.sum())
+    # per-stage split (flatten / bin / raster) from the library's own events, sampled on a few extra steps
+    stage_samples = []
+    for _ in range(min(20, args.steps)):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        step(sync=True)
+        stage_samples.append(rast.last_stage_ms())
+    stage_ms = np.median(np.array(stage_samples), axis=0)
+    rast.set_profiling(False)
+
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    ms_per_step = total_ms_max / args.steps
+    counts = rast.last_counts()
+    pixels = info["pixels_per_step"] * world
+    value = pixels / (ms_per_step * 1e-3) / 1e6
+    lines_per_s = counts["lines"] * world / (ms_per_step * 1e-3)
+
+    peak, peak_src = measured_peak()
+    raster_s = float(stage_ms[2]) * 1e-3
+    achieved = info["out_bytes"] / raster_s / 1e9 if raster_s > 0 else 0.0
+    step_alg = info["in_bytes"] + info["out_bytes"]
+    roofline = {
+        "bound": "hbm", "kernel": "raster_kernel (K3: accumulate + row scan + fill rule + store)",
+        "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "peak_source": peak_src,
+        "traffic": recorded_traffic(args.workload),
+        "algorithmic_bytes_per_launch": info["out_bytes"], "kernel_ms": round(float(stage_ms[2]), 5),
+        "stage_ms": {"flatten": round(float(stage_ms[0]), 5), "bin": round(float(stage_ms[1]), 5), "raster": round(float(stage_ms[2]), 5)},
+        "step_algorithmic_bytes": step_alg, "step_frac": round(step_alg / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+    }
+
+    # ---- e2e: the trait-level C-ABI call with HOST buffers (H2D of the path, kernels, D2H of the f64 mask) ----
+    e2e = None
+    cpu_baseline = None
+    if args.workload == "c2":
+        path, tr, (w, h) = info["host_path"], info["host_tr"], info["host_size"]
+        img = rast.host_alloc((h, w), np.float64)  # pinned host image, as the contract asks
+        for _ in range(2):
+            rast.mask(path, tr, img, rb.FillRule.NonZero)
+        n_e2e = max(5, min(20, args.steps))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            rast.mask(path, tr, img, rb.FillRule.NonZero)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_e2e
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        h2d = path.points.nbytes + path.kinds.nbytes + path.subpath_offsets.nbytes + path.closed.nbytes
+        e2e = {"value": round(w * h * world / dt / 1e6, 1), "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(img.nbytes),
+               "ms_per_call": round(dt * 1e3, 4), "call": "rgpu_mask (f64 strided host image, pinned)"}
+        # f32 variant of the same call, for context
+        img32 = rast.host_alloc((h, w), np.float32)
+        rast.mask(path, tr, img32, rb.FillRule.NonZero)
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            rast.mask(path, tr, img32, rb.FillRule.NonZero)
+        e2e["f32_ms_per_call"] = round((time.perf_counter() - t0) / n_e2e * 1e3, 4)
+        if rank == 0 and world == 1:
+            cpu_baseline = cpu_reference_c2(threads=1, budget_s=12.0)
+
+    if rank == 0:
+        out = {
+            "metric": "fill throughput (Rasterizer::mask, nonzero), pixels rasterized per second", "value": round(value, 1), "unit": "Mpix/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 geometry / Q7.24 fixed-point accumulation / f32 coverage",
+            "data": "synthetic" if args.workload == "c4" else "reference asset (flat fixture of data/*.path), random-free",
+            "config": {"workload": info["workload"], "canvas": info["canvas"], "items_per_gpu": info["items_per_gpu"],
+                       "flatness": 0.05, "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
+                       "parallelism": f"{world} independent replicas/shards, no collective"},
+            "lines_per_s": round(lines_per_s, 1), "lines_per_step_per_gpu": counts["lines"], "line_refs_per_step_per_gpu": counts["line_refs"],
+            "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
+            "roofline": roofline, "clocks": clocks,
+            "step_ms_min_med_max": [round(float(per_step.min()), 5), round(float(np.median(per_step)), 5), round(float(per_step.max()), 5)],
+        }
+        if e2e is not None:
+            out["e2e"] = e2e
+        if cpu_baseline is not None:
+            out["cpu_baseline"] = cpu_baseline
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_reference_c2(threads: int, budget_s: float):
+    """Times the CPU oracle (restatement of SignedDifferenceRasterizer::mask; the Rust reference cannot be built
+    here) on config 2: img.clear() + mask per iteration as benches/rasterize_bench.rs:99-108 does."""
+    import oracle as O
+    from rasterize_b200 import assets
+    p = assets.load_path("material")
+    c2 = assets.expected()["paths"]["material"]["c2"]
+    w, h = c2["size"]
+    tr = np.array(c2["tr"])
+    op = O.OraclePath.from_flat(p.points, p.kinds, p.subpath_offsets, p.closed)
+    img = np.zeros((h, w))
+    op.mask_threads(tr, O.NONZERO, img, threads)  # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        img[:] = 0
+        op.mask_threads(tr, O.NONZERO, img, threads)
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 200:
+            break
+    dt = (time.perf_counter() - t0) / n
+    return {"value": round(w * h / dt / 1e6, 1), "unit": "Mpix/s", "cores": threads, "kind": "port",
+            "sample": f"{n} x (clear + mask) of material.path at {w}x{h}, nonzero, {threads} thread(s), {dt * 1e3:.2f} ms each",
+            "host_cores": os.cpu_count()}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path on the host cores.  The Rust crate cannot
+    be compiled in this image (no cargo/rustc), so this is the oracle port with all the host threads it can use
+    (rows are independent: one band of rows per thread)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if args.workload != "c2":
+        print(json.dumps({"impl": "reference", "unavailable": "reference arm is implemented for the c2 workload"}))
+        return
+    threads = os.cpu_count() or 1
+    import oracle as O
+    from rasterize_b200 import assets
+    p = assets.load_path("material")
+    c2 = assets.expected()["paths"]["material"]["c2"]
+    w, h = c2["size"]
+    tr = np.array(c2["tr"])
+    op = O.OraclePath.from_flat(p.points, p.kinds, p.subpath_offsets, p.closed)
+    img = np.zeros((h, w))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps = min(args.steps, 60)
+    for _ in range(min(max(args.warmup, 1), 5)):
+        img[:] = 0
+        op.mask_threads(tr, O.NONZERO, img, threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        img[:] = 0
+        op.mask_threads(tr, O.NONZERO, img, threads)
+    dt = (time.perf_counter() - t0) / steps
+    value = round(w * h / dt / 1e6, 1)
+    lines = assets.expected()["paths"]["material"]["c2"]["lines"]
+    out = {
+        "impl": "reference", "metric": "fill throughput (Rasterizer::mask, nonzero), pixels rasterized per second", "value": value,
+        "unit": "Mpix/s", "n_gpus": world, "steps": steps, "warmup": min(max(args.warmup, 1), 5), "ms_per_step": round(dt * 1e3, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "reference asset (flat fixture of data/*.path)",
+        "config": {"workload": "c2: data/material.path (21106 segments) fitted to 4096x4096, Rasterizer::mask, nonzero", "canvas": [w, h],
+                   "items_per_gpu": 1, "flatness": 0.05},
+        "lines_per_s": round(lines / dt, 1),
+        "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} x (clear + mask) of material.path at {w}x{h}, {threads} threads (one band of rows each)"},
+        "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

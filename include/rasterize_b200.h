@@ -153,6 +153,11 @@ int rgpu_render_batch_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, u
 /* Lines produced by the flatten stage of the last completed batch, and kernels launched since create. */
 int rgpu_last_counts(rgpu_ctx* ctx, uint64_t* n_lines, uint64_t* n_line_refs, uint64_t* n_launches);
 
+/* Optional per-stage device timing of batches (CUDA events on the context's stream around the flatten, bin and
+ * raster stages).  rgpu_last_stage_ms is valid after rgpu_batch_status / *_sync: out = {flatten, bin, raster} ms. */
+int rgpu_set_profiling(rgpu_ctx* ctx, int enable);
+int rgpu_last_stage_ms(rgpu_ctx* ctx, float out[3]);
+
 /* LinColor (f32x4) device image -> RGBA8 device image: `From<LinColor> for RGBA` (src/color.rs:164-175) with the
  * x86 `l2s` polynomial (src/simd/x86.rs:197-214). n = pixels. */
 int rgpu_to_rgba8_dev(rgpu_ctx* ctx, const float* lin_dev, uint8_t* rgba_dev, size_t n_pixels);

@@ -85,6 +85,11 @@ orc_paint* orc_paint_linear(const double* stop_pos, const float* stop_colors, si
 orc_paint* orc_paint_radial(const double* stop_pos, const float* stop_colors, size_t n, int sort_stops, int units,
                             int linear_colors, int spread, const double tr[6], const double center[2], double radius,
                             const double fcenter[2], double fradius);
+/* same, but stop colours are given in STORED space (already converted when !linear_colors) and kept verbatim */
+orc_paint* orc_paint_linear_stored(const double* stop_pos, const float* stop_colors, size_t n, int units, int linear_colors, int spread,
+                                   const double tr[6], const double start[2], const double end[2]);
+orc_paint* orc_paint_radial_stored(const double* stop_pos, const float* stop_colors, size_t n, int units, int linear_colors, int spread,
+                                   const double tr[6], const double center[2], double radius, const double fcenter[2], double fradius);
 void orc_paint_free(orc_paint*);
 void orc_paint_at(const orc_paint*, double x, double y, float out[4]);
 int orc_paint_radial_offset(const orc_paint*, double x, double y, double* out); /* 0 = None */

@@ -255,6 +255,19 @@ orc_paint* orc_paint_radial(const double* pos, const float* colors, size_t n, in
                               Point(center[0], center[1]), radius, Point(fcenter[0], fcenter[1]), fradius);
     return r;
 }
+orc_paint* orc_paint_linear_stored(const double* pos, const float* colors, size_t n, int units, int linear_colors, int spread,
+                                   const double tr[6], const double start[2], const double end[2]) {
+    // construct as linear_colors (no convert_to_srgb), then restore the flag: `at` applies into_linear iff !linear_colors
+    auto* r = orc_paint_linear(pos, colors, n, 0, units, 1, spread, tr, start, end);
+    r->p.linear_colors = linear_colors != 0;
+    return r;
+}
+orc_paint* orc_paint_radial_stored(const double* pos, const float* colors, size_t n, int units, int linear_colors, int spread,
+                                   const double tr[6], const double center[2], double radius, const double fcenter[2], double fradius) {
+    auto* r = orc_paint_radial(pos, colors, n, 0, units, 1, spread, tr, center, radius, fcenter, fradius);
+    r->p.linear_colors = linear_colors != 0;
+    return r;
+}
 void orc_paint_free(orc_paint* p) { delete p; }
 void orc_paint_at(const orc_paint* p, double x, double y, float out[4]) {
     LinColor c = p->p.at(Point(x, y));

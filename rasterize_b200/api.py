@@ -540,6 +540,15 @@ class GpuRasterizer:
         ffi.lib().rgpu_last_counts(self.ctx, C.byref(a), C.byref(b), C.byref(c))
         return dict(lines=a.value, line_refs=b.value, launches=c.value)
 
+    def set_profiling(self, on: bool) -> None:
+        self._check(ffi.lib().rgpu_set_profiling(self.ctx, int(on)))
+
+    def last_stage_ms(self):
+        """(flatten_ms, bin_ms, raster_ms) of the last profiled batch, from CUDA events on the context's stream."""
+        out = (C.c_float * 3)()
+        self._check(ffi.lib().rgpu_last_stage_ms(self.ctx, out))
+        return float(out[0]), float(out[1]), float(out[2])
+
     def stream(self) -> int:
         return int(ffi.lib().rgpu_stream(self.ctx) or 0)
 

@@ -1,4 +1,4 @@
-// K2 — binning of flattened lines into (job, scanline band) bins, plus the exclusive scans used by K1/K2.
+// K2 — binning of flattened lines into (job, scanline band) bins (the scans live in scan.cu).
 //
 // Rows are independent in the signed-difference rasterizer (reference src/rasterize.rs:421-469: accumulation is
 // per (line,row); :478-503: the scan runs along x within a row), so a line is referenced once from every band
@@ -6,7 +6,6 @@
 //   first = floor(max(min_y, 0)),  end = min(H, ceil(max(max_y, 0)))     (src/rasterize.rs:414, 421)
 // Lines with |dy| < EPSILON add nothing (src/rasterize.rs:400-403) and are dropped here.
 #include "rgpu_internal.cuh"
-#include <cub/device/device_scan.cuh>
 
 namespace rgpu {
 
@@ -75,16 +74,6 @@ bin_fill_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const uint32_t
 }
 
 }  // namespace
-
-size_t scan_temp_bytes(uint32_t n) {
-    size_t bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
-    return bytes;
-}
-
-void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, void* temp, size_t temp_bytes, cudaStream_t s) {
-    cub::DeviceScan::ExclusiveSum(temp, temp_bytes, in, out, (int)n, s);
-}
 
 static inline uint32_t line_grid(cudaStream_t) { return 148 * 8; }
 

@@ -75,6 +75,10 @@ struct rgpu_ctx {
     // last submission (for status / retry)
     uint64_t need_lines = 0, need_refs = 0;
     uint32_t last_total_slots = 0;
+    // optional stage timing
+    bool profiling = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
 };
 
 namespace {
@@ -369,14 +373,19 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     CK(ctx, cudaMemsetAsync(d_cur, 0, sizeof(uint32_t) * (band_acc + 1), s));
 
     double thr = 16.0 * ctx->flatness * ctx->flatness;  // PathFlattenIter::new, src/path.rs:749
+    const bool prof = ctx->profiling;
+    ctx->ev_valid = false;
+    if (prof) CK(ctx, cudaEventRecord(ctx->ev[0], s));
     launch_flatten_count(d_jobs, n_live, item_acc, thr, d_counts, d_status, s);
     launch_exclusive_scan(d_counts, d_offs, total_slots + 1, ctx->scan_temp.p, ctx->scan_temp.cap, s);
     launch_flatten_emit(d_jobs, n_live, item_acc, thr, d_offs, d_lines, (uint32_t)ctx->lines_cap, d_status, s);
+    if (prof) CK(ctx, cudaEventRecord(ctx->ev[1], s));
     launch_bin_count(d_jobs, n_live, d_offs, total_slots, d_lines, d_bc, ts.th, d_status, s);
     launch_exclusive_scan(d_bc, d_bo, band_acc + 1, ctx->scan_temp.p, ctx->scan_temp.cap, s);
     launch_bin_fill(d_jobs, n_live, d_offs, total_slots, d_lines, d_bo, band_acc, d_cur, d_refs, (uint32_t)ctx->refs_cap, ts.th,
                     d_status, s);
     ctx->n_launches += 6;
+    if (prof) CK(ctx, cudaEventRecord(ctx->ev[2], s));
     if (flags & RGPU_BATCH_INDEPENDENT) {
         launch_raster(variant, d_jobs, n_live, 0, 0, tile_acc, d_paints, d_lines, d_bo, d_refs, d_status, s);
         ctx->n_launches += 1;
@@ -386,6 +395,10 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
             launch_raster(variant, d_jobs, 1, j, d.tile_begin, d.n_bands * d.n_chunks, d_paints, d_lines, d_bo, d_refs, d_status, s);
             ctx->n_launches += 1;
         }
+    }
+    if (prof) {
+        CK(ctx, cudaEventRecord(ctx->ev[3], s));
+        ctx->ev_valid = true;
     }
     CK(ctx, cudaMemcpyAsync(ctx->h_status, d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
     CK(ctx, cudaGetLastError());
@@ -488,6 +501,8 @@ void rgpu_destroy(rgpu_ctx* ctx) {
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_jobs) cudaFreeHost(ctx->h_jobs);
     if (ctx->h_paints) cudaFreeHost(ctx->h_paints);
+    for (int i = 0; i < 4; i++)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -595,6 +610,24 @@ int rgpu_last_counts(rgpu_ctx* ctx, uint64_t* n_lines, uint64_t* n_line_refs, ui
     if (n_lines) *n_lines = ctx->last_lines;
     if (n_line_refs) *n_line_refs = ctx->last_refs;
     if (n_launches) *n_launches = ctx->n_launches;
+    return RGPU_OK;
+}
+
+int rgpu_set_profiling(rgpu_ctx* ctx, int enable) {
+    if (!ctx) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (enable && !ctx->ev[0])
+        for (int i = 0; i < 4; i++) CK(ctx, cudaEventCreate(&ctx->ev[i]));
+    ctx->profiling = enable != 0;
+    ctx->ev_valid = false;
+    return RGPU_OK;
+}
+
+int rgpu_last_stage_ms(rgpu_ctx* ctx, float out[3]) {
+    if (!ctx || !out) return RGPU_ERR_INVALID;
+    if (!ctx->ev_valid) return fail(ctx, RGPU_ERR_INVALID, "no profiled batch (call rgpu_set_profiling(ctx, 1) first)");
+    CK(ctx, cudaEventSynchronize(ctx->ev[3]));
+    for (int i = 0; i < 3; i++) CK(ctx, cudaEventElapsedTime(&out[i], ctx->ev[i], ctx->ev[i + 1]));
     return RGPU_OK;
 }
 

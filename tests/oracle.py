@@ -106,6 +106,8 @@ def lib():
     sig("orc_paint_solid", vp, pf)
     sig("orc_paint_linear", vp, pd, pf, sz, i32, i32, i32, i32, pd, pd, pd)
     sig("orc_paint_radial", vp, pd, pf, sz, i32, i32, i32, i32, pd, pd, dbl, pd, dbl)
+    sig("orc_paint_linear_stored", vp, pd, pf, sz, i32, i32, i32, pd, pd, pd)
+    sig("orc_paint_radial_stored", vp, pd, pf, sz, i32, i32, i32, pd, pd, dbl, pd, dbl)
     sig("orc_paint_free", None, vp)
     sig("orc_paint_at", None, vp, dbl, dbl, pf)
     sig("orc_paint_radial_offset", i32, vp, dbl, dbl, pd)
