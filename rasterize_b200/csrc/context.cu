@@ -59,7 +59,7 @@ struct rgpu_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     // device scratch (grow-only)
-    DevBuf jobs, paints, slot_counts, slot_offs, lines, band_counts, band_offs, band_cursor, refs, scan_temp, status;
+    DevBuf jobs, paints, slot_counts, slot_offs, lines, line_job, band_counts, band_offs, band_cursor, refs, scan_temp, status;
     DevBuf img_f32, img_f64, img_lin;  // staging canvases of the host-buffer entry points
     size_t lines_cap = 0, refs_cap = 0;
     // pinned host
@@ -259,7 +259,7 @@ bool build_paint(const rgpu_job& job, PaintDev& out) {
     return true;
 }
 
-int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, int close_flag) {
+int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, int close_flag, bool ordered_lines = false) {
     if (n_jobs == 0) return RGPU_OK;
     if (!jobs) return fail(ctx, RGPU_ERR_INVALID, "jobs is NULL");
     if (!(ctx->flatness > 0.0)) return fail(ctx, RGPU_ERR_INVALID, "flatness must be > 0 (the reference loops forever on 0)");
@@ -342,16 +342,22 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     size_t want_refs = std::max<uint64_t>(ctx->refs_cap, want_lines * 2);
     if ((rc = ensure_dev(ctx, ctx->jobs, sizeof(JobDev) * n_live))) return rc;
     if ((rc = ensure_dev(ctx, ctx->paints, sizeof(PaintDev) * std::max<uint32_t>(n_paints, 1)))) return rc;
-    if ((rc = ensure_dev(ctx, ctx->slot_counts, sizeof(uint32_t) * (total_slots + 1)))) return rc;
-    if ((rc = ensure_dev(ctx, ctx->slot_offs, sizeof(uint32_t) * (total_slots + 1)))) return rc;
+    if (ordered_lines) {
+        if ((rc = ensure_dev(ctx, ctx->slot_counts, sizeof(uint32_t) * (total_slots + 1)))) return rc;
+        if ((rc = ensure_dev(ctx, ctx->slot_offs, sizeof(uint32_t) * (total_slots + 1)))) return rc;
+    }
     if ((rc = ensure_dev(ctx, ctx->lines, sizeof(double4) * want_lines))) return rc;
     ctx->lines_cap = std::min<size_t>(ctx->lines.cap / sizeof(double4), 0xfffffff0u);
+    const bool need_line_job = !ordered_lines && n_live > 1;
+    if (need_line_job) {
+        if ((rc = ensure_dev(ctx, ctx->line_job, sizeof(uint32_t) * ctx->lines_cap))) return rc;
+    }
     if ((rc = ensure_dev(ctx, ctx->refs, sizeof(uint32_t) * want_refs))) return rc;
     ctx->refs_cap = std::min<size_t>(ctx->refs.cap / sizeof(uint32_t), 0xfffffff0u);
     if ((rc = ensure_dev(ctx, ctx->band_counts, sizeof(uint32_t) * (band_acc + 1)))) return rc;
     if ((rc = ensure_dev(ctx, ctx->band_offs, sizeof(uint32_t) * (band_acc + 1)))) return rc;
     if ((rc = ensure_dev(ctx, ctx->band_cursor, sizeof(uint32_t) * (band_acc + 1)))) return rc;
-    size_t tb = std::max(scan_temp_bytes(total_slots + 1), scan_temp_bytes(band_acc + 1));
+    size_t tb = std::max(ordered_lines ? scan_temp_bytes(total_slots + 1) : 0, scan_temp_bytes(band_acc + 1));
     if ((rc = ensure_dev(ctx, ctx->scan_temp, tb))) return rc;
 
     cudaStream_t s = ctx->stream;
@@ -376,15 +382,23 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     const bool prof = ctx->profiling;
     ctx->ev_valid = false;
     if (prof) CK(ctx, cudaEventRecord(ctx->ev[0], s));
-    launch_flatten_count(d_jobs, n_live, item_acc, thr, d_counts, d_status, s);
-    launch_exclusive_scan(d_counts, d_offs, total_slots + 1, ctx->scan_temp.p, ctx->scan_temp.cap, s);
-    launch_flatten_emit(d_jobs, n_live, item_acc, thr, d_offs, d_lines, (uint32_t)ctx->lines_cap, d_status, s);
+    uint32_t* d_line_job = need_line_job ? static_cast<uint32_t*>(ctx->line_job.p) : nullptr;
+    if (ordered_lines) {
+        launch_flatten_count(d_jobs, n_live, item_acc, thr, d_counts, d_status, s);
+        launch_exclusive_scan(d_counts, d_offs, total_slots + 1, ctx->scan_temp.p, ctx->scan_temp.cap, s);
+        launch_flatten_emit(d_jobs, n_live, item_acc, thr, d_offs, d_lines, (uint32_t)ctx->lines_cap, d_status, s);
+        ctx->n_launches += 3;
+    } else {
+        d_offs = nullptr;  // bin kernels then take the line count from status->n_lines
+        launch_flatten_fused(d_jobs, n_live, item_acc, thr, d_lines, d_line_job, (uint32_t)ctx->lines_cap, d_status, s);
+        ctx->n_launches += 1;
+    }
     if (prof) CK(ctx, cudaEventRecord(ctx->ev[1], s));
-    launch_bin_count(d_jobs, n_live, d_offs, total_slots, d_lines, d_bc, ts.th, d_status, s);
+    launch_bin_count(d_jobs, n_live, d_offs, total_slots, d_line_job, d_lines, d_bc, ts.th, d_status, s);
     launch_exclusive_scan(d_bc, d_bo, band_acc + 1, ctx->scan_temp.p, ctx->scan_temp.cap, s);
-    launch_bin_fill(d_jobs, n_live, d_offs, total_slots, d_lines, d_bo, band_acc, d_cur, d_refs, (uint32_t)ctx->refs_cap, ts.th,
-                    d_status, s);
-    ctx->n_launches += 6;
+    launch_bin_fill(d_jobs, n_live, d_offs, total_slots, d_line_job, d_lines, d_bo, band_acc, d_cur, d_refs, (uint32_t)ctx->refs_cap,
+                    ts.th, d_status, s);
+    ctx->n_launches += 3;
     if (prof) CK(ctx, cudaEventRecord(ctx->ev[2], s));
     if (flags & RGPU_BATCH_INDEPENDENT) {
         launch_raster(variant, d_jobs, n_live, 0, 0, tile_acc, d_paints, d_lines, d_bo, d_refs, d_status, s);
@@ -418,9 +432,9 @@ int check_status(rgpu_ctx* ctx) {
     return RGPU_OK;
 }
 
-int submit_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, int close_flag) {
+int submit_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, int close_flag, bool ordered_lines = false) {
     for (int attempt = 0; attempt < 4; attempt++) {
-        int rc = submit(ctx, jobs, n_jobs, flags, close_flag);
+        int rc = submit(ctx, jobs, n_jobs, flags, close_flag, ordered_lines);
         if (rc) return rc;
         rc = check_status(ctx);
         if (rc != RGPU_ERR_CAPACITY) return rc;
@@ -429,10 +443,12 @@ int submit_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t fla
         const Status& st = *ctx->h_status;
         size_t nl = std::max<size_t>(st.n_lines, ctx->lines_cap);
         if (st.lines_overflow) {
-            // n_lines is written by bin_count, which is skipped on overflow: read the scan total instead
-            uint32_t total = 0;
-            uint32_t* d_offs = static_cast<uint32_t*>(ctx->slot_offs.p);
-            CK(ctx, cudaMemcpy(&total, d_offs + ctx->last_total_slots, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            uint32_t total = st.n_lines;  // fused flatten: every CTA added its exact count before checking capacity
+            if (ordered_lines) {
+                // n_lines is written by bin_count, which is skipped on overflow: read the scan total instead
+                uint32_t* d_offs = static_cast<uint32_t*>(ctx->slot_offs.p);
+                CK(ctx, cudaMemcpy(&total, d_offs + ctx->last_total_slots, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            }
             nl = (size_t)total + total / 16 + 64;
         }
         size_t nr = st.refs_overflow ? (size_t)st.n_refs + st.n_refs / 16 + 64 : std::max<size_t>(ctx->refs_cap, nl * 2);
@@ -493,7 +509,7 @@ void rgpu_destroy(rgpu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->jobs, &ctx->paints, &ctx->slot_counts, &ctx->slot_offs, &ctx->lines, &ctx->band_counts, &ctx->band_offs,
+    DevBuf* bufs[] = {&ctx->jobs, &ctx->paints, &ctx->slot_counts, &ctx->slot_offs, &ctx->lines, &ctx->line_job, &ctx->band_counts, &ctx->band_offs,
                       &ctx->band_cursor, &ctx->refs, &ctx->scan_temp, &ctx->status, &ctx->img_f32, &ctx->img_f64, &ctx->img_lin};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
@@ -674,7 +690,7 @@ int rgpu_flatten(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int c
     job.row_stride = 1;
     job.width = 1;
     job.height = 1;
-    rc = submit_sync(ctx, &job, 1, RGPU_BATCH_INDEPENDENT, close ? 1 : 0);
+    rc = submit_sync(ctx, &job, 1, RGPU_BATCH_INDEPENDENT, close ? 1 : 0, /*ordered_lines=*/true);
     if (rc == RGPU_OK) {
         size_t n = ctx->last_lines;
         *n_out = n;

@@ -108,23 +108,104 @@ __device__ __forceinline__ void seg_split(const Seg& s, int kind, Seg& s0, Seg& 
     }
 }
 
+// State of one (item, slot) after loading, transforming and descending to the slot's subtree root.
+struct SlotCtx {
+    Seg seg;
+    int kind;
+    uint32_t job;
+    bool leaf_above;  // the subtree root is itself a leaf (the curve was flat above the depth-3 cut)
+};
+
+// Returns false when the slot produces no line.
+__device__ __forceinline__ bool slot_setup(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t t, double thr, SlotCtx& c,
+                                           Status* __restrict__ status) {
+    const uint32_t g = t >> kSlotDepth;
+    const uint32_t slot = t & (kSlotsPerItem - 1);
+    const uint32_t j = find_job(n_jobs, g, [&](uint32_t k) { return jobs[k].item_begin; });
+    const JobDev& job = jobs[j];
+    const uint2 item = job.items[g - job.item_begin];
+    const double* m = job.tr;
+    c.job = j;
+    c.leaf_above = false;
+    if (item.y & kItemClosing) {
+        // closing line of a subpath: Line::new(subpath.end(), subpath.start()).transform(tr), src/path.rs:781-785.
+        // Emitted when the subpath is closed or `close` is set, even if zero length.
+        const bool emit_it = (item.y & kItemExplicitClosed) || job.close;
+        if (slot != 0 || !emit_it) return false;
+        c.kind = 2;
+        c.seg.p[0] = tr_apply(m, job.pts[item.x]);
+        c.seg.p[1] = tr_apply(m, job.pts[item.y & kItemIndexMask]);
+    } else {
+        c.kind = (int)item.y;
+        if (c.kind == 2 && slot != 0) return false;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (i < c.kind) c.seg.p[i] = tr_apply(m, job.pts[item.x + i]);
+    }
+    // descend to this slot's subtree root (bits of `slot`, most significant first)
+#pragma unroll 1
+    for (int level = 0; level < kSlotDepth; level++) {
+        if (seg_has_nan(c.seg, c.kind)) {
+            atomicExch(&status->nan_flag, 1u);
+            return false;
+        }
+        if (seg_flatness(c.seg, c.kind) < thr) {
+            // a leaf above the cut: owned by the slot whose remaining bits are all zero
+            const uint32_t rest = slot & ((1u << (kSlotDepth - level)) - 1u);
+            if (rest != 0) return false;
+            c.leaf_above = true;
+            return true;
+        }
+        Seg s0, s1;
+        seg_split(c.seg, c.kind, s0, s1);
+        c.seg = ((slot >> (kSlotDepth - 1 - level)) & 1u) ? s1 : s0;
+    }
+    return true;
+}
+
+// Depth-first walk of the slot's subtree in the reference's order (left half first); `stack` holds pending right
+// halves.  Calls emit(x0,y0,x1,y1) for every leaf and returns the number of leaves.
+template <class Emit>
+__device__ __forceinline__ uint32_t slot_walk(const SlotCtx& c, double thr, Status* __restrict__ status, Emit emit) {
+    const int kind = c.kind;
+    Seg seg = c.seg;
+    if (c.leaf_above) {
+        emit(seg.p[0].x, seg.p[0].y, seg.p[kind - 1].x, seg.p[kind - 1].y);
+        return 1;
+    }
+    Seg stack[kMaxStack];
+    int top = 0;
+    uint32_t count = 0;
+    while (true) {
+        if (seg_has_nan(seg, kind)) { atomicExch(&status->nan_flag, 1u); break; }
+        if (seg_flatness(seg, kind) < thr) {
+            emit(seg.p[0].x, seg.p[0].y, seg.p[kind - 1].x, seg.p[kind - 1].y);
+            count++;
+            if (top == 0) break;
+            seg = stack[--top];
+        } else {
+            if (top >= kMaxStack) { atomicExch(&status->depth_flag, 1u); break; }
+            Seg s0, s1;
+            seg_split(seg, kind, s0, s1);
+            stack[top++] = s1;
+            seg = s0;
+        }
+    }
+    return count;
+}
+
+// Ordered two-pass form (count, [scan], emit): lines land in the reference's exact order — `Path::flatten` parity.
 template <bool EMIT>
 __global__ void __launch_bounds__(128)
 flatten_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t total_items, double thr,
                uint32_t* __restrict__ slot_counts, const uint32_t* __restrict__ slot_offs, double4* __restrict__ lines,
                uint32_t lines_cap, Status* __restrict__ status) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t total_slots = total_items * kSlotsPerItem;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total_slots = total_items * kSlotsPerItem;
     if (t >= total_slots) {
         if (!EMIT && t == total_slots) slot_counts[t] = 0;  // sentinel so the scan yields the total
         return;
     }
-    uint32_t g = t >> kSlotDepth;
-    uint32_t slot = t & (kSlotsPerItem - 1);
-    uint32_t j = find_job(n_jobs, g, [&](uint32_t k) { return jobs[k].item_begin; });
-    const JobDev& job = jobs[j];
-    uint2 item = job.items[g - job.item_begin];
-
     uint32_t out = 0, out_end = 0;
     if (EMIT) {
         out = slot_offs[t];
@@ -135,79 +216,65 @@ flatten_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t total_
             return;
         }
     }
-    uint32_t count = 0;
-
-    int kind;
-    Seg seg;
-    const double* m = job.tr;
-    if (item.y & kItemClosing) {
-        // closing line of a subpath: Line::new(subpath.end(), subpath.start()).transform(tr), src/path.rs:781-785.
-        // Emitted when the subpath is closed or `close` is set, even if zero length.
-        bool emit_it = (item.y & kItemExplicitClosed) || job.close;
-        if (slot != 0 || !emit_it) {
-            if (!EMIT) slot_counts[t] = 0;
-            return;
-        }
-        kind = 2;
-        seg.p[0] = tr_apply(m, job.pts[item.x]);
-        seg.p[1] = tr_apply(m, job.pts[item.y & kItemIndexMask]);
-    } else {
-        kind = (int)item.y;
-        if (kind == 2 && slot != 0) {
-            if (!EMIT) slot_counts[t] = 0;
-            return;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            if (i < kind) seg.p[i] = tr_apply(m, job.pts[item.x + i]);
-    }
-
-    // descend to this slot's subtree root (bits of `slot`, most significant first)
-    bool leaf_above = false;
-#pragma unroll 1
-    for (int level = 0; level < kSlotDepth; level++) {
-        if (seg_has_nan(seg, kind)) { atomicExch(&status->nan_flag, 1u); if (!EMIT) slot_counts[t] = 0; return; }
-        if (seg_flatness(seg, kind) < thr) {
-            // a leaf above the cut: owned by the slot whose remaining bits are all zero
-            uint32_t rest = slot & ((1u << (kSlotDepth - level)) - 1u);
-            if (rest != 0) { if (!EMIT) slot_counts[t] = 0; return; }
-            leaf_above = true;
-            break;
-        }
-        Seg s0, s1;
-        seg_split(seg, kind, s0, s1);
-        seg = ((slot >> (kSlotDepth - 1 - level)) & 1u) ? s1 : s0;
-    }
-
-    if (leaf_above) {
-        if (EMIT) lines[out] = make_double4(seg.p[0].x, seg.p[0].y, seg.p[kind - 1].x, seg.p[kind - 1].y);
-        else slot_counts[t] = 1;
+    SlotCtx c;
+    if (!slot_setup(jobs, n_jobs, t, thr, c, status)) {
+        if (!EMIT) slot_counts[t] = 0;
         return;
     }
-
-    // depth-first walk of the subtree: `stack` holds pending right halves
-    Seg stack[kMaxStack];
-    int top = 0;
-    bool have = true;
-    while (have) {
-        if (seg_has_nan(seg, kind)) { atomicExch(&status->nan_flag, 1u); break; }
-        if (seg_flatness(seg, kind) < thr) {
-            if (EMIT) {
-                if (out < out_end) lines[out] = make_double4(seg.p[0].x, seg.p[0].y, seg.p[kind - 1].x, seg.p[kind - 1].y);
-                out++;
-            } else {
-                count++;
-            }
-            if (top > 0) seg = stack[--top]; else have = false;
-        } else {
-            if (top >= kMaxStack) { atomicExch(&status->depth_flag, 1u); break; }
-            Seg s0, s1;
-            seg_split(seg, kind, s0, s1);
-            stack[top++] = s1;
-            seg = s0;
-        }
+    if (EMIT) {
+        slot_walk(c, thr, status, [&](double x0, double y0, double x1, double y1) {
+            if (out < out_end) lines[out] = make_double4(x0, y0, x1, y1);
+            out++;
+        });
+    } else {
+        slot_counts[t] = slot_walk(c, thr, status, [](double, double, double, double) {});
     }
-    if (!EMIT) slot_counts[t] = count;
+}
+
+// Unordered single-kernel form for the raster path (accumulation does not care about line order): every thread
+// counts its slot, the CTA reserves one contiguous range with a single atomic, every thread walks its slot again
+// and writes.  Same arithmetic, same lines, no slot arrays, no scan, one launch.
+__global__ void __launch_bounds__(128)
+flatten_fused_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t total_items, double thr, double4* __restrict__ lines,
+                     uint32_t* __restrict__ line_job, uint32_t lines_cap, Status* __restrict__ status) {
+    __shared__ uint32_t s_warp[4];
+    __shared__ uint32_t s_base;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total_slots = total_items * kSlotsPerItem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SlotCtx c;
+    const bool ok = t < total_slots && slot_setup(jobs, n_jobs, t, thr, c, status);
+    const uint32_t count = ok ? slot_walk(c, thr, status, [](double, double, double, double) {}) : 0u;
+    uint32_t incl = count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += nb;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const uint32_t v = s_warp[w];
+        if (w < warp) before += v;
+        total += v;
+    }
+    if (threadIdx.x == 0) s_base = total ? atomicAdd(&status->n_lines, total) : 0u;
+    __syncthreads();
+    if (count == 0) return;
+    const uint32_t base = s_base;
+    if (base + total > lines_cap || base + total < base) {  // capacity exceeded: flag, the host grows and re-runs
+        atomicExch(&status->lines_overflow, 1u);
+        return;
+    }
+    uint32_t out = base + before + incl - count;
+    const uint32_t j = c.job;
+    slot_walk(c, thr, status, [&](double x0, double y0, double x1, double y1) {
+        lines[out] = make_double4(x0, y0, x1, y1);
+        if (line_job) line_job[out] = j;
+        out++;
+    });
 }
 
 }  // namespace
@@ -223,6 +290,13 @@ void launch_flatten_emit(const JobDev* jobs, uint32_t n_jobs, uint32_t total_ite
     uint32_t n = total_items * kSlotsPerItem;
     if (n == 0) return;
     flatten_kernel<true><<<(n + 127) / 128, 128, 0, s>>>(jobs, n_jobs, total_items, thr, nullptr, slot_offs, lines, lines_cap, status);
+}
+
+void launch_flatten_fused(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, double4* lines, uint32_t* line_job,
+                          uint32_t lines_cap, Status* status, cudaStream_t s) {
+    uint32_t n = total_items * kSlotsPerItem;
+    if (n == 0) return;
+    flatten_fused_kernel<<<(n + 127) / 128, 128, 0, s>>>(jobs, n_jobs, total_items, thr, lines, line_job, lines_cap, status);
 }
 
 }  // namespace rgpu

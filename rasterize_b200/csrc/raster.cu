@@ -26,8 +26,6 @@ constexpr double kEps = 2.220446049250313e-16;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 
-__device__ __forceinline__ int to_fixed(double v) { return __double2int_rn(v * kFixScale); }
-
 // ---- colour maths (f32, never contracted: the reference uses plain SSE mul/add) -------------------------
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
@@ -142,94 +140,106 @@ __device__ float4 paint_at(const PaintDev& P, int x, int y) {
 }
 
 // ---- coverage from the fixed-point winding ---------------------------------------------------------------
+// NonZero: min(|w|, 1) (the reference's `value < 1e-6 -> 0` only matters to mask_iter's pixel dropping, which
+// the COVERAGE / FILL paths apply themselves; below 1e-6 the two differ by < 1e-6).  EvenOdd is exact in integers.
 __device__ __forceinline__ float coverage_from_fixed(int acc, int rule) {
     constexpr float kInv = 1.0f / 16777216.0f;
     if (rule == 1) {
-        // abs(((w + 1) rem_euclid 2) - 1), exact in integers
+        // abs(((w + 1) rem_euclid 2) - 1)
         int t = (acc + kFixOne) & (2 * kFixOne - 1);
-        int v = t - kFixOne;
-        v = v < 0 ? -v : v;
-        return (float)v * kInv;
+        return fabsf((float)(t - kFixOne)) * kInv;
     }
-    unsigned a = (unsigned)(acc < 0 ? -acc : acc);
-    if (a >= (unsigned)kFixOne) return 1.0f;
-    if (a < 17u) return 0.0f;  // value < 1e-6  <=>  a < 16.78
-    return (float)a * kInv;
+    return fminf(fabsf((float)acc) * kInv, 1.0f);
 }
 
 // ---- accumulation of one clipped piece over the rows of a band --------------------------------------------
 // (ax,ay)-(bx,by): piece after the reference's right-edge / x<0 handling.  Rows [row0,row1) of the canvas,
 // columns [cx0, cx0+ncols) of it are this tile; `wc` is the reference's `width` (= img.width - 1).
+__device__ __forceinline__ int to_fixed_f(float v) { return __float2int_rn(v * 16777216.0f); }
+
 __device__ void accumulate_piece(double ax, double ay, double bx, double by, int row0, int row1, int cx0, int ncols, double wc,
                                  int* __restrict__ cells, int pitch, int* __restrict__ carry, int* __restrict__ touched) {
     if (fabs(ay - by) < kEps) return;  // src/rasterize.rs:400-403
-    double dir = 1.0;
+    const int tile_end = cx0 + ncols;
+    // x-extent of the piece decides how much work this tile has to do for it
+    const double xmin = fmin(ax, bx), xmax = fmax(ax, bx);
+    if (xmin >= (double)tile_end) return;  // entirely right of the tile: contributes nothing here
+    float dirf = 1.0f;
     if (!(ay < by)) {  // src/rasterize.rs:405-409
         double t;
         t = ax; ax = bx; bx = t;
         t = ay; ay = by; by = t;
-        dir = -1.0;
+        dirf = -1.0f;
     }
-    double dxdy = (bx - ax) / (by - ay);
     // rows of the reference loop (src/rasterize.rs:414, 421) intersected with the band
-    double ys = floor(fmax(ay, 0.0));
-    double ye = ceil(fmax(by, 0.0));
-    int rb = ys >= (double)row1 ? row1 : max(row0, (int)ys);
-    int re = ye >= (double)row1 ? row1 : (int)ye;
-    int wci = (int)wc;
-    int tile_end = cx0 + ncols;
+    const double ys = floor(fmax(ay, 0.0));
+    const double ye = ceil(fmax(by, 0.0));
+    const int rb = ys >= (double)row1 ? row1 : max(row0, (int)ys);
+    const int re = ye >= (double)row1 ? row1 : (int)ye;
+    if (rb >= re) return;
+    if (xmax < (double)cx0 - 1.0) {
+        // entirely left of the tile (with a pixel of slack for the span's last column): only the cover d = dir*dy
+        // of every row reaches this tile, through the carry
+        for (int y = rb; y < re; y++) {
+            double dy = fmin((double)(y + 1), by) - fmax((double)y, ay);
+            atomicAdd(&carry[y - row0], to_fixed_f(dirf * (float)dy));
+        }
+        return;
+    }
+    const double dxdy = (bx - ax) / (by - ay);
+    const int wci = (int)wc;
     for (int y = rb; y < re; y++) {
-        double yt = fmax((double)y, ay);
-        double yb = fmin((double)(y + 1), by);
-        double dy = yb - yt;
-        double d = dir * dy;
-        double x = ax + (yt - ay) * dxdy;  // the reference accumulates x row by row; this differs by rounding only
-        double xn = x + dxdy * dy;
-        double x0 = fmin(x, xn), x1 = fmax(x, xn);
-        double x0_floor = fmax(floor(x0), 0.0);
-        double x1_ceil = fmin(ceil(x1), wc);
-        int x0i = min(max((int)x0_floor, 0), wci);
-        int x1i = min(max((int)x1_ceil, 0), wci);
-        if (x0i >= tile_end) continue;  // entirely right of this tile
-        int r = y - row0;
-        int fd = to_fixed(d);
-        bool narrow = x1i <= x0i + 1;
-        int last = narrow ? x0i + 1 : x1i;  // last column that receives a delta
-        if (last < cx0) {                   // entirely left: only its cover reaches this tile
+        const double yt = fmax((double)y, ay);
+        const double dy = fmin((double)(y + 1), by) - yt;
+        const double x = ax + (yt - ay) * dxdy;  // the reference accumulates x row by row; this differs by rounding only
+        const double xn = x + dxdy * dy;
+        const double x0 = fmin(x, xn), x1 = fmax(x, xn);
+        const double x0_floor = fmax(floor(x0), 0.0);
+        const double x1_ceil = fmin(ceil(x1), wc);
+        const int x0i = min(max((int)x0_floor, 0), wci);
+        const int x1i = min(max((int)x1_ceil, 0), wci);
+        if (x0i >= tile_end) continue;  // this row's span is right of the tile
+        const int r = y - row0;
+        const float d = dirf * (float)dy;
+        const int fd = to_fixed_f(d);
+        const bool narrow = x1i <= x0i + 1;
+        const int last = narrow ? x0i + 1 : x1i;  // last column that receives a delta
+        if (last < cx0) {                         // this row's span is left of the tile: only its cover arrives
             atomicAdd(&carry[r], fd);
             continue;
         }
-        double c0, s = 0.0, a1 = 0.0, am = 0.0;
-        int n = x1i - x0i;
+        // Positions stay f64 (f32 ulp at x ~ 4096 would already exceed the 1e-4 budget); the fractional parts are
+        // in [0,1] and the area polynomials are evaluated in f32 (error ~1e-7 of a pixel).
+        float c0, sf = 0.f, a1 = 0.f, am = 0.f;
+        const int n = x1i - x0i;
         if (narrow) {
-            double xmf = 0.5 * (x + xn) - x0_floor;  // src/rasterize.rs:439
-            c0 = 1.0 - xmf;
+            c0 = 1.0f - (float)(0.5 * (x + xn) - x0_floor);  // 1 - xmf, src/rasterize.rs:439
         } else {
-            s = 1.0 / (x1 - x0);  // src/rasterize.rs:446-450
-            double x0f = x0 - x0_floor;
-            double x1f = x1 - x1_ceil + 1.0;
-            c0 = 0.5 * s * (1.0 - x0f) * (1.0 - x0f);
-            am = 0.5 * s * x1f * x1f;
-            a1 = s * (1.5 - x0f);
+            sf = 1.0f / (float)(x1 - x0);  // src/rasterize.rs:446-450
+            const float x0f = (float)(x0 - x0_floor);
+            const float x1f = (float)(x1 - x1_ceil + 1.0);
+            c0 = 0.5f * sf * (1.0f - x0f) * (1.0f - x0f);
+            am = 0.5f * sf * x1f * x1f;
+            a1 = sf * (1.5f - x0f);
         }
         // coverage (as a fraction of d) of pixel x0i + j == running sum of the reference's deltas
-        auto cov = [&](int j) -> double {
-            if (j <= 0) return j == 0 ? c0 : 0.0;
-            if (narrow || j >= n) return 1.0;
-            if (j == n - 1) return 1.0 - am;
-            return a1 + (double)(j - 1) * s;
+        auto cov = [&](int j) -> float {
+            if (j <= 0) return j == 0 ? c0 : 0.0f;
+            if (narrow || j >= n) return 1.0f;
+            if (j == n - 1) return 1.0f - am;
+            return a1 + (float)(j - 1) * sf;
         };
-        int kb = max(x0i, cx0);
-        int ke = min(last, tile_end - 1);
+        const int kb = max(x0i, cx0);
+        const int ke = min(last, tile_end - 1);
         int prev = 0;
         if (kb > x0i) {  // the part of the span left of the tile collapses into the carry
-            prev = to_fixed(d * cov(kb - 1 - x0i));
+            prev = to_fixed_f(d * cov(kb - 1 - x0i));
             atomicAdd(&carry[r], prev);
         }
         int* rowp = cells + r * pitch - cx0;
         for (int k = kb; k <= ke; k++) {
-            int cur = (k == last) ? fd : to_fixed(d * cov(k - x0i));
-            int diff = cur - prev;
+            const int cur = (k == last) ? fd : to_fixed_f(d * cov(k - x0i));
+            const int diff = cur - prev;
             if (diff != 0) atomicAdd(&rowp[k], diff);
             prev = cur;
         }
@@ -334,67 +344,89 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     const int warp = tid >> 5, lane = tid & 31;
     const int wout = job.width_out;
     const bool any = touched != 0;
+    const int nseg = min(CW / 128, (wout - cx0 + 127) >> 7);
     for (int r = warp; r < row1 - row0; r += kWarps) {
         int acc = carry[r];
         int* rowc = cells + r * kPitch;
         const int y = row0 + r;
-        for (int seg = 0; seg < CW / 128; seg++) {
-            int xs = cx0 + seg * 128;
-            if (xs >= wout) break;
-            int col = seg * 128 + lane * 4;
-            int w0, w1, w2, w3;
-            if (any) {
-                int4 v = *reinterpret_cast<const int4*>(rowc + col);
-                int p0 = v.x, p1 = p0 + v.y, p2 = p1 + v.z, p3 = p2 + v.w;
-                int incl = p3;
+        if (mode != kModeFill) {
+            float* out = reinterpret_cast<float*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride + cx0;
+            const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+            const int wrem = wout - cx0;  // columns of this row that exist from the tile's first column on
+            for (int seg = 0; seg < nseg; seg++) {
+                const int col = seg * 128 + lane * 4;
+                int w0, w1, w2, w3;
+                if (any) {
+                    const int4 v = *reinterpret_cast<const int4*>(rowc + col);
+                    const int p0 = v.x, p1 = p0 + v.y, p2 = p1 + v.z, p3 = p2 + v.w;
+                    int incl = p3;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    int nb = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += nb;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += nb;
+                    }
+                    const int base = acc + incl - p3;
+                    w0 = base + p0; w1 = base + p1; w2 = base + p2; w3 = base + p3;
+                    acc += __shfl_sync(0xffffffffu, incl, 31);
+                } else {
+                    w0 = w1 = w2 = w3 = acc;
                 }
-                int base = acc + incl - p3;
-                w0 = base + p0; w1 = base + p1; w2 = base + p2; w3 = base + p3;
-                acc += __shfl_sync(0xffffffffu, incl, 31);
-            } else {
-                w0 = w1 = w2 = w3 = acc;
-            }
-            float4 cv = make_float4(coverage_from_fixed(w0, rule), coverage_from_fixed(w1, rule), coverage_from_fixed(w2, rule),
-                                    coverage_from_fixed(w3, rule));
-            int x = xs + lane * 4;
-            if (mode != kModeFill) {
-                float* out = reinterpret_cast<float*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride;
+                float4 cv = make_float4(coverage_from_fixed(w0, rule), coverage_from_fixed(w1, rule), coverage_from_fixed(w2, rule),
+                                        coverage_from_fixed(w3, rule));
                 if (mode == kModeCoverage) {  // mask_iter drops abs(alpha) < 1e-6 (src/rasterize.rs:348)
                     if (cv.x < 1e-6f) cv.x = 0.f;
                     if (cv.y < 1e-6f) cv.y = 0.f;
                     if (cv.z < 1e-6f) cv.z = 0.f;
                     if (cv.w < 1e-6f) cv.w = 0.f;
                 }
-                if (x + 3 < wout && ((reinterpret_cast<uintptr_t>(out + x) & 15) == 0)) {
-                    *reinterpret_cast<float4*>(out + x) = cv;
+                if (vec_ok && col + 3 < wrem) {
+                    __stcs(reinterpret_cast<float4*>(out + col), cv);  // streaming 128-bit store, written once
                 } else {
-                    if (x < wout) out[x] = cv.x;
-                    if (x + 1 < wout) out[x + 1] = cv.y;
-                    if (x + 2 < wout) out[x + 2] = cv.z;
-                    if (x + 3 < wout) out[x + 3] = cv.w;
+                    if (col < wrem) out[col] = cv.x;
+                    if (col + 1 < wrem) out[col + 1] = cv.y;
+                    if (col + 2 < wrem) out[col + 2] = cv.z;
+                    if (col + 3 < wrem) out[col + 3] = cv.w;
                 }
-            } else {
+            }
+        } else {
+            float4* out = reinterpret_cast<float4*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride;
+            for (int seg = 0; seg < nseg; seg++) {
+                const int xs = cx0 + seg * 128;
+                const int col = seg * 128 + lane * 4;
+                int w0, w1, w2, w3;
+                if (any) {
+                    const int4 v = *reinterpret_cast<const int4*>(rowc + col);
+                    const int p0 = v.x, p1 = p0 + v.y, p2 = p1 + v.z, p3 = p2 + v.w;
+                    int incl = p3;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += nb;
+                    }
+                    const int base = acc + incl - p3;
+                    w0 = base + p0; w1 = base + p1; w2 = base + p2; w3 = base + p3;
+                    acc += __shfl_sync(0xffffffffu, incl, 31);
+                } else {
+                    w0 = w1 = w2 = w3 = acc;
+                }
+                const float4 cv = make_float4(coverage_from_fixed(w0, rule), coverage_from_fixed(w1, rule),
+                                              coverage_from_fixed(w2, rule), coverage_from_fixed(w3, rule));
+                if (!__any_sync(0xffffffffu, fmaxf(fmaxf(cv.x, cv.y), fmaxf(cv.z, cv.w)) >= 1e-6f)) continue;  // nothing to paint
                 // stage coverage so that consecutive lanes composite consecutive pixels (coalesced 16 B accesses)
                 *reinterpret_cast<float4*>(rowc + col) = cv;
                 __syncwarp();
-                float4* out = reinterpret_cast<float4*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride;
                 const float* covs = reinterpret_cast<const float*>(rowc + seg * 128);
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    int px = xs + i * 32 + lane;
-                    float alpha = covs[i * 32 + lane];
+                    const int px = xs + i * 32 + lane;
+                    const float alpha = covs[i * 32 + lane];
                     if (px < wout && alpha >= 1e-6f) {
-                        float4 color = (job.paint_index >= 0) ? paint_at(s_paint, px, y)
-                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 color = (job.paint_index >= 0) ? paint_at(s_paint, px, y) : make_float4(0.f, 0.f, 0.f, 0.f);
                         // with_alpha: self * (alpha as f32), src/color.rs:347-349
                         color = make_float4(fmul(color.x, alpha), fmul(color.y, alpha), fmul(color.z, alpha), fmul(color.w, alpha));
                         // blend_over: other + self * (1 - other.alpha), src/color.rs:342-344
                         float4 dstc = out[px];
-                        float k = fsub(1.0f, color.w);
+                        const float k = fsub(1.0f, color.w);
                         dstc = make_float4(fadd(color.x, fmul(dstc.x, k)), fadd(color.y, fmul(dstc.y, k)), fadd(color.z, fmul(dstc.z, k)),
                                            fadd(color.w, fmul(dstc.w, k)));
                         out[px] = dstc;

@@ -77,11 +77,16 @@ void launch_flatten_emit(const JobDev* jobs, uint32_t n_jobs, uint32_t total_ite
                          double4* lines, uint32_t lines_cap, Status* status, cudaStream_t s);
 size_t scan_temp_bytes(uint32_t n);
 void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, void* temp, size_t temp_bytes, cudaStream_t s);
-void launch_bin_count(const JobDev* jobs, uint32_t n_jobs, const uint32_t* slot_offs, uint32_t total_slots, const double4* lines,
-                      uint32_t* band_counts, int band_rows, Status* status, cudaStream_t s);
-void launch_bin_fill(const JobDev* jobs, uint32_t n_jobs, const uint32_t* slot_offs, uint32_t total_slots, const double4* lines,
-                     const uint32_t* band_offs, uint32_t total_bands, uint32_t* band_cursor, uint32_t* refs, uint32_t refs_cap,
-                     int band_rows, Status* status, cudaStream_t s);
+// Unordered single-kernel flatten for the raster path: count + CTA-level reservation + emit (see flatten.cu).
+// Writes status->n_lines (must be zero on entry) and, when line_job != nullptr, the job of every line.
+void launch_flatten_fused(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, double4* lines, uint32_t* line_job,
+                          uint32_t lines_cap, Status* status, cudaStream_t s);
+// slot_offs == nullptr: lines came from launch_flatten_fused (count in status->n_lines, jobs in line_job)
+void launch_bin_count(const JobDev* jobs, uint32_t n_jobs, const uint32_t* slot_offs, uint32_t total_slots, const uint32_t* line_job,
+                      const double4* lines, uint32_t* band_counts, int band_rows, Status* status, cudaStream_t s);
+void launch_bin_fill(const JobDev* jobs, uint32_t n_jobs, const uint32_t* slot_offs, uint32_t total_slots, const uint32_t* line_job,
+                     const double4* lines, const uint32_t* band_offs, uint32_t total_bands, uint32_t* band_cursor, uint32_t* refs,
+                     uint32_t refs_cap, int band_rows, Status* status, cudaStream_t s);
 // tile geometry of the raster kernel variants
 struct TileShape { int cw, th; };
 TileShape raster_tile_shape(int variant);
