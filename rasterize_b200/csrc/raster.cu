@@ -152,147 +152,160 @@ __device__ __forceinline__ float coverage_from_fixed(int acc, int rule) {
     return fminf(fabsf((float)acc) * kInv, 1.0f);
 }
 
-// ---- accumulation of one clipped piece over the rows of a band --------------------------------------------
-// (ax,ay)-(bx,by): piece after the reference's right-edge / x<0 handling.  Rows [row0,row1) of the canvas,
-// columns [cx0, cx0+ncols) of it are this tile; `wc` is the reference's `width` (= img.width - 1).
+// ---- shared-memory cell layout --------------------------------------------------------------------------
+// Cell (row r, tile column x) lives at r*pitch + swz(x), swz(x) = x + 4*(x/32): every group of 32 columns is
+// followed by 4 padding ints.  In the scan phase lane l owns columns [32l, 32l+32) of a 1024-column row; with the
+// padding its 128-bit loads hit bank-quad (l + i) mod 8, so each 8-lane wavefront is conflict-free, and the
+// transposed read-back (lane l reads columns [128i + 4l, +4)) is conflict-free too.
+__device__ __forceinline__ int swz(int x) { return x + ((x >> 5) << 2); }
+
 __device__ __forceinline__ int to_fixed_f(float v) { return __float2int_rn(v * 16777216.0f); }
 
-__device__ void accumulate_piece(double ax, double ay, double bx, double by, int row0, int row1, int cx0, int ncols, double wc,
-                                 int* __restrict__ cells, int pitch, int* __restrict__ carry, int* __restrict__ touched) {
-    if (fabs(ay - by) < kEps) return;  // src/rasterize.rs:400-403
-    const int tile_end = cx0 + ncols;
-    // x-extent of the piece decides how much work this tile has to do for it
+struct TileGeom {
+    int row0, row1;   // canvas rows [row0, row1) of this band
+    int cx0;          // first canvas column of the tile
+    int tile_end;     // cx0 + number of reference columns in the tile (incl. the overflow column)
+    int pitch;
+    double wc;        // reference `width` (= img.width - 1)
+    int wci;
+};
+
+// One (piece, row) span: the body of the reference's row loop (src/rasterize.rs:421-469) for canvas row y.
+// (ax,ay) is the piece's upper end (ay < by), dirf = +-1.  Pixel coverages (running sums of the reference's
+// deltas) are rounded to Q7.24 and their differences added to the cells; whatever falls left of the tile
+// collapses into the row's carry.
+__device__ __forceinline__ void span_row(double ax, double ay, double by, double dxdy, float dirf, int y, const TileGeom& g,
+                                         int* __restrict__ cells, int* __restrict__ carry, int* __restrict__ row_touched) {
+    const double yt = fmax((double)y, ay);
+    const double dy = fmin((double)(y + 1), by) - yt;
+    const double x = ax + (yt - ay) * dxdy;  // the reference accumulates x row by row; this differs by rounding only
+    const double xn = x + dxdy * dy;
+    const double x0 = fmin(x, xn), x1 = fmax(x, xn);
+    const double x0_floor = fmax(floor(x0), 0.0);
+    const double x1_ceil = fmin(ceil(x1), g.wc);
+    const int x0i = min(max((int)x0_floor, 0), g.wci);
+    const int x1i = min(max((int)x1_ceil, 0), g.wci);
+    if (x0i >= g.tile_end) return;  // this row's span is right of the tile
+    const int r = y - g.row0;
+    const float d = dirf * (float)dy;
+    const int fd = to_fixed_f(d);
+    const bool narrow = x1i <= x0i + 1;
+    const int last = narrow ? x0i + 1 : x1i;  // last column that receives a delta
+    if (last < g.cx0) {                       // this row's span is left of the tile: only its cover arrives
+        atomicAdd(&carry[r], fd);
+        return;
+    }
+    // Positions stay f64 (f32 ulp at x ~ 4096 would already exceed the 1e-4 budget); the fractional parts are in
+    // [0,1] and the area polynomials are evaluated in f32 (error ~1e-7 of a pixel).
+    float c0, sf = 0.f, a1 = 0.f, am = 0.f;
+    const int n = x1i - x0i;
+    if (narrow) {
+        c0 = 1.0f - (float)(0.5 * (x + xn) - x0_floor);  // 1 - xmf, src/rasterize.rs:439
+    } else {
+        sf = 1.0f / (float)(x1 - x0);  // src/rasterize.rs:446-450
+        const float x0f = (float)(x0 - x0_floor);
+        const float x1f = (float)(x1 - x1_ceil + 1.0);
+        c0 = 0.5f * sf * (1.0f - x0f) * (1.0f - x0f);
+        am = 0.5f * sf * x1f * x1f;
+        a1 = sf * (1.5f - x0f);
+    }
+    // coverage (as a fraction of d) of pixel x0i + j == running sum of the reference's deltas
+    auto cov = [&](int j) -> float {
+        if (j <= 0) return j == 0 ? c0 : 0.0f;
+        if (narrow || j >= n) return 1.0f;
+        if (j == n - 1) return 1.0f - am;
+        return a1 + (float)(j - 1) * sf;
+    };
+    const int kb = max(x0i, g.cx0);
+    const int ke = min(last, g.tile_end - 1);
+    int prev = 0;
+    if (kb > x0i) {  // the part of the span left of the tile collapses into the carry
+        prev = to_fixed_f(d * cov(kb - 1 - x0i));
+        atomicAdd(&carry[r], prev);
+    }
+    int* rowp = cells + r * g.pitch;
+    for (int k = kb; k <= ke; k++) {
+        const int cur = (k == last) ? fd : to_fixed_f(d * cov(k - x0i));
+        const int diff = cur - prev;
+        if (diff != 0) atomicAdd(&rowp[swz(k - g.cx0)], diff);
+        prev = cur;
+    }
+    row_touched[r] = 1;
+}
+
+// Oriented piece ready for span_row, or nothing.  Returns the band rows [rb, re) it touches.
+struct Piece {
+    double ax, ay, by, dxdy;
+    float dirf;
+    int rb, re;
+    int cls;  // 0 = nothing to do, 1 = entirely left of the tile (cover only), 2 = needs span_row
+};
+
+__device__ __forceinline__ Piece classify_piece(double ax, double ay, double bx, double by, const TileGeom& g) {
+    Piece p;
+    p.cls = 0;
+    p.rb = p.re = 0;
+    p.dirf = 1.0f;
+    p.dxdy = 0.0;
+    if (fabs(ay - by) < kEps) { p.ax = ax; p.ay = ay; p.by = by; return p; }  // src/rasterize.rs:400-403
     const double xmin = fmin(ax, bx), xmax = fmax(ax, bx);
-    if (xmin >= (double)tile_end) return;  // entirely right of the tile: contributes nothing here
-    float dirf = 1.0f;
     if (!(ay < by)) {  // src/rasterize.rs:405-409
         double t;
         t = ax; ax = bx; bx = t;
         t = ay; ay = by; by = t;
-        dirf = -1.0f;
+        p.dirf = -1.0f;
     }
+    p.ax = ax; p.ay = ay; p.by = by;
+    if (xmin >= (double)g.tile_end) return p;  // entirely right of the tile: contributes nothing here
     // rows of the reference loop (src/rasterize.rs:414, 421) intersected with the band
     const double ys = floor(fmax(ay, 0.0));
     const double ye = ceil(fmax(by, 0.0));
-    const int rb = ys >= (double)row1 ? row1 : max(row0, (int)ys);
-    const int re = ye >= (double)row1 ? row1 : (int)ye;
-    if (rb >= re) return;
-    if (xmax < (double)cx0 - 1.0) {
-        // entirely left of the tile (with a pixel of slack for the span's last column): only the cover d = dir*dy
-        // of every row reaches this tile, through the carry
-        for (int y = rb; y < re; y++) {
-            double dy = fmin((double)(y + 1), by) - fmax((double)y, ay);
-            atomicAdd(&carry[y - row0], to_fixed_f(dirf * (float)dy));
-        }
-        return;
-    }
-    const double dxdy = (bx - ax) / (by - ay);
-    const int wci = (int)wc;
-    for (int y = rb; y < re; y++) {
-        const double yt = fmax((double)y, ay);
-        const double dy = fmin((double)(y + 1), by) - yt;
-        const double x = ax + (yt - ay) * dxdy;  // the reference accumulates x row by row; this differs by rounding only
-        const double xn = x + dxdy * dy;
-        const double x0 = fmin(x, xn), x1 = fmax(x, xn);
-        const double x0_floor = fmax(floor(x0), 0.0);
-        const double x1_ceil = fmin(ceil(x1), wc);
-        const int x0i = min(max((int)x0_floor, 0), wci);
-        const int x1i = min(max((int)x1_ceil, 0), wci);
-        if (x0i >= tile_end) continue;  // this row's span is right of the tile
-        const int r = y - row0;
-        const float d = dirf * (float)dy;
-        const int fd = to_fixed_f(d);
-        const bool narrow = x1i <= x0i + 1;
-        const int last = narrow ? x0i + 1 : x1i;  // last column that receives a delta
-        if (last < cx0) {                         // this row's span is left of the tile: only its cover arrives
-            atomicAdd(&carry[r], fd);
-            continue;
-        }
-        // Positions stay f64 (f32 ulp at x ~ 4096 would already exceed the 1e-4 budget); the fractional parts are
-        // in [0,1] and the area polynomials are evaluated in f32 (error ~1e-7 of a pixel).
-        float c0, sf = 0.f, a1 = 0.f, am = 0.f;
-        const int n = x1i - x0i;
-        if (narrow) {
-            c0 = 1.0f - (float)(0.5 * (x + xn) - x0_floor);  // 1 - xmf, src/rasterize.rs:439
-        } else {
-            sf = 1.0f / (float)(x1 - x0);  // src/rasterize.rs:446-450
-            const float x0f = (float)(x0 - x0_floor);
-            const float x1f = (float)(x1 - x1_ceil + 1.0);
-            c0 = 0.5f * sf * (1.0f - x0f) * (1.0f - x0f);
-            am = 0.5f * sf * x1f * x1f;
-            a1 = sf * (1.5f - x0f);
-        }
-        // coverage (as a fraction of d) of pixel x0i + j == running sum of the reference's deltas
-        auto cov = [&](int j) -> float {
-            if (j <= 0) return j == 0 ? c0 : 0.0f;
-            if (narrow || j >= n) return 1.0f;
-            if (j == n - 1) return 1.0f - am;
-            return a1 + (float)(j - 1) * sf;
-        };
-        const int kb = max(x0i, cx0);
-        const int ke = min(last, tile_end - 1);
-        int prev = 0;
-        if (kb > x0i) {  // the part of the span left of the tile collapses into the carry
-            prev = to_fixed_f(d * cov(kb - 1 - x0i));
-            atomicAdd(&carry[r], prev);
-        }
-        int* rowp = cells + r * pitch - cx0;
-        for (int k = kb; k <= ke; k++) {
-            const int cur = (k == last) ? fd : to_fixed_f(d * cov(k - x0i));
-            const int diff = cur - prev;
-            if (diff != 0) atomicAdd(&rowp[k], diff);
-            prev = cur;
-        }
-        *touched = 1;
+    p.rb = ys >= (double)g.row1 ? g.row1 : max(g.row0, (int)ys);
+    p.re = ye >= (double)g.row1 ? g.row1 : (int)ye;
+    if (p.rb >= p.re) return p;
+    if (xmax < (double)g.cx0 - 1.0) { p.cls = 1; return p; }  // a pixel of slack for the span's last column
+    p.dxdy = (bx - ax) / (by - ay);
+    p.cls = 2;
+    return p;
+}
+
+// cover-only rows of a piece that lies entirely left of the tile
+__device__ __forceinline__ void left_cover(const Piece& p, const TileGeom& g, int* __restrict__ carry) {
+    for (int y = p.rb; y < p.re; y++) {
+        const double dy = fmin((double)(y + 1), p.by) - fmax((double)y, p.ay);
+        atomicAdd(&carry[y - g.row0], to_fixed_f(p.dirf * (float)dy));
     }
 }
 
-// One flattened line -> the reference's clipping -> up to two pieces
-__device__ void accumulate_line(const double4 l, int row0, int row1, int cx0, int ncols, double wc, int* cells, int pitch, int* carry,
-                                int* touched) {
-    double p0x = l.x, p0y = l.y, p1x = l.z, p1y = l.w;
-    // src/rasterize.rs:370-387: lines crossing x == width
-    if (p0x > wc || p1x > wc) {
-        if (p0x > wc && p1x > wc) {
-            p0x = wc - 0.001;
-            p1x = wc - 0.001;
-        } else {
-            double t = (p0x - wc) / (p0x - p1x);
-            double my = (1.0 - t) * p0y + t * p1y;
-            if (p0x < wc) { p1x = wc; p1y = my; } else { p0x = wc; p0y = my; }
-        }
-    }
-    // src/rasterize.rs:923-937 split_at_zero_x
-    if (p0x >= 0.0 && p1x >= 0.0) {
-        accumulate_piece(p0x, p0y, p1x, p1y, row0, row1, cx0, ncols, wc, cells, pitch, carry, touched);
-    } else if (p0x <= 0.0 && p1x <= 0.0) {
-        accumulate_piece(0.0, p0y, 0.0, p1y, row0, row1, cx0, ncols, wc, cells, pitch, carry, touched);
-    } else {
-        double t = p0x / (p0x - p1x);
-        double mx = (1.0 - t) * p0x + t * p1x;
-        double my = (1.0 - t) * p0y + t * p1y;
-        if (p0x < 0.0) {
-            accumulate_piece(mx, my, p1x, p1y, row0, row1, cx0, ncols, wc, cells, pitch, carry, touched);
-            // rest = ((0, p0.y), mid) goes through the same function again in the reference
-            if (mx <= 0.0) accumulate_piece(0.0, p0y, 0.0, my, row0, row1, cx0, ncols, wc, cells, pitch, carry, touched);
-            else accumulate_piece(0.0, p0y, mx, my, row0, row1, cx0, ncols, wc, cells, pitch, carry, touched);
-        } else {
-            accumulate_piece(p0x, p0y, mx, my, row0, row1, cx0, ncols, wc, cells, pitch, carry, touched);
-            if (mx <= 0.0) accumulate_piece(0.0, my, 0.0, p1y, row0, row1, cx0, ncols, wc, cells, pitch, carry, touched);
-            else accumulate_piece(mx, my, 0.0, p1y, row0, row1, cx0, ncols, wc, cells, pitch, carry, touched);
-        }
-    }
+__device__ void piece_serial(double ax, double ay, double bx, double by, const TileGeom& g, int* cells, int* carry, int* row_touched) {
+    const Piece p = classify_piece(ax, ay, bx, by, g);
+    if (p.cls == 1) left_cover(p, g, carry);
+    else if (p.cls == 2)
+        for (int y = p.rb; y < p.re; y++) span_row(p.ax, p.ay, p.by, p.dxdy, p.dirf, y, g, cells, carry, row_touched);
 }
+
+constexpr int kMaxSpans = 4096;
 
 template <int CW, int TH>
 __global__ void __launch_bounds__(kThreads)
 raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
               const PaintDev* __restrict__ paints, const double4* __restrict__ lines, const uint32_t* __restrict__ band_offs,
               const uint32_t* __restrict__ refs, const Status* __restrict__ status) {
-    constexpr int kPitch = CW + 4;
-    __shared__ __align__(16) int cells[TH * kPitch];
+    constexpr int kPitch = CW + CW / 8;  // swizzled row pitch
+    constexpr int kRowBits = (TH <= 8) ? 3 : 6;
+    static_assert(TH <= 64 && CW % 128 == 0, "tile shape");
+    // dynamic shared memory (> 48 KB static limit): cells | piece constants | span list
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int* cells = reinterpret_cast<int*>(smem_raw);
+    double* p_ax = reinterpret_cast<double*>(smem_raw + sizeof(int) * TH * kPitch);
+    double* p_ay = p_ax + kThreads;
+    double* p_by = p_ay + kThreads;
+    double* p_dxdy = p_by + kThreads;
+    float* p_dir = reinterpret_cast<float*>(p_dxdy + kThreads);
+    unsigned short* spans = reinterpret_cast<unsigned short*>(p_dir + kThreads);
     __shared__ int carry[TH];
-    __shared__ int touched;
+    __shared__ int row_touched[TH];
+    __shared__ int n_spans;
     __shared__ uint32_t s_job;
     __shared__ PaintDev s_paint;
 
@@ -302,9 +315,9 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     uint32_t tile = tile_first + blockIdx.x;
     if (tid == 0) {
         s_job = job_first + find_job(n_jobs, tile, [&](uint32_t k) { return jobs[job_first + k].tile_begin; });
-        touched = 0;
+        n_spans = 0;
     }
-    if (tid < TH) carry[tid] = 0;
+    if (tid < TH) { carry[tid] = 0; row_touched[tid] = 0; }
     {
         int4 z = make_int4(0, 0, 0, 0);
         int4* c4 = reinterpret_cast<int4*>(cells);
@@ -313,13 +326,18 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     __syncthreads();
     const JobDev& job = jobs[s_job];
     uint32_t lt = tile - job.tile_begin;
-    int band = (int)(lt / job.n_chunks);
-    int chunk = (int)(lt - (uint32_t)band * job.n_chunks);
-    int row0 = band * TH;
-    int row1 = min(row0 + TH, job.height);
-    int cx0 = chunk * CW;
-    double wc = job.clamp_w;
-    int ncols = min(CW, (int)wc + 1 - cx0);  // columns that exist in the reference image (incl. the overflow column)
+    const int band = (int)(lt / job.n_chunks);
+    const int chunk = (int)(lt - (uint32_t)band * job.n_chunks);
+    TileGeom g;
+    g.row0 = band * TH;
+    g.row1 = min(g.row0 + TH, job.height);
+    g.cx0 = chunk * CW;
+    g.wc = job.clamp_w;
+    g.wci = (int)g.wc;
+    g.tile_end = g.cx0 + min(CW, g.wci + 1 - g.cx0);  // columns that exist in the reference image (incl. overflow column)
+    g.pitch = kPitch;
+    const int row0 = g.row0, row1 = g.row1, cx0 = g.cx0;
+    const double wc = g.wc;
     const int mode = job.mode;
     const int rule = job.rule;
 
@@ -329,99 +347,172 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
         for (int i = tid; i < (int)(sizeof(PaintDev) / 4); i += kThreads) dst[i] = src[i];
     }
 
-    // ---- phase 1: accumulate the band's lines ----------------------------------------------------------
-    uint32_t gb = job.band_begin + (uint32_t)band;
-    uint32_t rbeg = band_offs[gb], rend = band_offs[gb + 1];
-    if (ncols > 0) {
-        for (uint32_t r = rbeg + tid; r < rend; r += kThreads) {
-            double4 l = lines[refs[r]];
-            accumulate_line(l, row0, row1, cx0, ncols, wc, cells, kPitch, carry, &touched);
+    // ---- phase 1: accumulate the band's lines, kThreads references per round ------------------------------
+    const uint32_t gb = job.band_begin + (uint32_t)band;
+    const uint32_t rbeg = band_offs[gb], rend = band_offs[gb + 1];
+    for (uint32_t r0 = rbeg; r0 < rend; r0 += kThreads) {
+        // 1a: one reference per thread: the reference's clipping, orientation, row range; spans are appended to
+        //     a shared list so that 1b runs one lane per (piece,row) span with no row-loop divergence
+        const uint32_t r = r0 + tid;
+        if (r < rend) {
+            const double4 l = lines[refs[r]];
+            double p0x = l.x, p0y = l.y, p1x = l.z, p1y = l.w;
+            // src/rasterize.rs:370-387: lines crossing x == width
+            if (p0x > wc || p1x > wc) {
+                if (p0x > wc && p1x > wc) {
+                    p0x = wc - 0.001;
+                    p1x = wc - 0.001;
+                } else {
+                    const double t = (p0x - wc) / (p0x - p1x);
+                    const double my = (1.0 - t) * p0y + t * p1y;
+                    if (p0x < wc) { p1x = wc; p1y = my; } else { p0x = wc; p0y = my; }
+                }
+            }
+            // src/rasterize.rs:923-937 split_at_zero_x
+            if (p0x < 0.0 || p1x < 0.0) {
+                if (p0x <= 0.0 && p1x <= 0.0) {
+                    p0x = 0.0;
+                    p1x = 0.0;
+                } else {
+                    const double t = p0x / (p0x - p1x);
+                    const double mx = (1.0 - t) * p0x + t * p1x;
+                    const double my = (1.0 - t) * p0y + t * p1y;
+                    // the outside part, folded onto x = 0, goes through the same function again in the reference;
+                    // rare (only lines crossing the left edge): done serially by this thread
+                    if (p0x < 0.0) {
+                        if (mx <= 0.0) piece_serial(0.0, p0y, 0.0, my, g, cells, carry, row_touched);
+                        else piece_serial(0.0, p0y, mx, my, g, cells, carry, row_touched);
+                        p0x = mx; p0y = my;
+                    } else {
+                        if (mx <= 0.0) piece_serial(0.0, my, 0.0, p1y, g, cells, carry, row_touched);
+                        else piece_serial(mx, my, 0.0, p1y, g, cells, carry, row_touched);
+                        p1x = mx; p1y = my;
+                    }
+                }
+            }
+            const Piece p = classify_piece(p0x, p0y, p1x, p1y, g);
+            if (p.cls == 1) {
+                left_cover(p, g, carry);
+            } else if (p.cls == 2) {
+                const int n = p.re - p.rb;
+                const int base = atomicAdd(&n_spans, n);
+                if (base + n <= kMaxSpans) {
+                    p_ax[tid] = p.ax; p_ay[tid] = p.ay; p_by[tid] = p.by; p_dxdy[tid] = p.dxdy; p_dir[tid] = p.dirf;
+                    for (int k = 0; k < n; k++) spans[base + k] = (unsigned short)((tid << kRowBits) | (p.rb + k - row0));
+                } else {  // span list full (only possible for TH = 64): do the rows here
+                    for (int y = p.rb; y < p.re; y++) span_row(p.ax, p.ay, p.by, p.dxdy, p.dirf, y, g, cells, carry, row_touched);
+                }
+            }
         }
+        __syncthreads();
+        // 1b: one lane per span
+        const int ns = min(n_spans, kMaxSpans);
+        for (int i = tid; i < ns; i += kThreads) {
+            const int e = spans[i];
+            const int slot = e >> kRowBits;
+            const int y = row0 + (e & ((1 << kRowBits) - 1));
+            span_row(p_ax[slot], p_ay[slot], p_by[slot], p_dxdy[slot], p_dir[slot], y, g, cells, carry, row_touched);
+        }
+        __syncthreads();
+        if (tid == 0) n_spans = 0;
+        // (the next round's 1a only appends after reading n_spans == 0: order it)
+        __syncthreads();
     }
-    __syncthreads();
+    if (rbeg == rend) __syncthreads();
 
     // ---- phase 2: per-row scan, fill rule, store / composite --------------------------------------------
+    // A warp takes a row; lane l owns 32 consecutive columns per 1024-column block: serial prefix in registers,
+    // ONE warp scan of the 32 lane totals per block, coverage written back to shared memory in place (as floats)
+    // and read back transposed so that global stores are full 512 B coalesced 128-bit accesses.
     const int warp = tid >> 5, lane = tid & 31;
     const int wout = job.width_out;
-    const bool any = touched != 0;
-    const int nseg = min(CW / 128, (wout - cx0 + 127) >> 7);
+    const int wrem = min(wout - cx0, CW);  // visible columns of this tile
     for (int r = warp; r < row1 - row0; r += kWarps) {
         int acc = carry[r];
         int* rowc = cells + r * kPitch;
         const int y = row0 + r;
-        if (mode != kModeFill) {
-            float* out = reinterpret_cast<float*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride + cx0;
-            const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-            const int wrem = wout - cx0;  // columns of this row that exist from the tile's first column on
-            for (int seg = 0; seg < nseg; seg++) {
-                const int col = seg * 128 + lane * 4;
-                int w0, w1, w2, w3;
-                if (any) {
-                    const int4 v = *reinterpret_cast<const int4*>(rowc + col);
-                    const int p0 = v.x, p1 = p0 + v.y, p2 = p1 + v.z, p3 = p2 + v.w;
-                    int incl = p3;
+        const bool touched = row_touched[r] != 0;
+        for (int blk = 0; blk * 1024 < wrem; blk++) {
+            int* bc = rowc + blk * (1024 + 128);  // swz(blk*1024)
+            if constexpr (CW >= 1024) {
+                if (touched) {
+                    int v[32];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int4 q = *reinterpret_cast<const int4*>(bc + lane * 36 + i * 4);
+                        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+                    }
+#pragma unroll
+                    for (int i = 1; i < 32; i++) v[i] += v[i - 1];
+                    int incl = v[31];
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const int nb = __shfl_up_sync(0xffffffffu, incl, o);
                         if (lane >= o) incl += nb;
                     }
-                    const int base = acc + incl - p3;
-                    w0 = base + p0; w1 = base + p1; w2 = base + p2; w3 = base + p3;
+                    const int base = acc + incl - v[31];
                     acc += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        float4 cv = make_float4(coverage_from_fixed(base + v[4 * i], rule), coverage_from_fixed(base + v[4 * i + 1], rule),
+                                                coverage_from_fixed(base + v[4 * i + 2], rule), coverage_from_fixed(base + v[4 * i + 3], rule));
+                        *reinterpret_cast<float4*>(bc + lane * 36 + i * 4) = cv;
+                    }
                 } else {
-                    w0 = w1 = w2 = w3 = acc;
+                    const float c = coverage_from_fixed(acc, rule);
+                    const float4 cv = make_float4(c, c, c, c);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) *reinterpret_cast<float4*>(bc + lane * 36 + i * 4) = cv;
                 }
-                float4 cv = make_float4(coverage_from_fixed(w0, rule), coverage_from_fixed(w1, rule), coverage_from_fixed(w2, rule),
-                                        coverage_from_fixed(w3, rule));
-                if (mode == kModeCoverage) {  // mask_iter drops abs(alpha) < 1e-6 (src/rasterize.rs:348)
-                    if (cv.x < 1e-6f) cv.x = 0.f;
-                    if (cv.y < 1e-6f) cv.y = 0.f;
-                    if (cv.z < 1e-6f) cv.z = 0.f;
-                    if (cv.w < 1e-6f) cv.w = 0.f;
+            } else {
+                // narrow tiles (CW = 128): 4 columns per lane, shuffle scan
+                const int col = lane * 4;
+                const int4 q = *reinterpret_cast<const int4*>(bc + swz(col));
+                const int p0 = q.x, p1 = p0 + q.y, p2 = p1 + q.z, p3 = p2 + q.w;
+                int incl = p3;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += nb;
                 }
-                if (vec_ok && col + 3 < wrem) {
-                    __stcs(reinterpret_cast<float4*>(out + col), cv);  // streaming 128-bit store, written once
-                } else {
-                    if (col < wrem) out[col] = cv.x;
-                    if (col + 1 < wrem) out[col + 1] = cv.y;
-                    if (col + 2 < wrem) out[col + 2] = cv.z;
-                    if (col + 3 < wrem) out[col + 3] = cv.w;
-                }
+                const int base = acc + incl - p3;
+                acc += __shfl_sync(0xffffffffu, incl, 31);
+                *reinterpret_cast<float4*>(bc + swz(col)) = make_float4(coverage_from_fixed(base + p0, rule), coverage_from_fixed(base + p1, rule),
+                                                                          coverage_from_fixed(base + p2, rule), coverage_from_fixed(base + p3, rule));
             }
-        } else {
-            float4* out = reinterpret_cast<float4*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride;
-            for (int seg = 0; seg < nseg; seg++) {
-                const int xs = cx0 + seg * 128;
-                const int col = seg * 128 + lane * 4;
-                int w0, w1, w2, w3;
-                if (any) {
-                    const int4 v = *reinterpret_cast<const int4*>(rowc + col);
-                    const int p0 = v.x, p1 = p0 + v.y, p2 = p1 + v.z, p3 = p2 + v.w;
-                    int incl = p3;
+            __syncwarp();
+            // transposed read-back: lane l takes columns [128*i + 4l, +4) of the block
+            const int bw = min(wrem - blk * 1024, 1024);  // visible columns of this block
+            if (mode != kModeFill) {
+                float* out = reinterpret_cast<float*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride + cx0 + blk * 1024;
+                const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int nb = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += nb;
+                for (int i = 0; i < (CW >= 1024 ? 8 : 1); i++) {
+                    const int col = i * 128 + lane * 4;
+                    if (col >= bw) break;
+                    float4 cv = *reinterpret_cast<const float4*>(bc + swz(col));
+                    if (mode == kModeCoverage) {  // mask_iter drops abs(alpha) < 1e-6 (src/rasterize.rs:348)
+                        if (cv.x < 1e-6f) cv.x = 0.f;
+                        if (cv.y < 1e-6f) cv.y = 0.f;
+                        if (cv.z < 1e-6f) cv.z = 0.f;
+                        if (cv.w < 1e-6f) cv.w = 0.f;
                     }
-                    const int base = acc + incl - p3;
-                    w0 = base + p0; w1 = base + p1; w2 = base + p2; w3 = base + p3;
-                    acc += __shfl_sync(0xffffffffu, incl, 31);
-                } else {
-                    w0 = w1 = w2 = w3 = acc;
+                    if (vec_ok && col + 3 < bw) {
+                        __stcs(reinterpret_cast<float4*>(out + col), cv);  // streaming 128-bit store, written once
+                    } else {
+                        if (col < bw) out[col] = cv.x;
+                        if (col + 1 < bw) out[col + 1] = cv.y;
+                        if (col + 2 < bw) out[col + 2] = cv.z;
+                        if (col + 3 < bw) out[col + 3] = cv.w;
+                    }
                 }
-                const float4 cv = make_float4(coverage_from_fixed(w0, rule), coverage_from_fixed(w1, rule),
-                                              coverage_from_fixed(w2, rule), coverage_from_fixed(w3, rule));
-                if (!__any_sync(0xffffffffu, fmaxf(fmaxf(cv.x, cv.y), fmaxf(cv.z, cv.w)) >= 1e-6f)) continue;  // nothing to paint
-                // stage coverage so that consecutive lanes composite consecutive pixels (coalesced 16 B accesses)
-                *reinterpret_cast<float4*>(rowc + col) = cv;
-                __syncwarp();
-                const float* covs = reinterpret_cast<const float*>(rowc + seg * 128);
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int px = xs + i * 32 + lane;
-                    const float alpha = covs[i * 32 + lane];
-                    if (px < wout && alpha >= 1e-6f) {
-                        float4 color = (job.paint_index >= 0) ? paint_at(s_paint, px, y) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                float4* out = reinterpret_cast<float4*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride + cx0 + blk * 1024;
+                const float* covs = reinterpret_cast<const float*>(bc);
+                for (int px = lane; px < bw; px += 32) {  // consecutive lanes composite consecutive pixels (16 B each)
+                    const float alpha = covs[swz(px)];
+                    if (alpha >= 1e-6f) {
+                        float4 color = (job.paint_index >= 0) ? paint_at(s_paint, cx0 + blk * 1024 + px, y) : make_float4(0.f, 0.f, 0.f, 0.f);
                         // with_alpha: self * (alpha as f32), src/color.rs:347-349
                         color = make_float4(fmul(color.x, alpha), fmul(color.y, alpha), fmul(color.z, alpha), fmul(color.w, alpha));
                         // blend_over: other + self * (1 - other.alpha), src/color.rs:342-344
@@ -432,8 +523,8 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
                         out[px] = dstc;
                     }
                 }
-                __syncwarp();
             }
+            __syncwarp();
         }
     }
 }
@@ -470,14 +561,32 @@ TileShape raster_tile_shape(int variant) {
     return TileShape{1024, 8};
 }
 
+template <int CW, int TH>
+constexpr size_t raster_smem_bytes() {
+    return sizeof(int) * TH * (CW + CW / 8) + sizeof(double) * 4 * kThreads + sizeof(float) * kThreads + sizeof(unsigned short) * kMaxSpans;
+}
+
+template <int CW, int TH>
+static void launch_raster_t(const JobDev* jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first, uint32_t n_tiles,
+                            const PaintDev* paints, const double4* lines, const uint32_t* band_offs, const uint32_t* refs,
+                            const Status* status, cudaStream_t s) {
+    constexpr size_t smem = raster_smem_bytes<CW, TH>();
+    static bool configured[64] = {};  // per template instance and per device: the attribute belongs to the device's function
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaFuncSetAttribute(raster_kernel<CW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev] = true;
+    }
+    raster_kernel<CW, TH><<<n_tiles, kThreads, smem, s>>>(jobs, n_jobs, job_first, tile_first, paints, lines, band_offs, refs, status);
+}
+
 void launch_raster(int variant, const JobDev* jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first, uint32_t n_tiles,
                    const PaintDev* paints, const double4* lines, const uint32_t* band_offs, const uint32_t* refs,
                    const Status* status, cudaStream_t s) {
     if (n_tiles == 0) return;
-    if (variant == 1)
-        raster_kernel<128, 64><<<n_tiles, kThreads, 0, s>>>(jobs, n_jobs, job_first, tile_first, paints, lines, band_offs, refs, status);
-    else
-        raster_kernel<1024, 8><<<n_tiles, kThreads, 0, s>>>(jobs, n_jobs, job_first, tile_first, paints, lines, band_offs, refs, status);
+    if (variant == 1) launch_raster_t<128, 64>(jobs, n_jobs, job_first, tile_first, n_tiles, paints, lines, band_offs, refs, status, s);
+    else launch_raster_t<1024, 8>(jobs, n_jobs, job_first, tile_first, n_tiles, paints, lines, band_offs, refs, status, s);
 }
 
 void launch_to_rgba8(const float4* lin, uchar4* out, size_t n, cudaStream_t s) {
