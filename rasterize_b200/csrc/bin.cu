@@ -1,9 +1,12 @@
-// K2 — binning of flattened lines into (job, scanline band) bins (the scans live in scan.cu).
+// K2 — binning of flattened lines into tiles: one bin per (job, scanline band, column chunk).
 //
 // Rows are independent in the signed-difference rasterizer (reference src/rasterize.rs:421-469: accumulation is
-// per (line,row); :478-503: the scan runs along x within a row), so a line is referenced once from every band
-// of `band_rows` rows its y-range touches.  The row range is the reference's own:
+// per (line,row); :478-503: the scan runs along x within a row), so a line is referenced from every band of
+// `band_rows` rows its y-range touches, and inside a band from every chunk of `chunk_cols` columns its cells can
+// land in.  The row range is the reference's own:
 //   first = floor(max(min_y, 0)),  end = min(H, ceil(max(max_y, 0)))     (src/rasterize.rs:414, 421)
+// The column range is conservative (x of the line over the band's rows, clamped like the reference clamps to
+// [0, width], one pixel of slack on both sides); the raster kernel drops what does not land in its tile.
 // Lines with |dy| < EPSILON add nothing (src/rasterize.rs:400-403) and are dropped here.
 #include "rgpu_internal.cuh"
 
@@ -27,15 +30,15 @@ __device__ __forceinline__ uint32_t line_job_of(const JobDev* __restrict__ jobs,
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 bin_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const uint32_t* __restrict__ slot_offs, uint32_t total_slots,
-           const uint32_t* __restrict__ line_job, const double4* __restrict__ lines, uint32_t* __restrict__ band_counts,
-           const uint32_t* __restrict__ band_offs, uint32_t total_bands, uint32_t* __restrict__ refs, uint32_t refs_cap, int band_rows,
-           Status* __restrict__ status) {
+           const uint32_t* __restrict__ line_job, const double4* __restrict__ lines, uint32_t* __restrict__ tile_counts,
+           const uint32_t* __restrict__ tile_offs, uint32_t total_tiles, uint32_t* __restrict__ refs, uint32_t refs_cap, int band_rows,
+           int chunk_cols, Status* __restrict__ status) {
     if (status->lines_overflow | status->nan_flag | status->depth_flag) return;
     const uint32_t n_lines = slot_offs ? slot_offs[total_slots] : status->n_lines;
     if (!FILL) {
         if (slot_offs && blockIdx.x == 0 && threadIdx.x == 0) status->n_lines = n_lines;
     } else {
-        const uint32_t n_refs = band_offs[total_bands];
+        const uint32_t n_refs = tile_offs[total_tiles];
         if (blockIdx.x == 0 && threadIdx.x == 0) status->n_refs = n_refs;
         if (n_refs > refs_cap) {
             if (blockIdx.x == 0 && threadIdx.x == 0) status->refs_overflow = 1u;
@@ -46,12 +49,13 @@ bin_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const uint32_t* __r
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); i0 < n_lines; i0 += stride) {  // warp-uniform bound
         const uint32_t i = i0 + lane;
-        int b0 = 0, b1 = -1;
-        uint32_t base = 0;
+        int b0 = 0, b1 = -1, n_chunks = 1;
+        uint32_t tile_base = 0;
+        double x0 = 0, y0 = 0, x1 = 0, y1 = 0, wc = 0;
         if (i < n_lines) {
             const double4 l = lines[i];
             const uint32_t j = line_job_of(jobs, n_jobs, slot_offs, line_job, i);
-            const double y0 = l.y, y1 = l.w;
+            x0 = l.x; y0 = l.y; x1 = l.z; y1 = l.w;
             if (fabs(y0 - y1) >= kEps) {  // horizontal (or NaN) lines add no signed coverage
                 const double H = (double)jobs[j].height;
                 const double lo = fmin(y0, y1), hi = fmax(y0, y1);
@@ -61,25 +65,47 @@ bin_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const uint32_t* __r
                     if (first < end) {
                         b0 = (int)first / band_rows;
                         b1 = ((int)end - 1) / band_rows;
-                        base = jobs[j].band_begin;
+                        tile_base = jobs[j].tile_begin;
+                        n_chunks = (int)jobs[j].n_chunks;
+                        wc = jobs[j].clamp_w;
                     }
                 }
             }
         }
+        const double dxdy = (x1 - x0) / (y1 - y0);
         for (int b = b0;; b++) {
-            const bool valid = b <= b1;
-            const unsigned m = __ballot_sync(0xffffffffu, valid);
-            if (m == 0) break;
-            if (valid) {
-                const uint32_t key = base + (uint32_t)b;
-                const unsigned peers = __match_any_sync(m, key);
-                const int leader = __ffs(peers) - 1;
-                uint32_t slot0 = 0;
-                if ((int)lane == leader) slot0 = atomicAdd(&band_counts[key], (uint32_t)__popc(peers));
-                if (FILL) {
-                    slot0 = __shfl_sync(peers, slot0, leader);
-                    const uint32_t rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
-                    refs[band_offs[key] + slot0 + rank] = i;
+            const bool bvalid = b <= b1;
+            if (__ballot_sync(0xffffffffu, bvalid) == 0) break;
+            int c0 = 0, c1 = -1;
+            if (bvalid) {
+                if (n_chunks > 1) {
+                    // x of the line at the top and bottom of its part inside this band, clamped like the reference
+                    const double ya = fmax((double)(b * band_rows), fmin(y0, y1));
+                    const double yb = fmin((double)((b + 1) * band_rows), fmax(y0, y1));
+                    const double xa = x0 + (ya - y0) * dxdy, xb = x0 + (yb - y0) * dxdy;
+                    const double lo = fmin(fmax(fmin(xa, xb), 0.0), wc), hi = fmin(fmax(fmax(xa, xb), 0.0), wc);
+                    c0 = max(0, (int)(lo - 1.0) / chunk_cols);
+                    c1 = min(n_chunks - 1, (int)(hi + 2.0) / chunk_cols);
+                    if (!(lo == lo) || !(hi == hi)) { c0 = 0; c1 = n_chunks - 1; }  // NaN from degenerate input: be conservative
+                } else {
+                    c0 = c1 = 0;
+                }
+            }
+            for (int c = c0;; c++) {
+                const bool valid = bvalid && c <= c1;
+                const unsigned m = __ballot_sync(0xffffffffu, valid);
+                if (m == 0) break;
+                if (valid) {
+                    const uint32_t key = tile_base + (uint32_t)b * (uint32_t)n_chunks + (uint32_t)c;
+                    const unsigned peers = __match_any_sync(m, key);
+                    const int leader = __ffs(peers) - 1;
+                    uint32_t slot0 = 0;
+                    if ((int)lane == leader) slot0 = atomicAdd(&tile_counts[key], (uint32_t)__popc(peers));
+                    if (FILL) {
+                        slot0 = __shfl_sync(peers, slot0, leader);
+                        const uint32_t rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
+                        refs[tile_offs[key] + slot0 + rank] = i;
+                    }
                 }
             }
         }
@@ -91,16 +117,16 @@ bin_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const uint32_t* __r
 static inline uint32_t line_grid(cudaStream_t) { return 148 * 8; }
 
 void launch_bin_count(const JobDev* jobs, uint32_t n_jobs, const uint32_t* slot_offs, uint32_t total_slots, const uint32_t* line_job,
-                      const double4* lines, uint32_t* band_counts, int band_rows, Status* status, cudaStream_t s) {
-    bin_kernel<false><<<line_grid(s), 256, 0, s>>>(jobs, n_jobs, slot_offs, total_slots, line_job, lines, band_counts, nullptr, 0, nullptr,
-                                                   0, band_rows, status);
+                      const double4* lines, uint32_t* tile_counts, int band_rows, int chunk_cols, Status* status, cudaStream_t s) {
+    bin_kernel<false><<<line_grid(s), 256, 0, s>>>(jobs, n_jobs, slot_offs, total_slots, line_job, lines, tile_counts, nullptr, 0, nullptr,
+                                                   0, band_rows, chunk_cols, status);
 }
 
 void launch_bin_fill(const JobDev* jobs, uint32_t n_jobs, const uint32_t* slot_offs, uint32_t total_slots, const uint32_t* line_job,
-                     const double4* lines, const uint32_t* band_offs, uint32_t total_bands, uint32_t* band_cursor, uint32_t* refs,
-                     uint32_t refs_cap, int band_rows, Status* status, cudaStream_t s) {
-    bin_kernel<true><<<line_grid(s), 256, 0, s>>>(jobs, n_jobs, slot_offs, total_slots, line_job, lines, band_cursor, band_offs, total_bands,
-                                                  refs, refs_cap, band_rows, status);
+                     const double4* lines, const uint32_t* tile_offs, uint32_t total_tiles, uint32_t* tile_cursor, uint32_t* refs,
+                     uint32_t refs_cap, int band_rows, int chunk_cols, Status* status, cudaStream_t s) {
+    bin_kernel<true><<<line_grid(s), 256, 0, s>>>(jobs, n_jobs, slot_offs, total_slots, line_job, lines, tile_cursor, tile_offs, total_tiles,
+                                                  refs, refs_cap, band_rows, chunk_cols, status);
 }
 
 }  // namespace rgpu

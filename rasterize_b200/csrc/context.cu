@@ -59,7 +59,8 @@ struct rgpu_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     // device scratch (grow-only)
-    DevBuf jobs, paints, slot_counts, slot_offs, lines, line_job, band_counts, band_offs, band_cursor, refs, scan_temp, status;
+    DevBuf jobs, paints, slot_counts, slot_offs, lines, line_job, zero_block, tile_offs, refs, scan_temp, status, tile_state;
+    uint32_t epoch = 0;
     DevBuf img_f32, img_f64, img_lin;  // staging canvases of the host-buffer entry points
     size_t lines_cap = 0, refs_cap = 0;
     // pinned host
@@ -354,11 +355,27 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     }
     if ((rc = ensure_dev(ctx, ctx->refs, sizeof(uint32_t) * want_refs))) return rc;
     ctx->refs_cap = std::min<size_t>(ctx->refs.cap / sizeof(uint32_t), 0xfffffff0u);
-    if ((rc = ensure_dev(ctx, ctx->band_counts, sizeof(uint32_t) * (band_acc + 1)))) return rc;
-    if ((rc = ensure_dev(ctx, ctx->band_offs, sizeof(uint32_t) * (band_acc + 1)))) return rc;
-    if ((rc = ensure_dev(ctx, ctx->band_cursor, sizeof(uint32_t) * (band_acc + 1)))) return rc;
-    size_t tb = std::max(ordered_lines ? scan_temp_bytes(total_slots + 1) : 0, scan_temp_bytes(band_acc + 1));
+    // one block that must be zero at the start of every batch: [tickets | tile_counts | tile_cursor], one memset
+    const uint32_t n_raster_launches = (flags & RGPU_BATCH_INDEPENDENT) ? 1u : n_live;
+    const size_t tickets_off = 0;
+    const size_t counts_off = ((size_t)n_raster_launches * 4 + 255) & ~(size_t)255;
+    const size_t cursor_off = counts_off + (((size_t)(tile_acc + 1) * 4 + 255) & ~(size_t)255);
+    const size_t zero_bytes = cursor_off + (((size_t)(tile_acc + 1) * 4 + 255) & ~(size_t)255);
+    if ((rc = ensure_dev(ctx, ctx->zero_block, zero_bytes))) return rc;
+    if ((rc = ensure_dev(ctx, ctx->tile_offs, sizeof(uint32_t) * (tile_acc + 1)))) return rc;
+    size_t tb = std::max(ordered_lines ? scan_temp_bytes(total_slots + 1) : 0, scan_temp_bytes(tile_acc + 1));
     if ((rc = ensure_dev(ctx, ctx->scan_temp, tb))) return rc;
+    // carry look-back state, validated by epoch (cleared only when (re)allocated or when the epoch wraps)
+    {
+        size_t need = sizeof(unsigned long long) * kStateRows * (size_t)tile_acc;
+        size_t before = ctx->tile_state.cap;
+        if ((rc = ensure_dev(ctx, ctx->tile_state, need))) return rc;
+        ctx->epoch++;
+        if (ctx->tile_state.cap != before || ctx->epoch >= (1u << 30)) {
+            CK(ctx, cudaMemsetAsync(ctx->tile_state.p, 0, ctx->tile_state.cap, ctx->stream));
+            if (ctx->epoch >= (1u << 30)) ctx->epoch = 1;
+        }
+    }
 
     cudaStream_t s = ctx->stream;
     JobDev* d_jobs = static_cast<JobDev*>(ctx->jobs.p);
@@ -367,16 +384,18 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     uint32_t* d_counts = static_cast<uint32_t*>(ctx->slot_counts.p);
     uint32_t* d_offs = static_cast<uint32_t*>(ctx->slot_offs.p);
     double4* d_lines = static_cast<double4*>(ctx->lines.p);
-    uint32_t* d_bc = static_cast<uint32_t*>(ctx->band_counts.p);
-    uint32_t* d_bo = static_cast<uint32_t*>(ctx->band_offs.p);
-    uint32_t* d_cur = static_cast<uint32_t*>(ctx->band_cursor.p);
+    char* zb = static_cast<char*>(ctx->zero_block.p);
+    uint32_t* d_tickets = reinterpret_cast<uint32_t*>(zb + tickets_off);
+    uint32_t* d_bc = reinterpret_cast<uint32_t*>(zb + counts_off);
+    uint32_t* d_cur = reinterpret_cast<uint32_t*>(zb + cursor_off);
+    uint32_t* d_bo = static_cast<uint32_t*>(ctx->tile_offs.p);
+    unsigned long long* d_state = static_cast<unsigned long long*>(ctx->tile_state.p);
     uint32_t* d_refs = static_cast<uint32_t*>(ctx->refs.p);
 
     CK(ctx, cudaMemcpyAsync(d_jobs, ctx->h_jobs, sizeof(JobDev) * n_live, cudaMemcpyHostToDevice, s));
     if (n_paints) CK(ctx, cudaMemcpyAsync(d_paints, ctx->h_paints, sizeof(PaintDev) * n_paints, cudaMemcpyHostToDevice, s));
     CK(ctx, cudaMemsetAsync(d_status, 0, sizeof(Status), s));
-    CK(ctx, cudaMemsetAsync(d_bc, 0, sizeof(uint32_t) * (band_acc + 1), s));
-    CK(ctx, cudaMemsetAsync(d_cur, 0, sizeof(uint32_t) * (band_acc + 1), s));
+    CK(ctx, cudaMemsetAsync(zb, 0, zero_bytes, s));
 
     double thr = 16.0 * ctx->flatness * ctx->flatness;  // PathFlattenIter::new, src/path.rs:749
     const bool prof = ctx->profiling;
@@ -394,19 +413,20 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         ctx->n_launches += 1;
     }
     if (prof) CK(ctx, cudaEventRecord(ctx->ev[1], s));
-    launch_bin_count(d_jobs, n_live, d_offs, total_slots, d_line_job, d_lines, d_bc, ts.th, d_status, s);
-    launch_exclusive_scan(d_bc, d_bo, band_acc + 1, ctx->scan_temp.p, ctx->scan_temp.cap, s);
-    launch_bin_fill(d_jobs, n_live, d_offs, total_slots, d_line_job, d_lines, d_bo, band_acc, d_cur, d_refs, (uint32_t)ctx->refs_cap,
-                    ts.th, d_status, s);
+    launch_bin_count(d_jobs, n_live, d_offs, total_slots, d_line_job, d_lines, d_bc, ts.th, ts.cw, d_status, s);
+    launch_exclusive_scan(d_bc, d_bo, tile_acc + 1, ctx->scan_temp.p, ctx->scan_temp.cap, s);
+    launch_bin_fill(d_jobs, n_live, d_offs, total_slots, d_line_job, d_lines, d_bo, tile_acc, d_cur, d_refs, (uint32_t)ctx->refs_cap,
+                    ts.th, ts.cw, d_status, s);
     ctx->n_launches += 3;
     if (prof) CK(ctx, cudaEventRecord(ctx->ev[2], s));
     if (flags & RGPU_BATCH_INDEPENDENT) {
-        launch_raster(variant, d_jobs, n_live, 0, 0, tile_acc, d_paints, d_lines, d_bo, d_refs, d_status, s);
+        launch_raster(variant, d_jobs, n_live, 0, 0, tile_acc, d_paints, d_lines, d_bo, d_refs, d_state, ctx->epoch, d_tickets, d_status, s);
         ctx->n_launches += 1;
     } else {
         for (uint32_t j = 0; j < n_live; j++) {
             const JobDev& d = ctx->h_jobs[j];
-            launch_raster(variant, d_jobs, 1, j, d.tile_begin, d.n_bands * d.n_chunks, d_paints, d_lines, d_bo, d_refs, d_status, s);
+            launch_raster(variant, d_jobs, 1, j, d.tile_begin, d.n_bands * d.n_chunks, d_paints, d_lines, d_bo, d_refs, d_state, ctx->epoch,
+                          d_tickets + j, d_status, s);
             ctx->n_launches += 1;
         }
     }
@@ -509,8 +529,8 @@ void rgpu_destroy(rgpu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->jobs, &ctx->paints, &ctx->slot_counts, &ctx->slot_offs, &ctx->lines, &ctx->line_job, &ctx->band_counts, &ctx->band_offs,
-                      &ctx->band_cursor, &ctx->refs, &ctx->scan_temp, &ctx->status, &ctx->img_f32, &ctx->img_f64, &ctx->img_lin};
+    DevBuf* bufs[] = {&ctx->jobs, &ctx->paints, &ctx->slot_counts, &ctx->slot_offs, &ctx->lines, &ctx->line_job, &ctx->zero_block, &ctx->tile_offs,
+                      &ctx->tile_state, &ctx->refs, &ctx->scan_temp, &ctx->status, &ctx->img_f32, &ctx->img_f64, &ctx->img_lin};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);

@@ -14,8 +14,9 @@
 // coverage of each pixel it crosses (the running sum of the reference's deltas), rounded to Q7.24 fixed point,
 // and the DIFFERENCES of consecutive rounded coverages are added with integer shared-memory atomics.  Integer
 // addition is associative, so the result does not depend on the order threads arrive, and the differences
-// telescope: whatever subset of a span's cells falls left of a tile sums to exactly the rounded coverage at the
-// tile edge, so tiles of one band agree on their carry-in without communicating.
+// telescope: the cells of a span that fall in one tile sum to (rounded coverage at the tile's last column) -
+// (rounded coverage left of its first column), so the per-row totals the tiles of a band exchange through the
+// carry look-back are exact integers and the result is bit-identical from run to run.
 #include "rgpu_internal.cuh"
 
 namespace rgpu {
@@ -172,10 +173,11 @@ struct TileGeom {
 
 // One (piece, row) span: the body of the reference's row loop (src/rasterize.rs:421-469) for canvas row y.
 // (ax,ay) is the piece's upper end (ay < by), dirf = +-1.  Pixel coverages (running sums of the reference's
-// deltas) are rounded to Q7.24 and their differences added to the cells; whatever falls left of the tile
-// collapses into the row's carry.
+// deltas) are rounded to Q7.24 and the differences of consecutive rounded coverages are added to the cells of
+// THIS tile only; their sum (a telescoping difference) goes to the row's tile total, from which the tiles to the
+// right derive their carry-in.  Parts of the span in other tiles are added by those tiles (2-D bins).
 __device__ __forceinline__ void span_row(double ax, double ay, double by, double dxdy, float dirf, int y, const TileGeom& g,
-                                         int* __restrict__ cells, int* __restrict__ carry, int* __restrict__ row_touched) {
+                                         int* __restrict__ cells, int* __restrict__ rowtot, int* __restrict__ row_touched) {
     const double yt = fmax((double)y, ay);
     const double dy = fmin((double)(y + 1), by) - yt;
     const double x = ax + (yt - ay) * dxdy;  // the reference accumulates x row by row; this differs by rounding only
@@ -191,10 +193,7 @@ __device__ __forceinline__ void span_row(double ax, double ay, double by, double
     const int fd = to_fixed_f(d);
     const bool narrow = x1i <= x0i + 1;
     const int last = narrow ? x0i + 1 : x1i;  // last column that receives a delta
-    if (last < g.cx0) {                       // this row's span is left of the tile: only its cover arrives
-        atomicAdd(&carry[r], fd);
-        return;
-    }
+    if (last < g.cx0) return;                 // this row's span is left of the tile: it arrives through the look-back
     // Positions stay f64 (f32 ulp at x ~ 4096 would already exceed the 1e-4 budget); the fractional parts are in
     // [0,1] and the area polynomials are evaluated in f32 (error ~1e-7 of a pixel).
     float c0, sf = 0.f, a1 = 0.f, am = 0.f;
@@ -218,11 +217,8 @@ __device__ __forceinline__ void span_row(double ax, double ay, double by, double
     };
     const int kb = max(x0i, g.cx0);
     const int ke = min(last, g.tile_end - 1);
-    int prev = 0;
-    if (kb > x0i) {  // the part of the span left of the tile collapses into the carry
-        prev = to_fixed_f(d * cov(kb - 1 - x0i));
-        atomicAdd(&carry[r], prev);
-    }
+    const int first = (kb > x0i) ? to_fixed_f(d * cov(kb - 1 - x0i)) : 0;  // rounded coverage just left of the tile
+    int prev = first;
     int* rowp = cells + r * g.pitch;
     for (int k = kb; k <= ke; k++) {
         const int cur = (k == last) ? fd : to_fixed_f(d * cov(k - x0i));
@@ -230,6 +226,7 @@ __device__ __forceinline__ void span_row(double ax, double ay, double by, double
         if (diff != 0) atomicAdd(&rowp[swz(k - g.cx0)], diff);
         prev = cur;
     }
+    atomicAdd(&rowtot[r], prev - first);
     row_touched[r] = 1;
 }
 
@@ -238,7 +235,7 @@ struct Piece {
     double ax, ay, by, dxdy;
     float dirf;
     int rb, re;
-    int cls;  // 0 = nothing to do, 1 = entirely left of the tile (cover only), 2 = needs span_row
+    int cls;  // 0 = nothing to do in this tile, 2 = needs span_row
 };
 
 __device__ __forceinline__ Piece classify_piece(double ax, double ay, double bx, double by, const TileGeom& g) {
@@ -256,32 +253,35 @@ __device__ __forceinline__ Piece classify_piece(double ax, double ay, double bx,
         p.dirf = -1.0f;
     }
     p.ax = ax; p.ay = ay; p.by = by;
-    if (xmin >= (double)g.tile_end) return p;  // entirely right of the tile: contributes nothing here
+    if (xmin >= (double)g.tile_end) return p;    // entirely right of the tile: contributes nothing here
+    if (xmax < (double)g.cx0 - 1.0) return p;    // entirely left (a pixel of slack for the span's last column): look-back
     // rows of the reference loop (src/rasterize.rs:414, 421) intersected with the band
     const double ys = floor(fmax(ay, 0.0));
     const double ye = ceil(fmax(by, 0.0));
     p.rb = ys >= (double)g.row1 ? g.row1 : max(g.row0, (int)ys);
     p.re = ye >= (double)g.row1 ? g.row1 : (int)ye;
     if (p.rb >= p.re) return p;
-    if (xmax < (double)g.cx0 - 1.0) { p.cls = 1; return p; }  // a pixel of slack for the span's last column
     p.dxdy = (bx - ax) / (by - ay);
     p.cls = 2;
     return p;
 }
 
-// cover-only rows of a piece that lies entirely left of the tile
-__device__ __forceinline__ void left_cover(const Piece& p, const TileGeom& g, int* __restrict__ carry) {
-    for (int y = p.rb; y < p.re; y++) {
-        const double dy = fmin((double)(y + 1), p.by) - fmax((double)y, p.ay);
-        atomicAdd(&carry[y - g.row0], to_fixed_f(p.dirf * (float)dy));
-    }
+__device__ void piece_serial(double ax, double ay, double bx, double by, const TileGeom& g, int* cells, int* rowtot, int* row_touched) {
+    const Piece p = classify_piece(ax, ay, bx, by, g);
+    if (p.cls == 2)
+        for (int y = p.rb; y < p.re; y++) span_row(p.ax, p.ay, p.by, p.dxdy, p.dirf, y, g, cells, rowtot, row_touched);
 }
 
-__device__ void piece_serial(double ax, double ay, double bx, double by, const TileGeom& g, int* cells, int* carry, int* row_touched) {
-    const Piece p = classify_piece(ax, ay, bx, by, g);
-    if (p.cls == 1) left_cover(p, g, carry);
-    else if (p.cls == 2)
-        for (int y = p.rb; y < p.re; y++) span_row(p.ax, p.ay, p.by, p.dxdy, p.dirf, y, g, cells, carry, row_touched);
+// ---- carry look-back state: one 64-bit word per (tile, row): [63:34] epoch, [33:32] flag, [31:0] value ---------
+constexpr unsigned long long kFlagAgg = 1ull << 32;     // value = this tile's row total
+constexpr unsigned long long kFlagPrefix = 2ull << 32;  // value = inclusive prefix over the tiles of the band so far
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 constexpr int kMaxSpans = 4096;
@@ -289,8 +289,9 @@ constexpr int kMaxSpans = 4096;
 template <int CW, int TH>
 __global__ void __launch_bounds__(kThreads)
 raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
-              const PaintDev* __restrict__ paints, const double4* __restrict__ lines, const uint32_t* __restrict__ band_offs,
-              const uint32_t* __restrict__ refs, const Status* __restrict__ status) {
+              const PaintDev* __restrict__ paints, const double4* __restrict__ lines, const uint32_t* __restrict__ tile_offs,
+              const uint32_t* __restrict__ refs, unsigned long long* __restrict__ tile_state, uint32_t epoch,
+              uint32_t* __restrict__ ticket, const Status* __restrict__ status) {
     constexpr int kPitch = CW + CW / 8;  // swizzled row pitch
     constexpr int kRowBits = (TH <= 8) ? 3 : 6;
     static_assert(TH <= 64 && CW % 128 == 0, "tile shape");
@@ -304,7 +305,9 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     float* p_dir = reinterpret_cast<float*>(p_dxdy + kThreads);
     unsigned short* spans = reinterpret_cast<unsigned short*>(p_dir + kThreads);
     __shared__ int carry[TH];
+    __shared__ int rowtot[TH];
     __shared__ int row_touched[TH];
+    __shared__ uint32_t s_tile;
     __shared__ int n_spans;
     __shared__ uint32_t s_job;
     __shared__ PaintDev s_paint;
@@ -312,18 +315,21 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     if (status->lines_overflow | status->refs_overflow | status->nan_flag | status->depth_flag) return;
 
     const int tid = threadIdx.x;
-    uint32_t tile = tile_first + blockIdx.x;
     if (tid == 0) {
-        s_job = job_first + find_job(n_jobs, tile, [&](uint32_t k) { return jobs[job_first + k].tile_begin; });
+        // dynamic tile id: a tile only ever waits (carry look-back) on tiles with smaller ids, which have started
+        const uint32_t t = tile_first + atomicAdd(ticket, 1u);
+        s_tile = t;
+        s_job = job_first + find_job(n_jobs, t, [&](uint32_t k) { return jobs[job_first + k].tile_begin; });
         n_spans = 0;
     }
-    if (tid < TH) { carry[tid] = 0; row_touched[tid] = 0; }
+    if (tid < TH) { carry[tid] = 0; rowtot[tid] = 0; row_touched[tid] = 0; }
     {
         int4 z = make_int4(0, 0, 0, 0);
         int4* c4 = reinterpret_cast<int4*>(cells);
         for (int i = tid; i < TH * kPitch / 4; i += kThreads) c4[i] = z;
     }
     __syncthreads();
+    const uint32_t tile = s_tile;
     const JobDev& job = jobs[s_job];
     uint32_t lt = tile - job.tile_begin;
     const int band = (int)(lt / job.n_chunks);
@@ -348,8 +354,7 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     }
 
     // ---- phase 1: accumulate the band's lines, kThreads references per round ------------------------------
-    const uint32_t gb = job.band_begin + (uint32_t)band;
-    const uint32_t rbeg = band_offs[gb], rend = band_offs[gb + 1];
+    const uint32_t rbeg = tile_offs[tile], rend = tile_offs[tile + 1];
     for (uint32_t r0 = rbeg; r0 < rend; r0 += kThreads) {
         // 1a: one reference per thread: the reference's clipping, orientation, row range; spans are appended to
         //     a shared list so that 1b runs one lane per (piece,row) span with no row-loop divergence
@@ -380,27 +385,25 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
                     // the outside part, folded onto x = 0, goes through the same function again in the reference;
                     // rare (only lines crossing the left edge): done serially by this thread
                     if (p0x < 0.0) {
-                        if (mx <= 0.0) piece_serial(0.0, p0y, 0.0, my, g, cells, carry, row_touched);
-                        else piece_serial(0.0, p0y, mx, my, g, cells, carry, row_touched);
+                        if (mx <= 0.0) piece_serial(0.0, p0y, 0.0, my, g, cells, rowtot, row_touched);
+                        else piece_serial(0.0, p0y, mx, my, g, cells, rowtot, row_touched);
                         p0x = mx; p0y = my;
                     } else {
-                        if (mx <= 0.0) piece_serial(0.0, my, 0.0, p1y, g, cells, carry, row_touched);
-                        else piece_serial(mx, my, 0.0, p1y, g, cells, carry, row_touched);
+                        if (mx <= 0.0) piece_serial(0.0, my, 0.0, p1y, g, cells, rowtot, row_touched);
+                        else piece_serial(mx, my, 0.0, p1y, g, cells, rowtot, row_touched);
                         p1x = mx; p1y = my;
                     }
                 }
             }
             const Piece p = classify_piece(p0x, p0y, p1x, p1y, g);
-            if (p.cls == 1) {
-                left_cover(p, g, carry);
-            } else if (p.cls == 2) {
+            if (p.cls == 2) {
                 const int n = p.re - p.rb;
                 const int base = atomicAdd(&n_spans, n);
                 if (base + n <= kMaxSpans) {
                     p_ax[tid] = p.ax; p_ay[tid] = p.ay; p_by[tid] = p.by; p_dxdy[tid] = p.dxdy; p_dir[tid] = p.dirf;
                     for (int k = 0; k < n; k++) spans[base + k] = (unsigned short)((tid << kRowBits) | (p.rb + k - row0));
                 } else {  // span list full (only possible for TH = 64): do the rows here
-                    for (int y = p.rb; y < p.re; y++) span_row(p.ax, p.ay, p.by, p.dxdy, p.dirf, y, g, cells, carry, row_touched);
+                    for (int y = p.rb; y < p.re; y++) span_row(p.ax, p.ay, p.by, p.dxdy, p.dirf, y, g, cells, rowtot, row_touched);
                 }
             }
         }
@@ -411,7 +414,7 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
             const int e = spans[i];
             const int slot = e >> kRowBits;
             const int y = row0 + (e & ((1 << kRowBits) - 1));
-            span_row(p_ax[slot], p_ay[slot], p_by[slot], p_dxdy[slot], p_dir[slot], y, g, cells, carry, row_touched);
+            span_row(p_ax[slot], p_ay[slot], p_by[slot], p_dxdy[slot], p_dir[slot], y, g, cells, rowtot, row_touched);
         }
         __syncthreads();
         if (tid == 0) n_spans = 0;
@@ -419,6 +422,34 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
         __syncthreads();
     }
     if (rbeg == rend) __syncthreads();
+
+    // ---- carry-in: decoupled look-back over the tiles to the left in this band --------------------------------
+    // Every tile publishes its per-row totals (flag AGG), sums its predecessors' totals until it meets an
+    // inclusive prefix, then publishes its own inclusive prefix.  Words carry the batch epoch, so the state needs
+    // no clearing between batches.  Single-chunk jobs have no neighbours and skip all of this.
+    if (job.n_chunks > 1) {
+        if (tid < TH && tid < kStateRows) {
+            const int agg = rowtot[tid];
+            unsigned long long* st = tile_state + (size_t)tile * kStateRows + tid;
+            const unsigned long long ep = (unsigned long long)epoch << 34;
+            if (chunk == 0) {
+                st_state(st, ep | kFlagPrefix | (unsigned long long)(uint32_t)agg);
+            } else {
+                st_state(st, ep | kFlagAgg | (unsigned long long)(uint32_t)agg);
+                int sum = 0;
+                for (int k = 1; k <= chunk; k++) {
+                    const unsigned long long* ps = tile_state + (size_t)(tile - (uint32_t)k) * kStateRows + tid;
+                    unsigned long long v;
+                    do { v = ld_state(ps); } while ((uint32_t)(v >> 34) != epoch);
+                    sum += (int)(uint32_t)v;
+                    if ((v & (3ull << 32)) == kFlagPrefix) break;
+                }
+                carry[tid] = sum;
+                st_state(st, ep | kFlagPrefix | (unsigned long long)(uint32_t)(sum + agg));
+            }
+        }
+        __syncthreads();
+    }
 
     // ---- phase 2: per-row scan, fill rule, store / composite --------------------------------------------
     // A warp takes a row; lane l owns 32 consecutive columns per 1024-column block: serial prefix in registers,
@@ -568,8 +599,8 @@ constexpr size_t raster_smem_bytes() {
 
 template <int CW, int TH>
 static void launch_raster_t(const JobDev* jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first, uint32_t n_tiles,
-                            const PaintDev* paints, const double4* lines, const uint32_t* band_offs, const uint32_t* refs,
-                            const Status* status, cudaStream_t s) {
+                            const PaintDev* paints, const double4* lines, const uint32_t* tile_offs, const uint32_t* refs,
+                            unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, cudaStream_t s) {
     constexpr size_t smem = raster_smem_bytes<CW, TH>();
     static bool configured[64] = {};  // per template instance and per device: the attribute belongs to the device's function
     int dev = 0;
@@ -578,15 +609,18 @@ static void launch_raster_t(const JobDev* jobs, uint32_t n_jobs, uint32_t job_fi
         cudaFuncSetAttribute(raster_kernel<CW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured[dev] = true;
     }
-    raster_kernel<CW, TH><<<n_tiles, kThreads, smem, s>>>(jobs, n_jobs, job_first, tile_first, paints, lines, band_offs, refs, status);
+    raster_kernel<CW, TH><<<n_tiles, kThreads, smem, s>>>(jobs, n_jobs, job_first, tile_first, paints, lines, tile_offs, refs, tile_state,
+                                                          epoch, ticket, status);
 }
 
 void launch_raster(int variant, const JobDev* jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first, uint32_t n_tiles,
-                   const PaintDev* paints, const double4* lines, const uint32_t* band_offs, const uint32_t* refs,
-                   const Status* status, cudaStream_t s) {
+                   const PaintDev* paints, const double4* lines, const uint32_t* tile_offs, const uint32_t* refs,
+                   unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, cudaStream_t s) {
     if (n_tiles == 0) return;
-    if (variant == 1) launch_raster_t<128, 64>(jobs, n_jobs, job_first, tile_first, n_tiles, paints, lines, band_offs, refs, status, s);
-    else launch_raster_t<1024, 8>(jobs, n_jobs, job_first, tile_first, n_tiles, paints, lines, band_offs, refs, status, s);
+    if (variant == 1)
+        launch_raster_t<128, 64>(jobs, n_jobs, job_first, tile_first, n_tiles, paints, lines, tile_offs, refs, tile_state, epoch, ticket, status, s);
+    else
+        launch_raster_t<1024, 8>(jobs, n_jobs, job_first, tile_first, n_tiles, paints, lines, tile_offs, refs, tile_state, epoch, ticket, status, s);
 }
 
 void launch_to_rgba8(const float4* lin, uchar4* out, size_t n, cudaStream_t s) {
