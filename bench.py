@@ -138,7 +138,7 @@ def glyph_path(rb, seed: int):
 
 
 def build_workload(name: str, rb, rast, rank: int, world: int, torch):
-    from rasterize_b200 import assets, ffi
+    from rasterize_b200 import assets, ffi, sharding
     ex = assets.expected()["paths"]
     dev = torch.device("cuda", torch.cuda.current_device())
     if name == "c2":
@@ -171,10 +171,9 @@ def build_workload(name: str, rb, rast, rank: int, world: int, torch):
         w, hfull = c5["size"]
         bands = int(os.environ.get("RB_BANDS", "8"))
         band = rank % bands
-        y0, y1 = hfull * band // bands, hfull * (band + 1) // bands
+        y0, y1 = sharding.band_rows(hfull, band, bands)
         h = y1 - y0
-        tr = np.array(c5["tr"]).copy()
-        tr[5] -= y0  # band-local translate(0, -y0): the y<0 / y>=H clipping crops exactly
+        tr = sharding.band_transform(c5["tr"], y0)  # band-local translate(0, -y0): the reference's own y clipping crops exactly
         canvas = torch.empty((h, w), dtype=torch.float32, device=dev)
         dp = rast.upload(path)
         jobs = [rb.Job(dp, tr, rb.FillRule.NonZero, ffi.JOB_MASK, canvas.data_ptr(), w, h, w)]

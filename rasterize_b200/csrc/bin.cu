@@ -31,8 +31,8 @@ template <bool FILL>
 __global__ void __launch_bounds__(256)
 bin_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const uint32_t* __restrict__ slot_offs, uint32_t total_slots,
            const uint32_t* __restrict__ line_job, const double4* __restrict__ lines, uint32_t* __restrict__ tile_counts,
-           const uint32_t* __restrict__ tile_offs, uint32_t total_tiles, uint32_t* __restrict__ refs, uint32_t refs_cap, int band_rows,
-           int chunk_cols, Status* __restrict__ status) {
+           const uint32_t* __restrict__ tile_offs, uint32_t total_tiles, double4* __restrict__ bin_lines, uint32_t refs_cap, int band_shift,
+           int chunk_shift, Status* __restrict__ status) {
     if (status->lines_overflow | status->nan_flag | status->depth_flag) return;
     const uint32_t n_lines = slot_offs ? slot_offs[total_slots] : status->n_lines;
     if (!FILL) {
@@ -52,8 +52,9 @@ bin_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const uint32_t* __r
         int b0 = 0, b1 = -1, n_chunks = 1;
         uint32_t tile_base = 0;
         double x0 = 0, y0 = 0, x1 = 0, y1 = 0, wc = 0;
+        double4 l = make_double4(0, 0, 0, 0);
         if (i < n_lines) {
-            const double4 l = lines[i];
+            l = lines[i];
             const uint32_t j = line_job_of(jobs, n_jobs, slot_offs, line_job, i);
             x0 = l.x; y0 = l.y; x1 = l.z; y1 = l.w;
             if (fabs(y0 - y1) >= kEps) {  // horizontal (or NaN) lines add no signed coverage
@@ -63,8 +64,8 @@ bin_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const uint32_t* __r
                     const double first = floor(fmax(lo, 0.0));
                     const double end = fmin(H, ceil(hi));
                     if (first < end) {
-                        b0 = (int)first / band_rows;
-                        b1 = ((int)end - 1) / band_rows;
+                        b0 = (int)first >> band_shift;
+                        b1 = ((int)end - 1) >> band_shift;
                         tile_base = jobs[j].tile_begin;
                         n_chunks = (int)jobs[j].n_chunks;
                         wc = jobs[j].clamp_w;
@@ -72,7 +73,10 @@ bin_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const uint32_t* __r
                 }
             }
         }
-        const double dxdy = (x1 - x0) / (y1 - y0);
+        // column range per band in f32 with 1.5 px of slack each side (conservative; the raster kernel is exact)
+        const float fx0 = (float)x0, fy0 = (float)y0;
+        const float fdxdy = (float)((x1 - x0) / (y1 - y0));
+        const float fylo = (float)fmin(y0, y1), fyhi = (float)fmax(y0, y1), fwc = (float)wc;
         for (int b = b0;; b++) {
             const bool bvalid = b <= b1;
             if (__ballot_sync(0xffffffffu, bvalid) == 0) break;
@@ -80,12 +84,12 @@ bin_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const uint32_t* __r
             if (bvalid) {
                 if (n_chunks > 1) {
                     // x of the line at the top and bottom of its part inside this band, clamped like the reference
-                    const double ya = fmax((double)(b * band_rows), fmin(y0, y1));
-                    const double yb = fmin((double)((b + 1) * band_rows), fmax(y0, y1));
-                    const double xa = x0 + (ya - y0) * dxdy, xb = x0 + (yb - y0) * dxdy;
-                    const double lo = fmin(fmax(fmin(xa, xb), 0.0), wc), hi = fmin(fmax(fmax(xa, xb), 0.0), wc);
-                    c0 = max(0, (int)(lo - 1.0) / chunk_cols);
-                    c1 = min(n_chunks - 1, (int)(hi + 2.0) / chunk_cols);
+                    const float ya = fmaxf((float)(b << band_shift), fylo);
+                    const float yb = fminf((float)((b + 1) << band_shift), fyhi);
+                    const float xa = fx0 + (ya - fy0) * fdxdy, xb = fx0 + (yb - fy0) * fdxdy;
+                    const float lo = fminf(fmaxf(fminf(xa, xb), 0.0f), fwc), hi = fminf(fmaxf(fmaxf(xa, xb), 0.0f), fwc);
+                    c0 = max(0, (int)(lo - 1.5f) >> chunk_shift);
+                    c1 = min(n_chunks - 1, (int)(hi + 2.5f) >> chunk_shift);
                     if (!(lo == lo) || !(hi == hi)) { c0 = 0; c1 = n_chunks - 1; }  // NaN from degenerate input: be conservative
                 } else {
                     c0 = c1 = 0;
@@ -104,7 +108,7 @@ bin_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const uint32_t* __r
                     if (FILL) {
                         slot0 = __shfl_sync(peers, slot0, leader);
                         const uint32_t rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
-                        refs[tile_offs[key] + slot0 + rank] = i;
+                        bin_lines[tile_offs[key] + slot0 + rank] = l;  // the line itself: the raster kernel reads its bin coalesced
                     }
                 }
             }
@@ -115,18 +119,23 @@ bin_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const uint32_t* __r
 }  // namespace
 
 static inline uint32_t line_grid(cudaStream_t) { return 148 * 8; }
+static inline int log2i(int v) {
+    int s = 0;
+    while ((1 << s) < v) s++;
+    return s;  // tile shapes are powers of two
+}
 
 void launch_bin_count(const JobDev* jobs, uint32_t n_jobs, const uint32_t* slot_offs, uint32_t total_slots, const uint32_t* line_job,
                       const double4* lines, uint32_t* tile_counts, int band_rows, int chunk_cols, Status* status, cudaStream_t s) {
     bin_kernel<false><<<line_grid(s), 256, 0, s>>>(jobs, n_jobs, slot_offs, total_slots, line_job, lines, tile_counts, nullptr, 0, nullptr,
-                                                   0, band_rows, chunk_cols, status);
+                                                   0, log2i(band_rows), log2i(chunk_cols), status);
 }
 
 void launch_bin_fill(const JobDev* jobs, uint32_t n_jobs, const uint32_t* slot_offs, uint32_t total_slots, const uint32_t* line_job,
-                     const double4* lines, const uint32_t* tile_offs, uint32_t total_tiles, uint32_t* tile_cursor, uint32_t* refs,
+                     const double4* lines, const uint32_t* tile_offs, uint32_t total_tiles, uint32_t* tile_cursor, double4* bin_lines,
                      uint32_t refs_cap, int band_rows, int chunk_cols, Status* status, cudaStream_t s) {
     bin_kernel<true><<<line_grid(s), 256, 0, s>>>(jobs, n_jobs, slot_offs, total_slots, line_job, lines, tile_cursor, tile_offs, total_tiles,
-                                                  refs, refs_cap, band_rows, chunk_cols, status);
+                                                  bin_lines, refs_cap, log2i(band_rows), log2i(chunk_cols), status);
 }
 
 }  // namespace rgpu

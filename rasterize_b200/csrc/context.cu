@@ -340,7 +340,7 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
 
     // scratch sizing (optimistic; grown and re-run on overflow by *_sync)
     size_t want_lines = std::max<uint64_t>(ctx->lines_cap, est_lines);
-    size_t want_refs = std::max<uint64_t>(ctx->refs_cap, want_lines * 2);
+    size_t want_refs = std::max<uint64_t>(ctx->refs_cap, want_lines + want_lines / 2);
     if ((rc = ensure_dev(ctx, ctx->jobs, sizeof(JobDev) * n_live))) return rc;
     if ((rc = ensure_dev(ctx, ctx->paints, sizeof(PaintDev) * std::max<uint32_t>(n_paints, 1)))) return rc;
     if (ordered_lines) {
@@ -353,8 +353,8 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     if (need_line_job) {
         if ((rc = ensure_dev(ctx, ctx->line_job, sizeof(uint32_t) * ctx->lines_cap))) return rc;
     }
-    if ((rc = ensure_dev(ctx, ctx->refs, sizeof(uint32_t) * want_refs))) return rc;
-    ctx->refs_cap = std::min<size_t>(ctx->refs.cap / sizeof(uint32_t), 0xfffffff0u);
+    if ((rc = ensure_dev(ctx, ctx->refs, sizeof(double4) * want_refs))) return rc;
+    ctx->refs_cap = std::min<size_t>(ctx->refs.cap / sizeof(double4), 0xfffffff0u);
     // one block that must be zero at the start of every batch: [tickets | tile_counts | tile_cursor], one memset
     const uint32_t n_raster_launches = (flags & RGPU_BATCH_INDEPENDENT) ? 1u : n_live;
     const size_t tickets_off = 0;
@@ -390,7 +390,7 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     uint32_t* d_cur = reinterpret_cast<uint32_t*>(zb + cursor_off);
     uint32_t* d_bo = static_cast<uint32_t*>(ctx->tile_offs.p);
     unsigned long long* d_state = static_cast<unsigned long long*>(ctx->tile_state.p);
-    uint32_t* d_refs = static_cast<uint32_t*>(ctx->refs.p);
+    double4* d_refs = static_cast<double4*>(ctx->refs.p);
 
     CK(ctx, cudaMemcpyAsync(d_jobs, ctx->h_jobs, sizeof(JobDev) * n_live, cudaMemcpyHostToDevice, s));
     if (n_paints) CK(ctx, cudaMemcpyAsync(d_paints, ctx->h_paints, sizeof(PaintDev) * n_paints, cudaMemcpyHostToDevice, s));
@@ -420,13 +420,13 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     ctx->n_launches += 3;
     if (prof) CK(ctx, cudaEventRecord(ctx->ev[2], s));
     if (flags & RGPU_BATCH_INDEPENDENT) {
-        launch_raster(variant, d_jobs, n_live, 0, 0, tile_acc, d_paints, d_lines, d_bo, d_refs, d_state, ctx->epoch, d_tickets, d_status, s);
+        launch_raster(variant, d_jobs, ctx->h_jobs, n_live, 0, 0, tile_acc, d_paints, d_bo, d_refs, d_state, ctx->epoch, d_tickets, d_status, s);
         ctx->n_launches += 1;
     } else {
         for (uint32_t j = 0; j < n_live; j++) {
             const JobDev& d = ctx->h_jobs[j];
-            launch_raster(variant, d_jobs, 1, j, d.tile_begin, d.n_bands * d.n_chunks, d_paints, d_lines, d_bo, d_refs, d_state, ctx->epoch,
-                          d_tickets + j, d_status, s);
+            launch_raster(variant, d_jobs, ctx->h_jobs, 1, j, d.tile_begin, d.n_bands * d.n_chunks, d_paints, d_bo, d_refs, d_state,
+                          ctx->epoch, d_tickets + j, d_status, s);
             ctx->n_launches += 1;
         }
     }
@@ -475,8 +475,8 @@ int submit_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t fla
         int rc2;
         if ((rc2 = ensure_dev(ctx, ctx->lines, sizeof(double4) * nl))) return rc2;
         ctx->lines_cap = ctx->lines.cap / sizeof(double4);
-        if ((rc2 = ensure_dev(ctx, ctx->refs, sizeof(uint32_t) * nr))) return rc2;
-        ctx->refs_cap = ctx->refs.cap / sizeof(uint32_t);
+        if ((rc2 = ensure_dev(ctx, ctx->refs, sizeof(double4) * nr))) return rc2;
+        ctx->refs_cap = ctx->refs.cap / sizeof(double4);
     }
     return fail(ctx, RGPU_ERR_CAPACITY, "internal scratch overflow persisted after 4 attempts");
 }

@@ -24,8 +24,6 @@ namespace rgpu {
 namespace {
 
 constexpr double kEps = 2.220446049250313e-16;
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
 
 // ---- colour maths (f32, never contracted: the reference uses plain SSE mul/add) -------------------------
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
@@ -143,22 +141,24 @@ __device__ float4 paint_at(const PaintDev& P, int x, int y) {
 // ---- coverage from the fixed-point winding ---------------------------------------------------------------
 // NonZero: min(|w|, 1) (the reference's `value < 1e-6 -> 0` only matters to mask_iter's pixel dropping, which
 // the COVERAGE / FILL paths apply themselves; below 1e-6 the two differ by < 1e-6).  EvenOdd is exact in integers.
-__device__ __forceinline__ float coverage_from_fixed(int acc, int rule) {
+template <bool EVENODD>
+__device__ __forceinline__ float coverage_from_fixed(int acc) {
     constexpr float kInv = 1.0f / 16777216.0f;
-    if (rule == 1) {
+    if (EVENODD) {
         // abs(((w + 1) rem_euclid 2) - 1)
-        int t = (acc + kFixOne) & (2 * kFixOne - 1);
+        const int t = (acc + kFixOne) & (2 * kFixOne - 1);
         return fabsf((float)(t - kFixOne)) * kInv;
     }
     return fminf(fabsf((float)acc) * kInv, 1.0f);
 }
 
 // ---- shared-memory cell layout --------------------------------------------------------------------------
-// Cell (row r, tile column x) lives at r*pitch + swz(x), swz(x) = x + 4*(x/32): every group of 32 columns is
-// followed by 4 padding ints.  In the scan phase lane l owns columns [32l, 32l+32) of a 1024-column row; with the
-// padding its 128-bit loads hit bank-quad (l + i) mod 8, so each 8-lane wavefront is conflict-free, and the
-// transposed read-back (lane l reads columns [128i + 4l, +4)) is conflict-free too.
-__device__ __forceinline__ int swz(int x) { return x + ((x >> 5) << 2); }
+// In the scan phase lane l owns L = CW/32 consecutive columns of a row.  Cell (row r, tile column x) lives at
+// r*pitch + swz<L>(x), swz<L>(x) = x + 4*(x/L): every run of L columns is followed by 4 padding ints, so the
+// 128-bit accesses of 8 consecutive lanes (stride L+4 ints) fall on distinct bank quads — conflict-free both for
+// the per-lane runs and (up to one 2-way pair for L = 16) for the transposed read-back used for coalesced stores.
+template <int L>
+__device__ __forceinline__ int swz(int x) { return x + ((x / L) << 2); }
 
 __device__ __forceinline__ int to_fixed_f(float v) { return __float2int_rn(v * 16777216.0f); }
 
@@ -176,6 +176,7 @@ struct TileGeom {
 // deltas) are rounded to Q7.24 and the differences of consecutive rounded coverages are added to the cells of
 // THIS tile only; their sum (a telescoping difference) goes to the row's tile total, from which the tiles to the
 // right derive their carry-in.  Parts of the span in other tiles are added by those tiles (2-D bins).
+template <int L>
 __device__ __forceinline__ void span_row(double ax, double ay, double by, double dxdy, float dirf, int y, const TileGeom& g,
                                          int* __restrict__ cells, int* __restrict__ rowtot, int* __restrict__ row_touched) {
     const double yt = fmax((double)y, ay);
@@ -223,7 +224,7 @@ __device__ __forceinline__ void span_row(double ax, double ay, double by, double
     for (int k = kb; k <= ke; k++) {
         const int cur = (k == last) ? fd : to_fixed_f(d * cov(k - x0i));
         const int diff = cur - prev;
-        if (diff != 0) atomicAdd(&rowp[swz(k - g.cx0)], diff);
+        if (diff != 0) atomicAdd(&rowp[swz<L>(k - g.cx0)], diff);
         prev = cur;
     }
     atomicAdd(&rowtot[r], prev - first);
@@ -266,10 +267,11 @@ __device__ __forceinline__ Piece classify_piece(double ax, double ay, double bx,
     return p;
 }
 
+template <int L>
 __device__ void piece_serial(double ax, double ay, double bx, double by, const TileGeom& g, int* cells, int* rowtot, int* row_touched) {
     const Piece p = classify_piece(ax, ay, bx, by, g);
     if (p.cls == 2)
-        for (int y = p.rb; y < p.re; y++) span_row(p.ax, p.ay, p.by, p.dxdy, p.dirf, y, g, cells, rowtot, row_touched);
+        for (int y = p.rb; y < p.re; y++) span_row<L>(p.ax, p.ay, p.by, p.dxdy, p.dirf, y, g, cells, rowtot, row_touched);
 }
 
 // ---- carry look-back state: one 64-bit word per (tile, row): [63:34] epoch, [33:32] flag, [31:0] value ---------
@@ -284,54 +286,157 @@ __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long lo
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-constexpr int kMaxSpans = 4096;
+// Tile shapes: <CW columns, TH rows, THREADS>.  L = CW/32 columns per lane in the scan phase.
+template <int CW, int TH, int THREADS>
+struct TileCfg {
+    static constexpr int kL = CW / 32;
+    static constexpr int kPitch = CW + 4 * 32;               // 32 runs of L columns, 4 padding ints each
+    static constexpr int kWarps = THREADS / 32;
+    static constexpr int kRowBits = (TH <= 8) ? 3 : 6;
+    static constexpr int kWarpSpanCap = (TH <= 8) ? 32 * TH : 512;  // per-warp span list entries
+    static constexpr size_t smem_bytes() {
+        return sizeof(int) * TH * kPitch + sizeof(double) * 4 * THREADS + sizeof(float) * THREADS +
+               sizeof(unsigned short) * kWarpSpanCap * kWarps;
+    }
+};
 
-template <int CW, int TH>
-__global__ void __launch_bounds__(kThreads)
-raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
-              const PaintDev* __restrict__ paints, const double4* __restrict__ lines, const uint32_t* __restrict__ tile_offs,
-              const uint32_t* __restrict__ refs, unsigned long long* __restrict__ tile_state, uint32_t epoch,
-              uint32_t* __restrict__ ticket, const Status* __restrict__ status) {
-    constexpr int kPitch = CW + CW / 8;  // swizzled row pitch
-    constexpr int kRowBits = (TH <= 8) ? 3 : 6;
-    static_assert(TH <= 64 && CW % 128 == 0, "tile shape");
-    // dynamic shared memory (> 48 KB static limit): cells | piece constants | span list
+template <int CW, int TH, int THREADS, bool EVENODD, class Cfg>
+__device__ __forceinline__ void scan_rows(const JobDev& job, const PaintDev& s_paint, int* cells, const int* carry, const int* row_touched,
+                                          int row0, int row1, int cx0, int mode, int tid) {
+    constexpr int L = Cfg::kL;
+    constexpr int NQ = L / 4;  // 128-bit words per lane run
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wout = job.width_out;
+    const int bw = min(wout - cx0, CW);  // visible columns of this tile
+    for (int r = warp; r < row1 - row0; r += Cfg::kWarps) {
+        const int acc = carry[r];
+        int* bc = cells + r * Cfg::kPitch;
+        const int y = row0 + r;
+        if (row_touched[r]) {
+            int v[L];
+#pragma unroll
+            for (int i = 0; i < NQ; i++) {
+                const int4 q = *reinterpret_cast<const int4*>(bc + lane * (L + 4) + i * 4);
+                v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+            }
+#pragma unroll
+            for (int i = 1; i < L; i++) v[i] += v[i - 1];
+            int incl = v[L - 1];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += nb;
+            }
+            const int base = acc + incl - v[L - 1];
+#pragma unroll
+            for (int i = 0; i < NQ; i++) {
+                const float4 cv = make_float4(coverage_from_fixed<EVENODD>(base + v[4 * i]), coverage_from_fixed<EVENODD>(base + v[4 * i + 1]),
+                                              coverage_from_fixed<EVENODD>(base + v[4 * i + 2]), coverage_from_fixed<EVENODD>(base + v[4 * i + 3]));
+                *reinterpret_cast<float4*>(bc + lane * (L + 4) + i * 4) = cv;
+            }
+        } else {
+            const float c = coverage_from_fixed<EVENODD>(acc);  // no line touched this row of the tile: constant coverage
+            const float4 cv = make_float4(c, c, c, c);
+#pragma unroll
+            for (int i = 0; i < NQ; i++) *reinterpret_cast<float4*>(bc + lane * (L + 4) + i * 4) = cv;
+        }
+        __syncwarp();
+        // transposed read-back: lane l takes columns [128*i + 4l, +4): full 512 B coalesced 128-bit stores
+        if (mode != kModeFill) {
+            float* out = reinterpret_cast<float*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride + cx0;
+            const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+#pragma unroll
+            for (int i = 0; i < CW / 128; i++) {
+                const int col = i * 128 + lane * 4;
+                if (col < bw) {
+                    float4 cv = *reinterpret_cast<const float4*>(bc + swz<L>(col));
+                    if (mode == kModeCoverage) {  // mask_iter drops abs(alpha) < 1e-6 (src/rasterize.rs:348)
+                        if (cv.x < 1e-6f) cv.x = 0.f;
+                        if (cv.y < 1e-6f) cv.y = 0.f;
+                        if (cv.z < 1e-6f) cv.z = 0.f;
+                        if (cv.w < 1e-6f) cv.w = 0.f;
+                    }
+                    if (vec_ok && col + 3 < bw) {
+                        __stcs(reinterpret_cast<float4*>(out + col), cv);  // streaming store: written once, never re-read
+                    } else {
+                        out[col] = cv.x;
+                        if (col + 1 < bw) out[col + 1] = cv.y;
+                        if (col + 2 < bw) out[col + 2] = cv.z;
+                        if (col + 3 < bw) out[col + 3] = cv.w;
+                    }
+                }
+            }
+        } else {
+            float4* out = reinterpret_cast<float4*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride + cx0;
+            const float* covs = reinterpret_cast<const float*>(bc);
+            for (int px = lane; px < bw; px += 32) {  // consecutive lanes composite consecutive pixels (16 B each)
+                const float alpha = covs[swz<L>(px)];
+                if (alpha >= 1e-6f) {
+                    float4 color = (job.paint_index >= 0) ? paint_at(s_paint, cx0 + px, y) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    // with_alpha: self * (alpha as f32), src/color.rs:347-349
+                    color = make_float4(fmul(color.x, alpha), fmul(color.y, alpha), fmul(color.z, alpha), fmul(color.w, alpha));
+                    // blend_over: other + self * (1 - other.alpha), src/color.rs:342-344
+                    float4 dstc = out[px];
+                    const float k = fsub(1.0f, color.w);
+                    dstc = make_float4(fadd(color.x, fmul(dstc.x, k)), fadd(color.y, fmul(dstc.y, k)), fadd(color.z, fmul(dstc.z, k)),
+                                       fadd(color.w, fmul(dstc.w, k)));
+                    out[px] = dstc;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// `one_job`: the launch covers a single job whose descriptor travels in the kernel parameters (constant bank:
+// no dependent global loads before the tile can start).
+template <int CW, int TH, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first, const JobDev one_job,
+              const PaintDev* __restrict__ paints, const uint32_t* __restrict__ tile_offs, const double4* __restrict__ bin_lines,
+              unsigned long long* __restrict__ tile_state, uint32_t epoch, uint32_t* __restrict__ ticket,
+              const Status* __restrict__ status) {
+    using Cfg = TileCfg<CW, TH, THREADS>;
+    constexpr int L = Cfg::kL;
+    static_assert(TH <= 64 && CW % 128 == 0 && L % 4 == 0, "tile shape");
+    // dynamic shared memory: cells | piece constants | per-warp span lists
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int* cells = reinterpret_cast<int*>(smem_raw);
-    double* p_ax = reinterpret_cast<double*>(smem_raw + sizeof(int) * TH * kPitch);
-    double* p_ay = p_ax + kThreads;
-    double* p_by = p_ay + kThreads;
-    double* p_dxdy = p_by + kThreads;
-    float* p_dir = reinterpret_cast<float*>(p_dxdy + kThreads);
-    unsigned short* spans = reinterpret_cast<unsigned short*>(p_dir + kThreads);
+    double* p_ax = reinterpret_cast<double*>(smem_raw + sizeof(int) * TH * Cfg::kPitch);
+    double* p_ay = p_ax + THREADS;
+    double* p_by = p_ay + THREADS;
+    double* p_dxdy = p_by + THREADS;
+    float* p_dir = reinterpret_cast<float*>(p_dxdy + THREADS);
+    unsigned short* spans_all = reinterpret_cast<unsigned short*>(p_dir + THREADS);
     __shared__ int carry[TH];
     __shared__ int rowtot[TH];
     __shared__ int row_touched[TH];
     __shared__ uint32_t s_tile;
-    __shared__ int n_spans;
     __shared__ uint32_t s_job;
     __shared__ PaintDev s_paint;
 
-    if (status->lines_overflow | status->refs_overflow | status->nan_flag | status->depth_flag) return;
-
     const int tid = threadIdx.x;
-    if (tid == 0) {
-        // dynamic tile id: a tile only ever waits (carry look-back) on tiles with smaller ids, which have started
-        const uint32_t t = tile_first + atomicAdd(ticket, 1u);
-        s_tile = t;
-        s_job = job_first + find_job(n_jobs, t, [&](uint32_t k) { return jobs[job_first + k].tile_begin; });
-        n_spans = 0;
-    }
+    const int warp = tid >> 5, lane = tid & 31;
+    // dynamic tile id: a tile only ever waits (carry look-back) on tiles with smaller ids, which have started
+    uint32_t my_ticket = 0;
+    if (tid == 0) my_ticket = atomicAdd(ticket, 1u);
+    const uint32_t bad = status->lines_overflow | status->refs_overflow | status->nan_flag | status->depth_flag;
     if (tid < TH) { carry[tid] = 0; rowtot[tid] = 0; row_touched[tid] = 0; }
     {
-        int4 z = make_int4(0, 0, 0, 0);
+        const int4 z = make_int4(0, 0, 0, 0);
         int4* c4 = reinterpret_cast<int4*>(cells);
-        for (int i = tid; i < TH * kPitch / 4; i += kThreads) c4[i] = z;
+        for (int i = tid; i < TH * Cfg::kPitch / 4; i += THREADS) c4[i] = z;
+    }
+    if (tid == 0) {
+        const uint32_t t = tile_first + my_ticket;
+        s_tile = t;
+        s_job = (n_jobs == 1) ? job_first : job_first + find_job(n_jobs, t, [&](uint32_t k) { return jobs[job_first + k].tile_begin; });
     }
     __syncthreads();
+    if (bad) return;
     const uint32_t tile = s_tile;
-    const JobDev& job = jobs[s_job];
-    uint32_t lt = tile - job.tile_begin;
+    const JobDev& job = (n_jobs == 1) ? one_job : jobs[s_job];
+    const uint32_t lt = tile - job.tile_begin;
     const int band = (int)(lt / job.n_chunks);
     const int chunk = (int)(lt - (uint32_t)band * job.n_chunks);
     TileGeom g;
@@ -341,26 +446,30 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     g.wc = job.clamp_w;
     g.wci = (int)g.wc;
     g.tile_end = g.cx0 + min(CW, g.wci + 1 - g.cx0);  // columns that exist in the reference image (incl. overflow column)
-    g.pitch = kPitch;
+    g.pitch = Cfg::kPitch;
     const int row0 = g.row0, row1 = g.row1, cx0 = g.cx0;
     const double wc = g.wc;
     const int mode = job.mode;
-    const int rule = job.rule;
 
     if (mode == kModeFill && job.paint_index >= 0) {
         const int* src = reinterpret_cast<const int*>(&paints[job.paint_index]);
         int* dst = reinterpret_cast<int*>(&s_paint);
-        for (int i = tid; i < (int)(sizeof(PaintDev) / 4); i += kThreads) dst[i] = src[i];
+        for (int i = tid; i < (int)(sizeof(PaintDev) / 4); i += THREADS) dst[i] = src[i];
     }
 
-    // ---- phase 1: accumulate the band's lines, kThreads references per round ------------------------------
+    // ---- phase 1: accumulate the tile's lines.  Warps work independently: 32 lines per round per warp ------
+    // 1a: one line per lane — the reference's clipping, orientation and row range; the (piece,row) spans of the
+    //     32 lines are compacted into the warp's span list (warp prefix sum, no atomics)
+    // 1b: one lane per span — no row-loop divergence
+    unsigned short* spans = spans_all + warp * Cfg::kWarpSpanCap;
     const uint32_t rbeg = tile_offs[tile], rend = tile_offs[tile + 1];
-    for (uint32_t r0 = rbeg; r0 < rend; r0 += kThreads) {
-        // 1a: one reference per thread: the reference's clipping, orientation, row range; spans are appended to
-        //     a shared list so that 1b runs one lane per (piece,row) span with no row-loop divergence
-        const uint32_t r = r0 + tid;
+    for (uint32_t r0 = rbeg + warp * 32; r0 < rend; r0 += THREADS) {
+        const uint32_t r = r0 + lane;
+        Piece p;
+        p.cls = 0;
+        p.rb = p.re = 0;
         if (r < rend) {
-            const double4 l = lines[refs[r]];
+            const double4 l = bin_lines[r];
             double p0x = l.x, p0y = l.y, p1x = l.z, p1y = l.w;
             // src/rasterize.rs:370-387: lines crossing x == width
             if (p0x > wc || p1x > wc) {
@@ -383,45 +492,51 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
                     const double mx = (1.0 - t) * p0x + t * p1x;
                     const double my = (1.0 - t) * p0y + t * p1y;
                     // the outside part, folded onto x = 0, goes through the same function again in the reference;
-                    // rare (only lines crossing the left edge): done serially by this thread
+                    // rare (only lines crossing the left edge): done serially by this lane
                     if (p0x < 0.0) {
-                        if (mx <= 0.0) piece_serial(0.0, p0y, 0.0, my, g, cells, rowtot, row_touched);
-                        else piece_serial(0.0, p0y, mx, my, g, cells, rowtot, row_touched);
+                        if (mx <= 0.0) piece_serial<L>(0.0, p0y, 0.0, my, g, cells, rowtot, row_touched);
+                        else piece_serial<L>(0.0, p0y, mx, my, g, cells, rowtot, row_touched);
                         p0x = mx; p0y = my;
                     } else {
-                        if (mx <= 0.0) piece_serial(0.0, my, 0.0, p1y, g, cells, rowtot, row_touched);
-                        else piece_serial(mx, my, 0.0, p1y, g, cells, rowtot, row_touched);
+                        if (mx <= 0.0) piece_serial<L>(0.0, my, 0.0, p1y, g, cells, rowtot, row_touched);
+                        else piece_serial<L>(mx, my, 0.0, p1y, g, cells, rowtot, row_touched);
                         p1x = mx; p1y = my;
                     }
                 }
             }
-            const Piece p = classify_piece(p0x, p0y, p1x, p1y, g);
-            if (p.cls == 2) {
-                const int n = p.re - p.rb;
-                const int base = atomicAdd(&n_spans, n);
-                if (base + n <= kMaxSpans) {
-                    p_ax[tid] = p.ax; p_ay[tid] = p.ay; p_by[tid] = p.by; p_dxdy[tid] = p.dxdy; p_dir[tid] = p.dirf;
-                    for (int k = 0; k < n; k++) spans[base + k] = (unsigned short)((tid << kRowBits) | (p.rb + k - row0));
-                } else {  // span list full (only possible for TH = 64): do the rows here
-                    for (int y = p.rb; y < p.re; y++) span_row(p.ax, p.ay, p.by, p.dxdy, p.dirf, y, g, cells, rowtot, row_touched);
-                }
+            p = classify_piece(p0x, p0y, p1x, p1y, g);
+        }
+        int n = (p.cls == 2) ? p.re - p.rb : 0;
+        int incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int base = incl - n;
+        if (n > 0) {
+            if (base + n <= Cfg::kWarpSpanCap) {
+                p_ax[tid] = p.ax; p_ay[tid] = p.ay; p_by[tid] = p.by; p_dxdy[tid] = p.dxdy; p_dir[tid] = p.dirf;
+                for (int k = 0; k < n; k++) spans[base + k] = (unsigned short)((lane << Cfg::kRowBits) | (p.rb + k - row0));
+            } else {  // list full (only possible for TH = 64): do the rows here
+                for (int y = p.rb; y < p.re; y++) span_row<L>(p.ax, p.ay, p.by, p.dxdy, p.dirf, y, g, cells, rowtot, row_touched);
             }
         }
-        __syncthreads();
-        // 1b: one lane per span
-        const int ns = min(n_spans, kMaxSpans);
-        for (int i = tid; i < ns; i += kThreads) {
+        __syncwarp();
+        // lanes are in list order: everything before the first lane that did not fit is in the list
+        const unsigned nofit = __ballot_sync(0xffffffffu, n > 0 && base + n > Cfg::kWarpSpanCap);
+        const int ns = nofit ? __shfl_sync(0xffffffffu, base, __ffs(nofit) - 1) : total;
+        const int wbase = warp * 32;
+        for (int i = lane; i < ns; i += 32) {
             const int e = spans[i];
-            const int slot = e >> kRowBits;
-            const int y = row0 + (e & ((1 << kRowBits) - 1));
-            span_row(p_ax[slot], p_ay[slot], p_by[slot], p_dxdy[slot], p_dir[slot], y, g, cells, rowtot, row_touched);
+            const int slot = wbase + (e >> Cfg::kRowBits);
+            const int y = row0 + (e & ((1 << Cfg::kRowBits) - 1));
+            span_row<L>(p_ax[slot], p_ay[slot], p_by[slot], p_dxdy[slot], p_dir[slot], y, g, cells, rowtot, row_touched);
         }
-        __syncthreads();
-        if (tid == 0) n_spans = 0;
-        // (the next round's 1a only appends after reading n_spans == 0: order it)
-        __syncthreads();
+        __syncwarp();
     }
-    if (rbeg == rend) __syncthreads();
+    __syncthreads();
 
     // ---- carry-in: decoupled look-back over the tiles to the left in this band --------------------------------
     // Every tile publishes its per-row totals (flag AGG), sums its predecessors' totals until it meets an
@@ -452,112 +567,11 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     }
 
     // ---- phase 2: per-row scan, fill rule, store / composite --------------------------------------------
-    // A warp takes a row; lane l owns 32 consecutive columns per 1024-column block: serial prefix in registers,
-    // ONE warp scan of the 32 lane totals per block, coverage written back to shared memory in place (as floats)
-    // and read back transposed so that global stores are full 512 B coalesced 128-bit accesses.
-    const int warp = tid >> 5, lane = tid & 31;
-    const int wout = job.width_out;
-    const int wrem = min(wout - cx0, CW);  // visible columns of this tile
-    for (int r = warp; r < row1 - row0; r += kWarps) {
-        int acc = carry[r];
-        int* rowc = cells + r * kPitch;
-        const int y = row0 + r;
-        const bool touched = row_touched[r] != 0;
-        for (int blk = 0; blk * 1024 < wrem; blk++) {
-            int* bc = rowc + blk * (1024 + 128);  // swz(blk*1024)
-            if constexpr (CW >= 1024) {
-                if (touched) {
-                    int v[32];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int4 q = *reinterpret_cast<const int4*>(bc + lane * 36 + i * 4);
-                        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
-                    }
-#pragma unroll
-                    for (int i = 1; i < 32; i++) v[i] += v[i - 1];
-                    int incl = v[31];
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int nb = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += nb;
-                    }
-                    const int base = acc + incl - v[31];
-                    acc += __shfl_sync(0xffffffffu, incl, 31);
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        float4 cv = make_float4(coverage_from_fixed(base + v[4 * i], rule), coverage_from_fixed(base + v[4 * i + 1], rule),
-                                                coverage_from_fixed(base + v[4 * i + 2], rule), coverage_from_fixed(base + v[4 * i + 3], rule));
-                        *reinterpret_cast<float4*>(bc + lane * 36 + i * 4) = cv;
-                    }
-                } else {
-                    const float c = coverage_from_fixed(acc, rule);
-                    const float4 cv = make_float4(c, c, c, c);
-#pragma unroll
-                    for (int i = 0; i < 8; i++) *reinterpret_cast<float4*>(bc + lane * 36 + i * 4) = cv;
-                }
-            } else {
-                // narrow tiles (CW = 128): 4 columns per lane, shuffle scan
-                const int col = lane * 4;
-                const int4 q = *reinterpret_cast<const int4*>(bc + swz(col));
-                const int p0 = q.x, p1 = p0 + q.y, p2 = p1 + q.z, p3 = p2 + q.w;
-                int incl = p3;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int nb = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += nb;
-                }
-                const int base = acc + incl - p3;
-                acc += __shfl_sync(0xffffffffu, incl, 31);
-                *reinterpret_cast<float4*>(bc + swz(col)) = make_float4(coverage_from_fixed(base + p0, rule), coverage_from_fixed(base + p1, rule),
-                                                                          coverage_from_fixed(base + p2, rule), coverage_from_fixed(base + p3, rule));
-            }
-            __syncwarp();
-            // transposed read-back: lane l takes columns [128*i + 4l, +4) of the block
-            const int bw = min(wrem - blk * 1024, 1024);  // visible columns of this block
-            if (mode != kModeFill) {
-                float* out = reinterpret_cast<float*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride + cx0 + blk * 1024;
-                const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-#pragma unroll
-                for (int i = 0; i < (CW >= 1024 ? 8 : 1); i++) {
-                    const int col = i * 128 + lane * 4;
-                    if (col >= bw) break;
-                    float4 cv = *reinterpret_cast<const float4*>(bc + swz(col));
-                    if (mode == kModeCoverage) {  // mask_iter drops abs(alpha) < 1e-6 (src/rasterize.rs:348)
-                        if (cv.x < 1e-6f) cv.x = 0.f;
-                        if (cv.y < 1e-6f) cv.y = 0.f;
-                        if (cv.z < 1e-6f) cv.z = 0.f;
-                        if (cv.w < 1e-6f) cv.w = 0.f;
-                    }
-                    if (vec_ok && col + 3 < bw) {
-                        __stcs(reinterpret_cast<float4*>(out + col), cv);  // streaming 128-bit store, written once
-                    } else {
-                        if (col < bw) out[col] = cv.x;
-                        if (col + 1 < bw) out[col + 1] = cv.y;
-                        if (col + 2 < bw) out[col + 2] = cv.z;
-                        if (col + 3 < bw) out[col + 3] = cv.w;
-                    }
-                }
-            } else {
-                float4* out = reinterpret_cast<float4*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride + cx0 + blk * 1024;
-                const float* covs = reinterpret_cast<const float*>(bc);
-                for (int px = lane; px < bw; px += 32) {  // consecutive lanes composite consecutive pixels (16 B each)
-                    const float alpha = covs[swz(px)];
-                    if (alpha >= 1e-6f) {
-                        float4 color = (job.paint_index >= 0) ? paint_at(s_paint, cx0 + blk * 1024 + px, y) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        // with_alpha: self * (alpha as f32), src/color.rs:347-349
-                        color = make_float4(fmul(color.x, alpha), fmul(color.y, alpha), fmul(color.z, alpha), fmul(color.w, alpha));
-                        // blend_over: other + self * (1 - other.alpha), src/color.rs:342-344
-                        float4 dstc = out[px];
-                        const float k = fsub(1.0f, color.w);
-                        dstc = make_float4(fadd(color.x, fmul(dstc.x, k)), fadd(color.y, fmul(dstc.y, k)), fadd(color.z, fmul(dstc.z, k)),
-                                           fadd(color.w, fmul(dstc.w, k)));
-                        out[px] = dstc;
-                    }
-                }
-            }
-            __syncwarp();
-        }
-    }
+    // A warp takes a row; lane l owns L consecutive columns: serial prefix in registers, ONE warp scan of the 32
+    // lane totals, coverage written back to shared memory in place (as floats) and read back transposed so that
+    // global stores are full 512 B coalesced 128-bit accesses.
+    if (job.rule == 1) scan_rows<CW, TH, THREADS, true, Cfg>(job, s_paint, cells, carry, row_touched, row0, row1, cx0, mode, tid);
+    else scan_rows<CW, TH, THREADS, false, Cfg>(job, s_paint, cells, carry, row_touched, row0, row1, cx0, mode, tid);
 }
 
 // `From<LinColor> for RGBA`, src/color.rs:164-175 with the x86 l2s polynomial; `as u8` saturates
@@ -587,40 +601,38 @@ __global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restri
 
 }  // namespace
 
-TileShape raster_tile_shape(int variant) {
-    if (variant == 1) return TileShape{128, 64};
-    return TileShape{1024, 8};
-}
 
-template <int CW, int TH>
-constexpr size_t raster_smem_bytes() {
-    return sizeof(int) * TH * (CW + CW / 8) + sizeof(double) * 4 * kThreads + sizeof(float) * kThreads + sizeof(unsigned short) * kMaxSpans;
-}
-
-template <int CW, int TH>
-static void launch_raster_t(const JobDev* jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first, uint32_t n_tiles,
-                            const PaintDev* paints, const double4* lines, const uint32_t* tile_offs, const uint32_t* refs,
+template <int CW, int TH, int THREADS>
+static void launch_raster_t(const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
+                            uint32_t n_tiles, const PaintDev* paints, const uint32_t* tile_offs, const double4* bin_lines,
                             unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, cudaStream_t s) {
-    constexpr size_t smem = raster_smem_bytes<CW, TH>();
+    constexpr size_t smem = TileCfg<CW, TH, THREADS>::smem_bytes();
     static bool configured[64] = {};  // per template instance and per device: the attribute belongs to the device's function
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaFuncSetAttribute(raster_kernel<CW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(raster_kernel<CW, TH, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured[dev] = true;
     }
-    raster_kernel<CW, TH><<<n_tiles, kThreads, smem, s>>>(jobs, n_jobs, job_first, tile_first, paints, lines, tile_offs, refs, tile_state,
-                                                          epoch, ticket, status);
+    raster_kernel<CW, TH, THREADS><<<n_tiles, THREADS, smem, s>>>(jobs, n_jobs, job_first, tile_first, h_jobs[job_first], paints, tile_offs,
+                                                                  bin_lines, tile_state, epoch, ticket, status);
 }
 
-void launch_raster(int variant, const JobDev* jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first, uint32_t n_tiles,
-                   const PaintDev* paints, const double4* lines, const uint32_t* tile_offs, const uint32_t* refs,
+TileShape raster_tile_shape(int variant) {
+    if (variant == 1) return TileShape{128, 64};
+    return TileShape{512, 8};
+}
+
+void launch_raster(int variant, const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
+                   uint32_t n_tiles, const PaintDev* paints, const uint32_t* tile_offs, const double4* bin_lines,
                    unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, cudaStream_t s) {
     if (n_tiles == 0) return;
     if (variant == 1)
-        launch_raster_t<128, 64>(jobs, n_jobs, job_first, tile_first, n_tiles, paints, lines, tile_offs, refs, tile_state, epoch, ticket, status, s);
+        launch_raster_t<128, 64, 256>(jobs, h_jobs, n_jobs, job_first, tile_first, n_tiles, paints, tile_offs, bin_lines, tile_state, epoch,
+                                      ticket, status, s);
     else
-        launch_raster_t<1024, 8>(jobs, n_jobs, job_first, tile_first, n_tiles, paints, lines, tile_offs, refs, tile_state, epoch, ticket, status, s);
+        launch_raster_t<512, 8, 128>(jobs, h_jobs, n_jobs, job_first, tile_first, n_tiles, paints, tile_offs, bin_lines, tile_state, epoch,
+                                     ticket, status, s);
 }
 
 void launch_to_rgba8(const float4* lin, uchar4* out, size_t n, cudaStream_t s) {

@@ -7,7 +7,7 @@
 //   slot_offs   u32[8*items+1]               exclusive scan of slot_counts; last = total lines
 //   lines       double4[n_lines]             flattened lines in the reference's order (x0,y0,x1,y1)
 //   tile_counts u32[tiles+1] / tile_offs     per (job, band, chunk) tile reference counts / exclusive scan
-//   refs        u32[n_refs]                  line indices grouped by tile (order inside a tile is
+//   bin_lines   double4[n_refs]              the lines of every tile, grouped by tile (order inside a tile is
 //                                            irrelevant: accumulation is fixed-point, hence associative)
 //   tile_state  u64[tiles*8]                 per-row tile totals / inclusive prefixes for the carry look-back
 //   canvases    caller-owned                 f32 coverage or f32x4 LinColor
@@ -87,15 +87,16 @@ void launch_flatten_fused(const JobDev* jobs, uint32_t n_jobs, uint32_t total_it
 void launch_bin_count(const JobDev* jobs, uint32_t n_jobs, const uint32_t* slot_offs, uint32_t total_slots, const uint32_t* line_job,
                       const double4* lines, uint32_t* tile_counts, int band_rows, int chunk_cols, Status* status, cudaStream_t s);
 void launch_bin_fill(const JobDev* jobs, uint32_t n_jobs, const uint32_t* slot_offs, uint32_t total_slots, const uint32_t* line_job,
-                     const double4* lines, const uint32_t* tile_offs, uint32_t total_tiles, uint32_t* tile_cursor, uint32_t* refs,
+                     const double4* lines, const uint32_t* tile_offs, uint32_t total_tiles, uint32_t* tile_cursor, double4* bin_lines,
                      uint32_t refs_cap, int band_rows, int chunk_cols, Status* status, cudaStream_t s);
 // tile geometry of the raster kernel variants
 struct TileShape { int cw, th; };
 TileShape raster_tile_shape(int variant);
 // `ticket` is a zeroed device counter private to this launch (dynamic tile ids for the carry look-back);
 // `tile_state` holds kMaxBandRows u64 words per tile, validated by `epoch` (no clearing between batches).
-void launch_raster(int variant, const JobDev* jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first, uint32_t n_tiles,
-                   const PaintDev* paints, const double4* lines, const uint32_t* tile_offs, const uint32_t* refs,
+// `h_jobs` is the host copy of the job table: single-job launches pass their descriptor by value.
+void launch_raster(int variant, const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
+                   uint32_t n_tiles, const PaintDev* paints, const uint32_t* tile_offs, const double4* bin_lines,
                    unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, cudaStream_t s);
 void launch_to_rgba8(const float4* lin, uchar4* out, size_t n, cudaStream_t s);
 void launch_fill_color(float4* lin, size_t n, float4 color, cudaStream_t s);
