@@ -9,7 +9,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "librasterize_b200.so"
-SOURCES = ["flatten.cu", "scan.cu", "bin.cu", "raster.cu", "context.cu"]
+SOURCES = ["flatten.cu", "scan.cu", "bin.cu", "raster.cu", "small.cu", "context.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
@@ -52,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if verbose:
         print("\n".join(log))
     objs = [str(objdir / (s + ".o")) for s in SOURCES]
-    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-Xcompiler", "-pthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

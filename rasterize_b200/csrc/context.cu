@@ -3,12 +3,15 @@
 // CUDA kernels or fails.
 #include "../../include/rasterize_b200.h"
 #include "rgpu_internal.cuh"
+#include "host_pool.hpp"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace rgpu;
@@ -76,6 +79,9 @@ struct rgpu_ctx {
     // last submission (for status / retry)
     uint64_t need_lines = 0, need_refs = 0;
     uint32_t last_total_slots = 0;
+    // host-side result pipeline (chunked D2H overlapped with threaded widening into the caller's image)
+    std::unique_ptr<rgpu::HostPool> pool;
+    std::vector<cudaEvent_t> chunk_ev;
     // optional stage timing
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -280,6 +286,7 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     int last_paint_index = -1;
     const rgpu_job* last_paint_job = nullptr;
     uint32_t n_live = 0;
+    bool all_small = true;
     for (size_t j = 0; j < n_jobs; j++) {
         const rgpu_job& in = jobs[j];
         if (!in.path) return fail(ctx, RGPU_ERR_INVALID, "job.path is NULL");
@@ -326,11 +333,46 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         band_acc += d.n_bands;
         tile_acc += d.n_bands * d.n_chunks;
         est_lines += (uint64_t)in.path->n_curves * 24 + (in.path->n_items - in.path->n_curves) + 16;
+        all_small = all_small && small_canvas_eligible(in.width, in.height, in.mode);
         ctx->h_jobs[n_live++] = d;
     }
     ctx->need_lines = ctx->need_refs = 0;
     if (n_live == 0) {
         std::memset(ctx->h_status, 0, sizeof(Status));
+        return RGPU_OK;
+    }
+    if (all_small && !ordered_lines) {
+        // every canvas fits one CTA's shared memory: a single fused kernel per launch, nothing else touches HBM
+        if ((rc = ensure_dev(ctx, ctx->jobs, sizeof(JobDev) * n_live))) return rc;
+        if ((rc = ensure_dev(ctx, ctx->paints, sizeof(PaintDev) * std::max<uint32_t>(n_paints, 1)))) return rc;
+        cudaStream_t s = ctx->stream;
+        JobDev* d_jobs = static_cast<JobDev*>(ctx->jobs.p);
+        PaintDev* d_paints = static_cast<PaintDev*>(ctx->paints.p);
+        Status* d_status = static_cast<Status*>(ctx->status.p);
+        CK(ctx, cudaMemcpyAsync(d_jobs, ctx->h_jobs, sizeof(JobDev) * n_live, cudaMemcpyHostToDevice, s));
+        if (n_paints) CK(ctx, cudaMemcpyAsync(d_paints, ctx->h_paints, sizeof(PaintDev) * n_paints, cudaMemcpyHostToDevice, s));
+        CK(ctx, cudaMemsetAsync(d_status, 0, sizeof(Status), s));
+        const double thr = 16.0 * ctx->flatness * ctx->flatness;  // PathFlattenIter::new, src/path.rs:749
+        const bool prof = ctx->profiling;
+        ctx->ev_valid = false;
+        if (prof) {
+            CK(ctx, cudaEventRecord(ctx->ev[0], s));
+            CK(ctx, cudaEventRecord(ctx->ev[1], s));
+            CK(ctx, cudaEventRecord(ctx->ev[2], s));
+        }
+        if (flags & RGPU_BATCH_INDEPENDENT) {
+            launch_small_canvas(d_jobs, 0, n_live, d_paints, thr, d_status, s);
+            ctx->n_launches += 1;
+        } else {
+            for (uint32_t j = 0; j < n_live; j++) launch_small_canvas(d_jobs, j, 1, d_paints, thr, d_status, s);
+            ctx->n_launches += n_live;
+        }
+        if (prof) {
+            CK(ctx, cudaEventRecord(ctx->ev[3], s));
+            ctx->ev_valid = true;
+        }
+        CK(ctx, cudaMemcpyAsync(ctx->h_status, d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaGetLastError());
         return RGPU_OK;
     }
     uint64_t total_slots64 = (uint64_t)item_acc * kSlotsPerItem + 1;
@@ -539,6 +581,8 @@ void rgpu_destroy(rgpu_ctx* ctx) {
     if (ctx->h_paints) cudaFreeHost(ctx->h_paints);
     for (int i = 0; i < 4; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
+    ctx->pool.reset();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -781,6 +825,55 @@ int rgpu_coverage_f32(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], 
     return RGPU_OK;
 }
 
+// f32 device image -> strided f64 host image: the D2H copy is cut into row chunks; as soon as a chunk has landed in
+// pinned staging the pool widens it into the caller's image while the next chunks are still crossing PCIe.  The
+// caller's memory may be pageable (it is only written by host threads).
+static int download_widen(rgpu_ctx* ctx, const float* d_img, size_t w, size_t h, double* dst, rgpu_shape shape) {
+    int rc;
+    if ((rc = ensure_stage(ctx, sizeof(float) * w * h))) return rc;
+    if (!ctx->pool) {
+        unsigned n = std::thread::hardware_concurrency();
+        ctx->pool.reset(new rgpu::HostPool(std::max(1u, std::min(n ? n : 4u, 32u))));
+    }
+    float* stage = static_cast<float*>(ctx->h_stage);
+    const size_t target_rows = std::max<size_t>(1, (size_t)(4u << 20) / (w * sizeof(float)));  // ~4 MB per chunk
+    const size_t n_chunks = (h + target_rows - 1) / target_rows;
+    while (ctx->chunk_ev.size() < n_chunks) {
+        cudaEvent_t e;
+        CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->chunk_ev.push_back(e);
+    }
+    for (size_t c = 0; c < n_chunks; c++) {
+        const size_t r0 = c * target_rows, r1 = std::min(h, r0 + target_rows);
+        CK(ctx, cudaMemcpyAsync(stage + r0 * w, d_img + r0 * w, sizeof(float) * w * (r1 - r0), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaEventRecord(ctx->chunk_ev[c], ctx->stream));
+    }
+    const unsigned workers = ctx->pool->size();
+    const size_t rs = shape.row_stride, cs = shape.col_stride;
+    for (size_t c = 0; c < n_chunks; c++) {
+        const size_t r0 = c * target_rows, r1 = std::min(h, r0 + target_rows);
+        CK(ctx, cudaEventSynchronize(ctx->chunk_ev[c]));
+        const size_t rows = r1 - r0;
+        const size_t parts = std::min<size_t>(workers, rows);
+        for (size_t p = 0; p < parts; p++) {
+            const size_t a = r0 + rows * p / parts, b = r0 + rows * (p + 1) / parts;
+            ctx->pool->submit([=] {
+                for (size_t y = a; y < b; y++) {
+                    const float* srow = stage + y * w;
+                    double* drow = dst + y * rs;
+                    if (cs == 1) {
+                        for (size_t x = 0; x < w; x++) drow[x] = (double)srow[x];
+                    } else {
+                        for (size_t x = 0; x < w; x++) drow[x * cs] = (double)srow[x];
+                    }
+                }
+            });
+        }
+    }
+    ctx->pool->wait();
+    return RGPU_OK;
+}
+
 int rgpu_mask(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill_rule, double* img, rgpu_shape shape) {
     if (!ctx || !tr) return RGPU_ERR_INVALID;
     CK(ctx, cudaSetDevice(ctx->device));
@@ -790,25 +883,7 @@ int rgpu_mask(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill
     float* d = nullptr;
     int rc = mask_to_device(ctx, path, tr, fill_rule, RGPU_JOB_MASK, w, h, &d);
     if (rc) return rc;
-    // widen on the device, then one strided D2H straight into the caller's image
-    if ((rc = ensure_dev(ctx, ctx->img_f64, sizeof(double) * w * h))) return rc;
-    double* d64 = static_cast<double*>(ctx->img_f64.p);
-    launch_f32_to_f64(d, d64, w * h, ctx->stream);
-    ctx->n_launches++;
-    double* dst = img + shape.start;
-    if (shape.col_stride == 1) {
-        CK(ctx, cudaMemcpy2DAsync(dst, shape.row_stride * sizeof(double), d64, w * sizeof(double), w * sizeof(double), h,
-                                  cudaMemcpyDeviceToHost, ctx->stream));
-        CK(ctx, cudaStreamSynchronize(ctx->stream));
-    } else {
-        if ((rc = ensure_stage(ctx, sizeof(double) * w * h))) return rc;
-        CK(ctx, cudaMemcpyAsync(ctx->h_stage, d64, sizeof(double) * w * h, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(ctx, cudaStreamSynchronize(ctx->stream));
-        const double* src = static_cast<const double*>(ctx->h_stage);
-        for (size_t y = 0; y < h; y++)
-            for (size_t x = 0; x < w; x++) dst[y * shape.row_stride + x * shape.col_stride] = src[y * w + x];
-    }
-    return RGPU_OK;
+    return download_widen(ctx, d, w, h, img + shape.start, shape);
 }
 
 int rgpu_mask_iter(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], size_t width, size_t height, int fill_rule,

@@ -17,274 +17,13 @@
 // telescope: the cells of a span that fall in one tile sum to (rounded coverage at the tile's last column) -
 // (rounded coverage left of its first column), so the per-row totals the tiles of a band exchange through the
 // carry look-back are exact integers and the result is bit-identical from run to run.
-#include "rgpu_internal.cuh"
+#include "raster_device.cuh"
 
 namespace rgpu {
 
 namespace {
 
-constexpr double kEps = 2.220446049250313e-16;
-
-// ---- colour maths (f32, never contracted: the reference uses plain SSE mul/add) -------------------------
-__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
-
-// src/simd/x86.rs:217-244, one lane
-__device__ __forceinline__ float s2l_lane(float v) {
-    float x1 = fsub(fmul(2.0843103538116825f, v), 1.0843103538116827f);
-    float x2 = fmul(x1, x1);
-    float x3 = fmul(x2, x1);
-    float high = fadd(fadd(fadd(0.23361048543711943f, fmul(0.4665843122387033f, x1)), fmul(0.26901741378006355f, x2)),
-                      fmul(0.031661580753065945f, x3));
-    return (v <= 0.04045f) ? fmul(v, 0.07739938080495357f) : high;
-}
-// src/simd/x86.rs:197-214, one lane
-__device__ __forceinline__ float l2s_lane(float x0) {
-    float x1 = __fsqrt_rn(x0);
-    float x2 = __fsqrt_rn(x1);
-    float x3 = __fsqrt_rn(x2);
-    float high = fsub(fadd(fadd(fmul(-0.01848558f, x0), fmul(0.6445592f, x1)), fmul(0.70994765f, x2)), fmul(0.33605254f, x3));
-    return (x0 <= 0.0031308f) ? fmul(x0, 12.92f) : high;
-}
-// LinColor::unmultiply, src/color.rs:308-317
-__device__ __forceinline__ float4 unmultiply(float4 c) {
-    if (c.w <= 1e-6f) return make_float4(0.f, 0.f, 0.f, 0.f);
-    return make_float4(__fdiv_rn(c.x, c.w), __fdiv_rn(c.y, c.w), __fdiv_rn(c.z, c.w), __fdiv_rn(c.w, c.w));
-}
-// LinColor::into_linear, src/color.rs:330-332 (all four lanes go through the polynomial, alpha included)
-__device__ __forceinline__ float4 into_linear(float4 c) {
-    float4 u = unmultiply(c);
-    float a = c.w;
-    return make_float4(fmul(s2l_lane(u.x), a), fmul(s2l_lane(u.y), a), fmul(s2l_lane(u.z), a), fmul(s2l_lane(u.w), a));
-}
-
-// f64::rem_euclid
-__device__ __forceinline__ double rem_euclid(double x, double rhs) {
-    double r = fmod(x, rhs);
-    return r < 0.0 ? r + fabs(rhs) : r;
-}
-
-// GradStops::at, src/grad.rs:116-139
-__device__ float4 stops_at(const PaintDev& P, double t) {
-    int lo = 0, hi = P.n_stops;
-    while (lo < hi) {
-        int mid = lo + ((hi - lo) >> 1);
-        if (P.stop_pos[mid] < t) lo = mid + 1; else hi = mid;
-    }
-    int index = lo, size = P.n_stops;
-    if (index == 0) return make_float4(P.stop_col[0][0], P.stop_col[0][1], P.stop_col[0][2], P.stop_col[0][3]);
-    if (index == size)
-        return make_float4(P.stop_col[size - 1][0], P.stop_col[size - 1][1], P.stop_col[size - 1][2], P.stop_col[size - 1][3]);
-    double pos0 = P.stop_pos[index - 1], pos1 = P.stop_pos[index];
-    float r = (float)((t - pos0) / (pos1 - pos0));
-    float ir = fsub(1.0f, r);
-    const float* c0 = P.stop_col[index - 1];
-    const float* c1 = P.stop_col[index];
-    // lerp: other * t + self * (1 - t), src/color.rs:352-354
-    return make_float4(fadd(fmul(c1[0], r), fmul(c0[0], ir)), fadd(fmul(c1[1], r), fmul(c0[1], ir)),
-                       fadd(fmul(c1[2], r), fmul(c0[2], ir)), fadd(fmul(c1[3], r), fmul(c0[3], ir)));
-}
-
-// utils::quadratic_solve + GradRadial::offset root selection, src/utils.rs:205-231, src/grad.rs:361-396
-__device__ bool radial_offset(const PaintDev& P, double px, double py, double& out) {
-    double cdx = __dsub_rn(P.p0x, P.p1x), cdy = __dsub_rn(P.p0y, P.p1y);
-    double pdx = __dsub_rn(px, P.p1x), pdy = __dsub_rn(py, P.p1y);
-    double rd = __dsub_rn(P.r0, P.r1);
-    double a = __dsub_rn(__dadd_rn(__dmul_rn(cdx, cdx), __dmul_rn(cdy, cdy)), __dmul_rn(rd, rd));
-    double b = __dmul_rn(-2.0, __dadd_rn(__dadd_rn(__dmul_rn(cdx, pdx), __dmul_rn(cdy, pdy)), __dmul_rn(P.r1, rd)));
-    double c = __dsub_rn(__dadd_rn(__dmul_rn(pdx, pdx), __dmul_rn(pdy, pdy)), __dmul_rn(P.r1, P.r1));
-    if (fabs(a) < kEps) {
-        if (fabs(b) > kEps) { out = __ddiv_rn(-c, b); return true; }
-        return false;
-    }
-    double disc = __dsub_rn(__dmul_rn(b, b), __dmul_rn(__dmul_rn(4.0, a), c));
-    if (fabs(disc) < kEps) { out = __ddiv_rn(-b, __dmul_rn(2.0, a)); return true; }
-    if (disc > 0.0) {
-        double sq = __dsqrt_rn(disc);
-        double t0, t1;
-        if (b >= 0.0) {
-            double mul = __dsub_rn(-b, sq);
-            t0 = __ddiv_rn(mul, __dmul_rn(2.0, a));
-            t1 = __ddiv_rn(__dmul_rn(2.0, c), mul);
-        } else {
-            double mul = __dadd_rn(-b, sq);
-            t0 = __ddiv_rn(__dmul_rn(2.0, c), mul);
-            t1 = __ddiv_rn(mul, __dmul_rn(2.0, a));
-        }
-        out = isnan(t0) ? t1 : (isnan(t1) ? t0 : fmax(t0, t1));
-        return true;
-    }
-    return false;
-}
-
-// Paint::at for a pixel centre, after pixel_tr (src/rasterize.rs:93-96)
-__device__ float4 paint_at(const PaintDev& P, int x, int y) {
-    if (P.kind == 0) return make_float4(P.solid[0], P.solid[1], P.solid[2], P.solid[3]);
-    double fx = (double)x + 0.5, fy = (double)y + 0.5;
-    const double* m = P.pixel_tr;
-    double px = __dadd_rn(__dadd_rn(__dmul_rn(fx, m[0]), __dmul_rn(fy, m[1])), m[2]);
-    double py = __dadd_rn(__dadd_rn(__dmul_rn(fx, m[3]), __dmul_rn(fy, m[4])), m[5]);
-    double t;
-    if (P.kind == 1) {
-        // (point - start).dot(dir), src/grad.rs:204
-        t = __dadd_rn(__dmul_rn(__dsub_rn(px, P.p0x), P.dirx), __dmul_rn(__dsub_rn(py, P.p0y), P.diry));
-    } else {
-        if (!radial_offset(P, px, py, t)) return make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (P.spread == 1) t = rem_euclid(t, 1.0);
-    else if (P.spread == 2) t = fabs(rem_euclid(t + 1.0, 2.0) - 1.0);
-    float4 c = stops_at(P, t);
-    return P.linear_colors ? c : into_linear(c);
-}
-
-// ---- coverage from the fixed-point winding ---------------------------------------------------------------
-// NonZero: min(|w|, 1) (the reference's `value < 1e-6 -> 0` only matters to mask_iter's pixel dropping, which
-// the COVERAGE / FILL paths apply themselves; below 1e-6 the two differ by < 1e-6).  EvenOdd is exact in integers.
-template <bool EVENODD>
-__device__ __forceinline__ float coverage_from_fixed(int acc) {
-    constexpr float kInv = 1.0f / 16777216.0f;
-    if (EVENODD) {
-        // abs(((w + 1) rem_euclid 2) - 1)
-        const int t = (acc + kFixOne) & (2 * kFixOne - 1);
-        return fabsf((float)(t - kFixOne)) * kInv;
-    }
-    return fminf(fabsf((float)acc) * kInv, 1.0f);
-}
-
-// ---- shared-memory cell layout --------------------------------------------------------------------------
-// In the scan phase lane l owns L = CW/32 consecutive columns of a row.  Cell (row r, tile column x) lives at
-// r*pitch + swz<L>(x), swz<L>(x) = x + 4*(x/L): every run of L columns is followed by 4 padding ints, so the
-// 128-bit accesses of 8 consecutive lanes (stride L+4 ints) fall on distinct bank quads — conflict-free both for
-// the per-lane runs and (up to one 2-way pair for L = 16) for the transposed read-back used for coalesced stores.
-template <int L>
-__device__ __forceinline__ int swz(int x) { return x + ((x / L) << 2); }
-
-__device__ __forceinline__ int to_fixed_f(float v) { return __float2int_rn(v * 16777216.0f); }
-
-struct TileGeom {
-    int row0, row1;   // canvas rows [row0, row1) of this band
-    int cx0;          // first canvas column of the tile
-    int tile_end;     // cx0 + number of reference columns in the tile (incl. the overflow column)
-    int pitch;
-    double wc;        // reference `width` (= img.width - 1)
-    int wci;
-};
-
-// One (piece, row) span: the body of the reference's row loop (src/rasterize.rs:421-469) for canvas row y.
-// (ax,ay) is the piece's upper end (ay < by), dirf = +-1.  Pixel coverages (running sums of the reference's
-// deltas) are rounded to Q7.24 and the differences of consecutive rounded coverages are added to the cells of
-// THIS tile only; their sum (a telescoping difference) goes to the row's tile total, from which the tiles to the
-// right derive their carry-in.  Parts of the span in other tiles are added by those tiles (2-D bins).
-template <int L>
-__device__ __forceinline__ void span_row(double ax, double ay, double by, double dxdy, float dirf, int y, const TileGeom& g,
-                                         int* __restrict__ cells, int* __restrict__ rowtot, int* __restrict__ row_touched) {
-    const double yt = fmax((double)y, ay);
-    const double dy = fmin((double)(y + 1), by) - yt;
-    const double x = ax + (yt - ay) * dxdy;  // the reference accumulates x row by row; this differs by rounding only
-    const double xn = x + dxdy * dy;
-    const double x0 = fmin(x, xn), x1 = fmax(x, xn);
-    const double x0_floor = fmax(floor(x0), 0.0);
-    const double x1_ceil = fmin(ceil(x1), g.wc);
-    const int x0i = min(max((int)x0_floor, 0), g.wci);
-    const int x1i = min(max((int)x1_ceil, 0), g.wci);
-    if (x0i >= g.tile_end) return;  // this row's span is right of the tile
-    const int r = y - g.row0;
-    const float d = dirf * (float)dy;
-    const int fd = to_fixed_f(d);
-    const bool narrow = x1i <= x0i + 1;
-    const int last = narrow ? x0i + 1 : x1i;  // last column that receives a delta
-    if (last < g.cx0) return;                 // this row's span is left of the tile: it arrives through the look-back
-    // Positions stay f64 (f32 ulp at x ~ 4096 would already exceed the 1e-4 budget); the fractional parts are in
-    // [0,1] and the area polynomials are evaluated in f32 (error ~1e-7 of a pixel).
-    float c0, sf = 0.f, a1 = 0.f, am = 0.f;
-    const int n = x1i - x0i;
-    if (narrow) {
-        c0 = 1.0f - (float)(0.5 * (x + xn) - x0_floor);  // 1 - xmf, src/rasterize.rs:439
-    } else {
-        sf = 1.0f / (float)(x1 - x0);  // src/rasterize.rs:446-450
-        const float x0f = (float)(x0 - x0_floor);
-        const float x1f = (float)(x1 - x1_ceil + 1.0);
-        c0 = 0.5f * sf * (1.0f - x0f) * (1.0f - x0f);
-        am = 0.5f * sf * x1f * x1f;
-        a1 = sf * (1.5f - x0f);
-    }
-    // coverage (as a fraction of d) of pixel x0i + j == running sum of the reference's deltas
-    auto cov = [&](int j) -> float {
-        if (j <= 0) return j == 0 ? c0 : 0.0f;
-        if (narrow || j >= n) return 1.0f;
-        if (j == n - 1) return 1.0f - am;
-        return a1 + (float)(j - 1) * sf;
-    };
-    const int kb = max(x0i, g.cx0);
-    const int ke = min(last, g.tile_end - 1);
-    const int first = (kb > x0i) ? to_fixed_f(d * cov(kb - 1 - x0i)) : 0;  // rounded coverage just left of the tile
-    int prev = first;
-    int* rowp = cells + r * g.pitch;
-    for (int k = kb; k <= ke; k++) {
-        const int cur = (k == last) ? fd : to_fixed_f(d * cov(k - x0i));
-        const int diff = cur - prev;
-        if (diff != 0) atomicAdd(&rowp[swz<L>(k - g.cx0)], diff);
-        prev = cur;
-    }
-    atomicAdd(&rowtot[r], prev - first);
-    row_touched[r] = 1;
-}
-
-// Oriented piece ready for span_row, or nothing.  Returns the band rows [rb, re) it touches.
-struct Piece {
-    double ax, ay, by, dxdy;
-    float dirf;
-    int rb, re;
-    int cls;  // 0 = nothing to do in this tile, 2 = needs span_row
-};
-
-__device__ __forceinline__ Piece classify_piece(double ax, double ay, double bx, double by, const TileGeom& g) {
-    Piece p;
-    p.cls = 0;
-    p.rb = p.re = 0;
-    p.dirf = 1.0f;
-    p.dxdy = 0.0;
-    if (fabs(ay - by) < kEps) { p.ax = ax; p.ay = ay; p.by = by; return p; }  // src/rasterize.rs:400-403
-    const double xmin = fmin(ax, bx), xmax = fmax(ax, bx);
-    if (!(ay < by)) {  // src/rasterize.rs:405-409
-        double t;
-        t = ax; ax = bx; bx = t;
-        t = ay; ay = by; by = t;
-        p.dirf = -1.0f;
-    }
-    p.ax = ax; p.ay = ay; p.by = by;
-    if (xmin >= (double)g.tile_end) return p;    // entirely right of the tile: contributes nothing here
-    if (xmax < (double)g.cx0 - 1.0) return p;    // entirely left (a pixel of slack for the span's last column): look-back
-    // rows of the reference loop (src/rasterize.rs:414, 421) intersected with the band
-    const double ys = floor(fmax(ay, 0.0));
-    const double ye = ceil(fmax(by, 0.0));
-    p.rb = ys >= (double)g.row1 ? g.row1 : max(g.row0, (int)ys);
-    p.re = ye >= (double)g.row1 ? g.row1 : (int)ye;
-    if (p.rb >= p.re) return p;
-    p.dxdy = (bx - ax) / (by - ay);
-    p.cls = 2;
-    return p;
-}
-
-template <int L>
-__device__ void piece_serial(double ax, double ay, double bx, double by, const TileGeom& g, int* cells, int* rowtot, int* row_touched) {
-    const Piece p = classify_piece(ax, ay, bx, by, g);
-    if (p.cls == 2)
-        for (int y = p.rb; y < p.re; y++) span_row<L>(p.ax, p.ay, p.by, p.dxdy, p.dirf, y, g, cells, rowtot, row_touched);
-}
-
-// ---- carry look-back state: one 64-bit word per (tile, row): [63:34] epoch, [33:32] flag, [31:0] value ---------
-constexpr unsigned long long kFlagAgg = 1ull << 32;     // value = this tile's row total
-constexpr unsigned long long kFlagPrefix = 2ull << 32;  // value = inclusive prefix over the tiles of the band so far
-__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
+using namespace rs;
 
 // Tile shapes: <CW columns, TH rows, THREADS>.  L = CW/32 columns per lane in the scan phase.
 template <int CW, int TH, int THREADS>
@@ -458,83 +197,15 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     }
 
     // ---- phase 1: accumulate the tile's lines.  Warps work independently: 32 lines per round per warp ------
-    // 1a: one line per lane — the reference's clipping, orientation and row range; the (piece,row) spans of the
-    //     32 lines are compacted into the warp's span list (warp prefix sum, no atomics)
-    // 1b: one lane per span — no row-loop divergence
+    // (see warp_accumulate_round: 1a one line per lane, spans compacted per warp; 1b one lane per span)
     unsigned short* spans = spans_all + warp * Cfg::kWarpSpanCap;
     const uint32_t rbeg = tile_offs[tile], rend = tile_offs[tile + 1];
     for (uint32_t r0 = rbeg + warp * 32; r0 < rend; r0 += THREADS) {
         const uint32_t r = r0 + lane;
-        Piece p;
-        p.cls = 0;
-        p.rb = p.re = 0;
-        if (r < rend) {
-            const double4 l = bin_lines[r];
-            double p0x = l.x, p0y = l.y, p1x = l.z, p1y = l.w;
-            // src/rasterize.rs:370-387: lines crossing x == width
-            if (p0x > wc || p1x > wc) {
-                if (p0x > wc && p1x > wc) {
-                    p0x = wc - 0.001;
-                    p1x = wc - 0.001;
-                } else {
-                    const double t = (p0x - wc) / (p0x - p1x);
-                    const double my = (1.0 - t) * p0y + t * p1y;
-                    if (p0x < wc) { p1x = wc; p1y = my; } else { p0x = wc; p0y = my; }
-                }
-            }
-            // src/rasterize.rs:923-937 split_at_zero_x
-            if (p0x < 0.0 || p1x < 0.0) {
-                if (p0x <= 0.0 && p1x <= 0.0) {
-                    p0x = 0.0;
-                    p1x = 0.0;
-                } else {
-                    const double t = p0x / (p0x - p1x);
-                    const double mx = (1.0 - t) * p0x + t * p1x;
-                    const double my = (1.0 - t) * p0y + t * p1y;
-                    // the outside part, folded onto x = 0, goes through the same function again in the reference;
-                    // rare (only lines crossing the left edge): done serially by this lane
-                    if (p0x < 0.0) {
-                        if (mx <= 0.0) piece_serial<L>(0.0, p0y, 0.0, my, g, cells, rowtot, row_touched);
-                        else piece_serial<L>(0.0, p0y, mx, my, g, cells, rowtot, row_touched);
-                        p0x = mx; p0y = my;
-                    } else {
-                        if (mx <= 0.0) piece_serial<L>(0.0, my, 0.0, p1y, g, cells, rowtot, row_touched);
-                        else piece_serial<L>(mx, my, 0.0, p1y, g, cells, rowtot, row_touched);
-                        p1x = mx; p1y = my;
-                    }
-                }
-            }
-            p = classify_piece(p0x, p0y, p1x, p1y, g);
-        }
-        int n = (p.cls == 2) ? p.re - p.rb : 0;
-        int incl = n;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int nb = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += nb;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        const int base = incl - n;
-        if (n > 0) {
-            if (base + n <= Cfg::kWarpSpanCap) {
-                p_ax[tid] = p.ax; p_ay[tid] = p.ay; p_by[tid] = p.by; p_dxdy[tid] = p.dxdy; p_dir[tid] = p.dirf;
-                for (int k = 0; k < n; k++) spans[base + k] = (unsigned short)((lane << Cfg::kRowBits) | (p.rb + k - row0));
-            } else {  // list full (only possible for TH = 64): do the rows here
-                for (int y = p.rb; y < p.re; y++) span_row<L>(p.ax, p.ay, p.by, p.dxdy, p.dirf, y, g, cells, rowtot, row_touched);
-            }
-        }
-        __syncwarp();
-        // lanes are in list order: everything before the first lane that did not fit is in the list
-        const unsigned nofit = __ballot_sync(0xffffffffu, n > 0 && base + n > Cfg::kWarpSpanCap);
-        const int ns = nofit ? __shfl_sync(0xffffffffu, base, __ffs(nofit) - 1) : total;
-        const int wbase = warp * 32;
-        for (int i = lane; i < ns; i += 32) {
-            const int e = spans[i];
-            const int slot = wbase + (e >> Cfg::kRowBits);
-            const int y = row0 + (e & ((1 << Cfg::kRowBits) - 1));
-            span_row<L>(p_ax[slot], p_ay[slot], p_by[slot], p_dxdy[slot], p_dir[slot], y, g, cells, rowtot, row_touched);
-        }
-        __syncwarp();
+        const bool valid = r < rend;
+        const double4 l = valid ? bin_lines[r] : make_double4(0, 0, 0, 0);
+        warp_accumulate_round<L, Cfg::kRowBits, Cfg::kWarpSpanCap>(l, valid, g, cells, rowtot, row_touched, p_ax, p_ay, p_by, p_dxdy, p_dir,
+                                                                  spans, tid);
     }
     __syncthreads();
 

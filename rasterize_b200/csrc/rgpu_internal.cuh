@@ -98,6 +98,10 @@ TileShape raster_tile_shape(int variant);
 void launch_raster(int variant, const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
                    uint32_t n_tiles, const PaintDev* paints, const uint32_t* tile_offs, const double4* bin_lines,
                    unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, cudaStream_t s);
+// Fused one-CTA-per-job pipeline for canvases of at most 64 x 64 visible pixels (small.cu)
+bool small_canvas_eligible(uint32_t width, uint32_t height, int mode);
+void launch_small_canvas(const JobDev* jobs, uint32_t job_first, uint32_t n_jobs, const PaintDev* paints, double thr, Status* status,
+                         cudaStream_t s);
 void launch_to_rgba8(const float4* lin, uchar4* out, size_t n, cudaStream_t s);
 void launch_fill_color(float4* lin, size_t n, float4 color, cudaStream_t s);
 void launch_f32_to_f64(const float* in, double* out, size_t n, cudaStream_t s);
