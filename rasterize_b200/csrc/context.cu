@@ -6,8 +6,12 @@
 #include "host_pool.hpp"
 
 #include <algorithm>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -65,6 +69,9 @@ struct rgpu_ctx {
     DevBuf jobs, paints, slot_counts, slot_offs, lines, line_job, zero_block, tile_offs, refs, scan_temp, status, tile_state;
     uint32_t epoch = 0;
     DevBuf img_f32, img_f64, img_lin;  // staging canvases of the host-buffer entry points
+    DevBuf tmp_pts, tmp_items;         // device copy of the path of the current host-buffer call (grow-only, no per-call cudaMalloc)
+    uint2* h_items = nullptr;          // pinned staging of the item list
+    size_t h_items_cap = 0;
     size_t lines_cap = 0, refs_cap = 0;
     // pinned host
     Status* h_status = nullptr;
@@ -206,6 +213,26 @@ int upload_path(rgpu_ctx* ctx, const rgpu_path* path, rgpu_dpath* dp) {
     }
     // `items` is pageable: the async copy is staged by the driver before returning, but be explicit
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RGPU_OK;
+}
+
+// Device copy of a host path in the context's grow-only scratch (host-buffer entry points): no cudaMalloc / cudaFree
+// and no extra synchronisation per call; the copies are ordered before the kernels on the context's stream.
+int stage_path(rgpu_ctx* ctx, const rgpu_path* path, rgpu_dpath* dp) {
+    std::vector<uint2> items;
+    build_items(path, items, dp->n_curves);
+    dp->n_points = path->n_points;
+    dp->n_items = (uint32_t)items.size();
+    int rc;
+    if ((rc = ensure_dev(ctx, ctx->tmp_pts, sizeof(double2) * std::max<uint32_t>(dp->n_points, 1)))) return rc;
+    if ((rc = ensure_dev(ctx, ctx->tmp_items, sizeof(uint2) * std::max<uint32_t>(dp->n_items, 1)))) return rc;
+    if ((rc = ensure_pinned(ctx, ctx->h_items, ctx->h_items_cap, std::max<size_t>(items.size(), 1)))) return rc;
+    // a previous call's copy out of h_items has completed: every host-buffer entry point ends with a stream sync
+    std::memcpy(ctx->h_items, items.data(), sizeof(uint2) * items.size());
+    dp->pts = static_cast<double2*>(ctx->tmp_pts.p);
+    dp->items = static_cast<uint2*>(ctx->tmp_items.p);
+    if (dp->n_points) CK(ctx, cudaMemcpyAsync(dp->pts, path->points, sizeof(double2) * dp->n_points, cudaMemcpyHostToDevice, ctx->stream));
+    if (dp->n_items) CK(ctx, cudaMemcpyAsync(dp->items, ctx->h_items, sizeof(uint2) * dp->n_items, cudaMemcpyHostToDevice, ctx->stream));
     return RGPU_OK;
 }
 
@@ -572,13 +599,14 @@ void rgpu_destroy(rgpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->jobs, &ctx->paints, &ctx->slot_counts, &ctx->slot_offs, &ctx->lines, &ctx->line_job, &ctx->zero_block, &ctx->tile_offs,
-                      &ctx->tile_state, &ctx->refs, &ctx->scan_temp, &ctx->status, &ctx->img_f32, &ctx->img_f64, &ctx->img_lin};
+                      &ctx->tile_state, &ctx->refs, &ctx->scan_temp, &ctx->status, &ctx->img_f32, &ctx->img_f64, &ctx->img_lin, &ctx->tmp_pts, &ctx->tmp_items};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_jobs) cudaFreeHost(ctx->h_jobs);
     if (ctx->h_paints) cudaFreeHost(ctx->h_paints);
+    if (ctx->h_items) cudaFreeHost(ctx->h_items);
     for (int i = 0; i < 4; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
@@ -739,11 +767,11 @@ int rgpu_flatten(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int c
     *n_out = 0;
     if (path->n_segments == 0 || path->n_subpaths == 0) return RGPU_OK;
     rgpu_dpath dp;
-    rc = upload_path(ctx, path, &dp);
-    if (rc) { free_path(&dp); return rc; }
+    rc = stage_path(ctx, path, &dp);
+    if (rc) return rc;
     // flatten only: run count + scan + emit through a throw-away 1x1 mask job so that one code path serves both
     float* d_dummy = nullptr;
-    if ((rc = ensure_dev(ctx, ctx->img_f32, 64))) { free_path(&dp); return rc; }
+    if ((rc = ensure_dev(ctx, ctx->img_f32, 64))) return rc;
     d_dummy = static_cast<float*>(ctx->img_f32.p);
     rgpu_job job;
     std::memset(&job, 0, sizeof(job));
@@ -766,7 +794,6 @@ int rgpu_flatten(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int c
             if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = RGPU_ERR_CUDA; }
         }
     }
-    free_path(&dp);
     return rc;
 }
 
@@ -784,8 +811,8 @@ static int mask_to_device(rgpu_ctx* ctx, const rgpu_path* path, const double tr[
         CK(ctx, cudaMemsetAsync(d_img, 0, sizeof(float) * width * height, ctx->stream));
         return RGPU_OK;
     }
-    rc = upload_path(ctx, path, &dp);
-    if (rc) { free_path(&dp); return rc; }
+    rc = stage_path(ctx, path, &dp);
+    if (rc) return rc;
     rgpu_job job;
     std::memset(&job, 0, sizeof(job));
     job.path = &dp;
@@ -796,9 +823,7 @@ static int mask_to_device(rgpu_ctx* ctx, const rgpu_path* path, const double tr[
     job.row_stride = width;
     job.width = (uint32_t)width;
     job.height = (uint32_t)height;
-    rc = submit_sync(ctx, &job, 1, RGPU_BATCH_INDEPENDENT, 1);
-    free_path(&dp);
-    return rc;
+    return submit_sync(ctx, &job, 1, RGPU_BATCH_INDEPENDENT, 1);
 }
 
 int rgpu_mask_f32(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill_rule, float* img, size_t width, size_t height) {
@@ -823,6 +848,23 @@ int rgpu_coverage_f32(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], 
     CK(ctx, cudaMemcpyAsync(out, d, sizeof(float) * width * height, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return RGPU_OK;
+}
+
+// f32 -> f64 row with non-temporal stores: a plain store stream would first read every destination line for
+// ownership (134 MB of extra DRAM reads on a 4096^2 mask), which is what bounds the host side of rgpu_mask.
+static inline void widen_row(const float* __restrict__ src, double* __restrict__ dst, size_t n) {
+#if defined(__SSE2__)
+    size_t x = 0;
+    while (x < n && (reinterpret_cast<uintptr_t>(dst + x) & 15)) { dst[x] = (double)src[x]; x++; }
+    for (; x + 4 <= n; x += 4) {
+        const __m128 v = _mm_loadu_ps(src + x);
+        _mm_stream_pd(dst + x, _mm_cvtps_pd(v));
+        _mm_stream_pd(dst + x + 2, _mm_cvtps_pd(_mm_movehl_ps(v, v)));
+    }
+    for (; x < n; x++) dst[x] = (double)src[x];
+#else
+    for (size_t x = 0; x < n; x++) dst[x] = (double)src[x];
+#endif
 }
 
 // f32 device image -> strided f64 host image: the D2H copy is cut into row chunks; as soon as a chunk has landed in
@@ -862,11 +904,14 @@ static int download_widen(rgpu_ctx* ctx, const float* d_img, size_t w, size_t h,
                     const float* srow = stage + y * w;
                     double* drow = dst + y * rs;
                     if (cs == 1) {
-                        for (size_t x = 0; x < w; x++) drow[x] = (double)srow[x];
+                        widen_row(srow, drow, w);
                     } else {
                         for (size_t x = 0; x < w; x++) drow[x * cs] = (double)srow[x];
                     }
                 }
+#if defined(__SSE2__)
+                _mm_sfence();
+#endif
             });
         }
     }
@@ -883,6 +928,16 @@ int rgpu_mask(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill
     float* d = nullptr;
     int rc = mask_to_device(ctx, path, tr, fill_rule, RGPU_JOB_MASK, w, h, &d);
     if (rc) return rc;
+    static const bool device_widen = getenv("RGPU_MASK_DEVICE_WIDEN") != nullptr;  // A/B switch for benchmarking
+    if (device_widen && shape.col_stride == 1) {
+        if ((rc = ensure_dev(ctx, ctx->img_f64, sizeof(double) * w * h))) return rc;
+        double* d64 = static_cast<double*>(ctx->img_f64.p);
+        launch_f32_to_f64(d, d64, w * h, ctx->stream);
+        CK(ctx, cudaMemcpy2DAsync(img + shape.start, shape.row_stride * sizeof(double), d64, w * sizeof(double), w * sizeof(double), h,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        return RGPU_OK;
+    }
     return download_widen(ctx, d, w, h, img + shape.start, shape);
 }
 
@@ -940,8 +995,8 @@ int rgpu_fill(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill
         CK(ctx, cudaMemcpyAsync(d_img, st, sizeof(float4) * w * h, cudaMemcpyHostToDevice, ctx->stream));
     }
     rgpu_dpath dp;
-    rc = upload_path(ctx, path, &dp);
-    if (rc) { free_path(&dp); return rc; }
+    rc = stage_path(ctx, path, &dp);
+    if (rc) return rc;
     rgpu_job job;
     std::memset(&job, 0, sizeof(job));
     job.path = &dp;
@@ -955,7 +1010,6 @@ int rgpu_fill(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill
     job.width = (uint32_t)w;
     job.height = (uint32_t)h;
     rc = submit_sync(ctx, &job, 1, RGPU_BATCH_ORDERED, 1);
-    free_path(&dp);
     if (rc) return rc;
     if (dense_rows) {
         CK(ctx, cudaMemcpy2DAsync(dst, shape.row_stride * sizeof(float4), d_img, w * sizeof(float4), w * sizeof(float4), h,

@@ -70,7 +70,10 @@ flatten_fused_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     SlotCtx c;
     const bool ok = t < total_slots && slot_setup(jobs, n_jobs, t, thr, c, status);
-    const uint32_t count = ok ? slot_walk(c, thr, status, [](double, double, double, double) {}) : 0u;
+    // finite control points cannot produce NaN below: skip the per-node has_nans test (see seg_all_finite)
+    const bool fin = ok && seg_all_finite(c.seg, c.kind);
+    auto nop = [](double, double, double, double) {};
+    const uint32_t count = !ok ? 0u : (fin ? slot_walk<false>(c, thr, status, nop) : slot_walk<true>(c, thr, status, nop));
     uint32_t incl = count;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -96,11 +99,13 @@ flatten_fused_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t 
     }
     uint32_t out = base + before + incl - count;
     const uint32_t j = c.job;
-    slot_walk(c, thr, status, [&](double x0, double y0, double x1, double y1) {
+    auto emit = [&](double x0, double y0, double x1, double y1) {
         lines[out] = make_double4(x0, y0, x1, y1);
         if (line_job) line_job[out] = j;
         out++;
-    });
+    };
+    if (fin) slot_walk<false>(c, thr, status, emit);
+    else slot_walk<true>(c, thr, status, emit);
 }
 
 }  // namespace

@@ -153,7 +153,18 @@ __device__ __forceinline__ bool slot_setup(const JobDev* __restrict__ jobs, uint
 
 // Depth-first walk of the slot's subtree in the reference's order (left half first); `stack` holds pending right
 // halves.  Calls emit(x0,y0,x1,y1) for every leaf and returns the number of leaves.
-template <class Emit>
+// True when every control point is finite and far from overflow: all descendants are convex combinations of the
+// root's points, so no NaN can appear below it and the per-node has_nans test of the reference (src/path.rs:765)
+// can never fire — slot_walk<false> may then skip it.
+__device__ __forceinline__ bool seg_all_finite(const Seg& s, int kind) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (i < kind) ok = ok && fabs(s.p[i].x) < 1e300 && fabs(s.p[i].y) < 1e300;
+    return ok;
+}
+
+template <bool CHECK_NAN = true, class Emit>
 __device__ __forceinline__ uint32_t slot_walk(const SlotCtx& c, double thr, Status* __restrict__ status, Emit emit) {
     const int kind = c.kind;
     Seg seg = c.seg;
@@ -165,7 +176,7 @@ __device__ __forceinline__ uint32_t slot_walk(const SlotCtx& c, double thr, Stat
     int top = 0;
     uint32_t count = 0;
     while (true) {
-        if (seg_has_nan(seg, kind)) { atomicExch(&status->nan_flag, 1u); break; }
+        if (CHECK_NAN && seg_has_nan(seg, kind)) { atomicExch(&status->nan_flag, 1u); break; }
         if (seg_flatness(seg, kind) < thr) {
             emit(seg.p[0].x, seg.p[0].y, seg.p[kind - 1].x, seg.p[kind - 1].y);
             count++;

@@ -258,6 +258,43 @@ static __device__ void piece_serial(double ax, double ay, double bx, double by, 
         for (int y = p.rb; y < p.re; y++) span_row<L>(p.ax, p.ay, p.by, p.dxdy, p.dirf, y, g, cells, rowtot, row_touched);
 }
 
+// The reference's signed_difference_line for ONE line, serially in the calling thread (clipping + all rows).
+template <int L>
+static __device__ void line_serial(const double4 l, const TileGeom& g, int* cells, int* rowtot, int* row_touched) {
+    const double wc = g.wc;
+    double p0x = l.x, p0y = l.y, p1x = l.z, p1y = l.w;
+    if (p0x > wc || p1x > wc) {  // src/rasterize.rs:370-387
+        if (p0x > wc && p1x > wc) {
+            p0x = wc - 0.001;
+            p1x = wc - 0.001;
+        } else {
+            const double t = (p0x - wc) / (p0x - p1x);
+            const double my = (1.0 - t) * p0y + t * p1y;
+            if (p0x < wc) { p1x = wc; p1y = my; } else { p0x = wc; p0y = my; }
+        }
+    }
+    if (p0x < 0.0 || p1x < 0.0) {  // src/rasterize.rs:923-937
+        if (p0x <= 0.0 && p1x <= 0.0) {
+            p0x = 0.0;
+            p1x = 0.0;
+        } else {
+            const double t = p0x / (p0x - p1x);
+            const double mx = (1.0 - t) * p0x + t * p1x;
+            const double my = (1.0 - t) * p0y + t * p1y;
+            if (p0x < 0.0) {
+                if (mx <= 0.0) piece_serial<L>(0.0, p0y, 0.0, my, g, cells, rowtot, row_touched);
+                else piece_serial<L>(0.0, p0y, mx, my, g, cells, rowtot, row_touched);
+                p0x = mx; p0y = my;
+            } else {
+                if (mx <= 0.0) piece_serial<L>(0.0, my, 0.0, p1y, g, cells, rowtot, row_touched);
+                else piece_serial<L>(mx, my, 0.0, p1y, g, cells, rowtot, row_touched);
+                p1x = mx; p1y = my;
+            }
+        }
+    }
+    piece_serial<L>(p0x, p0y, p1x, p1y, g, cells, rowtot, row_touched);
+}
+
 // One round of phase 1 for a warp: up to 32 lines, one per lane.
 // 1a: the reference's right-edge / x<0 clipping, orientation and row range; the (piece,row) spans of the 32 lines
 //     are compacted into the warp's span list (warp prefix sum, no atomics)

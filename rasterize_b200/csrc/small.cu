@@ -41,7 +41,7 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
     unsigned short* spans_all = reinterpret_cast<unsigned short*>(p_dir + kSmThreads);
     __shared__ int rowtot[kSmMaxH];
     __shared__ int row_touched[kSmMaxH];
-    __shared__ uint32_t s_warp[kSmWarps];
+    __shared__ uint32_t n_lines_s;
     __shared__ PaintDev s_paint;
 
     const int tid = threadIdx.x;
@@ -73,55 +73,48 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
     __syncthreads();
 
     // ---- K1 into shared memory, K3 phase 1 from shared memory -----------------------------------------------
+    // One depth-first walk per slot: every leaf claims a place in the shared line window with a shared-memory
+    // atomic (the order of lines is irrelevant to the fixed-point accumulation).  If the window is full the
+    // emitting thread rasterizes that line itself, so any path size works; ordinary glyphs fit in one window.
     const uint32_t total_slots = job.n_items * kSlotsPerItem;
-    uint32_t lines_total = 0;
+    uint32_t my_lines = 0;
     for (uint32_t s0 = 0; s0 < total_slots; s0 += kSmThreads) {
+        if (tid == 0) n_lines_s = 0;
+        __syncthreads();
         // the job table entry doubles as a one-job table for slot_setup: slot t of this job is global slot
         // item_begin*8 + t of a table whose only entry starts at item_begin
         const uint32_t t = s0 + tid;
         SlotCtx c;
-        const bool ok = t < total_slots && slot_setup(&job, 1, job.item_begin * kSlotsPerItem + t, thr, c, status);
-        const uint32_t count = ok ? slot_walk(c, thr, status, [](double, double, double, double) {}) : 0u;
-        uint32_t incl = count;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += nb;
+        if (t < total_slots && slot_setup(&job, 1, job.item_begin * kSlotsPerItem + t, thr, c, status)) {
+            auto emit = [&](double x0, double y0, double x1, double y1) {
+                const uint32_t k = atomicAdd(&n_lines_s, 1u);
+                if (k < (uint32_t)kSmLineCap) {
+                    lines_s[k] = make_double4(x0, y0, x1, y1);
+                } else {  // window full: rasterize here (serial in this thread)
+                    line_serial<kSmNoSwz>(make_double4(x0, y0, x1, y1), g, cells, rowtot, row_touched);
+                }
+            };
+            if (seg_all_finite(c.seg, c.kind)) my_lines += slot_walk<false>(c, thr, status, emit);
+            else my_lines += slot_walk<true>(c, thr, status, emit);
         }
-        if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-        uint32_t before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < kSmWarps; w++) {
-            const uint32_t v = s_warp[w];
-            if (w < warp) before += v;
-            total += v;
+        const uint32_t n = min(n_lines_s, (uint32_t)kSmLineCap);
+        for (uint32_t i0 = warp * 32; i0 < n; i0 += kSmThreads) {
+            const uint32_t i = i0 + lane;
+            const bool valid = i < n;
+            const double4 l = valid ? lines_s[i] : make_double4(0, 0, 0, 0);
+            warp_accumulate_round<kSmNoSwz, kSmRowBits, kSmSpanCap>(l, valid, g, cells, rowtot, row_touched, p_ax, p_ay, p_by, p_dxdy, p_dir,
+                                                                    spans, tid);
         }
-        const uint32_t first = before + incl - count;  // index of this thread's first line in the round
-        lines_total += total;
-        // windows of kSmLineCap lines (one window for ordinary glyphs)
-        for (uint32_t w0 = 0; w0 < total; w0 += kSmLineCap) {
-            if (count && first < w0 + kSmLineCap && first + count > w0) {
-                uint32_t k = first;
-                slot_walk(c, thr, status, [&](double x0, double y0, double x1, double y1) {
-                    if (k >= w0 && k < w0 + kSmLineCap) lines_s[k - w0] = make_double4(x0, y0, x1, y1);
-                    k++;
-                });
-            }
-            __syncthreads();
-            const uint32_t n = min((uint32_t)kSmLineCap, total - w0);
-            for (uint32_t i0 = warp * 32; i0 < n; i0 += kSmThreads) {
-                const uint32_t i = i0 + lane;
-                const bool valid = i < n;
-                const double4 l = valid ? lines_s[i] : make_double4(0, 0, 0, 0);
-                warp_accumulate_round<kSmNoSwz, kSmRowBits, kSmSpanCap>(l, valid, g, cells, rowtot, row_touched, p_ax, p_ay, p_by, p_dxdy,
-                                                                        p_dir, spans, tid);
-            }
-            __syncthreads();
-        }
-        __syncthreads();  // s_warp is rewritten by the next round
+        __syncthreads();
     }
-    if (tid == 0 && lines_total) atomicAdd(&status->n_lines, lines_total);
+    // line count of the batch (statistics only): one atomic per warp
+    {
+        uint32_t v = my_lines;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(&status->n_lines, v);
+    }
     __syncthreads();
 
     // ---- K3 phase 2 + K4: two rows per warp iteration (16 lanes x 4 columns each) ----------------------------
