@@ -86,6 +86,7 @@ struct rgpu_ctx {
     // last submission (for status / retry)
     uint64_t need_lines = 0, need_refs = 0;
     uint32_t last_total_slots = 0;
+    Status* d_status_cur = nullptr;  // device status block of the last submission, not yet fetched
     // host-side result pipeline (chunked D2H overlapped with threaded widening into the caller's image)
     std::unique_ptr<rgpu::HostPool> pool;
     std::vector<cudaEvent_t> chunk_ev;
@@ -366,6 +367,7 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     ctx->need_lines = ctx->need_refs = 0;
     if (n_live == 0) {
         std::memset(ctx->h_status, 0, sizeof(Status));
+        ctx->d_status_cur = nullptr;
         return RGPU_OK;
     }
     if (all_small && !ordered_lines) {
@@ -398,7 +400,7 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
             CK(ctx, cudaEventRecord(ctx->ev[3], s));
             ctx->ev_valid = true;
         }
-        CK(ctx, cudaMemcpyAsync(ctx->h_status, d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
+        ctx->d_status_cur = d_status;
         CK(ctx, cudaGetLastError());
         return RGPU_OK;
     }
@@ -406,34 +408,53 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     if (total_slots64 > 0x7fffffffull) return fail(ctx, RGPU_ERR_INVALID, "batch too large (more than 2^28 path items)");
     uint32_t total_slots = item_acc * kSlotsPerItem;
     ctx->last_total_slots = total_slots;
-
-    // scratch sizing (optimistic; grown and re-run on overflow by *_sync)
-    size_t want_lines = std::max<uint64_t>(ctx->lines_cap, est_lines);
-    size_t want_refs = std::max<uint64_t>(ctx->refs_cap, want_lines + want_lines / 2);
     if ((rc = ensure_dev(ctx, ctx->jobs, sizeof(JobDev) * n_live))) return rc;
     if ((rc = ensure_dev(ctx, ctx->paints, sizeof(PaintDev) * std::max<uint32_t>(n_paints, 1)))) return rc;
+    cudaStream_t s = ctx->stream;
+    JobDev* d_jobs = static_cast<JobDev*>(ctx->jobs.p);
+    PaintDev* d_paints = static_cast<PaintDev*>(ctx->paints.p);
+    const double thr = 16.0 * ctx->flatness * ctx->flatness;  // PathFlattenIter::new, src/path.rs:749
+    const bool prof = ctx->profiling;
+    ctx->ev_valid = false;
+
     if (ordered_lines) {
+        // `Path::flatten` parity: count -> scan -> emit in the reference's order; nothing is rasterized
+        size_t want_lines = std::max<uint64_t>(ctx->lines_cap, est_lines);
         if ((rc = ensure_dev(ctx, ctx->slot_counts, sizeof(uint32_t) * (total_slots + 1)))) return rc;
         if ((rc = ensure_dev(ctx, ctx->slot_offs, sizeof(uint32_t) * (total_slots + 1)))) return rc;
+        if ((rc = ensure_dev(ctx, ctx->lines, sizeof(double4) * want_lines))) return rc;
+        ctx->lines_cap = std::min<size_t>(ctx->lines.cap / sizeof(double4), 0xfffffff0u);
+        if ((rc = ensure_dev(ctx, ctx->scan_temp, scan_temp_bytes(total_slots + 1)))) return rc;
+        Status* d_status = static_cast<Status*>(ctx->status.p);
+        uint32_t* d_counts = static_cast<uint32_t*>(ctx->slot_counts.p);
+        uint32_t* d_offs = static_cast<uint32_t*>(ctx->slot_offs.p);
+        CK(ctx, cudaMemcpyAsync(d_jobs, ctx->h_jobs, sizeof(JobDev) * n_live, cudaMemcpyHostToDevice, s));
+        CK(ctx, cudaMemsetAsync(d_status, 0, sizeof(Status), s));
+        launch_flatten_count(d_jobs, n_live, item_acc, thr, d_counts, d_status, s);
+        launch_exclusive_scan(d_counts, d_offs, total_slots + 1, ctx->scan_temp.p, ctx->scan_temp.cap, s);
+        launch_flatten_emit(d_jobs, n_live, item_acc, thr, d_offs, static_cast<double4*>(ctx->lines.p), (uint32_t)ctx->lines_cap, d_status, s);
+        CK(ctx, cudaMemcpyAsync(&d_status->n_lines, d_offs + total_slots, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        ctx->n_launches += 3;
+        ctx->d_status_cur = d_status;
+        CK(ctx, cudaGetLastError());
+        return RGPU_OK;
     }
-    if ((rc = ensure_dev(ctx, ctx->lines, sizeof(double4) * want_lines))) return rc;
-    ctx->lines_cap = std::min<size_t>(ctx->lines.cap / sizeof(double4), 0xfffffff0u);
-    const bool need_line_job = !ordered_lines && n_live > 1;
-    if (need_line_job) {
-        if ((rc = ensure_dev(ctx, ctx->line_job, sizeof(uint32_t) * ctx->lines_cap))) return rc;
-    }
+
+    // ---- raster path: [flatten + count per tile] -> scan -> [flatten + write bins] -> raster -------------------
+    size_t want_refs = std::max<uint64_t>(ctx->refs_cap, est_lines + est_lines / 2);
     if ((rc = ensure_dev(ctx, ctx->refs, sizeof(double4) * want_refs))) return rc;
     ctx->refs_cap = std::min<size_t>(ctx->refs.cap / sizeof(double4), 0xfffffff0u);
-    // one block that must be zero at the start of every batch: [tickets | tile_counts | tile_cursor], one memset
+    // one block that must be zero at the start of every batch, cleared by ONE memset:
+    // [status | raster tickets | tile_counts | tile_cursor | scan tile states]
     const uint32_t n_raster_launches = (flags & RGPU_BATCH_INDEPENDENT) ? 1u : n_live;
-    const size_t tickets_off = 0;
-    const size_t counts_off = ((size_t)n_raster_launches * 4 + 255) & ~(size_t)255;
-    const size_t cursor_off = counts_off + (((size_t)(tile_acc + 1) * 4 + 255) & ~(size_t)255);
-    const size_t zero_bytes = cursor_off + (((size_t)(tile_acc + 1) * 4 + 255) & ~(size_t)255);
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t tickets_off = up(sizeof(Status));
+    const size_t counts_off = tickets_off + up((size_t)n_raster_launches * 4);
+    const size_t cursor_off = counts_off + up((size_t)(tile_acc + 1) * 4);
+    const size_t scan_off = cursor_off + up((size_t)(tile_acc + 1) * 4);
+    const size_t zero_bytes = scan_off + up(scan_temp_bytes(tile_acc + 1));
     if ((rc = ensure_dev(ctx, ctx->zero_block, zero_bytes))) return rc;
     if ((rc = ensure_dev(ctx, ctx->tile_offs, sizeof(uint32_t) * (tile_acc + 1)))) return rc;
-    size_t tb = std::max(ordered_lines ? scan_temp_bytes(total_slots + 1) : 0, scan_temp_bytes(tile_acc + 1));
-    if ((rc = ensure_dev(ctx, ctx->scan_temp, tb))) return rc;
     // carry look-back state, validated by epoch (cleared only when (re)allocated or when the epoch wraps)
     {
         size_t need = sizeof(unsigned long long) * kStateRows * (size_t)tile_acc;
@@ -445,47 +466,24 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
             if (ctx->epoch >= (1u << 30)) ctx->epoch = 1;
         }
     }
-
-    cudaStream_t s = ctx->stream;
-    JobDev* d_jobs = static_cast<JobDev*>(ctx->jobs.p);
-    PaintDev* d_paints = static_cast<PaintDev*>(ctx->paints.p);
-    Status* d_status = static_cast<Status*>(ctx->status.p);
-    uint32_t* d_counts = static_cast<uint32_t*>(ctx->slot_counts.p);
-    uint32_t* d_offs = static_cast<uint32_t*>(ctx->slot_offs.p);
-    double4* d_lines = static_cast<double4*>(ctx->lines.p);
     char* zb = static_cast<char*>(ctx->zero_block.p);
+    Status* d_status = reinterpret_cast<Status*>(zb);
     uint32_t* d_tickets = reinterpret_cast<uint32_t*>(zb + tickets_off);
     uint32_t* d_bc = reinterpret_cast<uint32_t*>(zb + counts_off);
     uint32_t* d_cur = reinterpret_cast<uint32_t*>(zb + cursor_off);
+    void* d_scan = zb + scan_off;
     uint32_t* d_bo = static_cast<uint32_t*>(ctx->tile_offs.p);
-    unsigned long long* d_state = static_cast<unsigned long long*>(ctx->tile_state.p);
     double4* d_refs = static_cast<double4*>(ctx->refs.p);
+    unsigned long long* d_state = static_cast<unsigned long long*>(ctx->tile_state.p);
 
     CK(ctx, cudaMemcpyAsync(d_jobs, ctx->h_jobs, sizeof(JobDev) * n_live, cudaMemcpyHostToDevice, s));
     if (n_paints) CK(ctx, cudaMemcpyAsync(d_paints, ctx->h_paints, sizeof(PaintDev) * n_paints, cudaMemcpyHostToDevice, s));
-    CK(ctx, cudaMemsetAsync(d_status, 0, sizeof(Status), s));
     CK(ctx, cudaMemsetAsync(zb, 0, zero_bytes, s));
-
-    double thr = 16.0 * ctx->flatness * ctx->flatness;  // PathFlattenIter::new, src/path.rs:749
-    const bool prof = ctx->profiling;
-    ctx->ev_valid = false;
     if (prof) CK(ctx, cudaEventRecord(ctx->ev[0], s));
-    uint32_t* d_line_job = need_line_job ? static_cast<uint32_t*>(ctx->line_job.p) : nullptr;
-    if (ordered_lines) {
-        launch_flatten_count(d_jobs, n_live, item_acc, thr, d_counts, d_status, s);
-        launch_exclusive_scan(d_counts, d_offs, total_slots + 1, ctx->scan_temp.p, ctx->scan_temp.cap, s);
-        launch_flatten_emit(d_jobs, n_live, item_acc, thr, d_offs, d_lines, (uint32_t)ctx->lines_cap, d_status, s);
-        ctx->n_launches += 3;
-    } else {
-        d_offs = nullptr;  // bin kernels then take the line count from status->n_lines
-        launch_flatten_fused(d_jobs, n_live, item_acc, thr, d_lines, d_line_job, (uint32_t)ctx->lines_cap, d_status, s);
-        ctx->n_launches += 1;
-    }
+    launch_flatten_bin_count(d_jobs, n_live, item_acc, thr, d_bc, ts.th, ts.cw, d_status, s);
     if (prof) CK(ctx, cudaEventRecord(ctx->ev[1], s));
-    launch_bin_count(d_jobs, n_live, d_offs, total_slots, d_line_job, d_lines, d_bc, ts.th, ts.cw, d_status, s);
-    launch_exclusive_scan(d_bc, d_bo, tile_acc + 1, ctx->scan_temp.p, ctx->scan_temp.cap, s);
-    launch_bin_fill(d_jobs, n_live, d_offs, total_slots, d_line_job, d_lines, d_bo, tile_acc, d_cur, d_refs, (uint32_t)ctx->refs_cap,
-                    ts.th, ts.cw, d_status, s);
+    launch_exclusive_scan(d_bc, d_bo, tile_acc + 1, d_scan, 0, s, /*temp_is_zero=*/true);
+    launch_flatten_bin_emit(d_jobs, n_live, item_acc, thr, d_bo, tile_acc, d_cur, d_refs, (uint32_t)ctx->refs_cap, ts.th, ts.cw, d_status, s);
     ctx->n_launches += 3;
     if (prof) CK(ctx, cudaEventRecord(ctx->ev[2], s));
     if (flags & RGPU_BATCH_INDEPENDENT) {
@@ -503,12 +501,17 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         CK(ctx, cudaEventRecord(ctx->ev[3], s));
         ctx->ev_valid = true;
     }
-    CK(ctx, cudaMemcpyAsync(ctx->h_status, d_status, sizeof(Status), cudaMemcpyDeviceToHost, s));
+    ctx->d_status_cur = d_status;
     CK(ctx, cudaGetLastError());
     return RGPU_OK;
 }
 
 int check_status(rgpu_ctx* ctx) {
+    // the device-side status of the last submission is fetched only here (keeps the submission path copy-free)
+    if (ctx->d_status_cur) {
+        CK(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status_cur, sizeof(Status), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d_status_cur = nullptr;
+    }
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     const Status& st = *ctx->h_status;
     if (st.nan_flag) return fail(ctx, RGPU_ERR_NAN, "cannot flatten segment with NaN");
@@ -542,10 +545,13 @@ int submit_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t fla
         }
         size_t nr = st.refs_overflow ? (size_t)st.n_refs + st.n_refs / 16 + 64 : std::max<size_t>(ctx->refs_cap, nl * 2);
         int rc2;
-        if ((rc2 = ensure_dev(ctx, ctx->lines, sizeof(double4) * nl))) return rc2;
-        ctx->lines_cap = ctx->lines.cap / sizeof(double4);
-        if ((rc2 = ensure_dev(ctx, ctx->refs, sizeof(double4) * nr))) return rc2;
-        ctx->refs_cap = ctx->refs.cap / sizeof(double4);
+        if (ordered_lines) {
+            if ((rc2 = ensure_dev(ctx, ctx->lines, sizeof(double4) * nl))) return rc2;
+            ctx->lines_cap = ctx->lines.cap / sizeof(double4);
+        } else {
+            if ((rc2 = ensure_dev(ctx, ctx->refs, sizeof(double4) * nr))) return rc2;
+            ctx->refs_cap = ctx->refs.cap / sizeof(double4);
+        }
     }
     return fail(ctx, RGPU_ERR_CAPACITY, "internal scratch overflow persisted after 4 attempts");
 }

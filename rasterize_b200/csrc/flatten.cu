@@ -108,6 +108,46 @@ flatten_fused_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t 
     else slot_walk<true>(c, thr, status, emit);
 }
 
+// Flatten fused with binning.  PASS 0: count lines per tile; PASS 1: write lines into their bins.
+// (A CTA-level shared-memory aggregation of the tile counters was tried and measured slower: the cost of these
+// passes is the per-leaf tile-range arithmetic inside the divergent walk, not the global atomics — ~35 lines per
+// tile counter spread over the whole launch.)
+template <int PASS>
+__global__ void __launch_bounds__(128)
+flatten_bin_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t total_items, double thr, uint32_t* __restrict__ tile_counts,
+                   const uint32_t* __restrict__ tile_offs, uint32_t total_tiles, double4* __restrict__ bin_lines, uint32_t refs_cap,
+                   int band_shift, int chunk_shift, Status* __restrict__ status) {
+    if (PASS == 1) {
+        if (status->nan_flag | status->depth_flag) return;
+        const uint32_t n_refs = tile_offs[total_tiles];
+        if (blockIdx.x == 0 && threadIdx.x == 0) status->n_refs = n_refs;
+        if (n_refs > refs_cap) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) status->refs_overflow = 1u;
+            return;
+        }
+    }
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total_slots = total_items * kSlotsPerItem;
+    SlotCtx c;
+    uint32_t count = 0;
+    if (t < total_slots && slot_setup(jobs, n_jobs, t, thr, c, status)) {
+        const JobDev& job = jobs[c.job];
+        auto emit = [&](double x0, double y0, double x1, double y1) {
+            for_each_tile(job, x0, y0, x1, y1, band_shift, chunk_shift, [&](uint32_t key) {
+                const uint32_t slot = atomicAdd(&tile_counts[key], 1u);
+                if (PASS == 1) bin_lines[tile_offs[key] + slot] = make_double4(x0, y0, x1, y1);
+            });
+        };
+        // finite control points cannot produce NaN below: skip the per-node has_nans test (see seg_all_finite)
+        count = seg_all_finite(c.seg, c.kind) ? slot_walk<false>(c, thr, status, emit) : slot_walk<true>(c, thr, status, emit);
+    }
+    if (PASS == 0) {  // total line count of the batch (statistics): one atomic per warp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+        if ((threadIdx.x & 31) == 0 && count) atomicAdd(&status->n_lines, count);
+    }
+}
+
 }  // namespace
 
 void launch_flatten_count(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, uint32_t* slot_counts,
@@ -128,6 +168,29 @@ void launch_flatten_fused(const JobDev* jobs, uint32_t n_jobs, uint32_t total_it
     uint32_t n = total_items * kSlotsPerItem;
     if (n == 0) return;
     flatten_fused_kernel<<<(n + 127) / 128, 128, 0, s>>>(jobs, n_jobs, total_items, thr, lines, line_job, lines_cap, status);
+}
+
+static inline int log2i(int v) {
+    int s = 0;
+    while ((1 << s) < v) s++;
+    return s;  // tile shapes are powers of two
+}
+
+void launch_flatten_bin_count(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, uint32_t* tile_counts,
+                              int band_rows, int chunk_cols, Status* status, cudaStream_t s) {
+    uint32_t n = total_items * kSlotsPerItem;
+    if (n == 0) return;
+    flatten_bin_kernel<0><<<(n + 127) / 128, 128, 0, s>>>(jobs, n_jobs, total_items, thr, tile_counts, nullptr, 0, nullptr, 0,
+                                                          log2i(band_rows), log2i(chunk_cols), status);
+}
+
+void launch_flatten_bin_emit(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, const uint32_t* tile_offs,
+                             uint32_t total_tiles, uint32_t* tile_cursor, double4* bin_lines, uint32_t refs_cap, int band_rows,
+                             int chunk_cols, Status* status, cudaStream_t s) {
+    uint32_t n = total_items * kSlotsPerItem;
+    if (n == 0) return;
+    flatten_bin_kernel<1><<<(n + 127) / 128, 128, 0, s>>>(jobs, n_jobs, total_items, thr, tile_cursor, tile_offs, total_tiles, bin_lines,
+                                                          refs_cap, log2i(band_rows), log2i(chunk_cols), status);
 }
 
 }  // namespace rgpu

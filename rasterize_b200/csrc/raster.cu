@@ -74,7 +74,30 @@ __device__ __forceinline__ void scan_rows(const JobDev& job, const PaintDev& s_p
                 *reinterpret_cast<float4*>(bc + lane * (L + 4) + i * 4) = cv;
             }
         } else {
-            const float c = coverage_from_fixed<EVENODD>(acc);  // no line touched this row of the tile: constant coverage
+            float c = coverage_from_fixed<EVENODD>(acc);  // no line touched this row of the tile: constant coverage
+            if (mode != kModeFill) {
+                // straight from registers: no shared-memory round trip for empty rows (most of a sparse canvas)
+                if (mode == kModeCoverage && c < 1e-6f) c = 0.f;
+                const float4 cv = make_float4(c, c, c, c);
+                float* out = reinterpret_cast<float*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride + cx0;
+                const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+#pragma unroll
+                for (int i = 0; i < CW / 128; i++) {
+                    const int col = i * 128 + lane * 4;
+                    if (col < bw) {
+                        if (vec_ok && col + 3 < bw) {
+                            __stcs(reinterpret_cast<float4*>(out + col), cv);
+                        } else {
+                            out[col] = c;
+                            if (col + 1 < bw) out[col + 1] = c;
+                            if (col + 2 < bw) out[col + 2] = c;
+                            if (col + 3 < bw) out[col + 3] = c;
+                        }
+                    }
+                }
+                continue;
+            }
+            if (c < 1e-6f) continue;  // FILL: nothing to composite on this row
             const float4 cv = make_float4(c, c, c, c);
 #pragma unroll
             for (int i = 0; i < NQ; i++) *reinterpret_cast<float4*>(bc + lane * (L + 4) + i * 4) = cv;
@@ -161,11 +184,6 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     if (tid == 0) my_ticket = atomicAdd(ticket, 1u);
     const uint32_t bad = status->lines_overflow | status->refs_overflow | status->nan_flag | status->depth_flag;
     if (tid < TH) { carry[tid] = 0; rowtot[tid] = 0; row_touched[tid] = 0; }
-    {
-        const int4 z = make_int4(0, 0, 0, 0);
-        int4* c4 = reinterpret_cast<int4*>(cells);
-        for (int i = tid; i < TH * Cfg::kPitch / 4; i += THREADS) c4[i] = z;
-    }
     if (tid == 0) {
         const uint32_t t = tile_first + my_ticket;
         s_tile = t;
@@ -200,6 +218,12 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     // (see warp_accumulate_round: 1a one line per lane, spans compacted per warp; 1b one lane per span)
     unsigned short* spans = spans_all + warp * Cfg::kWarpSpanCap;
     const uint32_t rbeg = tile_offs[tile], rend = tile_offs[tile + 1];
+    if (rbeg < rend) {  // tiles without lines never read their cells (row_touched stays 0): no need to clear them
+        const int4 z = make_int4(0, 0, 0, 0);
+        int4* c4 = reinterpret_cast<int4*>(cells);
+        for (int i = tid; i < TH * Cfg::kPitch / 4; i += THREADS) c4[i] = z;
+        __syncthreads();
+    }
     for (uint32_t r0 = rbeg + warp * 32; r0 < rend; r0 += THREADS) {
         const uint32_t r = r0 + lane;
         const bool valid = r < rend;

@@ -78,11 +78,21 @@ void launch_flatten_count(const JobDev* jobs, uint32_t n_jobs, uint32_t total_it
 void launch_flatten_emit(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, const uint32_t* slot_offs,
                          double4* lines, uint32_t lines_cap, Status* status, cudaStream_t s);
 size_t scan_temp_bytes(uint32_t n);
-void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, void* temp, size_t temp_bytes, cudaStream_t s);
+// `temp` must be zero on entry; pass temp_is_zero = true when the caller has already cleared it
+void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, void* temp, size_t temp_bytes, cudaStream_t s,
+                           bool temp_is_zero = false);
 // Unordered single-kernel flatten for the raster path: count + CTA-level reservation + emit (see flatten.cu).
 // Writes status->n_lines (must be zero on entry) and, when line_job != nullptr, the job of every line.
 void launch_flatten_fused(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, double4* lines, uint32_t* line_job,
                           uint32_t lines_cap, Status* status, cudaStream_t s);
+// Flatten fused with binning (raster path): pass 0 walks every slot and counts lines per tile (and in total, into
+// status->n_lines); after an exclusive scan of the tile counts, pass 1 walks again and writes every line straight
+// into the bins of the tiles it touches.  No global line buffer.
+void launch_flatten_bin_count(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, uint32_t* tile_counts,
+                              int band_rows, int chunk_cols, Status* status, cudaStream_t s);
+void launch_flatten_bin_emit(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, const uint32_t* tile_offs,
+                             uint32_t total_tiles, uint32_t* tile_cursor, double4* bin_lines, uint32_t refs_cap, int band_rows,
+                             int chunk_cols, Status* status, cudaStream_t s);
 // slot_offs == nullptr: lines came from launch_flatten_fused (count in status->n_lines, jobs in line_job)
 void launch_bin_count(const JobDev* jobs, uint32_t n_jobs, const uint32_t* slot_offs, uint32_t total_slots, const uint32_t* line_job,
                       const double4* lines, uint32_t* tile_counts, int band_rows, int chunk_cols, Status* status, cudaStream_t s);
@@ -105,6 +115,41 @@ void launch_small_canvas(const JobDev* jobs, uint32_t job_first, uint32_t n_jobs
 void launch_to_rgba8(const float4* lin, uchar4* out, size_t n, cudaStream_t s);
 void launch_fill_color(float4* lin, size_t n, float4 color, cudaStream_t s);
 void launch_f32_to_f64(const float* in, double* out, size_t n, cudaStream_t s);
+
+// Tiles a flattened line may touch: every band of 2^band_shift rows its y-range covers (the reference's own row
+// range, src/rasterize.rs:414, 421) and, inside a band, every chunk of 2^chunk_shift columns its cells can land in
+// (x over the band's rows, clamped like the reference clamps to [0, width], 1.5 px of slack; the raster kernel is
+// exact and drops what is not in its tile).  Lines with |dy| < EPSILON add nothing (src/rasterize.rs:400-403).
+// Calls f(global tile index) for each.
+template <class F>
+__device__ __forceinline__ void for_each_tile(const JobDev& job, double x0, double y0, double x1, double y1, int band_shift,
+                                              int chunk_shift, F f) {
+    if (!(fabs(y0 - y1) >= 2.220446049250313e-16)) return;
+    const double H = (double)job.height;
+    const double lo = fmin(y0, y1), hi = fmax(y0, y1);
+    if (!(hi > 0.0) || !(lo < H)) return;
+    const double first = floor(fmax(lo, 0.0));
+    const double end = fmin(H, ceil(hi));
+    if (!(first < end)) return;
+    const int b0 = (int)first >> band_shift, b1 = ((int)end - 1) >> band_shift;
+    const int n_chunks = (int)job.n_chunks;
+    if (n_chunks == 1) {
+        for (int b = b0; b <= b1; b++) f(job.tile_begin + (uint32_t)b);
+        return;
+    }
+    const float fx0 = (float)x0, fy0 = (float)y0, fdxdy = (float)((x1 - x0) / (y1 - y0));
+    const float fylo = (float)lo, fyhi = (float)hi, fwc = (float)job.clamp_w;
+    for (int b = b0; b <= b1; b++) {
+        const float ya = fmaxf((float)(b << band_shift), fylo);
+        const float yb = fminf((float)((b + 1) << band_shift), fyhi);
+        const float xa = fx0 + (ya - fy0) * fdxdy, xb = fx0 + (yb - fy0) * fdxdy;
+        const float xl = fminf(fmaxf(fminf(xa, xb), 0.0f), fwc), xh = fminf(fmaxf(fmaxf(xa, xb), 0.0f), fwc);
+        int c0 = max(0, (int)(xl - 1.5f) >> chunk_shift);
+        int c1 = min(n_chunks - 1, (int)(xh + 2.5f) >> chunk_shift);
+        if (!(xl == xl) || !(xh == xh)) { c0 = 0; c1 = n_chunks - 1; }  // NaN from degenerate input: be conservative
+        for (int c = c0; c <= c1; c++) f(job.tile_begin + (uint32_t)b * (uint32_t)n_chunks + (uint32_t)c);
+    }
+}
 
 // upper_bound-style search: largest j with begin[j] <= v, over a strided member of JobDev
 template <class F>

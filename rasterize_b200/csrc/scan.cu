@@ -115,11 +115,11 @@ size_t scan_temp_bytes(uint32_t n) {
 }
 
 // `temp` layout: [0..4) tile counter, [16..) tile states
-void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, void* temp, size_t temp_bytes, cudaStream_t s) {
+void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, void* temp, size_t temp_bytes, cudaStream_t s, bool temp_is_zero) {
     if (n == 0) return;
     uint32_t tiles = (n + kTile - 1) / kTile;
     (void)temp_bytes;
-    cudaMemsetAsync(temp, 0, 16 + (size_t)tiles * sizeof(unsigned long long), s);
+    if (!temp_is_zero) cudaMemsetAsync(temp, 0, 16 + (size_t)tiles * sizeof(unsigned long long), s);
     auto* counter = static_cast<uint32_t*>(temp);
     auto* state = reinterpret_cast<unsigned long long*>(static_cast<char*>(temp) + 16);
     scan_kernel<<<tiles, kScanThreads, 0, s>>>(in, out, n, state, counter);
