@@ -306,6 +306,10 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     uint32_t max_w = 0;
     for (size_t j = 0; j < n_jobs; j++) max_w = std::max(max_w, jobs[j].width);
     int variant = (max_w <= 128) ? 1 : 0;
+    if (variant == 0) {
+        static const int forced = getenv("RGPU_TILE_VARIANT") ? atoi(getenv("RGPU_TILE_VARIANT")) : 0;  // tuning knob
+        if (forced >= 2 && forced <= 4) variant = forced;
+    }
     TileShape ts = raster_tile_shape(variant);
 
     uint32_t item_acc = 0, band_acc = 0, tile_acc = 0, n_paints = 0;

@@ -314,20 +314,30 @@ static void launch_raster_t(const JobDev* jobs, const JobDev* h_jobs, uint32_t n
 }
 
 TileShape raster_tile_shape(int variant) {
-    if (variant == 1) return TileShape{128, 64};
-    return TileShape{512, 8};
+    switch (variant) {
+        case 1: return TileShape{128, 64};   // canvases at most 128 px wide (larger than the fused small-canvas kernel takes)
+        case 2: return TileShape{512, 8};    // tuning alternatives (RGPU_TILE_VARIANT), measured slower on C2 and C5
+        case 3: return TileShape{512, 16};
+        case 4: return TileShape{1024, 4};
+        default: return TileShape{1024, 8};  // best of the r1 sweep: C2 46 us, C5 band 130 us (profiles/r1_tile_sweep.txt)
+    }
 }
 
 void launch_raster(int variant, const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
                    uint32_t n_tiles, const PaintDev* paints, const uint32_t* tile_offs, const double4* bin_lines,
                    unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, cudaStream_t s) {
     if (n_tiles == 0) return;
-    if (variant == 1)
-        launch_raster_t<128, 64, 256>(jobs, h_jobs, n_jobs, job_first, tile_first, n_tiles, paints, tile_offs, bin_lines, tile_state, epoch,
-                                      ticket, status, s);
-    else
-        launch_raster_t<512, 8, 128>(jobs, h_jobs, n_jobs, job_first, tile_first, n_tiles, paints, tile_offs, bin_lines, tile_state, epoch,
-                                     ticket, status, s);
+#define RGPU_LAUNCH(CW, TH, THREADS)                                                                                              \
+    launch_raster_t<CW, TH, THREADS>(jobs, h_jobs, n_jobs, job_first, tile_first, n_tiles, paints, tile_offs, bin_lines, tile_state, epoch, \
+                                     ticket, status, s)
+    switch (variant) {
+        case 1: RGPU_LAUNCH(128, 64, 256); break;
+        case 2: RGPU_LAUNCH(512, 8, 128); break;
+        case 3: RGPU_LAUNCH(512, 16, 128); break;
+        case 4: RGPU_LAUNCH(1024, 4, 128); break;
+        default: RGPU_LAUNCH(1024, 8, 128); break;
+    }
+#undef RGPU_LAUNCH
 }
 
 void launch_to_rgba8(const float4* lin, uchar4* out, size_t n, cudaStream_t s) {

@@ -179,24 +179,39 @@ __device__ __forceinline__ void span_row(double ax, double ay, double by, double
     const bool narrow = x1i <= x0i + 1;
     const int last = narrow ? x0i + 1 : x1i;  // last column that receives a delta
     if (last < g.cx0) return;                 // this row's span is left of the tile: it arrives through the look-back
+    int* rowp = cells + r * g.pitch;
+    if (narrow) {
+        // The common case (a span inside one pixel column, src/rasterize.rs:437-444): two cells, x0i and x0i + 1,
+        // with rounded coverages ca = F(d * (1 - xmf)) and fd.
+        const float c0 = 1.0f - (float)(0.5 * (x + xn) - x0_floor);  // 1 - xmf
+        const int ca = to_fixed_f(d * c0);
+        int tot = 0;
+        if (x0i >= g.cx0) {  // x0i < tile_end was checked above
+            if (ca != 0) atomicAdd(&rowp[swz<L>(x0i - g.cx0)], ca);
+            tot = ca;
+        }
+        if (x0i + 1 < g.tile_end) {  // x0i + 1 >= cx0 holds because last >= cx0
+            const int cb = fd - ca;
+            if (cb != 0) atomicAdd(&rowp[swz<L>(x0i + 1 - g.cx0)], cb);
+            tot += cb;
+        }
+        atomicAdd(&rowtot[r], tot);
+        row_touched[r] = 1;
+        return;
+    }
     // Positions stay f64 (f32 ulp at x ~ 4096 would already exceed the 1e-4 budget); the fractional parts are in
     // [0,1] and the area polynomials are evaluated in f32 (error ~1e-7 of a pixel).
-    float c0, sf = 0.f, a1 = 0.f, am = 0.f;
     const int n = x1i - x0i;
-    if (narrow) {
-        c0 = 1.0f - (float)(0.5 * (x + xn) - x0_floor);  // 1 - xmf, src/rasterize.rs:439
-    } else {
-        sf = 1.0f / (float)(x1 - x0);  // src/rasterize.rs:446-450
-        const float x0f = (float)(x0 - x0_floor);
-        const float x1f = (float)(x1 - x1_ceil + 1.0);
-        c0 = 0.5f * sf * (1.0f - x0f) * (1.0f - x0f);
-        am = 0.5f * sf * x1f * x1f;
-        a1 = sf * (1.5f - x0f);
-    }
+    const float sf = 1.0f / (float)(x1 - x0);  // src/rasterize.rs:446-450
+    const float x0f = (float)(x0 - x0_floor);
+    const float x1f = (float)(x1 - x1_ceil + 1.0);
+    const float c0 = 0.5f * sf * (1.0f - x0f) * (1.0f - x0f);
+    const float am = 0.5f * sf * x1f * x1f;
+    const float a1 = sf * (1.5f - x0f);
     // coverage (as a fraction of d) of pixel x0i + j == running sum of the reference's deltas
     auto cov = [&](int j) -> float {
         if (j <= 0) return j == 0 ? c0 : 0.0f;
-        if (narrow || j >= n) return 1.0f;
+        if (j >= n) return 1.0f;
         if (j == n - 1) return 1.0f - am;
         return a1 + (float)(j - 1) * sf;
     };
@@ -204,7 +219,6 @@ __device__ __forceinline__ void span_row(double ax, double ay, double by, double
     const int ke = min(last, g.tile_end - 1);
     const int first = (kb > x0i) ? to_fixed_f(d * cov(kb - 1 - x0i)) : 0;  // rounded coverage just left of the tile
     int prev = first;
-    int* rowp = cells + r * g.pitch;
     for (int k = kb; k <= ke; k++) {
         const int cur = (k == last) ? fd : to_fixed_f(d * cov(k - x0i));
         const int diff = cur - prev;

@@ -29,7 +29,7 @@ constexpr int kFixOne = 1 << kFixShift;
 constexpr double kFixScale = 16777216.0;
 
 constexpr int kMaxStops = 32;
-constexpr int kStateRows = 8;             // rows per tile in the carry look-back state (chunked tiles have 8 rows)
+constexpr int kStateRows = 16;            // rows per tile in the carry look-back state (chunked tiles have 8 rows)
 
 enum JobMode : int { kModeMask = 0, kModeCoverage = 1, kModeFill = 2 };
 
