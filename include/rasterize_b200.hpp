@@ -1,0 +1,245 @@
+// rasterize_b200.hpp — C++17 host-side mirror of the reference's interface for the fill path, header-only, on
+// top of the C ABI in rasterize_b200.h.  The reference is compiled code (Rust); with no Rust toolchain in this
+// image the same seam is stated in C++: same names, argument meaning and error behaviour
+// (aslpavel/rasterize v0.6.7, paths relative to the crate):
+//
+//   Point, Transform            src/geometry.rs:103, 317-539
+//   FillRule, Size              src/path.rs:21-29, src/rasterize.rs:38-41
+//   Path, PathBuilder           src/path.rs:227-233, 800-1056   (flat storage: this is what crosses the FFI)
+//   Pixel, Rasterizer           src/rasterize.rs:44-101          (name, mask, mask_iter, fill)
+//   LinColor, GradLinear/Radial src/color.rs:268-374, src/grad.rs:150-226, 307-426 (as paint descriptions)
+//   GpuRasterizer               the new implementor of Rasterizer (north star)
+//
+// Errors: a non-zero status from the C ABI throws rasterize::Error (the Rust shim panics, as the reference does
+// on NaN input, src/path.rs:765-767).  There is no CPU fallback.
+#pragma once
+#include "rasterize_b200.h"
+
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace rasterize {
+
+using Scalar = double;
+constexpr Scalar EPSILON = std::numeric_limits<double>::epsilon();
+constexpr Scalar DEFAULT_FLATNESS = 0.05;  // src/path.rs:16
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error("rasterize_b200 error " + std::to_string(c) + ": " + m), code(c) {}
+};
+
+struct Point {
+    Scalar x = 0, y = 0;
+};
+
+struct Size {
+    size_t width = 0, height = 0;
+};
+
+enum class FillRule : int { NonZero = RGPU_NONZERO, EvenOdd = RGPU_EVENODD };
+
+struct Pixel {
+    size_t x, y;
+    Scalar alpha;
+};
+
+// 2x3 affine [m00, m01, m02, m10, m11, m12]
+struct Transform {
+    Scalar m[6] = {1, 0, 0, 0, 1, 0};
+    static Transform identity() { return {}; }
+    static Transform new_translate(Scalar tx, Scalar ty) { Transform t; t.m[2] = tx; t.m[5] = ty; return t; }
+    static Transform new_scale(Scalar sx, Scalar sy) { Transform t; t.m[0] = sx; t.m[4] = sy; return t; }
+    static Transform new_rotate(Scalar a) {
+        Transform t;
+        const Scalar s = std::sin(a), c = std::cos(a);
+        t.m[0] = c; t.m[1] = -s; t.m[3] = s; t.m[4] = c;
+        return t;
+    }
+    Point apply(Point p) const { return {p.x * m[0] + p.y * m[1] + m[2], p.x * m[3] + p.y * m[4] + m[5]}; }
+    Transform operator*(const Transform& o) const {  // src/geometry.rs:519-539
+        Transform r;
+        r.m[0] = m[0] * o.m[0] + m[1] * o.m[3];
+        r.m[1] = m[0] * o.m[1] + m[1] * o.m[4];
+        r.m[2] = m[0] * o.m[2] + m[1] * o.m[5] + m[2];
+        r.m[3] = m[3] * o.m[0] + m[4] * o.m[3];
+        r.m[4] = m[3] * o.m[1] + m[4] * o.m[4];
+        r.m[5] = m[3] * o.m[2] + m[4] * o.m[5] + m[5];
+        return r;
+    }
+    Transform pre_translate(Scalar tx, Scalar ty) const { return *this * new_translate(tx, ty); }
+    Transform pre_scale(Scalar sx, Scalar sy) const { return *this * new_scale(sx, sy); }
+    Transform pre_rotate(Scalar a) const { return *this * new_rotate(a); }
+};
+
+// `Shape`, src/image.rs:6-17, over caller-owned memory
+template <class P>
+struct ImageMut {
+    P* data;
+    rgpu_shape shape;
+    static ImageMut dense(P* data, size_t height, size_t width) { return {data, rgpu_shape{0, width, height, width, 1}}; }
+    size_t width() const { return shape.width; }
+    size_t height() const { return shape.height; }
+    P& at(size_t row, size_t col) { return data[shape.start + row * shape.row_stride + col * shape.col_stride]; }
+};
+
+class PathBuilder;
+
+// Flat `Path { segments, subpaths, closed }`
+class Path {
+public:
+    std::vector<Scalar> points;          // x,y pairs, segments back to back
+    std::vector<uint8_t> kinds;          // 2 = Line, 3 = Quad, 4 = Cubic
+    std::vector<uint32_t> subpath_offsets;
+    std::vector<uint8_t> closed;
+
+    static PathBuilder builder();
+    bool is_empty() const { return closed.empty(); }
+    size_t segments_count() const { return kinds.size(); }
+    rgpu_path ffi() const {
+        rgpu_path p;
+        p.points = points.data();
+        p.kinds = kinds.data();
+        p.subpath_offsets = closed.empty() ? nullptr : subpath_offsets.data();
+        p.closed = closed.data();
+        p.n_points = (uint32_t)(points.size() / 2);
+        p.n_segments = (uint32_t)kinds.size();
+        p.n_subpaths = (uint32_t)closed.size();
+        return p;
+    }
+};
+
+// `PathBuilder` (move_to / line_to / quad_to / cubic_to / close / build), src/path.rs:813-943.
+// arc_to is a host-side arc -> cubic conversion in the reference (src/path.rs:945-972) and stays there.
+class PathBuilder {
+public:
+    PathBuilder& move_to(Point p) { finish(false); pos_ = p; return *this; }
+    PathBuilder& close() { finish(true); return *this; }
+    PathBuilder& line_to(Point p) {
+        if (!(std::fabs(pos_.x - p.x) < EPSILON && std::fabs(pos_.y - p.y) < EPSILON)) {  // src/path.rs:895-903
+            push(pos_); push(p);
+            path_.kinds.push_back(2);
+            pos_ = p;
+        }
+        return *this;
+    }
+    PathBuilder& quad_to(Point p1, Point p2) { push(pos_); push(p1); push(p2); path_.kinds.push_back(3); pos_ = p2; return *this; }
+    PathBuilder& cubic_to(Point p1, Point p2, Point p3) {
+        push(pos_); push(p1); push(p2); push(p3);
+        path_.kinds.push_back(4);
+        pos_ = p3;
+        return *this;
+    }
+    Path build() {
+        finish(false);
+        Path out = std::move(path_);
+        *this = PathBuilder();
+        return out;
+    }
+
+private:
+    void push(Point p) { path_.points.push_back(p.x); path_.points.push_back(p.y); }
+    void finish(bool close) {  // subpath_finish, src/path.rs:849-868
+        const uint32_t n = (uint32_t)path_.kinds.size();
+        if (n == 0 || (!path_.subpath_offsets.empty() && path_.subpath_offsets.back() == n)) return;
+        if (path_.subpath_offsets.empty()) path_.subpath_offsets.push_back(0);
+        if (close) {
+            size_t first = path_.subpath_offsets.back(), off = 0;
+            for (size_t i = 0; i < first; i++) off += path_.kinds[i];
+            pos_ = {path_.points[2 * off], path_.points[2 * off + 1]};
+        }
+        path_.subpath_offsets.push_back(n);
+        path_.closed.push_back(close ? 1 : 0);
+    }
+    Path path_;
+    Point pos_{0, 0};
+};
+inline PathBuilder Path::builder() { return PathBuilder(); }
+
+// Paint description handed to `Rasterizer::fill` (the `gpu_desc` hook of INTEGRATION.md §3)
+struct Paint {
+    rgpu_paint desc{};
+    std::vector<double> stop_pos;
+    std::vector<float> stop_colors;
+    static Paint solid(float r, float g, float b, float a) {
+        Paint p;
+        p.desc.kind = RGPU_PAINT_SOLID;
+        p.desc.tr[0] = p.desc.tr[4] = 1.0;
+        p.desc.solid[0] = r; p.desc.solid[1] = g; p.desc.solid[2] = b; p.desc.solid[3] = a;
+        return p;
+    }
+    const rgpu_paint* ffi() {
+        desc.n_stops = (uint32_t)stop_pos.size();
+        desc.stop_pos = stop_pos.data();
+        desc.stop_colors = stop_colors.data();
+        return &desc;
+    }
+};
+
+// `pub trait Rasterizer`, src/rasterize.rs:44-101
+class Rasterizer {
+public:
+    virtual ~Rasterizer() = default;
+    virtual const char* name() const = 0;
+    virtual void mask(const Path& path, Transform tr, ImageMut<Scalar> img, FillRule fill_rule) = 0;
+    virtual std::vector<Pixel> mask_iter(const Path& path, Transform tr, Size size, FillRule fill_rule) = 0;
+    virtual void fill(const Path& path, Transform tr, FillRule fill_rule, Paint& paint, ImageMut<float> img, const double* path_bbox = nullptr) = 0;
+};
+
+class GpuRasterizer final : public Rasterizer {
+public:
+    explicit GpuRasterizer(Scalar flatness = DEFAULT_FLATNESS, int device = 0) {
+        const int rc = rgpu_create(device, flatness, &ctx_);
+        if (rc != RGPU_OK) throw Error(rc, rgpu_last_error(nullptr));
+    }
+    ~GpuRasterizer() override { rgpu_destroy(ctx_); }
+    GpuRasterizer(const GpuRasterizer&) = delete;
+    GpuRasterizer& operator=(const GpuRasterizer&) = delete;
+
+    const char* name() const override { return rgpu_name(); }
+
+    void mask(const Path& path, Transform tr, ImageMut<Scalar> img, FillRule fill_rule) override {
+        const rgpu_path p = path.ffi();
+        check(rgpu_mask(ctx_, &p, tr.m, (int)fill_rule, img.data, img.shape));
+    }
+    std::vector<Pixel> mask_iter(const Path& path, Transform tr, Size size, FillRule fill_rule) override {
+        const rgpu_path p = path.ffi();
+        std::vector<rgpu_pixel> buf(size.width * size.height ? size.width * size.height : 1);
+        size_t n = 0;
+        check(rgpu_mask_iter(ctx_, &p, tr.m, size.width, size.height, (int)fill_rule, buf.data(), buf.size(), &n));
+        std::vector<Pixel> out(n);
+        for (size_t i = 0; i < n; i++) out[i] = {buf[i].x, buf[i].y, buf[i].alpha};
+        return out;
+    }
+    void fill(const Path& path, Transform tr, FillRule fill_rule, Paint& paint, ImageMut<float> img, const double* path_bbox = nullptr) override {
+        const rgpu_path p = path.ffi();
+        check(rgpu_fill(ctx_, &p, tr.m, (int)fill_rule, paint.ffi(), path_bbox, img.data, img.shape));
+    }
+    // `Path::flatten(tr, flatness, close)`: (x0,y0,x1,y1) per line, reference order
+    std::vector<double> flatten(const Path& path, Transform tr, bool close = true) {
+        const rgpu_path p = path.ffi();
+        std::vector<double> lines(4 * (path.segments_count() * 32 + 64));
+        size_t n = 0;
+        int rc = rgpu_flatten(ctx_, &p, tr.m, close, lines.data(), lines.size() / 4, &n);
+        if (rc == RGPU_ERR_CAPACITY) {
+            lines.resize(4 * n);
+            rc = rgpu_flatten(ctx_, &p, tr.m, close, lines.data(), n, &n);
+        }
+        check(rc);
+        lines.resize(4 * n);
+        return lines;
+    }
+    rgpu_ctx* raw() { return ctx_; }
+
+private:
+    void check(int rc) const {
+        if (rc != RGPU_OK) throw Error(rc, rgpu_last_error(ctx_));
+    }
+    rgpu_ctx* ctx_ = nullptr;
+};
+
+}  // namespace rasterize

@@ -1,0 +1,90 @@
+// C++ restatement of the reference's own rasterizer tests (src/rasterize.rs:1065-1161: test_rasterizer and
+// test_fill_rule) with the GpuRasterizer in the loop, through include/rasterize_b200.hpp -> the C ABI.
+// Built and run by tests/test_gpu_cpp_host.py on the GPU box.  Exit code 0 = all assertions hold.
+#include "rasterize_b200.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+
+using namespace rasterize;
+
+#define CHECK(cond)                                                        \
+    do {                                                                   \
+        if (!(cond)) {                                                     \
+            std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+            std::exit(1);                                                  \
+        }                                                                  \
+    } while (0)
+
+static void test_rasterizer(Rasterizer& rasterizer) {
+    const double expected[] = {
+        0.0, 1.0, 1.0,  1.0,  1.0, 1.0,  1.0,  1.0, 0.0,
+        0.0, 0.5, 1.0,  1.0,  1.0, 1.0,  1.0,  0.5, 0.0,
+        0.0, 0.0, 0.25, 0.75, 1.0, 0.75, 0.25, 0.0, 0.0,
+        0.0, 0.0, 0.0,  0.0,  0.0, 0.0,  0.0,  0.0, 0.0,
+    };
+    Path path = Path::builder()
+                    .move_to({1.0, 0.0}).line_to({1.0, 1.0}).line_to({2.0, 2.0}).line_to({4.0, 3.0}).line_to({5.0, 3.0})
+                    .line_to({7.0, 2.0}).line_to({8.0, 1.0}).line_to({8.0, 0.0}).close().build();
+    std::vector<double> img(9 * 4, 0.0);
+    rasterizer.mask(path, Transform::identity(), ImageMut<double>::dense(img.data(), 4, 9), FillRule::EvenOdd);
+    for (int i = 0; i < 36; i++) CHECK(std::fabs(img[i] - expected[i]) <= 1e-6);
+    // square that goes exactly through the sides of the image
+    Path sq = Path::builder().move_to({1, 1}).line_to({1, 3}).line_to({2, 3}).line_to({2, 1}).close().build();
+    std::vector<double> img2(9, 0.0);
+    rasterizer.mask(sq, Transform::identity(), ImageMut<double>::dense(img2.data(), 3, 3), FillRule::EvenOdd);
+}
+
+static void test_fill_rule(Rasterizer& rasterizer) {
+    // M50,0 21,90 98,35 2,35 79,90z M110,0 h90 v90 h-90z M130,20 h50 v50 h-50 z M210,0 h90 v90 h-90 z M230,20 v50 h50 v-50 z
+    Path path = Path::builder()
+                    .move_to({50, 0}).line_to({21, 90}).line_to({98, 35}).line_to({2, 35}).line_to({79, 90}).close()
+                    .move_to({110, 0}).line_to({200, 0}).line_to({200, 90}).line_to({110, 90}).close()
+                    .move_to({130, 20}).line_to({180, 20}).line_to({180, 70}).line_to({130, 70}).close()
+                    .move_to({210, 0}).line_to({300, 0}).line_to({300, 90}).line_to({210, 90}).close()
+                    .move_to({230, 20}).line_to({230, 70}).line_to({280, 70}).line_to({280, 20}).close()
+                    .build();
+    // Path::size: bbox (2,0)-(300,90) -> 300 x 92 image, shift = translate(1 - 2, 1 - 0)
+    const size_t w = 300, h = 92;
+    const Transform tr = Transform::new_translate(-1.0, 1.0);
+    std::vector<double> img(w * h, 0.0);
+    auto view = ImageMut<double>::dense(img.data(), h, w);
+    const size_t y = 50, x0 = 50, x1 = 150, x2 = 250;
+    rasterizer.mask(path, tr, view, FillRule::EvenOdd);
+    CHECK(std::fabs(view.at(y, x0)) < 1e-6 && std::fabs(view.at(y, x1)) < 1e-6 && std::fabs(view.at(y, x2)) < 1e-6);
+    double area = 0;
+    for (double v : img) area += v;
+    CHECK(std::fabs(area - 13130.0) < 1.0);
+    std::fill(img.begin(), img.end(), 0.0);
+    rasterizer.mask(path, tr, view, FillRule::NonZero);
+    CHECK(std::fabs(view.at(y, x0) - 1.0) < 1e-6 && std::fabs(view.at(y, x1) - 1.0) < 1e-6 && std::fabs(view.at(y, x2)) < 1e-6);
+    area = 0;
+    for (double v : img) area += v;
+    CHECK(std::fabs(area - 16492.5) < 1.0);
+    // mask_iter never yields pixels outside the size and agrees with mask away from the overflow column
+    auto px = rasterizer.mask_iter(path, tr, Size{w, h}, FillRule::NonZero);
+    CHECK(!px.empty());
+    for (const Pixel& p : px) {
+        CHECK(p.x < w && p.y < h && std::fabs(p.alpha) >= 1e-6);
+        if (p.x + 1 < w) CHECK(std::fabs(p.alpha - view.at(p.y, p.x)) <= 1e-4);
+    }
+    // fill: solid paint over a transparent LinColor image
+    std::vector<float> lin(w * h * 4, 0.f);
+    Paint red = Paint::solid(0.5f, 0.0f, 0.0f, 0.5f);
+    rasterizer.fill(path, tr, FillRule::NonZero, red, ImageMut<float>{lin.data(), rgpu_shape{0, w, h, w, 1}});
+    CHECK(std::fabs(lin[(y * w + x0) * 4 + 3] - 0.5f) < 1e-4f && std::fabs(lin[(y * w + x2) * 4 + 3]) < 1e-6f);
+}
+
+int main() {
+    GpuRasterizer r;
+    CHECK(std::string(r.name()) == "gpu-signed-difference");
+    test_rasterizer(r);
+    test_fill_rule(r);
+    // NaN control point -> error (reference panics, src/path.rs:765-767)
+    Path bad = Path::builder().move_to({0, 0}).quad_to({std::nan(""), 1}, {2, 2}).build();
+    bool threw = false;
+    try { r.flatten(bad, Transform::identity()); } catch (const Error& e) { threw = e.code == RGPU_ERR_NAN; }
+    CHECK(threw);
+    std::puts("cpp host tests ok");
+    return 0;
+}
