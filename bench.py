@@ -298,8 +298,9 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         h2d = path.points.nbytes + path.kinds.nbytes + path.subpath_offsets.nbytes + path.closed.nbytes
-        e2e = {"value": round(w * h * world / dt / 1e6, 1), "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(img.nbytes),
-               "ms_per_call": round(dt * 1e3, 4), "call": "rgpu_mask (f64 strided host image, pinned)"}
+        e2e = {"value": round(w * h * world / dt / 1e6, 1), "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(w * h * 4),
+               "ms_per_call": round(dt * 1e3, 4),
+               "call": "rgpu_mask: host path in, f64 host image out (f32 crosses PCIe in chunks, widened to f64 on the host while later chunks copy)"}
         # f32 variant of the same call, for context
         img32 = rast.host_alloc((h, w), np.float32)
         rast.mask(path, tr, img32, rb.FillRule.NonZero)
