@@ -10,8 +10,11 @@
 // operand order follows the reference expression trees exactly.
 //
 // Parallelisation: the subdivision tree of every item is cut at depth 3; each of the 8 subtrees ("slots") is
-// walked depth-first by its own thread with an explicit stack of pending right halves.  A count pass sizes
-// every slot, an exclusive scan places them, an emit pass writes the lines in the reference's order.
+// walked depth-first by its own thread with an explicit stack of pending right halves.
+//   * `rgpu_flatten` (ordered): a count pass sizes every slot, an exclusive scan places them, an emit pass writes
+//     the lines in the reference's order.
+//   * raster path: the walk is fused with binning — pass 0 counts lines per tile, pass 1 writes every line straight
+//     into the bins of the tiles it touches (flatten_bin_kernel); no global line buffer.
 #include "flatten_device.cuh"
 
 namespace rgpu {
@@ -55,57 +58,6 @@ flatten_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t total_
     } else {
         slot_counts[t] = slot_walk(c, thr, status, [](double, double, double, double) {});
     }
-}
-
-// Unordered single-kernel form for the raster path (accumulation does not care about line order): every thread
-// counts its slot, the CTA reserves one contiguous range with a single atomic, every thread walks its slot again
-// and writes.  Same arithmetic, same lines, no slot arrays, no scan, one launch.
-__global__ void __launch_bounds__(128)
-flatten_fused_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t total_items, double thr, double4* __restrict__ lines,
-                     uint32_t* __restrict__ line_job, uint32_t lines_cap, Status* __restrict__ status) {
-    __shared__ uint32_t s_warp[4];
-    __shared__ uint32_t s_base;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t total_slots = total_items * kSlotsPerItem;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    SlotCtx c;
-    const bool ok = t < total_slots && slot_setup(jobs, n_jobs, t, thr, c, status);
-    // finite control points cannot produce NaN below: skip the per-node has_nans test (see seg_all_finite)
-    const bool fin = ok && seg_all_finite(c.seg, c.kind);
-    auto nop = [](double, double, double, double) {};
-    const uint32_t count = !ok ? 0u : (fin ? slot_walk<false>(c, thr, status, nop) : slot_walk<true>(c, thr, status, nop));
-    uint32_t incl = count;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += nb;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t before = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < 4; w++) {
-        const uint32_t v = s_warp[w];
-        if (w < warp) before += v;
-        total += v;
-    }
-    if (threadIdx.x == 0) s_base = total ? atomicAdd(&status->n_lines, total) : 0u;
-    __syncthreads();
-    if (count == 0) return;
-    const uint32_t base = s_base;
-    if (base + total > lines_cap || base + total < base) {  // capacity exceeded: flag, the host grows and re-runs
-        atomicExch(&status->lines_overflow, 1u);
-        return;
-    }
-    uint32_t out = base + before + incl - count;
-    const uint32_t j = c.job;
-    auto emit = [&](double x0, double y0, double x1, double y1) {
-        lines[out] = make_double4(x0, y0, x1, y1);
-        if (line_job) line_job[out] = j;
-        out++;
-    };
-    if (fin) slot_walk<false>(c, thr, status, emit);
-    else slot_walk<true>(c, thr, status, emit);
 }
 
 // Flatten fused with binning.  PASS 0: count lines per tile; PASS 1: write lines into their bins.
@@ -161,13 +113,6 @@ void launch_flatten_emit(const JobDev* jobs, uint32_t n_jobs, uint32_t total_ite
     uint32_t n = total_items * kSlotsPerItem;
     if (n == 0) return;
     flatten_kernel<true><<<(n + 127) / 128, 128, 0, s>>>(jobs, n_jobs, total_items, thr, nullptr, slot_offs, lines, lines_cap, status);
-}
-
-void launch_flatten_fused(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, double4* lines, uint32_t* line_job,
-                          uint32_t lines_cap, Status* status, cudaStream_t s) {
-    uint32_t n = total_items * kSlotsPerItem;
-    if (n == 0) return;
-    flatten_fused_kernel<<<(n + 127) / 128, 128, 0, s>>>(jobs, n_jobs, total_items, thr, lines, line_job, lines_cap, status);
 }
 
 static inline int log2i(int v) {

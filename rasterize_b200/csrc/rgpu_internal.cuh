@@ -81,10 +81,6 @@ size_t scan_temp_bytes(uint32_t n);
 // `temp` must be zero on entry; pass temp_is_zero = true when the caller has already cleared it
 void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, void* temp, size_t temp_bytes, cudaStream_t s,
                            bool temp_is_zero = false);
-// Unordered single-kernel flatten for the raster path: count + CTA-level reservation + emit (see flatten.cu).
-// Writes status->n_lines (must be zero on entry) and, when line_job != nullptr, the job of every line.
-void launch_flatten_fused(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, double4* lines, uint32_t* line_job,
-                          uint32_t lines_cap, Status* status, cudaStream_t s);
 // Flatten fused with binning (raster path): pass 0 walks every slot and counts lines per tile (and in total, into
 // status->n_lines); after an exclusive scan of the tile counts, pass 1 walks again and writes every line straight
 // into the bins of the tiles it touches.  No global line buffer.
@@ -93,12 +89,6 @@ void launch_flatten_bin_count(const JobDev* jobs, uint32_t n_jobs, uint32_t tota
 void launch_flatten_bin_emit(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, const uint32_t* tile_offs,
                              uint32_t total_tiles, uint32_t* tile_cursor, double4* bin_lines, uint32_t refs_cap, int band_rows,
                              int chunk_cols, Status* status, cudaStream_t s);
-// slot_offs == nullptr: lines came from launch_flatten_fused (count in status->n_lines, jobs in line_job)
-void launch_bin_count(const JobDev* jobs, uint32_t n_jobs, const uint32_t* slot_offs, uint32_t total_slots, const uint32_t* line_job,
-                      const double4* lines, uint32_t* tile_counts, int band_rows, int chunk_cols, Status* status, cudaStream_t s);
-void launch_bin_fill(const JobDev* jobs, uint32_t n_jobs, const uint32_t* slot_offs, uint32_t total_slots, const uint32_t* line_job,
-                     const double4* lines, const uint32_t* tile_offs, uint32_t total_tiles, uint32_t* tile_cursor, double4* bin_lines,
-                     uint32_t refs_cap, int band_rows, int chunk_cols, Status* status, cudaStream_t s);
 // tile geometry of the raster kernel variants
 struct TileShape { int cw, th; };
 TileShape raster_tile_shape(int variant);
