@@ -30,6 +30,8 @@ namespace {
 
 thread_local std::string g_create_err;
 
+constexpr uint64_t kFixedBinBudget = 2ull << 30;  // bytes of fixed-capacity tile bins before the two-pass scheme takes over
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -73,6 +75,12 @@ struct rgpu_ctx {
     uint2* h_items = nullptr;          // pinned staging of the item list
     size_t h_items_cap = 0;
     size_t lines_cap = 0, refs_cap = 0;
+    // fixed-capacity tile bins (single flatten walk): bin_cap is the largest per-tile capacity any batch needed so
+    // far; a batch whose tiles x capacity exceeds kFixedBinBudget uses the exact count -> scan -> emit scheme
+    uint32_t bin_cap = 0;
+    bool two_pass = getenv("RGPU_TWO_PASS") != nullptr;  // A/B switch: always use the exact two-pass scheme
+    bool last_fixed = false;
+    uint32_t last_tiles = 0;
     // pinned host
     Status* h_status = nullptr;
     void* h_stage = nullptr;
@@ -444,21 +452,36 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         return RGPU_OK;
     }
 
-    // ---- raster path: [flatten + count per tile] -> scan -> [flatten + write bins] -> raster -------------------
-    size_t want_refs = std::max<uint64_t>(ctx->refs_cap, est_lines + est_lines / 2);
+    // ---- raster path -------------------------------------------------------------------------------------------
+    // fixed bins (default): [flatten + write fixed-capacity bins] -> raster               (2 launches)
+    // two-pass (fallback):  [flatten + count per tile] -> scan -> [flatten + write bins] -> raster
+    uint32_t bin_cap = 0;
+    if (!ctx->two_pass) {
+        // first guess: four times the average load the line estimate predicts; a tile that wants more raises
+        // refs_overflow + bin_max and the *_sync entry points re-run with the exact capacity
+        uint64_t avg = (est_lines + est_lines / 2) / std::max<uint32_t>(tile_acc, 1) + 1;
+        uint32_t guess = 64;
+        while (guess < 4 * avg && guess < 4096) guess <<= 1;
+        bin_cap = std::max(ctx->bin_cap, guess);
+        if ((uint64_t)bin_cap * tile_acc * sizeof(double4) > kFixedBinBudget) bin_cap = 0;
+    }
+    const bool fixed = bin_cap != 0;
+    ctx->last_fixed = fixed;
+    ctx->last_tiles = tile_acc;
+    size_t want_refs = fixed ? (size_t)bin_cap * tile_acc : std::max<uint64_t>(ctx->refs_cap, est_lines + est_lines / 2);
     if ((rc = ensure_dev(ctx, ctx->refs, sizeof(double4) * want_refs))) return rc;
     ctx->refs_cap = std::min<size_t>(ctx->refs.cap / sizeof(double4), 0xfffffff0u);
     // one block that must be zero at the start of every batch, cleared by ONE memset:
-    // [status | raster tickets | tile_counts | tile_cursor | scan tile states]
+    // [status | raster tickets | tile_counts | (two-pass only: tile_cursor | scan tile states)]
     const uint32_t n_raster_launches = (flags & RGPU_BATCH_INDEPENDENT) ? 1u : n_live;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t tickets_off = up(sizeof(Status));
     const size_t counts_off = tickets_off + up((size_t)n_raster_launches * 4);
     const size_t cursor_off = counts_off + up((size_t)(tile_acc + 1) * 4);
-    const size_t scan_off = cursor_off + up((size_t)(tile_acc + 1) * 4);
-    const size_t zero_bytes = scan_off + up(scan_temp_bytes(tile_acc + 1));
+    const size_t scan_off = cursor_off + (fixed ? 0 : up((size_t)(tile_acc + 1) * 4));
+    const size_t zero_bytes = scan_off + (fixed ? 0 : up(scan_temp_bytes(tile_acc + 1)));
     if ((rc = ensure_dev(ctx, ctx->zero_block, zero_bytes))) return rc;
-    if ((rc = ensure_dev(ctx, ctx->tile_offs, sizeof(uint32_t) * (tile_acc + 1)))) return rc;
+    if (!fixed && (rc = ensure_dev(ctx, ctx->tile_offs, sizeof(uint32_t) * (tile_acc + 1)))) return rc;
     // carry look-back state, validated by epoch (cleared only when (re)allocated or when the epoch wraps)
     {
         size_t need = sizeof(unsigned long long) * kStateRows * (size_t)tile_acc;
@@ -476,7 +499,7 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     uint32_t* d_bc = reinterpret_cast<uint32_t*>(zb + counts_off);
     uint32_t* d_cur = reinterpret_cast<uint32_t*>(zb + cursor_off);
     void* d_scan = zb + scan_off;
-    uint32_t* d_bo = static_cast<uint32_t*>(ctx->tile_offs.p);
+    uint32_t* d_bo = fixed ? d_bc : static_cast<uint32_t*>(ctx->tile_offs.p);
     double4* d_refs = static_cast<double4*>(ctx->refs.p);
     unsigned long long* d_state = static_cast<unsigned long long*>(ctx->tile_state.p);
 
@@ -484,19 +507,25 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     if (n_paints) CK(ctx, cudaMemcpyAsync(d_paints, ctx->h_paints, sizeof(PaintDev) * n_paints, cudaMemcpyHostToDevice, s));
     CK(ctx, cudaMemsetAsync(zb, 0, zero_bytes, s));
     if (prof) CK(ctx, cudaEventRecord(ctx->ev[0], s));
-    launch_flatten_bin_count(d_jobs, n_live, item_acc, thr, d_bc, ts.th, ts.cw, d_status, s);
-    if (prof) CK(ctx, cudaEventRecord(ctx->ev[1], s));
-    launch_exclusive_scan(d_bc, d_bo, tile_acc + 1, d_scan, 0, s, /*temp_is_zero=*/true);
-    launch_flatten_bin_emit(d_jobs, n_live, item_acc, thr, d_bo, tile_acc, d_cur, d_refs, (uint32_t)ctx->refs_cap, ts.th, ts.cw, d_status, s);
-    ctx->n_launches += 3;
+    if (fixed) {
+        launch_flatten_bin_fixed(d_jobs, n_live, item_acc, thr, d_bc, d_refs, bin_cap, ts.th, ts.cw, d_status, s);
+        ctx->n_launches += 1;
+        if (prof) CK(ctx, cudaEventRecord(ctx->ev[1], s));
+    } else {
+        launch_flatten_bin_count(d_jobs, n_live, item_acc, thr, d_bc, ts.th, ts.cw, d_status, s);
+        if (prof) CK(ctx, cudaEventRecord(ctx->ev[1], s));
+        launch_exclusive_scan(d_bc, d_bo, tile_acc + 1, d_scan, 0, s, /*temp_is_zero=*/true);
+        launch_flatten_bin_emit(d_jobs, n_live, item_acc, thr, d_bo, tile_acc, d_cur, d_refs, (uint32_t)ctx->refs_cap, ts.th, ts.cw, d_status, s);
+        ctx->n_launches += 3;
+    }
     if (prof) CK(ctx, cudaEventRecord(ctx->ev[2], s));
     if (flags & RGPU_BATCH_INDEPENDENT) {
-        launch_raster(variant, d_jobs, ctx->h_jobs, n_live, 0, 0, tile_acc, d_paints, d_bo, d_refs, d_state, ctx->epoch, d_tickets, d_status, s);
+        launch_raster(variant, d_jobs, ctx->h_jobs, n_live, 0, 0, tile_acc, d_paints, d_bo, bin_cap, d_refs, d_state, ctx->epoch, d_tickets, d_status, s);
         ctx->n_launches += 1;
     } else {
         for (uint32_t j = 0; j < n_live; j++) {
             const JobDev& d = ctx->h_jobs[j];
-            launch_raster(variant, d_jobs, ctx->h_jobs, 1, j, d.tile_begin, d.n_bands * d.n_chunks, d_paints, d_bo, d_refs, d_state,
+            launch_raster(variant, d_jobs, ctx->h_jobs, 1, j, d.tile_begin, d.n_bands * d.n_chunks, d_paints, d_bo, bin_cap, d_refs, d_state,
                           ctx->epoch, d_tickets + j, d_status, s);
             ctx->n_launches += 1;
         }
@@ -547,12 +576,18 @@ int submit_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t fla
             }
             nl = (size_t)total + total / 16 + 64;
         }
-        size_t nr = st.refs_overflow ? (size_t)st.n_refs + st.n_refs / 16 + 64 : std::max<size_t>(ctx->refs_cap, nl * 2);
         int rc2;
         if (ordered_lines) {
             if ((rc2 = ensure_dev(ctx, ctx->lines, sizeof(double4) * nl))) return rc2;
             ctx->lines_cap = ctx->lines.cap / sizeof(double4);
+        } else if (ctx->last_fixed) {
+            // a tile wanted more lines than its fixed bin holds: bin_max is exact (every line took a slot number),
+            // so one re-run with that capacity succeeds
+            uint32_t want = st.bin_max + st.bin_max / 8 + 8;
+            want = (want + 31u) & ~31u;
+            ctx->bin_cap = std::max(ctx->bin_cap, want);  // submit() falls back to two-pass if this blows the budget
         } else {
+            size_t nr = st.refs_overflow ? (size_t)st.n_refs + st.n_refs / 16 + 64 : std::max<size_t>(ctx->refs_cap, nl * 2);
             if ((rc2 = ensure_dev(ctx, ctx->refs, sizeof(double4) * nr))) return rc2;
             ctx->refs_cap = ctx->refs.cap / sizeof(double4);
         }

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(128)
 flatten_bin_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t total_items, double thr, uint32_t* __restrict__ tile_counts,
                    const uint32_t* __restrict__ tile_offs, uint32_t total_tiles, double4* __restrict__ bin_lines, uint32_t refs_cap,
                    int band_shift, int chunk_shift, Status* __restrict__ status) {
+    // PASS 2 = single pass with fixed-capacity bins: refs_cap is the per-tile capacity
     if (PASS == 1) {
         if (status->nan_flag | status->depth_flag) return;
         const uint32_t n_refs = tile_offs[total_tiles];
@@ -81,22 +82,36 @@ flatten_bin_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t to
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t total_slots = total_items * kSlotsPerItem;
     SlotCtx c;
-    uint32_t count = 0;
+    uint32_t count = 0, n_refs = 0;
     if (t < total_slots && slot_setup(jobs, n_jobs, t, thr, c, status)) {
         const JobDev& job = jobs[c.job];
         auto emit = [&](double x0, double y0, double x1, double y1) {
             for_each_tile(job, x0, y0, x1, y1, band_shift, chunk_shift, [&](uint32_t key) {
                 const uint32_t slot = atomicAdd(&tile_counts[key], 1u);
                 if (PASS == 1) bin_lines[tile_offs[key] + slot] = make_double4(x0, y0, x1, y1);
+                if (PASS == 2) {
+                    n_refs++;
+                    if (slot < refs_cap) {
+                        bin_lines[(size_t)key * refs_cap + slot] = make_double4(x0, y0, x1, y1);
+                    } else {
+                        status->refs_overflow = 1u;
+                        atomicMax(&status->bin_max, slot + 1u);
+                    }
+                }
             });
         };
         // finite control points cannot produce NaN below: skip the per-node has_nans test (see seg_all_finite)
         count = seg_all_finite(c.seg, c.kind) ? slot_walk<false>(c, thr, status, emit) : slot_walk<true>(c, thr, status, emit);
     }
-    if (PASS == 0) {  // total line count of the batch (statistics): one atomic per warp
+    if (PASS != 1) {  // total line count of the batch (statistics): one atomic per warp
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
         if ((threadIdx.x & 31) == 0 && count) atomicAdd(&status->n_lines, count);
+    }
+    if (PASS == 2) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_refs += __shfl_xor_sync(0xffffffffu, n_refs, o);
+        if ((threadIdx.x & 31) == 0 && n_refs) atomicAdd(&status->n_refs, n_refs);
     }
 }
 
@@ -136,6 +151,14 @@ void launch_flatten_bin_emit(const JobDev* jobs, uint32_t n_jobs, uint32_t total
     if (n == 0) return;
     flatten_bin_kernel<1><<<(n + 127) / 128, 128, 0, s>>>(jobs, n_jobs, total_items, thr, tile_cursor, tile_offs, total_tiles, bin_lines,
                                                           refs_cap, log2i(band_rows), log2i(chunk_cols), status);
+}
+
+void launch_flatten_bin_fixed(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, uint32_t* tile_counts,
+                              double4* bin_lines, uint32_t bin_cap, int band_rows, int chunk_cols, Status* status, cudaStream_t s) {
+    uint32_t n = total_items * kSlotsPerItem;
+    if (n == 0) return;
+    flatten_bin_kernel<2><<<(n + 127) / 128, 128, 0, s>>>(jobs, n_jobs, total_items, thr, tile_counts, nullptr, 0, bin_lines, bin_cap,
+                                                          log2i(band_rows), log2i(chunk_cols), status);
 }
 
 }  // namespace rgpu

@@ -155,9 +155,9 @@ __device__ __forceinline__ void scan_rows(const JobDev& job, const PaintDev& s_p
 template <int CW, int TH, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first, const JobDev one_job,
-              const PaintDev* __restrict__ paints, const uint32_t* __restrict__ tile_offs, const double4* __restrict__ bin_lines,
-              unsigned long long* __restrict__ tile_state, uint32_t epoch, uint32_t* __restrict__ ticket,
-              const Status* __restrict__ status) {
+              const PaintDev* __restrict__ paints, const uint32_t* __restrict__ tile_offs, uint32_t bin_cap,
+              const double4* __restrict__ bin_lines, unsigned long long* __restrict__ tile_state, uint32_t epoch,
+              uint32_t* __restrict__ ticket, const Status* __restrict__ status) {
     using Cfg = TileCfg<CW, TH, THREADS>;
     constexpr int L = Cfg::kL;
     static_assert(TH <= 64 && CW % 128 == 0 && L % 4 == 0, "tile shape");
@@ -217,7 +217,14 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     // ---- phase 1: accumulate the tile's lines.  Warps work independently: 32 lines per round per warp ------
     // (see warp_accumulate_round: 1a one line per lane, spans compacted per warp; 1b one lane per span)
     unsigned short* spans = spans_all + warp * Cfg::kWarpSpanCap;
-    const uint32_t rbeg = tile_offs[tile], rend = tile_offs[tile + 1];
+    uint32_t rbeg, rend;
+    if (bin_cap) {  // fixed-capacity bins: tile_offs holds the per-tile counts
+        rbeg = tile * bin_cap;
+        rend = rbeg + min(tile_offs[tile], bin_cap);
+    } else {
+        rbeg = tile_offs[tile];
+        rend = tile_offs[tile + 1];
+    }
     if (rbeg < rend) {  // tiles without lines never read their cells (row_touched stays 0): no need to clear them
         const int4 z = make_int4(0, 0, 0, 0);
         int4* c4 = reinterpret_cast<int4*>(cells);
@@ -299,7 +306,7 @@ __global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restri
 
 template <int CW, int TH, int THREADS>
 static void launch_raster_t(const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
-                            uint32_t n_tiles, const PaintDev* paints, const uint32_t* tile_offs, const double4* bin_lines,
+                            uint32_t n_tiles, const PaintDev* paints, const uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
                             unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, cudaStream_t s) {
     constexpr size_t smem = TileCfg<CW, TH, THREADS>::smem_bytes();
     static bool configured[64] = {};  // per template instance and per device: the attribute belongs to the device's function
@@ -310,7 +317,7 @@ static void launch_raster_t(const JobDev* jobs, const JobDev* h_jobs, uint32_t n
         configured[dev] = true;
     }
     raster_kernel<CW, TH, THREADS><<<n_tiles, THREADS, smem, s>>>(jobs, n_jobs, job_first, tile_first, h_jobs[job_first], paints, tile_offs,
-                                                                  bin_lines, tile_state, epoch, ticket, status);
+                                                                  bin_cap, bin_lines, tile_state, epoch, ticket, status);
 }
 
 TileShape raster_tile_shape(int variant) {
@@ -324,12 +331,12 @@ TileShape raster_tile_shape(int variant) {
 }
 
 void launch_raster(int variant, const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
-                   uint32_t n_tiles, const PaintDev* paints, const uint32_t* tile_offs, const double4* bin_lines,
+                   uint32_t n_tiles, const PaintDev* paints, const uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
                    unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, cudaStream_t s) {
     if (n_tiles == 0) return;
 #define RGPU_LAUNCH(CW, TH, THREADS)                                                                                              \
-    launch_raster_t<CW, TH, THREADS>(jobs, h_jobs, n_jobs, job_first, tile_first, n_tiles, paints, tile_offs, bin_lines, tile_state, epoch, \
-                                     ticket, status, s)
+    launch_raster_t<CW, TH, THREADS>(jobs, h_jobs, n_jobs, job_first, tile_first, n_tiles, paints, tile_offs, bin_cap, bin_lines, tile_state, \
+                                     epoch, ticket, status, s)
     switch (variant) {
         case 1: RGPU_LAUNCH(128, 64, 256); break;
         case 2: RGPU_LAUNCH(512, 8, 128); break;
