@@ -314,10 +314,6 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     uint32_t max_w = 0;
     for (size_t j = 0; j < n_jobs; j++) max_w = std::max(max_w, jobs[j].width);
     int variant = (max_w <= 128) ? 1 : 0;
-    if (variant == 0) {
-        static const int forced = getenv("RGPU_TILE_VARIANT") ? atoi(getenv("RGPU_TILE_VARIANT")) : 0;  // tuning knob
-        if (forced >= 2 && forced <= 4) variant = forced;
-    }
     TileShape ts = raster_tile_shape(variant);
 
     uint32_t item_acc = 0, band_acc = 0, tile_acc = 0, n_paints = 0;
@@ -519,14 +515,15 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         ctx->n_launches += 3;
     }
     if (prof) CK(ctx, cudaEventRecord(ctx->ev[2], s));
+    const bool zero_early = est_lines + est_lines / 2 >= 2ull * tile_acc;  // most tiles will hold lines
     if (flags & RGPU_BATCH_INDEPENDENT) {
-        launch_raster(variant, d_jobs, ctx->h_jobs, n_live, 0, 0, tile_acc, d_paints, d_bo, bin_cap, d_refs, d_state, ctx->epoch, d_tickets, d_status, s);
+        launch_raster(variant, d_jobs, ctx->h_jobs, n_live, 0, 0, tile_acc, d_paints, d_bo, bin_cap, d_refs, d_state, ctx->epoch, d_tickets, d_status, zero_early, s);
         ctx->n_launches += 1;
     } else {
         for (uint32_t j = 0; j < n_live; j++) {
             const JobDev& d = ctx->h_jobs[j];
             launch_raster(variant, d_jobs, ctx->h_jobs, 1, j, d.tile_begin, d.n_bands * d.n_chunks, d_paints, d_bo, bin_cap, d_refs, d_state,
-                          ctx->epoch, d_tickets + j, d_status, s);
+                          ctx->epoch, d_tickets + j, d_status, zero_early, s);
             ctx->n_launches += 1;
         }
     }

@@ -61,9 +61,10 @@ flatten_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t total_
 }
 
 // Flatten fused with binning.  PASS 0: count lines per tile; PASS 1: write lines into their bins.
-// (A CTA-level shared-memory aggregation of the tile counters was tried and measured slower: the cost of these
-// passes is the per-leaf tile-range arithmetic inside the divergent walk, not the global atomics — ~35 lines per
-// tile counter spread over the whole launch.)
+// Tried and measured no faster on C2 / C5 (round 1): CTA-level shared-memory aggregation of the tile counters; deferring
+// the bin store behind the next leaf; and a warp work-sharing schedule (32 lanes on a shared LIFO of pending nodes in
+// shared memory, critical path = subdivision depth) — its tail is set by runs of heavy curves landing in one warp, and
+// with batches small enough to avoid that (strided, 8 items) it ties this kernel (33 us on C2); only C5 gained (31 -> 22 us).
 template <int PASS>
 __global__ void __launch_bounds__(128)
 flatten_bin_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t total_items, double thr, uint32_t* __restrict__ tile_counts,

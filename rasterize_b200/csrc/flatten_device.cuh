@@ -32,6 +32,9 @@ __device__ __forceinline__ bool seg_has_nan(const Seg& s, int kind) {
     return n;
 }
 
+// Curve::end(): selected without a runtime array index, which would push the whole Seg into local memory
+__device__ __forceinline__ P2 seg_end(const Seg& s, int kind) { return kind == 4 ? s.p[3] : (kind == 3 ? s.p[2] : s.p[1]); }
+
 // Rust f64::max: NaN operands are ruled out by has_nans before this is evaluated
 __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
 
@@ -169,7 +172,8 @@ __device__ __forceinline__ uint32_t slot_walk(const SlotCtx& c, double thr, Stat
     const int kind = c.kind;
     Seg seg = c.seg;
     if (c.leaf_above) {
-        emit(seg.p[0].x, seg.p[0].y, seg.p[kind - 1].x, seg.p[kind - 1].y);
+        const P2 e = seg_end(seg, kind);
+        emit(seg.p[0].x, seg.p[0].y, e.x, e.y);
         return 1;
     }
     Seg stack[kMaxStack];
@@ -178,7 +182,8 @@ __device__ __forceinline__ uint32_t slot_walk(const SlotCtx& c, double thr, Stat
     while (true) {
         if (CHECK_NAN && seg_has_nan(seg, kind)) { atomicExch(&status->nan_flag, 1u); break; }
         if (seg_flatness(seg, kind) < thr) {
-            emit(seg.p[0].x, seg.p[0].y, seg.p[kind - 1].x, seg.p[kind - 1].y);
+            const P2 e = seg_end(seg, kind);
+            emit(seg.p[0].x, seg.p[0].y, e.x, e.y);
             count++;
             if (top == 0) break;
             seg = stack[--top];

@@ -19,6 +19,8 @@
 // carry look-back are exact integers and the result is bit-identical from run to run.
 #include "raster_device.cuh"
 
+#include <type_traits>
+
 namespace rgpu {
 
 namespace {
@@ -29,33 +31,36 @@ using namespace rs;
 template <int CW, int TH, int THREADS>
 struct TileCfg {
     static constexpr int kL = CW / 32;
-    static constexpr int kPitch = CW + 4 * 32;               // 32 runs of L columns, 4 padding ints each
     static constexpr int kWarps = THREADS / 32;
     static constexpr int kRowBits = (TH <= 8) ? 3 : 6;
-    static constexpr int kWarpSpanCap = (TH <= 8) ? 32 * TH : 512;  // per-warp span list entries
-    static constexpr size_t smem_bytes() {
-        return sizeof(int) * TH * kPitch + sizeof(double) * 4 * THREADS + sizeof(float) * THREADS +
-               sizeof(unsigned short) * kWarpSpanCap * kWarps;
-    }
+    // per-warp span list: (source lane, band row) packed in a byte when the row fits 3 bits
+    using SpanT = typename std::conditional<(TH <= 8), unsigned char, unsigned short>::type;
+    static constexpr int kWarpSpanCap = (TH <= 8) ? 224 : 512;  // lanes that do not fit do their rows serially
+    static constexpr size_t kCellBytes = sizeof(int) * TH * CW;
+    static constexpr size_t kPieceBytes = sizeof(double) * 4 * THREADS;  // reused for the paint in the scan phase
+    static constexpr size_t smem_bytes() { return kCellBytes + kPieceBytes + sizeof(SpanT) * kWarpSpanCap * kWarps; }
+    static_assert(kPieceBytes >= sizeof(PaintDev), "the paint is staged over the piece constants");
 };
 
+// Phase 2 for the rows of one warp.  Lane l owns L consecutive columns: serial prefix in registers, ONE warp scan of the
+// 32 lane totals, coverage written back to shared memory in place (as floats) and read back transposed so that global
+// stores are full 512 B coalesced 128-bit accesses.  Rows no line touched are written straight from registers.
 template <int CW, int TH, int THREADS, bool EVENODD, class Cfg>
 __device__ __forceinline__ void scan_rows(const JobDev& job, const PaintDev& s_paint, int* cells, const int* carry, const int* row_touched,
                                           int row0, int row1, int cx0, int mode, int tid) {
     constexpr int L = Cfg::kL;
     constexpr int NQ = L / 4;  // 128-bit words per lane run
     const int warp = tid >> 5, lane = tid & 31;
-    const int wout = job.width_out;
-    const int bw = min(wout - cx0, CW);  // visible columns of this tile
+    const int bw = min(job.width_out - cx0, CW);  // visible columns of this tile
     for (int r = warp; r < row1 - row0; r += Cfg::kWarps) {
         const int acc = carry[r];
-        int* bc = cells + r * Cfg::kPitch;
+        int* bc = cells + r * CW;
         const int y = row0 + r;
         if (row_touched[r]) {
             int v[L];
 #pragma unroll
             for (int i = 0; i < NQ; i++) {
-                const int4 q = *reinterpret_cast<const int4*>(bc + lane * (L + 4) + i * 4);
+                const int4 q = *reinterpret_cast<const int4*>(bc + swz<true>(lane * L + i * 4));
                 v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
             }
 #pragma unroll
@@ -71,7 +76,7 @@ __device__ __forceinline__ void scan_rows(const JobDev& job, const PaintDev& s_p
             for (int i = 0; i < NQ; i++) {
                 const float4 cv = make_float4(coverage_from_fixed<EVENODD>(base + v[4 * i]), coverage_from_fixed<EVENODD>(base + v[4 * i + 1]),
                                               coverage_from_fixed<EVENODD>(base + v[4 * i + 2]), coverage_from_fixed<EVENODD>(base + v[4 * i + 3]));
-                *reinterpret_cast<float4*>(bc + lane * (L + 4) + i * 4) = cv;
+                *reinterpret_cast<float4*>(bc + swz<true>(lane * L + i * 4)) = cv;
             }
         } else {
             float c = coverage_from_fixed<EVENODD>(acc);  // no line touched this row of the tile: constant coverage
@@ -80,59 +85,49 @@ __device__ __forceinline__ void scan_rows(const JobDev& job, const PaintDev& s_p
                 if (mode == kModeCoverage && c < 1e-6f) c = 0.f;
                 const float4 cv = make_float4(c, c, c, c);
                 float* out = reinterpret_cast<float*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride + cx0;
-                const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+                if (bw == CW && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
 #pragma unroll
-                for (int i = 0; i < CW / 128; i++) {
-                    const int col = i * 128 + lane * 4;
-                    if (col < bw) {
-                        if (vec_ok && col + 3 < bw) {
-                            __stcs(reinterpret_cast<float4*>(out + col), cv);
-                        } else {
-                            out[col] = c;
-                            if (col + 1 < bw) out[col + 1] = c;
-                            if (col + 2 < bw) out[col + 2] = c;
-                            if (col + 3 < bw) out[col + 3] = c;
-                        }
-                    }
+                    for (int i = 0; i < CW / 128; i++) __stcs(reinterpret_cast<float4*>(out + i * 128 + lane * 4), cv);
+                } else {
+                    for (int col = lane; col < bw; col += 32) out[col] = c;
                 }
                 continue;
             }
             if (c < 1e-6f) continue;  // FILL: nothing to composite on this row
             const float4 cv = make_float4(c, c, c, c);
 #pragma unroll
-            for (int i = 0; i < NQ; i++) *reinterpret_cast<float4*>(bc + lane * (L + 4) + i * 4) = cv;
+            for (int i = 0; i < NQ; i++) *reinterpret_cast<float4*>(bc + swz<true>(lane * L + i * 4)) = cv;
         }
         __syncwarp();
         // transposed read-back: lane l takes columns [128*i + 4l, +4): full 512 B coalesced 128-bit stores
         if (mode != kModeFill) {
             float* out = reinterpret_cast<float*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride + cx0;
-            const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+            if (bw == CW && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {  // whole, aligned tile row: no per-word tests
 #pragma unroll
-            for (int i = 0; i < CW / 128; i++) {
-                const int col = i * 128 + lane * 4;
-                if (col < bw) {
-                    float4 cv = *reinterpret_cast<const float4*>(bc + swz<L>(col));
+                for (int i = 0; i < CW / 128; i++) {
+                    const int col = i * 128 + lane * 4;
+                    float4 cv = *reinterpret_cast<const float4*>(bc + swz<true>(col));
                     if (mode == kModeCoverage) {  // mask_iter drops abs(alpha) < 1e-6 (src/rasterize.rs:348)
                         if (cv.x < 1e-6f) cv.x = 0.f;
                         if (cv.y < 1e-6f) cv.y = 0.f;
                         if (cv.z < 1e-6f) cv.z = 0.f;
                         if (cv.w < 1e-6f) cv.w = 0.f;
                     }
-                    if (vec_ok && col + 3 < bw) {
-                        __stcs(reinterpret_cast<float4*>(out + col), cv);  // streaming store: written once, never re-read
-                    } else {
-                        out[col] = cv.x;
-                        if (col + 1 < bw) out[col + 1] = cv.y;
-                        if (col + 2 < bw) out[col + 2] = cv.z;
-                        if (col + 3 < bw) out[col + 3] = cv.w;
-                    }
+                    __stcs(reinterpret_cast<float4*>(out + col), cv);  // streaming store: written once, never re-read
+                }
+            } else {
+                const float* covs = reinterpret_cast<const float*>(bc);
+                for (int col = lane; col < bw; col += 32) {
+                    float cvx = covs[swz<true>(col)];
+                    if (mode == kModeCoverage && cvx < 1e-6f) cvx = 0.f;
+                    out[col] = cvx;
                 }
             }
         } else {
             float4* out = reinterpret_cast<float4*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride + cx0;
             const float* covs = reinterpret_cast<const float*>(bc);
             for (int px = lane; px < bw; px += 32) {  // consecutive lanes composite consecutive pixels (16 B each)
-                const float alpha = covs[swz<L>(px)];
+                const float alpha = covs[swz<true>(px)];
                 if (alpha >= 1e-6f) {
                     float4 color = (job.paint_index >= 0) ? paint_at(s_paint, cx0 + px, y) : make_float4(0.f, 0.f, 0.f, 0.f);
                     // with_alpha: self * (alpha as f32), src/color.rs:347-349
@@ -153,29 +148,28 @@ __device__ __forceinline__ void scan_rows(const JobDev& job, const PaintDev& s_p
 // `one_job`: the launch covers a single job whose descriptor travels in the kernel parameters (constant bank:
 // no dependent global loads before the tile can start).
 template <int CW, int TH, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, (TH <= 8 ? 6 : 2))
 raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first, const JobDev one_job,
               const PaintDev* __restrict__ paints, const uint32_t* __restrict__ tile_offs, uint32_t bin_cap,
               const double4* __restrict__ bin_lines, unsigned long long* __restrict__ tile_state, uint32_t epoch,
-              uint32_t* __restrict__ ticket, const Status* __restrict__ status) {
+              uint32_t* __restrict__ ticket, const Status* __restrict__ status, uint32_t zero_early) {
     using Cfg = TileCfg<CW, TH, THREADS>;
-    constexpr int L = Cfg::kL;
-    static_assert(TH <= 64 && CW % 128 == 0 && L % 4 == 0, "tile shape");
-    // dynamic shared memory: cells | piece constants | per-warp span lists
+    using SpanT = typename Cfg::SpanT;
+    static_assert(TH <= 64 && CW % 128 == 0 && Cfg::kL % 4 == 0, "tile shape");
+    // dynamic shared memory: cells | piece constants (later: the paint) | per-warp span lists
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int* cells = reinterpret_cast<int*>(smem_raw);
-    double* p_ax = reinterpret_cast<double*>(smem_raw + sizeof(int) * TH * Cfg::kPitch);
+    double* p_ax = reinterpret_cast<double*>(smem_raw + Cfg::kCellBytes);
     double* p_ay = p_ax + THREADS;
     double* p_by = p_ay + THREADS;
     double* p_dxdy = p_by + THREADS;
-    float* p_dir = reinterpret_cast<float*>(p_dxdy + THREADS);
-    unsigned short* spans_all = reinterpret_cast<unsigned short*>(p_dir + THREADS);
+    SpanT* spans_all = reinterpret_cast<SpanT*>(p_dxdy + THREADS);
+    const PaintDev& s_paint = *reinterpret_cast<const PaintDev*>(p_ax);
     __shared__ int carry[TH];
     __shared__ int rowtot[TH];
     __shared__ int row_touched[TH];
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_job;
-    __shared__ PaintDev s_paint;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -183,6 +177,15 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     uint32_t my_ticket = 0;
     if (tid == 0) my_ticket = atomicAdd(ticket, 1u);
     const uint32_t bad = status->lines_overflow | status->refs_overflow | status->nan_flag | status->depth_flag;
+    // dense batches clear the cells while the ticket is on its way; sparse ones (most tiles without a line) clear only
+    // the tiles that need it, once the tile is known
+    auto clear_cells = [&]() {
+        const int4 z = make_int4(0, 0, 0, 0);
+        int4* c4 = reinterpret_cast<int4*>(cells);
+#pragma unroll 4
+        for (int i = tid; i < TH * CW / 4; i += THREADS) c4[i] = z;
+    };
+    if (zero_early) clear_cells();
     if (tid < TH) { carry[tid] = 0; rowtot[tid] = 0; row_touched[tid] = 0; }
     if (tid == 0) {
         const uint32_t t = tile_first + my_ticket;
@@ -191,11 +194,15 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     }
     __syncthreads();
     if (bad) return;
-    const uint32_t tile = s_tile;
     const JobDev& job = (n_jobs == 1) ? one_job : jobs[s_job];
-    const uint32_t lt = tile - job.tile_begin;
-    const int band = (int)(lt / job.n_chunks);
-    const int chunk = (int)(lt - (uint32_t)band * job.n_chunks);
+    // Tiles are taken in CHUNK-major order (all bands of column chunk 0, then chunk 1, ...): the left neighbour a tile's
+    // carry depends on was started a whole column of bands earlier, so it has normally published its inclusive prefix by
+    // the time this tile looks back — band-major order would start the tiles of a band together and make every tile wait
+    // for the slowest one to its left.  Bins and look-back state stay indexed band-major.
+    const uint32_t lt = s_tile - job.tile_begin;
+    const int chunk = (int)(lt / job.n_bands);
+    const int band = (int)(lt - (uint32_t)chunk * job.n_bands);
+    const uint32_t tile = job.tile_begin + (uint32_t)band * job.n_chunks + (uint32_t)chunk;
     TileGeom g;
     g.row0 = band * TH;
     g.row1 = min(g.row0 + TH, job.height);
@@ -203,20 +210,14 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     g.wc = job.clamp_w;
     g.wci = (int)g.wc;
     g.tile_end = g.cx0 + min(CW, g.wci + 1 - g.cx0);  // columns that exist in the reference image (incl. overflow column)
-    g.pitch = Cfg::kPitch;
+    g.pitch = CW;
     const int row0 = g.row0, row1 = g.row1, cx0 = g.cx0;
-    const double wc = g.wc;
     const int mode = job.mode;
 
-    if (mode == kModeFill && job.paint_index >= 0) {
-        const int* src = reinterpret_cast<const int*>(&paints[job.paint_index]);
-        int* dst = reinterpret_cast<int*>(&s_paint);
-        for (int i = tid; i < (int)(sizeof(PaintDev) / 4); i += THREADS) dst[i] = src[i];
-    }
-
-    // ---- phase 1: accumulate the tile's lines.  Warps work independently: 32 lines per round per warp ------
-    // (see warp_accumulate_round: 1a one line per lane, spans compacted per warp; 1b one lane per span)
-    unsigned short* spans = spans_all + warp * Cfg::kWarpSpanCap;
+    // ---- phase 1: accumulate the tile's lines.  The lines are split evenly over the warps, which then work
+    // independently, 32 lines per round (see warp_accumulate_round: 1a one line per lane, spans compacted per warp;
+    // 1b one lane per span) ------------------------------------------------------------------------------------------
+    SpanT* spans = spans_all + warp * Cfg::kWarpSpanCap;
     uint32_t rbeg, rend;
     if (bin_cap) {  // fixed-capacity bins: tile_offs holds the per-tile counts
         rbeg = tile * bin_cap;
@@ -225,53 +226,69 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
         rbeg = tile_offs[tile];
         rend = tile_offs[tile + 1];
     }
-    if (rbeg < rend) {  // tiles without lines never read their cells (row_touched stays 0): no need to clear them
-        const int4 z = make_int4(0, 0, 0, 0);
-        int4* c4 = reinterpret_cast<int4*>(cells);
-        for (int i = tid; i < TH * Cfg::kPitch / 4; i += THREADS) c4[i] = z;
+    if (!zero_early && rbeg < rend) {  // tiles without lines never read their cells (row_touched stays 0)
+        clear_cells();
         __syncthreads();
     }
-    for (uint32_t r0 = rbeg + warp * 32; r0 < rend; r0 += THREADS) {
-        const uint32_t r = r0 + lane;
-        const bool valid = r < rend;
-        const double4 l = valid ? bin_lines[r] : make_double4(0, 0, 0, 0);
-        warp_accumulate_round<L, Cfg::kRowBits, Cfg::kWarpSpanCap>(l, valid, g, cells, rowtot, row_touched, p_ax, p_ay, p_by, p_dxdy, p_dir,
-                                                                  spans, tid);
+    {
+        const uint32_t per = (rend - rbeg + Cfg::kWarps - 1) / Cfg::kWarps;
+        const uint32_t wbeg = rbeg + (uint32_t)warp * per, wend = min(wbeg + per, rend);
+        for (uint32_t r0 = wbeg; r0 < wend; r0 += 32) {
+            const uint32_t r = r0 + lane;
+            const bool valid = r < wend;
+            const double4 l = valid ? bin_lines[r] : make_double4(0, 0, 0, 0);
+            warp_accumulate_round<true, Cfg::kRowBits, Cfg::kWarpSpanCap, SpanT>(l, valid, g, cells, rowtot, row_touched, p_ax, p_ay, p_by, p_dxdy,
+                                                                           spans, tid);
+        }
     }
     __syncthreads();
+    // the piece constants are dead: stage the paint over them
+    if (mode == kModeFill && job.paint_index >= 0) {
+        const int* src = reinterpret_cast<const int*>(&paints[job.paint_index]);
+        int* dst = reinterpret_cast<int*>(p_ax);
+        for (int i = tid; i < (int)(sizeof(PaintDev) / 4); i += THREADS) dst[i] = src[i];
+    }
 
     // ---- carry-in: decoupled look-back over the tiles to the left in this band --------------------------------
     // Every tile publishes its per-row totals (flag AGG), sums its predecessors' totals until it meets an
-    // inclusive prefix, then publishes its own inclusive prefix.  Words carry the batch epoch, so the state needs
-    // no clearing between batches.  Single-chunk jobs have no neighbours and skip all of this.
+    // inclusive prefix, then publishes its own inclusive prefix.  A warp handles a row at a time and looks at up to
+    // 32 predecessors at once.  Words carry the batch epoch, so the state needs no clearing between batches.
+    // Single-chunk jobs have no neighbours and skip all of this.
     if (job.n_chunks > 1) {
-        if (tid < TH && tid < kStateRows) {
-            const int agg = rowtot[tid];
-            unsigned long long* st = tile_state + (size_t)tile * kStateRows + tid;
-            const unsigned long long ep = (unsigned long long)epoch << 34;
+        const unsigned long long ep = (unsigned long long)epoch << 34;
+        for (int r = warp; r < TH && r < kStateRows; r += Cfg::kWarps) {
+            const int agg = rowtot[r];
+            unsigned long long* st = tile_state + (size_t)tile * kStateRows + r;
             if (chunk == 0) {
-                st_state(st, ep | kFlagPrefix | (unsigned long long)(uint32_t)agg);
-            } else {
-                st_state(st, ep | kFlagAgg | (unsigned long long)(uint32_t)agg);
-                int sum = 0;
-                for (int k = 1; k <= chunk; k++) {
-                    const unsigned long long* ps = tile_state + (size_t)(tile - (uint32_t)k) * kStateRows + tid;
-                    unsigned long long v;
+                if (lane == 0) st_state(st, ep | kFlagPrefix | (unsigned long long)(uint32_t)agg);
+                continue;
+            }
+            if (lane == 0) st_state(st, ep | kFlagAgg | (unsigned long long)(uint32_t)agg);
+            int sum = 0;
+            for (int k0 = 1; k0 <= chunk; k0 += 32) {
+                const int k = k0 + lane;
+                unsigned long long v = 0;
+                if (k <= chunk) {
+                    const unsigned long long* ps = tile_state + (size_t)(tile - (uint32_t)k) * kStateRows + r;
                     do { v = ld_state(ps); } while ((uint32_t)(v >> 34) != epoch);
-                    sum += (int)(uint32_t)v;
-                    if ((v & (3ull << 32)) == kFlagPrefix) break;
                 }
-                carry[tid] = sum;
+                const unsigned pm = __ballot_sync(0xffffffffu, k <= chunk && (v & (3ull << 32)) == kFlagPrefix);
+                const int first = pm ? __ffs(pm) - 1 : 31;  // nearest predecessor that already holds an inclusive prefix
+                int contrib = (k <= chunk && lane <= first) ? (int)(uint32_t)v : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                sum += contrib;
+                if (pm) break;
+            }
+            if (lane == 0) {
+                carry[r] = sum;
                 st_state(st, ep | kFlagPrefix | (unsigned long long)(uint32_t)(sum + agg));
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
 
     // ---- phase 2: per-row scan, fill rule, store / composite --------------------------------------------
-    // A warp takes a row; lane l owns L consecutive columns: serial prefix in registers, ONE warp scan of the 32
-    // lane totals, coverage written back to shared memory in place (as floats) and read back transposed so that
-    // global stores are full 512 B coalesced 128-bit accesses.
     if (job.rule == 1) scan_rows<CW, TH, THREADS, true, Cfg>(job, s_paint, cells, carry, row_touched, row0, row1, cx0, mode, tid);
     else scan_rows<CW, TH, THREADS, false, Cfg>(job, s_paint, cells, carry, row_touched, row0, row1, cx0, mode, tid);
 }
@@ -307,41 +324,36 @@ __global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restri
 template <int CW, int TH, int THREADS>
 static void launch_raster_t(const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
                             uint32_t n_tiles, const PaintDev* paints, const uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
-                            unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, cudaStream_t s) {
+                            unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, cudaStream_t s) {
     constexpr size_t smem = TileCfg<CW, TH, THREADS>::smem_bytes();
     static bool configured[64] = {};  // per template instance and per device: the attribute belongs to the device's function
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
         cudaFuncSetAttribute(raster_kernel<CW, TH, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(raster_kernel<CW, TH, THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured[dev] = true;
     }
     raster_kernel<CW, TH, THREADS><<<n_tiles, THREADS, smem, s>>>(jobs, n_jobs, job_first, tile_first, h_jobs[job_first], paints, tile_offs,
-                                                                  bin_cap, bin_lines, tile_state, epoch, ticket, status);
+                                                                  bin_cap, bin_lines, tile_state, epoch, ticket, status, zero_early ? 1u : 0u);
 }
 
 TileShape raster_tile_shape(int variant) {
     switch (variant) {
         case 1: return TileShape{128, 64};   // canvases at most 128 px wide (larger than the fused small-canvas kernel takes)
-        case 2: return TileShape{512, 8};    // tuning alternatives (RGPU_TILE_VARIANT), measured slower on C2 and C5
-        case 3: return TileShape{512, 16};
-        case 4: return TileShape{1024, 4};
-        default: return TileShape{1024, 8};  // best of the r1 sweep: C2 46 us, C5 band 130 us (profiles/r1_tile_sweep.txt)
+        default: return TileShape{1024, 8};  // best of the r1 sweep over {256,512,1024} x {4,8,16} (profiles/r1_tile_sweep.txt)
     }
 }
 
 void launch_raster(int variant, const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
                    uint32_t n_tiles, const PaintDev* paints, const uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
-                   unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, cudaStream_t s) {
+                   unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, cudaStream_t s) {
     if (n_tiles == 0) return;
 #define RGPU_LAUNCH(CW, TH, THREADS)                                                                                              \
     launch_raster_t<CW, TH, THREADS>(jobs, h_jobs, n_jobs, job_first, tile_first, n_tiles, paints, tile_offs, bin_cap, bin_lines, tile_state, \
-                                     epoch, ticket, status, s)
+                                     epoch, ticket, status, zero_early, s)
     switch (variant) {
         case 1: RGPU_LAUNCH(128, 64, 256); break;
-        case 2: RGPU_LAUNCH(512, 8, 128); break;
-        case 3: RGPU_LAUNCH(512, 16, 128); break;
-        case 4: RGPU_LAUNCH(1024, 4, 128); break;
         default: RGPU_LAUNCH(1024, 8, 128); break;
     }
 #undef RGPU_LAUNCH

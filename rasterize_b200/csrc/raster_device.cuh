@@ -137,12 +137,15 @@ __device__ __forceinline__ float coverage_from_fixed(int acc) {
 }
 
 // ---- shared-memory cell layout --------------------------------------------------------------------------
-// In the scan phase lane l owns L = CW/32 consecutive columns of a row.  Cell (row r, tile column x) lives at
-// r*pitch + swz<L>(x), swz<L>(x) = x + 4*(x/L): every run of L columns is followed by 4 padding ints, so the
-// 128-bit accesses of 8 consecutive lanes (stride L+4 ints) fall on distinct bank quads — conflict-free both for
-// the per-lane runs and (up to one 2-way pair for L = 16) for the transposed read-back used for coalesced stores.
-template <int L>
-__device__ __forceinline__ int swz(int x) { return x + ((x / L) << 2); }
+// In the scan phase lane l owns 32 consecutive columns of a row (a "run": 8 words of 128 bits).  Cell (row r, tile
+// column x) lives at r*pitch + swz(x), where swz XORs the word index inside a run with the run index: the 128-bit
+// accesses of 8 consecutive lanes then fall on 8 distinct bank groups both when every lane reads word i of its own run
+// (scan) and when lane l reads the word of columns [128 i + 4 l, +4) (transposed read-back for coalesced stores) —
+// conflict-free without padding.  SWZ = false (one CTA per small canvas) keeps plain row-major cells.
+template <bool SWZ>
+__device__ __forceinline__ int swz(int x) {
+    return SWZ ? (x ^ (((x >> 5) & 7) << 2)) : x;
+}
 
 __device__ __forceinline__ int to_fixed_f(float v) { return __float2int_rn(v * 16777216.0f); }
 
@@ -160,7 +163,7 @@ struct TileGeom {
 // deltas) are rounded to Q7.24 and the differences of consecutive rounded coverages are added to the cells of
 // THIS tile only; their sum (a telescoping difference) goes to the row's tile total, from which the tiles to the
 // right derive their carry-in.  Parts of the span in other tiles are added by those tiles (2-D bins).
-template <int L>
+template <bool SWZ>
 __device__ __forceinline__ void span_row(double ax, double ay, double by, double dxdy, float dirf, int y, const TileGeom& g,
                                          int* __restrict__ cells, int* __restrict__ rowtot, int* __restrict__ row_touched) {
     const double yt = fmax((double)y, ay);
@@ -187,12 +190,12 @@ __device__ __forceinline__ void span_row(double ax, double ay, double by, double
         const int ca = to_fixed_f(d * c0);
         int tot = 0;
         if (x0i >= g.cx0) {  // x0i < tile_end was checked above
-            if (ca != 0) atomicAdd(&rowp[swz<L>(x0i - g.cx0)], ca);
+            if (ca != 0) atomicAdd(&rowp[swz<SWZ>(x0i - g.cx0)], ca);
             tot = ca;
         }
         if (x0i + 1 < g.tile_end) {  // x0i + 1 >= cx0 holds because last >= cx0
             const int cb = fd - ca;
-            if (cb != 0) atomicAdd(&rowp[swz<L>(x0i + 1 - g.cx0)], cb);
+            if (cb != 0) atomicAdd(&rowp[swz<SWZ>(x0i + 1 - g.cx0)], cb);
             tot += cb;
         }
         atomicAdd(&rowtot[r], tot);
@@ -222,7 +225,7 @@ __device__ __forceinline__ void span_row(double ax, double ay, double by, double
     for (int k = kb; k <= ke; k++) {
         const int cur = (k == last) ? fd : to_fixed_f(d * cov(k - x0i));
         const int diff = cur - prev;
-        if (diff != 0) atomicAdd(&rowp[swz<L>(k - g.cx0)], diff);
+        if (diff != 0) atomicAdd(&rowp[swz<SWZ>(k - g.cx0)], diff);
         prev = cur;
     }
     atomicAdd(&rowtot[r], prev - first);
@@ -265,15 +268,15 @@ __device__ __forceinline__ Piece classify_piece(double ax, double ay, double bx,
     return p;
 }
 
-template <int L>
+template <bool SWZ>
 static __device__ void piece_serial(double ax, double ay, double bx, double by, const TileGeom& g, int* cells, int* rowtot, int* row_touched) {
     const Piece p = classify_piece(ax, ay, bx, by, g);
     if (p.cls == 2)
-        for (int y = p.rb; y < p.re; y++) span_row<L>(p.ax, p.ay, p.by, p.dxdy, p.dirf, y, g, cells, rowtot, row_touched);
+        for (int y = p.rb; y < p.re; y++) span_row<SWZ>(p.ax, p.ay, p.by, p.dxdy, p.dirf, y, g, cells, rowtot, row_touched);
 }
 
 // The reference's signed_difference_line for ONE line, serially in the calling thread (clipping + all rows).
-template <int L>
+template <bool SWZ>
 static __device__ void line_serial(const double4 l, const TileGeom& g, int* cells, int* rowtot, int* row_touched) {
     const double wc = g.wc;
     double p0x = l.x, p0y = l.y, p1x = l.z, p1y = l.w;
@@ -296,33 +299,35 @@ static __device__ void line_serial(const double4 l, const TileGeom& g, int* cell
             const double mx = (1.0 - t) * p0x + t * p1x;
             const double my = (1.0 - t) * p0y + t * p1y;
             if (p0x < 0.0) {
-                if (mx <= 0.0) piece_serial<L>(0.0, p0y, 0.0, my, g, cells, rowtot, row_touched);
-                else piece_serial<L>(0.0, p0y, mx, my, g, cells, rowtot, row_touched);
+                if (mx <= 0.0) piece_serial<SWZ>(0.0, p0y, 0.0, my, g, cells, rowtot, row_touched);
+                else piece_serial<SWZ>(0.0, p0y, mx, my, g, cells, rowtot, row_touched);
                 p0x = mx; p0y = my;
             } else {
-                if (mx <= 0.0) piece_serial<L>(0.0, my, 0.0, p1y, g, cells, rowtot, row_touched);
-                else piece_serial<L>(mx, my, 0.0, p1y, g, cells, rowtot, row_touched);
+                if (mx <= 0.0) piece_serial<SWZ>(0.0, my, 0.0, p1y, g, cells, rowtot, row_touched);
+                else piece_serial<SWZ>(mx, my, 0.0, p1y, g, cells, rowtot, row_touched);
                 p1x = mx; p1y = my;
             }
         }
     }
-    piece_serial<L>(p0x, p0y, p1x, p1y, g, cells, rowtot, row_touched);
+    piece_serial<SWZ>(p0x, p0y, p1x, p1y, g, cells, rowtot, row_touched);
 }
 
 // One round of phase 1 for a warp: up to 32 lines, one per lane.
 // 1a: the reference's right-edge / x<0 clipping, orientation and row range; the (piece,row) spans of the 32 lines
 //     are compacted into the warp's span list (warp prefix sum, no atomics)
 // 1b: one lane per span — no row-loop divergence
-// p_* are indexed by the thread id (piece constants), `spans` is this warp's list of CAP entries.
-template <int L, int ROWBITS, int CAP>
+// p_* are indexed by the thread id (piece constants), `spans` is this warp's list of CAP entries of
+// (source lane << ROWBITS | band row); the orientation of the 32 pieces travels in a ballot mask.
+template <bool SWZ, int ROWBITS, int CAP, class SpanT>
 __device__ __forceinline__ void warp_accumulate_round(const double4 l, bool valid, const TileGeom& g, int* __restrict__ cells,
                                                       int* __restrict__ rowtot, int* __restrict__ row_touched, double* p_ax, double* p_ay,
-                                                      double* p_by, double* p_dxdy, float* p_dir, unsigned short* spans, int tid) {
+                                                      double* p_by, double* p_dxdy, SpanT* spans, int tid) {
     const int lane = tid & 31;
     const double wc = g.wc;
     Piece p;
     p.cls = 0;
     p.rb = p.re = 0;
+    p.dirf = 1.0f;
     if (valid) {
         double p0x = l.x, p0y = l.y, p1x = l.z, p1y = l.w;
         // src/rasterize.rs:370-387: lines crossing x == width
@@ -348,12 +353,12 @@ __device__ __forceinline__ void warp_accumulate_round(const double4 l, bool vali
                 // the outside part, folded onto x = 0, goes through the same function again in the reference;
                 // rare (only lines crossing the left edge): done serially by this lane
                 if (p0x < 0.0) {
-                    if (mx <= 0.0) piece_serial<L>(0.0, p0y, 0.0, my, g, cells, rowtot, row_touched);
-                    else piece_serial<L>(0.0, p0y, mx, my, g, cells, rowtot, row_touched);
+                    if (mx <= 0.0) piece_serial<SWZ>(0.0, p0y, 0.0, my, g, cells, rowtot, row_touched);
+                    else piece_serial<SWZ>(0.0, p0y, mx, my, g, cells, rowtot, row_touched);
                     p0x = mx; p0y = my;
                 } else {
-                    if (mx <= 0.0) piece_serial<L>(0.0, my, 0.0, p1y, g, cells, rowtot, row_touched);
-                    else piece_serial<L>(mx, my, 0.0, p1y, g, cells, rowtot, row_touched);
+                    if (mx <= 0.0) piece_serial<SWZ>(0.0, my, 0.0, p1y, g, cells, rowtot, row_touched);
+                    else piece_serial<SWZ>(mx, my, 0.0, p1y, g, cells, rowtot, row_touched);
                     p1x = mx; p1y = my;
                 }
             }
@@ -371,22 +376,24 @@ __device__ __forceinline__ void warp_accumulate_round(const double4 l, bool vali
     const int base = incl - n;
     if (n > 0) {
         if (base + n <= CAP) {
-            p_ax[tid] = p.ax; p_ay[tid] = p.ay; p_by[tid] = p.by; p_dxdy[tid] = p.dxdy; p_dir[tid] = p.dirf;
-            for (int k = 0; k < n; k++) spans[base + k] = (unsigned short)((lane << ROWBITS) | (p.rb + k - g.row0));
+            p_ax[tid] = p.ax; p_ay[tid] = p.ay; p_by[tid] = p.by; p_dxdy[tid] = p.dxdy;
+            for (int k = 0; k < n; k++) spans[base + k] = (SpanT)((lane << ROWBITS) | (p.rb + k - g.row0));
         } else {  // list full (only possible for tall tiles): do the rows here
-            for (int y = p.rb; y < p.re; y++) span_row<L>(p.ax, p.ay, p.by, p.dxdy, p.dirf, y, g, cells, rowtot, row_touched);
+            for (int y = p.rb; y < p.re; y++) span_row<SWZ>(p.ax, p.ay, p.by, p.dxdy, p.dirf, y, g, cells, rowtot, row_touched);
         }
     }
     __syncwarp();
     // lanes are in list order: everything before the first lane that did not fit is in the list
+    const unsigned neg = __ballot_sync(0xffffffffu, p.dirf < 0.0f);
     const unsigned nofit = __ballot_sync(0xffffffffu, n > 0 && base + n > CAP);
     const int ns = nofit ? __shfl_sync(0xffffffffu, base, __ffs(nofit) - 1) : total;
     const int wbase = tid & ~31;
     for (int i = lane; i < ns; i += 32) {
         const int e = spans[i];
-        const int slot = wbase + (e >> ROWBITS);
+        const int src = e >> ROWBITS;
+        const int slot = wbase + src;
         const int y = g.row0 + (e & ((1 << ROWBITS) - 1));
-        span_row<L>(p_ax[slot], p_ay[slot], p_by[slot], p_dxdy[slot], p_dir[slot], y, g, cells, rowtot, row_touched);
+        span_row<SWZ>(p_ax[slot], p_ay[slot], p_by[slot], p_dxdy[slot], ((neg >> src) & 1u) ? -1.0f : 1.0f, y, g, cells, rowtot, row_touched);
     }
     __syncwarp();
 }

@@ -22,14 +22,13 @@ constexpr int kSmWarps = kSmThreads / 32;
 constexpr int kSmMaxW = 64, kSmMaxH = 64;
 constexpr int kSmPitch = 68;        // 64 columns + overflow column, padded to a multiple of 4 ints
 constexpr int kSmLineCap = 768;     // lines kept in shared memory per window (24 KB)
-constexpr int kSmNoSwz = 1 << 20;   // swz<L>(x) == x for every x < L: plain row-major cells
 constexpr int kSmRowBits = 6;
 constexpr int kSmSpanCap = 256;     // per-warp span list (lanes that do not fit do their rows serially)
 
 __global__ void __launch_bounds__(kSmThreads, 3)
 small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const PaintDev* __restrict__ paints, double thr,
                     Status* __restrict__ status) {
-    // dynamic shared memory (> 48 KB): line window | cells | piece constants | per-warp span lists
+    // dynamic shared memory (> 48 KB): line window | cells (plain row-major) | piece constants | per-warp span lists
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double4* lines_s = reinterpret_cast<double4*>(smem_raw);
     int* cells = reinterpret_cast<int*>(lines_s + kSmLineCap);
@@ -37,8 +36,7 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
     double* p_ay = p_ax + kSmThreads;
     double* p_by = p_ay + kSmThreads;
     double* p_dxdy = p_by + kSmThreads;
-    float* p_dir = reinterpret_cast<float*>(p_dxdy + kSmThreads);
-    unsigned short* spans_all = reinterpret_cast<unsigned short*>(p_dir + kSmThreads);
+    unsigned short* spans_all = reinterpret_cast<unsigned short*>(p_dxdy + kSmThreads);
     __shared__ int rowtot[kSmMaxH];
     __shared__ int row_touched[kSmMaxH];
     __shared__ uint32_t n_lines_s;
@@ -91,7 +89,7 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
                 if (k < (uint32_t)kSmLineCap) {
                     lines_s[k] = make_double4(x0, y0, x1, y1);
                 } else {  // window full: rasterize here (serial in this thread)
-                    line_serial<kSmNoSwz>(make_double4(x0, y0, x1, y1), g, cells, rowtot, row_touched);
+                    line_serial<false>(make_double4(x0, y0, x1, y1), g, cells, rowtot, row_touched);
                 }
             };
             if (seg_all_finite(c.seg, c.kind)) my_lines += slot_walk<false>(c, thr, status, emit);
@@ -103,8 +101,7 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
             const uint32_t i = i0 + lane;
             const bool valid = i < n;
             const double4 l = valid ? lines_s[i] : make_double4(0, 0, 0, 0);
-            warp_accumulate_round<kSmNoSwz, kSmRowBits, kSmSpanCap>(l, valid, g, cells, rowtot, row_touched, p_ax, p_ay, p_by, p_dxdy, p_dir,
-                                                                    spans, tid);
+            warp_accumulate_round<false, kSmRowBits, kSmSpanCap, unsigned short>(l, valid, g, cells, rowtot, row_touched, p_ax, p_ay, p_by, p_dxdy, spans, tid);
         }
         __syncthreads();
     }
@@ -200,7 +197,7 @@ void launch_small_canvas(const JobDev* jobs, uint32_t job_first, uint32_t n_jobs
                          cudaStream_t s) {
     if (n_jobs == 0) return;
     constexpr size_t smem = sizeof(double4) * kSmLineCap + sizeof(int) * kSmMaxH * kSmPitch + sizeof(double) * 4 * kSmThreads +
-                            sizeof(float) * kSmThreads + sizeof(unsigned short) * kSmSpanCap * kSmWarps;
+                            sizeof(unsigned short) * kSmSpanCap * kSmWarps;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
