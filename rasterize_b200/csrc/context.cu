@@ -80,6 +80,9 @@ struct rgpu_ctx {
     uint32_t bin_cap = 0;
     bool two_pass = getenv("RGPU_TWO_PASS") != nullptr;  // A/B switch: always use the exact two-pass scheme
     bool last_fixed = false;
+    DevBuf fixed_block;            // [status A | status B | tickets | tile counters], self-cleaning (see submit)
+    uint32_t fx_tickets_cap = 0, fx_tiles_cap = 0, fx_parity = 0;
+    cudaEvent_t h_tables_ev = nullptr;  // completion of the last upload out of h_jobs / h_paints
     uint32_t last_tiles = 0;
     // pinned host
     Status* h_status = nullptr;
@@ -309,6 +312,8 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     int rc;
     if ((rc = ensure_pinned(ctx, ctx->h_jobs, ctx->h_jobs_cap, n_jobs))) return rc;
     if ((rc = ensure_pinned(ctx, ctx->h_paints, ctx->h_paints_cap, n_jobs))) return rc;
+    // the previous batch's table upload reads these pinned buffers asynchronously: let it finish before overwriting
+    CK(ctx, cudaEventSynchronize(ctx->h_tables_ev));
 
     // tile variant: small canvases get a (128 x 64) tile, everything else (1024 x 8)
     uint32_t max_w = 0;
@@ -388,6 +393,7 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         Status* d_status = static_cast<Status*>(ctx->status.p);
         CK(ctx, cudaMemcpyAsync(d_jobs, ctx->h_jobs, sizeof(JobDev) * n_live, cudaMemcpyHostToDevice, s));
         if (n_paints) CK(ctx, cudaMemcpyAsync(d_paints, ctx->h_paints, sizeof(PaintDev) * n_paints, cudaMemcpyHostToDevice, s));
+        CK(ctx, cudaEventRecord(ctx->h_tables_ev, s));
         CK(ctx, cudaMemsetAsync(d_status, 0, sizeof(Status), s));
         const double thr = 16.0 * ctx->flatness * ctx->flatness;  // PathFlattenIter::new, src/path.rs:749
         const bool prof = ctx->profiling;
@@ -437,6 +443,7 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         uint32_t* d_counts = static_cast<uint32_t*>(ctx->slot_counts.p);
         uint32_t* d_offs = static_cast<uint32_t*>(ctx->slot_offs.p);
         CK(ctx, cudaMemcpyAsync(d_jobs, ctx->h_jobs, sizeof(JobDev) * n_live, cudaMemcpyHostToDevice, s));
+        CK(ctx, cudaEventRecord(ctx->h_tables_ev, s));
         CK(ctx, cudaMemsetAsync(d_status, 0, sizeof(Status), s));
         launch_flatten_count(d_jobs, n_live, item_acc, thr, d_counts, d_status, s);
         launch_exclusive_scan(d_counts, d_offs, total_slots + 1, ctx->scan_temp.p, ctx->scan_temp.cap, s);
@@ -467,17 +474,8 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     size_t want_refs = fixed ? (size_t)bin_cap * tile_acc : std::max<uint64_t>(ctx->refs_cap, est_lines + est_lines / 2);
     if ((rc = ensure_dev(ctx, ctx->refs, sizeof(double4) * want_refs))) return rc;
     ctx->refs_cap = std::min<size_t>(ctx->refs.cap / sizeof(double4), 0xfffffff0u);
-    // one block that must be zero at the start of every batch, cleared by ONE memset:
-    // [status | raster tickets | tile_counts | (two-pass only: tile_cursor | scan tile states)]
     const uint32_t n_raster_launches = (flags & RGPU_BATCH_INDEPENDENT) ? 1u : n_live;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    const size_t tickets_off = up(sizeof(Status));
-    const size_t counts_off = tickets_off + up((size_t)n_raster_launches * 4);
-    const size_t cursor_off = counts_off + up((size_t)(tile_acc + 1) * 4);
-    const size_t scan_off = cursor_off + (fixed ? 0 : up((size_t)(tile_acc + 1) * 4));
-    const size_t zero_bytes = scan_off + (fixed ? 0 : up(scan_temp_bytes(tile_acc + 1)));
-    if ((rc = ensure_dev(ctx, ctx->zero_block, zero_bytes))) return rc;
-    if (!fixed && (rc = ensure_dev(ctx, ctx->tile_offs, sizeof(uint32_t) * (tile_acc + 1)))) return rc;
     // carry look-back state, validated by epoch (cleared only when (re)allocated or when the epoch wraps)
     {
         size_t need = sizeof(unsigned long long) * kStateRows * (size_t)tile_acc;
@@ -489,22 +487,60 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
             if (ctx->epoch >= (1u << 30)) ctx->epoch = 1;
         }
     }
-    char* zb = static_cast<char*>(ctx->zero_block.p);
-    Status* d_status = reinterpret_cast<Status*>(zb);
-    uint32_t* d_tickets = reinterpret_cast<uint32_t*>(zb + tickets_off);
-    uint32_t* d_bc = reinterpret_cast<uint32_t*>(zb + counts_off);
-    uint32_t* d_cur = reinterpret_cast<uint32_t*>(zb + cursor_off);
-    void* d_scan = zb + scan_off;
-    uint32_t* d_bo = fixed ? d_bc : static_cast<uint32_t*>(ctx->tile_offs.p);
+    Status* d_status = nullptr;
+    Status* d_status_next = nullptr;
+    uint32_t *d_tickets = nullptr, *d_bc = nullptr, *d_cur = nullptr, *d_bo = nullptr;
+    void* d_scan = nullptr;
+    if (fixed) {
+        // Self-cleaning block [status A | status B | raster tickets | tile counters]: the kernels leave the tickets and
+        // counters zero (raster.cu) and clear the OTHER status block for the batch after this one (flatten.cu), so the
+        // steady state needs no memset.  Only growing the block clears it wholesale.
+        if (n_raster_launches > ctx->fx_tickets_cap || tile_acc > ctx->fx_tiles_cap) {
+            const size_t tcap = std::max<size_t>(n_raster_launches + n_raster_launches / 2, 64);
+            const size_t ccap = std::max<size_t>((size_t)tile_acc + tile_acc / 2, 1024);
+            const size_t bytes = 512 + up(tcap * 4) + up(ccap * 4);
+            if ((rc = ensure_dev(ctx, ctx->fixed_block, bytes))) return rc;
+            CK(ctx, cudaMemsetAsync(ctx->fixed_block.p, 0, ctx->fixed_block.cap, s));
+            ctx->fx_tickets_cap = (uint32_t)tcap;
+            ctx->fx_tiles_cap = (uint32_t)ccap;
+        }
+        char* fb = static_cast<char*>(ctx->fixed_block.p);
+        d_status = reinterpret_cast<Status*>(fb + (ctx->fx_parity ? 256 : 0));
+        d_status_next = reinterpret_cast<Status*>(fb + (ctx->fx_parity ? 0 : 256));
+        ctx->fx_parity ^= 1u;
+        d_tickets = reinterpret_cast<uint32_t*>(fb + 512);
+        d_bc = reinterpret_cast<uint32_t*>(fb + 512 + up((size_t)ctx->fx_tickets_cap * 4));
+        d_bo = d_bc;
+        if (item_acc == 0) CK(ctx, cudaMemsetAsync(d_status_next, 0, sizeof(Status), s));  // no flatten launch to do it
+    } else {
+        // two-pass: one block that must be zero at the start of the batch, cleared by ONE memset:
+        // [status | raster tickets | tile_counts | tile_cursor | scan tile states]
+        const size_t tickets_off = up(sizeof(Status));
+        const size_t counts_off = tickets_off + up((size_t)n_raster_launches * 4);
+        const size_t cursor_off = counts_off + up((size_t)(tile_acc + 1) * 4);
+        const size_t scan_off = cursor_off + up((size_t)(tile_acc + 1) * 4);
+        const size_t zero_bytes = scan_off + up(scan_temp_bytes(tile_acc + 1));
+        if ((rc = ensure_dev(ctx, ctx->zero_block, zero_bytes))) return rc;
+        if ((rc = ensure_dev(ctx, ctx->tile_offs, sizeof(uint32_t) * (tile_acc + 1)))) return rc;
+        char* zb = static_cast<char*>(ctx->zero_block.p);
+        d_status = reinterpret_cast<Status*>(zb);
+        d_tickets = reinterpret_cast<uint32_t*>(zb + tickets_off);
+        d_bc = reinterpret_cast<uint32_t*>(zb + counts_off);
+        d_cur = reinterpret_cast<uint32_t*>(zb + cursor_off);
+        d_scan = zb + scan_off;
+        d_bo = static_cast<uint32_t*>(ctx->tile_offs.p);
+        CK(ctx, cudaMemsetAsync(zb, 0, zero_bytes, s));
+    }
     double4* d_refs = static_cast<double4*>(ctx->refs.p);
     unsigned long long* d_state = static_cast<unsigned long long*>(ctx->tile_state.p);
 
-    CK(ctx, cudaMemcpyAsync(d_jobs, ctx->h_jobs, sizeof(JobDev) * n_live, cudaMemcpyHostToDevice, s));
+    // a single job travels in the kernel parameters; a table is uploaded only for multi-job batches
+    if (n_live > 1 || !fixed) CK(ctx, cudaMemcpyAsync(d_jobs, ctx->h_jobs, sizeof(JobDev) * n_live, cudaMemcpyHostToDevice, s));
     if (n_paints) CK(ctx, cudaMemcpyAsync(d_paints, ctx->h_paints, sizeof(PaintDev) * n_paints, cudaMemcpyHostToDevice, s));
-    CK(ctx, cudaMemsetAsync(zb, 0, zero_bytes, s));
+    if (n_live > 1 || !fixed || n_paints) CK(ctx, cudaEventRecord(ctx->h_tables_ev, s));
     if (prof) CK(ctx, cudaEventRecord(ctx->ev[0], s));
     if (fixed) {
-        launch_flatten_bin_fixed(d_jobs, n_live, item_acc, thr, d_bc, d_refs, bin_cap, ts.th, ts.cw, d_status, s);
+        launch_flatten_bin_fixed(d_jobs, ctx->h_jobs, n_live, item_acc, thr, d_bc, d_refs, bin_cap, ts.th, ts.cw, d_status, d_status_next, s);
         ctx->n_launches += 1;
         if (prof) CK(ctx, cudaEventRecord(ctx->ev[1], s));
     } else {
@@ -515,15 +551,17 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         ctx->n_launches += 3;
     }
     if (prof) CK(ctx, cudaEventRecord(ctx->ev[2], s));
+    static const bool no_pdl = getenv("RGPU_NO_PDL") != nullptr;  // A/B switch
+    const bool pdl_ok = fixed && !prof && !no_pdl;
     const bool zero_early = est_lines + est_lines / 2 >= 2ull * tile_acc;  // most tiles will hold lines
     if (flags & RGPU_BATCH_INDEPENDENT) {
-        launch_raster(variant, d_jobs, ctx->h_jobs, n_live, 0, 0, tile_acc, d_paints, d_bo, bin_cap, d_refs, d_state, ctx->epoch, d_tickets, d_status, zero_early, s);
+        launch_raster(variant, d_jobs, ctx->h_jobs, n_live, 0, 0, tile_acc, d_paints, d_bo, bin_cap, d_refs, d_state, ctx->epoch, d_tickets, d_status, zero_early, /*pdl=*/pdl_ok, s);
         ctx->n_launches += 1;
     } else {
         for (uint32_t j = 0; j < n_live; j++) {
             const JobDev& d = ctx->h_jobs[j];
             launch_raster(variant, d_jobs, ctx->h_jobs, 1, j, d.tile_begin, d.n_bands * d.n_chunks, d_paints, d_bo, bin_cap, d_refs, d_state,
-                          ctx->epoch, d_tickets + j, d_status, zero_early, s);
+                          ctx->epoch, d_tickets + j, d_status, zero_early, /*pdl=*/pdl_ok && j == 0, s);
             ctx->n_launches += 1;
         }
     }
@@ -625,6 +663,7 @@ int rgpu_create(int device, double flatness, rgpu_ctx** out) {
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->h_status), sizeof(Status));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->status.p, 256);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->h_tables_ev, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         g_create_err = std::string("rgpu_create: ") + cudaGetErrorString(e);
         delete ctx;
@@ -641,7 +680,7 @@ void rgpu_destroy(rgpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->jobs, &ctx->paints, &ctx->slot_counts, &ctx->slot_offs, &ctx->lines, &ctx->line_job, &ctx->zero_block, &ctx->tile_offs,
-                      &ctx->tile_state, &ctx->refs, &ctx->scan_temp, &ctx->status, &ctx->img_f32, &ctx->img_f64, &ctx->img_lin, &ctx->tmp_pts, &ctx->tmp_items};
+                      &ctx->tile_state, &ctx->fixed_block, &ctx->refs, &ctx->scan_temp, &ctx->status, &ctx->img_f32, &ctx->img_f64, &ctx->img_lin, &ctx->tmp_pts, &ctx->tmp_items};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
@@ -652,6 +691,7 @@ void rgpu_destroy(rgpu_ctx* ctx) {
     for (int i = 0; i < 4; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
+    if (ctx->h_tables_ev) cudaEventDestroy(ctx->h_tables_ev);
     ctx->pool.reset();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -67,9 +67,17 @@ flatten_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t total_
 // with batches small enough to avoid that (strided, 8 items) it ties this kernel (33 us on C2); only C5 gained (31 -> 22 us).
 template <int PASS>
 __global__ void __launch_bounds__(128)
-flatten_bin_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t total_items, double thr, uint32_t* __restrict__ tile_counts,
-                   const uint32_t* __restrict__ tile_offs, uint32_t total_tiles, double4* __restrict__ bin_lines, uint32_t refs_cap,
-                   int band_shift, int chunk_shift, Status* __restrict__ status) {
+flatten_bin_kernel(const JobDev* __restrict__ jobs_in, uint32_t n_jobs, const __grid_constant__ JobDev one_job, uint32_t total_items, double thr,
+                   uint32_t* __restrict__ tile_counts, const uint32_t* __restrict__ tile_offs, uint32_t total_tiles,
+                   double4* __restrict__ bin_lines, uint32_t refs_cap, int band_shift, int chunk_shift, Status* __restrict__ status,
+                   Status* __restrict__ next_status) {
+    // a single job travels in the kernel parameters (constant bank): no table upload, no dependent global load
+    const JobDev* __restrict__ jobs = (n_jobs == 1 && !jobs_in) ? &one_job : jobs_in;
+    // let the raster kernel behind us start its prologue as soon as every CTA of this grid is running (it waits for this
+    // grid to complete before it reads anything we write)
+    asm volatile("griddepcontrol.launch_dependents;");
+    // the status block of the NEXT batch is cleared here (the two blocks alternate), so batches need no memset
+    if (next_status && blockIdx.x == 0 && threadIdx.x < sizeof(Status) / 4) reinterpret_cast<uint32_t*>(next_status)[threadIdx.x] = 0u;
     // PASS 2 = single pass with fixed-capacity bins: refs_cap is the per-tile capacity
     if (PASS == 1) {
         if (status->nan_flag | status->depth_flag) return;
@@ -141,8 +149,8 @@ void launch_flatten_bin_count(const JobDev* jobs, uint32_t n_jobs, uint32_t tota
                               int band_rows, int chunk_cols, Status* status, cudaStream_t s) {
     uint32_t n = total_items * kSlotsPerItem;
     if (n == 0) return;
-    flatten_bin_kernel<0><<<(n + 127) / 128, 128, 0, s>>>(jobs, n_jobs, total_items, thr, tile_counts, nullptr, 0, nullptr, 0,
-                                                          log2i(band_rows), log2i(chunk_cols), status);
+    flatten_bin_kernel<0><<<(n + 127) / 128, 128, 0, s>>>(jobs, n_jobs, JobDev{}, total_items, thr, tile_counts, nullptr, 0, nullptr, 0,
+                                                          log2i(band_rows), log2i(chunk_cols), status, nullptr);
 }
 
 void launch_flatten_bin_emit(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, const uint32_t* tile_offs,
@@ -150,16 +158,17 @@ void launch_flatten_bin_emit(const JobDev* jobs, uint32_t n_jobs, uint32_t total
                              int chunk_cols, Status* status, cudaStream_t s) {
     uint32_t n = total_items * kSlotsPerItem;
     if (n == 0) return;
-    flatten_bin_kernel<1><<<(n + 127) / 128, 128, 0, s>>>(jobs, n_jobs, total_items, thr, tile_cursor, tile_offs, total_tiles, bin_lines,
-                                                          refs_cap, log2i(band_rows), log2i(chunk_cols), status);
+    flatten_bin_kernel<1><<<(n + 127) / 128, 128, 0, s>>>(jobs, n_jobs, JobDev{}, total_items, thr, tile_cursor, tile_offs, total_tiles,
+                                                          bin_lines, refs_cap, log2i(band_rows), log2i(chunk_cols), status, nullptr);
 }
 
-void launch_flatten_bin_fixed(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, uint32_t* tile_counts,
-                              double4* bin_lines, uint32_t bin_cap, int band_rows, int chunk_cols, Status* status, cudaStream_t s) {
+void launch_flatten_bin_fixed(const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t total_items, double thr,
+                              uint32_t* tile_counts, double4* bin_lines, uint32_t bin_cap, int band_rows, int chunk_cols, Status* status,
+                              Status* next_status, cudaStream_t s) {
     uint32_t n = total_items * kSlotsPerItem;
     if (n == 0) return;
-    flatten_bin_kernel<2><<<(n + 127) / 128, 128, 0, s>>>(jobs, n_jobs, total_items, thr, tile_counts, nullptr, 0, bin_lines, bin_cap,
-                                                          log2i(band_rows), log2i(chunk_cols), status);
+    flatten_bin_kernel<2><<<(n + 127) / 128, 128, 0, s>>>(n_jobs == 1 ? nullptr : jobs, n_jobs, h_jobs[0], total_items, thr, tile_counts, nullptr,
+                                                          0, bin_lines, bin_cap, log2i(band_rows), log2i(chunk_cols), status, next_status);
 }
 
 }  // namespace rgpu

@@ -150,9 +150,9 @@ __device__ __forceinline__ void scan_rows(const JobDev& job, const PaintDev& s_p
 template <int CW, int TH, int THREADS>
 __global__ void __launch_bounds__(THREADS, (TH <= 8 ? 6 : 2))
 raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first, const JobDev one_job,
-              const PaintDev* __restrict__ paints, const uint32_t* __restrict__ tile_offs, uint32_t bin_cap,
+              const PaintDev* __restrict__ paints, uint32_t* __restrict__ tile_offs, uint32_t bin_cap,
               const double4* __restrict__ bin_lines, unsigned long long* __restrict__ tile_state, uint32_t epoch,
-              uint32_t* __restrict__ ticket, const Status* __restrict__ status, uint32_t zero_early) {
+              uint32_t* __restrict__ ticket, const Status* status, uint32_t zero_early, uint32_t n_tiles) {
     using Cfg = TileCfg<CW, TH, THREADS>;
     using SpanT = typename Cfg::SpanT;
     static_assert(TH <= 64 && CW % 128 == 0 && Cfg::kL % 4 == 0, "tile shape");
@@ -168,15 +168,13 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     __shared__ int carry[TH];
     __shared__ int rowtot[TH];
     __shared__ int row_touched[TH];
-    __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_job;
+    __shared__ uint32_t s_tile, s_job, s_chunk, s_band, s_count, s_bad;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     // dynamic tile id: a tile only ever waits (carry look-back) on tiles with smaller ids, which have started
     uint32_t my_ticket = 0;
     if (tid == 0) my_ticket = atomicAdd(ticket, 1u);
-    const uint32_t bad = status->lines_overflow | status->refs_overflow | status->nan_flag | status->depth_flag;
     // dense batches clear the cells while the ticket is on its way; sparse ones (most tiles without a line) clear only
     // the tiles that need it, once the tile is known
     auto clear_cells = [&]() {
@@ -187,22 +185,41 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     };
     if (zero_early) clear_cells();
     if (tid < TH) { carry[tid] = 0; rowtot[tid] = 0; row_touched[tid] = 0; }
-    if (tid == 0) {
-        const uint32_t t = tile_first + my_ticket;
-        s_tile = t;
-        s_job = (n_jobs == 1) ? job_first : job_first + find_job(n_jobs, t, [&](uint32_t k) { return jobs[job_first + k].tile_begin; });
-    }
-    __syncthreads();
-    if (bad) return;
-    const JobDev& job = (n_jobs == 1) ? one_job : jobs[s_job];
+    // Programmatic dependent launch: everything above overlaps the tail of the flatten kernel; the bins, their counters and
+    // the status flags it writes are read only after it has completed (no-op when launched without the attribute).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // volatile: loads through a `const __restrict__` pointer are invariant to the compiler and may be hoisted above the
+    // wait, where the flatten kernel has not raised its flags yet
+    // (thread 0 alone reads them, next to its ticket, and broadcasts the verdict with the tile)
+    const volatile uint32_t* flags = reinterpret_cast<const volatile uint32_t*>(status);
     // Tiles are taken in CHUNK-major order (all bands of column chunk 0, then chunk 1, ...): the left neighbour a tile's
     // carry depends on was started a whole column of bands earlier, so it has normally published its inclusive prefix by
     // the time this tile looks back — band-major order would start the tiles of a band together and make every tile wait
     // for the slowest one to its left.  Bins and look-back state stay indexed band-major.
-    const uint32_t lt = s_tile - job.tile_begin;
-    const int chunk = (int)(lt / job.n_bands);
-    const int band = (int)(lt - (uint32_t)chunk * job.n_bands);
-    const uint32_t tile = job.tile_begin + (uint32_t)band * job.n_chunks + (uint32_t)chunk;
+    if (tid == 0) {
+        s_bad = flags[0] | flags[1] | flags[2] | flags[3];  // nan, depth, lines_overflow, refs_overflow
+        if (my_ticket == n_tiles - 1) *ticket = 0u;  // every ticket of this launch is drawn: leave the counter clean
+        const uint32_t t = tile_first + my_ticket;
+        const uint32_t j = (n_jobs == 1) ? job_first : job_first + find_job(n_jobs, t, [&](uint32_t k) { return jobs[job_first + k].tile_begin; });
+        const JobDev& jb = (n_jobs == 1) ? one_job : jobs[j];
+        const uint32_t lt = t - jb.tile_begin;
+        const uint32_t chunk = lt / jb.n_bands;
+        const uint32_t band = lt - chunk * jb.n_bands;
+        const uint32_t tile = jb.tile_begin + band * jb.n_chunks + chunk;
+        s_job = j;
+        s_chunk = chunk;
+        s_band = band;
+        s_tile = tile;
+        if (bin_cap) {  // fixed-capacity bins: tile_offs holds the per-tile counts; leave the counter clean for the next batch
+            s_count = min(tile_offs[tile], bin_cap);
+            tile_offs[tile] = 0u;
+        }
+    }
+    __syncthreads();
+    if (s_bad) return;
+    const JobDev& job = (n_jobs == 1) ? one_job : jobs[s_job];
+    const uint32_t tile = s_tile;
+    const int chunk = (int)s_chunk, band = (int)s_band;
     TileGeom g;
     g.row0 = band * TH;
     g.row1 = min(g.row0 + TH, job.height);
@@ -219,9 +236,9 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     // 1b one lane per span) ------------------------------------------------------------------------------------------
     SpanT* spans = spans_all + warp * Cfg::kWarpSpanCap;
     uint32_t rbeg, rend;
-    if (bin_cap) {  // fixed-capacity bins: tile_offs holds the per-tile counts
+    if (bin_cap) {
         rbeg = tile * bin_cap;
-        rend = rbeg + min(tile_offs[tile], bin_cap);
+        rend = rbeg + s_count;
     } else {
         rbeg = tile_offs[tile];
         rend = tile_offs[tile + 1];
@@ -323,8 +340,8 @@ __global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restri
 
 template <int CW, int TH, int THREADS>
 static void launch_raster_t(const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
-                            uint32_t n_tiles, const PaintDev* paints, const uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
-                            unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, cudaStream_t s) {
+                            uint32_t n_tiles, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
+                            unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, bool pdl, cudaStream_t s) {
     constexpr size_t smem = TileCfg<CW, TH, THREADS>::smem_bytes();
     static bool configured[64] = {};  // per template instance and per device: the attribute belongs to the device's function
     int dev = 0;
@@ -334,8 +351,20 @@ static void launch_raster_t(const JobDev* jobs, const JobDev* h_jobs, uint32_t n
         cudaFuncSetAttribute(raster_kernel<CW, TH, THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured[dev] = true;
     }
-    raster_kernel<CW, TH, THREADS><<<n_tiles, THREADS, smem, s>>>(jobs, n_jobs, job_first, tile_first, h_jobs[job_first], paints, tile_offs,
-                                                                  bin_cap, bin_lines, tile_state, epoch, ticket, status, zero_early ? 1u : 0u);
+    // `pdl`: launched with programmatic stream serialization — the CTAs may start while the preceding kernel of the stream
+    // (the flatten pass, which triggers early) is still draining, and block in griddepcontrol.wait until it has completed
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_tiles);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, raster_kernel<CW, TH, THREADS>, jobs, n_jobs, job_first, tile_first, h_jobs[job_first], paints, tile_offs, bin_cap,
+                       bin_lines, tile_state, epoch, ticket, status, zero_early ? 1u : 0u, n_tiles);
 }
 
 TileShape raster_tile_shape(int variant) {
@@ -346,12 +375,12 @@ TileShape raster_tile_shape(int variant) {
 }
 
 void launch_raster(int variant, const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
-                   uint32_t n_tiles, const PaintDev* paints, const uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
-                   unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, cudaStream_t s) {
+                   uint32_t n_tiles, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
+                   unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, bool pdl, cudaStream_t s) {
     if (n_tiles == 0) return;
 #define RGPU_LAUNCH(CW, TH, THREADS)                                                                                              \
     launch_raster_t<CW, TH, THREADS>(jobs, h_jobs, n_jobs, job_first, tile_first, n_tiles, paints, tile_offs, bin_cap, bin_lines, tile_state, \
-                                     epoch, ticket, status, zero_early, s)
+                                     epoch, ticket, status, zero_early, pdl, s)
     switch (variant) {
         case 1: RGPU_LAUNCH(128, 64, 256); break;
         default: RGPU_LAUNCH(1024, 8, 128); break;

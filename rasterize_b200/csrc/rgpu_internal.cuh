@@ -93,20 +93,27 @@ void launch_flatten_bin_emit(const JobDev* jobs, uint32_t n_jobs, uint32_t total
 // Single-pass variant: every tile owns a fixed bin of `bin_cap` lines at bin_lines[tile * bin_cap]; tile_counts ends
 // up holding the number of lines each tile wanted.  A tile that wants more than bin_cap sets refs_overflow (and
 // bin_max) and the host re-runs with a larger capacity or with the exact two-pass scheme.
-void launch_flatten_bin_fixed(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, uint32_t* tile_counts,
-                              double4* bin_lines, uint32_t bin_cap, int band_rows, int chunk_cols, Status* status, cudaStream_t s);
+// `h_jobs` is the host copy of the job table: a single-job batch passes its descriptor by value and `jobs` is not read.
+// `next_status` (may be NULL) is cleared for the following batch.
+void launch_flatten_bin_fixed(const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t total_items, double thr,
+                              uint32_t* tile_counts, double4* bin_lines, uint32_t bin_cap, int band_rows, int chunk_cols, Status* status,
+                              Status* next_status, cudaStream_t s);
 // tile geometry of the raster kernel variants
 struct TileShape { int cw, th; };
 TileShape raster_tile_shape(int variant);
 // `ticket` is a zeroed device counter private to this launch (dynamic tile ids for the carry look-back);
 // `tile_state` holds kMaxBandRows u64 words per tile, validated by `epoch` (no clearing between batches).
 // `h_jobs` is the host copy of the job table: single-job launches pass their descriptor by value.
+// `pdl`: the launch directly follows the flatten kernel in the stream and may overlap its tail (programmatic dependent
+// launch); the kernel waits for it before reading anything it wrote.
 // `zero_early`: clear every tile's cells before its id is known (pays off when most tiles hold lines).
 // bin_cap == 0: tile t's lines are bin_lines[tile_offs[t] .. tile_offs[t+1]); bin_cap > 0: fixed bins, tile t's lines
 // are bin_lines[t*bin_cap .. t*bin_cap + tile_offs[t]) (tile_offs then holds the per-tile COUNTS).
+// With fixed bins every tile clears its own counter after reading it and the last ticket resets the ticket counter, so
+// the next batch finds them zero without a memset.
 void launch_raster(int variant, const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
-                   uint32_t n_tiles, const PaintDev* paints, const uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
-                   unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, cudaStream_t s);
+                   uint32_t n_tiles, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
+                   unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, bool pdl, cudaStream_t s);
 // Fused one-CTA-per-job pipeline for canvases of at most 64 x 64 visible pixels (small.cu)
 bool small_canvas_eligible(uint32_t width, uint32_t height, int mode);
 void launch_small_canvas(const JobDev* jobs, uint32_t job_first, uint32_t n_jobs, const PaintDev* paints, double thr, Status* status,
