@@ -164,6 +164,21 @@ int rgpu_to_rgba8_dev(rgpu_ctx* ctx, const float* lin_dev, uint8_t* rgba_dev, si
 /* fill a LinColor device image with a constant (Layer::new with bg, src/scene.rs:483-501) */
 int rgpu_fill_color_dev(rgpu_ctx* ctx, float* lin_dev, size_t n_pixels, const float color[4]);
 
+/* `Layer::compose` on device (src/scene.rs:532-565) for the Clip and Opacity arms of `Pipeline::render_rec`
+ * (src/scene.rs:436-457).  Layers are dense device images; `*_origin` is the element index of the top-left pixel of the
+ * intersection rectangle inside each layer and `*_stride` its row pitch, both in pixels; width x height is that
+ * rectangle (computed by the caller as Layer::compose does from the layers' x / y / size).
+ *   rgpu_layer_scale_by_mask_dev:  lin[p] = lin[p] * mask[p]                 (Clip: child_layer.compose(mask_layer, ..))
+ *   rgpu_layer_blend_over_dev:     dst[p] = dst[p].blend_over(src[p] [* opacity])   (Clip / Opacity: layer.compose(child_layer, ..))
+ * `use_opacity == 0` leaves the source unscaled (the Clip arm), otherwise it is multiplied by `opacity` as f32. */
+int rgpu_layer_scale_by_mask_dev(rgpu_ctx* ctx, float* lin_dev, size_t lin_origin, size_t lin_stride, const float* mask_dev,
+                                 size_t mask_origin, size_t mask_stride, size_t width, size_t height);
+int rgpu_layer_blend_over_dev(rgpu_ctx* ctx, float* dst_dev, size_t dst_origin, size_t dst_stride, const float* src_dev,
+                              size_t src_origin, size_t src_stride, size_t width, size_t height, int use_opacity, float opacity);
+/* LinColor device image -> RGBA8 HOST image in one call (conversion kernel + a 4 B/pixel download): the export step that
+ * follows `Scene::render` in every CLI run (`ImageOwned<LinColor>` -> RGBA8, src/image.rs:136-231, src/color.rs:164-175). */
+int rgpu_download_rgba8(rgpu_ctx* ctx, const float* lin_dev, size_t n_pixels, uint8_t* rgba_host);
+
 /* ---- plumbing ----------------------------------------------------------------------------------- */
 void* rgpu_stream(rgpu_ctx* ctx);  /* cudaStream_t the context launches on */
 int rgpu_sync(rgpu_ctx* ctx);

@@ -128,6 +128,24 @@ typedef struct {
 } orc_fill_job;
 long orc_scene_fill_jobs(const orc_scene*, const double tr[6], const double* view_minmax, orc_fill_job* out, size_t cap);
 
+/* The whole node table Pipeline::build produces (src/scene.rs:268-357), in allocation order: children come before their
+ * parents and the root is the last node.  kind: 0 Fill, 1 Group, 2 Opacity, 3 Clip.  Group children are
+ * children[child_begin .. child_begin + child_count); Opacity / Clip have one child in `child`. */
+typedef struct {
+    int kind;
+    orc_path* path;   /* borrowed: Fill path / Clip path, else NULL */
+    orc_paint* paint; /* borrowed: Fill paint, else NULL */
+    int fill_rule;
+    double tr[6];     /* Fill: node.tr ; Clip: node.clip_tr */
+    double bbox[4];   /* node.bbox */
+    double opacity;
+    long child;
+    long child_begin, child_count;
+} orc_pipe_node;
+/* returns the node count (call with out == NULL to size); *n_children_out = total entries of `children` */
+long orc_scene_pipeline(const orc_scene*, const double tr[6], const double* view_minmax, orc_pipe_node* out, size_t cap,
+                        long* children, size_t children_cap, size_t* n_children_out);
+
 /* LCG of benches/scene_bench.rs:53-88 */
 double orc_lcg_uniform(uint32_t* state);
 /* synthetic glyph of SURVEY §8d C4: 3 closed contours x 6 cubics, coords uniform()*56+4, seed = index+1 */

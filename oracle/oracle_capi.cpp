@@ -433,4 +433,46 @@ long orc_scene_fill_jobs(const orc_scene* cs, const double tr[6], const double* 
     return (long)n;
 }
 
+long orc_scene_pipeline(const orc_scene* cs, const double tr[6], const double* view, orc_pipe_node* out, size_t cap, long* children,
+                        size_t children_cap, size_t* n_children_out) {
+    auto* s = const_cast<orc_scene*>(cs);
+    Pipeline p;
+    std::optional<BBox> v;
+    if (view) v = BB(view);
+    p.build_rec(*s->s, v, TR(tr));
+    size_t nc = 0;
+    for (size_t id = 0; id < p.nodes.size(); id++) {
+        const PipelineNode& node = p.nodes[id];
+        if (out && id < cap) {
+            orc_pipe_node& o = out[id];
+            o.kind = (int)node.kind;
+            o.path = nullptr;
+            o.paint = nullptr;
+            o.fill_rule = (int)node.fill_rule;
+            o.opacity = node.opacity;
+            o.child = (long)node.child;
+            o.child_begin = (long)nc;
+            o.child_count = (long)node.children.size();
+            TR_out(node.kind == PipelineNode::Clip ? node.clip_tr : node.tr, o.tr);
+            o.bbox[0] = node.bbox.min.x; o.bbox[1] = node.bbox.min.y; o.bbox[2] = node.bbox.max.x; o.bbox[3] = node.bbox.max.y;
+            if (node.path) {
+                auto pp = std::make_unique<orc_path>(); pp->p = *node.path;
+                o.path = pp.get();
+                s->job_paths.push_back(std::move(pp));
+            }
+            if (node.paint) {
+                auto pa = std::make_unique<orc_paint>(); pa->p = *node.paint;
+                o.paint = pa.get();
+                s->job_paints.push_back(std::move(pa));
+            }
+        }
+        for (size_t c : node.children) {
+            if (children && nc < children_cap) children[nc] = (long)c;
+            nc++;
+        }
+    }
+    if (n_children_out) *n_children_out = nc;
+    return (long)p.nodes.size();
+}
+
 }  // extern "C"

@@ -578,6 +578,24 @@ class GpuRasterizer:
     def to_rgba8(self, lin_ptr: int, rgba_ptr: int, n_pixels: int) -> None:
         self._check(ffi.lib().rgpu_to_rgba8_dev(self.ctx, C.c_void_p(lin_ptr), C.c_void_p(rgba_ptr), n_pixels))
 
+    def layer_scale_by_mask(self, lin_ptr, lin_origin, lin_stride, mask_ptr, mask_origin, mask_stride, width, height) -> None:
+        """`child_layer.compose(mask_layer, |dst, src| dst * src)` on the intersection rectangle (src/scene.rs:453-455)."""
+        self._check(ffi.lib().rgpu_layer_scale_by_mask_dev(self.ctx, C.c_void_p(lin_ptr), lin_origin, lin_stride, C.c_void_p(mask_ptr),
+                                                            mask_origin, mask_stride, width, height))
+
+    def layer_blend_over(self, dst_ptr, dst_origin, dst_stride, src_ptr, src_origin, src_stride, width, height, opacity=None) -> None:
+        """`layer.compose(child_layer, |dst, src| dst.blend_over(src [* opacity]))` (src/scene.rs:436-457)."""
+        self._check(ffi.lib().rgpu_layer_blend_over_dev(self.ctx, C.c_void_p(dst_ptr), dst_origin, dst_stride, C.c_void_p(src_ptr), src_origin,
+                                                         src_stride, width, height, int(opacity is not None),
+                                                         float(opacity if opacity is not None else 1.0)))
+
+    def download_rgba8(self, lin_ptr: int, shape) -> np.ndarray:
+        """LinColor device image -> RGBA8 host image [H, W, 4] u8 (conversion on device, 4 B/pixel over PCIe)."""
+        h, w = shape
+        out = np.empty((h, w, 4), dtype=np.uint8)
+        self._check(ffi.lib().rgpu_download_rgba8(self.ctx, C.c_void_p(lin_ptr), h * w, out.ctypes.data))
+        return out
+
     def fill_color(self, lin_ptr: int, n_pixels: int, color) -> None:
         c = np.asarray(color, dtype=np.float32)
         self._check(ffi.lib().rgpu_fill_color_dev(self.ctx, C.c_void_p(lin_ptr), n_pixels, c.ctypes.data_as(C.POINTER(C.c_float))))

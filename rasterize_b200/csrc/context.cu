@@ -839,6 +839,44 @@ int rgpu_fill_color_dev(rgpu_ctx* ctx, float* lin_dev, size_t n_pixels, const fl
     return RGPU_OK;
 }
 
+int rgpu_layer_scale_by_mask_dev(rgpu_ctx* ctx, float* lin_dev, size_t lin_origin, size_t lin_stride, const float* mask_dev,
+                                 size_t mask_origin, size_t mask_stride, size_t width, size_t height) {
+    if (!ctx || ((!lin_dev || !mask_dev) && width * height)) return RGPU_ERR_INVALID;
+    if (width > 0xffffffffull || height > 0xffffffffull) return fail(ctx, RGPU_ERR_INVALID, "layer too large");
+    CK(ctx, cudaSetDevice(ctx->device));
+    launch_scale_by_mask(reinterpret_cast<float4*>(lin_dev) + lin_origin, lin_stride, mask_dev + mask_origin, mask_stride, (uint32_t)width,
+                         (uint32_t)height, ctx->stream);
+    ctx->n_launches++;
+    CK(ctx, cudaGetLastError());
+    return RGPU_OK;
+}
+
+int rgpu_layer_blend_over_dev(rgpu_ctx* ctx, float* dst_dev, size_t dst_origin, size_t dst_stride, const float* src_dev, size_t src_origin,
+                              size_t src_stride, size_t width, size_t height, int use_opacity, float opacity) {
+    if (!ctx || ((!dst_dev || !src_dev) && width * height)) return RGPU_ERR_INVALID;
+    if (width > 0xffffffffull || height > 0xffffffffull) return fail(ctx, RGPU_ERR_INVALID, "layer too large");
+    CK(ctx, cudaSetDevice(ctx->device));
+    launch_blend_over(reinterpret_cast<float4*>(dst_dev) + dst_origin, dst_stride, reinterpret_cast<const float4*>(src_dev) + src_origin,
+                      src_stride, (uint32_t)width, (uint32_t)height, use_opacity != 0, opacity, ctx->stream);
+    ctx->n_launches++;
+    CK(ctx, cudaGetLastError());
+    return RGPU_OK;
+}
+
+int rgpu_download_rgba8(rgpu_ctx* ctx, const float* lin_dev, size_t n_pixels, uint8_t* rgba_host) {
+    if (!ctx || ((!lin_dev || !rgba_host) && n_pixels)) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (n_pixels == 0) return RGPU_OK;
+    int rc;
+    if ((rc = ensure_dev(ctx, ctx->img_f32, 4 * n_pixels))) return rc;  // RGBA8 staging shares the f32 mask scratch
+    uchar4* d_rgba = static_cast<uchar4*>(ctx->img_f32.p);
+    launch_to_rgba8(reinterpret_cast<const float4*>(lin_dev), d_rgba, n_pixels, ctx->stream);
+    ctx->n_launches++;
+    CK(ctx, cudaMemcpyAsync(rgba_host, d_rgba, 4 * n_pixels, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RGPU_OK;
+}
+
 // ---- trait-level entry points ------------------------------------------------------------------------
 
 int rgpu_flatten(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int close, double* lines_out, size_t cap, size_t* n_out) {

@@ -121,6 +121,11 @@ void launch_small_canvas(const JobDev* jobs, uint32_t job_first, uint32_t n_jobs
 void launch_to_rgba8(const float4* lin, uchar4* out, size_t n, cudaStream_t s);
 void launch_fill_color(float4* lin, size_t n, float4 color, cudaStream_t s);
 void launch_f32_to_f64(const float* in, double* out, size_t n, cudaStream_t s);
+// Layer::compose on device (compose.cu): strides in pixels, pointers already offset to the intersection rectangle
+void launch_scale_by_mask(float4* lin, unsigned long long lin_stride, const float* mask, unsigned long long mask_stride, uint32_t width,
+                          uint32_t height, cudaStream_t s);
+void launch_blend_over(float4* dst, unsigned long long dst_stride, const float4* src, unsigned long long src_stride, uint32_t width,
+                       uint32_t height, bool use_opacity, float opacity, cudaStream_t s);
 
 // Tiles a flattened line may touch: every band of 2^band_shift rows its y-range covers (the reference's own row
 // range, src/rasterize.rs:414, 421) and, inside a band, every chunk of 2^chunk_shift columns its cells can land in

@@ -90,3 +90,75 @@ def oracle_paint(d):
     return O.OraclePaint(h)
 
 
+
+
+# ---- full pipelines (clip / opacity) -------------------------------------------------------------------------
+def _layer_geom(bbox):
+    x0, y0 = math.floor(bbox[0]), math.floor(bbox[1])
+    return int(x0), int(y0), max(0, int(math.ceil(bbox[2])) - int(x0)), max(0, int(math.ceil(bbox[3])) - int(y0))
+
+
+def _intersect(a, b):
+    """(ax, ay, aw, ah), (bx, by, bw, bh) -> slices into a and b of Layer::compose's rectangle (src/scene.rs:540-549)."""
+    x0, x1 = max(a[0], b[0]), min(a[0] + a[2], b[0] + b[2])
+    y0, y1 = max(a[1], b[1]), min(a[1] + a[3], b[1] + b[3])
+    if x1 <= x0 or y1 <= y0:
+        return None
+    return (slice(y0 - a[1], y1 - a[1]), slice(x0 - a[0], x1 - a[0])), (slice(y0 - b[1], y1 - b[1]), slice(x0 - b[0], x1 - b[0]))
+
+
+def _blend_over(dst, src):
+    """f32, unfused: other + self * (1 - other.alpha), src/color.rs:342-344"""
+    k = np.float32(1.0) - src[..., 3:4]
+    return src + dst * k
+
+
+def render_pipeline_oracle(pl):
+    """`Pipeline::render_rec` (src/scene.rs:397-459) with the oracle's `fill` / `mask` and numpy f32 layer composition."""
+    nodes = pl.nodes
+
+    def render(node_id, view, bg):
+        geom = _layer_geom(view if view is not None else nodes[node_id].bbox)
+        img = np.zeros((geom[3], geom[2], 4), dtype=np.float32)
+        if bg is not None:
+            img[:] = bg
+        rec(node_id, img, geom)
+        return img, geom
+
+    def rec(node_id, img, geom):
+        n = nodes[node_id]
+        lx, ly, W, H = geom
+        if n.kind == 0:
+            col_min = max(0, min(math.floor(n.bbox[0]) - lx, W))
+            col_max = max(col_min, min(math.ceil(n.bbox[2]) - lx + 1, W))
+            row_min = max(0, min(math.floor(n.bbox[1]) - ly, H))
+            row_max = max(row_min, min(math.ceil(n.bbox[3]) - ly + 1, H))
+            tr = O.transform_mul(O.translate(-math.floor(n.bbox[0]), -math.floor(n.bbox[1])), n.tr)
+            shape = O.Shape(row_min * W + col_min, col_max - col_min, row_max - row_min, W, 1)
+            if shape.width and shape.height:
+                opath(n.path).fill(tr, int(n.fill_rule), oracle_paint(n.paint_desc), img, shape=shape)
+        elif n.kind == 1:
+            for c in n.children:
+                rec(c, img, geom)
+        elif n.kind == 2:
+            child, cg = render(n.child, None, None)
+            r = _intersect(geom, cg)
+            if r:
+                img[r[0]] = _blend_over(img[r[0]], child[r[1]] * np.float32(n.opacity))
+        elif n.kind == 3:
+            mg = _layer_geom(n.bbox)
+            mask = np.zeros((mg[3], mg[2]), dtype=np.float64)
+            child, cg = render(n.child, None, None)
+            if mask.size:
+                opath(n.path).mask(O.transform_mul(O.translate(-float(mg[0]), -float(mg[1])), n.tr), int(n.fill_rule), mask)
+            r = _intersect(cg, mg)
+            if r:
+                child[r[0]] = child[r[0]] * mask[r[1]].astype(np.float32)[..., None]
+            r = _intersect(geom, cg)
+            if r:
+                img[r[0]] = _blend_over(img[r[0]], child[r[1]])
+
+    if not nodes:
+        return 0, 0, np.zeros((0, 0, 4), dtype=np.float32)
+    img, geom = render(len(nodes) - 1, pl.view, pl.bg)
+    return geom[0], geom[1], img

@@ -48,6 +48,12 @@ class FillJob(C.Structure):
                 ("bbox", C.c_double * 4)]
 
 
+class PipeNode(C.Structure):
+    _fields_ = [("kind", C.c_int), ("path", C.c_void_p), ("paint", C.c_void_p), ("fill_rule", C.c_int), ("tr", C.c_double * 6),
+                ("bbox", C.c_double * 4), ("opacity", C.c_double), ("child", C.c_long), ("child_begin", C.c_long),
+                ("child_count", C.c_long)]
+
+
 _lib = None
 
 
@@ -123,6 +129,7 @@ def lib():
     sig("orc_layer_data", pf, vp)
     sig("orc_layer_free", None, vp)
     sig("orc_scene_fill_jobs", C.c_long, vp, pd, pd, C.POINTER(FillJob), sz)
+    sig("orc_scene_pipeline", C.c_long, vp, pd, pd, C.POINTER(PipeNode), sz, C.POINTER(C.c_long), sz, psz)
     sig("orc_lcg_uniform", dbl, C.POINTER(C.c_uint32))
     sig("orc_glyph", vp, C.c_uint32)
     _lib = L
@@ -389,6 +396,29 @@ class OracleScene:
             jobs.append(dict(path=OraclePath(j.path, owned=False), paint=OraclePaint(j.paint, owned=False), fill_rule=j.fill_rule,
                              tr=np.array(j.tr[:]), bbox=np.array(j.bbox[:]), _keep=self))
         return jobs
+
+
+def _pipeline(self, tr=IDENTITY, view=None):
+    """Node table of Pipeline::build (children before parents, root last): list of dict(kind, path, paint, fill_rule, tr,
+    bbox, opacity, child, children)."""
+    v = None if view is None else np.asarray(view, dtype=np.float64)
+    vp = None if v is None else _pd(v)
+    nch = C.c_size_t()
+    n = lib().orc_scene_pipeline(self.h, _pd(_tr(tr)), vp, None, 0, None, 0, C.byref(nch))
+    buf = (PipeNode * max(n, 1))()
+    ch = (C.c_long * max(nch.value, 1))()
+    lib().orc_scene_pipeline(self.h, _pd(_tr(tr)), vp, buf, n, ch, nch.value, C.byref(nch))
+    nodes = []
+    for i in range(n):
+        j = buf[i]
+        nodes.append(dict(kind=j.kind, path=OraclePath(j.path, owned=False) if j.path else None,
+                          paint=OraclePaint(j.paint, owned=False) if j.paint else None, fill_rule=j.fill_rule, tr=np.array(j.tr[:]),
+                          bbox=np.array(j.bbox[:]), opacity=j.opacity, child=j.child,
+                          children=[ch[k] for k in range(j.child_begin, j.child_begin + j.child_count)], _keep=self))
+    return nodes
+
+
+OracleScene.pipeline = _pipeline
 
 
 def fit_size(bbox, w, h, align=1):

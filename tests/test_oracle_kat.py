@@ -412,3 +412,26 @@ def test_nan_panics():
     p = O.OraclePath.from_flat([[0, 0], [float("nan"), 1]], [2], [0, 1], [0])
     with pytest.raises(ValueError):
         p.flatten()
+
+
+def test_right_edge_wrap_quirk():
+    """A reference DEFECT the oracle reproduces and the GPU path deliberately does not.
+
+    `signed_difference_line` cuts a line that crosses x == width at that column and keeps the inside half, choosing it with
+    `p0.x() < width` (src/rasterize.rs:377-383).  When p0.x == width exactly and the line continues to the right, the test
+    is false and the OUTSIDE half is kept; its cells land at `row_offset + x0i` with x0i > width, i.e. in the first columns
+    of the NEXT row (src/rasterize.rs:437-444), or out of bounds (a panic) on the last row.  Expected values traced by hand
+    from the reference for M0,0 L5,0 L7,4 L0,4 Z on a 6 x 6 image (width - 1 == 5): the geometric answer is 1.0 in rows 0..3.
+    """
+    p = O.OraclePath.parse(b"M0,0 L5,0 L7,4 L0,4 Z")
+    img = np.zeros((6, 6))
+    p.mask(O.IDENTITY, O.NONZERO, img)
+    expected = np.array([
+        [1.0, 1.0, 1.0, 1.0, 1.0, 0.25],     # col 0: -1 (left edge), col 5: +0.75
+        [0.75, 0.75, 0.75, 0.75, 0.75, 0.5],  # col 0: -1 + 0.25 wrapped from row 0
+        [0.25, 0.25, 0.25, 0.25, 0.25, 0.25],  # col 0: -1 + 0.75 wrapped from row 1
+        [0.25, 0.0, 0.0, 0.0, 0.0, 0.0],      # row 2's cells (x0i = 6) land here: col 0 +0.75, col 1 +0.25
+        [0.25, 1.0, 1.0, 1.0, 1.0, 1.0],      # row 3's cells land in row 4
+        [0.0, 0.0, 0.0, 0.0, 0.0, 0.0],
+    ])
+    np.testing.assert_allclose(img, expected, atol=1e-12)
