@@ -1,12 +1,13 @@
 #!/usr/bin/env python
 """Benchmark of the fill hot path (BASELINE.json: Mpix/s, flattened lines/s, nonzero fill) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4|c5]
 
 A step is one pass of the hot path (flatten -> bin -> signed-difference raster) over one batch:
   c2 (default, BASELINE configs[1]): data/material.path fitted to 4096x4096, `Rasterizer::mask`, non-zero.
   c4: a batch of synthetic random-cubic glyphs at 64x64 (SURVEY §8d generator), mask per glyph.
   c5: tv.path stroked on a 32768-wide canvas, this rank's band of rows (band sharding).
+  c1 / c3: Scene::render of the squirrel CLI scene (512 px) / firefox.scene (2048 x 2048) on a device-resident layer + RGBA8.
 N > 1 (under torchrun): every rank runs the same per-GPU workload on its own device with no data-path collective
 (independent paths of a batch / bands of a canvas) => weak scaling; value = units of all ranks / max-over-ranks time.
 
@@ -181,6 +182,46 @@ def build_workload(name: str, rb, rast, rank: int, world: int, torch):
                     canvas=[w, h], items_per_gpu=1, pixels_per_step=w * h, in_bytes=path.input_bytes(), out_bytes=4 * w * h,
                     keep=[dp, canvas])
         return jobs, True, info
+    if name in ("c1", "c3"):
+        # Scene::render of a Fill-only scene on a device-resident LinColor layer + RGBA8 export (SURVEY §8d "(s)" bytes):
+        # c1 = examples/rasterize default scene for squirrel.path -w 512; c3 = firefox.scene at 2048 x 2048 (14 gradient fills)
+        import math
+        sc = assets.load_scene("squirrel_cli_512" if name == "c1" else "firefox_2048")
+        x0, y0, x1, y1 = sc.view
+        lx, ly = math.floor(x0), math.floor(y0)
+        W, H = math.ceil(x1) - lx, math.ceil(y1) - ly
+        layer = torch.empty((H, W, 4), dtype=torch.float32, device=dev)
+        rgba = torch.empty((H, W, 4), dtype=torch.uint8, device=dev)
+        jobs, keep, in_bytes = [], [], 0
+        for f in sc.fills:
+            bx0, by0, bx1, by1 = f.bbox
+            col_min = max(0, min(math.floor(bx0) - lx, W))
+            col_max = max(col_min, min(math.ceil(bx1) - lx + 1, W))
+            row_min = max(0, min(math.floor(by0) - ly, H))
+            row_max = max(row_min, min(math.ceil(by1) - ly + 1, H))
+            tr = rb.Transform.new_translate(-math.floor(bx0), -math.floor(by0)) * rb.Transform.from_array(f.tr)
+            dp = rast.upload(f.path)
+            keep.append(dp)
+            in_bytes += f.path.input_bytes()
+            jobs.append(rb.Job(dp, tr, f.fill_rule, ffi.JOB_FILL, layer.data_ptr(), col_max - col_min, row_max - row_min, W,
+                               origin=row_min * W + col_min, paint=f.paint, path_bbox=f.path_bbox))
+        bg = sc.bg
+
+        def pre():
+            if bg is not None:
+                rast.fill_color(layer.data_ptr(), W * H, bg)
+            else:
+                rast.device_zero(layer.data_ptr(), W * H * 16)
+
+        def post():
+            rast.to_rgba8(layer.data_ptr(), rgba.data_ptr(), W * H)
+
+        what = ("c1: examples/rasterize scene of data/squirrel.path at 512 px (checkerboard + fill over #f0f0f0)" if name == "c1"
+                else "c3: data/firefox.scene Scene::render at 2048x2048, 14 linear/radial gradient fills")
+        info = dict(workload=what + ", device-resident LinColor layer + RGBA8 export", canvas=[W, H], items_per_gpu=len(jobs),
+                    pixels_per_step=W * H, in_bytes=in_bytes, out_bytes=(16 + 4) * W * H, keep=[keep, layer, rgba], pre_step=pre,
+                    post_step=post, extra_launches_per_step=2)
+        return jobs, False, info
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -208,8 +249,14 @@ def run_ours(args):
     stream = torch.cuda.ExternalStream(rast.stream(), device=torch.device("cuda", local_rank))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
+    pre_step, post_step = info.get("pre_step"), info.get("post_step")
+
     def step(sync=False):
+        if pre_step:
+            pre_step()
         rast.submit_prepared(prepared, independent=independent, sync=sync)
+        if post_step:
+            post_step()
 
     # first call sizes the scratch buffers (and re-runs on overflow); then untimed warm-up
     step(sync=True)
@@ -313,7 +360,9 @@ def run_ours(args):
 
     if rank == 0:
         out = {
-            "metric": "fill throughput (Rasterizer::mask, nonzero), pixels rasterized per second", "value": round(value, 1), "unit": "Mpix/s",
+            "metric": ("scene render throughput (Scene::render fills + RGBA8 export), pixels per second" if args.workload in ("c1", "c3")
+                       else "fill throughput (Rasterizer::mask, nonzero), pixels rasterized per second"),
+            "value": round(value, 1), "unit": "Mpix/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 geometry / Q7.24 fixed-point accumulation / f32 coverage",
             "data": "synthetic" if args.workload == "c4" else "reference asset (flat fixture of data/*.path), random-free",
@@ -412,7 +461,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -560,7 +560,9 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     } else {
         for (uint32_t j = 0; j < n_live; j++) {
             const JobDev& d = ctx->h_jobs[j];
-            launch_raster(variant, d_jobs, ctx->h_jobs, 1, j, d.tile_begin, d.n_bands * d.n_chunks, d_paints, d_bo, bin_cap, d_refs, d_state,
+            // a FILL launch spends its time evaluating the paint per pixel: same tile, four times the threads
+            launch_raster((variant == 0 && d.mode == kModeFill && d.paint_index >= 0 && ctx->h_paints[d.paint_index].kind != 0) ? 2 : variant,
+                          d_jobs, ctx->h_jobs, 1, j, d.tile_begin, d.n_bands * d.n_chunks, d_paints, d_bo, bin_cap, d_refs, d_state,
                           ctx->epoch, d_tickets + j, d_status, zero_early, /*pdl=*/pdl_ok && j == 0, s);
             ctx->n_launches += 1;
         }

@@ -45,9 +45,11 @@ struct TileCfg {
 // Phase 2 for the rows of one warp.  Lane l owns L consecutive columns: serial prefix in registers, ONE warp scan of the
 // 32 lane totals, coverage written back to shared memory in place (as floats) and read back transposed so that global
 // stores are full 512 B coalesced 128-bit accesses.  Rows no line touched are written straight from registers.
-template <int CW, int TH, int THREADS, bool EVENODD, class Cfg>
+template <int CW, int TH, int THREADS, bool EVENODD, bool FILL, class Cfg>
 __device__ __forceinline__ void scan_rows(const JobDev& job, const PaintDev& s_paint, int* cells, const int* carry, const int* row_touched,
-                                          int row0, int row1, int cx0, int mode, int tid) {
+                                          int* row_live, int row0, int row1, int cx0, int mode_in, int tid) {
+    // FILL = false: the launch holds no FILL job and the paint / composite code is not even compiled in
+    const int mode = (!FILL && mode_in == kModeFill) ? kModeMask : mode_in;
     constexpr int L = Cfg::kL;
     constexpr int NQ = L / 4;  // 128-bit words per lane run
     const int warp = tid >> 5, lane = tid & 31;
@@ -80,7 +82,7 @@ __device__ __forceinline__ void scan_rows(const JobDev& job, const PaintDev& s_p
             }
         } else {
             float c = coverage_from_fixed<EVENODD>(acc);  // no line touched this row of the tile: constant coverage
-            if (mode != kModeFill) {
+            if (!FILL || mode != kModeFill) {
                 // straight from registers: no shared-memory round trip for empty rows (most of a sparse canvas)
                 if (mode == kModeCoverage && c < 1e-6f) c = 0.f;
                 const float4 cv = make_float4(c, c, c, c);
@@ -93,62 +95,75 @@ __device__ __forceinline__ void scan_rows(const JobDev& job, const PaintDev& s_p
                 }
                 continue;
             }
-            if (c < 1e-6f) continue;  // FILL: nothing to composite on this row
+            // FILL: stage the constant coverage like a scanned row (or mark the row as having nothing to composite)
+            if (lane == 0) row_live[r] = c >= 1e-6f;
+            if (c < 1e-6f) continue;
             const float4 cv = make_float4(c, c, c, c);
 #pragma unroll
             for (int i = 0; i < NQ; i++) *reinterpret_cast<float4*>(bc + swz<true>(lane * L + i * 4)) = cv;
+            continue;
+        }
+        if (FILL && mode == kModeFill) {
+            if (lane == 0) row_live[r] = 1;
+            continue;  // composited below by the whole CTA
         }
         __syncwarp();
         // transposed read-back: lane l takes columns [128*i + 4l, +4): full 512 B coalesced 128-bit stores
-        if (mode != kModeFill) {
-            float* out = reinterpret_cast<float*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride + cx0;
-            if (bw == CW && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {  // whole, aligned tile row: no per-word tests
+        float* out = reinterpret_cast<float*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride + cx0;
+        if (bw == CW && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {  // whole, aligned tile row: no per-word tests
 #pragma unroll
-                for (int i = 0; i < CW / 128; i++) {
-                    const int col = i * 128 + lane * 4;
-                    float4 cv = *reinterpret_cast<const float4*>(bc + swz<true>(col));
-                    if (mode == kModeCoverage) {  // mask_iter drops abs(alpha) < 1e-6 (src/rasterize.rs:348)
-                        if (cv.x < 1e-6f) cv.x = 0.f;
-                        if (cv.y < 1e-6f) cv.y = 0.f;
-                        if (cv.z < 1e-6f) cv.z = 0.f;
-                        if (cv.w < 1e-6f) cv.w = 0.f;
-                    }
-                    __stcs(reinterpret_cast<float4*>(out + col), cv);  // streaming store: written once, never re-read
+            for (int i = 0; i < CW / 128; i++) {
+                const int col = i * 128 + lane * 4;
+                float4 cv = *reinterpret_cast<const float4*>(bc + swz<true>(col));
+                if (mode == kModeCoverage) {  // mask_iter drops abs(alpha) < 1e-6 (src/rasterize.rs:348)
+                    if (cv.x < 1e-6f) cv.x = 0.f;
+                    if (cv.y < 1e-6f) cv.y = 0.f;
+                    if (cv.z < 1e-6f) cv.z = 0.f;
+                    if (cv.w < 1e-6f) cv.w = 0.f;
                 }
-            } else {
-                const float* covs = reinterpret_cast<const float*>(bc);
-                for (int col = lane; col < bw; col += 32) {
-                    float cvx = covs[swz<true>(col)];
-                    if (mode == kModeCoverage && cvx < 1e-6f) cvx = 0.f;
-                    out[col] = cvx;
-                }
+                __stcs(reinterpret_cast<float4*>(out + col), cv);  // streaming store: written once, never re-read
             }
         } else {
-            float4* out = reinterpret_cast<float4*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride + cx0;
             const float* covs = reinterpret_cast<const float*>(bc);
-            for (int px = lane; px < bw; px += 32) {  // consecutive lanes composite consecutive pixels (16 B each)
-                const float alpha = covs[swz<true>(px)];
-                if (alpha >= 1e-6f) {
-                    float4 color = (job.paint_index >= 0) ? paint_at(s_paint, cx0 + px, y) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    // with_alpha: self * (alpha as f32), src/color.rs:347-349
-                    color = make_float4(fmul(color.x, alpha), fmul(color.y, alpha), fmul(color.z, alpha), fmul(color.w, alpha));
-                    // blend_over: other + self * (1 - other.alpha), src/color.rs:342-344
-                    float4 dstc = out[px];
-                    const float k = fsub(1.0f, color.w);
-                    dstc = make_float4(fadd(color.x, fmul(dstc.x, k)), fadd(color.y, fmul(dstc.y, k)), fadd(color.z, fmul(dstc.z, k)),
-                                       fadd(color.w, fmul(dstc.w, k)));
-                    out[px] = dstc;
-                }
+            for (int col = lane; col < bw; col += 32) {
+                float cvx = covs[swz<true>(col)];
+                if (mode == kModeCoverage && cvx < 1e-6f) cvx = 0.f;
+                out[col] = cvx;
             }
         }
         __syncwarp();
+    }
+    if (!FILL || mode != kModeFill) return;
+    // ---- K4: paint + composite.  The per-pixel paint evaluation (f64 point transform, gradient offset, stop search,
+    // sRGB -> linear) is hundreds of dependent instructions, so the tile's pixels are spread over ALL threads of the CTA:
+    // consecutive threads take consecutive pixels of a row (16 B each, coalesced read-modify-write).
+    __syncthreads();
+    const int rows = row1 - row0;
+    const float* covs = reinterpret_cast<const float*>(cells);
+    for (int p = tid; p < rows * bw; p += THREADS) {
+        const int r = p / bw, px = p - r * bw;
+        if (!row_live[r]) continue;
+        const float alpha = covs[r * CW + swz<true>(px)];
+        if (alpha >= 1e-6f) {
+            const int y = row0 + r;
+            float4* out = reinterpret_cast<float4*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride + cx0;
+            float4 color = (job.paint_index >= 0) ? paint_at(s_paint, cx0 + px, y) : make_float4(0.f, 0.f, 0.f, 0.f);
+            // with_alpha: self * (alpha as f32), src/color.rs:347-349
+            color = make_float4(fmul(color.x, alpha), fmul(color.y, alpha), fmul(color.z, alpha), fmul(color.w, alpha));
+            // blend_over: other + self * (1 - other.alpha), src/color.rs:342-344
+            float4 dstc = out[px];
+            const float k = fsub(1.0f, color.w);
+            dstc = make_float4(fadd(color.x, fmul(dstc.x, k)), fadd(color.y, fmul(dstc.y, k)), fadd(color.z, fmul(dstc.z, k)),
+                               fadd(color.w, fmul(dstc.w, k)));
+            out[px] = dstc;
+        }
     }
 }
 
 // `one_job`: the launch covers a single job whose descriptor travels in the kernel parameters (constant bank:
 // no dependent global loads before the tile can start).
-template <int CW, int TH, int THREADS>
-__global__ void __launch_bounds__(THREADS, (TH <= 8 ? 6 : 2))
+template <int CW, int TH, int THREADS, bool FILL>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : 1))
 raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first, const JobDev one_job,
               const PaintDev* __restrict__ paints, uint32_t* __restrict__ tile_offs, uint32_t bin_cap,
               const double4* __restrict__ bin_lines, unsigned long long* __restrict__ tile_state, uint32_t epoch,
@@ -260,7 +275,7 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     }
     __syncthreads();
     // the piece constants are dead: stage the paint over them
-    if (mode == kModeFill && job.paint_index >= 0) {
+    if (FILL && mode == kModeFill && job.paint_index >= 0) {
         const int* src = reinterpret_cast<const int*>(&paints[job.paint_index]);
         int* dst = reinterpret_cast<int*>(p_ax);
         for (int i = tid; i < (int)(sizeof(PaintDev) / 4); i += THREADS) dst[i] = src[i];
@@ -305,9 +320,9 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     }
     __syncthreads();
 
-    // ---- phase 2: per-row scan, fill rule, store / composite --------------------------------------------
-    if (job.rule == 1) scan_rows<CW, TH, THREADS, true, Cfg>(job, s_paint, cells, carry, row_touched, row0, row1, cx0, mode, tid);
-    else scan_rows<CW, TH, THREADS, false, Cfg>(job, s_paint, cells, carry, row_touched, row0, row1, cx0, mode, tid);
+    // ---- phase 2: per-row scan, fill rule, store / composite (rowtot is dead: FILL reuses it as a per-row live flag) ----
+    if (job.rule == 1) scan_rows<CW, TH, THREADS, true, FILL, Cfg>(job, s_paint, cells, carry, row_touched, rowtot, row0, row1, cx0, mode, tid);
+    else scan_rows<CW, TH, THREADS, false, FILL, Cfg>(job, s_paint, cells, carry, row_touched, rowtot, row0, row1, cx0, mode, tid);
 }
 
 // `From<LinColor> for RGBA`, src/color.rs:164-175 with the x86 l2s polynomial; `as u8` saturates
@@ -338,7 +353,7 @@ __global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restri
 }  // namespace
 
 
-template <int CW, int TH, int THREADS>
+template <int CW, int TH, int THREADS, bool FILL>
 static void launch_raster_t(const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
                             uint32_t n_tiles, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
                             unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, bool pdl, cudaStream_t s) {
@@ -347,8 +362,8 @@ static void launch_raster_t(const JobDev* jobs, const JobDev* h_jobs, uint32_t n
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaFuncSetAttribute(raster_kernel<CW, TH, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(raster_kernel<CW, TH, THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(raster_kernel<CW, TH, THREADS, FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(raster_kernel<CW, TH, THREADS, FILL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured[dev] = true;
     }
     // `pdl`: launched with programmatic stream serialization — the CTAs may start while the preceding kernel of the stream
@@ -363,13 +378,14 @@ static void launch_raster_t(const JobDev* jobs, const JobDev* h_jobs, uint32_t n
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, raster_kernel<CW, TH, THREADS>, jobs, n_jobs, job_first, tile_first, h_jobs[job_first], paints, tile_offs, bin_cap,
+    cudaLaunchKernelEx(&cfg, raster_kernel<CW, TH, THREADS, FILL>, jobs, n_jobs, job_first, tile_first, h_jobs[job_first], paints, tile_offs, bin_cap,
                        bin_lines, tile_state, epoch, ticket, status, zero_early ? 1u : 0u, n_tiles);
 }
 
 TileShape raster_tile_shape(int variant) {
     switch (variant) {
         case 1: return TileShape{128, 64};   // canvases at most 128 px wide (larger than the fused small-canvas kernel takes)
+        case 2: return TileShape{1024, 8};   // same tile, 512 threads: FILL launches (per-pixel paint evaluation dominates)
         default: return TileShape{1024, 8};  // best of the r1 sweep over {256,512,1024} x {4,8,16} (profiles/r1_tile_sweep.txt)
     }
 }
@@ -378,11 +394,21 @@ void launch_raster(int variant, const JobDev* jobs, const JobDev* h_jobs, uint32
                    uint32_t n_tiles, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
                    unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, bool pdl, cudaStream_t s) {
     if (n_tiles == 0) return;
-#define RGPU_LAUNCH(CW, TH, THREADS)                                                                                              \
-    launch_raster_t<CW, TH, THREADS>(jobs, h_jobs, n_jobs, job_first, tile_first, n_tiles, paints, tile_offs, bin_cap, bin_lines, tile_state, \
-                                     epoch, ticket, status, zero_early, pdl, s)
+    // launches without a FILL job run the instantiation that carries no paint / composite code (fewer registers)
+    bool fill = false;
+    for (uint32_t j = 0; j < n_jobs && !fill; j++) fill = h_jobs[job_first + j].mode == kModeFill;
+#define RGPU_LAUNCH(CW, TH, THREADS)                                                                                                  \
+    do {                                                                                                                              \
+        if (fill)                                                                                                                     \
+            launch_raster_t<CW, TH, THREADS, true>(jobs, h_jobs, n_jobs, job_first, tile_first, n_tiles, paints, tile_offs, bin_cap, bin_lines, \
+                                                   tile_state, epoch, ticket, status, zero_early, pdl, s);                            \
+        else                                                                                                                          \
+            launch_raster_t<CW, TH, THREADS, false>(jobs, h_jobs, n_jobs, job_first, tile_first, n_tiles, paints, tile_offs, bin_cap, bin_lines, \
+                                                    tile_state, epoch, ticket, status, zero_early, pdl, s);                           \
+    } while (0)
     switch (variant) {
         case 1: RGPU_LAUNCH(128, 64, 256); break;
+        case 2: RGPU_LAUNCH(1024, 8, 512); break;
         default: RGPU_LAUNCH(1024, 8, 128); break;
     }
 #undef RGPU_LAUNCH
