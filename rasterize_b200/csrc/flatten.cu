@@ -17,11 +17,16 @@
 //     into the bins of the tiles it touches (flatten_bin_kernel); no global line buffer.
 #include "flatten_device.cuh"
 
+#include <cstdlib>
+
 namespace rgpu {
 
 namespace {
 
 using namespace fl;
+
+constexpr int kDeepCutDepth = 5;              // 32 slots per item for small batches (see launch_flatten_bin_fixed)
+constexpr uint32_t kDeepCutMaxItems = 8192;
 
 // Ordered two-pass form (count, [scan], emit): lines land in the reference's exact order — `Path::flatten` parity.
 template <bool EMIT>
@@ -65,7 +70,7 @@ flatten_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t total_
 // the bin store behind the next leaf; and a warp work-sharing schedule (32 lanes on a shared LIFO of pending nodes in
 // shared memory, critical path = subdivision depth) — its tail is set by runs of heavy curves landing in one warp, and
 // with batches small enough to avoid that (strided, 8 items) it ties this kernel (33 us on C2); only C5 gained (31 -> 22 us).
-template <int PASS>
+template <int PASS, int DEPTH>
 __global__ void __launch_bounds__(128)
 flatten_bin_kernel(const JobDev* __restrict__ jobs_in, uint32_t n_jobs, const __grid_constant__ JobDev one_job, uint32_t total_items, double thr,
                    uint32_t* __restrict__ tile_counts, const uint32_t* __restrict__ tile_offs, uint32_t total_tiles,
@@ -89,10 +94,10 @@ flatten_bin_kernel(const JobDev* __restrict__ jobs_in, uint32_t n_jobs, const __
         }
     }
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t total_slots = total_items * kSlotsPerItem;
+    const uint32_t total_slots = total_items << DEPTH;
     SlotCtx c;
     uint32_t count = 0, n_refs = 0;
-    if (t < total_slots && slot_setup(jobs, n_jobs, t, thr, c, status)) {
+    if (t < total_slots && slot_setup<DEPTH>(jobs, n_jobs, t, thr, c, status)) {
         const JobDev& job = jobs[c.job];
         auto emit = [&](double x0, double y0, double x1, double y1) {
             for_each_tile(job, x0, y0, x1, y1, band_shift, chunk_shift, [&](uint32_t key) {
@@ -149,7 +154,7 @@ void launch_flatten_bin_count(const JobDev* jobs, uint32_t n_jobs, uint32_t tota
                               int band_rows, int chunk_cols, Status* status, cudaStream_t s) {
     uint32_t n = total_items * kSlotsPerItem;
     if (n == 0) return;
-    flatten_bin_kernel<0><<<(n + 127) / 128, 128, 0, s>>>(jobs, n_jobs, JobDev{}, total_items, thr, tile_counts, nullptr, 0, nullptr, 0,
+    flatten_bin_kernel<0, kSlotDepth><<<(n + 127) / 128, 128, 0, s>>>(jobs, n_jobs, JobDev{}, total_items, thr, tile_counts, nullptr, 0, nullptr, 0,
                                                           log2i(band_rows), log2i(chunk_cols), status, nullptr);
 }
 
@@ -158,17 +163,29 @@ void launch_flatten_bin_emit(const JobDev* jobs, uint32_t n_jobs, uint32_t total
                              int chunk_cols, Status* status, cudaStream_t s) {
     uint32_t n = total_items * kSlotsPerItem;
     if (n == 0) return;
-    flatten_bin_kernel<1><<<(n + 127) / 128, 128, 0, s>>>(jobs, n_jobs, JobDev{}, total_items, thr, tile_cursor, tile_offs, total_tiles,
+    flatten_bin_kernel<1, kSlotDepth><<<(n + 127) / 128, 128, 0, s>>>(jobs, n_jobs, JobDev{}, total_items, thr, tile_cursor, tile_offs, total_tiles,
                                                           bin_lines, refs_cap, log2i(band_rows), log2i(chunk_cols), status, nullptr);
 }
 
 void launch_flatten_bin_fixed(const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t total_items, double thr,
                               uint32_t* tile_counts, double4* bin_lines, uint32_t bin_cap, int band_rows, int chunk_cols, Status* status,
                               Status* next_status, cudaStream_t s) {
-    uint32_t n = total_items * kSlotsPerItem;
-    if (n == 0) return;
-    flatten_bin_kernel<2><<<(n + 127) / 128, 128, 0, s>>>(n_jobs == 1 ? nullptr : jobs, n_jobs, h_jobs[0], total_items, thr, tile_counts, nullptr,
-                                                          0, bin_lines, bin_cap, log2i(band_rows), log2i(chunk_cols), status, next_status);
+    if (total_items == 0) return;
+    // Few items (a scene's fills, one stroked outline): cut every subdivision tree two levels deeper, 32 slots per item —
+    // four times the threads, each with a quarter of the subtree, because such batches are bound by the longest
+    // depth-first walk, not by throughput.
+    static const uint32_t deep_max = getenv("RGPU_DEEP_CUT_ITEMS") ? (uint32_t)atoll(getenv("RGPU_DEEP_CUT_ITEMS")) : kDeepCutMaxItems;  // tuning knob
+    if (total_items <= deep_max) {
+        const uint32_t n = total_items << kDeepCutDepth;
+        flatten_bin_kernel<2, kDeepCutDepth><<<(n + 127) / 128, 128, 0, s>>>(n_jobs == 1 ? nullptr : jobs, n_jobs, h_jobs[0], total_items, thr,
+                                                                             tile_counts, nullptr, 0, bin_lines, bin_cap, log2i(band_rows),
+                                                                             log2i(chunk_cols), status, next_status);
+    } else {
+        const uint32_t n = total_items << kSlotDepth;
+        flatten_bin_kernel<2, kSlotDepth><<<(n + 127) / 128, 128, 0, s>>>(n_jobs == 1 ? nullptr : jobs, n_jobs, h_jobs[0], total_items, thr,
+                                                                          tile_counts, nullptr, 0, bin_lines, bin_cap, log2i(band_rows),
+                                                                          log2i(chunk_cols), status, next_status);
+    }
 }
 
 }  // namespace rgpu

@@ -107,11 +107,12 @@ struct SlotCtx {
     bool leaf_above;  // the subtree root is itself a leaf (the curve was flat above the depth-3 cut)
 };
 
-// Returns false when the slot produces no line.
+// Returns false when the slot produces no line.  DEPTH = level at which the subdivision tree is cut into slots.
+template <int DEPTH = kSlotDepth>
 __device__ __forceinline__ bool slot_setup(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t t, double thr, SlotCtx& c,
                                            Status* __restrict__ status) {
-    const uint32_t g = t >> kSlotDepth;
-    const uint32_t slot = t & (kSlotsPerItem - 1);
+    const uint32_t g = t >> DEPTH;
+    const uint32_t slot = t & ((1u << DEPTH) - 1u);
     const uint32_t j = find_job(n_jobs, g, [&](uint32_t k) { return jobs[k].item_begin; });
     const JobDev& job = jobs[j];
     const uint2 item = job.items[g - job.item_begin];
@@ -135,21 +136,21 @@ __device__ __forceinline__ bool slot_setup(const JobDev* __restrict__ jobs, uint
     }
     // descend to this slot's subtree root (bits of `slot`, most significant first)
 #pragma unroll 1
-    for (int level = 0; level < kSlotDepth; level++) {
+    for (int level = 0; level < DEPTH; level++) {
         if (seg_has_nan(c.seg, c.kind)) {
             atomicExch(&status->nan_flag, 1u);
             return false;
         }
         if (seg_flatness(c.seg, c.kind) < thr) {
             // a leaf above the cut: owned by the slot whose remaining bits are all zero
-            const uint32_t rest = slot & ((1u << (kSlotDepth - level)) - 1u);
+            const uint32_t rest = slot & ((1u << (DEPTH - level)) - 1u);
             if (rest != 0) return false;
             c.leaf_above = true;
             return true;
         }
         Seg s0, s1;
         seg_split(c.seg, c.kind, s0, s1);
-        c.seg = ((slot >> (kSlotDepth - 1 - level)) & 1u) ? s1 : s0;
+        c.seg = ((slot >> (DEPTH - 1 - level)) & 1u) ? s1 : s0;
     }
     return true;
 }
