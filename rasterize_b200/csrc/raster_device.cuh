@@ -163,73 +163,102 @@ struct TileGeom {
 // deltas) are rounded to Q7.24 and the differences of consecutive rounded coverages are added to the cells of
 // THIS tile only; their sum (a telescoping difference) goes to the row's tile total, from which the tiles to the
 // right derive their carry-in.  Parts of the span in other tiles are added by those tiles (2-D bins).
+// The body comes in three parts so that a warp can run the two shapes of span separately (no divergence between the
+// two-cell common case and the per-pixel loop of wide spans): span_head, span_narrow, span_wide.
+struct SpanHead {
+    double x, xn;            // x at the top / bottom of the row's piece of the line
+    double x0, x1;           // min / max of the two
+    int x0i, x1i;            // first / last affected column (clamped like the reference)
+    int r;                   // row inside the band
+    int fd;                  // Q7.24 of d
+    float d;                 // signed y extent in this row
+    bool live;               // touches this tile
+    bool narrow;             // at most two cells (src/rasterize.rs:437-444)
+};
+
+__device__ __forceinline__ SpanHead span_head(double ax, double ay, double by, double dxdy, float dirf, int y, const TileGeom& g) {
+    SpanHead h;
+    const double yt = fmax((double)y, ay);
+    const double dy = fmin((double)(y + 1), by) - yt;
+    h.x = ax + (yt - ay) * dxdy;  // the reference accumulates x row by row; this differs by rounding only
+    h.xn = h.x + dxdy * dy;
+    h.x0 = fmin(h.x, h.xn);
+    h.x1 = fmax(h.x, h.xn);
+    // x0.floor().max(0.0) / x1.ceil().min(width), src/rasterize.rs:431-436, through the integer conversions
+    h.x0i = min(max(__double2int_rd(h.x0), 0), g.wci);
+    h.x1i = min(max(__double2int_ru(h.x1), 0), g.wci);
+    h.r = y - g.row0;
+    h.d = dirf * (float)dy;
+    h.fd = to_fixed_f(h.d);
+    h.narrow = h.x1i <= h.x0i + 1;
+    const int last = h.narrow ? h.x0i + 1 : h.x1i;  // last column that receives a delta
+    // right of the tile: nothing here; left of it: the span arrives through the look-back
+    h.live = h.x0i < g.tile_end && last >= g.cx0;
+    return h;
+}
+
+// The common case (a span inside one pixel column): two cells, x0i and x0i + 1, with rounded coverages
+// ca = F(d * (1 - xmf)) and fd.
+template <bool SWZ>
+__device__ __forceinline__ void span_narrow(const SpanHead& h, const TileGeom& g, int* __restrict__ cells, int* __restrict__ rowtot,
+                                            int* __restrict__ row_touched) {
+    int* rowp = cells + h.r * g.pitch;
+    const float c0 = 1.0f - (float)(0.5 * (h.x + h.xn) - (double)h.x0i);  // 1 - xmf
+    const int ca = to_fixed_f(h.d * c0);
+    int tot = 0;
+    if (h.x0i >= g.cx0) {  // x0i < tile_end holds (live)
+        atomicAdd(&rowp[swz<SWZ>(h.x0i - g.cx0)], ca);
+        tot = ca;
+    }
+    if (h.x0i + 1 < g.tile_end) {  // x0i + 1 >= cx0 holds (live)
+        const int cb = h.fd - ca;
+        atomicAdd(&rowp[swz<SWZ>(h.x0i + 1 - g.cx0)], cb);
+        tot += cb;
+    }
+    atomicAdd(&rowtot[h.r], tot);
+    row_touched[h.r] = 1;
+}
+
+// Spans over three or more columns (src/rasterize.rs:445-468).  Positions stay f64 (f32 ulp at x ~ 4096 would already
+// exceed the 1e-4 budget); the fractional parts are in [0,1] and the area polynomials are evaluated in f32 (error
+// ~1e-7 of a pixel).
+template <bool SWZ>
+__device__ __forceinline__ void span_wide(const SpanHead& h, const TileGeom& g, int* __restrict__ cells, int* __restrict__ rowtot,
+                                          int* __restrict__ row_touched) {
+    int* rowp = cells + h.r * g.pitch;
+    const int n = h.x1i - h.x0i;
+    const float sf = 1.0f / (float)(h.x1 - h.x0);
+    const float x0f = (float)(h.x0 - (double)h.x0i);
+    const float x1f = (float)(h.x1 - (double)h.x1i + 1.0);
+    const float c0 = 0.5f * sf * (1.0f - x0f) * (1.0f - x0f);
+    const float cl = 1.0f - 0.5f * sf * x1f * x1f;  // 1 - am: coverage of the last-but-one column
+    const float a1 = sf * (1.5f - x0f);
+    // coverage (as a fraction of d) of pixel x0i + j == running sum of the reference's deltas, for 0 <= j < n
+    auto cov = [&](int j) -> float {
+        float t = a1 + (float)(j - 1) * sf;
+        t = (j == 0) ? c0 : t;
+        return (j == n - 1) ? cl : t;
+    };
+    const int kb = max(h.x0i, g.cx0);
+    const int ke = min(h.x1i, g.tile_end - 1);
+    const int first = (kb > h.x0i) ? to_fixed_f(h.d * cov(kb - 1 - h.x0i)) : 0;  // rounded coverage just left of the tile
+    int prev = first;
+    for (int k = kb; k <= ke; k++) {
+        const int cur = (k == h.x1i) ? h.fd : to_fixed_f(h.d * cov(k - h.x0i));
+        atomicAdd(&rowp[swz<SWZ>(k - g.cx0)], cur - prev);
+        prev = cur;
+    }
+    atomicAdd(&rowtot[h.r], prev - first);
+    row_touched[h.r] = 1;
+}
+
 template <bool SWZ>
 __device__ __forceinline__ void span_row(double ax, double ay, double by, double dxdy, float dirf, int y, const TileGeom& g,
                                          int* __restrict__ cells, int* __restrict__ rowtot, int* __restrict__ row_touched) {
-    const double yt = fmax((double)y, ay);
-    const double dy = fmin((double)(y + 1), by) - yt;
-    const double x = ax + (yt - ay) * dxdy;  // the reference accumulates x row by row; this differs by rounding only
-    const double xn = x + dxdy * dy;
-    const double x0 = fmin(x, xn), x1 = fmax(x, xn);
-    const double x0_floor = fmax(floor(x0), 0.0);
-    const double x1_ceil = fmin(ceil(x1), g.wc);
-    const int x0i = min(max((int)x0_floor, 0), g.wci);
-    const int x1i = min(max((int)x1_ceil, 0), g.wci);
-    if (x0i >= g.tile_end) return;  // this row's span is right of the tile
-    const int r = y - g.row0;
-    const float d = dirf * (float)dy;
-    const int fd = to_fixed_f(d);
-    const bool narrow = x1i <= x0i + 1;
-    const int last = narrow ? x0i + 1 : x1i;  // last column that receives a delta
-    if (last < g.cx0) return;                 // this row's span is left of the tile: it arrives through the look-back
-    int* rowp = cells + r * g.pitch;
-    if (narrow) {
-        // The common case (a span inside one pixel column, src/rasterize.rs:437-444): two cells, x0i and x0i + 1,
-        // with rounded coverages ca = F(d * (1 - xmf)) and fd.
-        const float c0 = 1.0f - (float)(0.5 * (x + xn) - x0_floor);  // 1 - xmf
-        const int ca = to_fixed_f(d * c0);
-        int tot = 0;
-        if (x0i >= g.cx0) {  // x0i < tile_end was checked above
-            if (ca != 0) atomicAdd(&rowp[swz<SWZ>(x0i - g.cx0)], ca);
-            tot = ca;
-        }
-        if (x0i + 1 < g.tile_end) {  // x0i + 1 >= cx0 holds because last >= cx0
-            const int cb = fd - ca;
-            if (cb != 0) atomicAdd(&rowp[swz<SWZ>(x0i + 1 - g.cx0)], cb);
-            tot += cb;
-        }
-        atomicAdd(&rowtot[r], tot);
-        row_touched[r] = 1;
-        return;
-    }
-    // Positions stay f64 (f32 ulp at x ~ 4096 would already exceed the 1e-4 budget); the fractional parts are in
-    // [0,1] and the area polynomials are evaluated in f32 (error ~1e-7 of a pixel).
-    const int n = x1i - x0i;
-    const float sf = 1.0f / (float)(x1 - x0);  // src/rasterize.rs:446-450
-    const float x0f = (float)(x0 - x0_floor);
-    const float x1f = (float)(x1 - x1_ceil + 1.0);
-    const float c0 = 0.5f * sf * (1.0f - x0f) * (1.0f - x0f);
-    const float am = 0.5f * sf * x1f * x1f;
-    const float a1 = sf * (1.5f - x0f);
-    // coverage (as a fraction of d) of pixel x0i + j == running sum of the reference's deltas
-    auto cov = [&](int j) -> float {
-        if (j <= 0) return j == 0 ? c0 : 0.0f;
-        if (j >= n) return 1.0f;
-        if (j == n - 1) return 1.0f - am;
-        return a1 + (float)(j - 1) * sf;
-    };
-    const int kb = max(x0i, g.cx0);
-    const int ke = min(last, g.tile_end - 1);
-    const int first = (kb > x0i) ? to_fixed_f(d * cov(kb - 1 - x0i)) : 0;  // rounded coverage just left of the tile
-    int prev = first;
-    for (int k = kb; k <= ke; k++) {
-        const int cur = (k == last) ? fd : to_fixed_f(d * cov(k - x0i));
-        const int diff = cur - prev;
-        if (diff != 0) atomicAdd(&rowp[swz<SWZ>(k - g.cx0)], diff);
-        prev = cur;
-    }
-    atomicAdd(&rowtot[r], prev - first);
-    row_touched[r] = 1;
+    const SpanHead h = span_head(ax, ay, by, dxdy, dirf, y, g);
+    if (!h.live) return;
+    if (h.narrow) span_narrow<SWZ>(h, g, cells, rowtot, row_touched);
+    else span_wide<SWZ>(h, g, cells, rowtot, row_touched);
 }
 
 // Oriented piece ready for span_row, or nothing.  Returns the band rows [rb, re) it touches.
@@ -388,12 +417,39 @@ __device__ __forceinline__ void warp_accumulate_round(const double4 l, bool vali
     const unsigned nofit = __ballot_sync(0xffffffffu, n > 0 && base + n > CAP);
     const int ns = nofit ? __shfl_sync(0xffffffffu, base, __ffs(nofit) - 1) : total;
     const int wbase = tid & ~31;
-    for (int i = lane; i < ns; i += 32) {
+    // pass 1: every span's head; two-cell spans finish here, wide ones are compacted back into the front of the list
+    // (entries below the read position are already consumed)
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int n_wide = 0;
+    for (int i0 = 0; i0 < ns; i0 += 32) {
+        const int i = i0 + lane;
+        int e = 0;
+        bool wide = false;
+        if (i < ns) {
+            e = spans[i];
+            const int src = e >> ROWBITS;
+            const int slot = wbase + src;
+            const int y = g.row0 + (e & ((1 << ROWBITS) - 1));
+            const SpanHead h = span_head(p_ax[slot], p_ay[slot], p_by[slot], p_dxdy[slot], ((neg >> src) & 1u) ? -1.0f : 1.0f, y, g);
+            if (h.live) {
+                if (h.narrow) span_narrow<SWZ>(h, g, cells, rowtot, row_touched);
+                else wide = true;
+            }
+        }
+        const unsigned wm = __ballot_sync(0xffffffffu, wide);
+        __syncwarp();  // this round's entries are read before any is overwritten
+        if (wide) spans[n_wide + __popc(wm & lt_mask)] = (SpanT)e;
+        n_wide += __popc(wm);
+    }
+    __syncwarp();
+    // pass 2: the wide spans, one lane each
+    for (int i = lane; i < n_wide; i += 32) {
         const int e = spans[i];
         const int src = e >> ROWBITS;
         const int slot = wbase + src;
         const int y = g.row0 + (e & ((1 << ROWBITS) - 1));
-        span_row<SWZ>(p_ax[slot], p_ay[slot], p_by[slot], p_dxdy[slot], ((neg >> src) & 1u) ? -1.0f : 1.0f, y, g, cells, rowtot, row_touched);
+        const SpanHead h = span_head(p_ax[slot], p_ay[slot], p_by[slot], p_dxdy[slot], ((neg >> src) & 1u) ? -1.0f : 1.0f, y, g);
+        span_wide<SWZ>(h, g, cells, rowtot, row_touched);
     }
     __syncwarp();
 }
