@@ -25,7 +25,7 @@ constexpr int kSmLineCap = 768;     // lines kept in shared memory per window (2
 constexpr int kSmRowBits = 6;
 constexpr int kSmSpanCap = 256;     // per-warp span list (lanes that do not fit do their rows serially)
 
-__global__ void __launch_bounds__(kSmThreads, 3)
+__global__ void __launch_bounds__(kSmThreads, 4)
 small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const PaintDev* __restrict__ paints, double thr,
                     Status* __restrict__ status) {
     // dynamic shared memory (> 48 KB): line window | cells (plain row-major) | piece constants | per-warp span lists
