@@ -378,7 +378,7 @@ def run_ours(args):
             out["e2e"] = e2e
         if cpu_baseline is not None:
             out["cpu_baseline"] = cpu_baseline
-        print(json.dumps(out))
+        _emit(json.dumps(out))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -417,7 +417,7 @@ def run_reference(args):
     if rank != 0:
         return
     if args.workload != "c2":
-        print(json.dumps({"impl": "reference", "unavailable": "reference arm is implemented for the c2 workload"}))
+        _emit(json.dumps({"impl": "reference", "unavailable": "reference arm is implemented for the c2 workload"}))
         return
     threads = os.cpu_count() or 1
     import oracle as O
@@ -452,10 +452,22 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    _emit(json.dumps(out))
+
+
+def _emit(line: str) -> None:
+    """The ONE JSON line goes to the real stdout; everything libraries print (NCCL banners ...) was sent to stderr."""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # stray prints of native libraries (e.g. "NCCL version ...") must not pollute the result line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

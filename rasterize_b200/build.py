@@ -38,9 +38,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     objdir = PKG / "build"
     objdir.mkdir(exist_ok=True)
     procs = []
+    extra = os.environ.get("RGPU_NVCC_EXTRA", "").split()  # tuning builds, e.g. -DRGPU_FLAT_MINB=9
     for src in SOURCES:
         obj = objdir / (src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(obj)]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

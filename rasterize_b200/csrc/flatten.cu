@@ -19,6 +19,10 @@
 
 #include <cstdlib>
 
+#ifndef RGPU_FLAT_MINB
+#define RGPU_FLAT_MINB 10  // 48 registers: the whole grid of a 4096^2 path is resident in one wave (sweep: 1 / 9 / 10 -> 38.9 / 31.7 / 30.9 us)
+#endif
+
 namespace rgpu {
 
 namespace {
@@ -71,7 +75,7 @@ flatten_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t total_
 // shared memory, critical path = subdivision depth) — its tail is set by runs of heavy curves landing in one warp, and
 // with batches small enough to avoid that (strided, 8 items) it ties this kernel (33 us on C2); only C5 gained (31 -> 22 us).
 template <int PASS, int DEPTH>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, RGPU_FLAT_MINB)
 flatten_bin_kernel(const JobDev* __restrict__ jobs_in, uint32_t n_jobs, const __grid_constant__ JobDev one_job, uint32_t total_items, double thr,
                    uint32_t* __restrict__ tile_counts, const uint32_t* __restrict__ tile_offs, uint32_t total_tiles,
                    double4* __restrict__ bin_lines, uint32_t refs_cap, int band_shift, int chunk_shift, Status* __restrict__ status,
