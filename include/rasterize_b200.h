@@ -153,6 +153,9 @@ int rgpu_render_batch_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, u
 /* Lines produced by the flatten stage of the last completed batch, and kernels launched since create. */
 int rgpu_last_counts(rgpu_ctx* ctx, uint64_t* n_lines, uint64_t* n_line_refs, uint64_t* n_launches);
 
+/* Bytes the last rgpu_mask / rgpu_mask_f32 call moved over PCIe (path upload; image download: f32 rows + f64 rows). */
+int rgpu_last_transfer_bytes(rgpu_ctx* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+
 /* Optional per-stage device timing of batches (CUDA events on the context's stream around the flatten, bin and
  * raster stages).  rgpu_last_stage_ms is valid after rgpu_batch_status / *_sync: out = {flatten, bin, raster} ms. */
 int rgpu_set_profiling(rgpu_ctx* ctx, int enable);

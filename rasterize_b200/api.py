@@ -540,6 +540,12 @@ class GpuRasterizer:
         ffi.lib().rgpu_last_counts(self.ctx, C.byref(a), C.byref(b), C.byref(c))
         return dict(lines=a.value, line_refs=b.value, launches=c.value)
 
+    def last_transfer_bytes(self):
+        """(h2d, d2h) bytes the last `mask` call moved over PCIe."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(ffi.lib().rgpu_last_transfer_bytes(self.ctx, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def set_profiling(self, on: bool) -> None:
         self._check(ffi.lib().rgpu_set_profiling(self.ctx, int(on)))
 

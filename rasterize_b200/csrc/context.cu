@@ -94,6 +94,7 @@ struct rgpu_ctx {
     size_t h_paints_cap = 0;
     // stats
     uint64_t n_launches = 0, last_lines = 0, last_refs = 0;
+    uint64_t last_h2d_bytes = 0, last_d2h_bytes = 0;  // PCIe traffic of the last host-buffer call
     // last submission (for status / retry)
     uint64_t need_lines = 0, need_refs = 0;
     uint32_t last_total_slots = 0;
@@ -101,6 +102,7 @@ struct rgpu_ctx {
     // host-side result pipeline (chunked D2H overlapped with threaded widening into the caller's image)
     std::unique_ptr<rgpu::HostPool> pool;
     std::vector<cudaEvent_t> chunk_ev;
+    double widen_dev_frac = 0.2;  // share of the rows of an f64 result widened on the device (adapts, see download_widen)
     // optional stage timing
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -245,6 +247,8 @@ int stage_path(rgpu_ctx* ctx, const rgpu_path* path, rgpu_dpath* dp) {
     dp->items = static_cast<uint2*>(ctx->tmp_items.p);
     if (dp->n_points) CK(ctx, cudaMemcpyAsync(dp->pts, path->points, sizeof(double2) * dp->n_points, cudaMemcpyHostToDevice, ctx->stream));
     if (dp->n_items) CK(ctx, cudaMemcpyAsync(dp->items, ctx->h_items, sizeof(uint2) * dp->n_items, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->last_h2d_bytes = sizeof(double2) * dp->n_points + sizeof(uint2) * dp->n_items;
+    ctx->last_d2h_bytes = 0;
     return RGPU_OK;
 }
 
@@ -805,6 +809,13 @@ int rgpu_last_counts(rgpu_ctx* ctx, uint64_t* n_lines, uint64_t* n_line_refs, ui
     return RGPU_OK;
 }
 
+int rgpu_last_transfer_bytes(rgpu_ctx* ctx, uint64_t* h2d, uint64_t* d2h) {
+    if (!ctx) return RGPU_ERR_INVALID;
+    if (h2d) *h2d = ctx->last_h2d_bytes;
+    if (d2h) *d2h = ctx->last_d2h_bytes;
+    return RGPU_OK;
+}
+
 int rgpu_set_profiling(rgpu_ctx* ctx, int enable) {
     if (!ctx) return RGPU_ERR_INVALID;
     CK(ctx, cudaSetDevice(ctx->device));
@@ -957,6 +968,7 @@ int rgpu_mask_f32(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int 
     if (rc) return rc;
     CK(ctx, cudaMemcpyAsync(img, d, sizeof(float) * width * height, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->last_d2h_bytes = sizeof(float) * width * height;
     return RGPU_OK;
 }
 
@@ -989,9 +1001,14 @@ static inline void widen_row(const float* __restrict__ src, double* __restrict__
 #endif
 }
 
-// f32 device image -> strided f64 host image: the D2H copy is cut into row chunks; as soon as a chunk has landed in
-// pinned staging the pool widens it into the caller's image while the next chunks are still crossing PCIe.  The
-// caller's memory may be pageable (it is only written by host threads).
+// f32 device image -> strided f64 host image.  Two producers fill the caller's image at once:
+//   * the BOTTOM rows cross PCIe as f32 in row chunks; as soon as a chunk has landed in pinned staging the pool widens
+//     it into the caller's image while the next chunks are still in flight (the caller's memory may be pageable: only
+//     host threads write it);
+//   * when the caller's image is pinned and dense along x, the TOP rows are widened on the device and DMA'd straight
+//     into place as f64 behind the f32 chunks, so the copy engine keeps working while the host threads catch up.
+// The split adapts from call to call to whichever side finished last (host widening bandwidth differs a lot between
+// hosts: 134 MB of f64 stores per 4096^2 mask).
 static int download_widen(rgpu_ctx* ctx, const float* d_img, size_t w, size_t h, double* dst, rgpu_shape shape) {
     int rc;
     if ((rc = ensure_stage(ctx, sizeof(float) * w * h))) return rc;
@@ -999,23 +1016,44 @@ static int download_widen(rgpu_ctx* ctx, const float* d_img, size_t w, size_t h,
         unsigned n = std::thread::hardware_concurrency();
         ctx->pool.reset(new rgpu::HostPool(std::max(1u, std::min(n ? n : 4u, 32u))));
     }
+    // rows [0, h_dev) go the device-widened way
+    size_t h_dev = 0;
+    if (shape.col_stride == 1 && h >= 64) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, dst) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+            h_dev = std::min(h - 1, (size_t)((double)h * ctx->widen_dev_frac));
+        } else {
+            cudaGetLastError();  // pageable memory reports an error on older runtimes
+        }
+    }
+    if (h_dev) {
+        if ((rc = ensure_dev(ctx, ctx->img_f64, sizeof(double) * w * h_dev))) return rc;
+        launch_f32_to_f64(d_img, static_cast<double*>(ctx->img_f64.p), w * h_dev, ctx->stream);
+        ctx->n_launches++;
+    }
     float* stage = static_cast<float*>(ctx->h_stage);
     const size_t target_rows = std::max<size_t>(1, (size_t)(4u << 20) / (w * sizeof(float)));  // ~4 MB per chunk
-    const size_t n_chunks = (h + target_rows - 1) / target_rows;
-    while (ctx->chunk_ev.size() < n_chunks) {
+    const size_t n_chunks = (h - h_dev + target_rows - 1) / target_rows;
+    while (ctx->chunk_ev.size() < n_chunks + 1) {
         cudaEvent_t e;
         CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->chunk_ev.push_back(e);
     }
     for (size_t c = 0; c < n_chunks; c++) {
-        const size_t r0 = c * target_rows, r1 = std::min(h, r0 + target_rows);
+        const size_t r0 = h_dev + c * target_rows, r1 = std::min(h, r0 + target_rows);
         CK(ctx, cudaMemcpyAsync(stage + r0 * w, d_img + r0 * w, sizeof(float) * w * (r1 - r0), cudaMemcpyDeviceToHost, ctx->stream));
         CK(ctx, cudaEventRecord(ctx->chunk_ev[c], ctx->stream));
     }
+    if (h_dev) {
+        CK(ctx, cudaMemcpy2DAsync(dst, shape.row_stride * sizeof(double), ctx->img_f64.p, w * sizeof(double), w * sizeof(double), h_dev,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaEventRecord(ctx->chunk_ev[n_chunks], ctx->stream));
+    }
+    ctx->last_d2h_bytes = sizeof(float) * w * (h - h_dev) + sizeof(double) * w * h_dev;
     const unsigned workers = ctx->pool->size();
     const size_t rs = shape.row_stride, cs = shape.col_stride;
     for (size_t c = 0; c < n_chunks; c++) {
-        const size_t r0 = c * target_rows, r1 = std::min(h, r0 + target_rows);
+        const size_t r0 = h_dev + c * target_rows, r1 = std::min(h, r0 + target_rows);
         CK(ctx, cudaEventSynchronize(ctx->chunk_ev[c]));
         const size_t rows = r1 - r0;
         const size_t parts = std::min<size_t>(workers, rows);
@@ -1037,7 +1075,17 @@ static int download_widen(rgpu_ctx* ctx, const float* d_img, size_t w, size_t h,
             });
         }
     }
-    ctx->pool->wait();
+    if (h_dev) {
+        // which producer is late?  (the f64 DMA is queued behind the f32 chunks)
+        const bool dma_done_first = cudaEventQuery(ctx->chunk_ev[n_chunks]) == cudaSuccess;
+        ctx->pool->wait();
+        const bool host_done_first = cudaEventQuery(ctx->chunk_ev[n_chunks]) != cudaSuccess;
+        CK(ctx, cudaEventSynchronize(ctx->chunk_ev[n_chunks]));
+        if (dma_done_first) ctx->widen_dev_frac = std::min(0.6, ctx->widen_dev_frac + 0.03);       // host threads are the bottleneck
+        else if (host_done_first) ctx->widen_dev_frac = std::max(0.0, ctx->widen_dev_frac - 0.03);  // PCIe is
+    } else {
+        ctx->pool->wait();
+    }
     return RGPU_OK;
 }
 

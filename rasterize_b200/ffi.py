@@ -58,7 +58,7 @@ _lib = None
 SYMBOLS = [
     "rgpu_create", "rgpu_destroy", "rgpu_name", "rgpu_last_error", "rgpu_device_count", "rgpu_flatten", "rgpu_mask",
     "rgpu_mask_f32", "rgpu_mask_iter", "rgpu_coverage_f32", "rgpu_fill", "rgpu_path_upload", "rgpu_path_free",
-    "rgpu_render_batch", "rgpu_batch_status", "rgpu_render_batch_sync", "rgpu_last_counts", "rgpu_set_profiling",
+    "rgpu_render_batch", "rgpu_batch_status", "rgpu_render_batch_sync", "rgpu_last_counts", "rgpu_last_transfer_bytes", "rgpu_set_profiling",
     "rgpu_last_stage_ms", "rgpu_to_rgba8_dev", "rgpu_layer_scale_by_mask_dev", "rgpu_layer_blend_over_dev", "rgpu_download_rgba8",
     "rgpu_fill_color_dev", "rgpu_stream", "rgpu_sync", "rgpu_device_alloc", "rgpu_device_free", "rgpu_device_zero",
     "rgpu_memcpy_h2d", "rgpu_memcpy_d2h", "rgpu_host_alloc", "rgpu_host_free",
@@ -99,6 +99,7 @@ def lib():
     sig("rgpu_batch_status", i32, vp)
     sig("rgpu_render_batch_sync", i32, vp, C.POINTER(CJob), sz, u32)
     sig("rgpu_last_counts", i32, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
+    sig("rgpu_last_transfer_bytes", i32, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
     sig("rgpu_set_profiling", i32, vp, i32)
     sig("rgpu_last_stage_ms", i32, vp, pf)
     sig("rgpu_to_rgba8_dev", i32, vp, vp, vp, sz)

@@ -209,3 +209,23 @@ def test_c2_material_4096(rast):
         op.mask_threads(tr, int(rule), ref, threads=8)
         assert np.abs(img - ref).max() <= COV_TOL
     assert rast.last_counts()["lines"] == c2["lines"]
+
+
+def test_mask_pinned_f64_matches_pageable(rast):
+    """rgpu_mask into a PINNED f64 image takes the split path (top rows widened on the device and DMA'd as f64, bottom
+    rows widened by host threads): same pixels as the pageable path, for dense rows and for a row-strided view, over
+    several calls (the split moves from call to call)."""
+    p = assets.load_path("rust")
+    tr = np.array(assets.expected()["paths"]["rust"]["size_tr"]) * 3.0
+    w, h = 700, 900
+    ref = np.zeros((h, w))
+    rast.mask(p, tr, ref, rb.FillRule.NonZero)  # pageable: host widening only
+    pinned = rast.host_alloc((h, w + 16), np.float64)
+    for _ in range(6):
+        pinned[:] = -1.0
+        rast.mask(p, tr, pinned[:, :w], rb.FillRule.NonZero)
+        assert np.array_equal(pinned[:, :w], ref)
+        assert (pinned[:, w:] == -1.0).all()
+    oref = np.zeros((h, w))
+    opath(p).mask(tr, O.NONZERO, oref)
+    assert np.abs(ref - oref).max() <= COV_TOL
