@@ -286,38 +286,47 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
 
     // ---- carry-in: decoupled look-back over the tiles to the left in this band --------------------------------
     // Every tile publishes its per-row totals (flag AGG), sums its predecessors' totals until it meets an
-    // inclusive prefix, then publishes its own inclusive prefix.  A warp handles a row at a time and looks at up to
-    // 32 predecessors at once.  Words carry the batch epoch, so the state needs no clearing between batches.
+    // inclusive prefix, then publishes its own inclusive prefix.  All rows look back at once, each with a window of
+    // predecessors.  Words carry the batch epoch, so the state needs no clearing between batches.
     // Single-chunk jobs have no neighbours and skip all of this.
     if (job.n_chunks > 1) {
+        // every row of the tile looks back at once: a group of LPR lanes per row, lane k of the group on predecessor k
+        constexpr int LPR = (THREADS / TH >= 32) ? 32 : (THREADS / TH);  // 16 for the 1024 x 8 tile with 128 threads
+        static_assert(LPR >= 1 && (LPR & (LPR - 1)) == 0, "lanes per row must be a power of two");
         const unsigned long long ep = (unsigned long long)epoch << 34;
-        for (int r = warp; r < TH && r < kStateRows; r += Cfg::kWarps) {
+        const int r = tid / LPR, gl = tid % LPR;
+        if (r < TH && r < kStateRows) {  // uniform per warp: a warp holds 32 / LPR whole rows
             const int agg = rowtot[r];
             unsigned long long* st = tile_state + (size_t)tile * kStateRows + r;
             if (chunk == 0) {
-                if (lane == 0) st_state(st, ep | kFlagPrefix | (unsigned long long)(uint32_t)agg);
-                continue;
-            }
-            if (lane == 0) st_state(st, ep | kFlagAgg | (unsigned long long)(uint32_t)agg);
-            int sum = 0;
-            for (int k0 = 1; k0 <= chunk; k0 += 32) {
-                const int k = k0 + lane;
-                unsigned long long v = 0;
-                if (k <= chunk) {
-                    const unsigned long long* ps = tile_state + (size_t)(tile - (uint32_t)k) * kStateRows + r;
-                    do { v = ld_state(ps); } while ((uint32_t)(v >> 34) != epoch);
-                }
-                const unsigned pm = __ballot_sync(0xffffffffu, k <= chunk && (v & (3ull << 32)) == kFlagPrefix);
-                const int first = pm ? __ffs(pm) - 1 : 31;  // nearest predecessor that already holds an inclusive prefix
-                int contrib = (k <= chunk && lane <= first) ? (int)(uint32_t)v : 0;
+                if (gl == 0) st_state(st, ep | kFlagPrefix | (unsigned long long)(uint32_t)agg);
+            } else {
+                if (gl == 0) st_state(st, ep | kFlagAgg | (unsigned long long)(uint32_t)agg);
+                const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((lane / LPR) * LPR));
+                int sum = 0;
+                bool done = false;
+                for (int k0 = 1; k0 <= chunk; k0 += LPR) {  // same trip count for every row of the tile
+                    const int k = k0 + gl;
+                    const bool look = !done && k <= chunk;
+                    unsigned long long v = 0;
+                    if (look) {
+                        const unsigned long long* ps = tile_state + (size_t)(tile - (uint32_t)k) * kStateRows + r;
+                        do { v = ld_state(ps); } while ((uint32_t)(v >> 34) != epoch);
+                    }
+                    const unsigned pm = __ballot_sync(0xffffffffu, look && (v & (3ull << 32)) == kFlagPrefix) & gmask;
+                    // nearest predecessor of this row that already holds an inclusive prefix
+                    const int first = pm ? (__ffs(pm) - 1) % LPR : LPR - 1;
+                    int contrib = (look && gl <= first) ? (int)(uint32_t)v : 0;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-                sum += contrib;
-                if (pm) break;
-            }
-            if (lane == 0) {
-                carry[r] = sum;
-                st_state(st, ep | kFlagPrefix | (unsigned long long)(uint32_t)(sum + agg));
+                    for (int o = LPR / 2; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                    sum += contrib;
+                    done = done || pm != 0;
+                    if (__all_sync(0xffffffffu, done)) break;
+                }
+                if (gl == 0) {
+                    carry[r] = sum;
+                    st_state(st, ep | kFlagPrefix | (unsigned long long)(uint32_t)(sum + agg));
+                }
             }
         }
     }
