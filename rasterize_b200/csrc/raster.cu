@@ -248,6 +248,14 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     g.pitch = CW;
     const int row0 = g.row0, row1 = g.row1, cx0 = g.cx0;
     const int mode = job.mode;
+    // Early look-back probe: in chunk-major order the left neighbour has normally published its inclusive prefix long
+    // ago, so its state word is requested NOW and consumed after phase 1 — the round trip overlaps the bin loads and
+    // the accumulation instead of following them.
+    constexpr int LPR = (THREADS / TH >= 32) ? 32 : (THREADS / TH);  // lanes per row in the look-back (16 for 1024 x 8 / 128)
+    static_assert(LPR >= 1 && (LPR & (LPR - 1)) == 0, "lanes per row must be a power of two");
+    unsigned long long early = 0;
+    if (job.n_chunks > 1 && chunk > 0 && tid % LPR == 0 && tid / LPR < TH && tid / LPR < kStateRows)
+        early = ld_state(tile_state + (size_t)(tile - 1u) * kStateRows + tid / LPR);
 
     // ---- phase 1: accumulate the tile's lines.  The lines are split evenly over the warps, which then work
     // independently, 32 lines per round (see warp_accumulate_round: 1a one line per lane, spans compacted per warp;
@@ -291,8 +299,6 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     // Single-chunk jobs have no neighbours and skip all of this.
     if (job.n_chunks > 1) {
         // every row of the tile looks back at once: a group of LPR lanes per row, lane k of the group on predecessor k
-        constexpr int LPR = (THREADS / TH >= 32) ? 32 : (THREADS / TH);  // 16 for the 1024 x 8 tile with 128 threads
-        static_assert(LPR >= 1 && (LPR & (LPR - 1)) == 0, "lanes per row must be a power of two");
         const unsigned long long ep = (unsigned long long)epoch << 34;
         const int r = tid / LPR, gl = tid % LPR;
         if (r < TH && r < kStateRows) {  // uniform per warp: a warp holds 32 / LPR whole rows
@@ -304,8 +310,11 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
                 if (gl == 0) st_state(st, ep | kFlagAgg | (unsigned long long)(uint32_t)agg);
                 const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((lane / LPR) * LPR));
                 int sum = 0;
-                bool done = false;
-                for (int k0 = 1; k0 <= chunk; k0 += LPR) {  // same trip count for every row of the tile
+                // the early probe settles the row when it already saw this batch's inclusive prefix
+                bool done = (uint32_t)(early >> 34) == epoch && (early & (3ull << 32)) == kFlagPrefix;
+                if (done) sum = (int)(uint32_t)early;
+                done = __shfl_sync(0xffffffffu, done, (lane / LPR) * LPR);
+                for (int k0 = 1; k0 <= chunk && !__all_sync(0xffffffffu, done); k0 += LPR) {  // same trip count for every row of the tile
                     const int k = k0 + gl;
                     const bool look = !done && k <= chunk;
                     unsigned long long v = 0;
