@@ -140,22 +140,24 @@ __device__ __forceinline__ void scan_rows(const JobDev& job, const PaintDev& s_p
     __syncthreads();
     const int rows = row1 - row0;
     const float* covs = reinterpret_cast<const float*>(cells);
-    for (int p = tid; p < rows * bw; p += THREADS) {
-        const int r = p / bw, px = p - r * bw;
+    constexpr int TPR = (THREADS >= TH) ? THREADS / TH : 1;  // threads per tile row (power of two)
+    for (int r = tid / TPR; r < rows; r += (THREADS / TPR)) {
         if (!row_live[r]) continue;
-        const float alpha = covs[r * CW + swz<true>(px)];
-        if (alpha >= 1e-6f) {
-            const int y = row0 + r;
-            float4* out = reinterpret_cast<float4*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride + cx0;
-            float4 color = (job.paint_index >= 0) ? paint_at(s_paint, cx0 + px, y) : make_float4(0.f, 0.f, 0.f, 0.f);
-            // with_alpha: self * (alpha as f32), src/color.rs:347-349
-            color = make_float4(fmul(color.x, alpha), fmul(color.y, alpha), fmul(color.z, alpha), fmul(color.w, alpha));
-            // blend_over: other + self * (1 - other.alpha), src/color.rs:342-344
-            float4 dstc = out[px];
-            const float k = fsub(1.0f, color.w);
-            dstc = make_float4(fadd(color.x, fmul(dstc.x, k)), fadd(color.y, fmul(dstc.y, k)), fadd(color.z, fmul(dstc.z, k)),
-                               fadd(color.w, fmul(dstc.w, k)));
-            out[px] = dstc;
+        const int y = row0 + r;
+        float4* out = reinterpret_cast<float4*>(job.canvas) + job.origin + (unsigned long long)y * job.row_stride + cx0;
+        for (int px = tid % TPR; px < bw; px += TPR) {
+            const float alpha = covs[r * CW + swz<true>(px)];
+            if (alpha >= 1e-6f) {
+                float4 color = (job.paint_index >= 0) ? paint_at(s_paint, cx0 + px, y) : make_float4(0.f, 0.f, 0.f, 0.f);
+                // with_alpha: self * (alpha as f32), src/color.rs:347-349
+                color = make_float4(fmul(color.x, alpha), fmul(color.y, alpha), fmul(color.z, alpha), fmul(color.w, alpha));
+                // blend_over: other + self * (1 - other.alpha), src/color.rs:342-344
+                float4 dstc = out[px];
+                const float k = fsub(1.0f, color.w);
+                dstc = make_float4(fadd(color.x, fmul(dstc.x, k)), fadd(color.y, fmul(dstc.y, k)), fadd(color.z, fmul(dstc.z, k)),
+                                   fadd(color.w, fmul(dstc.w, k)));
+                out[px] = dstc;
+            }
         }
     }
 }
@@ -163,7 +165,7 @@ __device__ __forceinline__ void scan_rows(const JobDev& job, const PaintDev& s_p
 // `one_job`: the launch covers a single job whose descriptor travels in the kernel parameters (constant bank:
 // no dependent global loads before the tile can start).
 template <int CW, int TH, int THREADS, bool FILL>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : 1))
+__global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : (THREADS >= 512 ? 2 : 1)))
 raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first, const JobDev one_job,
               const PaintDev* __restrict__ paints, uint32_t* __restrict__ tile_offs, uint32_t bin_cap,
               const double4* __restrict__ bin_lines, unsigned long long* __restrict__ tile_state, uint32_t epoch,

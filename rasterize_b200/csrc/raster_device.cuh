@@ -34,6 +34,7 @@ __device__ __forceinline__ float l2s_lane(float x0) {
 // LinColor::unmultiply, src/color.rs:308-317
 __device__ __forceinline__ float4 unmultiply(float4 c) {
     if (c.w <= 1e-6f) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c.w == 1.0f) return c;  // x / 1 == x exactly: opaque colours (the usual gradient stop) skip four divisions
     return make_float4(__fdiv_rn(c.x, c.w), __fdiv_rn(c.y, c.w), __fdiv_rn(c.z, c.w), __fdiv_rn(c.w, c.w));
 }
 // LinColor::into_linear, src/color.rs:330-332 (all four lanes go through the polynomial, alpha included)
