@@ -559,7 +559,7 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     const bool pdl_ok = fixed && !prof && !no_pdl;
     const bool zero_early = est_lines + est_lines / 2 >= 2ull * tile_acc;  // most tiles will hold lines
     if (flags & RGPU_BATCH_INDEPENDENT) {
-        launch_raster(variant, d_jobs, ctx->h_jobs, n_live, 0, 0, tile_acc, d_paints, d_bo, bin_cap, d_refs, d_state, ctx->epoch, d_tickets, d_status, zero_early, /*pdl=*/pdl_ok, s);
+        launch_raster(variant, d_jobs, ctx->h_jobs, n_live, 0, 0, tile_acc, d_paints, d_bo, bin_cap, d_refs, d_state, ctx->epoch, d_tickets, d_status, zero_early, /*pdl=*/pdl_ok ? 1 : 0, s);
         ctx->n_launches += 1;
     } else {
         for (uint32_t j = 0; j < n_live; j++) {
@@ -567,7 +567,7 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
             // a FILL launch spends its time evaluating the paint per pixel: same tile, four times the threads
             launch_raster((variant == 0 && d.mode == kModeFill && d.paint_index >= 0 && ctx->h_paints[d.paint_index].kind != 0) ? 2 : variant,
                           d_jobs, ctx->h_jobs, 1, j, d.tile_begin, d.n_bands * d.n_chunks, d_paints, d_bo, bin_cap, d_refs, d_state,
-                          ctx->epoch, d_tickets + j, d_status, zero_early, /*pdl=*/pdl_ok && j == 0, s);
+                          ctx->epoch, d_tickets + j, d_status, zero_early, /*pdl=*/pdl_ok ? (j == 0 ? 1 : 2) : 0, s);
             ctx->n_launches += 1;
         }
     }

@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : (THREADS >= 512
 raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first, const JobDev one_job,
               const PaintDev* __restrict__ paints, uint32_t* __restrict__ tile_offs, uint32_t bin_cap,
               const double4* __restrict__ bin_lines, unsigned long long* __restrict__ tile_state, uint32_t epoch,
-              uint32_t* __restrict__ ticket, const Status* status, uint32_t zero_early, uint32_t n_tiles) {
+              uint32_t* __restrict__ ticket, const Status* status, uint32_t zero_early, uint32_t n_tiles, uint32_t late_wait) {
     using Cfg = TileCfg<CW, TH, THREADS>;
     using SpanT = typename Cfg::SpanT;
     static_assert(TH <= 64 && CW % 128 == 0 && Cfg::kL % 4 == 0, "tile shape");
@@ -207,7 +207,12 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     if (tid < TH) { carry[tid] = 0; rowtot[tid] = 0; row_touched[tid] = 0; }
     // Programmatic dependent launch: everything above overlaps the tail of the flatten kernel; the bins, their counters and
     // the status flags it writes are read only after it has completed (no-op when launched without the attribute).
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // `late_wait` (the 2nd, 3rd ... launch of an ordered batch): the kernel before us is the previous fill of the same
+    // canvas; only the composite at the end depends on it, so the wait moves there and this tile's accumulation overlaps
+    // the previous fill's compositing.  The flatten kernel is long complete by then: the first raster launch lets its
+    // dependents go only after its own wait has returned.
+    if (!late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     // volatile: loads through a `const __restrict__` pointer are invariant to the compiler and may be hoisted above the
     // wait, where the flatten kernel has not raised its flags yet
     // (thread 0 alone reads them, next to its ticket, and broadcasts the verdict with the tile)
@@ -344,6 +349,7 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     __syncthreads();
 
     // ---- phase 2: per-row scan, fill rule, store / composite (rowtot is dead: FILL reuses it as a per-row live flag) ----
+    if (late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous fill of this canvas is complete
     if (job.rule == 1) scan_rows<CW, TH, THREADS, true, FILL, Cfg>(job, s_paint, cells, carry, row_touched, rowtot, row0, row1, cx0, mode, tid);
     else scan_rows<CW, TH, THREADS, false, FILL, Cfg>(job, s_paint, cells, carry, row_touched, rowtot, row0, row1, cx0, mode, tid);
 }
@@ -379,7 +385,7 @@ __global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restri
 template <int CW, int TH, int THREADS, bool FILL>
 static void launch_raster_t(const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
                             uint32_t n_tiles, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
-                            unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, bool pdl, cudaStream_t s) {
+                            unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, int pdl, cudaStream_t s) {
     constexpr size_t smem = TileCfg<CW, TH, THREADS>::smem_bytes();
     static bool configured[64] = {};  // per template instance and per device: the attribute belongs to the device's function
     int dev = 0;
@@ -400,9 +406,9 @@ static void launch_raster_t(const JobDev* jobs, const JobDev* h_jobs, uint32_t n
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = pdl ? 1 : 0;  // pdl: 0 = plain launch, 1 = wait at the top (behind the flatten kernel), 2 = late wait
     cudaLaunchKernelEx(&cfg, raster_kernel<CW, TH, THREADS, FILL>, jobs, n_jobs, job_first, tile_first, h_jobs[job_first], paints, tile_offs, bin_cap,
-                       bin_lines, tile_state, epoch, ticket, status, zero_early ? 1u : 0u, n_tiles);
+                       bin_lines, tile_state, epoch, ticket, status, zero_early ? 1u : 0u, n_tiles, pdl == 2 ? 1u : 0u);
 }
 
 TileShape raster_tile_shape(int variant) {
@@ -415,7 +421,7 @@ TileShape raster_tile_shape(int variant) {
 
 void launch_raster(int variant, const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
                    uint32_t n_tiles, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
-                   unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, bool pdl, cudaStream_t s) {
+                   unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, int pdl, cudaStream_t s) {
     if (n_tiles == 0) return;
     // launches without a FILL job run the instantiation that carries no paint / composite code (fewer registers)
     bool fill = false;

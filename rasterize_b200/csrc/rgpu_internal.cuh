@@ -104,8 +104,9 @@ TileShape raster_tile_shape(int variant);
 // `ticket` is a zeroed device counter private to this launch (dynamic tile ids for the carry look-back);
 // `tile_state` holds kMaxBandRows u64 words per tile, validated by `epoch` (no clearing between batches).
 // `h_jobs` is the host copy of the job table: single-job launches pass their descriptor by value.
-// `pdl`: the launch directly follows the flatten kernel in the stream and may overlap its tail (programmatic dependent
-// launch); the kernel waits for it before reading anything it wrote.
+// `pdl` (programmatic dependent launch): 1 = the launch directly follows the flatten kernel in the stream and may overlap
+// its tail; the kernel waits for it before reading anything it wrote.  2 = the launch follows the previous fill of the same
+// canvas in an ordered batch: it accumulates its tiles while that fill composites and waits only before compositing.  0 = plain.
 // `zero_early`: clear every tile's cells before its id is known (pays off when most tiles hold lines).
 // bin_cap == 0: tile t's lines are bin_lines[tile_offs[t] .. tile_offs[t+1]); bin_cap > 0: fixed bins, tile t's lines
 // are bin_lines[t*bin_cap .. t*bin_cap + tile_offs[t]) (tile_offs then holds the per-tile COUNTS).
@@ -113,7 +114,7 @@ TileShape raster_tile_shape(int variant);
 // the next batch finds them zero without a memset.
 void launch_raster(int variant, const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
                    uint32_t n_tiles, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
-                   unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, bool pdl, cudaStream_t s);
+                   unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, int pdl, cudaStream_t s);
 // Fused one-CTA-per-job pipeline for canvases of at most 64 x 64 visible pixels (small.cu)
 bool small_canvas_eligible(uint32_t width, uint32_t height, int mode);
 void launch_small_canvas(const JobDev* jobs, uint32_t job_first, uint32_t n_jobs, const PaintDev* paints, double thr, Status* status,
