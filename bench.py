@@ -243,6 +243,8 @@ def run_ours(args):
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # the ranks of a node share its host cores: split them between the widening pools of the e2e leg
+    os.environ.setdefault("RGPU_HOST_THREADS", str(max(2, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))))
     rast = rb.GpuRasterizer(device=local_rank)
     jobs, independent, info = build_workload(args.workload, rb, rast, rank, world, torch)
     prepared = rast.prepare_batch(jobs)

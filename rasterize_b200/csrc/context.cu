@@ -1013,7 +1013,9 @@ static int download_widen(rgpu_ctx* ctx, const float* d_img, size_t w, size_t h,
     int rc;
     if ((rc = ensure_stage(ctx, sizeof(float) * w * h))) return rc;
     if (!ctx->pool) {
+        // RGPU_HOST_THREADS: widening threads of this context (one process per GPU shares the host's cores with its peers)
         unsigned n = std::thread::hardware_concurrency();
+        if (const char* e = getenv("RGPU_HOST_THREADS")) n = (unsigned)std::max(1, atoi(e));
         ctx->pool.reset(new rgpu::HostPool(std::max(1u, std::min(n ? n : 4u, 32u))));
     }
     // rows [0, h_dev) go the device-widened way

@@ -229,3 +229,26 @@ def test_mask_pinned_f64_matches_pageable(rast):
     oref = np.zeros((h, w))
     opath(p).mask(tr, O.NONZERO, oref)
     assert np.abs(ref - oref).max() <= COV_TOL
+
+
+def test_two_pass_fallback_matches(monkeypatch):
+    """The exact count -> scan -> emit binning (taken when fixed-capacity bins would exceed their memory budget) gives the
+    same pixels as the single-pass scheme: forced through its A/B switch on a fresh context."""
+    p = assets.load_path("rust")
+    tr = np.array(assets.expected()["paths"]["rust"]["size_tr"]) * 2.0
+    w, h = 1500, 700  # two column chunks: the carry look-back runs too
+    a = np.zeros((h, w))
+    r1 = rb.GpuRasterizer()
+    r1.mask(p, tr, a, rb.FillRule.EvenOdd)
+    r1.close()
+    monkeypatch.setenv("RGPU_TWO_PASS", "1")
+    r2 = rb.GpuRasterizer()
+    b = np.zeros((h, w))
+    r2.mask(p, tr, b, rb.FillRule.EvenOdd)
+    launches = r2.last_counts()["launches"]
+    r2.close()
+    assert np.array_equal(a, b)
+    assert launches >= 4  # count, scan, emit, raster
+    ref = np.zeros((h, w))
+    opath(p).mask(tr, O.EVENODD, ref)
+    assert np.abs(a - ref).max() <= COV_TOL
