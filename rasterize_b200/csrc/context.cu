@@ -1155,10 +1155,34 @@ int rgpu_fill(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill
     float4* d_img = static_cast<float4*>(ctx->img_lin.p);
     float* dst = img + 4 * shape.start;
     bool dense_rows = shape.col_stride == 1;
+    // Only pixels inside the bounding box of the transformed control points (the curve lies in their convex hull) can be
+    // covered, so only that rectangle of the image has to cross PCIe, both ways; the kernels still see the whole view
+    // (clipping at the view's edges is part of the reference's arithmetic).  Parts left of the view fold onto column 0
+    // and parts beyond the right edge onto the last column: the clamps below keep those columns in.
+    size_t rx0 = 0, rx1 = w, ry0 = 0, ry1 = h;
+    {
+        double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+        bool finite = true;
+        for (uint32_t i = 0; i < path->n_points; i++) {
+            const double px = path->points[2 * i], py = path->points[2 * i + 1];
+            const double x = px * tr[0] + py * tr[1] + tr[2], y = px * tr[3] + py * tr[4] + tr[5];
+            finite = finite && std::isfinite(x) && std::isfinite(y);
+            xmin = std::min(xmin, x); xmax = std::max(xmax, x);
+            ymin = std::min(ymin, y); ymax = std::max(ymax, y);
+        }
+        if (finite && path->n_points) {
+            auto clampi = [](double v, size_t hi) { return (size_t)std::min<double>(std::max(v, 0.0), (double)hi); };
+            rx0 = clampi(std::floor(xmin) - 2.0, w); rx1 = clampi(std::ceil(xmax) + 3.0, w);
+            ry0 = clampi(std::floor(ymin) - 1.0, h); ry1 = clampi(std::ceil(ymax) + 2.0, h);
+            if (rx1 <= rx0 || ry1 <= ry0) rx0 = rx1 = ry0 = ry1 = 0;  // nothing of the view can change
+        }
+    }
+    const size_t rw = rx1 - rx0, rh = ry1 - ry0;
     // host image -> device canvas
     if (dense_rows) {
-        CK(ctx, cudaMemcpy2DAsync(d_img, w * sizeof(float4), dst, shape.row_stride * sizeof(float4), w * sizeof(float4), h,
-                                  cudaMemcpyHostToDevice, ctx->stream));
+        if (rw && rh)
+            CK(ctx, cudaMemcpy2DAsync(d_img + ry0 * w + rx0, w * sizeof(float4), dst + 4 * (ry0 * shape.row_stride + rx0),
+                                      shape.row_stride * sizeof(float4), rw * sizeof(float4), rh, cudaMemcpyHostToDevice, ctx->stream));
     } else {
         if ((rc = ensure_stage(ctx, sizeof(float4) * w * h))) return rc;
         float4* st = static_cast<float4*>(ctx->h_stage);
@@ -1184,8 +1208,9 @@ int rgpu_fill(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill
     rc = submit_sync(ctx, &job, 1, RGPU_BATCH_ORDERED, 1);
     if (rc) return rc;
     if (dense_rows) {
-        CK(ctx, cudaMemcpy2DAsync(dst, shape.row_stride * sizeof(float4), d_img, w * sizeof(float4), w * sizeof(float4), h,
-                                  cudaMemcpyDeviceToHost, ctx->stream));
+        if (rw && rh)
+            CK(ctx, cudaMemcpy2DAsync(dst + 4 * (ry0 * shape.row_stride + rx0), shape.row_stride * sizeof(float4), d_img + ry0 * w + rx0,
+                                      w * sizeof(float4), rw * sizeof(float4), rh, cudaMemcpyDeviceToHost, ctx->stream));
         CK(ctx, cudaStreamSynchronize(ctx->stream));
     } else {
         float4* st = static_cast<float4*>(ctx->h_stage);

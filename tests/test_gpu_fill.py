@@ -136,3 +136,24 @@ def test_to_rgba8_edge_values(rast):
     assert np.array_equal(got, O.lin_to_rgba(vals))
     rast.device_free(d_in)
     rast.device_free(d_out)
+
+
+@pytest.mark.parametrize("offset", [(300.0, 180.0), (-40.0, -25.0), (830.0, 520.0), (2000.0, 2000.0)])
+def test_fill_small_shape_on_big_image(rast, offset):
+    """rgpu_fill moves only the bounding rectangle of the transformed path over PCIe: a small shape placed inside a large
+    image, hanging over its left/top edge, over its right/bottom edge, and entirely outside must give the oracle's
+    pixels everywhere (the rest of the image is left untouched)."""
+    p = assets.load_path("squirrel")
+    e = assets.expected()["paths"]["squirrel"]
+    tr = O.transform_mul(O.translate(*offset), np.array(e["size_tr"]) * np.array([0.25, 0.25, 0.25, 0.25, 0.25, 0.25]))
+    W, H = 900, 600
+    rng = np.random.default_rng(3)
+    bg = rng.random((H, W, 4), dtype=np.float32) * 0.4
+    bg[..., 3] += 0.5
+    got, ref = bg.copy(), bg.copy()
+    color = np.float32([0.1, 0.3, 0.6, 0.8])
+    rast.fill(p, tr, rb.FillRule.EvenOdd, rb.LinColor(*color), got)
+    opath(p).fill(tr, O.EVENODD, O.OraclePaint.solid(color), ref, shape=O.Shape(0, W, H, W, 1))
+    assert np.abs(got - ref).max() <= LIN_TOL
+    changed = np.abs(ref - bg).max(axis=2) > 0
+    assert np.array_equal(got[~changed], bg[~changed])
