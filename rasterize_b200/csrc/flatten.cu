@@ -20,7 +20,7 @@
 #include <cstdlib>
 
 #ifndef RGPU_FLAT_MINB
-#define RGPU_FLAT_MINB 10  // 48 registers: the whole grid of a 4096^2 path is resident in one wave (sweep: 1 / 9 / 10 -> 38.9 / 31.7 / 30.9 us)
+#define RGPU_FLAT_MINB 9  // 56 registers: sweep with the per-warp leaf queue on C2 — 8 / 9 / 10 CTAs per SM -> 26.6 / 26.6 / 29.2 us
 #endif
 
 namespace rgpu {
@@ -29,6 +29,7 @@ namespace {
 
 using namespace fl;
 
+constexpr int kWarpQueue = 96;                 // leaves a warp parks in shared memory before binning them (flatten_bin_kernel<2>)
 constexpr int kDeepCutDepth = 5;              // 32 slots per item for small batches (see launch_flatten_bin_fixed)
 constexpr uint32_t kDeepCutMaxItems = 8192;
 
@@ -101,25 +102,58 @@ flatten_bin_kernel(const JobDev* __restrict__ jobs_in, uint32_t n_jobs, const __
     const uint32_t total_slots = total_items << DEPTH;
     SlotCtx c;
     uint32_t count = 0, n_refs = 0;
+    auto bin_one = [&](const JobDev& job, double x0, double y0, double x1, double y1) {
+        for_each_tile(job, x0, y0, x1, y1, band_shift, chunk_shift, [&](uint32_t key) {
+            const uint32_t slot = atomicAdd(&tile_counts[key], 1u);
+            if (PASS == 1) bin_lines[tile_offs[key] + slot] = make_double4(x0, y0, x1, y1);
+            if (PASS == 2) {
+                n_refs++;
+                if (slot < refs_cap) {
+                    bin_lines[(size_t)key * refs_cap + slot] = make_double4(x0, y0, x1, y1);
+                } else {
+                    status->refs_overflow = 1u;
+                    atomicMax(&status->bin_max, slot + 1u);
+                }
+            }
+        });
+    };
+    // PASS 2: the depth-first walks of a warp's lanes reach their leaves at different times; doing the tile arithmetic,
+    // the counter atomic and the bin store inside the walk would make every lane sit through every other lane's
+    // emission.  Leaves are parked in a per-warp shared queue instead (one shared atomic + a 32 B store) and binned after
+    // the walk, 32 at a time with all lanes busy.
+    __shared__ double4 q_line[PASS == 2 ? 4 : 1][PASS == 2 ? kWarpQueue : 1];
+    __shared__ uint32_t q_job[PASS == 2 ? 4 : 1][PASS == 2 ? kWarpQueue : 1];
+    __shared__ uint32_t q_n[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (PASS == 2) {
+        if (lane == 0) q_n[warp] = 0;
+        __syncwarp();
+    }
     if (t < total_slots && slot_setup<DEPTH>(jobs, n_jobs, t, thr, c, status)) {
         const JobDev& job = jobs[c.job];
         auto emit = [&](double x0, double y0, double x1, double y1) {
-            for_each_tile(job, x0, y0, x1, y1, band_shift, chunk_shift, [&](uint32_t key) {
-                const uint32_t slot = atomicAdd(&tile_counts[key], 1u);
-                if (PASS == 1) bin_lines[tile_offs[key] + slot] = make_double4(x0, y0, x1, y1);
-                if (PASS == 2) {
-                    n_refs++;
-                    if (slot < refs_cap) {
-                        bin_lines[(size_t)key * refs_cap + slot] = make_double4(x0, y0, x1, y1);
-                    } else {
-                        status->refs_overflow = 1u;
-                        atomicMax(&status->bin_max, slot + 1u);
-                    }
+            if (PASS == 2) {
+                const uint32_t k = atomicAdd(&q_n[warp], 1u);
+                if (k < (uint32_t)kWarpQueue) {
+                    q_line[warp][k] = make_double4(x0, y0, x1, y1);
+                    q_job[warp][k] = c.job;
+                } else {
+                    bin_one(job, x0, y0, x1, y1);  // queue full (a warp of deep curves): bin it here
                 }
-            });
+            } else {
+                bin_one(job, x0, y0, x1, y1);
+            }
         };
         // finite control points cannot produce NaN below: skip the per-node has_nans test (see seg_all_finite)
         count = seg_all_finite(c.seg, c.kind) ? slot_walk<false>(c, thr, status, emit) : slot_walk<true>(c, thr, status, emit);
+    }
+    if (PASS == 2) {
+        __syncwarp();
+        const uint32_t n = min(q_n[warp], (uint32_t)kWarpQueue);
+        for (uint32_t i = lane; i < n; i += 32) {
+            const double4 l = q_line[warp][i];
+            bin_one(jobs[q_job[warp][i]], l.x, l.y, l.z, l.w);
+        }
     }
     if (PASS != 1) {  // total line count of the batch (statistics): one atomic per warp
 #pragma unroll
