@@ -333,7 +333,7 @@ def run_ours(args):
     if args.workload == "c2":
         path, tr, (w, h) = info["host_path"], info["host_tr"], info["host_size"]
         img = rast.host_alloc((h, w), np.float64)  # pinned host image, as the contract asks
-        for _ in range(8):  # also lets the device/host widening split of rgpu_mask settle
+        for _ in range(16):  # also lets the device/host widening split of rgpu_mask settle
             rast.mask(path, tr, img, rb.FillRule.NonZero)
         n_e2e = max(5, min(20, args.steps))
         barrier()

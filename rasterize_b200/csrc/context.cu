@@ -9,6 +9,7 @@
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1008,7 +1009,9 @@ static inline void widen_row(const float* __restrict__ src, double* __restrict__
 //   * when the caller's image is pinned and dense along x, the TOP rows are widened on the device and DMA'd straight
 //     into place as f64 behind the f32 chunks, so the copy engine keeps working while the host threads catch up.
 // The split adapts from call to call to whichever side finished last (host widening bandwidth differs a lot between
-// hosts: 134 MB of f64 stores per 4096^2 mask).
+// hosts: 134 MB of f64 stores per 4096^2 mask).  Measured and rejected: a lossless row encoding of the mask (bit masks of
+// exact 0 / 1 per 32-pixel word + packed literals) expanded by the host threads — a quarter of the pixels of a 4096^2 mask
+// are literals (covered pixels are 1 - k * 2^-24 as often as exactly 1), the encode kernel costs 0.3 ms, and the call got slower.
 static int download_widen(rgpu_ctx* ctx, const float* d_img, size_t w, size_t h, double* dst, rgpu_shape shape) {
     int rc;
     if ((rc = ensure_stage(ctx, sizeof(float) * w * h))) return rc;
@@ -1054,9 +1057,15 @@ static int download_widen(rgpu_ctx* ctx, const float* d_img, size_t w, size_t h,
     ctx->last_d2h_bytes = sizeof(float) * w * (h - h_dev) + sizeof(double) * w * h_dev;
     const unsigned workers = ctx->pool->size();
     const size_t rs = shape.row_stride, cs = shape.col_stride;
+    static const bool trace = getenv("RGPU_E2E_TRACE") != nullptr;  // timing breakdown of this function on stderr
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    double t_first = 0, t_last = 0;
     for (size_t c = 0; c < n_chunks; c++) {
         const size_t r0 = h_dev + c * target_rows, r1 = std::min(h, r0 + target_rows);
         CK(ctx, cudaEventSynchronize(ctx->chunk_ev[c]));
+        if (c == 0) t_first = since();
+        t_last = since();
         const size_t rows = r1 - r0;
         const size_t parts = std::min<size_t>(workers, rows);
         for (size_t p = 0; p < parts; p++) {
@@ -1078,13 +1087,16 @@ static int download_widen(rgpu_ctx* ctx, const float* d_img, size_t w, size_t h,
         }
     }
     if (h_dev) {
-        // which producer is late?  (the f64 DMA is queued behind the f32 chunks)
-        const bool dma_done_first = cudaEventQuery(ctx->chunk_ev[n_chunks]) == cudaSuccess;
+        // which producer finishes last?  (the f64 DMA is queued behind the f32 chunks)  Move the split towards the other.
         ctx->pool->wait();
-        const bool host_done_first = cudaEventQuery(ctx->chunk_ev[n_chunks]) != cudaSuccess;
+        const double t_pool = since();
+        const bool host_was_last = cudaEventQuery(ctx->chunk_ev[n_chunks]) == cudaSuccess;
         CK(ctx, cudaEventSynchronize(ctx->chunk_ev[n_chunks]));
-        if (dma_done_first) ctx->widen_dev_frac = std::min(0.6, ctx->widen_dev_frac + 0.03);       // host threads are the bottleneck
-        else if (host_done_first) ctx->widen_dev_frac = std::max(0.0, ctx->widen_dev_frac - 0.03);  // PCIe is
+        if (trace)
+            fprintf(stderr, "download_widen: dev share %.2f, first f32 chunk %.3f ms, last %.3f ms, pool done %.3f ms, f64 dma done %.3f ms\n",
+                    ctx->widen_dev_frac, t_first, t_last, t_pool, since());
+        if (host_was_last) ctx->widen_dev_frac = std::min(0.6, ctx->widen_dev_frac + 0.02);
+        else ctx->widen_dev_frac = std::max(0.0, ctx->widen_dev_frac - 0.02);
     } else {
         ctx->pool->wait();
     }
