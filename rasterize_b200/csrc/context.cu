@@ -1112,16 +1112,6 @@ int rgpu_mask(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill
     float* d = nullptr;
     int rc = mask_to_device(ctx, path, tr, fill_rule, RGPU_JOB_MASK, w, h, &d);
     if (rc) return rc;
-    static const bool device_widen = getenv("RGPU_MASK_DEVICE_WIDEN") != nullptr;  // A/B switch for benchmarking
-    if (device_widen && shape.col_stride == 1) {
-        if ((rc = ensure_dev(ctx, ctx->img_f64, sizeof(double) * w * h))) return rc;
-        double* d64 = static_cast<double*>(ctx->img_f64.p);
-        launch_f32_to_f64(d, d64, w * h, ctx->stream);
-        CK(ctx, cudaMemcpy2DAsync(img + shape.start, shape.row_stride * sizeof(double), d64, w * sizeof(double), w * sizeof(double), h,
-                                  cudaMemcpyDeviceToHost, ctx->stream));
-        CK(ctx, cudaStreamSynchronize(ctx->stream));
-        return RGPU_OK;
-    }
     return download_widen(ctx, d, w, h, img + shape.start, shape);
 }
 
