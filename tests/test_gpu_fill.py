@@ -157,3 +157,13 @@ def test_fill_small_shape_on_big_image(rast, offset):
     assert np.abs(got - ref).max() <= LIN_TOL
     changed = np.abs(ref - bg).max(axis=2) > 0
     assert np.array_equal(got[~changed], bg[~changed])
+
+
+def test_ordered_fills_are_reproducible(rast):
+    """The fills of a scene are chained with dependent launches (a fill accumulates its tiles while the previous one is
+    still compositing): twenty renders of firefox.scene at 2048 x 2048 must be bit-identical."""
+    sc = assets.load_scene("firefox_2048")
+    first, _ = render_scene_gpu(rast, sc, to_rgba=False)
+    for _ in range(19):
+        again, _ = render_scene_gpu(rast, sc, to_rgba=False)
+        assert np.array_equal(first, again)
