@@ -301,6 +301,20 @@ bool build_paint(const rgpu_job& job, PaintDev& out) {
         out.stop_pos[i] = p->stop_pos[i];
         std::memcpy(out.stop_col[i], p->stop_colors + 4 * i, 16);
     }
+    for (int i = 1; i < out.n_stops; i++) out.stop_inv[i] = 1.0 / (out.stop_pos[i] - out.stop_pos[i - 1]);
+    if (p->kind == RGPU_PAINT_LINEAR) {
+        // t = (pixel_tr(p) - start) . dir is affine in the pixel centre: fold the two transforms once
+        const double* m = out.pixel_tr;
+        out.lin_a = m[0] * out.dirx + m[3] * out.diry;
+        out.lin_b = m[1] * out.dirx + m[4] * out.diry;
+        out.lin_c = (m[2] - out.p0x) * out.dirx + (m[5] - out.p0y) * out.diry;
+    } else {
+        // the pixel-independent terms of GradRadial::offset, src/grad.rs:361-372 (same expressions, evaluated once)
+        out.rad_cdx = out.p0x - out.p1x;
+        out.rad_cdy = out.p0y - out.p1y;
+        out.rad_rd = out.r0 - out.r1;
+        out.rad_a = (out.rad_cdx * out.rad_cdx + out.rad_cdy * out.rad_cdy) - out.rad_rd * out.rad_rd;
+    }
     if (out.n_stops == 0) {  // GradStops::new: empty list -> one opaque black stop, src/grad.rs:92-97
         out.n_stops = 1;
         out.stop_pos[0] = 0.0;

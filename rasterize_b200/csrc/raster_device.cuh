@@ -61,8 +61,9 @@ static __device__ float4 stops_at(const PaintDev& P, double t) {
     if (index == 0) return make_float4(P.stop_col[0][0], P.stop_col[0][1], P.stop_col[0][2], P.stop_col[0][3]);
     if (index == size)
         return make_float4(P.stop_col[size - 1][0], P.stop_col[size - 1][1], P.stop_col[size - 1][2], P.stop_col[size - 1][3]);
-    double pos0 = P.stop_pos[index - 1], pos1 = P.stop_pos[index];
-    float r = (float)((t - pos0) / (pos1 - pos0));
+    // ((t - p0.position) / (p1.position - p0.position)) as f32, src/grad.rs:133-137: the reciprocal of the stop interval
+    // is a per-paint constant (the f64 quotient and product agree to an ulp, far below the f32 cast)
+    float r = (float)((t - P.stop_pos[index - 1]) * P.stop_inv[index]);
     float ir = fsub(1.0f, r);
     const float* c0 = P.stop_col[index - 1];
     const float* c1 = P.stop_col[index];
@@ -73,10 +74,8 @@ static __device__ float4 stops_at(const PaintDev& P, double t) {
 
 // utils::quadratic_solve + GradRadial::offset root selection, src/utils.rs:205-231, src/grad.rs:361-396
 static __device__ bool radial_offset(const PaintDev& P, double px, double py, double& out) {
-    double cdx = __dsub_rn(P.p0x, P.p1x), cdy = __dsub_rn(P.p0y, P.p1y);
+    const double cdx = P.rad_cdx, cdy = P.rad_cdy, rd = P.rad_rd, a = P.rad_a;  // pixel-independent: hoisted to the host
     double pdx = __dsub_rn(px, P.p1x), pdy = __dsub_rn(py, P.p1y);
-    double rd = __dsub_rn(P.r0, P.r1);
-    double a = __dsub_rn(__dadd_rn(__dmul_rn(cdx, cdx), __dmul_rn(cdy, cdy)), __dmul_rn(rd, rd));
     double b = __dmul_rn(-2.0, __dadd_rn(__dadd_rn(__dmul_rn(cdx, pdx), __dmul_rn(cdy, pdy)), __dmul_rn(P.r1, rd)));
     double c = __dsub_rn(__dadd_rn(__dmul_rn(pdx, pdx), __dmul_rn(pdy, pdy)), __dmul_rn(P.r1, P.r1));
     if (fabs(a) < kEps) {
@@ -107,14 +106,15 @@ static __device__ bool radial_offset(const PaintDev& P, double px, double py, do
 static __device__ float4 paint_at(const PaintDev& P, int x, int y) {
     if (P.kind == 0) return make_float4(P.solid[0], P.solid[1], P.solid[2], P.solid[3]);
     double fx = (double)x + 0.5, fy = (double)y + 0.5;
-    const double* m = P.pixel_tr;
-    double px = __dadd_rn(__dadd_rn(__dmul_rn(fx, m[0]), __dmul_rn(fy, m[1])), m[2]);
-    double py = __dadd_rn(__dadd_rn(__dmul_rn(fx, m[3]), __dmul_rn(fy, m[4])), m[5]);
     double t;
     if (P.kind == 1) {
-        // (point - start).dot(dir), src/grad.rs:204
-        t = __dadd_rn(__dmul_rn(__dsub_rn(px, P.p0x), P.dirx), __dmul_rn(__dsub_rn(py, P.p0y), P.diry));
+        // (pixel_tr(p) - start).dot(dir), src/rasterize.rs:93-96 + src/grad.rs:204, as one affine form of the pixel centre
+        // (agrees with the reference's two-step evaluation to f64 rounding)
+        t = fma(fx, P.lin_a, fma(fy, P.lin_b, P.lin_c));
     } else {
+        const double* m = P.pixel_tr;
+        double px = __dadd_rn(__dadd_rn(__dmul_rn(fx, m[0]), __dmul_rn(fy, m[1])), m[2]);
+        double py = __dadd_rn(__dadd_rn(__dmul_rn(fx, m[3]), __dmul_rn(fy, m[4])), m[5]);
         if (!radial_offset(P, px, py, t)) return make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (P.spread == 1) t = rem_euclid(t, 1.0);

@@ -42,6 +42,10 @@ struct PaintDev {
     float solid[4];
     double stop_pos[kMaxStops];
     float stop_col[kMaxStops][4];
+    // per-paint constants hoisted out of the per-pixel evaluation (filled by the host, context.cu: build_paint)
+    double stop_inv[kMaxStops];  // 1 / (stop_pos[i] - stop_pos[i-1]) for i >= 1
+    double lin_a, lin_b, lin_c;  // linear: t = (x + 0.5) * lin_a + (y + 0.5) * lin_b + lin_c (pixel_tr and dir folded together)
+    double rad_cdx, rad_cdy, rad_rd, rad_a;  // radial: c - fc, r - fr, cd.cd - rd^2 (src/grad.rs:361-372)
 };
 
 struct JobDev {
