@@ -9,12 +9,13 @@
 // intrinsics (__dmul_rn/__dadd_rn/__dsub_rn): they are never contracted into FMAs, whatever -fmad says, and the
 // operand order follows the reference expression trees exactly.
 //
-// Parallelisation: the subdivision tree of every item is cut at depth 3; each of the 8 subtrees ("slots") is
-// walked depth-first by its own thread with an explicit stack of pending right halves.
+// Parallelisation: the subdivision tree of every item is cut at depth 3 (8 "slots"; depth 5 = 32 slots for small
+// batches); each slot's subtree is walked depth-first by its own thread with an explicit stack of pending right halves.
 //   * `rgpu_flatten` (ordered): a count pass sizes every slot, an exclusive scan places them, an emit pass writes
 //     the lines in the reference's order.
-//   * raster path: the walk is fused with binning — pass 0 counts lines per tile, pass 1 writes every line straight
-//     into the bins of the tiles it touches (flatten_bin_kernel); no global line buffer.
+//   * raster path: the walk is fused with binning (flatten_bin_kernel), no global line buffer.  Default (PASS 2): ONE
+//     walk; leaves are parked in a per-warp shared queue and then appended to the fixed-capacity bin of every tile they
+//     touch.  Fallback (PASS 0 / 1): count lines per tile, scan, walk again and write packed bins.
 #include "flatten_device.cuh"
 
 #include <cstdlib>

@@ -6,10 +6,10 @@
 //   slot_counts u32[8*items+1]               lines produced by each (item, depth-3 subtree) slot
 //   slot_offs   u32[8*items+1]               exclusive scan of slot_counts; last = total lines
 //   lines       double4[n_lines]             flattened lines in the reference's order (x0,y0,x1,y1)
-//   tile_counts u32[tiles+1] / tile_offs     per (job, band, chunk) tile reference counts / exclusive scan
-//   bin_lines   double4[n_refs]              the lines of every tile, grouped by tile (order inside a tile is
-//                                            irrelevant: accumulation is fixed-point, hence associative)
-//   tile_state  u64[tiles*8]                 per-row tile totals / inclusive prefixes for the carry look-back
+//   tile_counts u32[tiles]                   lines each (job, band, chunk) tile wants (self-cleaning: zeroed by the raster CTA)
+//   bin_lines   double4[tiles * bin_cap]     fixed-capacity bin per tile (order inside a tile is irrelevant: accumulation
+//                                            is fixed-point, hence associative); two-pass fallback: packed, with tile_offs
+//   tile_state  u64[tiles*16]                per-row tile totals / inclusive prefixes for the carry look-back
 //   canvases    caller-owned                 f32 coverage or f32x4 LinColor
 #pragma once
 #include <cuda_runtime.h>
@@ -86,9 +86,9 @@ size_t scan_temp_bytes(uint32_t n);
 // `temp` must be zero on entry; pass temp_is_zero = true when the caller has already cleared it
 void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, void* temp, size_t temp_bytes, cudaStream_t s,
                            bool temp_is_zero = false);
-// Flatten fused with binning (raster path): pass 0 walks every slot and counts lines per tile (and in total, into
-// status->n_lines); after an exclusive scan of the tile counts, pass 1 walks again and writes every line straight
-// into the bins of the tiles it touches.  No global line buffer.
+// Flatten fused with binning, two-pass fallback (fixed bins over budget): pass 0 walks every slot and counts lines per
+// tile (and in total, into status->n_lines); after an exclusive scan of the tile counts, pass 1 walks again and writes
+// every line straight into the packed bins of the tiles it touches.  No global line buffer.
 void launch_flatten_bin_count(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, uint32_t* tile_counts,
                               int band_rows, int chunk_cols, Status* status, cudaStream_t s);
 void launch_flatten_bin_emit(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, const uint32_t* tile_offs,
