@@ -35,7 +35,7 @@ struct TileCfg {
     static constexpr int kRowBits = (TH <= 8) ? 3 : 6;
     // per-warp span list: (source lane, band row) packed in a byte when the row fits 3 bits
     using SpanT = typename std::conditional<(TH <= 8), unsigned char, unsigned short>::type;
-    static constexpr int kWarpSpanCap = (TH <= 8) ? 224 : 512;  // lanes that do not fit do their rows serially
+    static constexpr int kWarpSpanCap = (TH <= 8) ? 208 : 512;  // lanes that do not fit do their rows serially
     static constexpr size_t kCellBytes = sizeof(int) * TH * CW;
     static constexpr size_t kPieceBytes = sizeof(double) * 4 * THREADS;  // reused for the paint in the scan phase
     static constexpr size_t smem_bytes() { return kCellBytes + kPieceBytes + sizeof(SpanT) * kWarpSpanCap * kWarps; }
@@ -186,6 +186,7 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     __shared__ int rowtot[TH];
     __shared__ int row_touched[TH];
     __shared__ uint32_t s_tile, s_job, s_chunk, s_band, s_count, s_bad;
+    __shared__ unsigned long long s_early[TH <= 8 ? TH : 1];  // left neighbour's look-back words, probed by thread 0 (below)
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -235,10 +236,21 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
         s_chunk = chunk;
         s_band = band;
         s_tile = tile;
+        // Early look-back probe: in chunk-major order the left neighbour has normally published its inclusive prefixes
+        // long ago.  Their state words are requested here, together with the bin counter, so that one memory round trip
+        // serves both; they are consumed after phase 1.
+        unsigned long long ev[TH <= 8 ? TH : 1];
+        const bool probe = TH <= 8 && jb.n_chunks > 1 && chunk > 0;
+        if (probe) {
+#pragma unroll
+            for (int r = 0; r < (TH <= 8 ? TH : 1); r++) ev[r] = ld_state(tile_state + (size_t)(tile - 1u) * kStateRows + r);
+        }
         if (bin_cap) {  // fixed-capacity bins: tile_offs holds the per-tile counts; leave the counter clean for the next batch
             s_count = min(tile_offs[tile], bin_cap);
             tile_offs[tile] = 0u;
         }
+#pragma unroll
+        for (int r = 0; r < (TH <= 8 ? TH : 1); r++) s_early[r] = probe ? ev[r] : 0ull;
     }
     __syncthreads();
     if (s_bad) return;
@@ -255,14 +267,8 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     g.pitch = CW;
     const int row0 = g.row0, row1 = g.row1, cx0 = g.cx0;
     const int mode = job.mode;
-    // Early look-back probe: in chunk-major order the left neighbour has normally published its inclusive prefix long
-    // ago, so its state word is requested NOW and consumed after phase 1 — the round trip overlaps the bin loads and
-    // the accumulation instead of following them.
     constexpr int LPR = (THREADS / TH >= 32) ? 32 : (THREADS / TH);  // lanes per row in the look-back (16 for 1024 x 8 / 128)
     static_assert(LPR >= 1 && (LPR & (LPR - 1)) == 0, "lanes per row must be a power of two");
-    unsigned long long early = 0;
-    if (job.n_chunks > 1 && chunk > 0 && tid % LPR == 0 && tid / LPR < TH && tid / LPR < kStateRows)
-        early = ld_state(tile_state + (size_t)(tile - 1u) * kStateRows + tid / LPR);
 
     // ---- phase 1: accumulate the tile's lines.  The lines are split evenly over the warps, which then work
     // independently, 32 lines per round (see warp_accumulate_round: 1a one line per lane, spans compacted per warp;
@@ -318,9 +324,9 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
                 const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((lane / LPR) * LPR));
                 int sum = 0;
                 // the early probe settles the row when it already saw this batch's inclusive prefix
+                const unsigned long long early = (TH <= 8) ? s_early[r] : 0ull;
                 bool done = (uint32_t)(early >> 34) == epoch && (early & (3ull << 32)) == kFlagPrefix;
                 if (done) sum = (int)(uint32_t)early;
-                done = __shfl_sync(0xffffffffu, done, (lane / LPR) * LPR);
                 for (int k0 = 1; k0 <= chunk && !__all_sync(0xffffffffu, done); k0 += LPR) {  // same trip count for every row of the tile
                     const int k = k0 + gl;
                     const bool look = !done && k <= chunk;
