@@ -359,6 +359,8 @@ def run_ours(args):
         e2e["f32_ms_per_call"] = round((time.perf_counter() - t0) / n_e2e * 1e3, 4)
         if rank == 0 and world == 1:
             cpu_baseline = cpu_reference_c2(threads=1, budget_s=12.0)
+    elif rank == 0 and world == 1:
+        cpu_baseline = cpu_reference_other(args.workload, budget_s=10.0)
 
     if rank == 0:
         out = {
@@ -409,6 +411,63 @@ def cpu_reference_c2(threads: int, budget_s: float):
     return {"value": round(w * h / dt / 1e6, 1), "unit": "Mpix/s", "cores": threads, "kind": "port",
             "sample": f"{n} x (clear + mask) of material.path at {w}x{h}, nonzero, {threads} thread(s), {dt * 1e3:.2f} ms each",
             "host_cores": os.cpu_count()}
+
+
+def cpu_reference_other(workload: str, budget_s: float):
+    """The CPU oracle (one thread, like the single-threaded reference) on a bounded sample of the other workloads."""
+    import math
+
+    import oracle as O
+    from rasterize_b200 import assets, sharding
+    t_end = time.perf_counter() + budget_s
+    if workload in ("c1", "c3"):
+        from helpers import render_scene_oracle
+        sc = assets.load_scene("squirrel_cli_512" if workload == "c1" else "firefox_2048")
+        render_scene_oracle(sc)  # warm-up
+        n, t0 = 0, time.perf_counter()
+        while True:
+            img = render_scene_oracle(sc)
+            O.lin_to_rgba(img)
+            n += 1
+            if time.perf_counter() > t_end or n >= 50:
+                break
+        dt = (time.perf_counter() - t0) / n
+        px = img.shape[0] * img.shape[1]
+        sample = f"{n} x Scene::render + RGBA8 of the {workload} scene ({img.shape[1]}x{img.shape[0]}), fills through the oracle's Rasterizer::fill, {dt * 1e3:.2f} ms each"
+    elif workload == "c4":
+        n_glyphs = 400
+        glyphs = [O.OraclePath.glyph(i + 1) for i in range(n_glyphs)]
+        img = np.zeros((64, 64))
+        n, t0 = 0, time.perf_counter()
+        while True:
+            for g in glyphs:
+                img[:] = 0
+                g.mask(O.IDENTITY, O.NONZERO, img)
+            n += 1
+            if time.perf_counter() > t_end or n >= 20:
+                break
+        dt = (time.perf_counter() - t0) / (n * n_glyphs)
+        px = 4096
+        sample = f"{n} x {n_glyphs} glyph masks at 64x64 (clear + mask), {dt * 1e6:.1f} us per glyph"
+    else:  # c5
+        p = assets.load_path("tv_stroked")
+        c5 = assets.expected()["paths"]["tv_stroked"]["c5"]
+        w, hfull = c5["size"]
+        y0, y1 = sharding.band_rows(hfull, 0 + 2, 8)  # a band that holds lines (band 0 is empty)
+        op = O.OraclePath.from_flat(p.points, p.kinds, p.subpath_offsets, p.closed)
+        img = np.zeros((y1 - y0, w))
+        tr = sharding.band_transform(c5["tr"], y0)
+        n, t0 = 0, time.perf_counter()
+        while True:
+            img[:] = 0
+            op.mask(tr, O.NONZERO, img)
+            n += 1
+            if time.perf_counter() > t_end or n >= 10:
+                break
+        dt = (time.perf_counter() - t0) / n
+        px = w * (y1 - y0)
+        sample = f"{n} x (clear + mask) of band 2 of 8 ({w}x{y1 - y0}) of tv.path stroked, {dt * 1e3:.1f} ms each"
+    return {"value": round(px / dt / 1e6, 1), "unit": "Mpix/s", "cores": 1, "kind": "port", "sample": sample, "host_cores": os.cpu_count()}
 
 
 def run_reference(args):
