@@ -15,6 +15,7 @@
 #pragma once
 #include "rasterize_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <limits>
@@ -234,12 +235,94 @@ public:
         return lines;
     }
     rgpu_ctx* raw() { return ctx_; }
-
-private:
     void check(int rc) const {
         if (rc != RGPU_OK) throw Error(rc, rgpu_last_error(ctx_));
     }
+
+private:
     rgpu_ctx* ctx_ = nullptr;
+};
+
+// `Layer<C>` (src/scene.rs:464-501) in device memory: integer origin, dense row-major pixels; C = LinColor (4 floats) or
+// Scalar coverage (1 float, the clip mask of the Clip arm).  The methods are the arms of `Pipeline::render_rec`
+// (src/scene.rs:397-459) with every pixel operation on the GPU; only `download*` crosses PCIe.
+class DeviceLayer {
+public:
+    DeviceLayer(GpuRasterizer& r, int32_t x, int32_t y, size_t width, size_t height, int channels, const float* color = nullptr)
+        : r_(r), x_(x), y_(y), w_(width), h_(height), ch_(channels) {
+        r_.check(rgpu_device_alloc(r_.raw(), std::max<size_t>(1, w_ * h_ * ch_ * sizeof(float)), &ptr_));
+        if (color && ch_ == 4) r_.check(rgpu_fill_color_dev(r_.raw(), data(), w_ * h_, color));
+        else r_.check(rgpu_device_zero(r_.raw(), ptr_, w_ * h_ * ch_ * sizeof(float)));
+    }
+    ~DeviceLayer() { rgpu_device_free(r_.raw(), ptr_); }
+    DeviceLayer(const DeviceLayer&) = delete;
+    DeviceLayer& operator=(const DeviceLayer&) = delete;
+    float* data() const { return static_cast<float*>(ptr_); }
+    size_t width() const { return w_; }
+    size_t height() const { return h_; }
+
+    // Fill arm: `path.fill(rasterizer, align * tr, fill_rule, paint, layer.view_mut(..))` on the whole layer
+    void fill(const Path& path, Transform tr, FillRule rule, Paint& paint) { job(path, tr, rule, RGPU_JOB_FILL, &paint); }
+    // the clip mask of the Clip arm: `path.mask(rasterizer, align * clip_tr, fill_rule, mask_layer)`
+    void mask(const Path& path, Transform tr, FillRule rule) { job(path, tr, rule, RGPU_JOB_MASK, nullptr); }
+    // `child_layer.compose(mask_layer, |dst, src| dst * src)` on the intersection rectangle (src/scene.rs:453-455)
+    void scale_by_mask(const DeviceLayer& m) {
+        Rect q;
+        if (!intersect(m, q)) return;
+        r_.check(rgpu_layer_scale_by_mask_dev(r_.raw(), data(), q.a, w_, m.data(), q.b, m.w_, q.w, q.h));
+    }
+    // `layer.compose(child_layer, |dst, src| dst.blend_over(src [* opacity]))` (src/scene.rs:436-457)
+    void blend_over(const DeviceLayer& src, const float* opacity = nullptr) {
+        Rect q;
+        if (!intersect(src, q)) return;
+        r_.check(rgpu_layer_blend_over_dev(r_.raw(), data(), q.a, w_, src.data(), q.b, src.w_, q.w, q.h, opacity != nullptr, opacity ? *opacity : 1.0f));
+    }
+    std::vector<float> download() const {
+        std::vector<float> out(w_ * h_ * ch_);
+        r_.check(rgpu_memcpy_d2h(r_.raw(), out.data(), ptr_, out.size() * sizeof(float)));
+        return out;
+    }
+    std::vector<uint8_t> download_rgba8() const {  // `From<LinColor> for RGBA` on the device, 4 B/pixel over PCIe
+        std::vector<uint8_t> out(w_ * h_ * 4);
+        r_.check(rgpu_download_rgba8(r_.raw(), data(), w_ * h_, out.data()));
+        return out;
+    }
+
+private:
+    struct Rect { size_t a, b, w, h; };
+    bool intersect(const DeviceLayer& o, Rect& q) const {  // src/scene.rs:540-549
+        const int64_t x0 = std::max<int64_t>(x_, o.x_), x1 = std::min<int64_t>(x_ + (int64_t)w_, o.x_ + (int64_t)o.w_);
+        const int64_t y0 = std::max<int64_t>(y_, o.y_), y1 = std::min<int64_t>(y_ + (int64_t)h_, o.y_ + (int64_t)o.h_);
+        if (x1 <= x0 || y1 <= y0) return false;
+        q = Rect{(size_t)((y0 - y_) * (int64_t)w_ + (x0 - x_)), (size_t)((y0 - o.y_) * (int64_t)o.w_ + (x0 - o.x_)), (size_t)(x1 - x0), (size_t)(y1 - y0)};
+        return true;
+    }
+    void job(const Path& path, Transform tr, FillRule rule, int mode, Paint* paint) {
+        if (w_ == 0 || h_ == 0) return;
+        const rgpu_path p = path.ffi();
+        rgpu_dpath* dp = nullptr;
+        r_.check(rgpu_path_upload(r_.raw(), &p, &dp));
+        rgpu_job j{};
+        j.path = dp;
+        // layer-local coordinates: `Transform::new_translate(-layer.x, -layer.y) * tr`
+        const Transform t = Transform::new_translate(-(double)x_, -(double)y_) * tr;
+        for (int i = 0; i < 6; i++) j.tr[i] = t.m[i];
+        j.fill_rule = (int)rule;
+        j.mode = mode;
+        j.paint = paint ? paint->ffi() : nullptr;
+        j.canvas = ptr_;
+        j.row_stride = w_;
+        j.width = (uint32_t)w_;
+        j.height = (uint32_t)h_;
+        const int rc = rgpu_render_batch_sync(r_.raw(), &j, 1, RGPU_BATCH_ORDERED);
+        rgpu_path_free(r_.raw(), dp);
+        r_.check(rc);
+    }
+    GpuRasterizer& r_;
+    int32_t x_, y_;
+    size_t w_, h_;
+    int ch_;
+    void* ptr_ = nullptr;
 };
 
 }  // namespace rasterize

@@ -75,11 +75,45 @@ static void test_fill_rule(Rasterizer& rasterizer) {
     CHECK(std::fabs(lin[(y * w + x0) * 4 + 3] - 0.5f) < 1e-4f && std::fabs(lin[(y * w + x2) * 4 + 3]) < 1e-6f);
 }
 
+// The Opacity and Clip arms of Pipeline::render_rec (src/scene.rs:436-457) on device layers, with solid colours so that
+// the expected pixels follow from `blend_over` / `Mul<f32>` by hand.
+static void test_layers(GpuRasterizer& r) {
+    const float bg[4] = {0.2f, 0.2f, 0.2f, 1.0f};
+    DeviceLayer layer(r, 0, 0, 40, 30, 4, bg);
+    // child layer at (10, 5), 20 x 10, covered entirely by a rectangle path in scene coordinates
+    DeviceLayer child(r, 10, 5, 20, 10, 4);
+    Path rect = Path::builder().move_to({5, 0}).line_to({35, 0}).line_to({35, 25}).line_to({5, 25}).close().build();
+    Paint red = Paint::solid(0.5f, 0.0f, 0.0f, 0.5f);
+    child.fill(rect, Transform::identity(), FillRule::NonZero, red);
+    // clip mask layer at (15, 0), 10 x 30: left half of it (x < 20 in scene coordinates) is inside the clip path
+    DeviceLayer mask(r, 15, 0, 10, 30, 1);
+    Path clip = Path::builder().move_to({0, 0}).line_to({20, 0}).line_to({20, 30}).line_to({0, 30}).close().build();
+    mask.mask(clip, Transform::identity(), FillRule::NonZero);
+    child.scale_by_mask(mask);  // only columns 15..24 of the scene are touched: 15..19 keep the colour, 20..24 become 0
+    const float opacity = 0.5f;
+    layer.blend_over(child, &opacity);
+    const std::vector<float> px = layer.download();
+    auto at = [&](int x, int y, int c) { return px[(size_t)(y * 40 + x) * 4 + c]; };
+    // outside the child layer: background
+    CHECK(at(2, 2, 0) == 0.2f && at(35, 20, 3) == 1.0f);
+    // child pixel left of the mask layer (x = 12): never multiplied by the mask (compose touches the intersection only)
+    // src = (0.5,0,0,0.5) * 0.5 = (0.25,0,0,0.25); dst = src + bg * 0.75
+    CHECK(std::fabs(at(12, 8, 0) - (0.25f + 0.2f * 0.75f)) < 1e-6f && std::fabs(at(12, 8, 1) - 0.15f) < 1e-6f && std::fabs(at(12, 8, 3) - 1.0f) < 1e-6f);
+    // inside the clip (x = 17): mask 1 -> same as above
+    CHECK(std::fabs(at(17, 8, 0) - 0.4f) < 1e-6f);
+    // masked out (x = 22): child * 0 -> background unchanged
+    CHECK(std::fabs(at(22, 8, 0) - 0.2f) < 1e-6f && std::fabs(at(22, 8, 3) - 1.0f) < 1e-6f);
+    // RGBA8 export: background 0.2 linear -> l2s(0.2) * 255 + 0.5 = 124 (x86 polynomial), alpha 255
+    const std::vector<uint8_t> rgba = layer.download_rgba8();
+    CHECK(rgba[3] == 255 && rgba[0] >= 123 && rgba[0] <= 125);
+}
+
 int main() {
     GpuRasterizer r;
     CHECK(std::string(r.name()) == "gpu-signed-difference");
     test_rasterizer(r);
     test_fill_rule(r);
+    test_layers(r);
     // NaN control point -> error (reference panics, src/path.rs:765-767)
     Path bad = Path::builder().move_to({0, 0}).quad_to({std::nan(""), 1}, {2, 2}).build();
     bool threw = false;
