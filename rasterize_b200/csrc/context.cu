@@ -23,7 +23,8 @@ using namespace rgpu;
 
 struct rgpu_dpath {
     double2* pts = nullptr;
-    uint2* items = nullptr;
+    uint2* items = nullptr;         // reference order (ordered flatten, two-pass binning)
+    uint2* items_packed = nullptr;  // curves first, then lines / closing items (single-pass binning)
     uint32_t n_points = 0, n_items = 0, n_curves = 0;
 };
 
@@ -192,6 +193,15 @@ int validate_path(rgpu_ctx* ctx, const rgpu_path* p) {
 
 // Build the device item list: the segments of each subpath followed by its closing item
 // (reference order of PathFlattenIter, src/path.rs:761-795).
+void pack_items(const std::vector<uint2>& items, std::vector<uint2>& packed) {
+    packed.clear();
+    packed.reserve(items.size());
+    for (const uint2& it : items)
+        if (!(it.y & kItemClosing) && it.y != 2u) packed.push_back(it);
+    for (const uint2& it : items)
+        if ((it.y & kItemClosing) || it.y == 2u) packed.push_back(it);
+}
+
 void build_items(const rgpu_path* p, std::vector<uint2>& items, uint32_t& n_curves) {
     std::vector<uint32_t> pt_off(p->n_segments + 1);
     uint32_t acc = 0;
@@ -214,17 +224,20 @@ void build_items(const rgpu_path* p, std::vector<uint2>& items, uint32_t& n_curv
 }
 
 int upload_path(rgpu_ctx* ctx, const rgpu_path* path, rgpu_dpath* dp) {
-    std::vector<uint2> items;
+    std::vector<uint2> items, packed;
     build_items(path, items, dp->n_curves);
+    pack_items(items, packed);
     dp->n_points = path->n_points;
     dp->n_items = (uint32_t)items.size();
+    items.insert(items.end(), packed.begin(), packed.end());  // one allocation: [reference order | curves first]
     if (dp->n_points) {
         CK(ctx, cudaMalloc(reinterpret_cast<void**>(&dp->pts), sizeof(double2) * dp->n_points));
         CK(ctx, cudaMemcpyAsync(dp->pts, path->points, sizeof(double2) * dp->n_points, cudaMemcpyHostToDevice, ctx->stream));
     }
     if (dp->n_items) {
-        CK(ctx, cudaMalloc(reinterpret_cast<void**>(&dp->items), sizeof(uint2) * dp->n_items));
-        CK(ctx, cudaMemcpyAsync(dp->items, items.data(), sizeof(uint2) * dp->n_items, cudaMemcpyHostToDevice, ctx->stream));
+        CK(ctx, cudaMalloc(reinterpret_cast<void**>(&dp->items), sizeof(uint2) * items.size()));
+        CK(ctx, cudaMemcpyAsync(dp->items, items.data(), sizeof(uint2) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
+        dp->items_packed = dp->items + dp->n_items;
     }
     // `items` is pageable: the async copy is staged by the driver before returning, but be explicit
     CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -234,21 +247,24 @@ int upload_path(rgpu_ctx* ctx, const rgpu_path* path, rgpu_dpath* dp) {
 // Device copy of a host path in the context's grow-only scratch (host-buffer entry points): no cudaMalloc / cudaFree
 // and no extra synchronisation per call; the copies are ordered before the kernels on the context's stream.
 int stage_path(rgpu_ctx* ctx, const rgpu_path* path, rgpu_dpath* dp) {
-    std::vector<uint2> items;
+    std::vector<uint2> items, packed;
     build_items(path, items, dp->n_curves);
+    pack_items(items, packed);
     dp->n_points = path->n_points;
     dp->n_items = (uint32_t)items.size();
+    items.insert(items.end(), packed.begin(), packed.end());  // [reference order | curves first]
     int rc;
     if ((rc = ensure_dev(ctx, ctx->tmp_pts, sizeof(double2) * std::max<uint32_t>(dp->n_points, 1)))) return rc;
-    if ((rc = ensure_dev(ctx, ctx->tmp_items, sizeof(uint2) * std::max<uint32_t>(dp->n_items, 1)))) return rc;
+    if ((rc = ensure_dev(ctx, ctx->tmp_items, sizeof(uint2) * std::max<size_t>(items.size(), 1)))) return rc;
     if ((rc = ensure_pinned(ctx, ctx->h_items, ctx->h_items_cap, std::max<size_t>(items.size(), 1)))) return rc;
     // a previous call's copy out of h_items has completed: every host-buffer entry point ends with a stream sync
     std::memcpy(ctx->h_items, items.data(), sizeof(uint2) * items.size());
     dp->pts = static_cast<double2*>(ctx->tmp_pts.p);
     dp->items = static_cast<uint2*>(ctx->tmp_items.p);
+    dp->items_packed = dp->items + dp->n_items;
     if (dp->n_points) CK(ctx, cudaMemcpyAsync(dp->pts, path->points, sizeof(double2) * dp->n_points, cudaMemcpyHostToDevice, ctx->stream));
-    if (dp->n_items) CK(ctx, cudaMemcpyAsync(dp->items, ctx->h_items, sizeof(uint2) * dp->n_items, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->last_h2d_bytes = sizeof(double2) * dp->n_points + sizeof(uint2) * dp->n_items;
+    if (dp->n_items) CK(ctx, cudaMemcpyAsync(dp->items, ctx->h_items, sizeof(uint2) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->last_h2d_bytes = sizeof(double2) * dp->n_points + sizeof(uint2) * items.size();
     ctx->last_d2h_bytes = 0;
     return RGPU_OK;
 }
@@ -373,6 +389,8 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         std::memcpy(d.tr, in.tr, sizeof(d.tr));
         d.pts = in.path->pts;
         d.items = in.path->items;
+        d.items_packed = in.path->items_packed;
+        d.n_curves = in.path->n_curves;
         d.item_begin = item_acc;
         d.n_items = in.path->n_items;
         d.width_out = (int32_t)in.width;
@@ -474,6 +492,17 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         return RGPU_OK;
     }
 
+    // packed flatten grid: per job (n_curves << depth) curve-slot threads, then one thread per line item, padded to whole warps
+    const int cut_depth = flatten_cut_depth(item_acc);
+    uint32_t thread_acc = 0;
+    for (uint32_t j = 0; j < n_live; j++) {
+        JobDev& d = ctx->h_jobs[j];
+        d.thread_begin = thread_acc;
+        const uint64_t n = ((uint64_t)d.n_curves << cut_depth) + (d.n_items - d.n_curves);
+        if (thread_acc + ((n + 31) & ~31ull) > 0x7fffffffull) return fail(ctx, RGPU_ERR_INVALID, "batch too large");
+        thread_acc += (uint32_t)((n + 31) & ~31ull);
+    }
+
     // ---- raster path -------------------------------------------------------------------------------------------
     // fixed bins (default): [flatten + write fixed-capacity bins] -> raster               (2 launches)
     // two-pass (fallback):  [flatten + count per tile] -> scan -> [flatten + write bins] -> raster
@@ -559,7 +588,7 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     if (n_live > 1 || !fixed || n_paints) CK(ctx, cudaEventRecord(ctx->h_tables_ev, s));
     if (prof) CK(ctx, cudaEventRecord(ctx->ev[0], s));
     if (fixed) {
-        launch_flatten_bin_fixed(d_jobs, ctx->h_jobs, n_live, item_acc, thr, d_bc, d_refs, bin_cap, ts.th, ts.cw, d_status, d_status_next, s);
+        launch_flatten_bin_fixed(d_jobs, ctx->h_jobs, n_live, thread_acc, cut_depth, thr, d_bc, d_refs, bin_cap, ts.th, ts.cw, d_status, d_status_next, s);
         ctx->n_launches += 1;
         if (prof) CK(ctx, cudaEventRecord(ctx->ev[1], s));
     } else {

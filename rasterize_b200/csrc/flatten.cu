@@ -100,7 +100,8 @@ flatten_bin_kernel(const JobDev* __restrict__ jobs_in, uint32_t n_jobs, const __
         }
     }
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t total_slots = total_items << DEPTH;
+    // PASS 2 runs on the packed grid (curve slots, then one thread per line item): `total_items` is its thread count
+    const uint32_t total_slots = (PASS == 2) ? total_items : (total_items << DEPTH);
     SlotCtx c;
     uint32_t count = 0, n_refs = 0;
     auto bin_one = [&](const JobDev& job, double x0, double y0, double x1, double y1) {
@@ -130,7 +131,7 @@ flatten_bin_kernel(const JobDev* __restrict__ jobs_in, uint32_t n_jobs, const __
         if (lane == 0) q_n[warp] = 0;
         __syncwarp();
     }
-    if (t < total_slots && slot_setup<DEPTH>(jobs, n_jobs, t, thr, c, status)) {
+    if (t < total_slots && (PASS == 2 ? slot_setup_packed<DEPTH>(jobs, n_jobs, t, thr, c, status) : slot_setup<DEPTH>(jobs, n_jobs, t, thr, c, status))) {
         const JobDev& job = jobs[c.job];
         auto emit = [&](double x0, double y0, double x1, double y1) {
             if (PASS == 2) {
@@ -206,24 +207,26 @@ void launch_flatten_bin_emit(const JobDev* jobs, uint32_t n_jobs, uint32_t total
                                                           bin_lines, refs_cap, log2i(band_rows), log2i(chunk_cols), status, nullptr);
 }
 
-void launch_flatten_bin_fixed(const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t total_items, double thr,
-                              uint32_t* tile_counts, double4* bin_lines, uint32_t bin_cap, int band_rows, int chunk_cols, Status* status,
-                              Status* next_status, cudaStream_t s) {
-    if (total_items == 0) return;
-    // Few items (a scene's fills, one stroked outline): cut every subdivision tree two levels deeper, 32 slots per item —
+int flatten_cut_depth(uint32_t total_items) {
+    // Few items (a scene's fills, one stroked outline): cut every subdivision tree two levels deeper, 32 slots per curve —
     // four times the threads, each with a quarter of the subtree, because such batches are bound by the longest
     // depth-first walk, not by throughput.
-    static const uint32_t deep_max = getenv("RGPU_DEEP_CUT_ITEMS") ? (uint32_t)atoll(getenv("RGPU_DEEP_CUT_ITEMS")) : kDeepCutMaxItems;  // tuning knob
-    if (total_items <= deep_max) {
-        const uint32_t n = total_items << kDeepCutDepth;
-        flatten_bin_kernel<2, kDeepCutDepth><<<(n + 127) / 128, 128, 0, s>>>(n_jobs == 1 ? nullptr : jobs, n_jobs, h_jobs[0], total_items, thr,
-                                                                             tile_counts, nullptr, 0, bin_lines, bin_cap, log2i(band_rows),
-                                                                             log2i(chunk_cols), status, next_status);
+    return total_items <= kDeepCutMaxItems ? kDeepCutDepth : kSlotDepth;
+}
+
+void launch_flatten_bin_fixed(const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t total_threads, int depth, double thr,
+                              uint32_t* tile_counts, double4* bin_lines, uint32_t bin_cap, int band_rows, int chunk_cols, Status* status,
+                              Status* next_status, cudaStream_t s) {
+    if (total_threads == 0) return;
+    const uint32_t grid = (total_threads + 127) / 128;
+    if (depth == kDeepCutDepth) {
+        flatten_bin_kernel<2, kDeepCutDepth><<<grid, 128, 0, s>>>(n_jobs == 1 ? nullptr : jobs, n_jobs, h_jobs[0], total_threads, thr, tile_counts,
+                                                                  nullptr, 0, bin_lines, bin_cap, log2i(band_rows), log2i(chunk_cols), status,
+                                                                  next_status);
     } else {
-        const uint32_t n = total_items << kSlotDepth;
-        flatten_bin_kernel<2, kSlotDepth><<<(n + 127) / 128, 128, 0, s>>>(n_jobs == 1 ? nullptr : jobs, n_jobs, h_jobs[0], total_items, thr,
-                                                                          tile_counts, nullptr, 0, bin_lines, bin_cap, log2i(band_rows),
-                                                                          log2i(chunk_cols), status, next_status);
+        flatten_bin_kernel<2, kSlotDepth><<<grid, 128, 0, s>>>(n_jobs == 1 ? nullptr : jobs, n_jobs, h_jobs[0], total_threads, thr, tile_counts,
+                                                               nullptr, 0, bin_lines, bin_cap, log2i(band_rows), log2i(chunk_cols), status,
+                                                               next_status);
     }
 }
 

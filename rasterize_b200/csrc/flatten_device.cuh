@@ -107,7 +107,13 @@ struct SlotCtx {
     bool leaf_above;  // the subtree root is itself a leaf (the curve was flat above the depth-3 cut)
 };
 
-// Returns false when the slot produces no line.  DEPTH = level at which the subdivision tree is cut into slots.
+// Loads item `item` of `job`, transforms it and descends to the root of subtree `slot`.  Returns false when the slot
+// produces no line.  DEPTH = level at which the subdivision tree is cut into slots.
+template <int DEPTH>
+__device__ __forceinline__ bool slot_from_item(const JobDev& job, uint32_t j, const uint2 item, uint32_t slot, double thr, SlotCtx& c,
+                                               Status* __restrict__ status);
+
+// Thread t of the (item, slot) grid: items in the reference's order, 2^DEPTH slots each.
 template <int DEPTH = kSlotDepth>
 __device__ __forceinline__ bool slot_setup(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t t, double thr, SlotCtx& c,
                                            Status* __restrict__ status) {
@@ -115,7 +121,28 @@ __device__ __forceinline__ bool slot_setup(const JobDev* __restrict__ jobs, uint
     const uint32_t slot = t & ((1u << DEPTH) - 1u);
     const uint32_t j = find_job(n_jobs, g, [&](uint32_t k) { return jobs[k].item_begin; });
     const JobDev& job = jobs[j];
-    const uint2 item = job.items[g - job.item_begin];
+    return slot_from_item<DEPTH>(job, j, job.items[g - job.item_begin], slot, thr, c, status);
+}
+
+// Thread t of the PACKED grid (raster path): per job, 2^DEPTH slot threads for each of its curves, then ONE thread for
+// each line / closing item (`items_packed` holds the curves first).  Lines — most items of a typical path — no longer
+// occupy 2^DEPTH threads of which all but one exit at once, so the grid is a fraction of the (item, slot) grid.
+template <int DEPTH>
+__device__ __forceinline__ bool slot_setup_packed(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t t, double thr, SlotCtx& c,
+                                                  Status* __restrict__ status) {
+    const uint32_t j = find_job(n_jobs, t, [&](uint32_t k) { return jobs[k].thread_begin; });
+    const JobDev& job = jobs[j];
+    const uint32_t lt = t - job.thread_begin;
+    const uint32_t curve_threads = job.n_curves << DEPTH;
+    if (lt < curve_threads) return slot_from_item<DEPTH>(job, j, job.items_packed[lt >> DEPTH], lt & ((1u << DEPTH) - 1u), thr, c, status);
+    const uint32_t g = job.n_curves + (lt - curve_threads);
+    if (g >= job.n_items) return false;  // padding threads of the job's last warp
+    return slot_from_item<DEPTH>(job, j, job.items_packed[g], 0u, thr, c, status);
+}
+
+template <int DEPTH>
+__device__ __forceinline__ bool slot_from_item(const JobDev& job, uint32_t j, const uint2 item, uint32_t slot, double thr, SlotCtx& c,
+                                               Status* __restrict__ status) {
     const double* m = job.tr;
     c.job = j;
     c.leaf_above = false;

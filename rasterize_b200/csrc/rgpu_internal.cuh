@@ -54,6 +54,9 @@ struct JobDev {
     const uint2* items;
     uint32_t item_begin;   // first global item of this job
     uint32_t n_items;
+    const uint2* items_packed;  // the same items, curves first (raster path: flatten_device.cuh slot_setup_packed)
+    uint32_t n_curves;          // curve items of this job
+    uint32_t thread_begin;      // first thread of this job in the packed grid
     uint32_t band_begin;   // first global band
     uint32_t n_bands;
     uint32_t n_chunks;
@@ -99,7 +102,11 @@ void launch_flatten_bin_emit(const JobDev* jobs, uint32_t n_jobs, uint32_t total
 // bin_max) and the host re-runs with a larger capacity or with the exact two-pass scheme.
 // `h_jobs` is the host copy of the job table: a single-job batch passes its descriptor by value and `jobs` is not read.
 // `next_status` (may be NULL) is cleared for the following batch.
-void launch_flatten_bin_fixed(const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t total_items, double thr,
+// The kernel runs on the PACKED grid: `total_threads` = sum of the jobs' thread counts, job j's threads start at
+// JobDev::thread_begin = multiples of 32, (n_curves << depth) curve-slot threads then one per line item;
+// `depth` = flatten_cut_depth(total items of the batch).
+int flatten_cut_depth(uint32_t total_items);
+void launch_flatten_bin_fixed(const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t total_threads, int depth, double thr,
                               uint32_t* tile_counts, double4* bin_lines, uint32_t bin_cap, int band_rows, int chunk_cols, Status* status,
                               Status* next_status, cudaStream_t s);
 // tile geometry of the raster kernel variants
