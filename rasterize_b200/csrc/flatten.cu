@@ -21,7 +21,7 @@
 #include <cstdlib>
 
 #ifndef RGPU_FLAT_MINB
-#define RGPU_FLAT_MINB 9  // 56 registers: sweep with the per-warp leaf queue on C2 — 8 / 9 / 10 CTAs per SM -> 26.6 / 26.6 / 29.2 us
+#define RGPU_FLAT_MINB 7  // 72 registers, no spills; with the packed grid the C2 launch is ~630 CTAs (one wave at any of 5..10 CTAs per SM)
 #endif
 
 namespace rgpu {
