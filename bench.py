@@ -5,7 +5,8 @@
 
 A step is one pass of the hot path (flatten -> bin -> signed-difference raster) over one batch:
   c2 (default, BASELINE configs[1]): data/material.path fitted to 4096x4096, `Rasterizer::mask`, non-zero.
-  c4: a batch of synthetic random-cubic glyphs at 64x64 (SURVEY §8d generator), mask per glyph.
+  c4: a batch of synthetic random-cubic glyphs at 64x64 (SURVEY §8d generator), solid fill onto a fresh LinColor canvas per glyph
+      (RB_C4_MASK=1: mask per glyph).
   c5: tv.path stroked on a 32768-wide canvas, this rank's band of rows (band sharding).
   c1 / c3: Scene::render of the squirrel CLI scene (512 px) / firefox.scene (2048 x 2048) on a device-resident layer + RGBA8.
 N > 1 (under torchrun): every rank runs the same per-GPU workload on its own device with no data-path collective
@@ -158,13 +159,21 @@ def build_workload(name: str, rb, rast, rank: int, world: int, torch):
         n = int(os.environ.get("RB_GLYPHS", "20000"))
         first = rank * n
         paths = [glyph_path(rb, first + i + 1) for i in range(n)]
-        slab = torch.empty((n, 64, 64), dtype=torch.float32, device=dev)
         dps = [rast.upload(p) for p in paths]
         ident = np.array([1.0, 0, 0, 0, 1.0, 0])
-        jobs = [rb.Job(dps[i], ident, rb.FillRule.NonZero, ffi.JOB_MASK, slab.data_ptr(), 64, 64, 64, origin=i * 4096) for i in range(n)]
-        info = dict(workload=f"c4: {n} synthetic random-cubic glyphs per GPU at 64x64, mask per glyph, nonzero", canvas=[64, 64],
-                    items_per_gpu=n, pixels_per_step=n * 4096, in_bytes=sum(p.input_bytes() for p in paths), out_bytes=4 * n * 4096,
-                    keep=[dps, slab])
+        if os.environ.get("RB_C4_MASK"):  # mask-only variant (SURVEY §8d C4 "(m)": 4 B per pixel)
+            slab = torch.empty((n, 64, 64), dtype=torch.float32, device=dev)
+            jobs = [rb.Job(dps[i], ident, rb.FillRule.NonZero, ffi.JOB_MASK, slab.data_ptr(), 64, 64, 64, origin=i * 4096) for i in range(n)]
+            what, px_bytes = "Rasterizer::mask per glyph (f32 coverage)", 4
+        else:  # SURVEY §8d C4 "(s)": every glyph filled with solid black onto its own fresh LinColor canvas, 16 B per pixel
+            slab = torch.empty((n, 64, 64, 4), dtype=torch.float32, device=dev)
+            black = rb.LinColor(0.0, 0.0, 0.0, 1.0)
+            jobs = [rb.Job(dps[i], ident, rb.FillRule.NonZero, ffi.JOB_RENDER, slab.data_ptr(), 64, 64, 64, origin=i * 4096, paint=black)
+                    for i in range(n)]
+            what, px_bytes = "Rasterizer::fill with solid black onto a fresh LinColor canvas per glyph (RGPU_JOB_RENDER)", 16
+        info = dict(workload=f"c4: {n} synthetic random-cubic glyphs per GPU at 64x64, {what}, nonzero", canvas=[64, 64],
+                    items_per_gpu=n, pixels_per_step=n * 4096, in_bytes=sum(p.input_bytes() for p in paths), out_bytes=px_bytes * n * 4096,
+                    keep=[dps, slab], metric="fill throughput (Rasterizer::fill, solid paint, nonzero), pixels rasterized per second" if px_bytes == 16 else None)
         return jobs, True, info
     if name == "c5":
         path = assets.load_path("tv_stroked")
@@ -185,42 +194,33 @@ def build_workload(name: str, rb, rast, rank: int, world: int, torch):
     if name in ("c1", "c3"):
         # Scene::render of a Fill-only scene on a device-resident LinColor layer + RGBA8 export (SURVEY §8d "(s)" bytes):
         # c1 = examples/rasterize default scene for squirrel.path -w 512; c3 = firefox.scene at 2048 x 2048 (14 gradient fills)
-        import math
+        from rasterize_b200 import scene as rscene
         sc = assets.load_scene("squirrel_cli_512" if name == "c1" else "firefox_2048")
-        x0, y0, x1, y1 = sc.view
-        lx, ly = math.floor(x0), math.floor(y0)
-        W, H = math.ceil(x1) - lx, math.ceil(y1) - ly
+        _, _, W, H, _ = rscene.fixture_jobs(rast, sc, 1)
         layer = torch.empty((H, W, 4), dtype=torch.float32, device=dev)
         rgba = torch.empty((H, W, 4), dtype=torch.uint8, device=dev)
-        jobs, keep, in_bytes = [], [], 0
-        for f in sc.fills:
-            bx0, by0, bx1, by1 = f.bbox
-            col_min = max(0, min(math.floor(bx0) - lx, W))
-            col_max = max(col_min, min(math.ceil(bx1) - lx + 1, W))
-            row_min = max(0, min(math.floor(by0) - ly, H))
-            row_max = max(row_min, min(math.ceil(by1) - ly + 1, H))
-            tr = rb.Transform.new_translate(-math.floor(bx0), -math.floor(by0)) * rb.Transform.from_array(f.tr)
-            dp = rast.upload(f.path)
-            keep.append(dp)
-            in_bytes += f.path.input_bytes()
-            jobs.append(rb.Job(dp, tr, f.fill_rule, ffi.JOB_FILL, layer.data_ptr(), col_max - col_min, row_max - row_min, W,
-                               origin=row_min * W + col_min, paint=f.paint, path_bbox=f.path_bbox))
+        jobs, keep, _, _, in_bytes = rscene.fixture_jobs(rast, sc, layer.data_ptr())
         bg = sc.bg
-
-        def pre():
-            if bg is not None:
-                rast.fill_color(layer.data_ptr(), W * H, bg)
-            else:
-                rast.device_zero(layer.data_ptr(), W * H * 16)
-
-        def post():
-            rast.to_rgba8(layer.data_ptr(), rgba.data_ptr(), W * H)
-
         what = ("c1: examples/rasterize scene of data/squirrel.path at 512 px (checkerboard + fill over #f0f0f0)" if name == "c1"
                 else "c3: data/firefox.scene Scene::render at 2048x2048, 14 linear/radial gradient fills")
-        info = dict(workload=what + ", device-resident LinColor layer + RGBA8 export", canvas=[W, H], items_per_gpu=len(jobs),
-                    pixels_per_step=W * H, in_bytes=in_bytes, out_bytes=(16 + 4) * W * H, keep=[keep, layer, rgba], pre_step=pre,
-                    post_step=post, extra_launches_per_step=2)
+        info = dict(canvas=[W, H], items_per_gpu=len(jobs), pixels_per_step=W * H, in_bytes=in_bytes, out_bytes=(16 + 4) * W * H,
+                    keep=[keep, layer, rgba])
+        if os.environ.get("RB_SCENE_ORDERED"):
+            # A/B: Layer::new kernel, one raster launch per fill (ordered batch), export kernel
+            def pre():
+                if bg is not None:
+                    rast.fill_color(layer.data_ptr(), W * H, bg)
+                else:
+                    rast.device_zero(layer.data_ptr(), W * H * 16)
+
+            def post():
+                rast.to_rgba8(layer.data_ptr(), rgba.data_ptr(), W * H)
+
+            info.update(workload=what + ", device-resident LinColor layer + RGBA8 export, one launch per fill (RB_SCENE_ORDERED)", pre_step=pre,
+                        post_step=post)
+        else:
+            info.update(workload=what + ", scene compositor: Layer::new + all fills + RGBA8 export in one raster launch, LinColor layer and RGBA8 image left in HBM",
+                        scene=dict(layer=layer.data_ptr(), W=W, H=H, bg=bg, rgba=rgba.data_ptr()))
         return jobs, False, info
     raise SystemExit(f"unknown workload {name}")
 
@@ -253,7 +253,12 @@ def run_ours(args):
 
     pre_step, post_step = info.get("pre_step"), info.get("post_step")
 
+    scn = info.get("scene")
+
     def step(sync=False):
+        if scn:
+            rast.submit_scene_prepared(prepared, scn["layer"], scn["W"], scn["H"], fresh=True, bg=scn["bg"], rgba_ptr=scn["rgba"], sync=sync)
+            return
         if pre_step:
             pre_step()
         rast.submit_prepared(prepared, independent=independent, sync=sync)
@@ -318,7 +323,8 @@ def run_ours(args):
     achieved = info["out_bytes"] / raster_s / 1e9 if raster_s > 0 else 0.0
     step_alg = info["in_bytes"] + info["out_bytes"]
     roofline = {
-        "bound": "hbm", "kernel": "raster_kernel (K3: accumulate + row scan + fill rule + store)",
+        "bound": "hbm", "kernel": ("scene_kernel (K3 + K4 for every fill of the layer + Layer::new + RGBA8 export)" if scn else
+                                   "raster_kernel (K3: accumulate + row scan + fill rule + store)"),
         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "peak_source": peak_src,
         "traffic": recorded_traffic(args.workload),
         "algorithmic_bytes_per_launch": info["out_bytes"], "kernel_ms": round(float(stage_ms[2]), 5),
@@ -364,8 +370,8 @@ def run_ours(args):
 
     if rank == 0:
         out = {
-            "metric": ("scene render throughput (Scene::render fills + RGBA8 export), pixels per second" if args.workload in ("c1", "c3")
-                       else "fill throughput (Rasterizer::mask, nonzero), pixels rasterized per second"),
+            "metric": info.get("metric") or ("scene render throughput (Scene::render fills + RGBA8 export), pixels per second" if args.workload in ("c1", "c3")
+                                             else "fill throughput (Rasterizer::mask, nonzero), pixels rasterized per second"),
             "value": round(value, 1), "unit": "Mpix/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 geometry / Q7.24 fixed-point accumulation / f32 coverage",
@@ -437,18 +443,23 @@ def cpu_reference_other(workload: str, budget_s: float):
     elif workload == "c4":
         n_glyphs = 400
         glyphs = [O.OraclePath.glyph(i + 1) for i in range(n_glyphs)]
-        img = np.zeros((64, 64))
+        as_mask = bool(os.environ.get("RB_C4_MASK"))
+        img = np.zeros((64, 64)) if as_mask else np.zeros((64, 64, 4), dtype=np.float32)
+        black = O.OraclePaint.solid([0.0, 0.0, 0.0, 1.0])
         n, t0 = 0, time.perf_counter()
         while True:
             for g in glyphs:
                 img[:] = 0
-                g.mask(O.IDENTITY, O.NONZERO, img)
+                if as_mask:
+                    g.mask(O.IDENTITY, O.NONZERO, img)
+                else:
+                    g.fill(O.IDENTITY, O.NONZERO, black, img)
             n += 1
             if time.perf_counter() > t_end or n >= 20:
                 break
         dt = (time.perf_counter() - t0) / (n * n_glyphs)
         px = 4096
-        sample = f"{n} x {n_glyphs} glyph masks at 64x64 (clear + mask), {dt * 1e6:.1f} us per glyph"
+        sample = f"{n} x {n_glyphs} glyph {'masks' if as_mask else 'solid fills (clear + Rasterizer::fill)'} at 64x64, {dt * 1e6:.1f} us per glyph"
     else:  # c5
         p = assets.load_path("tv_stroked")
         c5 = assets.expected()["paths"]["tv_stroked"]["c5"]

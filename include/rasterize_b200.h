@@ -123,7 +123,11 @@ void rgpu_path_free(rgpu_ctx* ctx, rgpu_dpath* p);
 enum {
     RGPU_JOB_MASK = 0,     /* Rasterizer::mask semantics  -> f32 coverage, last column = overflow column */
     RGPU_JOB_COVERAGE = 1, /* mask_iter semantics         -> f32 coverage, (width+1) internal columns */
-    RGPU_JOB_FILL = 2      /* Rasterizer::fill semantics  -> blend paint over LinColor canvas */
+    RGPU_JOB_FILL = 2,     /* Rasterizer::fill semantics  -> blend paint over LinColor canvas */
+    RGPU_JOB_RENDER = 3    /* `ImageOwned::new_default(size)` + Rasterizer::fill: the job CREATES its LinColor window
+                              (transparent, as Layer::new without a background) and fills onto it — bit-identical to
+                              RGPU_JOB_FILL on a zeroed window, but every pixel is written once and none is read
+                              (16 B per pixel; the glyph-batch form of BASELINE config 4) */
 };
 typedef struct {
     const rgpu_dpath* path;
@@ -150,6 +154,20 @@ int rgpu_render_batch(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32
 int rgpu_batch_status(rgpu_ctx* ctx);
 /* rgpu_render_batch + rgpu_batch_status with transparent scratch growth and re-run on internal overflow. */
 int rgpu_render_batch_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags);
+/* Every Fill of one layer in ONE raster launch: the Fill arm of `Pipeline::render_rec` (src/scene.rs:397-435) for all Fill
+ * nodes drawn onto a layer, fused with `Layer::new` (src/scene.rs:483-501) and, optionally, the RGBA8 export
+ * (`From<LinColor> for RGBA`, src/color.rs:164-175).  `layer_dev` is a dense width x height LinColor device image; every
+ * job must be an RGPU_JOB_FILL whose canvas is `layer_dev` with row_stride == width (origin selects its `view_mut`
+ * window).  Jobs are blended in submission order, exactly like RGPU_BATCH_ORDERED, but a layer tile stays on the SM while
+ * all its fills are applied, so the layer is written once.
+ *   fresh != 0: the layer is created here — every pixel starts from bg (NULL = transparent), as `Layer::new` does;
+ *   fresh == 0: the fills blend over what the layer already holds.
+ * rgba_dev (may be NULL): width x height RGBA8 device image that receives the finished layer. */
+int rgpu_render_scene(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, float* layer_dev, size_t width, size_t height, int fresh,
+                      const float* bg, uint8_t* rgba_dev);
+/* rgpu_render_scene + rgpu_batch_status with transparent scratch growth and re-run on internal overflow. */
+int rgpu_render_scene_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, float* layer_dev, size_t width, size_t height, int fresh,
+                           const float* bg, uint8_t* rgba_dev);
 /* Lines produced by the flatten stage of the last completed batch, and kernels launched since create. */
 int rgpu_last_counts(rgpu_ctx* ctx, uint64_t* n_lines, uint64_t* n_line_refs, uint64_t* n_launches);
 

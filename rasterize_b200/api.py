@@ -361,7 +361,7 @@ class Job:
     path: DevicePath
     tr: object
     fill_rule: FillRule
-    mode: int           # ffi.JOB_MASK / JOB_COVERAGE / JOB_FILL
+    mode: int           # ffi.JOB_MASK / JOB_COVERAGE / JOB_FILL / JOB_RENDER
     canvas: int         # device pointer
     width: int
     height: int
@@ -531,6 +531,21 @@ class GpuRasterizer:
 
     def render_batch(self, jobs: Iterable[Job], independent: bool = False, sync: bool = True) -> None:
         self.submit_prepared(self._cjobs(jobs), independent, sync)
+
+    def submit_scene_prepared(self, prepared, layer_ptr: int, width: int, height: int, fresh: bool = True, bg=None, rgba_ptr: int = 0,
+                              sync: bool = True) -> None:
+        """All FILL jobs of one dense device layer in one raster launch (`rgpu_render_scene`): the Fill arm of
+        `Pipeline::render_rec` (src/scene.rs:397-435) fused with `Layer::new` and, with `rgba_ptr`, the RGBA8 export."""
+        arr, n, _ = prepared
+        cbg = None
+        if fresh and bg is not None:
+            cbg = (C.c_float * 4)(*[float(v) for v in bg])
+        fn = ffi.lib().rgpu_render_scene_sync if sync else ffi.lib().rgpu_render_scene
+        self._check(fn(self.ctx, arr, n, layer_ptr, int(width), int(height), 1 if fresh else 0, cbg, rgba_ptr or None))
+
+    def render_scene(self, jobs: Iterable[Job], layer_ptr: int, width: int, height: int, fresh: bool = True, bg=None, rgba_ptr: int = 0,
+                     sync: bool = True) -> None:
+        self.submit_scene_prepared(self._cjobs(jobs), layer_ptr, width, height, fresh, bg, rgba_ptr, sync)
 
     def batch_status(self) -> None:
         self._check(ffi.lib().rgpu_batch_status(self.ctx))

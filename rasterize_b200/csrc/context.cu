@@ -340,9 +340,32 @@ bool build_paint(const rgpu_job& job, PaintDev& out) {
     return true;
 }
 
-int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, int close_flag, bool ordered_lines = false) {
-    if (n_jobs == 0) return RGPU_OK;
-    if (!jobs) return fail(ctx, RGPU_ERR_INVALID, "jobs is NULL");
+// `scene` (may be NULL): the jobs are the FILL jobs of one dense layer and are composited by the scene kernel (scene.cu) in
+// one launch; n_bands / n_chunks of *scene are filled in here.
+int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, int close_flag, bool ordered_lines = false,
+           SceneArgs* scene = nullptr);
+
+// Scene batches that cannot use the scene kernel (no fixed bins: two-pass scheme forced or over budget) or have nothing to
+// fill: background, the ordered per-fill launches, export.
+int scene_fallback(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, int close_flag, const SceneArgs& sc, bool with_jobs) {
+    const size_t n = (size_t)sc.width * sc.height;
+    if (sc.fresh) {
+        launch_fill_color(sc.layer, n, make_float4(sc.bg[0], sc.bg[1], sc.bg[2], sc.bg[3]), ctx->stream);
+        ctx->n_launches += 1;
+    }
+    int rc = RGPU_OK;
+    if (with_jobs) rc = submit(ctx, jobs, n_jobs, RGPU_BATCH_ORDERED, close_flag);
+    if (rc == RGPU_OK && sc.rgba) {
+        launch_to_rgba8(sc.layer, sc.rgba, n, ctx->stream);
+        ctx->n_launches += 1;
+    }
+    return rc;
+}
+
+int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, int close_flag, bool ordered_lines, SceneArgs* scene) {
+    if (n_jobs == 0 && !scene) return RGPU_OK;
+    if (!jobs && n_jobs) return fail(ctx, RGPU_ERR_INVALID, "jobs is NULL");
+    if (scene && (ctx->two_pass || n_jobs == 0)) return scene_fallback(ctx, jobs, n_jobs, close_flag, *scene, n_jobs != 0);
     if (!(ctx->flatness > 0.0)) return fail(ctx, RGPU_ERR_INVALID, "flatness must be > 0 (the reference loops forever on 0)");
     int rc;
     if ((rc = ensure_pinned(ctx, ctx->h_jobs, ctx->h_jobs_cap, n_jobs))) return rc;
@@ -354,7 +377,7 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     uint32_t max_w = 0;
     for (size_t j = 0; j < n_jobs; j++) max_w = std::max(max_w, jobs[j].width);
     int variant = (max_w <= 128) ? 1 : 0;
-    TileShape ts = raster_tile_shape(variant);
+    TileShape ts = scene ? scene_tile_shape() : raster_tile_shape(variant);
 
     uint32_t item_acc = 0, band_acc = 0, tile_acc = 0, n_paints = 0;
     uint64_t est_lines = 0;
@@ -372,13 +395,18 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         JobDev d;
         std::memset(&d, 0, sizeof(d));
         d.paint_index = -1;
-        if (in.mode == RGPU_JOB_FILL) {
+        if (in.mode < RGPU_JOB_MASK || in.mode > RGPU_JOB_RENDER) return fail(ctx, RGPU_ERR_INVALID, "unknown job mode");
+        if (in.mode == RGPU_JOB_FILL || in.mode == RGPU_JOB_RENDER) {
             if (!in.paint) return fail(ctx, RGPU_ERR_INVALID, "fill job without a paint");
             bool same = last_paint == in.paint && last_paint_job && in.paint->kind == RGPU_PAINT_SOLID;
             if (same) {
                 d.paint_index = last_paint_index;
             } else {
-                if (!build_paint(in, ctx->h_paints[n_paints])) continue;  // silent no-op fill
+                if (!build_paint(in, ctx->h_paints[n_paints])) {  // silent no-op fill; a RENDER job still creates its window
+                    if (in.mode == RGPU_JOB_RENDER)
+                        CK(ctx, cudaMemset2DAsync(static_cast<float4*>(in.canvas) + in.origin, in.row_stride * 16, 0, (size_t)in.width * 16, in.height, ctx->stream));
+                    continue;
+                }
                 d.paint_index = (int)n_paints;
                 last_paint = in.paint;
                 last_paint_index = d.paint_index;
@@ -403,22 +431,43 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         d.canvas = in.canvas;
         d.origin = in.origin;
         d.row_stride = in.row_stride;
+        if (scene) {
+            // the job's window inside the layer: its tile grid is the layer's (see scene.cu)
+            if (in.mode != RGPU_JOB_FILL) return fail(ctx, RGPU_ERR_INVALID, "scene batches take FILL jobs only");
+            if (in.canvas != (void*)scene->layer || in.row_stride != scene->width) return fail(ctx, RGPU_ERR_INVALID, "scene job is not a window of the layer");
+            const size_t vx = in.origin % scene->width, vy = in.origin / scene->width;
+            if (vx + in.width > scene->width || vy + in.height > scene->height) return fail(ctx, RGPU_ERR_INVALID, "scene job window leaves the layer");
+            d.ox = (int32_t)(vx % ts.cw);
+            d.oy = (int32_t)(vy % ts.th);
+            d.sc0 = (int32_t)(vx / ts.cw);
+            d.sb0 = (int32_t)(vy / ts.th);
+        }
         d.band_begin = band_acc;
-        d.n_bands = (in.height + ts.th - 1) / ts.th;
-        d.n_chunks = (in.width + ts.cw - 1) / ts.cw;
+        d.n_bands = (in.height + d.oy + ts.th - 1) / ts.th;
+        d.n_chunks = (in.width + d.ox + ts.cw - 1) / ts.cw;
         d.tile_begin = tile_acc;
         item_acc += d.n_items;
         band_acc += d.n_bands;
         tile_acc += d.n_bands * d.n_chunks;
         est_lines += (uint64_t)in.path->n_curves * 24 + (in.path->n_items - in.path->n_curves) + 16;
-        all_small = all_small && small_canvas_eligible(in.width, in.height, in.mode);
+        all_small = all_small && !scene && small_canvas_eligible(in.width, in.height, in.mode);
         ctx->h_jobs[n_live++] = d;
     }
     ctx->need_lines = ctx->need_refs = 0;
     if (n_live == 0) {
         std::memset(ctx->h_status, 0, sizeof(Status));
         ctx->d_status_cur = nullptr;
+        if (scene) return scene_fallback(ctx, jobs, n_jobs, close_flag, *scene, false);
         return RGPU_OK;
+    }
+    if (!(all_small && !ordered_lines)) {
+        // RENDER on the tiled path: clear the window, then an ordinary FILL (the fused small-canvas kernel writes it once)
+        for (uint32_t k = 0; k < n_live; k++) {
+            JobDev& d = ctx->h_jobs[k];
+            if (d.mode != kModeRender) continue;
+            CK(ctx, cudaMemset2DAsync(static_cast<float4*>(d.canvas) + d.origin, d.row_stride * 16, 0, (size_t)d.width_out * 16, d.height, ctx->stream));
+            d.mode = kModeFill;
+        }
     }
     if (all_small && !ordered_lines) {
         // every canvas fits one CTA's shared memory: a single fused kernel per launch, nothing else touches HBM
@@ -517,12 +566,13 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         if ((uint64_t)bin_cap * tile_acc * sizeof(double4) > kFixedBinBudget) bin_cap = 0;
     }
     const bool fixed = bin_cap != 0;
+    if (scene && !fixed) return scene_fallback(ctx, jobs, n_jobs, close_flag, *scene, true);
     ctx->last_fixed = fixed;
     ctx->last_tiles = tile_acc;
     size_t want_refs = fixed ? (size_t)bin_cap * tile_acc : std::max<uint64_t>(ctx->refs_cap, est_lines + est_lines / 2);
     if ((rc = ensure_dev(ctx, ctx->refs, sizeof(double4) * want_refs))) return rc;
     ctx->refs_cap = std::min<size_t>(ctx->refs.cap / sizeof(double4), 0xfffffff0u);
-    const uint32_t n_raster_launches = (flags & RGPU_BATCH_INDEPENDENT) ? 1u : n_live;
+    const uint32_t n_raster_launches = ((flags & RGPU_BATCH_INDEPENDENT) || scene) ? 1u : n_live;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     // carry look-back state, validated by epoch (cleared only when (re)allocated or when the epoch wraps)
     {
@@ -583,9 +633,9 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     unsigned long long* d_state = static_cast<unsigned long long*>(ctx->tile_state.p);
 
     // a single job travels in the kernel parameters; a table is uploaded only for multi-job batches
-    if (n_live > 1 || !fixed) CK(ctx, cudaMemcpyAsync(d_jobs, ctx->h_jobs, sizeof(JobDev) * n_live, cudaMemcpyHostToDevice, s));
+    if (n_live > 1 || !fixed || scene) CK(ctx, cudaMemcpyAsync(d_jobs, ctx->h_jobs, sizeof(JobDev) * n_live, cudaMemcpyHostToDevice, s));
     if (n_paints) CK(ctx, cudaMemcpyAsync(d_paints, ctx->h_paints, sizeof(PaintDev) * n_paints, cudaMemcpyHostToDevice, s));
-    if (n_live > 1 || !fixed || n_paints) CK(ctx, cudaEventRecord(ctx->h_tables_ev, s));
+    if (n_live > 1 || !fixed || n_paints || scene) CK(ctx, cudaEventRecord(ctx->h_tables_ev, s));
     if (prof) CK(ctx, cudaEventRecord(ctx->ev[0], s));
     if (fixed) {
         launch_flatten_bin_fixed(d_jobs, ctx->h_jobs, n_live, thread_acc, cut_depth, thr, d_bc, d_refs, bin_cap, ts.th, ts.cw, d_status, d_status_next, s);
@@ -602,7 +652,12 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     static const bool no_pdl = getenv("RGPU_NO_PDL") != nullptr;  // A/B switch
     const bool pdl_ok = fixed && !prof && !no_pdl;
     const bool zero_early = est_lines + est_lines / 2 >= 2ull * tile_acc;  // most tiles will hold lines
-    if (flags & RGPU_BATCH_INDEPENDENT) {
+    if (scene) {
+        scene->n_bands = (scene->height + ts.th - 1) / ts.th;
+        scene->n_chunks = (scene->width + ts.cw - 1) / ts.cw;
+        launch_scene(d_jobs, n_live, d_paints, d_bo, bin_cap, d_refs, d_state, ctx->epoch, d_tickets, d_status, *scene, /*pdl=*/pdl_ok && item_acc != 0, s);
+        ctx->n_launches += 1;
+    } else if (flags & RGPU_BATCH_INDEPENDENT) {
         launch_raster(variant, d_jobs, ctx->h_jobs, n_live, 0, 0, tile_acc, d_paints, d_bo, bin_cap, d_refs, d_state, ctx->epoch, d_tickets, d_status, zero_early, /*pdl=*/pdl_ok ? 1 : 0, s);
         ctx->n_launches += 1;
     } else {
@@ -642,9 +697,10 @@ int check_status(rgpu_ctx* ctx) {
     return RGPU_OK;
 }
 
-int submit_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, int close_flag, bool ordered_lines = false) {
+int submit_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, int close_flag, bool ordered_lines = false,
+                SceneArgs* scene = nullptr) {
     for (int attempt = 0; attempt < 4; attempt++) {
-        int rc = submit(ctx, jobs, n_jobs, flags, close_flag, ordered_lines);
+        int rc = submit(ctx, jobs, n_jobs, flags, close_flag, ordered_lines, scene);
         if (rc) return rc;
         rc = check_status(ctx);
         if (rc != RGPU_ERR_CAPACITY) return rc;
@@ -843,6 +899,42 @@ int rgpu_render_batch_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, u
     if (!ctx) return RGPU_ERR_INVALID;
     CK(ctx, cudaSetDevice(ctx->device));
     return submit_sync(ctx, jobs, n_jobs, flags, 1);
+}
+
+static int scene_args(rgpu_ctx* ctx, float* layer_dev, size_t width, size_t height, int fresh, const float* bg, uint8_t* rgba_dev, SceneArgs& sc) {
+    if (!layer_dev) return fail(ctx, RGPU_ERR_INVALID, "layer is NULL");
+    if (width > 0x3fffffffu || height > 0x3fffffffu) return fail(ctx, RGPU_ERR_INVALID, "layer too large");
+    std::memset(&sc, 0, sizeof(sc));
+    sc.layer = reinterpret_cast<float4*>(layer_dev);
+    sc.rgba = reinterpret_cast<uchar4*>(rgba_dev);
+    sc.width = (uint32_t)width;
+    sc.height = (uint32_t)height;
+    sc.fresh = fresh != 0;
+    sc.store_lin = 1;
+    if (fresh && bg) std::memcpy(sc.bg, bg, sizeof(sc.bg));
+    return RGPU_OK;
+}
+
+int rgpu_render_scene(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, float* layer_dev, size_t width, size_t height, int fresh,
+                      const float* bg, uint8_t* rgba_dev) {
+    if (!ctx) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (width == 0 || height == 0) return RGPU_OK;
+    SceneArgs sc;
+    int rc = scene_args(ctx, layer_dev, width, height, fresh, bg, rgba_dev, sc);
+    if (rc) return rc;
+    return submit(ctx, jobs, n_jobs, RGPU_BATCH_ORDERED, 1, false, &sc);
+}
+
+int rgpu_render_scene_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, float* layer_dev, size_t width, size_t height, int fresh,
+                           const float* bg, uint8_t* rgba_dev) {
+    if (!ctx) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (width == 0 || height == 0) return RGPU_OK;
+    SceneArgs sc;
+    int rc = scene_args(ctx, layer_dev, width, height, fresh, bg, rgba_dev, sc);
+    if (rc) return rc;
+    return submit_sync(ctx, jobs, n_jobs, RGPU_BATCH_ORDERED, 1, false, &sc);
 }
 
 int rgpu_last_counts(rgpu_ctx* ctx, uint64_t* n_lines, uint64_t* n_line_refs, uint64_t* n_launches) {

@@ -360,22 +360,9 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     else scan_rows<CW, TH, THREADS, false, FILL, Cfg>(job, s_paint, cells, carry, row_touched, rowtot, row0, row1, cx0, mode, tid);
 }
 
-// `From<LinColor> for RGBA`, src/color.rs:164-175 with the x86 l2s polynomial; `as u8` saturates
-__device__ __forceinline__ unsigned char f2u8(float v) {
-    if (!(v > 0.0f)) return 0;
-    if (v >= 255.0f) return 255;
-    return (unsigned char)v;
-}
 __global__ void to_rgba8_kernel(const float4* __restrict__ lin, uchar4* __restrict__ out, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float4 c = lin[i];
-        float4 u = unmultiply(c);
-        uchar4 o;
-        o.x = f2u8(fadd(fmul(l2s_lane(u.x), 255.0f), 0.5f));
-        o.y = f2u8(fadd(fmul(l2s_lane(u.y), 255.0f), 0.5f));
-        o.z = f2u8(fadd(fmul(l2s_lane(u.z), 255.0f), 0.5f));
-        o.w = f2u8(fadd(fmul(c.w, 255.0f), 0.5f));
-        out[i] = o;
+        out[i] = lin_to_rgba8(lin[i]);
     }
 }
 __global__ void fill_color_kernel(float4* __restrict__ lin, size_t n, float4 color) {

@@ -44,6 +44,22 @@ __device__ __forceinline__ float4 into_linear(float4 c) {
     return make_float4(fmul(s2l_lane(u.x), a), fmul(s2l_lane(u.y), a), fmul(s2l_lane(u.z), a), fmul(s2l_lane(u.w), a));
 }
 
+// `From<LinColor> for RGBA`, src/color.rs:164-175 with the x86 l2s polynomial; `as u8` saturates (NaN -> 0)
+__device__ __forceinline__ unsigned char f2u8(float v) {
+    if (!(v > 0.0f)) return 0;
+    if (v >= 255.0f) return 255;
+    return (unsigned char)v;
+}
+__device__ __forceinline__ uchar4 lin_to_rgba8(float4 c) {
+    const float4 u = unmultiply(c);
+    uchar4 o;
+    o.x = f2u8(fadd(fmul(l2s_lane(u.x), 255.0f), 0.5f));
+    o.y = f2u8(fadd(fmul(l2s_lane(u.y), 255.0f), 0.5f));
+    o.z = f2u8(fadd(fmul(l2s_lane(u.z), 255.0f), 0.5f));
+    o.w = f2u8(fadd(fmul(c.w, 255.0f), 0.5f));
+    return o;
+}
+
 // f64::rem_euclid
 __device__ __forceinline__ double rem_euclid(double x, double rhs) {
     double r = fmod(x, rhs);

@@ -31,7 +31,7 @@ constexpr double kFixScale = 16777216.0;
 constexpr int kMaxStops = 32;
 constexpr int kStateRows = 16;            // rows per tile in the carry look-back state (chunked tiles have 8 rows)
 
-enum JobMode : int { kModeMask = 0, kModeCoverage = 1, kModeFill = 2 };
+enum JobMode : int { kModeMask = 0, kModeCoverage = 1, kModeFill = 2, kModeRender = 3 };
 
 struct PaintDev {
     int kind, linear_colors, spread, n_stops;
@@ -67,6 +67,9 @@ struct JobDev {
     int32_t rule, mode, close, paint_index;
     void* canvas;
     unsigned long long origin, row_stride;  // elements
+    // scene batches (scene.cu): the job's tile grid is aligned with the LAYER's tiles.  (ox, oy) = position of the job's
+    // window inside its first layer tile, (sc0, sb0) = that tile's chunk / band index in the layer.  All zero otherwise.
+    int32_t ox, oy, sc0, sb0;
 };
 
 struct Status {
@@ -79,6 +82,9 @@ struct Status {
     uint32_t bin_max;   // fixed-capacity bins: largest per-tile line count seen (> capacity => refs_overflow)
     uint32_t pad[1];
 };
+
+// tile geometry of the raster kernel variants
+struct TileShape { int cw, th; };
 
 // ---- launch wrappers (defined in the .cu files) -------------------------------------------------
 void launch_flatten_count(const JobDev* jobs, uint32_t n_jobs, uint32_t total_items, double thr, uint32_t* slot_counts,
@@ -109,8 +115,6 @@ int flatten_cut_depth(uint32_t total_items);
 void launch_flatten_bin_fixed(const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t total_threads, int depth, double thr,
                               uint32_t* tile_counts, double4* bin_lines, uint32_t bin_cap, int band_rows, int chunk_cols, Status* status,
                               Status* next_status, cudaStream_t s);
-// tile geometry of the raster kernel variants
-struct TileShape { int cw, th; };
 TileShape raster_tile_shape(int variant);
 // `ticket` is a zeroed device counter private to this launch (dynamic tile ids for the carry look-back);
 // `tile_state` holds kMaxBandRows u64 words per tile, validated by `epoch` (no clearing between batches).
@@ -126,6 +130,20 @@ TileShape raster_tile_shape(int variant);
 void launch_raster(int variant, const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
                    uint32_t n_tiles, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
                    unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, int pdl, cudaStream_t s);
+// Scene compositor (scene.cu): every FILL job of a layer in one launch, one CTA per 512 x 8 LAYER tile, fills blended in
+// submission order inside the CTA.  Jobs carry layer-aligned tile grids (JobDev::ox/oy/sc0/sb0); fixed bins only.
+struct SceneArgs {
+    float4* layer;              // dense W x H LinColor layer (row pitch = width)
+    uchar4* rgba;               // optional RGBA8 export of the finished layer (same geometry), or NULL
+    uint32_t width, height;
+    uint32_t n_bands, n_chunks; // layer tile grid
+    float bg[4];                // fresh != 0: every pixel starts from this colour (`Layer::new`), else from the layer's content
+    int fresh, store_lin;
+};
+TileShape scene_tile_shape();
+void launch_scene(const JobDev* jobs, uint32_t n_jobs, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
+                  unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, const SceneArgs& sc, bool pdl,
+                  cudaStream_t s);
 // Fused one-CTA-per-job pipeline for canvases of at most 64 x 64 visible pixels (small.cu)
 bool small_canvas_eligible(uint32_t width, uint32_t height, int mode);
 void launch_small_canvas(const JobDev* jobs, uint32_t job_first, uint32_t n_jobs, const PaintDev* paints, double thr, Status* status,
@@ -154,7 +172,8 @@ __device__ __forceinline__ void for_each_tile(const JobDev& job, double x0, doub
     const double first = floor(fmax(lo, 0.0));
     const double end = fmin(H, ceil(hi));
     if (!(first < end)) return;
-    const int b0 = (int)first >> band_shift, b1 = ((int)end - 1) >> band_shift;
+    const int oy = job.oy, ox = job.ox;
+    const int b0 = ((int)first + oy) >> band_shift, b1 = ((int)end - 1 + oy) >> band_shift;
     const int n_chunks = (int)job.n_chunks;
     if (n_chunks == 1) {
         for (int b = b0; b <= b1; b++) f(job.tile_begin + (uint32_t)b);
@@ -163,12 +182,12 @@ __device__ __forceinline__ void for_each_tile(const JobDev& job, double x0, doub
     const float fx0 = (float)x0, fy0 = (float)y0, fdxdy = (float)((x1 - x0) / (y1 - y0));
     const float fylo = (float)lo, fyhi = (float)hi, fwc = (float)job.clamp_w;
     for (int b = b0; b <= b1; b++) {
-        const float ya = fmaxf((float)(b << band_shift), fylo);
-        const float yb = fminf((float)((b + 1) << band_shift), fyhi);
+        const float ya = fmaxf((float)((b << band_shift) - oy), fylo);
+        const float yb = fminf((float)(((b + 1) << band_shift) - oy), fyhi);
         const float xa = fx0 + (ya - fy0) * fdxdy, xb = fx0 + (yb - fy0) * fdxdy;
         const float xl = fminf(fmaxf(fminf(xa, xb), 0.0f), fwc), xh = fminf(fmaxf(fmaxf(xa, xb), 0.0f), fwc);
-        int c0 = max(0, (int)(xl - 1.5f) >> chunk_shift);
-        int c1 = min(n_chunks - 1, (int)(xh + 2.5f) >> chunk_shift);
+        int c0 = max(0, (__float2int_rd(xl - 1.5f) + ox) >> chunk_shift);
+        int c1 = min(n_chunks - 1, ((int)(xh + 2.5f) + ox) >> chunk_shift);
         if (!(xl == xl) || !(xh == xh)) { c0 = 0; c1 = n_chunks - 1; }  // NaN from degenerate input: be conservative
         for (int c = c0; c <= c1; c++) f(job.tile_begin + (uint32_t)b * (uint32_t)n_chunks + (uint32_t)c);
     }

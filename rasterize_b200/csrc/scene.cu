@@ -1,0 +1,277 @@
+// Scene compositor — every Fill of a layer in ONE launch, one CTA per LAYER tile.
+//
+// Replaces the per-node loop of `Pipeline::render_rec`'s Fill arm (reference src/scene.rs:397-435: for every Fill node
+// `path.fill(rasterizer, align * tr, fill_rule, paint, layer.view_mut(..))`) together with `Layer::new`'s background
+// (src/scene.rs:483-501) and the RGBA8 export that follows `Scene::render` in every CLI run (src/color.rs:164-175).
+//
+// The ordered batch of raster.cu issues one launch per fill because fills blend in order onto one canvas.  Here the order
+// is kept INSIDE a CTA instead: a CTA owns a 512 x 8 tile of the layer, keeps its LinColor pixels in shared memory
+// (64 KB), and walks the fills in submission order — accumulate the fill's lines of this tile (same fixed-point
+// signed-difference cells as raster.cu), carry-in from the tile to the left, row scan, fill rule, `Paint::at`,
+// `with_alpha`, `blend_over` into the shared tile.  The layer is read at most once and written once, however many fills
+// overlap (SURVEY §8d "(s)" bytes: 16 B x W x H, + 4 B with the RGBA8 export), and tiles the fills do not touch cost
+// nothing but the store.
+//
+// For this the jobs' tile grids are aligned with the layer's (JobDev::ox/oy/sc0/sb0): the flatten kernel bins a line
+// into the job tiles (job, band, chunk) exactly as for raster.cu, and job tile (b, c) IS layer tile (sb0 + b, sc0 + c).
+// The carry between the chunks of a band is a chained inclusive prefix per (job, tile, row) in `tile_state`: layer tiles
+// are taken in chunk-major ticket order, so the tile a CTA waits on was started a whole column of bands earlier.
+#include "raster_device.cuh"
+
+namespace rgpu {
+
+namespace {
+
+using namespace rs;
+
+constexpr int kScW = 512, kScH = 8, kScThreads = 512, kScWarps = kScThreads / 32;
+constexpr int kScL = kScW / 32;       // columns per lane in the row scan
+constexpr int kScSpanCap = 208;       // per-warp span list (lane << 3 | row)
+using ScSpanT = unsigned char;
+constexpr size_t kScColorBytes = sizeof(float4) * kScW * kScH;
+constexpr size_t kScCellBytes = sizeof(int) * kScW * kScH;
+constexpr size_t kScPieceBytes = sizeof(double) * 4 * kScThreads;  // reused for the paint while compositing
+constexpr size_t kScSmem = kScColorBytes + kScCellBytes + kScPieceBytes + sizeof(ScSpanT) * kScSpanCap * kScWarps;
+static_assert(kScPieceBytes >= sizeof(PaintDev), "the paint is staged over the piece constants");
+
+template <bool EVENODD>
+__device__ __forceinline__ void scan_row_inplace(int* bc, int acc, int lane) {
+    int v[kScL];
+#pragma unroll
+    for (int i = 0; i < kScL / 4; i++) {
+        const int4 q = *reinterpret_cast<const int4*>(bc + swz<true>(lane * kScL + i * 4));
+        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+    }
+#pragma unroll
+    for (int i = 1; i < kScL; i++) v[i] += v[i - 1];
+    int incl = v[kScL - 1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += nb;
+    }
+    const int base = acc + incl - v[kScL - 1];
+#pragma unroll
+    for (int i = 0; i < kScL / 4; i++) {
+        const float4 cv = make_float4(coverage_from_fixed<EVENODD>(base + v[4 * i]), coverage_from_fixed<EVENODD>(base + v[4 * i + 1]),
+                                      coverage_from_fixed<EVENODD>(base + v[4 * i + 2]), coverage_from_fixed<EVENODD>(base + v[4 * i + 3]));
+        *reinterpret_cast<float4*>(bc + swz<true>(lane * kScL + i * 4)) = cv;
+    }
+}
+
+__global__ void __launch_bounds__(kScThreads, 2)
+scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* __restrict__ paints, uint32_t* __restrict__ tile_offs,
+             uint32_t bin_cap, const double4* __restrict__ bin_lines, unsigned long long* __restrict__ tile_state, uint32_t epoch,
+             uint32_t* __restrict__ ticket, const Status* status, const SceneArgs sc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* color = reinterpret_cast<float4*>(smem_raw);
+    int* cells = reinterpret_cast<int*>(smem_raw + kScColorBytes);
+    double* p_ax = reinterpret_cast<double*>(smem_raw + kScColorBytes + kScCellBytes);
+    double* p_ay = p_ax + kScThreads;
+    double* p_by = p_ay + kScThreads;
+    double* p_dxdy = p_by + kScThreads;
+    ScSpanT* spans_all = reinterpret_cast<ScSpanT*>(p_dxdy + kScThreads);
+    const PaintDev& s_paint = *reinterpret_cast<const PaintDev*>(p_ax);
+    __shared__ int carry[kScH], rowtot[kScH], row_touched[kScH], row_live[kScH];
+    __shared__ float row_const[kScH];
+    __shared__ uint32_t s_ticket, s_count, s_bad;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t n_tiles = sc.n_bands * sc.n_chunks;
+    const uint32_t t = s_ticket;
+    // chunk-major order: the left neighbour of a tile started a column of bands earlier
+    const int C = (int)(t / sc.n_bands), B = (int)(t - (uint32_t)C * sc.n_bands);
+    const int X0 = C * kScW, Y0 = B * kScH;
+    const int tw = min(kScW, (int)sc.width - X0), th = min(kScH, (int)sc.height - Y0);
+    // The tile's pixels: `Layer::new` background, or what the layer holds (fills queued after a clip / opacity group).
+    // Everything launched before the flatten kernel is complete, so this overlaps the flatten kernel's tail.
+    {
+        const float4 bg = make_float4(sc.bg[0], sc.bg[1], sc.bg[2], sc.bg[3]);
+#pragma unroll
+        for (int r = 0; r < kScH; r++) {
+            float4 c = bg;
+            if (!sc.fresh) {
+                c = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < th && tid < tw) c = sc.layer[(size_t)(Y0 + r) * sc.width + X0 + tid];
+            }
+            color[r * kScW + tid] = c;
+        }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+    if (tid == 0) {
+        const volatile uint32_t* flags = reinterpret_cast<const volatile uint32_t*>(status);
+        s_bad = flags[0] | flags[1] | flags[2] | flags[3];  // nan, depth, lines_overflow, refs_overflow
+        if (t == n_tiles - 1) *ticket = 0u;  // every ticket of this launch is drawn: leave the counter clean
+    }
+    __syncthreads();
+    if (s_bad) {
+        // the host re-runs (or reports): leave the layer as it was and the tile counters clean
+        for (uint32_t j = tid; j < n_jobs; j += kScThreads) {
+            const JobDev& job = jobs[j];
+            const int b = B - job.sb0, c = C - job.sc0;
+            if (b >= 0 && b < (int)job.n_bands && c >= 0 && c < (int)job.n_chunks) tile_offs[job.tile_begin + (uint32_t)b * job.n_chunks + (uint32_t)c] = 0u;
+        }
+        return;
+    }
+    const unsigned long long ep = (unsigned long long)epoch << 34;
+    bool dirty = sc.fresh != 0;
+    ScSpanT* spans = spans_all + warp * kScSpanCap;
+
+    for (uint32_t j = 0; j < n_jobs; j++) {
+        const JobDev& job = jobs[j];
+        const int b = B - job.sb0, c = C - job.sc0;
+        if (b < 0 || b >= (int)job.n_bands || c < 0 || c >= (int)job.n_chunks) continue;  // uniform for the CTA
+        const uint32_t tile = job.tile_begin + (uint32_t)b * job.n_chunks + (uint32_t)c;
+        const bool chained = job.n_chunks > 1;
+        if (tid == 0) {
+            s_count = min(tile_offs[tile], bin_cap);
+            tile_offs[tile] = 0u;  // self-cleaning counters, as in raster.cu
+        }
+        if (tid < kScH) {
+            int cin = 0;
+            if (c > 0) {  // inclusive prefix of the job's tile to the left (published by the CTA of layer tile (B, C - 1))
+                const unsigned long long* ps = tile_state + (size_t)(tile - 1u) * kStateRows + tid;
+                unsigned long long v;
+                do { v = ld_state(ps); } while ((uint32_t)(v >> 34) != epoch || (v & (3ull << 32)) != kFlagPrefix);
+                cin = (int)(uint32_t)v;
+            }
+            carry[tid] = cin;
+            rowtot[tid] = 0;
+            row_touched[tid] = 0;
+        }
+        __syncthreads();
+        const uint32_t cnt = s_count;
+        if (cnt == 0) {
+            int any = 0;
+#pragma unroll
+            for (int r = 0; r < kScH; r++) any |= carry[r];
+            if (tid < kScH && chained) st_state(tile_state + (size_t)tile * kStateRows + tid, ep | kFlagPrefix | (unsigned long long)(uint32_t)carry[tid]);
+            if (!any) {  // the fill's window covers this tile, its geometry does not
+                __syncthreads();
+                continue;
+            }
+        }
+        TileGeom g;
+        g.row0 = b * kScH - job.oy;  // job rows of this tile: may start above the window (rows < 0 hold nothing)
+        g.row1 = min(g.row0 + kScH, job.height);
+        g.cx0 = c * kScW - job.ox;   // likewise for columns
+        g.wc = job.clamp_w;
+        g.wci = (int)g.wc;
+        g.tile_end = min(g.cx0 + kScW, g.wci + 1);
+        g.pitch = kScW;
+        if (cnt) {
+            {
+                const int4 z = make_int4(0, 0, 0, 0);
+                int4* c4 = reinterpret_cast<int4*>(cells);
+#pragma unroll
+                for (int i = tid; i < kScH * kScW / 4; i += kScThreads) c4[i] = z;
+            }
+            __syncthreads();
+            const uint32_t rbeg = tile * bin_cap, rend = rbeg + cnt;
+            const uint32_t per = (cnt + kScWarps - 1) / kScWarps;
+            const uint32_t wbeg = rbeg + (uint32_t)warp * per, wend = min(wbeg + per, rend);
+            for (uint32_t r0 = wbeg; r0 < wend; r0 += 32) {
+                const uint32_t r = r0 + lane;
+                const bool valid = r < wend;
+                const double4 l = valid ? bin_lines[r] : make_double4(0, 0, 0, 0);
+                warp_accumulate_round<true, 3, kScSpanCap, ScSpanT>(l, valid, g, cells, rowtot, row_touched, p_ax, p_ay, p_by, p_dxdy, spans, tid);
+            }
+            __syncthreads();
+            if (tid < kScH && chained)
+                st_state(tile_state + (size_t)tile * kStateRows + tid, ep | kFlagPrefix | (unsigned long long)(uint32_t)(carry[tid] + rowtot[tid]));
+        }
+        // the piece constants are dead: stage the paint over them
+        if (job.paint_index >= 0) {
+            const int* src = reinterpret_cast<const int*>(&paints[job.paint_index]);
+            int* dst = reinterpret_cast<int*>(p_ax);
+            for (int i = tid; i < (int)(sizeof(PaintDev) / 4); i += kScThreads) dst[i] = src[i];
+        }
+        // row scan + fill rule: one warp per row; coverage stays in the cells (as floats) for the compositing pass
+        if (warp < kScH) {
+            const int r = warp;
+            const int acc = carry[r];
+            if (row_touched[r]) {
+                if (job.rule == 1) scan_row_inplace<true>(cells + r * kScW, acc, lane);
+                else scan_row_inplace<false>(cells + r * kScW, acc, lane);
+                if (lane == 0) row_live[r] = 1;
+            } else if (lane == 0) {  // no line touched this row of the tile: constant coverage
+                const float cv = (job.rule == 1) ? coverage_from_fixed<true>(acc) : coverage_from_fixed<false>(acc);
+                row_const[r] = cv;
+                row_live[r] = cv >= 1e-6f;
+            }
+        }
+        __syncthreads();
+        // paint + composite (src/rasterize.rs:103-115): thread = layer column, the tile's 8 rows in turn
+        {
+            const int x = g.cx0 + tid;
+            const float* covs = reinterpret_cast<const float*>(cells);
+            if (x >= 0 && x < job.width_out) {
+                const int sx = swz<true>(tid);
+#pragma unroll 1
+                for (int r = 0; r < kScH; r++) {
+                    const int y = g.row0 + r;
+                    if (y < 0 || y >= g.row1 || !row_live[r]) continue;
+                    const float alpha = row_touched[r] ? covs[r * kScW + sx] : row_const[r];
+                    if (alpha >= 1e-6f) {  // mask_iter drops abs(alpha) < 1e-6, src/rasterize.rs:348
+                        float4 cl = (job.paint_index >= 0) ? paint_at(s_paint, x, y) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        // with_alpha: self * (alpha as f32), src/color.rs:347-349
+                        cl = make_float4(fmul(cl.x, alpha), fmul(cl.y, alpha), fmul(cl.z, alpha), fmul(cl.w, alpha));
+                        // blend_over: other + self * (1 - other.alpha), src/color.rs:342-344
+                        float4 d = color[r * kScW + tid];
+                        const float k = fsub(1.0f, cl.w);
+                        d = make_float4(fadd(cl.x, fmul(d.x, k)), fadd(cl.y, fmul(d.y, k)), fadd(cl.z, fmul(d.z, k)), fadd(cl.w, fmul(d.w, k)));
+                        color[r * kScW + tid] = d;
+                    }
+                }
+            }
+        }
+        dirty = true;
+        __syncthreads();
+    }
+
+    // ---- the tile leaves the SM once: LinColor and / or RGBA8, coalesced rows ----
+    if (tid < tw) {
+        for (int r = 0; r < th; r++) {
+            const float4 c = color[r * kScW + tid];  // only this thread wrote it
+            const size_t o = (size_t)(Y0 + r) * sc.width + X0 + tid;
+            if (dirty && sc.store_lin) sc.layer[o] = c;
+            if (sc.rgba) sc.rgba[o] = lin_to_rgba8(c);
+        }
+    }
+}
+
+}  // namespace
+
+TileShape scene_tile_shape() { return TileShape{kScW, kScH}; }
+
+void launch_scene(const JobDev* jobs, uint32_t n_jobs, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
+                  unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, const SceneArgs& sc, bool pdl,
+                  cudaStream_t s) {
+    const uint32_t n_tiles = sc.n_bands * sc.n_chunks;
+    if (n_tiles == 0) return;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaFuncSetAttribute(scene_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScSmem);
+        cudaFuncSetAttribute(scene_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured[dev] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_tiles);
+    cfg.blockDim = dim3(kScThreads);
+    cfg.dynamicSmemBytes = kScSmem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, scene_kernel, jobs, n_jobs, paints, tile_offs, bin_cap, bin_lines, tile_state, epoch, ticket, status, sc);
+}
+
+}  // namespace rgpu

@@ -53,7 +53,8 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
         for (int i = tid; i < kSmMaxH * kSmPitch / 4; i += kSmThreads) c4[i] = z;
     }
     if (tid < kSmMaxH) { rowtot[tid] = 0; row_touched[tid] = 0; }
-    if (mode == kModeFill && job.paint_index >= 0) {
+    const bool render = mode == kModeRender;  // fill onto a canvas created here: every pixel is written, none is read
+    if (mode >= kModeFill && job.paint_index >= 0) {
         const int* src = reinterpret_cast<const int*>(&paints[job.paint_index]);
         int* dst = reinterpret_cast<int*>(&s_paint);
         for (int i = tid; i < (int)(sizeof(PaintDev) / 4); i += kSmThreads) dst[i] = src[i];
@@ -140,7 +141,7 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
             cv = make_float4(coverage_from_fixed<false>(base + p0), coverage_from_fixed<false>(base + p1),
                              coverage_from_fixed<false>(base + p2), coverage_from_fixed<false>(base + p3));
         const int col = hl * 4;
-        if (mode != kModeFill) {
+        if (mode < kModeFill) {
             if (rvalid) {
                 if (mode == kModeCoverage) {  // mask_iter drops abs(alpha) < 1e-6 (src/rasterize.rs:348)
                     if (cv.x < 1e-6f) cv.x = 0.f;
@@ -168,15 +169,17 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
                 const int rr = r2 + (pidx >> 6), px = pidx & 63;
                 if (rr < hout && px < wout) {
                     const float alpha = reinterpret_cast<const float*>(cells + rr * kSmPitch)[px];
+                    float4* out = reinterpret_cast<float4*>(job.canvas) + job.origin + (unsigned long long)rr * job.row_stride;
                     if (alpha >= 1e-6f) {
-                        float4* out = reinterpret_cast<float4*>(job.canvas) + job.origin + (unsigned long long)rr * job.row_stride;
                         float4 color = (job.paint_index >= 0) ? paint_at(s_paint, px, rr) : make_float4(0.f, 0.f, 0.f, 0.f);
                         color = make_float4(fmul(color.x, alpha), fmul(color.y, alpha), fmul(color.z, alpha), fmul(color.w, alpha));
-                        float4 dstc = out[px];
+                        float4 dstc = render ? make_float4(0.f, 0.f, 0.f, 0.f) : out[px];  // `Layer::new`: transparent
                         const float k = fsub(1.0f, color.w);
                         dstc = make_float4(fadd(color.x, fmul(dstc.x, k)), fadd(color.y, fmul(dstc.y, k)), fadd(color.z, fmul(dstc.z, k)),
                                            fadd(color.w, fmul(dstc.w, k)));
-                        out[px] = dstc;
+                        if (render) __stcs(out + px, dstc); else out[px] = dstc;
+                    } else if (render) {
+                        __stcs(out + px, make_float4(0.f, 0.f, 0.f, 0.f));
                     }
                 }
             }

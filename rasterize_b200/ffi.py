@@ -12,7 +12,7 @@ PKG = _P(__file__).resolve().parent
 LIB_PATH = PKG / "librasterize_b200.so"
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NAN, ERR_DEPTH, ERR_CAPACITY = 0, -1, -2, -3, -4, -5
-JOB_MASK, JOB_COVERAGE, JOB_FILL = 0, 1, 2
+JOB_MASK, JOB_COVERAGE, JOB_FILL, JOB_RENDER = 0, 1, 2, 3
 BATCH_ORDERED, BATCH_INDEPENDENT = 0, 1
 MAX_STOPS = 32
 
@@ -58,7 +58,7 @@ _lib = None
 SYMBOLS = [
     "rgpu_create", "rgpu_destroy", "rgpu_name", "rgpu_last_error", "rgpu_device_count", "rgpu_flatten", "rgpu_mask",
     "rgpu_mask_f32", "rgpu_mask_iter", "rgpu_coverage_f32", "rgpu_fill", "rgpu_path_upload", "rgpu_path_free",
-    "rgpu_render_batch", "rgpu_batch_status", "rgpu_render_batch_sync", "rgpu_last_counts", "rgpu_last_transfer_bytes", "rgpu_set_profiling",
+    "rgpu_render_batch", "rgpu_batch_status", "rgpu_render_batch_sync", "rgpu_render_scene", "rgpu_render_scene_sync", "rgpu_last_counts", "rgpu_last_transfer_bytes", "rgpu_set_profiling",
     "rgpu_last_stage_ms", "rgpu_to_rgba8_dev", "rgpu_layer_scale_by_mask_dev", "rgpu_layer_blend_over_dev", "rgpu_download_rgba8",
     "rgpu_fill_color_dev", "rgpu_stream", "rgpu_sync", "rgpu_device_alloc", "rgpu_device_free", "rgpu_device_zero",
     "rgpu_memcpy_h2d", "rgpu_memcpy_d2h", "rgpu_host_alloc", "rgpu_host_free",
@@ -98,6 +98,8 @@ def lib():
     sig("rgpu_render_batch", i32, vp, C.POINTER(CJob), sz, u32)
     sig("rgpu_batch_status", i32, vp)
     sig("rgpu_render_batch_sync", i32, vp, C.POINTER(CJob), sz, u32)
+    sig("rgpu_render_scene", i32, vp, C.POINTER(CJob), sz, vp, sz, sz, i32, pf, vp)
+    sig("rgpu_render_scene_sync", i32, vp, C.POINTER(CJob), sz, vp, sz, sz, i32, pf, vp)
     sig("rgpu_last_counts", i32, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
     sig("rgpu_last_transfer_bytes", i32, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
     sig("rgpu_set_profiling", i32, vp, i32)

@@ -5,7 +5,9 @@ bounding boxes; here loaded from a fixture or built by the caller) and the recur
 every pixel operation runs on the GPU and every layer lives in HBM:
 
   Fill     -> one FILL job on a window of the current layer (the `view_mut` sub-image of src/scene.rs:412-429); the
-              consecutive fills of a layer are submitted as ONE ordered batch
+              consecutive fills of a layer go to the scene compositor (`rgpu_render_scene`): ONE raster launch in which every
+              layer tile stays on its SM while all its fills are blended in order, fused with `Layer::new`'s background
+              and, for the root, the RGBA8 export (RGPU_SCENE_ORDERED=1 selects the one-launch-per-fill ordered batch)
   Opacity  -> child rendered into its own device layer, `rgpu_layer_blend_over_dev(.., opacity)`
   Clip     -> clip path rasterized with `Rasterizer::mask` semantics into an f32 device layer, child layer scaled by it
               (`rgpu_layer_scale_by_mask_dev`) and blended over the parent
@@ -15,6 +17,7 @@ The only transfer is the final download (LinColor or RGBA8).
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -86,10 +89,14 @@ class DeviceLayer:
         self.channels = channels
         n = self.width * self.height
         self.ptr = rast.device_alloc(max(1, n * channels * 4))
-        if color is not None:
-            rast.fill_color(self.ptr, n, color)
-        else:
-            rast.device_zero(self.ptr, n * channels * 4)
+        # a colour layer is materialised by its first flush (`Layer::new` is fused into the scene kernel)
+        self.fresh = channels == 4 and n > 0 and not os.environ.get("RGPU_SCENE_ORDERED")
+        self.bg = color
+        if not self.fresh:
+            if color is not None:
+                rast.fill_color(self.ptr, n, color)
+            else:
+                rast.device_zero(self.ptr, n * channels * 4)
         self.pending: list = []  # FILL jobs not yet submitted (kept alive with their device paths)
         self.keep: list = []
 
@@ -98,12 +105,20 @@ class DeviceLayer:
             self.rast.device_free(self.ptr)
             self.ptr = 0
 
-    def flush(self):
-        """Submit the fills queued on this layer as one ordered batch (they may overlap: composited in order).  The
-        synchronous entry point is used so that an internal scratch overflow is retried before anything is composited on top."""
-        if self.pending:
-            self.rast.render_batch(self.pending, independent=False, sync=True)
+    def flush(self, rgba_ptr: int = 0):
+        """Submit the fills queued on this layer (they may overlap: composited in order).  The synchronous entry point is
+        used so that an internal scratch overflow is retried before anything is composited on top.  `rgba_ptr`: device
+        RGBA8 image that receives the layer as it stands after these fills."""
+        if os.environ.get("RGPU_SCENE_ORDERED") or self.channels != 4:
+            if self.pending:
+                self.rast.render_batch(self.pending, independent=False, sync=True)
+                self.pending = []
+            return
+        if self.pending or self.fresh or rgba_ptr:
+            if self.width and self.height:
+                self.rast.render_scene(self.pending, self.ptr, self.width, self.height, fresh=self.fresh, bg=self.bg, rgba_ptr=rgba_ptr, sync=True)
             self.pending = []
+            self.fresh = False
 
     def intersect(self, other: "DeviceLayer"):
         """Intersection rectangle of `Layer::compose` (src/scene.rs:540-549): (self origin, other origin, w, h)."""
@@ -158,12 +173,13 @@ def _render_rec(rast: GpuRasterizer, nodes, node_id: int, layer: DeviceLayer, tr
         raise ValueError(f"unknown pipeline node kind {node.kind}")
 
 
-def _render_node(rast, nodes, node_id, view, bg, trash) -> DeviceLayer:
+def _render_node(rast, nodes, node_id, view, bg, trash, flush: bool = True) -> DeviceLayer:
     """`Pipeline::render` (src/scene.rs:384-395): a fresh layer over `view` (or the node's bbox), then the node."""
     layer = DeviceLayer(rast, view if view is not None else nodes[node_id].bbox, 4, bg)
     trash.append(layer)
     _render_rec(rast, nodes, node_id, layer, trash)
-    layer.flush()
+    if flush:
+        layer.flush()
     return layer
 
 
@@ -174,7 +190,19 @@ def render(rast: GpuRasterizer, pipeline: Pipeline, rgba: bool = False):
     try:
         if not pipeline.nodes:
             return 0, 0, np.zeros((0, 0, 4), dtype=np.uint8 if rgba else np.float32)
-        root = _render_node(rast, pipeline.nodes, len(pipeline.nodes) - 1, pipeline.view, pipeline.bg, trash)
+        root = _render_node(rast, pipeline.nodes, len(pipeline.nodes) - 1, pipeline.view, pipeline.bg, trash, flush=False)
+        if rgba and root.width and root.height and not os.environ.get("RGPU_SCENE_ORDERED"):
+            # export fused into the root's last fill launch; 4 B / pixel cross PCIe
+            n = root.width * root.height
+            rgba_ptr = rast.device_alloc(n * 4)
+            try:
+                root.flush(rgba_ptr)
+                img = rast.to_host(rgba_ptr, (root.height, root.width, 4), np.uint8)
+            finally:
+                rast.device_free(rgba_ptr)
+            rast.batch_status()
+            return root.x, root.y, img
+        root.flush()
         if rgba:
             img = rast.download_rgba8(root.ptr, (root.height, root.width))
         else:
@@ -185,3 +213,25 @@ def render(rast: GpuRasterizer, pipeline: Pipeline, rgba: bool = False):
         rast.sync()
         for l in trash:
             l.free()
+
+
+def fixture_jobs(rast: GpuRasterizer, sc, layer_ptr: int):
+    """FILL jobs of a Fill-only scene fixture (`assets.load_scene`) on a dense layer over the scene's view, exactly as the
+    Fill arm of `Pipeline::render_rec` sets them up (src/scene.rs:407-430).  Returns (jobs, device paths, W, H, input bytes)."""
+    x0, y0, x1, y1 = sc.view
+    lx, ly = math.floor(x0), math.floor(y0)
+    W, H = math.ceil(x1) - lx, math.ceil(y1) - ly
+    jobs, keep, in_bytes = [], [], 0
+    for f in sc.fills:
+        bx0, by0, bx1, by1 = f.bbox
+        col_min = max(0, min(math.floor(bx0) - lx, W))
+        col_max = max(col_min, min(math.ceil(bx1) - lx + 1, W))
+        row_min = max(0, min(math.floor(by0) - ly, H))
+        row_max = max(row_min, min(math.ceil(by1) - ly + 1, H))
+        tr = Transform.new_translate(-math.floor(bx0), -math.floor(by0)) * Transform.from_array(f.tr)
+        dp = rast.upload(f.path)
+        keep.append(dp)
+        in_bytes += f.path.input_bytes()
+        jobs.append(Job(dp, tr, f.fill_rule, ffi.JOB_FILL, layer_ptr, col_max - col_min, row_max - row_min, W,
+                        origin=row_min * W + col_min, paint=f.paint, path_bbox=f.path_bbox))
+    return jobs, keep, W, H, in_bytes

@@ -151,3 +151,34 @@ def test_prepared_batch_resubmission_is_stable(rast):
     b = rast.to_host(canvas, (h, w), np.float32)
     assert np.array_equal(a, b)
     rast.device_free(canvas)
+
+
+def test_render_jobs_create_their_canvas(rast):
+    """RGPU_JOB_RENDER (`ImageOwned::new_default` + `Rasterizer::fill`) is bit-identical to RGPU_JOB_FILL on a zeroed
+    canvas, whatever the canvas held before: fused small-canvas kernel (64x64 glyphs) and tiled path (300x200)."""
+    n = 65
+    glyphs = [bench.glyph_path(rb, i + 1) for i in range(n)]
+    dps = [rast.upload(g) for g in glyphs]
+    ident = rb.Transform.identity()
+    paint = rb.LinColor(0.1, 0.2, 0.3, 0.6)
+    for w, h, tr in ((64, 64, ident), (300, 200, rb.Transform.new_scale(300 / 64.0, 200 / 64.0))):
+        nb = n * w * h * 16
+        slab = rast.device_alloc(nb)
+        rast.device_zero(slab, nb)
+        jobs = [rb.Job(dps[i], tr, rb.FillRule(i % 2), ffi.JOB_FILL, slab, w, h, w, origin=i * w * h, paint=paint) for i in range(n)]
+        rast.render_batch(jobs, independent=True)
+        want = rast.to_host(slab, (n, h, w, 4), np.float32)
+        rast.to_device(slab, np.full((n, h, w, 4), 3.0, dtype=np.float32))  # garbage the job must not read
+        jobs = [rb.Job(dps[i], tr, rb.FillRule(i % 2), ffi.JOB_RENDER, slab, w, h, w, origin=i * w * h, paint=paint) for i in range(n)]
+        rast.render_batch(jobs, independent=True)
+        got = rast.to_host(slab, (n, h, w, 4), np.float32)
+        assert np.array_equal(got, want)
+        assert got.any()
+        rast.device_free(slab)
+    # an empty path still creates (clears) its canvas
+    slab = rast.device_alloc(64 * 64 * 16)
+    rast.to_device(slab, np.full((64, 64, 4), 3.0, dtype=np.float32))
+    empty = rast.upload(rb.Path.empty())
+    rast.render_batch([rb.Job(empty, ident, rb.FillRule.NonZero, ffi.JOB_RENDER, slab, 64, 64, 64, paint=paint)], independent=True)
+    assert not rast.to_host(slab, (64, 64, 4), np.float32).any()
+    rast.device_free(slab)
