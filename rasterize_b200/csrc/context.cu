@@ -85,6 +85,12 @@ struct rgpu_ctx {
     DevBuf fixed_block;            // [status A | status B | tickets | tile counters], self-cleaning (see submit)
     uint32_t fx_tickets_cap = 0, fx_tiles_cap = 0, fx_parity = 0;
     cudaEvent_t h_tables_ev = nullptr;  // completion of the last upload out of h_jobs / h_paints
+    // what the device job / paint tables hold: a batch that is submitted again (the steady state of a render loop) finds
+    // its tables already in HBM and uploads nothing
+    struct TableShadow {
+        std::vector<unsigned char> bytes;
+        const void* dev = nullptr;
+    } jobs_shadow, paints_shadow;
     uint32_t last_tiles = 0;
     // pinned host
     Status* h_status = nullptr;
@@ -154,6 +160,16 @@ int ensure_pinned(rgpu_ctx* ctx, T*& p, size_t& cap, size_t count) {
     }
     CK(ctx, cudaMallocHost(reinterpret_cast<void**>(&p), want * sizeof(T)));
     cap = want;
+    return RGPU_OK;
+}
+
+// Copy a host table to its device buffer unless the buffer already holds exactly these bytes.
+int upload_table(rgpu_ctx* ctx, rgpu_ctx::TableShadow& sh, void* dev, const void* host, size_t bytes, bool& uploaded) {
+    if (sh.dev == dev && sh.bytes.size() == bytes && std::memcmp(sh.bytes.data(), host, bytes) == 0) return RGPU_OK;
+    CK(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    sh.bytes.assign(static_cast<const unsigned char*>(host), static_cast<const unsigned char*>(host) + bytes);
+    sh.dev = dev;
+    uploaded = true;
     return RGPU_OK;
 }
 
@@ -398,7 +414,9 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         if (in.mode < RGPU_JOB_MASK || in.mode > RGPU_JOB_RENDER) return fail(ctx, RGPU_ERR_INVALID, "unknown job mode");
         if (in.mode == RGPU_JOB_FILL || in.mode == RGPU_JOB_RENDER) {
             if (!in.paint) return fail(ctx, RGPU_ERR_INVALID, "fill job without a paint");
-            bool same = last_paint == in.paint && last_paint_job && in.paint->kind == RGPU_PAINT_SOLID;
+            // a solid paint is its colour: consecutive jobs with the same colour share one table entry
+            bool same = last_paint_job && in.paint->kind == RGPU_PAINT_SOLID && last_paint->kind == RGPU_PAINT_SOLID &&
+                        (last_paint == in.paint || std::memcmp(last_paint->solid, in.paint->solid, sizeof(in.paint->solid)) == 0);
             if (same) {
                 d.paint_index = last_paint_index;
             } else {
@@ -477,9 +495,10 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         JobDev* d_jobs = static_cast<JobDev*>(ctx->jobs.p);
         PaintDev* d_paints = static_cast<PaintDev*>(ctx->paints.p);
         Status* d_status = static_cast<Status*>(ctx->status.p);
-        CK(ctx, cudaMemcpyAsync(d_jobs, ctx->h_jobs, sizeof(JobDev) * n_live, cudaMemcpyHostToDevice, s));
-        if (n_paints) CK(ctx, cudaMemcpyAsync(d_paints, ctx->h_paints, sizeof(PaintDev) * n_paints, cudaMemcpyHostToDevice, s));
-        CK(ctx, cudaEventRecord(ctx->h_tables_ev, s));
+        bool uploaded = false;
+        if ((rc = upload_table(ctx, ctx->jobs_shadow, d_jobs, ctx->h_jobs, sizeof(JobDev) * n_live, uploaded))) return rc;
+        if (n_paints && (rc = upload_table(ctx, ctx->paints_shadow, d_paints, ctx->h_paints, sizeof(PaintDev) * n_paints, uploaded))) return rc;
+        if (uploaded) CK(ctx, cudaEventRecord(ctx->h_tables_ev, s));
         CK(ctx, cudaMemsetAsync(d_status, 0, sizeof(Status), s));
         const double thr = 16.0 * ctx->flatness * ctx->flatness;  // PathFlattenIter::new, src/path.rs:749
         const bool prof = ctx->profiling;
@@ -528,8 +547,9 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         Status* d_status = static_cast<Status*>(ctx->status.p);
         uint32_t* d_counts = static_cast<uint32_t*>(ctx->slot_counts.p);
         uint32_t* d_offs = static_cast<uint32_t*>(ctx->slot_offs.p);
-        CK(ctx, cudaMemcpyAsync(d_jobs, ctx->h_jobs, sizeof(JobDev) * n_live, cudaMemcpyHostToDevice, s));
-        CK(ctx, cudaEventRecord(ctx->h_tables_ev, s));
+        bool uploaded = false;
+        if ((rc = upload_table(ctx, ctx->jobs_shadow, d_jobs, ctx->h_jobs, sizeof(JobDev) * n_live, uploaded))) return rc;
+        if (uploaded) CK(ctx, cudaEventRecord(ctx->h_tables_ev, s));
         CK(ctx, cudaMemsetAsync(d_status, 0, sizeof(Status), s));
         launch_flatten_count(d_jobs, n_live, item_acc, thr, d_counts, d_status, s);
         launch_exclusive_scan(d_counts, d_offs, total_slots + 1, ctx->scan_temp.p, ctx->scan_temp.cap, s);
@@ -633,9 +653,12 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     unsigned long long* d_state = static_cast<unsigned long long*>(ctx->tile_state.p);
 
     // a single job travels in the kernel parameters; a table is uploaded only for multi-job batches
-    if (n_live > 1 || !fixed || scene) CK(ctx, cudaMemcpyAsync(d_jobs, ctx->h_jobs, sizeof(JobDev) * n_live, cudaMemcpyHostToDevice, s));
-    if (n_paints) CK(ctx, cudaMemcpyAsync(d_paints, ctx->h_paints, sizeof(PaintDev) * n_paints, cudaMemcpyHostToDevice, s));
-    if (n_live > 1 || !fixed || n_paints || scene) CK(ctx, cudaEventRecord(ctx->h_tables_ev, s));
+    {
+        bool uploaded = false;
+        if ((n_live > 1 || !fixed || scene) && (rc = upload_table(ctx, ctx->jobs_shadow, d_jobs, ctx->h_jobs, sizeof(JobDev) * n_live, uploaded))) return rc;
+        if (n_paints && (rc = upload_table(ctx, ctx->paints_shadow, d_paints, ctx->h_paints, sizeof(PaintDev) * n_paints, uploaded))) return rc;
+        if (uploaded) CK(ctx, cudaEventRecord(ctx->h_tables_ev, s));
+    }
     if (prof) CK(ctx, cudaEventRecord(ctx->ev[0], s));
     if (fixed) {
         launch_flatten_bin_fixed(d_jobs, ctx->h_jobs, n_live, thread_acc, cut_depth, thr, d_bc, d_refs, bin_cap, ts.th, ts.cw, d_status, d_status_next, s);

@@ -37,9 +37,18 @@ __device__ __forceinline__ float4 unmultiply(float4 c) {
     if (c.w == 1.0f) return c;  // x / 1 == x exactly: opaque colours (the usual gradient stop) skip four divisions
     return make_float4(__fdiv_rn(c.x, c.w), __fdiv_rn(c.y, c.w), __fdiv_rn(c.z, c.w), __fdiv_rn(c.w, c.w));
 }
+// The same inside `Paint::at` (per covered pixel of every gradient fill): one correctly rounded reciprocal instead of four
+// IEEE divisions.  The quotients may differ from x / a in the last bit (1e-7 relative, against a 2e-4 budget); a / a is 1
+// either way.  The RGBA8 export keeps the exact divisions (bit-exact conversion of a given LinColor image).
+__device__ __forceinline__ float4 unmultiply_rcp(float4 c) {
+    if (c.w <= 1e-6f) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c.w == 1.0f) return c;
+    const float inv = __frcp_rn(c.w);
+    return make_float4(fmul(c.x, inv), fmul(c.y, inv), fmul(c.z, inv), 1.0f);
+}
 // LinColor::into_linear, src/color.rs:330-332 (all four lanes go through the polynomial, alpha included)
 __device__ __forceinline__ float4 into_linear(float4 c) {
-    float4 u = unmultiply(c);
+    float4 u = unmultiply_rcp(c);
     float a = c.w;
     return make_float4(fmul(s2l_lane(u.x), a), fmul(s2l_lane(u.y), a), fmul(s2l_lane(u.z), a), fmul(s2l_lane(u.w), a));
 }

@@ -18,23 +18,33 @@
 // are taken in chunk-major ticket order, so the tile a CTA waits on was started a whole column of bands earlier.
 #include "raster_device.cuh"
 
+#include <cstdlib>
+
 namespace rgpu {
 
 namespace {
 
 using namespace rs;
 
-constexpr int kScW = 512, kScH = 8, kScThreads = 512, kScWarps = kScThreads / 32;
-constexpr int kScL = kScW / 32;       // columns per lane in the row scan
+constexpr int kScH = 8, kScThreads = 512, kScWarps = kScThreads / 32;
 constexpr int kScSpanCap = 208;       // per-warp span list (lane << 3 | row)
 using ScSpanT = unsigned char;
-constexpr size_t kScColorBytes = sizeof(float4) * kScW * kScH;
-constexpr size_t kScCellBytes = sizeof(int) * kScW * kScH;
-constexpr size_t kScPieceBytes = sizeof(double) * 4 * kScThreads;  // reused for the paint while compositing
-constexpr size_t kScSmem = kScColorBytes + kScCellBytes + kScPieceBytes + sizeof(ScSpanT) * kScSpanCap * kScWarps;
-static_assert(kScPieceBytes >= sizeof(PaintDev), "the paint is staged over the piece constants");
+constexpr size_t kScPieceBytes = sizeof(double) * 4 * kScThreads;  // reused for the paint + the covered-pixel list while compositing
+constexpr size_t kScPaintBytes = 2048;                              // the paint sits at the start of the piece constants ...
+static_assert(kScPaintBytes >= sizeof(PaintDev), "the paint is staged over the piece constants");
+template <int CW>
+struct ScCfg {
+    static constexpr int kL = CW / 32;                 // columns per lane in the row scan
+    static constexpr int kPix = CW * kScH;             // pixels of a tile
+    static constexpr int kPasses = kPix / kScThreads;  // pixels per thread
+    static constexpr size_t kColorBytes = sizeof(float4) * kPix;
+    static constexpr size_t kCellBytes = sizeof(int) * kPix;
+    static constexpr size_t kSmem = kColorBytes + kCellBytes + kScPieceBytes + sizeof(ScSpanT) * kScSpanCap * kScWarps;
+    static_assert(kScPaintBytes + sizeof(unsigned short) * kPix <= kScPieceBytes, "... followed by the covered-pixel list");
+    static_assert(CW % 128 == 0 && kPix % kScThreads == 0 && kPix <= 65536, "tile shape");
+};
 
-template <bool EVENODD>
+template <bool EVENODD, int kScL>
 __device__ __forceinline__ void scan_row_inplace(int* bc, int acc, int lane) {
     int v[kScL];
 #pragma unroll
@@ -59,22 +69,26 @@ __device__ __forceinline__ void scan_row_inplace(int* bc, int acc, int lane) {
     }
 }
 
+template <int kScW>
 __global__ void __launch_bounds__(kScThreads, 2)
 scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* __restrict__ paints, uint32_t* __restrict__ tile_offs,
              uint32_t bin_cap, const double4* __restrict__ bin_lines, unsigned long long* __restrict__ tile_state, uint32_t epoch,
              uint32_t* __restrict__ ticket, const Status* status, const SceneArgs sc) {
+    using Cfg = ScCfg<kScW>;
+    constexpr int kScL = Cfg::kL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* color = reinterpret_cast<float4*>(smem_raw);
-    int* cells = reinterpret_cast<int*>(smem_raw + kScColorBytes);
-    double* p_ax = reinterpret_cast<double*>(smem_raw + kScColorBytes + kScCellBytes);
+    int* cells = reinterpret_cast<int*>(smem_raw + Cfg::kColorBytes);
+    double* p_ax = reinterpret_cast<double*>(smem_raw + Cfg::kColorBytes + Cfg::kCellBytes);
     double* p_ay = p_ax + kScThreads;
     double* p_by = p_ay + kScThreads;
     double* p_dxdy = p_by + kScThreads;
     ScSpanT* spans_all = reinterpret_cast<ScSpanT*>(p_dxdy + kScThreads);
     const PaintDev& s_paint = *reinterpret_cast<const PaintDev*>(p_ax);
+    unsigned short* cov_list = reinterpret_cast<unsigned short*>(reinterpret_cast<unsigned char*>(p_ax) + kScPaintBytes);
     __shared__ int carry[kScH], rowtot[kScH], row_touched[kScH], row_live[kScH];
     __shared__ float row_const[kScH];
-    __shared__ uint32_t s_ticket, s_count, s_bad;
+    __shared__ uint32_t s_ticket, s_count, s_bad, s_ncov;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -91,13 +105,14 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
     {
         const float4 bg = make_float4(sc.bg[0], sc.bg[1], sc.bg[2], sc.bg[3]);
 #pragma unroll
-        for (int r = 0; r < kScH; r++) {
+        for (int k = 0; k < Cfg::kPasses; k++) {
+            const int p = k * kScThreads + tid, r = p / kScW, col = p % kScW;
             float4 c = bg;
             if (!sc.fresh) {
                 c = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < th && tid < tw) c = sc.layer[(size_t)(Y0 + r) * sc.width + X0 + tid];
+                if (r < th && col < tw) c = sc.layer[(size_t)(Y0 + r) * sc.width + X0 + col];
             }
-            color[r * kScW + tid] = c;
+            color[p] = c;
         }
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -131,6 +146,7 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
             s_count = min(tile_offs[tile], bin_cap);
             tile_offs[tile] = 0u;  // self-cleaning counters, as in raster.cu
         }
+        if (tid == 32) s_ncov = 0u;
         if (tid < kScH) {
             int cin = 0;
             if (c > 0) {  // inclusive prefix of the job's tile to the left (published by the CTA of layer tile (B, C - 1))
@@ -195,8 +211,8 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
             const int r = warp;
             const int acc = carry[r];
             if (row_touched[r]) {
-                if (job.rule == 1) scan_row_inplace<true>(cells + r * kScW, acc, lane);
-                else scan_row_inplace<false>(cells + r * kScW, acc, lane);
+                if (job.rule == 1) scan_row_inplace<true, kScL>(cells + r * kScW, acc, lane);
+                else scan_row_inplace<false, kScL>(cells + r * kScW, acc, lane);
                 if (lane == 0) row_live[r] = 1;
             } else if (lane == 0) {  // no line touched this row of the tile: constant coverage
                 const float cv = (job.rule == 1) ? coverage_from_fixed<true>(acc) : coverage_from_fixed<false>(acc);
@@ -205,28 +221,48 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
             }
         }
         __syncthreads();
-        // paint + composite (src/rasterize.rs:103-115): thread = layer column, the tile's 8 rows in turn
+        // paint + composite (src/rasterize.rs:103-115).  `Paint::at` costs hundreds of instructions per pixel, so the tile's
+        // covered pixels (alpha >= 1e-6: mask_iter drops the rest, src/rasterize.rs:348) are first compacted into a list —
+        // row segments stay contiguous — and then dealt out evenly: every warp works with all lanes, whatever the shape.
+        const float* covs = reinterpret_cast<const float*>(cells);
         {
-            const int x = g.cx0 + tid;
-            const float* covs = reinterpret_cast<const float*>(cells);
-            if (x >= 0 && x < job.width_out) {
-                const int sx = swz<true>(tid);
+            unsigned mine = 0;  // bit k: this thread's pixel of pass k is covered
+            int cnt_before = 0, my_pos[Cfg::kPasses];
+            const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+            for (int k = 0; k < Cfg::kPasses; k++) {
+                const int p = k * kScThreads + tid, r = p / kScW, col = p % kScW;
+                const int x = g.cx0 + col, y = g.row0 + r;
+                bool cov = x >= 0 && x < job.width_out && y >= 0 && y < g.row1 && row_live[r];
+                if (cov) cov = (row_touched[r] ? covs[r * kScW + swz<true>(col)] : row_const[r]) >= 1e-6f;
+                const unsigned bal = __ballot_sync(0xffffffffu, cov);
+                my_pos[k] = cnt_before + __popc(bal & lt_mask);
+                cnt_before += __popc(bal);
+                mine |= cov ? (1u << k) : 0u;
+            }
+            int base = 0;
+            if (lane == 0 && cnt_before) base = (int)atomicAdd(&s_ncov, (uint32_t)cnt_before);
+            base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+            for (int k = 0; k < Cfg::kPasses; k++)
+                if (mine & (1u << k)) cov_list[base + my_pos[k]] = (unsigned short)(k * kScThreads + tid);
+        }
+        __syncthreads();
+        {
+            const int n_cov = (int)s_ncov;
 #pragma unroll 1
-                for (int r = 0; r < kScH; r++) {
-                    const int y = g.row0 + r;
-                    if (y < 0 || y >= g.row1 || !row_live[r]) continue;
-                    const float alpha = row_touched[r] ? covs[r * kScW + sx] : row_const[r];
-                    if (alpha >= 1e-6f) {  // mask_iter drops abs(alpha) < 1e-6, src/rasterize.rs:348
-                        float4 cl = (job.paint_index >= 0) ? paint_at(s_paint, x, y) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        // with_alpha: self * (alpha as f32), src/color.rs:347-349
-                        cl = make_float4(fmul(cl.x, alpha), fmul(cl.y, alpha), fmul(cl.z, alpha), fmul(cl.w, alpha));
-                        // blend_over: other + self * (1 - other.alpha), src/color.rs:342-344
-                        float4 d = color[r * kScW + tid];
-                        const float k = fsub(1.0f, cl.w);
-                        d = make_float4(fadd(cl.x, fmul(d.x, k)), fadd(cl.y, fmul(d.y, k)), fadd(cl.z, fmul(d.z, k)), fadd(cl.w, fmul(d.w, k)));
-                        color[r * kScW + tid] = d;
-                    }
-                }
+            for (int i = tid; i < n_cov; i += kScThreads) {
+                const int p = cov_list[i], r = p / kScW, col = p % kScW;
+                const int x = g.cx0 + col, y = g.row0 + r;
+                const float alpha = row_touched[r] ? covs[r * kScW + swz<true>(col)] : row_const[r];
+                float4 cl = (job.paint_index >= 0) ? paint_at(s_paint, x, y) : make_float4(0.f, 0.f, 0.f, 0.f);
+                // with_alpha: self * (alpha as f32), src/color.rs:347-349
+                cl = make_float4(fmul(cl.x, alpha), fmul(cl.y, alpha), fmul(cl.z, alpha), fmul(cl.w, alpha));
+                // blend_over: other + self * (1 - other.alpha), src/color.rs:342-344
+                float4 d = color[p];
+                const float k = fsub(1.0f, cl.w);
+                d = make_float4(fadd(cl.x, fmul(d.x, k)), fadd(cl.y, fmul(d.y, k)), fadd(cl.z, fmul(d.z, k)), fadd(cl.w, fmul(d.w, k)));
+                color[p] = d;
             }
         }
         dirty = true;
@@ -234,10 +270,12 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
     }
 
     // ---- the tile leaves the SM once: LinColor and / or RGBA8, coalesced rows ----
-    if (tid < tw) {
-        for (int r = 0; r < th; r++) {
-            const float4 c = color[r * kScW + tid];  // only this thread wrote it
-            const size_t o = (size_t)(Y0 + r) * sc.width + X0 + tid;
+#pragma unroll 1
+    for (int k = 0; k < Cfg::kPasses; k++) {
+        const int p = k * kScThreads + tid, r = p / kScW, col = p % kScW;
+        if (r < th && col < tw) {
+            const float4 c = color[p];
+            const size_t o = (size_t)(Y0 + r) * sc.width + X0 + col;
             if (dirty && sc.store_lin) sc.layer[o] = c;
             if (sc.rgba) sc.rgba[o] = lin_to_rgba8(c);
         }
@@ -246,32 +284,54 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
 
 }  // namespace
 
-TileShape scene_tile_shape() { return TileShape{kScW, kScH}; }
+// Tile width: 512 x 8 by default; RGPU_SCENE_CW=128|256|512 selects another instantiation (tuning)
+static int scene_cw() {
+    static const int cw = [] {
+        const char* e = getenv("RGPU_SCENE_CW");
+        const int v = e ? atoi(e) : 0;
+        return (v == 128 || v == 256 || v == 512) ? v : 512;
+    }();
+    return cw;
+}
 
-void launch_scene(const JobDev* jobs, uint32_t n_jobs, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
-                  unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, const SceneArgs& sc, bool pdl,
-                  cudaStream_t s) {
+TileShape scene_tile_shape() { return TileShape{scene_cw(), kScH}; }
+
+template <int CW>
+static void launch_scene_t(const JobDev* jobs, uint32_t n_jobs, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap,
+                           const double4* bin_lines, unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status,
+                           const SceneArgs& sc, bool pdl, cudaStream_t s) {
     const uint32_t n_tiles = sc.n_bands * sc.n_chunks;
-    if (n_tiles == 0) return;
+    constexpr size_t smem = ScCfg<CW>::kSmem;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaFuncSetAttribute(scene_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScSmem);
-        cudaFuncSetAttribute(scene_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(scene_kernel<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(scene_kernel<CW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_tiles);
     cfg.blockDim = dim3(kScThreads);
-    cfg.dynamicSmemBytes = kScSmem;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, scene_kernel, jobs, n_jobs, paints, tile_offs, bin_cap, bin_lines, tile_state, epoch, ticket, status, sc);
+    cudaLaunchKernelEx(&cfg, scene_kernel<CW>, jobs, n_jobs, paints, tile_offs, bin_cap, bin_lines, tile_state, epoch, ticket, status, sc);
+}
+
+void launch_scene(const JobDev* jobs, uint32_t n_jobs, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
+                  unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, const SceneArgs& sc, bool pdl,
+                  cudaStream_t s) {
+    if (sc.n_bands * sc.n_chunks == 0) return;
+    switch (scene_cw()) {
+        case 128: launch_scene_t<128>(jobs, n_jobs, paints, tile_offs, bin_cap, bin_lines, tile_state, epoch, ticket, status, sc, pdl, s); break;
+        case 256: launch_scene_t<256>(jobs, n_jobs, paints, tile_offs, bin_cap, bin_lines, tile_state, epoch, ticket, status, sc, pdl, s); break;
+        default: launch_scene_t<512>(jobs, n_jobs, paints, tile_offs, bin_cap, bin_lines, tile_state, epoch, ticket, status, sc, pdl, s); break;
+    }
 }
 
 }  // namespace rgpu
