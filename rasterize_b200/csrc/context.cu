@@ -346,6 +346,7 @@ bool build_paint(const rgpu_job& job, PaintDev& out) {
         out.rad_cdy = out.p0y - out.p1y;
         out.rad_rd = out.r0 - out.r1;
         out.rad_a = (out.rad_cdx * out.rad_cdx + out.rad_cdy * out.rad_cdy) - out.rad_rd * out.rad_rd;
+        out.rad_inv2a = 1.0 / (2.0 * out.rad_a);
     }
     if (out.n_stops == 0) {  // GradStops::new: empty list -> one opaque black stop, src/grad.rs:92-97
         out.n_stops = 1;

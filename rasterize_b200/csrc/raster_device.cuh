@@ -60,6 +60,8 @@ __device__ __forceinline__ unsigned char f2u8(float v) {
     return (unsigned char)v;
 }
 __device__ __forceinline__ uchar4 lin_to_rgba8(float4 c) {
+    // transparent pixels (the empty part of a layer) unmultiply to zero and l2s(0) == 0: nothing to evaluate
+    if (c.w <= 1e-6f) return make_uchar4(0, 0, 0, f2u8(fadd(fmul(c.w, 255.0f), 0.5f)));
     const float4 u = unmultiply(c);
     uchar4 o;
     o.x = f2u8(fadd(fmul(l2s_lane(u.x), 255.0f), 0.5f));
@@ -77,11 +79,10 @@ __device__ __forceinline__ double rem_euclid(double x, double rhs) {
 
 // GradStops::at, src/grad.rs:116-139
 static __device__ float4 stops_at(const PaintDev& P, double t) {
-    int lo = 0, hi = P.n_stops;
-    while (lo < hi) {
-        int mid = lo + ((hi - lo) >> 1);
-        if (P.stop_pos[mid] < t) lo = mid + 1; else hi = mid;
-    }
+    // partition_point(position < t) over the sorted stops == the number of stops left of t: a branch-free count with a
+    // warp-uniform trip count instead of a divergent binary search
+    int lo = 0;
+    for (int i = 0; i < P.n_stops; i++) lo += (P.stop_pos[i] < t) ? 1 : 0;
     int index = lo, size = P.n_stops;
     if (index == 0) return make_float4(P.stop_col[0][0], P.stop_col[0][1], P.stop_col[0][2], P.stop_col[0][3]);
     if (index == size)
@@ -114,12 +115,12 @@ static __device__ bool radial_offset(const PaintDev& P, double px, double py, do
         double t0, t1;
         if (b >= 0.0) {
             double mul = __dsub_rn(-b, sq);
-            t0 = __ddiv_rn(mul, __dmul_rn(2.0, a));
+            t0 = __dmul_rn(mul, P.rad_inv2a);  // mul / (2 a): the reciprocal is a per-paint constant (agrees to an ulp)
             t1 = __ddiv_rn(__dmul_rn(2.0, c), mul);
         } else {
             double mul = __dadd_rn(-b, sq);
             t0 = __ddiv_rn(__dmul_rn(2.0, c), mul);
-            t1 = __ddiv_rn(mul, __dmul_rn(2.0, a));
+            t1 = __dmul_rn(mul, P.rad_inv2a);
         }
         out = isnan(t0) ? t1 : (isnan(t1) ? t0 : fmax(t0, t1));
         return true;

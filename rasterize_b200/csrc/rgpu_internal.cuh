@@ -46,6 +46,7 @@ struct PaintDev {
     double stop_inv[kMaxStops];  // 1 / (stop_pos[i] - stop_pos[i-1]) for i >= 1
     double lin_a, lin_b, lin_c;  // linear: t = (x + 0.5) * lin_a + (y + 0.5) * lin_b + lin_c (pixel_tr and dir folded together)
     double rad_cdx, rad_cdy, rad_rd, rad_a;  // radial: c - fc, r - fr, cd.cd - rd^2 (src/grad.rs:361-372)
+    double rad_inv2a;                        // 1 / (2 a)
 };
 
 struct JobDev {
