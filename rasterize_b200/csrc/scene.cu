@@ -5,8 +5,8 @@
 // (src/scene.rs:483-501) and the RGBA8 export that follows `Scene::render` in every CLI run (src/color.rs:164-175).
 //
 // The ordered batch of raster.cu issues one launch per fill because fills blend in order onto one canvas.  Here the order
-// is kept INSIDE a CTA instead: a CTA owns a 512 x 8 tile of the layer, keeps its LinColor pixels in shared memory
-// (64 KB), and walks the fills in submission order — accumulate the fill's lines of this tile (same fixed-point
+// is kept INSIDE a CTA instead: a CTA owns a 256 x 8 tile of the layer, keeps its LinColor pixels in shared memory
+// (32 KB), and walks the fills in submission order — accumulate the fill's lines of this tile (same fixed-point
 // signed-difference cells as raster.cu), carry-in from the tile to the left, row scan, fill rule, `Paint::at`,
 // `with_alpha`, `blend_over` into the shared tile.  The layer is read at most once and written once, however many fills
 // overlap (SURVEY §8d "(s)" bytes: 16 B x W x H, + 4 B with the RGBA8 export), and tiles the fills do not touch cost
@@ -26,22 +26,25 @@ namespace {
 
 using namespace rs;
 
-constexpr int kScH = 8, kScThreads = 512, kScWarps = kScThreads / 32;
+constexpr int kScH = 8;
 constexpr int kScSpanCap = 208;       // per-warp span list (lane << 3 | row)
 using ScSpanT = unsigned char;
-constexpr size_t kScPieceBytes = sizeof(double) * 4 * kScThreads;  // reused for the paint + the covered-pixel list while compositing
-constexpr size_t kScPaintBytes = 2048;                              // the paint sits at the start of the piece constants ...
+constexpr size_t kScPaintBytes = 2048;  // the paint sits at the start of the piece constants ...
 static_assert(kScPaintBytes >= sizeof(PaintDev), "the paint is staged over the piece constants");
-template <int CW>
+template <int CW, int THREADS>
 struct ScCfg {
-    static constexpr int kL = CW / 32;                 // columns per lane in the row scan
-    static constexpr int kPix = CW * kScH;             // pixels of a tile
-    static constexpr int kPasses = kPix / kScThreads;  // pixels per thread
+    static constexpr int kWarps = THREADS / 32;
+    static constexpr int kL = CW / 32;              // columns per lane in the row scan
+    static constexpr int kPix = CW * kScH;          // pixels of a tile
+    static constexpr int kPasses = kPix / THREADS;  // pixels per thread
     static constexpr size_t kColorBytes = sizeof(float4) * kPix;
     static constexpr size_t kCellBytes = sizeof(int) * kPix;
-    static constexpr size_t kSmem = kColorBytes + kCellBytes + kScPieceBytes + sizeof(ScSpanT) * kScSpanCap * kScWarps;
-    static_assert(kScPaintBytes + sizeof(unsigned short) * kPix <= kScPieceBytes, "... followed by the covered-pixel list");
-    static_assert(CW % 128 == 0 && kPix % kScThreads == 0 && kPix <= 65536, "tile shape");
+    // piece constants of the accumulation; reused for the paint + the covered-pixel list while compositing
+    static constexpr size_t kPieceBytes = (sizeof(double) * 4 * THREADS > kScPaintBytes + sizeof(unsigned short) * kPix)
+                                              ? sizeof(double) * 4 * THREADS : kScPaintBytes + sizeof(unsigned short) * kPix;
+    static constexpr size_t kSmem = kColorBytes + kCellBytes + kPieceBytes + sizeof(ScSpanT) * kScSpanCap * kWarps;
+    static constexpr int kMinBlocks = (THREADS >= 512) ? 2 : 4;  // 64 registers per thread
+    static_assert(CW % 128 == 0 && kPix % THREADS == 0 && kPix <= 65536 && kWarps >= kScH, "tile shape");
 };
 
 template <bool EVENODD, int kScL>
@@ -69,13 +72,13 @@ __device__ __forceinline__ void scan_row_inplace(int* bc, int acc, int lane) {
     }
 }
 
-template <int kScW>
-__global__ void __launch_bounds__(kScThreads, 2)
+template <int kScW, int kScThreads>
+__global__ void __launch_bounds__(kScThreads, (ScCfg<kScW, kScThreads>::kMinBlocks))
 scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* __restrict__ paints, uint32_t* __restrict__ tile_offs,
              uint32_t bin_cap, const double4* __restrict__ bin_lines, unsigned long long* __restrict__ tile_state, uint32_t epoch,
              uint32_t* __restrict__ ticket, const Status* status, const SceneArgs sc) {
-    using Cfg = ScCfg<kScW>;
-    constexpr int kScL = Cfg::kL;
+    using Cfg = ScCfg<kScW, kScThreads>;
+    constexpr int kScL = Cfg::kL, kScWarps = Cfg::kWarps;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* color = reinterpret_cast<float4*>(smem_raw);
     int* cells = reinterpret_cast<int*>(smem_raw + Cfg::kColorBytes);
@@ -83,7 +86,7 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
     double* p_ay = p_ax + kScThreads;
     double* p_by = p_ay + kScThreads;
     double* p_dxdy = p_by + kScThreads;
-    ScSpanT* spans_all = reinterpret_cast<ScSpanT*>(p_dxdy + kScThreads);
+    ScSpanT* spans_all = reinterpret_cast<ScSpanT*>(smem_raw + Cfg::kColorBytes + Cfg::kCellBytes + Cfg::kPieceBytes);
     const PaintDev& s_paint = *reinterpret_cast<const PaintDev*>(p_ax);
     unsigned short* cov_list = reinterpret_cast<unsigned short*>(reinterpret_cast<unsigned char*>(p_ax) + kScPaintBytes);
     __shared__ int carry[kScH], rowtot[kScH], row_touched[kScH], row_live[kScH];
@@ -284,35 +287,41 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
 
 }  // namespace
 
-// Tile width: 512 x 8 by default; RGPU_SCENE_CW=128|256|512 selects another instantiation (tuning)
+// Tile width / CTA size: 256 x 8 pixels, 256 threads (4 CTAs per SM) by default — C3: 234 us against 250 us for 512 x 8 / 512
+// threads and 256 us for 128 x 8 / 256; RGPU_SCENE_CW=128|256|512 and RGPU_SCENE_THREADS=256|512 select another instantiation
+static int scene_env(const char* name, int dflt, int a, int b, int c) {
+    const char* e = getenv(name);
+    const int v = e ? atoi(e) : 0;
+    return (v == a || v == b || v == c) ? v : dflt;
+}
 static int scene_cw() {
-    static const int cw = [] {
-        const char* e = getenv("RGPU_SCENE_CW");
-        const int v = e ? atoi(e) : 0;
-        return (v == 128 || v == 256 || v == 512) ? v : 512;
-    }();
+    static const int cw = scene_env("RGPU_SCENE_CW", 256, 128, 256, 512);
     return cw;
+}
+static int scene_threads() {
+    static const int t = scene_env("RGPU_SCENE_THREADS", 256, 256, 512, 512);
+    return (scene_cw() == 512) ? 512 : t;
 }
 
 TileShape scene_tile_shape() { return TileShape{scene_cw(), kScH}; }
 
-template <int CW>
+template <int CW, int THREADS>
 static void launch_scene_t(const JobDev* jobs, uint32_t n_jobs, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap,
                            const double4* bin_lines, unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status,
                            const SceneArgs& sc, bool pdl, cudaStream_t s) {
     const uint32_t n_tiles = sc.n_bands * sc.n_chunks;
-    constexpr size_t smem = ScCfg<CW>::kSmem;
+    constexpr size_t smem = ScCfg<CW, THREADS>::kSmem;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaFuncSetAttribute(scene_kernel<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(scene_kernel<CW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(scene_kernel<CW, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(scene_kernel<CW, THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_tiles);
-    cfg.blockDim = dim3(kScThreads);
+    cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -320,18 +329,21 @@ static void launch_scene_t(const JobDev* jobs, uint32_t n_jobs, const PaintDev* 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, scene_kernel<CW>, jobs, n_jobs, paints, tile_offs, bin_cap, bin_lines, tile_state, epoch, ticket, status, sc);
+    cudaLaunchKernelEx(&cfg, scene_kernel<CW, THREADS>, jobs, n_jobs, paints, tile_offs, bin_cap, bin_lines, tile_state, epoch, ticket, status, sc);
 }
 
 void launch_scene(const JobDev* jobs, uint32_t n_jobs, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
                   unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, const SceneArgs& sc, bool pdl,
                   cudaStream_t s) {
     if (sc.n_bands * sc.n_chunks == 0) return;
-    switch (scene_cw()) {
-        case 128: launch_scene_t<128>(jobs, n_jobs, paints, tile_offs, bin_cap, bin_lines, tile_state, epoch, ticket, status, sc, pdl, s); break;
-        case 256: launch_scene_t<256>(jobs, n_jobs, paints, tile_offs, bin_cap, bin_lines, tile_state, epoch, ticket, status, sc, pdl, s); break;
-        default: launch_scene_t<512>(jobs, n_jobs, paints, tile_offs, bin_cap, bin_lines, tile_state, epoch, ticket, status, sc, pdl, s); break;
-    }
+#define RGPU_SCENE(CW, T) launch_scene_t<CW, T>(jobs, n_jobs, paints, tile_offs, bin_cap, bin_lines, tile_state, epoch, ticket, status, sc, pdl, s)
+    const int cw = scene_cw(), th = scene_threads();
+    if (cw == 128 && th == 256) RGPU_SCENE(128, 256);
+    else if (cw == 128) RGPU_SCENE(128, 512);
+    else if (cw == 256 && th == 256) RGPU_SCENE(256, 256);
+    else if (cw == 256) RGPU_SCENE(256, 512);
+    else RGPU_SCENE(512, 512);
+#undef RGPU_SCENE
 }
 
 }  // namespace rgpu
