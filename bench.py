@@ -365,6 +365,31 @@ def run_ours(args):
         e2e["f32_ms_per_call"] = round((time.perf_counter() - t0) / n_e2e * 1e3, 4)
         if rank == 0 and world == 1:
             cpu_baseline = cpu_reference_c2(threads=1, budget_s=12.0)
+    elif args.workload in ("c1", "c3"):
+        # Scene::render + RGBA8 export through the host-buffer entry point: host paths in (H2D), pinned RGBA8 image out (D2H)
+        from rasterize_b200 import assets as _assets, scene as rscene
+        sc = _assets.load_scene("squirrel_cli_512" if args.workload == "c1" else "firefox_2048")
+        fills, W, H = rscene.fixture_fills_host(sc)
+        prepared_host = rast.prepare_scene_host(fills)
+        img = rast.host_alloc((H, W, 4), np.uint8)
+        for _ in range(5):
+            rast.render_scene_host(prepared_host, W, H, bg=sc.bg, rgba_out=img)
+        n_e2e = max(5, min(50, args.steps))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            rast.render_scene_host(prepared_host, W, H, bg=sc.bg, rgba_out=img)
+        dt = (time.perf_counter() - t0) / n_e2e
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        h2d, d2h = rast.last_transfer_bytes()
+        e2e = {"value": round(W * H * world / dt / 1e6, 1), "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_call": round(dt * 1e3, 4),
+               "call": "rgpu_render_scene_host: host paths + paints in, Layer::new + all fills + RGBA8 export on the device, pinned RGBA8 host image out"}
+        if rank == 0 and world == 1:
+            cpu_baseline = cpu_reference_other(args.workload, budget_s=10.0)
     elif rank == 0 and world == 1:
         cpu_baseline = cpu_reference_other(args.workload, budget_s=10.0)
 

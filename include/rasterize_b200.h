@@ -112,6 +112,23 @@ int rgpu_coverage_f32(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], 
 int rgpu_fill(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill_rule, const rgpu_paint* paint,
               const double* path_bbox, float* img, rgpu_shape shape);
 
+/* One Fill node of a host-side scene: what the Fill arm of `Pipeline::render_rec` holds per node (src/scene.rs:407-430).
+ * (x, y, width, height) is the `view_mut` window of the layer the node draws into, `tr` = align * node transform. */
+typedef struct {
+    const rgpu_path* path;
+    double tr[6];
+    int32_t fill_rule;
+    const rgpu_paint* paint;
+    const double* path_bbox; /* bounding-box units only, else NULL */
+    uint32_t x, y, width, height;
+} rgpu_scene_fill;
+/* `Scene::render` of a Fill-only pipeline (src/scene.rs:186-199, 384-435) followed by the export every CLI run does
+ * (`ImageOwned<LinColor>` -> RGBA8, src/color.rs:164-175), HOST buffers in and out: a width x height layer is created with
+ * `bg` (NULL = transparent), the fills are blended in order by the scene compositor (one raster launch), and the image is
+ * returned as RGBA8 (rgba_out, 4 B per pixel over PCIe) and / or LinColor (lin_out, f32 x 4); either may be NULL. */
+int rgpu_render_scene_host(rgpu_ctx* ctx, const rgpu_scene_fill* fills, size_t n_fills, size_t width, size_t height, const float* bg,
+                           float* lin_out, uint8_t* rgba_out);
+
 /* ---- device-resident entry points (inputs and outputs stay in HBM) -------------------------------- */
 int rgpu_path_upload(rgpu_ctx* ctx, const rgpu_path* path, rgpu_dpath** out);
 void rgpu_path_free(rgpu_ctx* ctx, rgpu_dpath* p);

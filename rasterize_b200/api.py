@@ -547,6 +547,42 @@ class GpuRasterizer:
                      sync: bool = True) -> None:
         self.submit_scene_prepared(self._cjobs(jobs), layer_ptr, width, height, fresh, bg, rgba_ptr, sync)
 
+    def prepare_scene_host(self, fills):
+        """Marshal host-side scene fills once: `fills` = iterable of (Path, tr, FillRule, paint, path_bbox | None, x, y, width, height)."""
+        fills = list(fills)
+        arr = (ffi.CSceneFill * max(len(fills), 1))()
+        keep: list = []
+        for i, (path, tr, rule, paint, bbox, x, y, w, h) in enumerate(fills):
+            cf = arr[i]
+            cp = path._c()
+            keep.append((cp, path))
+            cf.path = C.pointer(cp)
+            cf.tr[:] = [float(v) for v in _as_tr(tr)]
+            cf.fill_rule = int(rule)
+            pp = paint._c(keep)
+            keep.append(pp)
+            cf.paint = C.pointer(pp)
+            if bbox is not None:
+                bb = np.ascontiguousarray(bbox, dtype=np.float64)
+                keep.append(bb)
+                cf.path_bbox = bb.ctypes.data_as(C.POINTER(C.c_double))
+            cf.x, cf.y, cf.width, cf.height = int(x), int(y), int(w), int(h)
+        return arr, len(fills), keep
+
+    def render_scene_host(self, fills, width: int, height: int, bg=None, lin_out: np.ndarray | None = None, rgba_out: np.ndarray | None = None):
+        """`Scene::render` of a Fill-only pipeline + export, host buffers in and out (`rgpu_render_scene_host`).  `fills` is an
+        iterable as for `prepare_scene_host`, or its result.  Returns (lin_out, rgba_out)."""
+        arr, n, _ = fills if isinstance(fills, tuple) and len(fills) == 3 and isinstance(fills[1], int) else self.prepare_scene_host(fills)
+        cbg = (C.c_float * 4)(*[float(v) for v in bg]) if bg is not None else None
+        if lin_out is None and rgba_out is None:
+            rgba_out = np.empty((height, width, 4), dtype=np.uint8)
+        for a, dt in ((lin_out, np.float32), (rgba_out, np.uint8)):
+            assert a is None or (a.dtype == dt and a.flags.c_contiguous and a.shape == (height, width, 4))
+        self._check(ffi.lib().rgpu_render_scene_host(self.ctx, arr, n, int(width), int(height), cbg,
+                                                     lin_out.ctypes.data if lin_out is not None else None,
+                                                     rgba_out.ctypes.data if rgba_out is not None else None))
+        return lin_out, rgba_out
+
     def batch_status(self) -> None:
         self._check(ffi.lib().rgpu_batch_status(self.ctx))
 

@@ -961,6 +961,87 @@ int rgpu_render_scene_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, f
     return submit_sync(ctx, jobs, n_jobs, RGPU_BATCH_ORDERED, 1, false, &sc);
 }
 
+// `Scene::render` of a Fill-only pipeline + export with HOST buffers: all paths are staged into the context's grow-only
+// scratch with two copies (points, items), the scene compositor renders the layer in one raster launch and the image comes
+// back as RGBA8 (4 B per pixel) and / or LinColor.
+int rgpu_render_scene_host(rgpu_ctx* ctx, const rgpu_scene_fill* fills, size_t n_fills, size_t width, size_t height, const float* bg,
+                           float* lin_out, uint8_t* rgba_out) {
+    if (!ctx || (!fills && n_fills)) return RGPU_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (width == 0 || height == 0) return RGPU_OK;
+    if (!lin_out && !rgba_out) return fail(ctx, RGPU_ERR_INVALID, "no output image");
+    int rc;
+    size_t n_points = 0, n_items2 = 0;
+    std::vector<rgpu_dpath> dps(n_fills);
+    std::vector<std::vector<uint2>> items(n_fills);
+    for (size_t i = 0; i < n_fills; i++) {
+        const rgpu_scene_fill& f = fills[i];
+        if ((rc = validate_path(ctx, f.path))) return rc;
+        if (!f.paint) return fail(ctx, RGPU_ERR_INVALID, "fill without a paint");
+        if (f.paint->n_stops > RGPU_MAX_STOPS) return fail(ctx, RGPU_ERR_INVALID, "too many gradient stops");
+        if ((size_t)f.x + f.width > width || (size_t)f.y + f.height > height) return fail(ctx, RGPU_ERR_INVALID, "fill window leaves the layer");
+        std::vector<uint2> packed;
+        build_items(f.path, items[i], dps[i].n_curves);
+        pack_items(items[i], packed);
+        dps[i].n_points = f.path->n_points;
+        dps[i].n_items = (uint32_t)items[i].size();
+        items[i].insert(items[i].end(), packed.begin(), packed.end());  // [reference order | curves first]
+        n_points += f.path->n_points;
+        n_items2 += items[i].size();
+    }
+    const size_t pts_bytes = sizeof(double2) * n_points, items_bytes = sizeof(uint2) * n_items2;
+    if ((rc = ensure_dev(ctx, ctx->tmp_pts, std::max<size_t>(pts_bytes, 16)))) return rc;
+    if ((rc = ensure_dev(ctx, ctx->tmp_items, std::max<size_t>(items_bytes, 16)))) return rc;
+    if ((rc = ensure_stage(ctx, std::max<size_t>(pts_bytes + items_bytes, 16)))) return rc;
+    // every host-buffer entry point ends with a stream sync: the staging buffer is free
+    char* st = static_cast<char*>(ctx->h_stage);
+    size_t po = 0, io = 0;
+    for (size_t i = 0; i < n_fills; i++) {
+        dps[i].pts = static_cast<double2*>(ctx->tmp_pts.p) + po;
+        dps[i].items = static_cast<uint2*>(ctx->tmp_items.p) + io;
+        dps[i].items_packed = dps[i].items + dps[i].n_items;
+        if (dps[i].n_points) std::memcpy(st + sizeof(double2) * po, fills[i].path->points, sizeof(double2) * dps[i].n_points);
+        if (!items[i].empty()) std::memcpy(st + pts_bytes + sizeof(uint2) * io, items[i].data(), sizeof(uint2) * items[i].size());
+        po += dps[i].n_points;
+        io += items[i].size();
+    }
+    if (pts_bytes) CK(ctx, cudaMemcpyAsync(ctx->tmp_pts.p, st, pts_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (items_bytes) CK(ctx, cudaMemcpyAsync(ctx->tmp_items.p, st + pts_bytes, items_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t n_px = width * height;
+    if ((rc = ensure_dev(ctx, ctx->img_lin, sizeof(float4) * n_px))) return rc;
+    if (rgba_out && (rc = ensure_dev(ctx, ctx->img_f32, 4 * n_px))) return rc;  // RGBA8 staging shares the f32 mask scratch
+    std::vector<rgpu_job> jobs;
+    jobs.reserve(n_fills);
+    for (size_t i = 0; i < n_fills; i++) {
+        const rgpu_scene_fill& f = fills[i];
+        if (f.path->n_segments == 0 || f.path->n_subpaths == 0 || f.width == 0 || f.height == 0) continue;
+        rgpu_job j;
+        std::memset(&j, 0, sizeof(j));
+        j.path = &dps[i];
+        std::memcpy(j.tr, f.tr, sizeof(j.tr));
+        j.fill_rule = f.fill_rule;
+        j.mode = RGPU_JOB_FILL;
+        j.paint = f.paint;
+        j.path_bbox = f.path_bbox;
+        j.canvas = ctx->img_lin.p;
+        j.origin = (size_t)f.y * width + f.x;
+        j.row_stride = width;
+        j.width = f.width;
+        j.height = f.height;
+        jobs.push_back(j);
+    }
+    SceneArgs sc;
+    if ((rc = scene_args(ctx, static_cast<float*>(ctx->img_lin.p), width, height, 1, bg, rgba_out ? static_cast<uint8_t*>(ctx->img_f32.p) : nullptr, sc)))
+        return rc;
+    if ((rc = submit_sync(ctx, jobs.data(), jobs.size(), RGPU_BATCH_ORDERED, 1, false, &sc))) return rc;
+    if (rgba_out) CK(ctx, cudaMemcpyAsync(rgba_out, ctx->img_f32.p, 4 * n_px, cudaMemcpyDeviceToHost, ctx->stream));
+    if (lin_out) CK(ctx, cudaMemcpyAsync(lin_out, ctx->img_lin.p, sizeof(float4) * n_px, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->last_h2d_bytes = pts_bytes + items_bytes;
+    ctx->last_d2h_bytes = (rgba_out ? 4 * n_px : 0) + (lin_out ? sizeof(float4) * n_px : 0);
+    return RGPU_OK;
+}
+
 int rgpu_last_counts(rgpu_ctx* ctx, uint64_t* n_lines, uint64_t* n_line_refs, uint64_t* n_launches) {
     if (!ctx) return RGPU_ERR_INVALID;
     if (n_lines) *n_lines = ctx->last_lines;

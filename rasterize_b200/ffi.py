@@ -52,13 +52,18 @@ class CJob(C.Structure):
                 ("origin", C.c_size_t), ("row_stride", C.c_size_t), ("width", C.c_uint32), ("height", C.c_uint32)]
 
 
+class CSceneFill(C.Structure):
+    _fields_ = [("path", C.POINTER(CPath)), ("tr", C.c_double * 6), ("fill_rule", C.c_int32), ("paint", C.POINTER(CPaint)),
+                ("path_bbox", C.POINTER(C.c_double)), ("x", C.c_uint32), ("y", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32)]
+
+
 _lib = None
 
 #: every symbol include/rasterize_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "rgpu_create", "rgpu_destroy", "rgpu_name", "rgpu_last_error", "rgpu_device_count", "rgpu_flatten", "rgpu_mask",
     "rgpu_mask_f32", "rgpu_mask_iter", "rgpu_coverage_f32", "rgpu_fill", "rgpu_path_upload", "rgpu_path_free",
-    "rgpu_render_batch", "rgpu_batch_status", "rgpu_render_batch_sync", "rgpu_render_scene", "rgpu_render_scene_sync", "rgpu_last_counts", "rgpu_last_transfer_bytes", "rgpu_set_profiling",
+    "rgpu_render_batch", "rgpu_batch_status", "rgpu_render_batch_sync", "rgpu_render_scene", "rgpu_render_scene_sync", "rgpu_render_scene_host", "rgpu_last_counts", "rgpu_last_transfer_bytes", "rgpu_set_profiling",
     "rgpu_last_stage_ms", "rgpu_to_rgba8_dev", "rgpu_layer_scale_by_mask_dev", "rgpu_layer_blend_over_dev", "rgpu_download_rgba8",
     "rgpu_fill_color_dev", "rgpu_stream", "rgpu_sync", "rgpu_device_alloc", "rgpu_device_free", "rgpu_device_zero",
     "rgpu_memcpy_h2d", "rgpu_memcpy_d2h", "rgpu_host_alloc", "rgpu_host_free",
@@ -100,6 +105,7 @@ def lib():
     sig("rgpu_render_batch_sync", i32, vp, C.POINTER(CJob), sz, u32)
     sig("rgpu_render_scene", i32, vp, C.POINTER(CJob), sz, vp, sz, sz, i32, pf, vp)
     sig("rgpu_render_scene_sync", i32, vp, C.POINTER(CJob), sz, vp, sz, sz, i32, pf, vp)
+    sig("rgpu_render_scene_host", i32, vp, C.POINTER(CSceneFill), sz, sz, sz, pf, vp, vp)
     sig("rgpu_last_counts", i32, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
     sig("rgpu_last_transfer_bytes", i32, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
     sig("rgpu_set_profiling", i32, vp, i32)

@@ -235,3 +235,21 @@ def fixture_jobs(rast: GpuRasterizer, sc, layer_ptr: int):
         jobs.append(Job(dp, tr, f.fill_rule, ffi.JOB_FILL, layer_ptr, col_max - col_min, row_max - row_min, W,
                         origin=row_min * W + col_min, paint=f.paint, path_bbox=f.path_bbox))
     return jobs, keep, W, H, in_bytes
+
+
+def fixture_fills_host(sc):
+    """The same Fill nodes as `fixture_jobs`, as host-side tuples for `GpuRasterizer.render_scene_host`.
+    Returns (fills, W, H)."""
+    x0, y0, x1, y1 = sc.view
+    lx, ly = math.floor(x0), math.floor(y0)
+    W, H = math.ceil(x1) - lx, math.ceil(y1) - ly
+    fills = []
+    for f in sc.fills:
+        bx0, by0, bx1, by1 = f.bbox
+        col_min = max(0, min(math.floor(bx0) - lx, W))
+        col_max = max(col_min, min(math.ceil(bx1) - lx + 1, W))
+        row_min = max(0, min(math.floor(by0) - ly, H))
+        row_max = max(row_min, min(math.ceil(by1) - ly + 1, H))
+        tr = Transform.new_translate(-math.floor(bx0), -math.floor(by0)) * Transform.from_array(f.tr)
+        fills.append((f.path, tr, f.fill_rule, f.paint, f.path_bbox, col_min, row_min, col_max - col_min, row_max - row_min))
+    return fills, W, H

@@ -197,3 +197,46 @@ np.save('%s', r.to_host(layer, (H, W, 4), np.float32))
         outs.append(np.load(name))
         os.unlink(name)
     assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("name", ["squirrel_cli_512", "firefox_256", "linear_colors", "many_circles_64"])
+def test_render_scene_host_matches_device_path(rast, name):
+    """`rgpu_render_scene_host` (host paths in, host images out) is the device-resident scene render, bit for bit."""
+    sc = assets.load_scene(name)
+    fills, W, H = scene.fixture_fills_host(sc)
+    lin = np.empty((H, W, 4), dtype=np.float32)
+    rgba = np.empty((H, W, 4), dtype=np.uint8)
+    rast.render_scene_host(fills, W, H, bg=sc.bg, lin_out=lin, rgba_out=rgba)
+    h2d, d2h = rast.last_transfer_bytes()
+    assert d2h == W * H * 20 and h2d >= sum(f[0].input_bytes() for f in fills)
+
+    def make(layer):
+        jobs, keep, _, _, _ = scene.fixture_jobs(rast, sc, layer)
+        return jobs, keep
+
+    _, _, lin_b, rgba_b = both_ways(rast, make, W, H, sc.bg)
+    assert np.array_equal(lin, lin_b)
+    assert np.array_equal(rgba, rgba_b)
+    # RGBA8 only (the CLI's output): same bytes, a quarter of the download
+    _, rgba2 = rast.render_scene_host(fills, W, H, bg=sc.bg)
+    assert np.array_equal(rgba2, rgba)
+    assert rast.last_transfer_bytes()[1] == W * H * 4
+
+
+def test_render_scene_host_edge_cases(rast):
+    # no fills: the background alone
+    _, rgba = rast.render_scene_host([], 33, 9, bg=[1.0, 1.0, 1.0, 1.0])
+    assert (rgba == 255).all()
+    # empty path and zero-sized window are no-ops; a NaN control point is reported like the reference's panic
+    black = rb.LinColor(0, 0, 0, 1)
+    ident = rb.Transform.identity()
+    g = bench.glyph_path(rb, 3)
+    fills = [(rb.Path.empty(), ident, rb.FillRule.NonZero, black, None, 0, 0, 20, 9), (g, ident, rb.FillRule.NonZero, black, None, 5, 2, 0, 0)]
+    _, rgba = rast.render_scene_host(fills, 33, 9, bg=None)
+    assert not rgba.any()
+    bad = rb.Path(np.array([[0.0, 0.0], [np.nan, 1.0]]), np.array([2], dtype=np.uint8), np.array([0, 1], dtype=np.uint32), np.array([1], dtype=np.uint8))
+    with pytest.raises(rb.RgpuError) as e:
+        rast.render_scene_host([(bad, ident, rb.FillRule.NonZero, black, None, 0, 0, 33, 9)], 33, 9)
+    assert e.value.code == ffi.ERR_NAN
+    with pytest.raises(rb.RgpuError):  # window outside the layer
+        rast.render_scene_host([(g, ident, rb.FillRule.NonZero, black, None, 30, 0, 10, 9)], 33, 9)
