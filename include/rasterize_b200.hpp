@@ -234,6 +234,38 @@ public:
         lines.resize(4 * n);
         return lines;
     }
+    // One Fill node as the Fill arm of `Pipeline::render_rec` sets it up (src/scene.rs:407-430): `tr` = align * node
+    // transform, (x, y, width, height) = the `view_mut` window of the layer.
+    struct SceneFill {
+        const Path* path;
+        Transform tr;
+        FillRule fill_rule;
+        Paint* paint;
+        uint32_t x, y, width, height;
+        const double* path_bbox = nullptr;
+    };
+    // `Scene::render` of a Fill-only pipeline (src/scene.rs:186-199, 384-435) + the CLI's RGBA8 export in ONE call: a
+    // width x height layer created with `bg` (nullptr = transparent), fills blended in order by the scene compositor.
+    // Returns RGBA8; `lin` (optional) receives the LinColor layer (4 floats per pixel).
+    std::vector<uint8_t> render_scene(const std::vector<SceneFill>& fills, size_t width, size_t height, const float* bg = nullptr,
+                                      std::vector<float>* lin = nullptr) {
+        std::vector<rgpu_path> paths(fills.size());
+        std::vector<rgpu_scene_fill> ffi(fills.size());
+        for (size_t i = 0; i < fills.size(); i++) {
+            paths[i] = fills[i].path->ffi();
+            ffi[i] = rgpu_scene_fill{};
+            ffi[i].path = &paths[i];
+            for (int k = 0; k < 6; k++) ffi[i].tr[k] = fills[i].tr.m[k];
+            ffi[i].fill_rule = (int32_t)fills[i].fill_rule;
+            ffi[i].paint = fills[i].paint->ffi();
+            ffi[i].path_bbox = fills[i].path_bbox;
+            ffi[i].x = fills[i].x; ffi[i].y = fills[i].y; ffi[i].width = fills[i].width; ffi[i].height = fills[i].height;
+        }
+        std::vector<uint8_t> rgba(width * height * 4);
+        if (lin) lin->assign(width * height * 4, 0.0f);
+        check(rgpu_render_scene_host(ctx_, ffi.data(), ffi.size(), width, height, bg, lin ? lin->data() : nullptr, rgba.data()));
+        return rgba;
+    }
     rgpu_ctx* raw() { return ctx_; }
     void check(int rc) const {
         if (rc != RGPU_OK) throw Error(rc, rgpu_last_error(ctx_));

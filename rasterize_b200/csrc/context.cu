@@ -90,7 +90,9 @@ struct rgpu_ctx {
     struct TableShadow {
         std::vector<unsigned char> bytes;
         const void* dev = nullptr;
-    } jobs_shadow, paints_shadow;
+    } jobs_shadow, paints_shadow, lists_shadow;
+    DevBuf scene_lists;                  // per-band job lists of a scene batch (SceneArgs::band_offs / band_jobs)
+    std::vector<uint32_t> h_scene_lists;
     uint32_t last_tiles = 0;
     // pinned host
     Status* h_status = nullptr;
@@ -653,6 +655,31 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     double4* d_refs = static_cast<double4*>(ctx->refs.p);
     unsigned long long* d_state = static_cast<unsigned long long*>(ctx->tile_state.p);
 
+    if (scene) {
+        // per-band job lists (CSR, submission order inside a band): [offsets: n_bands + 1 | job indices]
+        scene->n_bands = (scene->height + ts.th - 1) / ts.th;
+        scene->n_chunks = (scene->width + ts.cw - 1) / ts.cw;
+        std::vector<uint32_t>& L = ctx->h_scene_lists;
+        const uint32_t nb = scene->n_bands;
+        L.assign(nb + 1, 0u);
+        for (uint32_t j = 0; j < n_live; j++) {
+            const JobDev& d = ctx->h_jobs[j];
+            for (uint32_t b = 0; b < d.n_bands; b++) L[d.sb0 + b + 1]++;
+        }
+        for (uint32_t b = 0; b < nb; b++) L[b + 1] += L[b];
+        const uint32_t total = L[nb];
+        L.resize(nb + 1 + total);
+        std::vector<uint32_t> cur(L.begin(), L.begin() + nb);
+        for (uint32_t j = 0; j < n_live; j++) {
+            const JobDev& d = ctx->h_jobs[j];
+            for (uint32_t b = 0; b < d.n_bands; b++) L[nb + 1 + cur[d.sb0 + b]++] = j;
+        }
+        if ((rc = ensure_dev(ctx, ctx->scene_lists, sizeof(uint32_t) * L.size()))) return rc;
+        bool up_lists = false;
+        if ((rc = upload_table(ctx, ctx->lists_shadow, ctx->scene_lists.p, L.data(), sizeof(uint32_t) * L.size(), up_lists))) return rc;
+        scene->band_offs = static_cast<const uint32_t*>(ctx->scene_lists.p);
+        scene->band_jobs = scene->band_offs + nb + 1;
+    }
     // a single job travels in the kernel parameters; a table is uploaded only for multi-job batches
     {
         bool uploaded = false;
@@ -677,8 +704,6 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     const bool pdl_ok = fixed && !prof && !no_pdl;
     const bool zero_early = est_lines + est_lines / 2 >= 2ull * tile_acc;  // most tiles will hold lines
     if (scene) {
-        scene->n_bands = (scene->height + ts.th - 1) / ts.th;
-        scene->n_chunks = (scene->width + ts.cw - 1) / ts.cw;
         launch_scene(d_jobs, n_live, d_paints, d_bo, bin_cap, d_refs, d_state, ctx->epoch, d_tickets, d_status, *scene, /*pdl=*/pdl_ok && item_acc != 0, s);
         ctx->n_launches += 1;
     } else if (flags & RGPU_BATCH_INDEPENDENT) {
@@ -810,7 +835,7 @@ void rgpu_destroy(rgpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->jobs, &ctx->paints, &ctx->slot_counts, &ctx->slot_offs, &ctx->lines, &ctx->line_job, &ctx->zero_block, &ctx->tile_offs,
-                      &ctx->tile_state, &ctx->fixed_block, &ctx->refs, &ctx->scan_temp, &ctx->status, &ctx->img_f32, &ctx->img_f64, &ctx->img_lin, &ctx->tmp_pts, &ctx->tmp_items};
+                      &ctx->tile_state, &ctx->fixed_block, &ctx->refs, &ctx->scan_temp, &ctx->status, &ctx->img_f32, &ctx->img_f64, &ctx->img_lin, &ctx->tmp_pts, &ctx->tmp_items, &ctx->scene_lists};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);

@@ -140,6 +140,10 @@ struct SceneArgs {
     uint32_t n_bands, n_chunks; // layer tile grid
     float bg[4];                // fresh != 0: every pixel starts from this colour (`Layer::new`), else from the layer's content
     int fresh, store_lin;
+    // jobs whose window reaches layer band B, in submission order: band_jobs[band_offs[B] .. band_offs[B + 1])
+    // (a CTA walks only those instead of the whole job table; filled in by the host, context.cu)
+    const uint32_t* band_offs;
+    const uint32_t* band_jobs;
 };
 TileShape scene_tile_shape();
 void launch_scene(const JobDev* jobs, uint32_t n_jobs, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,

@@ -128,8 +128,8 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
     __syncthreads();
     if (s_bad) {
         // the host re-runs (or reports): leave the layer as it was and the tile counters clean
-        for (uint32_t j = tid; j < n_jobs; j += kScThreads) {
-            const JobDev& job = jobs[j];
+        for (uint32_t k = sc.band_offs[B] + tid; k < sc.band_offs[B + 1]; k += kScThreads) {
+            const JobDev& job = jobs[sc.band_jobs[k]];
             const int b = B - job.sb0, c = C - job.sc0;
             if (b >= 0 && b < (int)job.n_bands && c >= 0 && c < (int)job.n_chunks) tile_offs[job.tile_begin + (uint32_t)b * job.n_chunks + (uint32_t)c] = 0u;
         }
@@ -139,8 +139,9 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
     bool dirty = sc.fresh != 0;
     ScSpanT* spans = spans_all + warp * kScSpanCap;
 
-    for (uint32_t j = 0; j < n_jobs; j++) {
-        const JobDev& job = jobs[j];
+    const uint32_t k_end = sc.band_offs[B + 1];
+    for (uint32_t k = sc.band_offs[B]; k < k_end; k++) {
+        const JobDev& job = jobs[sc.band_jobs[k]];
         const int b = B - job.sb0, c = C - job.sc0;
         if (b < 0 || b >= (int)job.n_bands || c < 0 || c >= (int)job.n_chunks) continue;  // uniform for the CTA
         const uint32_t tile = job.tile_begin + (uint32_t)b * job.n_chunks + (uint32_t)c;

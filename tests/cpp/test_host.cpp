@@ -108,12 +108,44 @@ static void test_layers(GpuRasterizer& r) {
     CHECK(rgba[3] == 255 && rgba[0] >= 123 && rgba[0] <= 125);
 }
 
+// `Scene::render` of a Fill-only pipeline through the scene compositor (one raster launch) against the same fills applied
+// one by one with the trait's `fill` on a host image: identical bits, and the RGBA8 export of that image.
+static void test_scene(GpuRasterizer& r) {
+    const size_t W = 700, H = 40;
+    const float bg[4] = {0.1f, 0.1f, 0.1f, 1.0f};
+    Path star = Path::builder().move_to({50, 0}).line_to({21, 90}).line_to({98, 35}).line_to({2, 35}).line_to({79, 90}).close().build();
+    Path blob = Path::builder().move_to({10, 10}).cubic_to({200, -30}, {400, 80}, {650, 5}).quad_to({300, 60}, {10, 30}).close().build();
+    Paint red = Paint::solid(0.5f, 0.0f, 0.0f, 0.5f), green = Paint::solid(0.0f, 0.3f, 0.0f, 0.3f);
+    // windows at unaligned offsets inside the layer; paths in window-local coordinates
+    std::vector<GpuRasterizer::SceneFill> fills = {
+        {&blob, Transform::identity(), FillRule::NonZero, &red, 13, 3, 680, 36},
+        {&star, Transform::new_translate(-3.0, -20.0), FillRule::EvenOdd, &green, 301, 7, 95, 30},
+        {&blob, Transform::new_translate(-100.0, 0.0), FillRule::EvenOdd, &green, 0, 0, 700, 40},
+    };
+    std::vector<float> lin;
+    const std::vector<uint8_t> rgba = r.render_scene(fills, W, H, bg, &lin);
+    std::vector<float> ref(W * H * 4);
+    for (size_t i = 0; i < W * H; i++) for (int c = 0; c < 4; c++) ref[i * 4 + c] = bg[c];
+    for (auto& f : fills) {
+        ImageMut<float> view{ref.data(), rgpu_shape{(size_t)f.y * W + f.x, f.width, f.height, W, 1}};
+        r.fill(*f.path, f.tr, f.fill_rule, *f.paint, view);
+    }
+    bool drew = false;
+    for (size_t i = 0; i < ref.size(); i++) {
+        CHECK(ref[i] == lin[i]);
+        drew = drew || (i % 4 == 0 && ref[i] > 0.3f);
+    }
+    CHECK(drew);
+    CHECK(rgba[3] == 255 && rgba.size() == W * H * 4);
+}
+
 int main() {
     GpuRasterizer r;
     CHECK(std::string(r.name()) == "gpu-signed-difference");
     test_rasterizer(r);
     test_fill_rule(r);
     test_layers(r);
+    test_scene(r);
     // NaN control point -> error (reference panics, src/path.rs:765-767)
     Path bad = Path::builder().move_to({0, 0}).quad_to({std::nan(""), 1}, {2, 2}).build();
     bool threw = false;

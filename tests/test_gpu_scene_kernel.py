@@ -115,7 +115,7 @@ def synthetic_jobs(rast, W, H, n_jobs, seed, max_w, max_h):
 
 
 @pytest.mark.parametrize("W,H,n_jobs,max_w,max_h", [(1300, 70, 24, 1300, 70), (517, 33, 40, 200, 33), (2049, 19, 12, 2049, 19), (64, 64, 6, 64, 64),
-                                                   (1536, 24, 30, 1100, 24)])
+                                                   (1536, 24, 30, 1100, 24), (900, 120, 600, 80, 60)])
 def test_unaligned_windows_bit_identical(rast, W, H, n_jobs, max_w, max_h):
     make = synthetic_jobs(rast, W, H, n_jobs, seed=W + H, max_w=max_w, max_h=max_h)
     lin_a, rgba_a, lin_b, rgba_b = both_ways(rast, make, W, H, bg=[0.1, 0.2, 0.3, 0.5])
