@@ -326,7 +326,7 @@ def run_ours(args):
         "bound": "hbm", "kernel": ("scene_kernel (K3 + K4 for every fill of the layer + Layer::new + RGBA8 export)" if scn else
                                    "raster_kernel (K3: accumulate + row scan + fill rule + store)"),
         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "peak_source": peak_src,
-        "traffic": recorded_traffic(args.workload),
+        "traffic": recorded_traffic(args.workload + ("_mask" if args.workload == "c4" and os.environ.get("RB_C4_MASK") else "")),
         "algorithmic_bytes_per_launch": info["out_bytes"], "kernel_ms": round(float(stage_ms[2]), 5),
         "stage_ms": {"flatten_and_bin": round(float(stage_ms[0]), 5), "two_pass_only_scan_and_emit": round(float(stage_ms[1]), 5),
                      "raster": round(float(stage_ms[2]), 5)},

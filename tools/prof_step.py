@@ -21,9 +21,23 @@ rast = rb.GpuRasterizer(device=0)
 jobs, independent, info = bench.build_workload(workload, rb, rast, 0, 1, torch)
 prepared = rast.prepare_batch(jobs)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-rast.submit_prepared(prepared, independent=independent, sync=True)
+scn = info.get("scene")
+
+
+def step():
+    if scn:  # c1 / c3: the scene compositor
+        rast.submit_scene_prepared(prepared, scn["layer"], scn["W"], scn["H"], fresh=True, bg=scn["bg"], rgba_ptr=scn["rgba"], sync=True)
+        return
+    if info.get("pre_step"):
+        info["pre_step"]()
+    rast.submit_prepared(prepared, independent=independent, sync=True)
+    if info.get("post_step"):
+        info["post_step"]()
+
+
+step()
 for _ in range(steps):
     flush.zero_()
     torch.cuda.synchronize()
-    rast.submit_prepared(prepared, independent=independent, sync=True)
+    step()
 print("ok", rast.last_counts())
