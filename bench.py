@@ -508,47 +508,99 @@ def cpu_reference_other(workload: str, budget_s: float):
 
 def run_reference(args):
     """`--impl reference`: the reference's CPU implementation of the path on the host cores.  The Rust crate cannot
-    be compiled in this image (no cargo/rustc), so this is the oracle port with all the host threads it can use
-    (rows are independent: one band of rows per thread)."""
+    be compiled in this image (no cargo/rustc), so this is the oracle port with all the host threads the workload can
+    use: rows are independent (c2, c5: one band of rows per thread), glyphs are independent (c4: glyphs dealt out over
+    std::threads, one private image each); a scene's fills blend in order onto one layer, so c1 / c3 run on one thread
+    exactly like the single-threaded reference.  Every step is a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    if args.workload != "c2":
-        _emit(json.dumps({"impl": "reference", "unavailable": "reference arm is implemented for the c2 workload"}))
-        return
     threads = os.cpu_count() or 1
     import oracle as O
-    from rasterize_b200 import assets
-    p = assets.load_path("material")
-    c2 = assets.expected()["paths"]["material"]["c2"]
-    w, h = c2["size"]
-    tr = np.array(c2["tr"])
-    op = O.OraclePath.from_flat(p.points, p.kinds, p.subpath_offsets, p.closed)
-    img = np.zeros((h, w))
+    from rasterize_b200 import assets, sharding
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    steps = min(args.steps, 60)
-    for _ in range(min(max(args.warmup, 1), 5)):
-        img[:] = 0
-        op.mask_threads(tr, O.NONZERO, img, threads)
+    wl = args.workload
+    metric = "fill throughput (Rasterizer::mask, nonzero), pixels rasterized per second"
+    lines = None
+    if wl in ("c2", "c5"):
+        name, key = ("material", "c2") if wl == "c2" else ("tv_stroked", "c5")
+        p = assets.load_path(name)
+        e = assets.expected()["paths"][name][key]
+        w, h = e["size"]
+        tr = np.array(e["tr"])
+        what = "c2: data/material.path (21106 segments) fitted to 4096x4096, Rasterizer::mask, nonzero"
+        sample_of = f"material.path at {w}x{h}"
+        if wl == "c5":
+            y0, y1 = sharding.band_rows(h, 2, 8)  # a band that holds lines (band 0 is empty)
+            tr = sharding.band_transform(e["tr"], y0)
+            what = f"c5: tv.path stroked (w=0.5 round/round) on a {w}x{h} canvas, band 2 of 8 ({y1 - y0} rows), mask, nonzero"
+            sample_of = f"band 2 of 8 ({w}x{y1 - y0}) of tv.path stroked"
+            h = y1 - y0
+        else:
+            lines = e["lines"]
+        op = O.OraclePath.from_flat(p.points, p.kinds, p.subpath_offsets, p.closed)
+        img = np.zeros((h, w))
+        canvas, items = [w, h], 1
+
+        def one_step():
+            img[:] = 0
+            op.mask_threads(tr, O.NONZERO, img, threads)
+
+        px, max_steps = w * h, (60 if wl == "c2" else 6)
+        sample = f"(clear + mask) of {sample_of}, {threads} threads (one band of rows each)"
+    elif wl == "c4":
+        n_glyphs = 4000
+        as_mask = bool(os.environ.get("RB_C4_MASK"))
+        glyphs = [O.OraclePath.glyph(i + 1) for i in range(n_glyphs)]
+        black = O.OraclePaint.solid([0.0, 0.0, 0.0, 1.0])
+
+        def one_step():
+            O.batch_threads(glyphs, O.IDENTITY, O.NONZERO, None if as_mask else black, 64, 64, threads)
+
+        metric = metric if as_mask else "fill throughput (Rasterizer::fill, solid paint, nonzero), pixels rasterized per second"
+        what = (f"c4: synthetic random-cubic glyphs at 64x64, {'Rasterizer::mask' if as_mask else 'Rasterizer::fill with solid black onto a fresh LinColor canvas'} "
+                "per glyph, nonzero")
+        canvas, items = [64, 64], n_glyphs
+        px, max_steps = n_glyphs * 4096, 20
+        sample = f"{n_glyphs} glyph {'masks' if as_mask else 'solid fills'} (clear + call) dealt out over {threads} std::threads (one private image per thread)"
+    else:  # c1 / c3: order-dependent fills on one layer -> one thread, like the reference
+        from helpers import render_scene_oracle
+        sc = assets.load_scene("squirrel_cli_512" if wl == "c1" else "firefox_2048")
+        threads = 1
+        shape = []
+
+        def one_step():
+            img = render_scene_oracle(sc)
+            O.lin_to_rgba(img)
+            shape[:] = [img.shape[1], img.shape[0]]
+
+        one_step()
+        metric = "scene render throughput (Scene::render fills + RGBA8 export), pixels per second"
+        what = ("c1: examples/rasterize scene of data/squirrel.path at 512 px (checkerboard + fill over #f0f0f0)" if wl == "c1"
+                else "c3: data/firefox.scene Scene::render at 2048x2048, 14 linear/radial gradient fills") + ", Scene::render + RGBA8 export"
+        canvas, items = list(shape), len(sc.fills)
+        px, max_steps = shape[0] * shape[1], (100 if wl == "c1" else 12)
+        sample = "Scene::render + RGBA8 export through the oracle's Rasterizer::fill, 1 thread (fills blend in order)"
+    steps = max(1, min(args.steps, max_steps))
+    warm = min(max(args.warmup, 1), 3)
+    for _ in range(warm):
+        one_step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        img[:] = 0
-        op.mask_threads(tr, O.NONZERO, img, threads)
+        one_step()
     dt = (time.perf_counter() - t0) / steps
-    value = round(w * h / dt / 1e6, 1)
-    lines = assets.expected()["paths"]["material"]["c2"]["lines"]
+    value = round(px / dt / 1e6, 1)
     out = {
-        "impl": "reference", "metric": "fill throughput (Rasterizer::mask, nonzero), pixels rasterized per second", "value": value,
-        "unit": "Mpix/s", "n_gpus": world, "steps": steps, "warmup": min(max(args.warmup, 1), 5), "ms_per_step": round(dt * 1e3, 4),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "reference asset (flat fixture of data/*.path)",
-        "config": {"workload": "c2: data/material.path (21106 segments) fitted to 4096x4096, Rasterizer::mask, nonzero", "canvas": [w, h],
-                   "items_per_gpu": 1, "flatness": 0.05},
-        "lines_per_s": round(lines / dt, 1),
-        "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps} x (clear + mask) of material.path at {w}x{h}, {threads} threads (one band of rows each)"},
+        "impl": "reference", "metric": metric, "value": value,
+        "unit": "Mpix/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": round(dt * 1e3, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic" if wl == "c4" else "reference asset (flat fixture of data/*.path)",
+        "config": {"workload": what, "canvas": canvas, "items_per_gpu": items, "flatness": 0.05},
+        "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": threads, "kind": "port", "sample": f"{steps} x {sample}", "host_cores": os.cpu_count()},
         "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if lines is not None:
+        out["lines_per_s"] = round(lines / dt, 1)
     _emit(json.dumps(out))
 
 

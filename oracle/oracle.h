@@ -150,6 +150,9 @@ long orc_scene_pipeline(const orc_scene*, const double tr[6], const double* view
 double orc_lcg_uniform(uint32_t* state);
 /* synthetic glyph of SURVEY §8d C4: 3 closed contours x 6 cubics, coords uniform()*56+4, seed = index+1 */
 orc_path* orc_glyph(uint32_t seed);
+/* n independent paths on `threads` host threads, each into a private w x h image: clear + mask (paint NULL) or clear + fill */
+int orc_batch_threads(const orc_path* const* paths, size_t n, const double tr[6], double flatness, int fill_rule, const orc_paint* paint,
+                      size_t w, size_t h, int threads);
 
 #ifdef __cplusplus
 }

@@ -186,6 +186,37 @@ int orc_mask_threads(const orc_path* p, const double tr[6], double flatness, int
     for (auto& t : ts) t.join();
     return 0;
 }
+// A batch of independent paths on `threads` host threads (bench.py --impl reference, config 4): thread k takes paths
+// k, k + threads, ... and renders each into its own w x h scratch image — `img.clear()` + `Rasterizer::mask` when
+// paint is NULL, `ImageOwned::new_default` + `Rasterizer::fill` otherwise — exactly what a caller of the
+// single-threaded reference would do with one rasterizer per thread.
+int orc_batch_threads(const orc_path* const* paths, size_t n, const double tr[6], double flatness, int rule, const orc_paint* paint,
+                      size_t w, size_t h, int threads) {
+    if (threads < 1) threads = 1;
+    std::vector<int> rc((size_t)threads, 0);
+    auto work = [&](int k) {
+        try {
+            Shape sh = Shape::simple(h, w);
+            std::vector<Scalar> m(paint ? 0 : w * h);
+            std::vector<LinColor> c(paint ? w * h : 0);
+            for (size_t i = (size_t)k; i < n; i += (size_t)threads) {
+                if (paint) {
+                    std::fill(c.begin(), c.end(), LinColor{});
+                    fill(paths[i]->p, TR(tr), flatness, (FillRule)rule, paint->p, c.data(), sh);
+                } else {
+                    std::fill(m.begin(), m.end(), 0.0);
+                    mask(paths[i]->p, TR(tr), flatness, (FillRule)rule, m.data(), m.size(), sh);
+                }
+            }
+        } catch (const std::exception&) { rc[(size_t)k] = -1; }
+    };
+    if (threads == 1) { work(0); return rc[0]; }
+    std::vector<std::thread> ts;
+    for (int k = 0; k < threads; k++) ts.emplace_back(work, k);
+    for (auto& t : ts) t.join();
+    for (int r : rc) if (r) { g_err = "orc_batch_threads: a path failed"; return -1; }
+    return 0;
+}
 long orc_mask_iter(const orc_path* p, const double tr[6], double flatness, size_t w, size_t h, int rule, orc_pixel* out, size_t cap) {
     size_t n = 0;
     try {

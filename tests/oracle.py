@@ -99,6 +99,7 @@ def lib():
     sig("orc_mask", i32, vp, pd, dbl, i32, pd, sz, Shape)
     sig("orc_mask_threads", i32, vp, pd, dbl, i32, pd, sz, sz, i32)
     sig("orc_mask_iter", C.c_long, vp, pd, dbl, sz, sz, i32, C.POINTER(PixelS), sz)
+    sig("orc_batch_threads", i32, C.POINTER(vp), sz, pd, dbl, i32, vp, sz, sz, i32)
     sig("orc_fill", i32, vp, pd, dbl, i32, vp, pf, Shape)
     sig("orc_rgba_to_lin", None, pu8, pf)
     sig("orc_lin_to_rgba", None, pf, pu8)
@@ -275,6 +276,15 @@ class OraclePath:
         if rc:
             raise ValueError(lib().orc_last_error().decode())
         return img
+
+
+def batch_threads(paths, tr, rule, paint, w: int, h: int, threads: int, flatness=DEFAULT_FLATNESS) -> None:
+    """n independent paths on `threads` host threads (std::thread inside the oracle), each rendered into a private
+    w x h image: clear + `Rasterizer::mask` (paint None) or clear + `Rasterizer::fill`.  Timing helper of bench.py."""
+    arr = (C.c_void_p * len(paths))(*[p.h for p in paths])
+    rc = lib().orc_batch_threads(arr, len(paths), _pd(_tr(tr)), flatness, rule, paint.h if paint is not None else None, w, h, threads)
+    if rc:
+        raise ValueError(lib().orc_last_error().decode())
 
 
 class OraclePaint:

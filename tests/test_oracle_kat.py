@@ -435,3 +435,10 @@ def test_right_edge_wrap_quirk():
         [0.0, 0.0, 0.0, 0.0, 0.0, 0.0],
     ])
     np.testing.assert_allclose(img, expected, atol=1e-12)
+
+
+def test_batch_threads_helper_runs():
+    """bench.py's multi-threaded CPU arm for glyph batches (timing helper: it renders into private scratch images)."""
+    glyphs = [O.OraclePath.glyph(i + 1) for i in range(5)]
+    O.batch_threads(glyphs, O.IDENTITY, O.NONZERO, None, 64, 64, 2)
+    O.batch_threads(glyphs, O.IDENTITY, O.EVENODD, O.OraclePaint.solid([0.0, 0.0, 0.0, 1.0]), 64, 64, 3)
