@@ -33,6 +33,8 @@ using namespace fl;
 constexpr int kWarpQueue = 96;                 // leaves a warp parks in shared memory before binning them (flatten_bin_kernel<2>)
 constexpr int kDeepCutDepth = 5;              // 32 slots per item for small batches (see launch_flatten_bin_fixed)
 constexpr uint32_t kDeepCutMaxItems = 8192;
+constexpr int kDeepestCutDepth = 7;           // 128 slots per item for tiny batches (one outline, one scene)
+constexpr uint32_t kDeepestCutMaxItems = 512;
 
 // Ordered two-pass form (count, [scan], emit): lines land in the reference's exact order — `Path::flatten` parity.
 template <bool EMIT>
@@ -211,6 +213,9 @@ int flatten_cut_depth(uint32_t total_items) {
     // Few items (a scene's fills, one stroked outline): cut every subdivision tree two levels deeper, 32 slots per curve —
     // four times the threads, each with a quarter of the subtree, because such batches are bound by the longest
     // depth-first walk, not by throughput.
+    static const int forced = getenv("RGPU_CUT_DEPTH") ? atoi(getenv("RGPU_CUT_DEPTH")) : 0;  // tuning: 3..9
+    if (forced >= 3 && forced <= 9) return forced;
+    if (total_items <= kDeepestCutMaxItems) return kDeepestCutDepth;
     return total_items <= kDeepCutMaxItems ? kDeepCutDepth : kSlotDepth;
 }
 
@@ -219,15 +224,19 @@ void launch_flatten_bin_fixed(const JobDev* jobs, const JobDev* h_jobs, uint32_t
                               Status* next_status, cudaStream_t s) {
     if (total_threads == 0) return;
     const uint32_t grid = (total_threads + 127) / 128;
-    if (depth == kDeepCutDepth) {
-        flatten_bin_kernel<2, kDeepCutDepth><<<grid, 128, 0, s>>>(n_jobs == 1 ? nullptr : jobs, n_jobs, h_jobs[0], total_threads, thr, tile_counts,
-                                                                  nullptr, 0, bin_lines, bin_cap, log2i(band_rows), log2i(chunk_cols), status,
-                                                                  next_status);
-    } else {
-        flatten_bin_kernel<2, kSlotDepth><<<grid, 128, 0, s>>>(n_jobs == 1 ? nullptr : jobs, n_jobs, h_jobs[0], total_threads, thr, tile_counts,
-                                                               nullptr, 0, bin_lines, bin_cap, log2i(band_rows), log2i(chunk_cols), status,
-                                                               next_status);
+#define RGPU_FLAT(D)                                                                                                                      \
+    flatten_bin_kernel<2, D><<<grid, 128, 0, s>>>(n_jobs == 1 ? nullptr : jobs, n_jobs, h_jobs[0], total_threads, thr, tile_counts, nullptr, 0, \
+                                                  bin_lines, bin_cap, log2i(band_rows), log2i(chunk_cols), status, next_status)
+    switch (depth) {
+        case 4: RGPU_FLAT(4); break;
+        case 5: RGPU_FLAT(5); break;
+        case 6: RGPU_FLAT(6); break;
+        case 7: RGPU_FLAT(7); break;
+        case 8: RGPU_FLAT(8); break;
+        case 9: RGPU_FLAT(9); break;
+        default: RGPU_FLAT(kSlotDepth); break;
     }
+#undef RGPU_FLAT
 }
 
 }  // namespace rgpu

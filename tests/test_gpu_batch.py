@@ -160,8 +160,10 @@ def test_render_jobs_create_their_canvas(rast):
     glyphs = [bench.glyph_path(rb, i + 1) for i in range(n)]
     dps = [rast.upload(g) for g in glyphs]
     ident = rb.Transform.identity()
-    paint = rb.LinColor(0.1, 0.2, 0.3, 0.6)
-    for w, h, tr in ((64, 64, ident), (300, 200, rb.Transform.new_scale(300 / 64.0, 200 / 64.0))):
+    grad = rb.GradRadial([(0.0, [0.8, 0.1, 0.1, 0.9]), (0.5, [0.1, 0.7, 0.2, 1.0]), (1.0, [0.0, 0.0, 0.3, 0.3])], rb.Units.UserSpaceOnUse, False,
+                         rb.GradSpread.Reflect, rb.Transform.identity(), (30.0, 34.0), 25.0, (26.0, 30.0), 3.0)
+    for (w, h, tr), paint in (((64, 64, ident), rb.LinColor(0.1, 0.2, 0.3, 0.6)), ((300, 200, rb.Transform.new_scale(300 / 64.0, 200 / 64.0)), rb.LinColor(0.1, 0.2, 0.3, 0.6)),
+                              ((64, 64, ident), grad), ((61, 47, ident), grad)):
         nb = n * w * h * 16
         slab = rast.device_alloc(nb)
         rast.device_zero(slab, nb)
@@ -179,6 +181,6 @@ def test_render_jobs_create_their_canvas(rast):
     slab = rast.device_alloc(64 * 64 * 16)
     rast.to_device(slab, np.full((64, 64, 4), 3.0, dtype=np.float32))
     empty = rast.upload(rb.Path.empty())
-    rast.render_batch([rb.Job(empty, ident, rb.FillRule.NonZero, ffi.JOB_RENDER, slab, 64, 64, 64, paint=paint)], independent=True)
+    rast.render_batch([rb.Job(empty, ident, rb.FillRule.NonZero, ffi.JOB_RENDER, slab, 64, 64, 64, paint=grad)], independent=True)
     assert not rast.to_host(slab, (64, 64, 4), np.float32).any()
     rast.device_free(slab)

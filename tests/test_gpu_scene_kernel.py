@@ -90,9 +90,14 @@ def synthetic_jobs(rast, W, H, n_jobs, seed, max_w, max_h):
         a = float(rng.uniform(0.3, 1.0))
         rgb = rng.uniform(0.0, 1.0, 3) * a
         kind = k % 3
+        bbox = None
         stops = [(0.0, [*(rng.uniform(0, 1, 3) * 0.8), 0.8]), (0.6, [0.1, 0.9, 0.3, 1.0]), (1.0, [*rng.uniform(0, 1, 3), 1.0])]
         if kind == 0:
             paint = rb.LinColor(float(rgb[0]), float(rgb[1]), float(rgb[2]), a)
+        elif kind == 1 and k % 2:
+            # objectBoundingBox units: resolved through the path's bbox (src/rasterize.rs:85-91)
+            paint = rb.GradLinear(stops, rb.Units.BoundingBox, bool(k & 2), rb.GradSpread(k % 3), rb.Transform.identity(), (0.1, 0.2), (0.9, 0.7))
+            bbox = np.array([4.0, 4.0, 60.0, 60.0])
         elif kind == 1:
             paint = rb.GradLinear(stops, rb.Units.UserSpaceOnUse, bool(k & 1), rb.GradSpread(k % 3), rb.Transform.identity(), (4.0, 8.0), (60.0, 50.0))
         else:
@@ -101,14 +106,14 @@ def synthetic_jobs(rast, W, H, n_jobs, seed, max_w, max_h):
         # the glyph overhangs the window on every side for some jobs (exercises the x < 0 / x > width / y clipping)
         s = float(rng.uniform(0.8, 1.4))
         tr = rb.Transform.new_translate(float(rng.uniform(-0.2, 0.1)) * w, float(rng.uniform(-0.2, 0.1)) * h) * rb.Transform.new_scale(s * w / 64.0, s * h / 64.0)
-        specs.append((bench.glyph_path(rb, 1000 * seed + k + 1), tr, rb.FillRule(k % 2), paint, x, y, w, h))
+        specs.append((bench.glyph_path(rb, 1000 * seed + k + 1), tr, rb.FillRule(k % 2), paint, x, y, w, h, bbox))
 
     def make(layer):
         jobs, keep = [], []
-        for path, tr, rule, paint, x, y, w, h in specs:
+        for path, tr, rule, paint, x, y, w, h, bbox in specs:
             dp = rast.upload(path)
             keep.append(dp)
-            jobs.append(rb.Job(dp, tr, rule, ffi.JOB_FILL, layer, w, h, W, origin=y * W + x, paint=paint))
+            jobs.append(rb.Job(dp, tr, rule, ffi.JOB_FILL, layer, w, h, W, origin=y * W + x, paint=paint, path_bbox=bbox))
         return jobs, keep
 
     return make
