@@ -119,6 +119,12 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
     const int wout = job.width_out, hout = job.height;
     const int half = lane >> 4, hl = lane & 15;
     const bool evenodd = job.rule == 1;
+    // per-thread constants of the composite loop: a solid paint is its colour (glyph batches), the canvas window's base
+    const bool solid = mode >= kModeFill && (job.paint_index < 0 || s_paint.kind == 0);
+    const float4 solid_c = (mode >= kModeFill && job.paint_index >= 0) ? make_float4(s_paint.solid[0], s_paint.solid[1], s_paint.solid[2], s_paint.solid[3])
+                                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* const out_base = reinterpret_cast<float4*>(job.canvas) + job.origin;
+    const unsigned long long row_stride = job.row_stride;
     for (int r2 = warp * 2; r2 < hout; r2 += kSmWarps * 2) {
         const int r = r2 + half;
         const bool rvalid = r < hout;
@@ -169,9 +175,9 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
                 const int rr = r2 + (pidx >> 6), px = pidx & 63;
                 if (rr < hout && px < wout) {
                     const float alpha = reinterpret_cast<const float*>(cells + rr * kSmPitch)[px];
-                    float4* out = reinterpret_cast<float4*>(job.canvas) + job.origin + (unsigned long long)rr * job.row_stride;
+                    float4* out = out_base + (unsigned long long)rr * row_stride;
                     if (alpha >= 1e-6f) {
-                        float4 color = (job.paint_index >= 0) ? paint_at(s_paint, px, rr) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 color = solid ? solid_c : paint_at(s_paint, px, rr);
                         color = make_float4(fmul(color.x, alpha), fmul(color.y, alpha), fmul(color.z, alpha), fmul(color.w, alpha));
                         float4 dstc = render ? make_float4(0.f, 0.f, 0.f, 0.f) : out[px];  // `Layer::new`: transparent
                         const float k = fsub(1.0f, color.w);
