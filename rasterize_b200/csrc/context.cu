@@ -674,11 +674,25 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
             const JobDev& d = ctx->h_jobs[j];
             for (uint32_t b = 0; b < d.n_bands; b++) L[nb + 1 + cur[d.sb0 + b]++] = j;
         }
+        {
+            // band order: estimated work (sum of the window widths of the band's jobs) descending, ties by index
+            std::vector<std::pair<uint64_t, uint32_t>> key(nb);
+            for (uint32_t b = 0; b < nb; b++) {
+                uint64_t wsum = 0;
+                for (uint32_t k = L[b]; k < L[b + 1]; k++) wsum += (uint64_t)ctx->h_jobs[L[nb + 1 + k]].width_out;
+                key[b] = {~wsum, b};  // ascending sort of (~work, index)
+            }
+            std::sort(key.begin(), key.end());
+            const size_t base = L.size();
+            L.resize(base + nb);
+            for (uint32_t b = 0; b < nb; b++) L[base + b] = key[b].second;
+        }
         if ((rc = ensure_dev(ctx, ctx->scene_lists, sizeof(uint32_t) * L.size()))) return rc;
         bool up_lists = false;
         if ((rc = upload_table(ctx, ctx->lists_shadow, ctx->scene_lists.p, L.data(), sizeof(uint32_t) * L.size(), up_lists))) return rc;
         scene->band_offs = static_cast<const uint32_t*>(ctx->scene_lists.p);
         scene->band_jobs = scene->band_offs + nb + 1;
+        scene->band_order = scene->band_offs + (L.size() - nb);
     }
     // a single job travels in the kernel parameters; a table is uploaded only for multi-job batches
     {

@@ -144,6 +144,9 @@ struct SceneArgs {
     // (a CTA walks only those instead of the whole job table; filled in by the host, context.cu)
     const uint32_t* band_offs;
     const uint32_t* band_jobs;
+    // bands in the order the tickets take them inside a column of tiles: heaviest first (bands are independent of one
+    // another; only the chunks of a band are chained), so the last CTAs of the launch are the cheap ones
+    const uint32_t* band_order;
 };
 TileShape scene_tile_shape();
 void launch_scene(const JobDev* jobs, uint32_t n_jobs, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,

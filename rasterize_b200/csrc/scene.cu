@@ -100,7 +100,7 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
     const uint32_t n_tiles = sc.n_bands * sc.n_chunks;
     const uint32_t t = s_ticket;
     // chunk-major order: the left neighbour of a tile started a column of bands earlier
-    const int C = (int)(t / sc.n_bands), B = (int)(t - (uint32_t)C * sc.n_bands);
+    const int C = (int)(t / sc.n_bands), B = (int)sc.band_order[t - (uint32_t)C * sc.n_bands];
     const int X0 = C * kScW, Y0 = B * kScH;
     const int tw = min(kScW, (int)sc.width - X0), th = min(kScH, (int)sc.height - Y0);
     // The tile's pixels: `Layer::new` background, or what the layer holds (fills queued after a clip / opacity group).
