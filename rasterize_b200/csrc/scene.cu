@@ -28,6 +28,7 @@ using namespace rs;
 
 constexpr int kScH = 8;
 constexpr int kScSpanCap = 208;       // per-warp span list (lane << 3 | row)
+constexpr int kScPre = 32;            // fills of a tile whose bin counter / carry words are fetched up front
 using ScSpanT = unsigned char;
 constexpr size_t kScPaintBytes = 2048;  // the paint sits at the start of the piece constants ...
 static_assert(kScPaintBytes >= sizeof(PaintDev), "the paint is staged over the piece constants");
@@ -92,6 +93,8 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
     __shared__ int carry[kScH], rowtot[kScH], row_touched[kScH], row_live[kScH];
     __shared__ float row_const[kScH];
     __shared__ uint32_t s_ticket, s_count, s_bad, s_ncov;
+    __shared__ uint32_t pre_cnt[kScPre];
+    __shared__ unsigned long long pre_state[kScPre][kScH];
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -139,24 +142,51 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
     bool dirty = sc.fresh != 0;
     ScSpanT* spans = spans_all + warp * kScSpanCap;
 
-    const uint32_t k_end = sc.band_offs[B + 1];
-    for (uint32_t k = sc.band_offs[B]; k < k_end; k++) {
+    const uint32_t k_begin = sc.band_offs[B], k_end = sc.band_offs[B + 1];
+    // One memory round trip for the whole walk instead of two per fill: the bin counters of this tile's first kScPre fills
+    // and the state words of their left neighbours are fetched together up front (in chunk-major order the neighbours
+    // have normally published long ago; a word that is not ready yet is polled when its fill comes up).
+    const uint32_t n_pre = min(k_end - k_begin, (uint32_t)kScPre);
+    for (uint32_t i = tid; i < n_pre * (kScH + 1); i += kScThreads) {
+        const uint32_t kk = i / (kScH + 1), w = i - kk * (kScH + 1);
+        const JobDev& job = jobs[sc.band_jobs[k_begin + kk]];
+        const int b = B - job.sb0, c = C - job.sc0;
+        const bool mine = b >= 0 && b < (int)job.n_bands && c >= 0 && c < (int)job.n_chunks;
+        const uint32_t tile = job.tile_begin + (uint32_t)b * job.n_chunks + (uint32_t)c;
+        if (w == 0) {
+            uint32_t n = 0;
+            if (mine) {
+                n = min(tile_offs[tile], bin_cap);
+                tile_offs[tile] = 0u;  // self-cleaning counters, as in raster.cu
+            }
+            pre_cnt[kk] = n;
+        } else {
+            pre_state[kk][w - 1] = (mine && c > 0) ? ld_state(tile_state + (size_t)(tile - 1u) * kStateRows + (w - 1)) : 0ull;
+        }
+    }
+    __syncthreads();
+    for (uint32_t k = k_begin; k < k_end; k++) {
         const JobDev& job = jobs[sc.band_jobs[k]];
         const int b = B - job.sb0, c = C - job.sc0;
         if (b < 0 || b >= (int)job.n_bands || c < 0 || c >= (int)job.n_chunks) continue;  // uniform for the CTA
         const uint32_t tile = job.tile_begin + (uint32_t)b * job.n_chunks + (uint32_t)c;
         const bool chained = job.n_chunks > 1;
+        const uint32_t kk = k - k_begin;
         if (tid == 0) {
-            s_count = min(tile_offs[tile], bin_cap);
-            tile_offs[tile] = 0u;  // self-cleaning counters, as in raster.cu
+            if (kk < n_pre) {
+                s_count = pre_cnt[kk];
+            } else {
+                s_count = min(tile_offs[tile], bin_cap);
+                tile_offs[tile] = 0u;
+            }
         }
         if (tid == 32) s_ncov = 0u;
         if (tid < kScH) {
             int cin = 0;
             if (c > 0) {  // inclusive prefix of the job's tile to the left (published by the CTA of layer tile (B, C - 1))
                 const unsigned long long* ps = tile_state + (size_t)(tile - 1u) * kStateRows + tid;
-                unsigned long long v;
-                do { v = ld_state(ps); } while ((uint32_t)(v >> 34) != epoch || (v & (3ull << 32)) != kFlagPrefix);
+                unsigned long long v = (kk < n_pre) ? pre_state[kk][tid] : ld_state(ps);
+                while ((uint32_t)(v >> 34) != epoch || (v & (3ull << 32)) != kFlagPrefix) v = ld_state(ps);
                 cin = (int)(uint32_t)v;
             }
             carry[tid] = cin;
