@@ -131,7 +131,7 @@ TileShape raster_tile_shape(int variant);
 void launch_raster(int variant, const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
                    uint32_t n_tiles, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
                    unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, int pdl, cudaStream_t s);
-// Scene compositor (scene.cu): every FILL job of a layer in one launch, one CTA per 512 x 8 LAYER tile, fills blended in
+// Scene compositor (scene.cu): every FILL job of a layer in one launch, one CTA per 256 x 8 LAYER tile, fills blended in
 // submission order inside the CTA.  Jobs carry layer-aligned tile grids (JobDev::ox/oy/sc0/sb0); fixed bins only.
 struct SceneArgs {
     float4* layer;              // dense W x H LinColor layer (row pitch = width)

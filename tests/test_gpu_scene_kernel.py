@@ -5,7 +5,7 @@
 * the CPU oracle's `Scene::render` (LinColor within 2e-4, RGBA8 within 1 LSB).
 
 Covers fresh layers with and without a background, fills over an existing layer, windows that are not aligned with the
-512 x 8 layer tiles (carry chain across chunks, rows above / columns left of a window), empty batches, and the
+256 x 8 layer tiles (carry chain across chunks, rows above / columns left of a window), empty batches, and the
 two-pass fallback.  Run on a B200: pytest -m gpu."""
 import os
 import subprocess
