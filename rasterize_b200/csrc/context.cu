@@ -76,6 +76,12 @@ struct rgpu_ctx {
     DevBuf tmp_pts, tmp_items;         // device copy of the path of the current host-buffer call (grow-only, no per-call cudaMalloc)
     uint2* h_items = nullptr;          // pinned staging of the item list
     size_t h_items_cap = 0;
+    double2* h_pts = nullptr;          // pinned staging of the control points of the current host-buffer call
+    size_t h_pts_cap = 0;
+    // item lists staged by the last single-path host-buffer call, valid while tmp_items holds them (see stage_path)
+    std::vector<unsigned char> staged_meta, staged_meta_tmp;
+    rgpu_dpath staged_dp;
+    bool staged_items_valid = false;
     size_t lines_cap = 0, refs_cap = 0;
     // fixed-capacity tile bins (single flatten walk): bin_cap is the largest per-tile capacity any batch needed so
     // far; a batch whose tiles x capacity exceeds kFixedBinBudget uses the exact count -> scan -> emit scheme
@@ -264,26 +270,57 @@ int upload_path(rgpu_ctx* ctx, const rgpu_path* path, rgpu_dpath* dp) {
 
 // Device copy of a host path in the context's grow-only scratch (host-buffer entry points): no cudaMalloc / cudaFree
 // and no extra synchronisation per call; the copies are ordered before the kernels on the context's stream.
+// The control points — the call's input — go through pinned staging every time (a true asynchronous DMA instead of the
+// driver's synchronous bounce of pageable memory).  The item lists are DERIVED from the path's structure (kinds, subpath
+// offsets, closed flags): when that structure is the one staged by the previous call they are already on the device.
 int stage_path(rgpu_ctx* ctx, const rgpu_path* path, rgpu_dpath* dp) {
+    int rc;
+    const size_t pts_bytes = sizeof(double2) * path->n_points;
+    if ((rc = ensure_dev(ctx, ctx->tmp_pts, std::max<size_t>(pts_bytes, 16)))) return rc;
+    if ((rc = ensure_pinned(ctx, ctx->h_pts, ctx->h_pts_cap, std::max<size_t>(path->n_points, 1)))) return rc;
+    // a previous call's copies out of the pinned buffers have completed: every host-buffer entry point ends with a stream sync
+    dp->pts = static_cast<double2*>(ctx->tmp_pts.p);
+    dp->n_points = path->n_points;
+    if (pts_bytes) {
+        std::memcpy(ctx->h_pts, path->points, pts_bytes);
+        CK(ctx, cudaMemcpyAsync(dp->pts, ctx->h_pts, pts_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->last_h2d_bytes = pts_bytes;
+    ctx->last_d2h_bytes = 0;
+    // structure of the path: [kinds | subpath offsets | closed flags]
+    const uint32_t counts[2] = {path->n_segments, path->n_subpaths};
+    const size_t off_bytes = sizeof(uint32_t) * ((size_t)path->n_subpaths + 1);
+    std::vector<unsigned char>& meta = ctx->staged_meta_tmp;
+    meta.resize(sizeof(counts) + off_bytes + path->n_segments + path->n_subpaths);
+    unsigned char* m = meta.data();
+    std::memcpy(m, counts, sizeof(counts));
+    std::memcpy(m + sizeof(counts), path->subpath_offsets, off_bytes);
+    std::memcpy(m + sizeof(counts) + off_bytes, path->kinds, path->n_segments);
+    std::memcpy(m + sizeof(counts) + off_bytes + path->n_segments, path->closed, path->n_subpaths);
+    if (ctx->staged_items_valid && meta == ctx->staged_meta && ctx->staged_dp.items == static_cast<uint2*>(ctx->tmp_items.p)) {
+        dp->items = ctx->staged_dp.items;
+        dp->items_packed = ctx->staged_dp.items_packed;
+        dp->n_items = ctx->staged_dp.n_items;
+        dp->n_curves = ctx->staged_dp.n_curves;
+        return RGPU_OK;
+    }
     std::vector<uint2> items, packed;
     build_items(path, items, dp->n_curves);
     pack_items(items, packed);
-    dp->n_points = path->n_points;
     dp->n_items = (uint32_t)items.size();
-    items.insert(items.end(), packed.begin(), packed.end());  // [reference order | curves first]
-    int rc;
-    if ((rc = ensure_dev(ctx, ctx->tmp_pts, sizeof(double2) * std::max<uint32_t>(dp->n_points, 1)))) return rc;
-    if ((rc = ensure_dev(ctx, ctx->tmp_items, sizeof(uint2) * std::max<size_t>(items.size(), 1)))) return rc;
-    if ((rc = ensure_pinned(ctx, ctx->h_items, ctx->h_items_cap, std::max<size_t>(items.size(), 1)))) return rc;
-    // a previous call's copy out of h_items has completed: every host-buffer entry point ends with a stream sync
+    const size_t n2 = items.size() + packed.size();  // [reference order | curves first]
+    ctx->staged_items_valid = false;
+    if ((rc = ensure_dev(ctx, ctx->tmp_items, sizeof(uint2) * std::max<size_t>(n2, 1)))) return rc;
+    if ((rc = ensure_pinned(ctx, ctx->h_items, ctx->h_items_cap, std::max<size_t>(n2, 1)))) return rc;
     std::memcpy(ctx->h_items, items.data(), sizeof(uint2) * items.size());
-    dp->pts = static_cast<double2*>(ctx->tmp_pts.p);
+    std::memcpy(ctx->h_items + items.size(), packed.data(), sizeof(uint2) * packed.size());
     dp->items = static_cast<uint2*>(ctx->tmp_items.p);
     dp->items_packed = dp->items + dp->n_items;
-    if (dp->n_points) CK(ctx, cudaMemcpyAsync(dp->pts, path->points, sizeof(double2) * dp->n_points, cudaMemcpyHostToDevice, ctx->stream));
-    if (dp->n_items) CK(ctx, cudaMemcpyAsync(dp->items, ctx->h_items, sizeof(uint2) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->last_h2d_bytes = sizeof(double2) * dp->n_points + sizeof(uint2) * items.size();
-    ctx->last_d2h_bytes = 0;
+    if (n2) CK(ctx, cudaMemcpyAsync(dp->items, ctx->h_items, sizeof(uint2) * n2, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->last_h2d_bytes += sizeof(uint2) * n2;
+    ctx->staged_meta.swap(meta);
+    ctx->staged_dp = *dp;
+    ctx->staged_items_valid = true;
     return RGPU_OK;
 }
 
@@ -857,6 +894,7 @@ void rgpu_destroy(rgpu_ctx* ctx) {
     if (ctx->h_jobs) cudaFreeHost(ctx->h_jobs);
     if (ctx->h_paints) cudaFreeHost(ctx->h_paints);
     if (ctx->h_items) cudaFreeHost(ctx->h_items);
+    if (ctx->h_pts) cudaFreeHost(ctx->h_pts);
     for (int i = 0; i < 4; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
@@ -1031,6 +1069,7 @@ int rgpu_render_scene_host(rgpu_ctx* ctx, const rgpu_scene_fill* fills, size_t n
     const size_t pts_bytes = sizeof(double2) * n_points, items_bytes = sizeof(uint2) * n_items2;
     if ((rc = ensure_dev(ctx, ctx->tmp_pts, std::max<size_t>(pts_bytes, 16)))) return rc;
     if ((rc = ensure_dev(ctx, ctx->tmp_items, std::max<size_t>(items_bytes, 16)))) return rc;
+    ctx->staged_items_valid = false;  // tmp_items is about to hold this scene's item lists
     if ((rc = ensure_stage(ctx, std::max<size_t>(pts_bytes + items_bytes, 16)))) return rc;
     // every host-buffer entry point ends with a stream sync: the staging buffer is free
     char* st = static_cast<char*>(ctx->h_stage);
@@ -1224,8 +1263,11 @@ static int mask_to_device(rgpu_ctx* ctx, const rgpu_path* path, const double tr[
         CK(ctx, cudaMemsetAsync(d_img, 0, sizeof(float) * width * height, ctx->stream));
         return RGPU_OK;
     }
+    static const bool trace = getenv("RGPU_E2E_TRACE") != nullptr;  // timing breakdown on stderr
+    const auto t0 = std::chrono::steady_clock::now();
     rc = stage_path(ctx, path, &dp);
     if (rc) return rc;
+    const auto t1 = std::chrono::steady_clock::now();
     rgpu_job job;
     std::memset(&job, 0, sizeof(job));
     job.path = &dp;
@@ -1236,7 +1278,14 @@ static int mask_to_device(rgpu_ctx* ctx, const rgpu_path* path, const double tr[
     job.row_stride = width;
     job.width = (uint32_t)width;
     job.height = (uint32_t)height;
-    return submit_sync(ctx, &job, 1, RGPU_BATCH_INDEPENDENT, 1);
+    rc = submit_sync(ctx, &job, 1, RGPU_BATCH_INDEPENDENT, 1);
+    if (trace) {
+        const auto t2 = std::chrono::steady_clock::now();
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        std::fprintf(stderr, "mask_to_device: stage_path %.3f ms (host item lists + 2 H2D enqueued), submit + kernels + status sync %.3f ms\n", ms(t0, t1),
+                     ms(t1, t2));
+    }
+    return rc;
 }
 
 int rgpu_mask_f32(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill_rule, float* img, size_t width, size_t height) {

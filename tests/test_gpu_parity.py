@@ -252,3 +252,23 @@ def test_two_pass_fallback_matches(monkeypatch):
     ref = np.zeros((h, w))
     opath(p).mask(tr, O.EVENODD, ref)
     assert np.abs(a - ref).max() <= COV_TOL
+
+
+def test_staged_item_lists_follow_the_path_structure(rast):
+    """The host-buffer entry points keep the item lists of the previous call on the device when the path's structure is
+    unchanged (only the control points are uploaded again).  Paths with the same counts but different structure, and the
+    same structure with different points, must each give their own result."""
+    pts = np.array([[2.0, 2.0], [30.0, 4.0], [30.0, 4.0], [40.0, 30.0], [8.0, 36.0], [8.0, 36.0], [2.0, 2.0]])
+    a = rb.Path(pts, np.array([2, 3, 2], dtype=np.uint8), np.array([0, 3], dtype=np.uint32), np.array([1], dtype=np.uint8))
+    b = rb.Path(pts, np.array([3, 2, 2], dtype=np.uint8), np.array([0, 3], dtype=np.uint32), np.array([1], dtype=np.uint8))   # kinds permuted
+    c = rb.Path(pts, np.array([2, 3, 2], dtype=np.uint8), np.array([0, 1, 3], dtype=np.uint32)[:3], np.array([1, 0], dtype=np.uint8))  # two subpaths
+    a2 = rb.Path(pts * 1.2 + 1.0, a.kinds, a.subpath_offsets, a.closed)  # same structure, other points
+    tr = rb.Transform.identity()
+    for p in (a, b, a, c, a2, a, b, c, a2):
+        for close in (True, False):
+            assert np.array_equal(rast.flatten(p, tr, close), opath(p).flatten(np.array(O.IDENTITY), close=close))
+        img = np.zeros((48, 52))
+        rast.mask(p, tr, img, rb.FillRule.NonZero)
+        ref = np.zeros((48, 52))
+        opath(p).mask(O.IDENTITY, O.NONZERO, ref)
+        assert np.abs(img - ref).max() <= COV_TOL
