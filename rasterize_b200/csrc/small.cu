@@ -44,7 +44,16 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const JobDev& job = jobs[job_first + blockIdx.x];
+    // the job descriptor is read all through the kernel: one cooperative copy into shared memory instead of repeated
+    // (L1-latency, alias-constrained) global loads
+    __shared__ JobDev s_job;
+    {
+        const int* src = reinterpret_cast<const int*>(&jobs[job_first + blockIdx.x]);
+        int* dst = reinterpret_cast<int*>(&s_job);
+        if (tid < (int)(sizeof(JobDev) / 4)) dst[tid] = src[tid];
+    }
+    __syncthreads();
+    const JobDev& job = s_job;
     const int mode = job.mode;
 
     {
