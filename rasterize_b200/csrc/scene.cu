@@ -171,6 +171,9 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
         if (b < 0 || b >= (int)job.n_bands || c < 0 || c >= (int)job.n_chunks) continue;  // uniform for the CTA
         const uint32_t tile = job.tile_begin + (uint32_t)b * job.n_chunks + (uint32_t)c;
         const bool chained = job.n_chunks > 1;
+        // the descriptor fields the loops below use, read once (the compiler would reload them around barriers and atomics)
+        const int job_wout = job.width_out, job_paint = job.paint_index;
+        const bool job_evenodd = job.rule == 1;
         const uint32_t kk = k - k_begin;
         if (tid == 0) {
             if (kk < n_pre) {
@@ -235,8 +238,8 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
                 st_state(tile_state + (size_t)tile * kStateRows + tid, ep | kFlagPrefix | (unsigned long long)(uint32_t)(carry[tid] + rowtot[tid]));
         }
         // the piece constants are dead: stage the paint over them
-        if (job.paint_index >= 0) {
-            const int* src = reinterpret_cast<const int*>(&paints[job.paint_index]);
+        if (job_paint >= 0) {
+            const int* src = reinterpret_cast<const int*>(&paints[job_paint]);
             int* dst = reinterpret_cast<int*>(p_ax);
             for (int i = tid; i < (int)(sizeof(PaintDev) / 4); i += kScThreads) dst[i] = src[i];
         }
@@ -245,11 +248,11 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
             const int r = warp;
             const int acc = carry[r];
             if (row_touched[r]) {
-                if (job.rule == 1) scan_row_inplace<true, kScL>(cells + r * kScW, acc, lane);
+                if (job_evenodd) scan_row_inplace<true, kScL>(cells + r * kScW, acc, lane);
                 else scan_row_inplace<false, kScL>(cells + r * kScW, acc, lane);
                 if (lane == 0) row_live[r] = 1;
             } else if (lane == 0) {  // no line touched this row of the tile: constant coverage
-                const float cv = (job.rule == 1) ? coverage_from_fixed<true>(acc) : coverage_from_fixed<false>(acc);
+                const float cv = job_evenodd ? coverage_from_fixed<true>(acc) : coverage_from_fixed<false>(acc);
                 row_const[r] = cv;
                 row_live[r] = cv >= 1e-6f;
             }
@@ -267,7 +270,7 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
             for (int k = 0; k < Cfg::kPasses; k++) {
                 const int p = k * kScThreads + tid, r = p / kScW, col = p % kScW;
                 const int x = g.cx0 + col, y = g.row0 + r;
-                bool cov = x >= 0 && x < job.width_out && y >= 0 && y < g.row1 && row_live[r];
+                bool cov = x >= 0 && x < job_wout && y >= 0 && y < g.row1 && row_live[r];
                 if (cov) cov = (row_touched[r] ? covs[r * kScW + swz<true>(col)] : row_const[r]) >= 1e-6f;
                 const unsigned bal = __ballot_sync(0xffffffffu, cov);
                 my_pos[k] = cnt_before + __popc(bal & lt_mask);
@@ -289,7 +292,7 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
                 const int p = cov_list[i], r = p / kScW, col = p % kScW;
                 const int x = g.cx0 + col, y = g.row0 + r;
                 const float alpha = row_touched[r] ? covs[r * kScW + swz<true>(col)] : row_const[r];
-                float4 cl = (job.paint_index >= 0) ? paint_at(s_paint, x, y) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 cl = (job_paint >= 0) ? paint_at(s_paint, x, y) : make_float4(0.f, 0.f, 0.f, 0.f);
                 // with_alpha: self * (alpha as f32), src/color.rs:347-349
                 cl = make_float4(fmul(cl.x, alpha), fmul(cl.y, alpha), fmul(cl.z, alpha), fmul(cl.w, alpha));
                 // blend_over: other + self * (1 - other.alpha), src/color.rs:342-344
