@@ -3,15 +3,18 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4|c5]
 
-A step is one pass of the hot path (flatten -> bin -> signed-difference raster) over one batch:
-  c2 (default, BASELINE configs[1]): data/material.path fitted to 4096x4096, `Rasterizer::mask`, non-zero.
-  c4: a batch of synthetic random-cubic glyphs at 64x64 (SURVEY §8d generator), solid fill onto a fresh LinColor canvas per glyph
-      (RB_C4_MASK=1: mask per glyph).
-  c5: tv.path stroked on the 32768 x 32768 canvas as 8 scanline bands; rank r renders bands r, r + N, ... (band sharding,
+A step is one pass of the hot path (flatten -> signed-difference raster -> composite) over one batch:
+  c4 (default, BASELINE configs[3], the config the metric's 1/2/4/8-GPU sweep and the north-star target are stated on):
+      a batch of 100 000 synthetic random-cubic glyphs at 64x64 (SURVEY §8d generator), each filled with solid black onto
+      its own fresh LinColor canvas (RB_C4_MASK=1: mask per glyph); rank r of N takes a contiguous range of glyphs
+      (sharded by path, fixed total work => strong scaling).
+  c5: tv.path stroked on the 32768 x 32768 canvas as 64 scanline bands; rank r renders bands r, r + N, ... (band sharding,
       SURVEY §8e; fixed total work => strong scaling).
+  c2: data/material.path fitted to 4096x4096, `Rasterizer::mask`, non-zero (one outline: replicas only at N > 1).
   c1 / c3: Scene::render of the squirrel CLI scene (512 px) / firefox.scene (2048 x 2048) on a device-resident layer + RGBA8.
-N > 1 (under torchrun): every rank runs the same per-GPU workload on its own device with no data-path collective
-(independent paths of a batch / bands of a canvas) => weak scaling; value = units of all ranks / max-over-ranks time.
+The default run also measures c5 (every N) and c2 / c3 (N = 1) briefly and reports them under "other_configs".
+No data-path collective anywhere (independent paths of a batch / bands of a canvas); value = units of the whole job /
+max-over-ranks device time.
 
 Timing: CUDA events on the rasterizer's own stream around every step, L2 flushed (256 MiB memset) between steps
 outside the event pairs; torch is used for device buffers, events, the barrier and the max-over-ranks reduction only.
@@ -140,8 +143,41 @@ def glyph_path(rb, seed: int):
     return b.build()
 
 
+C4_TOTAL_GLYPHS = 100_000  # BASELINE configs[3]
+C5_BANDS = 64              # fine scanline bands dealt round-robin over the ranks (work and output bytes both balance)
+
+
+def c4_total() -> int:
+    return int(os.environ.get("RB_GLYPHS", str(C4_TOTAL_GLYPHS)))
+
+
+def workload_label(name: str) -> str:
+    """config.workload of both arms (ours / --impl reference): the whole job, independent of the number of GPUs."""
+    if name == "c4":
+        what = ("Rasterizer::mask per glyph (f32 coverage)" if os.environ.get("RB_C4_MASK") else
+                "Path::fill with solid black onto a fresh LinColor canvas per glyph (ImageOwned::new_default + Rasterizer::fill)")
+        return f"c4: batch of {c4_total()} synthetic random-cubic glyph paths at 64x64, {what}, nonzero, sharded by path over the GPUs"
+    if name == "c2":
+        return "c2: data/material.path (21106 segments) fitted to 4096x4096, Rasterizer::mask, nonzero"
+    if name == "c5":
+        return ("c5: data/tv.path stroked (w=0.5 round/round) on a 32768x32768 canvas, Rasterizer::mask, nonzero, split into "
+                f"{int(os.environ.get('RB_BANDS', C5_BANDS))} scanline bands dealt round-robin over the GPUs")
+    if name == "c1":
+        return "c1: examples/rasterize scene of data/squirrel.path at 512 px (checkerboard + fill over #f0f0f0), Scene::render + RGBA8 export"
+    return "c3: data/firefox.scene Scene::render at 2048x2048, 14 linear/radial gradient fills, + RGBA8 export"
+
+
+def workload_metric(name: str) -> str:
+    if name in ("c1", "c3"):
+        return "scene render throughput (Scene::render fills + RGBA8 export), pixels per second"
+    if name == "c4" and not os.environ.get("RB_C4_MASK"):
+        return "fill throughput (Path::fill, solid paint, nonzero), pixels rasterized per second"
+    return "fill throughput (Rasterizer::mask, nonzero), pixels rasterized per second"
+
+
 def build_workload(name: str, rb, rast, rank: int, world: int, torch):
-    from rasterize_b200 import assets, ffi, sharding
+    """Device-resident form of a workload for rank `rank` of `world`.  Returns (step(sync) callable, info)."""
+    from rasterize_b200 import assets, ffi, sharding, synth
     ex = assets.expected()["paths"]
     dev = torch.device("cuda", torch.cuda.current_device())
     if name == "c2":
@@ -149,42 +185,52 @@ def build_workload(name: str, rb, rast, rank: int, world: int, torch):
         c2 = ex["material"]["c2"]
         w, h = c2["size"]
         tr = np.array(c2["tr"])
-        canvases = [torch.empty((h, w), dtype=torch.float32, device=dev)]
+        canvas = torch.empty((h, w), dtype=torch.float32, device=dev)
         dp = rast.upload(path)
-        jobs = [rb.Job(dp, tr, rb.FillRule.NonZero, ffi.JOB_MASK, canvases[0].data_ptr(), w, h, w)]
-        info = dict(workload="c2: data/material.path (21106 segments) fitted to 4096x4096, Rasterizer::mask, nonzero",
-                    canvas=[w, h], items_per_gpu=1, pixels_per_step=w * h, in_bytes=path.input_bytes(), out_bytes=4 * w * h,
-                    host_path=path, host_tr=tr, host_size=(w, h), keep=[dp, canvases])
-        return jobs, True, info
+        prepared = rast.prepare_batch([rb.Job(dp, tr, rb.FillRule.NonZero, ffi.JOB_MASK, canvas.data_ptr(), w, h, w)])
+        info = dict(canvas=[w, h], items=1, total_items=1, pixels_per_step=w * h, total_pixels=w * h, in_bytes=path.input_bytes(), out_bytes=4 * w * h,
+                    host_path=path, host_tr=tr, host_size=(w, h), keep=[dp, canvas, prepared], scaling="weak",
+                    parallelism=f"{world} independent replicas of the whole job (one outline does not shard below a band; see c5), no collective")
+        return (lambda sync=False: rast.submit_prepared(prepared, independent=True, sync=sync)), info
     if name == "c4":
-        n = int(os.environ.get("RB_GLYPHS", "20000"))
-        first = rank * n
-        paths = [glyph_path(rb, first + i + 1) for i in range(n)]
-        dps = [rast.upload(p) for p in paths]
-        ident = np.array([1.0, 0, 0, 0, 1.0, 0])
-        if os.environ.get("RB_C4_MASK"):  # mask-only variant (SURVEY §8d C4 "(m)": 4 B per pixel)
-            slab = torch.empty((n, 64, 64), dtype=torch.float32, device=dev)
-            jobs = [rb.Job(dps[i], ident, rb.FillRule.NonZero, ffi.JOB_MASK, slab.data_ptr(), 64, 64, 64, origin=i * 4096) for i in range(n)]
-            what, px_bytes = "Rasterizer::mask per glyph (f32 coverage)", 4
-        else:  # SURVEY §8d C4 "(s)": every glyph filled with solid black onto its own fresh LinColor canvas, 16 B per pixel
-            slab = torch.empty((n, 64, 64, 4), dtype=torch.float32, device=dev)
-            black = rb.LinColor(0.0, 0.0, 0.0, 1.0)
-            jobs = [rb.Job(dps[i], ident, rb.FillRule.NonZero, ffi.JOB_RENDER, slab.data_ptr(), 64, 64, 64, origin=i * 4096, paint=black)
-                    for i in range(n)]
-            what, px_bytes = "Rasterizer::fill with solid black onto a fresh LinColor canvas per glyph (RGPU_JOB_RENDER)", 16
-        info = dict(workload=f"c4: {n} synthetic random-cubic glyphs per GPU at 64x64, {what}, nonzero", canvas=[64, 64],
-                    items_per_gpu=n, pixels_per_step=n * 4096, in_bytes=sum(p.input_bytes() for p in paths), out_bytes=px_bytes * n * 4096,
-                    keep=[dps, slab], metric="fill throughput (Rasterizer::fill, solid paint, nonzero), pixels rasterized per second" if px_bytes == 16 else None)
-        return jobs, True, info
+        # strong scaling: the batch is fixed, rank r takes a contiguous range of glyphs cut by segment count
+        total = c4_total()
+        a, b = sharding.shard_range(total, rank, world, weights=np.full(total, 18.0))
+        n = b - a
+        batch = synth.glyph_batch(a + 1, n)  # glyph i of the batch has seed i + 1
+        dpb = rast.upload_batch(batch)
+        as_mask = bool(os.environ.get("RB_C4_MASK"))
+        px_bytes = 4 if as_mask else 16
+        slab = torch.empty((max(n, 1), 64, 64) if as_mask else (max(n, 1), 64, 64, 4), dtype=torch.float32, device=dev)
+        table = np.zeros(n, dtype=rb.JOB_DTYPE)
+        table["path"] = dpb.handles()
+        table["tr"] = np.array([1.0, 0, 0, 0, 1.0, 0])
+        table["fill_rule"] = int(rb.FillRule.NonZero)
+        table["mode"] = ffi.JOB_MASK if as_mask else ffi.JOB_RENDER
+        table["canvas"] = slab.data_ptr()
+        table["origin"] = np.arange(n, dtype=np.uint64) * np.uint64(4096)
+        table["row_stride"] = 64
+        table["width"] = 64
+        table["height"] = 64
+        keep: list = []
+        if not as_mask:
+            cp = rb.LinColor(0.0, 0.0, 0.0, 1.0)._c(keep)
+            keep.append(cp)
+            import ctypes
+            table["paint"] = ctypes.addressof(cp)
+        prepared = rast.prepare_job_table(table, independent=True, keep=keep)
+        info = dict(canvas=[64, 64], items=n, total_items=total, pixels_per_step=n * 4096, total_pixels=total * 4096,
+                    in_bytes=batch.input_bytes(), out_bytes=px_bytes * n * 4096, host_batch=batch, keep=[dpb, slab, prepared], scaling="strong",
+                    parallelism=f"glyphs [{a}, {b}) of {total} on this rank, {world} ranks, no collective")
+        return (lambda sync=False: (prepared.render(), rast.batch_status() if sync else None)), info
     if name == "c5":
-        # the whole 32768 x 32768 canvas as 8 scanline bands: rank r renders bands r, r + N, ... as independent
-        # jobs of one batch (band-local translate(0, -y0): the reference's own y clipping crops exactly), so the total work is
-        # fixed and N ranks split it => strong scaling.  Bands 0 and 7 hold no lines, bands 1..6 between 1387 and 3593.
+        # strong scaling: the whole 32768 x 32768 canvas as fine scanline bands, rank r renders bands r, r + N, ...
+        # as independent jobs of one batch (band-local translate(0, -y0): the reference's own y clipping crops exactly)
         path = assets.load_path("tv_stroked")
         c5 = ex["tv_stroked"]["c5"]
         w, hfull = c5["size"]
-        bands = int(os.environ.get("RB_BANDS", "8"))
-        mine = [b for b in range(bands) if b % world == rank % bands] if world <= bands else [rank % bands]
+        bands = int(os.environ.get("RB_BANDS", C5_BANDS))
+        mine = [b for b in range(bands) if b % world == rank]
         dp = rast.upload(path)
         jobs, canvases, rows = [], [], 0
         for b in mine:
@@ -193,11 +239,12 @@ def build_workload(name: str, rb, rast, rank: int, world: int, torch):
             canvases.append(canvas)
             rows += y1 - y0
             jobs.append(rb.Job(dp, sharding.band_transform(c5["tr"], y0), rb.FillRule.NonZero, ffi.JOB_MASK, canvas.data_ptr(), w, y1 - y0, w))
-        info = dict(workload=f"c5: tv.path stroked (w=0.5 round/round) on a {w}x{hfull} canvas as {bands} scanline bands, bands {mine} on this rank "
-                             f"({rows} rows), mask, nonzero",
-                    canvas=[w, rows], items_per_gpu=len(mine), pixels_per_step=w * rows, in_bytes=path.input_bytes() * len(mine), out_bytes=4 * w * rows,
-                    keep=[dp, canvases], scaling="strong" if world <= bands else "weak")
-        return jobs, True, info
+        prepared = rast.prepare_batch(jobs)
+        info = dict(canvas=[w, hfull], items=len(mine), total_items=bands, pixels_per_step=w * rows, total_pixels=w * hfull,
+                    in_bytes=path.input_bytes() * len(mine), out_bytes=4 * w * rows, host_path=path, host_tr=np.array(c5["tr"]), host_size=(w, hfull),
+                    bands=bands, keep=[dp, canvases, prepared], scaling="strong",
+                    parallelism=f"{len(mine)} of {bands} scanline bands ({rows} rows) on this rank, {world} ranks, no collective")
+        return (lambda sync=False: rast.submit_prepared(prepared, independent=True, sync=sync)), info
     if name in ("c1", "c3"):
         # Scene::render of a Fill-only scene on a device-resident LinColor layer + RGBA8 export (SURVEY §8d "(s)" bytes):
         # c1 = examples/rasterize default scene for squirrel.path -w 512; c3 = firefox.scene at 2048 x 2048 (14 gradient fills)
@@ -207,223 +254,264 @@ def build_workload(name: str, rb, rast, rank: int, world: int, torch):
         layer = torch.empty((H, W, 4), dtype=torch.float32, device=dev)
         rgba = torch.empty((H, W, 4), dtype=torch.uint8, device=dev)
         jobs, keep, _, _, in_bytes = rscene.fixture_jobs(rast, sc, layer.data_ptr())
+        prepared = rast.prepare_batch(jobs)
         bg = sc.bg
-        what = ("c1: examples/rasterize scene of data/squirrel.path at 512 px (checkerboard + fill over #f0f0f0)" if name == "c1"
-                else "c3: data/firefox.scene Scene::render at 2048x2048, 14 linear/radial gradient fills")
-        info = dict(canvas=[W, H], items_per_gpu=len(jobs), pixels_per_step=W * H, in_bytes=in_bytes, out_bytes=(16 + 4) * W * H,
-                    keep=[keep, layer, rgba])
+        info = dict(canvas=[W, H], items=len(jobs), total_items=len(jobs), pixels_per_step=W * H, total_pixels=W * H, in_bytes=in_bytes,
+                    out_bytes=(16 + 4) * W * H, keep=[keep, layer, rgba, prepared], scene_name="squirrel_cli_512" if name == "c1" else "firefox_2048",
+                    scaling="weak", parallelism=f"{world} independent replicas of the scene (fills blend in order on one layer), no collective")
         if os.environ.get("RB_SCENE_ORDERED"):
             # A/B: Layer::new kernel, one raster launch per fill (ordered batch), export kernel
-            def pre():
+            def step(sync=False):
                 if bg is not None:
                     rast.fill_color(layer.data_ptr(), W * H, bg)
                 else:
                     rast.device_zero(layer.data_ptr(), W * H * 16)
-
-            def post():
+                rast.submit_prepared(prepared, independent=False, sync=sync)
                 rast.to_rgba8(layer.data_ptr(), rgba.data_ptr(), W * H)
-
-            info.update(workload=what + ", device-resident LinColor layer + RGBA8 export, one launch per fill (RB_SCENE_ORDERED)", pre_step=pre,
-                        post_step=post)
+            info["variant"] = "one launch per fill (RB_SCENE_ORDERED)"
         else:
-            info.update(workload=what + ", scene compositor: Layer::new + all fills + RGBA8 export in one raster launch, LinColor layer and RGBA8 image left in HBM",
-                        scene=dict(layer=layer.data_ptr(), W=W, H=H, bg=bg, rgba=rgba.data_ptr()))
-        return jobs, False, info
+            def step(sync=False):
+                rast.submit_scene_prepared(prepared, layer.data_ptr(), W, H, fresh=True, bg=bg, rgba_ptr=rgba.data_ptr(), sync=sync)
+            info["variant"] = "scene compositor: Layer::new + all fills + RGBA8 export in one raster launch"
+            info["scene"] = True
+        return step, info
     raise SystemExit(f"unknown workload {name}")
 
 
-def run_ours(args):
-    import torch
+class Harness:
+    """Process-wide state of one bench run: device, rasterizer, distributed plumbing, L2 flush buffer."""
 
-    from rasterize_b200 import build as rb_build
-    rb_build.build()  # no-op when the in-tree .so is up to date
-    import rasterize_b200 as rb
+    def __init__(self):
+        import torch
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (rasterize_b200 has no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    # the ranks of a node share its host cores: split them between the widening pools of the e2e leg
-    os.environ.setdefault("RGPU_HOST_THREADS", str(max(2, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))))
-    rast = rb.GpuRasterizer(device=local_rank)
-    jobs, independent, info = build_workload(args.workload, rb, rast, rank, world, torch)
-    prepared = rast.prepare_batch(jobs)
-    stream = torch.cuda.ExternalStream(rast.stream(), device=torch.device("cuda", local_rank))
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+        from rasterize_b200 import build as rb_build
+        rb_build.build()  # no-op when the in-tree .so is up to date
+        import rasterize_b200 as rb
+        self.torch, self.rb = torch, rb
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (rasterize_b200 has no CPU fallback)")
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+        # the ranks of a node share its host cores: split them between the widening pools of the e2e legs
+        os.environ.setdefault("RGPU_HOST_THREADS", str(max(2, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", self.world))))))
+        self.rast = rb.GpuRasterizer(device=self.local_rank)
+        self.stream = torch.cuda.ExternalStream(self.rast.stream(), device=torch.device("cuda", self.local_rank))
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
-    pre_step, post_step = info.get("pre_step"), info.get("post_step")
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    scn = info.get("scene")
+    def max_over_ranks(self, v: float) -> float:
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def step(sync=False):
-        if scn:
-            rast.submit_scene_prepared(prepared, scn["layer"], scn["W"], scn["H"], fresh=True, bg=scn["bg"], rgba_ptr=scn["rgba"], sync=sync)
-            return
-        if pre_step:
-            pre_step()
-        rast.submit_prepared(prepared, independent=independent, sync=sync)
-        if post_step:
-            post_step()
+    def sum_over_ranks(self, v: float) -> float:
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
 
+
+def time_calls(hx: Harness, call, n: int, warm: int) -> float:
+    """Seconds per call of a synchronous host-buffer entry point: max over ranks of the wall time of n calls, bracketed by barriers."""
+    for _ in range(warm):
+        call()
+    hx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        call()
+    hx.torch.cuda.synchronize()
+    return hx.max_over_ranks((time.perf_counter() - t0) / n)
+
+
+def measure(hx: Harness, name: str, steps: int, warmup: int, with_cpu: bool, sample_clocks: bool):
+    """One workload on this rank's GPU: device-timed steps (inputs resident), roofline of the dominant kernel, e2e through
+    the host-buffer C-ABI call, CPU oracle beside it (rank 0)."""
+    torch, rb, rast = hx.torch, hx.rb, hx.rast
+    step, info = build_workload(name, rb, rast, hx.rank, hx.world, torch)
+    has_work = info["pixels_per_step"] > 0
     # first call sizes the scratch buffers (and re-runs on overflow); then untimed warm-up
-    step(sync=True)
-    counts0 = rast.last_counts()
-    for _ in range(max(args.warmup, 3)):
-        step()
-    rast.batch_status()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
-    sampler.start()
-    l0 = rast.last_counts()["launches"]
-    with torch.cuda.stream(stream):
-        for i in range(args.steps):
-            flush.zero_()  # L2 flush between timed iterations, outside the event pair
-            starts[i].record(stream)
+    if has_work:
+        step(sync=True)
+    for _ in range(max(warmup, 3)):
+        if has_work:
             step()
-            stops[i].record(stream)
-            if (i & 31) == 31 or i == args.steps - 1:
+    rast.batch_status()
+    sampler = ClockSampler(hx.local_rank) if sample_clocks else None
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    hx.barrier()
+    if sampler:
+        sampler.start()
+    l0 = rast.last_counts()["launches"]
+    with torch.cuda.stream(hx.stream):
+        for i in range(steps):
+            hx.flush.zero_()  # L2 flush between timed iterations, outside the event pair
+            starts[i].record(hx.stream)
+            if has_work:
+                step()
+            stops[i].record(hx.stream)
+            if (i & 31) == 31 or i == steps - 1:
                 rast.batch_status()  # surfaces device-side errors; also bounds the launch queue depth
-    barrier()
-    clocks = sampler.stop()
+    hx.barrier()
+    clocks = sampler.stop() if sampler else None
     launches = rast.last_counts()["launches"] - l0
     per_step = np.array([a.elapsed_time(b) for a, b in zip(starts, stops)])
-    total_ms = float(per_step.sum())
+    ms_per_step = hx.max_over_ranks(float(per_step.sum())) / steps
+    counts = rast.last_counts() if has_work else dict(lines=0, line_refs=0, launches=0)
     # per-stage split (flatten / bin / raster) from the library's own events, sampled on a few extra steps
-    rast.set_profiling(True)
-    stage_samples = []
-    for _ in range(min(20, args.steps)):
-        with torch.cuda.stream(stream):
-            flush.zero_()
-        step(sync=True)
-        stage_samples.append(rast.last_stage_ms())
-    stage_ms = np.median(np.array(stage_samples), axis=0)
-    rast.set_profiling(False)
-
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    ms_per_step = total_ms_max / args.steps
-    counts = rast.last_counts()
-    pixels = info["pixels_per_step"] * world
-    value = pixels / (ms_per_step * 1e-3) / 1e6
-    lines_per_s = counts["lines"] * world / (ms_per_step * 1e-3)
-
+    stage_ms = np.zeros(3)
+    if has_work:
+        rast.set_profiling(True)
+        samples = []
+        for _ in range(min(20, steps)):
+            with torch.cuda.stream(hx.stream):
+                hx.flush.zero_()
+            step(sync=True)
+            samples.append(rast.last_stage_ms())
+        stage_ms = np.median(np.array(samples), axis=0)
+        rast.set_profiling(False)
+    total_lines = hx.sum_over_ranks(float(counts["lines"]))
+    value = info["total_pixels"] / (ms_per_step * 1e-3) / 1e6
+    if info["scaling"] == "weak":
+        value *= hx.world
     peak, peak_src = measured_peak()
     raster_s = float(stage_ms[2]) * 1e-3
     achieved = info["out_bytes"] / raster_s / 1e9 if raster_s > 0 else 0.0
     step_alg = info["in_bytes"] + info["out_bytes"]
+    kernel = {"c4": "small_canvas_kernel (K1..K4 fused: flatten + accumulate + row scan + fill rule + composite + store, one CTA per glyph)",
+              "c1": "scene_kernel (K3 + K4 for every fill of the layer + Layer::new + RGBA8 export)",
+              "c3": "scene_kernel (K3 + K4 for every fill of the layer + Layer::new + RGBA8 export)"}.get(
+                  name, "raster_kernel (K3: accumulate + row scan + fill rule + store)")
     roofline = {
-        "bound": "hbm", "kernel": ("scene_kernel (K3 + K4 for every fill of the layer + Layer::new + RGBA8 export)" if scn else
-                                   "raster_kernel (K3: accumulate + row scan + fill rule + store)"),
-        "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "peak_source": peak_src,
-        "traffic": recorded_traffic(args.workload + ("_mask" if args.workload == "c4" and os.environ.get("RB_C4_MASK") else "")),
+        "bound": "hbm", "kernel": kernel, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+        "peak_source": peak_src, "traffic": recorded_traffic(name + ("_mask" if name == "c4" and os.environ.get("RB_C4_MASK") else "")),
         "algorithmic_bytes_per_launch": info["out_bytes"], "kernel_ms": round(float(stage_ms[2]), 5),
         "stage_ms": {"flatten_and_bin": round(float(stage_ms[0]), 5), "two_pass_only_scan_and_emit": round(float(stage_ms[1]), 5),
                      "raster": round(float(stage_ms[2]), 5)},
-        "step_algorithmic_bytes": step_alg, "step_frac": round(step_alg / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+        "step_algorithmic_bytes": step_alg,
+        "step_frac": round(hx.sum_over_ranks(step_alg) / (ms_per_step * 1e-3) / 1e9 / (peak * hx.world), 4),
+        "note": "rank 0's launch; achieved = algorithmic output bytes of the launch / its CUDA-event duration",
     }
 
-    # ---- e2e: the trait-level C-ABI call with HOST buffers (H2D of the path, kernels, D2H of the f64 mask) ----
+    # ---- e2e: the reference-facing C-ABI call with HOST buffers (H2D of the paths, kernels, D2H of the result) ----
     e2e = None
-    cpu_baseline = None
-    if args.workload == "c2":
+    n_e2e = max(3, min(10, steps))
+    if name == "c4":
+        batch = info["host_batch"]
+        n = len(batch)
+        as_mask = bool(os.environ.get("RB_C4_MASK"))
+        out = rast.host_alloc((max(n, 1), 64, 64) if as_mask else (max(n, 1), 64, 64, 4), np.float32)[:n]  # ONE pinned buffer per rank
+        black = None if as_mask else rb.LinColor(0.0, 0.0, 0.0, 1.0)
+        call = (lambda: rast.fill_batch_host(batch, rb.FillRule.NonZero, black, 64, 64, out)) if n else (lambda: None)
+        dt = time_calls(hx, call, n_e2e, 2)
+        h2d, d2h = rast.last_transfer_bytes() if n else (0, 0)
+        e2e = {"value": round(info["total_pixels"] / dt / 1e6, 1), "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_call": round(dt * 1e3, 3),
+               "call": "rgpu_fill_batch_host on this rank's shard: host path arrays in, kernels in chunks, every chunk's images copied with cudaMemcpyAsync "
+                       "on a second stream into ONE pinned host buffer while the next chunk renders (f32 LinColor, 16 B per pixel: PCIe-bound)"}
+        if not as_mask and n:
+            rgba = rast.host_alloc((n, 64, 64, 4), np.uint8)
+            dt8 = time_calls(hx, lambda: rast.fill_batch_host(batch, rb.FillRule.NonZero, black, 64, 64, rgba), n_e2e, 1)
+            e2e["rgba8_ms_per_call"] = round(dt8 * 1e3, 3)
+            e2e["rgba8_value"] = round(info["total_pixels"] / dt8 / 1e6, 1)
+    elif name == "c2":
         path, tr, (w, h) = info["host_path"], info["host_tr"], info["host_size"]
         img = rast.host_alloc((h, w), np.float64)  # pinned host image, as the contract asks
-        for _ in range(16):  # also lets the device/host widening split of rgpu_mask settle
-            rast.mask(path, tr, img, rb.FillRule.NonZero)
-        n_e2e = max(5, min(20, args.steps))
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            rast.mask(path, tr, img, rb.FillRule.NonZero)
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / n_e2e
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+        dt = time_calls(hx, lambda: rast.mask(path, tr, img, rb.FillRule.NonZero), max(5, min(20, steps)), 16)  # warm-up lets the widening split settle
         h2d, d2h = rast.last_transfer_bytes()  # what the last call really moved (path points + items up; f32 and f64 rows down)
-        e2e = {"value": round(w * h * world / dt / 1e6, 1), "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+        e2e = {"value": round(w * h * hx.world / dt / 1e6, 1), "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_call": round(dt * 1e3, 4),
                "call": "rgpu_mask: host path in, f64 pinned host image out (bottom rows cross PCIe as f32 and are widened by host threads, top rows are widened on the device and DMA'd as f64; the split adapts)"}
-        # f32 variant of the same call, for context
         img32 = rast.host_alloc((h, w), np.float32)
-        rast.mask(path, tr, img32, rb.FillRule.NonZero)
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            rast.mask(path, tr, img32, rb.FillRule.NonZero)
-        e2e["f32_ms_per_call"] = round((time.perf_counter() - t0) / n_e2e * 1e3, 4)
-        if rank == 0 and world == 1:
-            cpu_baseline = cpu_reference_c2(threads=1, budget_s=12.0)
-    elif args.workload in ("c1", "c3"):
+        e2e["f32_ms_per_call"] = round(time_calls(hx, lambda: rast.mask(path, tr, img32, rb.FillRule.NonZero), n_e2e, 1) * 1e3, 4)
+    elif name == "c5":
+        path, tr, (w, h) = info["host_path"], info["host_tr"], info["host_size"]
+        img = rast.host_alloc((h, w), np.float32)  # the whole canvas, pinned; this rank fills the rows of its bands
+        call = lambda: rast.mask_banded(path, tr, img, rb.FillRule.NonZero, n_bands=info["bands"], band_first=hx.rank, band_step=hx.world)  # noqa: E731
+        dt = time_calls(hx, call, max(2, min(4, steps)), 1)
+        h2d, d2h = rast.last_transfer_bytes()
+        e2e = {"value": round(info["total_pixels"] / dt / 1e6, 1), "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_call": round(dt * 1e3, 3),
+               "call": "rgpu_mask_banded_host(band_first = rank, band_step = ranks): host path in, this rank's bands rendered as one batch and copied "
+                       "into their rows of a pinned f32 host image of the whole canvas"}
+    elif name in ("c1", "c3"):
         # Scene::render + RGBA8 export through the host-buffer entry point: host paths in (H2D), pinned RGBA8 image out (D2H)
         from rasterize_b200 import assets as _assets, scene as rscene
-        sc = _assets.load_scene("squirrel_cli_512" if args.workload == "c1" else "firefox_2048")
+        sc = _assets.load_scene(info["scene_name"])
         fills, W, H = rscene.fixture_fills_host(sc)
         prepared_host = rast.prepare_scene_host(fills)
         img = rast.host_alloc((H, W, 4), np.uint8)
-        for _ in range(5):
-            rast.render_scene_host(prepared_host, W, H, bg=sc.bg, rgba_out=img)
-        n_e2e = max(5, min(50, args.steps))
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            rast.render_scene_host(prepared_host, W, H, bg=sc.bg, rgba_out=img)
-        dt = (time.perf_counter() - t0) / n_e2e
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+        dt = time_calls(hx, lambda: rast.render_scene_host(prepared_host, W, H, bg=sc.bg, rgba_out=img), max(5, min(50, steps)), 5)
         h2d, d2h = rast.last_transfer_bytes()
-        e2e = {"value": round(W * H * world / dt / 1e6, 1), "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+        e2e = {"value": round(W * H * hx.world / dt / 1e6, 1), "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_call": round(dt * 1e3, 4),
                "call": "rgpu_render_scene_host: host paths + paints in, Layer::new + all fills + RGBA8 export on the device, pinned RGBA8 host image out"}
-        if rank == 0 and world == 1:
-            cpu_baseline = cpu_reference_other(args.workload, budget_s=10.0)
-    elif rank == 0 and world == 1:
-        cpu_baseline = cpu_reference_other(args.workload, budget_s=10.0)
+    cpu_baseline = None
+    if with_cpu and hx.rank == 0:
+        cpu_baseline = cpu_reference_c2(threads=1, budget_s=10.0) if name == "c2" else cpu_reference_other(name, budget_s=10.0)
+    if hx.dist is not None:
+        hx.dist.barrier()  # the other ranks wait for rank 0's CPU leg instead of racing ahead into the next workload
 
-    if rank == 0:
-        out = {
-            "metric": info.get("metric") or ("scene render throughput (Scene::render fills + RGBA8 export), pixels per second" if args.workload in ("c1", "c3")
-                                             else "fill throughput (Rasterizer::mask, nonzero), pixels rasterized per second"),
-            "value": round(value, 1), "unit": "Mpix/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5),
-            "higher_is_better": True, "scaling": info.get("scaling", "weak"), "vs_baseline": None, "dtype": "f64 geometry / Q7.24 fixed-point accumulation / f32 coverage",
-            "data": "synthetic" if args.workload == "c4" else "reference asset (flat fixture of data/*.path), random-free",
-            "config": {"workload": info["workload"], "canvas": info["canvas"], "items_per_gpu": info["items_per_gpu"],
-                       "flatness": 0.05, "l2": "flushed between timed steps (256 MiB memset outside the event pairs)",
-                       "parallelism": f"{world} independent replicas/shards, no collective"},
-            "lines_per_s": round(lines_per_s, 1), "lines_per_step_per_gpu": counts["lines"], "line_refs_per_step_per_gpu": counts["line_refs"],
-            "gpu_launches": int(launches), "launches_per_step": launches / args.steps,
-            "roofline": roofline, "clocks": clocks,
-            "step_ms_min_med_max": [round(float(per_step.min()), 5), round(float(np.median(per_step)), 5), round(float(per_step.max()), 5)],
-        }
-        if e2e is not None:
-            out["e2e"] = e2e
-        if cpu_baseline is not None:
-            out["cpu_baseline"] = cpu_baseline
-        _emit(json.dumps(out))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    out = {
+        "metric": workload_metric(name), "value": round(value, 1), "unit": "Mpix/s", "n_gpus": hx.world, "steps": steps, "warmup": max(warmup, 3),
+        "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": info["scaling"], "vs_baseline": None,
+        "dtype": "f64 geometry / Q7.24 fixed-point accumulation / f32 coverage and colour",
+        "data": "synthetic" if name == "c4" else "reference asset (flat fixture of data/*.path), random-free",
+        "config": {"workload": workload_label(name), "canvas": info["canvas"], "total_items": info["total_items"], "items_this_rank": info["items"],
+                   "flatness": 0.05, "l2": "flushed between timed steps (256 MiB memset outside the event pairs)", "parallelism": info["parallelism"]},
+        "lines_per_s": round(total_lines / (ms_per_step * 1e-3), 1),
+        "lines_per_step": int(total_lines), "gpu_launches": int(launches), "launches_per_step": launches / steps, "roofline": roofline,
+        "step_ms_min_med_max": [round(float(per_step.min()), 5), round(float(np.median(per_step)), 5), round(float(per_step.max()), 5)],
+    }
+    if "variant" in info:
+        out["config"]["variant"] = info["variant"]
+    if clocks is not None:
+        out["clocks"] = clocks
+    if e2e is not None:
+        out["e2e"] = e2e
+    if cpu_baseline is not None:
+        out["cpu_baseline"] = cpu_baseline
+    del step, info
+    return out
+
+
+def run_ours(args):
+    hx = Harness()
+    main = measure(hx, args.workload, args.steps, args.warmup, with_cpu=True, sample_clocks=True)
+    # the other BASELINE configs, measured briefly in the same run (value, ms_per_step, roofline, e2e): c5 shards by scanline band
+    # at every N; c2 / c3 do not shard (replicas only), so they are measured at N = 1
+    others = {}
+    if args.others:
+        names = [n for n in (["c5", "c2", "c3"] if hx.world == 1 else ["c5"]) if n != args.workload]
+        for n in names:
+            try:
+                r = measure(hx, n, max(5, min(args.steps, 30)), min(args.warmup, 5), with_cpu=(hx.world == 1), sample_clocks=False)
+                others[n] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "lines_per_s", "gpu_launches", "e2e", "cpu_baseline")
+                             if k in r}
+                others[n]["roofline"] = {k: r["roofline"][k] for k in ("kernel", "achieved", "frac", "kernel_ms", "stage_ms", "step_frac")}
+            except Exception as e:  # a side measurement must not take the headline line down with it
+                others[n] = {"error": f"{type(e).__name__}: {e}"}
+    if hx.rank == 0:
+        if others:
+            main["other_configs"] = others
+        _emit(json.dumps(main))
+    if hx.dist is not None:
+        hx.dist.barrier()
+        hx.dist.destroy_process_group()
 
 
 def cpu_reference_c2(threads: int, budget_s: float):
@@ -518,7 +606,8 @@ def run_reference(args):
     be compiled in this image (no cargo/rustc), so this is the oracle port with all the host threads the workload can
     use: rows are independent (c2, c5: one band of rows per thread), glyphs are independent (c4: glyphs dealt out over
     std::threads, one private image each); a scene's fills blend in order onto one layer, so c1 / c3 run on one thread
-    exactly like the single-threaded reference.  Every step is a bounded sample of the workload."""
+    exactly like the single-threaded reference.  Every step is a bounded sample of the workload; config / metric / unit
+    are those of our arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -527,7 +616,6 @@ def run_reference(args):
     from rasterize_b200 import assets, sharding
     world = int(os.environ.get("WORLD_SIZE", "1"))
     wl = args.workload
-    metric = "fill throughput (Rasterizer::mask, nonzero), pixels rasterized per second"
     lines = None
     if wl in ("c2", "c5"):
         name, key = ("material", "c2") if wl == "c2" else ("tv_stroked", "c5")
@@ -535,19 +623,18 @@ def run_reference(args):
         e = assets.expected()["paths"][name][key]
         w, h = e["size"]
         tr = np.array(e["tr"])
-        what = "c2: data/material.path (21106 segments) fitted to 4096x4096, Rasterizer::mask, nonzero"
+        canvas, total_items = [w, h], 1
         sample_of = f"material.path at {w}x{h}"
         if wl == "c5":
-            y0, y1 = sharding.band_rows(h, 2, 8)  # a band that holds lines (band 0 is empty)
+            y0, y1 = sharding.band_rows(h, 2, 8)  # a band that holds lines (the top and bottom 1/8 of the canvas are empty)
             tr = sharding.band_transform(e["tr"], y0)
-            what = f"c5: tv.path stroked (w=0.5 round/round) on a {w}x{h} canvas, band 2 of 8 ({y1 - y0} rows), mask, nonzero"
-            sample_of = f"band 2 of 8 ({w}x{y1 - y0}) of tv.path stroked"
+            sample_of = f"rows [{y0}, {y1}) of the {w}x{h} canvas of tv.path stroked"
             h = y1 - y0
+            total_items = int(os.environ.get("RB_BANDS", C5_BANDS))
         else:
             lines = e["lines"]
         op = O.OraclePath.from_flat(p.points, p.kinds, p.subpath_offsets, p.closed)
         img = np.zeros((h, w))
-        canvas, items = [w, h], 1
 
         def one_step():
             img[:] = 0
@@ -564,12 +651,10 @@ def run_reference(args):
         def one_step():
             O.batch_threads(glyphs, O.IDENTITY, O.NONZERO, None if as_mask else black, 64, 64, threads)
 
-        metric = metric if as_mask else "fill throughput (Rasterizer::fill, solid paint, nonzero), pixels rasterized per second"
-        what = (f"c4: synthetic random-cubic glyphs at 64x64, {'Rasterizer::mask' if as_mask else 'Rasterizer::fill with solid black onto a fresh LinColor canvas'} "
-                "per glyph, nonzero")
-        canvas, items = [64, 64], n_glyphs
+        canvas, total_items = [64, 64], c4_total()
         px, max_steps = n_glyphs * 4096, 20
-        sample = f"{n_glyphs} glyph {'masks' if as_mask else 'solid fills'} (clear + call) dealt out over {threads} std::threads (one private image per thread)"
+        sample = (f"the first {n_glyphs} of the {c4_total()} glyphs, {'masks' if as_mask else 'solid fills'} (clear + call) dealt out over {threads} "
+                  "std::threads (one private image per thread)")
     else:  # c1 / c3: order-dependent fills on one layer -> one thread, like the reference
         from helpers import render_scene_oracle
         sc = assets.load_scene("squirrel_cli_512" if wl == "c1" else "firefox_2048")
@@ -582,10 +667,7 @@ def run_reference(args):
             shape[:] = [img.shape[1], img.shape[0]]
 
         one_step()
-        metric = "scene render throughput (Scene::render fills + RGBA8 export), pixels per second"
-        what = ("c1: examples/rasterize scene of data/squirrel.path at 512 px (checkerboard + fill over #f0f0f0)" if wl == "c1"
-                else "c3: data/firefox.scene Scene::render at 2048x2048, 14 linear/radial gradient fills") + ", Scene::render + RGBA8 export"
-        canvas, items = list(shape), len(sc.fills)
+        canvas, total_items = list(shape), len(sc.fills)
         px, max_steps = shape[0] * shape[1], (100 if wl == "c1" else 12)
         sample = "Scene::render + RGBA8 export through the oracle's Rasterizer::fill, 1 thread (fills blend in order)"
     steps = max(1, min(args.steps, max_steps))
@@ -598,10 +680,11 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / steps
     value = round(px / dt / 1e6, 1)
     out = {
-        "impl": "reference", "metric": metric, "value": value,
+        "impl": "reference", "metric": workload_metric(wl), "value": value,
         "unit": "Mpix/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": round(dt * 1e3, 4),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic" if wl == "c4" else "reference asset (flat fixture of data/*.path)",
-        "config": {"workload": what, "canvas": canvas, "items_per_gpu": items, "flatness": 0.05},
+        "higher_is_better": True, "scaling": "strong" if wl in ("c4", "c5") else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic" if wl == "c4" else "reference asset (flat fixture of data/*.path), random-free",
+        "config": {"workload": workload_label(wl), "canvas": canvas, "total_items": total_items, "flatness": 0.05},
         "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": threads, "kind": "port", "sample": f"{steps} x {sample}", "host_cores": os.cpu_count()},
         "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -629,7 +712,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--no-others", dest="others", action="store_false", help="skip the brief other_configs measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -217,6 +217,71 @@ int rgpu_layer_blend_over_dev(rgpu_ctx* ctx, float* dst_dev, size_t dst_origin, 
  * follows `Scene::render` in every CLI run (`ImageOwned<LinColor>` -> RGBA8, src/image.rs:136-231, src/color.rs:164-175). */
 int rgpu_download_rgba8(rgpu_ctx* ctx, const float* lin_dev, size_t n_pixels, uint8_t* rgba_host);
 
+/* ---- batches of independent paths (BASELINE config 4; SURVEY §8e "batch of independent paths") -------------- */
+/* Many paths in one flat encoding: `all` holds the subpaths of every path back to back and path i owns subpaths
+ * [path_subpath_offsets[i], path_subpath_offsets[i + 1]) (n_paths + 1 offsets, the first 0, the last all->n_subpaths).
+ * This is what a Rust caller builds from a `&[Path]` (src/path.rs:227-233) with one pass over `Path::subpaths()`. */
+
+/* Upload n_paths paths with two copies; element i of the batch (rgpu_path_batch_get) is an ordinary device path that
+ * rgpu_job::path may point to for as long as the batch lives. */
+typedef struct rgpu_dpath_batch rgpu_dpath_batch;
+int rgpu_path_upload_batch(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* path_subpath_offsets, size_t n_paths,
+                           rgpu_dpath_batch** out);
+const rgpu_dpath* rgpu_path_batch_get(const rgpu_dpath_batch* batch, size_t i);
+void rgpu_path_batch_free(rgpu_ctx* ctx, rgpu_dpath_batch* batch);
+
+/* A job list marshalled once and kept on the device: the steady state of a render loop that re-submits the same
+ * batch (rgpu_render_batch re-derives and compares its tables on every call, which for 10^5 glyph jobs costs more
+ * host time than the kernel takes).  `jobs` (and the paints they point to) must stay valid until rgpu_batch_free.
+ * rgpu_batch_render is asynchronous like rgpu_render_batch; rgpu_batch_status / rgpu_sync apply. */
+typedef struct rgpu_batch rgpu_batch;
+int rgpu_batch_create(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, rgpu_batch** out);
+int rgpu_batch_render(rgpu_ctx* ctx, rgpu_batch* batch);
+void rgpu_batch_free(rgpu_ctx* ctx, rgpu_batch* batch);
+
+/* Output formats of the host-buffer batch calls */
+enum {
+    RGPU_OUT_LINCOLOR = 0, /* f32 x 4 premultiplied linear, 16 B per pixel: what `Path::fill` leaves in an `ImageOwned<LinColor>` */
+    RGPU_OUT_RGBA8 = 1,    /* the same image after `From<LinColor> for RGBA` (src/color.rs:164-175), 4 B per pixel */
+    RGPU_OUT_COVERAGE = 2  /* f32 coverage, dense form of `Rasterizer::mask_iter` (no paint), 4 B per pixel */
+};
+/* `ImageOwned::new_default(Size { width, height })` + `Path::fill(rasterizer, tr, fill_rule, paint, &mut img)`
+ * (src/path.rs:492-507, src/rasterize.rs:70-115) for n_paths independent paths with HOST buffers: path i is filled at
+ * trs[6 i .. 6 i + 6) (NULL = identity for all) onto its own fresh image, and the images are returned back to back in
+ * `out_host` (n_paths x height x width pixels of `out_format`).  The batch runs in chunks: while chunk k renders,
+ * chunk k - 1 is on its way to the host on a second stream (cudaMemcpyAsync into `out_host`, which should be pinned),
+ * so the call is bound by the PCIe download.  `paint` is ignored for RGPU_OUT_COVERAGE. */
+int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* path_subpath_offsets, size_t n_paths, const double* trs,
+                         int fill_rule, const rgpu_paint* paint, uint32_t width, uint32_t height, int out_format, void* out_host);
+
+/* ---- several GPUs of one box (no collective: every device returns its shard over its own PCIe link) --- */
+/* One context + worker thread + streams per device; `devices` lists CUDA device ordinals (NULL = 0 .. n_devices-1). */
+typedef struct rgpu_multi rgpu_multi;
+int rgpu_multi_create(const int* devices, int n_devices, double flatness, rgpu_multi** out);
+void rgpu_multi_destroy(rgpu_multi* m);
+int rgpu_multi_device_count(const rgpu_multi* m);
+const char* rgpu_multi_last_error(const rgpu_multi* m); /* m may be NULL: error of the last failed rgpu_multi_create */
+/* rgpu_fill_batch_host sharded by path: device d takes a contiguous range of paths, cut so that the ranges hold equal
+ * numbers of segments, and writes its images into its own region of `out_host` (disjoint; same result as one device). */
+int rgpu_multi_fill_batch_host(rgpu_multi* m, const rgpu_path* all, const uint32_t* path_subpath_offsets, size_t n_paths,
+                               const double* trs, int fill_rule, const rgpu_paint* paint, uint32_t width, uint32_t height,
+                               int out_format, void* out_host);
+/* `Rasterizer::mask` (src/rasterize.rs:299-311) of ONE path on a huge canvas, sharded by scanline bands: rows are
+ * independent in the signed-difference rasterizer (src/rasterize.rs:421-469, 478-503), so the canvas is cut into
+ * n_bands bands of rows (0 = 8 per device; cut points are multiples of 8 rows), band b goes to device b mod n_devices
+ * (fine bands dealt round-robin balance both the raster work and the output bytes), every device flattens the path
+ * with a band-local translate(0, -y0) — the reference's own y clipping then crops exactly — and copies its bands into
+ * their rows of the host image.  `img` is a dense width x height image of f32 (elem_size 4, the device-native format)
+ * or f64 (elem_size 8, the trait's `Scalar`); it does not have to be zero on entry (every pixel is written).
+ * The result is bit-identical to the single-device rgpu_mask_f32 / rgpu_mask. */
+int rgpu_multi_mask_banded_host(rgpu_multi* m, const rgpu_path* path, const double tr[6], int fill_rule, void* img, size_t elem_size,
+                                size_t width, size_t height, uint32_t n_bands);
+/* The same band decomposition on ONE context (bands rendered as independent jobs of one batch); also what every worker
+ * of rgpu_multi_mask_banded_host runs for its bands.  band_first / band_step select bands band_first, band_first +
+ * band_step, ... of n_bands. */
+int rgpu_mask_banded_host(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill_rule, void* img, size_t elem_size,
+                          size_t width, size_t height, uint32_t n_bands, uint32_t band_first, uint32_t band_step);
+
 /* ---- plumbing ----------------------------------------------------------------------------------- */
 void* rgpu_stream(rgpu_ctx* ctx);  /* cudaStream_t the context launches on */
 int rgpu_sync(rgpu_ctx* ctx);

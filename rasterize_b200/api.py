@@ -176,6 +176,63 @@ class Path:
         return img
 
 
+class PathBatch:
+    """Many independent paths in one flat encoding: the subpaths of every path back to back plus, per path, the range of
+    subpaths it owns (`rgpu_path` + `path_subpath_offsets`, include/rasterize_b200.h)."""
+
+    def __init__(self, points, kinds, subpath_offsets, closed, path_subpath_offsets):
+        self.flat = Path(points, kinds, subpath_offsets, closed)
+        self.path_subpath_offsets = np.ascontiguousarray(path_subpath_offsets, dtype=np.uint32)
+        if len(self.path_subpath_offsets) == 0:
+            self.path_subpath_offsets = np.zeros(1, dtype=np.uint32)
+
+    @staticmethod
+    def from_paths(paths) -> "PathBatch":
+        paths = list(paths)
+        seg = np.cumsum([0] + [p.segments_count() for p in paths])
+        sub = np.cumsum([0] + [len(p.closed) for p in paths]).astype(np.uint32)
+        so = [np.zeros(1, dtype=np.uint32)]
+        for p, s0 in zip(paths, seg[:-1]):
+            if len(p.closed):
+                so.append(p.subpath_offsets[1:].astype(np.uint32) + np.uint32(s0))
+        return PathBatch(np.concatenate([p.points for p in paths]) if paths else np.zeros((0, 2)),
+                         np.concatenate([p.kinds for p in paths]) if paths else [], np.concatenate(so),
+                         np.concatenate([p.closed for p in paths]) if paths else [], sub)
+
+    def __len__(self) -> int:
+        return len(self.path_subpath_offsets) - 1
+
+    def _seg_range(self, a: int, b: int):
+        so = self.flat.subpath_offsets
+        pso = self.path_subpath_offsets
+        n_seg = len(self.flat.kinds)
+        s0 = int(so[pso[a]]) if len(so) and pso[a] < len(so) else n_seg
+        s1 = int(so[pso[b]]) if len(so) and pso[b] < len(so) else n_seg
+        return s0, s1
+
+    def slice(self, a: int, b: int) -> "PathBatch":
+        """Paths [a, b) as a batch of their own (rebased offsets; arrays are copies)."""
+        pso = self.path_subpath_offsets
+        s0, s1 = self._seg_range(a, b)
+        pt = np.concatenate([[0], np.cumsum(self.flat.kinds, dtype=np.int64)])
+        sub0, sub1 = int(pso[a]), int(pso[b])
+        so = self.flat.subpath_offsets[sub0:sub1 + 1].astype(np.int64) - s0 if sub1 > sub0 else np.zeros(0, dtype=np.int64)
+        return PathBatch(self.flat.points[pt[s0]:pt[s1]], self.flat.kinds[s0:s1], so, self.flat.closed[sub0:sub1], pso[a:b + 1] - pso[a])
+
+    def path(self, i: int) -> Path:
+        return self.slice(i, i + 1).flat
+
+    def segments_per_path(self) -> np.ndarray:
+        so = self.flat.subpath_offsets.astype(np.int64)
+        if len(so) == 0:
+            return np.zeros(len(self), dtype=np.int64)
+        b = so[self.path_subpath_offsets]
+        return b[1:] - b[:-1]
+
+    def input_bytes(self) -> int:
+        return self.flat.input_bytes()
+
+
 class PathBuilder:
     """`PathBuilder` (src/path.rs:800-1056) without arcs (arc -> cubic conversion stays on the Rust host side)."""
 
@@ -346,6 +403,75 @@ class DevicePath:
     def free(self):
         if self.h:
             ffi.lib().rgpu_path_free(self.rast.ctx, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DevicePathBatch:
+    """Device-resident `PathBatch` (`rgpu_dpath_batch`): element i is an ordinary device path."""
+
+    def __init__(self, rast: "GpuRasterizer", batch: PathBatch):
+        self.rast = rast
+        self.batch = batch
+        h = C.c_void_p()
+        c = batch.flat._c()
+        rast._check(ffi.lib().rgpu_path_upload_batch(rast.ctx, C.byref(c), batch.path_subpath_offsets.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                     len(batch), C.byref(h)))
+        self.h = h
+
+    def handle(self, i: int) -> int:
+        return int(ffi.lib().rgpu_path_batch_get(self.h, i) or 0)
+
+    def handles(self) -> np.ndarray:
+        """Device-path handles of all elements as u64 (they are elements of one array)."""
+        n = len(self.batch)
+        if n == 0:
+            return np.zeros(0, dtype=np.uint64)
+        h0 = self.handle(0)
+        stride = self.handle(1) - h0 if n > 1 else 0
+        return (np.uint64(h0) + np.arange(n, dtype=np.uint64) * np.uint64(stride)).astype(np.uint64)
+
+    def free(self):
+        if self.h:
+            ffi.lib().rgpu_path_batch_free(self.rast.ctx, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+#: numpy view of `rgpu_job` (include/rasterize_b200.h) for job tables built without a Python loop
+JOB_DTYPE = np.dtype([("path", np.uint64), ("tr", np.float64, 6), ("fill_rule", np.int32), ("mode", np.int32), ("paint", np.uint64),
+                      ("path_bbox", np.uint64), ("canvas", np.uint64), ("origin", np.uint64), ("row_stride", np.uint64),
+                      ("width", np.uint32), ("height", np.uint32)], align=True)
+
+
+class PreparedBatch:
+    """`rgpu_batch`: a job table marshalled once and kept on the device."""
+
+    def __init__(self, rast: "GpuRasterizer", table: np.ndarray, independent: bool, keep=None):
+        assert table.dtype == JOB_DTYPE and table.flags.c_contiguous and JOB_DTYPE.itemsize == C.sizeof(ffi.CJob)
+        self.rast, self.table, self.keep = rast, table, keep
+        h = C.c_void_p()
+        flags = ffi.BATCH_INDEPENDENT if independent else ffi.BATCH_ORDERED
+        rast._check(ffi.lib().rgpu_batch_create(rast.ctx, C.c_void_p(table.ctypes.data), len(table), flags, C.byref(h)))
+        self.h = h
+
+    def render(self) -> None:
+        """Asynchronous; `GpuRasterizer.batch_status()` waits and reports device-side errors."""
+        self.rast._check(ffi.lib().rgpu_batch_render(self.rast.ctx, self.h))
+
+    def free(self):
+        if self.h:
+            ffi.lib().rgpu_batch_free(self.rast.ctx, self.h)
             self.h = None
 
     def __del__(self):
@@ -586,6 +712,27 @@ class GpuRasterizer:
     def batch_status(self) -> None:
         self._check(ffi.lib().rgpu_batch_status(self.ctx))
 
+    # -- batches of independent paths (BASELINE config 4) / band-sharded masks (config 5) ---------------------------
+    def upload_batch(self, batch: PathBatch) -> DevicePathBatch:
+        return DevicePathBatch(self, batch)
+
+    def prepare_job_table(self, table: np.ndarray, independent: bool = True, keep=None) -> PreparedBatch:
+        return PreparedBatch(self, table, independent, keep)
+
+    def fill_batch_host(self, batch: PathBatch, fill_rule: FillRule, paint, width: int, height: int, out: np.ndarray, trs=None) -> np.ndarray:
+        """`ImageOwned::new_default` + `Path::fill` for every path of the batch, host buffers in and out
+        (`rgpu_fill_batch_host`).  `out` selects the format: f32 [n,H,W,4] LinColor, u8 [n,H,W,4] RGBA8, f32 [n,H,W] coverage."""
+        return _fill_batch_host(ffi.lib().rgpu_fill_batch_host, self.ctx, self._check, batch, fill_rule, paint, width, height, out, trs)
+
+    def mask_banded(self, path: Path, tr, img: np.ndarray, fill_rule: FillRule, n_bands: int = 8, band_first: int = 0, band_step: int = 1) -> None:
+        """`Rasterizer::mask` as independent scanline bands (`rgpu_mask_banded_host`); img is dense f32 or f64 [H, W]."""
+        if img.dtype not in (np.float32, np.float64) or not img.flags.c_contiguous or img.ndim != 2:
+            raise TypeError("banded mask image must be dense float32 / float64 [H, W]")
+        c = path._c()
+        t = _as_tr(tr)
+        self._check(ffi.lib().rgpu_mask_banded_host(self.ctx, C.byref(c), t.ctypes.data_as(C.POINTER(C.c_double)), int(fill_rule), img.ctypes.data,
+                                                    img.itemsize, img.shape[1], img.shape[0], n_bands, band_first, band_step))
+
     def last_counts(self):
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         ffi.lib().rgpu_last_counts(self.ctx, C.byref(a), C.byref(b), C.byref(c))
@@ -664,6 +811,74 @@ class GpuRasterizer:
         self._check(ffi.lib().rgpu_host_alloc(self.ctx, n, C.byref(p)))
         buf = (C.c_byte * n).from_address(p.value)
         return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def _fill_batch_host(fn, handle, check, batch: PathBatch, fill_rule, paint, width, height, out: np.ndarray, trs):
+    n = len(batch)
+    if out.dtype == np.float32 and out.shape == (n, height, width, 4):
+        fmt = ffi.OUT_LINCOLOR
+    elif out.dtype == np.uint8 and out.shape == (n, height, width, 4):
+        fmt = ffi.OUT_RGBA8
+    elif out.dtype == np.float32 and out.shape == (n, height, width):
+        fmt = ffi.OUT_COVERAGE
+    else:
+        raise TypeError("out must be f32 [n,H,W,4], u8 [n,H,W,4] or f32 [n,H,W]")
+    if not out.flags.c_contiguous:
+        raise ValueError("out must be dense")
+    keep: list = []
+    cp = paint._c(keep) if paint is not None else None
+    c = batch.flat._c()
+    t = None
+    if trs is not None:
+        t = np.ascontiguousarray(trs, dtype=np.float64).reshape(n, 6)
+    check(fn(handle, C.byref(c), batch.path_subpath_offsets.ctypes.data_as(C.POINTER(C.c_uint32)), n,
+             t.ctypes.data_as(C.POINTER(C.c_double)) if t is not None else None, int(fill_rule), C.byref(cp) if cp is not None else None,
+             width, height, fmt, out.ctypes.data))
+    return out
+
+
+class MultiGpuRasterizer:
+    """`rgpu_multi`: one context + worker thread per device of the box; batches shard by path, huge canvases by
+    scanline bands, no collective."""
+
+    def __init__(self, devices=None, flatness: float = DEFAULT_FLATNESS):
+        L = ffi.lib()
+        self.h = None
+        if devices is None:
+            devices = list(range(L.rgpu_device_count()))
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = L.rgpu_multi_create(arr, len(devices), float(flatness), C.byref(h))
+        if rc != 0:
+            raise RgpuError(rc, L.rgpu_multi_last_error(None).decode())
+        self.h = h
+        self.devices = list(devices)
+
+    def close(self):
+        if self.h:
+            ffi.lib().rgpu_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise RgpuError(rc, ffi.lib().rgpu_multi_last_error(self.h).decode())
+
+    def fill_batch_host(self, batch: PathBatch, fill_rule: FillRule, paint, width: int, height: int, out: np.ndarray, trs=None) -> np.ndarray:
+        return _fill_batch_host(ffi.lib().rgpu_multi_fill_batch_host, self.h, self._check, batch, fill_rule, paint, width, height, out, trs)
+
+    def mask_banded(self, path: Path, tr, img: np.ndarray, fill_rule: FillRule, n_bands: int = 0) -> None:
+        if img.dtype not in (np.float32, np.float64) or not img.flags.c_contiguous or img.ndim != 2:
+            raise TypeError("banded mask image must be dense float32 / float64 [H, W]")
+        c = path._c()
+        t = _as_tr(tr)
+        self._check(ffi.lib().rgpu_multi_mask_banded_host(self.h, C.byref(c), t.ctypes.data_as(C.POINTER(C.c_double)), int(fill_rule),
+                                                          img.ctypes.data, img.itemsize, img.shape[1], img.shape[0], n_bands))
 
 
 def CShapeOf(start, width, height, row_stride, col_stride) -> ffi.CShape:

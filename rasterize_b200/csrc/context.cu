@@ -119,6 +119,11 @@ struct rgpu_ctx {
     std::unique_ptr<rgpu::HostPool> pool;
     std::vector<cudaEvent_t> chunk_ev;
     double widen_dev_frac = 0.2;  // share of the rows of an f64 result widened on the device (adapts, see download_widen)
+    // rgpu_fill_batch_host: second stream for the downloads, a ring of output slabs and their events
+    static constexpr int kRing = 3;
+    cudaStream_t copy_stream = nullptr;
+    DevBuf ring_slab[kRing], ring_rgba[kRing];
+    cudaEvent_t ring_done[kRing] = {nullptr, nullptr, nullptr}, ring_copied[kRing] = {nullptr, nullptr, nullptr};
     // optional stage timing
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -418,11 +423,19 @@ int scene_fallback(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, int close
     return rc;
 }
 
-int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, int close_flag, bool ordered_lines, SceneArgs* scene) {
-    if (n_jobs == 0 && !scene) return RGPU_OK;
-    if (!jobs && n_jobs) return fail(ctx, RGPU_ERR_INVALID, "jobs is NULL");
-    if (scene && (ctx->two_pass || n_jobs == 0)) return scene_fallback(ctx, jobs, n_jobs, close_flag, *scene, n_jobs != 0);
-    if (!(ctx->flatness > 0.0)) return fail(ctx, RGPU_ERR_INVALID, "flatness must be > 0 (the reference loops forever on 0)");
+// Totals of a job list after build_tables() has turned it into the device form (ctx->h_jobs / ctx->h_paints).
+struct Tables {
+    int variant = 0;
+    TileShape ts{};
+    uint32_t item_acc = 0, band_acc = 0, tile_acc = 0, n_paints = 0, n_live = 0;
+    uint64_t est_lines = 0;
+    bool all_small = true;
+    bool gradients = false;  // some job has a gradient paint
+};
+
+// rgpu_job list -> JobDev / PaintDev tables in the context's pinned staging.  Jobs that draw nothing are dropped
+// (empty windows, silent no-op fills: src/rasterize.rs:87-92, 320-322).
+int build_tables(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, int close_flag, SceneArgs* scene, Tables& tb) {
     int rc;
     if ((rc = ensure_pinned(ctx, ctx->h_jobs, ctx->h_jobs_cap, n_jobs))) return rc;
     if ((rc = ensure_pinned(ctx, ctx->h_paints, ctx->h_paints_cap, n_jobs))) return rc;
@@ -432,8 +445,10 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     // tile variant: small canvases get a (128 x 64) tile, everything else (1024 x 8)
     uint32_t max_w = 0;
     for (size_t j = 0; j < n_jobs; j++) max_w = std::max(max_w, jobs[j].width);
-    int variant = (max_w <= 128) ? 1 : 0;
-    TileShape ts = scene ? scene_tile_shape() : raster_tile_shape(variant);
+    const int variant = (max_w <= 128) ? 1 : 0;
+    const TileShape ts = scene ? scene_tile_shape() : raster_tile_shape(variant);
+    tb.variant = variant;
+    tb.ts = ts;
 
     uint32_t item_acc = 0, band_acc = 0, tile_acc = 0, n_paints = 0;
     uint64_t est_lines = 0;
@@ -454,6 +469,7 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         if (in.mode < RGPU_JOB_MASK || in.mode > RGPU_JOB_RENDER) return fail(ctx, RGPU_ERR_INVALID, "unknown job mode");
         if (in.mode == RGPU_JOB_FILL || in.mode == RGPU_JOB_RENDER) {
             if (!in.paint) return fail(ctx, RGPU_ERR_INVALID, "fill job without a paint");
+            if (in.paint->n_stops > RGPU_MAX_STOPS) return fail(ctx, RGPU_ERR_INVALID, "too many gradient stops (RGPU_MAX_STOPS)");
             // a solid paint is its colour: consecutive jobs with the same colour share one table entry
             bool same = last_paint_job && in.paint->kind == RGPU_PAINT_SOLID && last_paint->kind == RGPU_PAINT_SOLID &&
                         (last_paint == in.paint || std::memcmp(last_paint->solid, in.paint->solid, sizeof(in.paint->solid)) == 0);
@@ -511,6 +527,30 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         all_small = all_small && !scene && small_canvas_eligible(in.width, in.height, in.mode);
         ctx->h_jobs[n_live++] = d;
     }
+    tb.item_acc = item_acc;
+    tb.band_acc = band_acc;
+    tb.tile_acc = tile_acc;
+    tb.n_paints = n_paints;
+    tb.n_live = n_live;
+    tb.est_lines = est_lines;
+    tb.all_small = all_small;
+    for (uint32_t k = 0; k < n_paints; k++) tb.gradients = tb.gradients || ctx->h_paints[k].kind != 0;
+    return RGPU_OK;
+}
+
+int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, int close_flag, bool ordered_lines, SceneArgs* scene) {
+    if (n_jobs == 0 && !scene) return RGPU_OK;
+    if (!jobs && n_jobs) return fail(ctx, RGPU_ERR_INVALID, "jobs is NULL");
+    if (scene && (ctx->two_pass || n_jobs == 0)) return scene_fallback(ctx, jobs, n_jobs, close_flag, *scene, n_jobs != 0);
+    if (!(ctx->flatness > 0.0)) return fail(ctx, RGPU_ERR_INVALID, "flatness must be > 0 (the reference loops forever on 0)");
+    int rc;
+    Tables tb;
+    if ((rc = build_tables(ctx, jobs, n_jobs, close_flag, scene, tb))) return rc;
+    const int variant = tb.variant;
+    const TileShape ts = tb.ts;
+    const uint32_t item_acc = tb.item_acc, tile_acc = tb.tile_acc, n_paints = tb.n_paints, n_live = tb.n_live;
+    const uint64_t est_lines = tb.est_lines;
+    const bool all_small = tb.all_small;
     ctx->need_lines = ctx->need_refs = 0;
     if (n_live == 0) {
         std::memset(ctx->h_status, 0, sizeof(Status));
@@ -549,10 +589,10 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
             CK(ctx, cudaEventRecord(ctx->ev[2], s));
         }
         if (flags & RGPU_BATCH_INDEPENDENT) {
-            launch_small_canvas(d_jobs, 0, n_live, d_paints, thr, d_status, s);
+            launch_small_canvas(d_jobs, 0, n_live, d_paints, thr, d_status, tb.gradients, s);
             ctx->n_launches += 1;
         } else {
-            for (uint32_t j = 0; j < n_live; j++) launch_small_canvas(d_jobs, j, 1, d_paints, thr, d_status, s);
+            for (uint32_t j = 0; j < n_live; j++) launch_small_canvas(d_jobs, j, 1, d_paints, thr, d_status, tb.gradients, s);
             ctx->n_launches += n_live;
         }
         if (prof) {
@@ -665,7 +705,8 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
         char* fb = static_cast<char*>(ctx->fixed_block.p);
         d_status = reinterpret_cast<Status*>(fb + (ctx->fx_parity ? 256 : 0));
         d_status_next = reinterpret_cast<Status*>(fb + (ctx->fx_parity ? 0 : 256));
-        ctx->fx_parity ^= 1u;
+        // fx_parity is toggled only once the flatten launch (which clears the other block) is issued: an early return
+        // on the fallible steps below must not leave the next batch on a block nobody cleared
         d_tickets = reinterpret_cast<uint32_t*>(fb + 512);
         d_bc = reinterpret_cast<uint32_t*>(fb + 512 + up((size_t)ctx->fx_tickets_cap * 4));
         d_bo = d_bc;
@@ -740,6 +781,7 @@ int submit(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t flags, i
     }
     if (prof) CK(ctx, cudaEventRecord(ctx->ev[0], s));
     if (fixed) {
+        ctx->fx_parity ^= 1u;
         launch_flatten_bin_fixed(d_jobs, ctx->h_jobs, n_live, thread_acc, cut_depth, thr, d_bc, d_refs, bin_cap, ts.th, ts.cw, d_status, d_status_next, s);
         ctx->n_launches += 1;
         if (prof) CK(ctx, cudaEventRecord(ctx->ev[1], s));
@@ -889,6 +931,14 @@ void rgpu_destroy(rgpu_ctx* ctx) {
                       &ctx->tile_state, &ctx->fixed_block, &ctx->refs, &ctx->scan_temp, &ctx->status, &ctx->img_f32, &ctx->img_f64, &ctx->img_lin, &ctx->tmp_pts, &ctx->tmp_items, &ctx->scene_lists};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    for (int i = 0; i < rgpu_ctx::kRing; i++) {
+        if (ctx->ring_slab[i].p) cudaFree(ctx->ring_slab[i].p);
+        if (ctx->ring_rgba[i].p) cudaFree(ctx->ring_rgba[i].p);
+        if (ctx->ring_done[i]) cudaEventDestroy(ctx->ring_done[i]);
+        if (ctx->ring_copied[i]) cudaEventDestroy(ctx->ring_copied[i]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_jobs) cudaFreeHost(ctx->h_jobs);
@@ -1553,3 +1603,5 @@ int rgpu_fill(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill
 }
 
 }  // extern "C"
+
+#include "multi.inl"

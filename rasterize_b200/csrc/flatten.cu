@@ -152,11 +152,51 @@ flatten_bin_kernel(const JobDev* __restrict__ jobs_in, uint32_t n_jobs, const __
         count = seg_all_finite(c.seg, c.kind) ? slot_walk<false>(c, thr, status, emit) : slot_walk<true>(c, thr, status, emit);
     }
     if (PASS == 2) {
+        // Binning, one lane per (line, band): a warp prefix sum over the band counts of 32 queued lines deals the
+        // (line, band) pairs out evenly, so a long straight edge that crosses hundreds of bands (tv.path on the
+        // 32768^2 canvas: up to 337) costs every lane a few dependent counter round trips instead of one lane hundreds
+        // (round 1: that chain was 0.18 ms of the C5 step and 28 % of the C2 flatten kernel's stall samples).
         __syncwarp();
         const uint32_t n = min(q_n[warp], (uint32_t)kWarpQueue);
-        for (uint32_t i = lane; i < n; i += 32) {
-            const double4 l = q_line[warp][i];
-            bin_one(jobs[q_job[warp][i]], l.x, l.y, l.z, l.w);
+        auto bin_band = [&](const JobDev& job, const double4 l, int b) {
+            for_band_tiles(job, l.x, l.y, l.z, l.w, b, band_shift, chunk_shift, [&](uint32_t key) {
+                const uint32_t slot = atomicAdd(&tile_counts[key], 1u);
+                n_refs++;
+                if (slot < refs_cap) {
+                    bin_lines[(size_t)key * refs_cap + slot] = l;
+                } else {
+                    status->refs_overflow = 1u;
+                    atomicMax(&status->bin_max, slot + 1u);
+                }
+            });
+        };
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t i = base + lane;
+            int b0 = 0, span = 0;
+            if (i < n) {
+                const double4 l = q_line[warp][i];
+                span = band_range(jobs[q_job[warp][i]], l.y, l.w, band_shift, b0);
+            }
+            int incl = span;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int excl = incl - span;
+            for (int w0 = 0; w0 < total; w0 += 32) {
+                const int w = w0 + lane;
+                int src = 0;  // lanes whose pairs all come before pair w == the lane that owns it
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int v = __shfl_sync(0xffffffffu, incl, src + step - 1);
+                    if (v <= w) src += step;
+                }
+                src = min(src, 31);
+                const int sb0 = __shfl_sync(0xffffffffu, b0, src), sex = __shfl_sync(0xffffffffu, excl, src);
+                if (w < total) bin_band(jobs[q_job[warp][base + src]], q_line[warp][base + src], sb0 + (w - sex));
+            }
         }
     }
     if (PASS != 1) {  // total line count of the batch (statistics): one atomic per warp

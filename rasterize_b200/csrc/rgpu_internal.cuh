@@ -154,8 +154,9 @@ void launch_scene(const JobDev* jobs, uint32_t n_jobs, const PaintDev* paints, u
                   cudaStream_t s);
 // Fused one-CTA-per-job pipeline for canvases of at most 64 x 64 visible pixels (small.cu)
 bool small_canvas_eligible(uint32_t width, uint32_t height, int mode);
+// `gradients`: some job of the launch has a gradient paint (selects the kernel variant that carries the paint evaluation)
 void launch_small_canvas(const JobDev* jobs, uint32_t job_first, uint32_t n_jobs, const PaintDev* paints, double thr, Status* status,
-                         cudaStream_t s);
+                         bool gradients, cudaStream_t s);
 void launch_to_rgba8(const float4* lin, uchar4* out, size_t n, cudaStream_t s);
 void launch_fill_color(float4* lin, size_t n, float4 color, cudaStream_t s);
 void launch_f32_to_f64(const float* in, double* out, size_t n, cudaStream_t s);
@@ -169,36 +170,52 @@ void launch_blend_over(float4* dst, unsigned long long dst_stride, const float4*
 // range, src/rasterize.rs:414, 421) and, inside a band, every chunk of 2^chunk_shift columns its cells can land in
 // (x over the band's rows, clamped like the reference clamps to [0, width], 1.5 px of slack; the raster kernel is
 // exact and drops what is not in its tile).  Lines with |dy| < EPSILON add nothing (src/rasterize.rs:400-403).
-// Calls f(global tile index) for each.
+//
+// band_range: first band (layer-aligned index) and number of bands of a line, 0 = the line adds nothing.
+__device__ __forceinline__ int band_range(const JobDev& job, double y0, double y1, int band_shift, int& b0) {
+    b0 = 0;
+    if (!(fabs(y0 - y1) >= 2.220446049250313e-16)) return 0;
+    const double H = (double)job.height;
+    const double lo = fmin(y0, y1), hi = fmax(y0, y1);
+    if (!(hi > 0.0) || !(lo < H)) return 0;
+    const double first = floor(fmax(lo, 0.0));
+    const double end = fmin(H, ceil(hi));
+    if (!(first < end)) return 0;
+    b0 = ((int)first + job.oy) >> band_shift;
+    return ((((int)end - 1 + job.oy) >> band_shift) - b0) + 1;
+}
+
+// The tiles of ONE band b (as counted by band_range) that the line may touch: calls f(global tile index) for each.
+// The x range over the band's rows is evaluated in f64 — at y ~ 32768 an f32 row coordinate is 2e-3 off, which a shallow
+// line's slope would turn into many pixels — with the slope itself from an f32 division (relative error 1e-7 of at
+// most the line's x extent: far inside the 1.5 px of slack).
+template <class F>
+__device__ __forceinline__ void for_band_tiles(const JobDev& job, double x0, double y0, double x1, double y1, int b, int band_shift,
+                                               int chunk_shift, F f) {
+    const int n_chunks = (int)job.n_chunks;
+    if (n_chunks == 1) {
+        f(job.tile_begin + (uint32_t)b);
+        return;
+    }
+    const int oy = job.oy, ox = job.ox;
+    const double lo = fmin(y0, y1), hi = fmax(y0, y1);
+    const double dxdy = (double)__fdividef((float)(x1 - x0), (float)(y1 - y0));
+    const double ya = fmax((double)((b << band_shift) - oy), lo);
+    const double yb = fmin((double)(((b + 1) << band_shift) - oy), hi);
+    const double xa = fma(ya - y0, dxdy, x0), xb = fma(yb - y0, dxdy, x0);
+    const double xl = fmin(fmax(fmin(xa, xb), 0.0), job.clamp_w), xh = fmin(fmax(fmax(xa, xb), 0.0), job.clamp_w);
+    int c0 = max(0, (__double2int_rd(xl - 1.5) + ox) >> chunk_shift);
+    int c1 = min(n_chunks - 1, (__double2int_rd(xh + 2.5) + ox) >> chunk_shift);
+    if (!(xl == xl) || !(xh == xh)) { c0 = 0; c1 = n_chunks - 1; }  // NaN from degenerate input: be conservative
+    for (int c = c0; c <= c1; c++) f(job.tile_begin + (uint32_t)b * (uint32_t)n_chunks + (uint32_t)c);
+}
+
 template <class F>
 __device__ __forceinline__ void for_each_tile(const JobDev& job, double x0, double y0, double x1, double y1, int band_shift,
                                               int chunk_shift, F f) {
-    if (!(fabs(y0 - y1) >= 2.220446049250313e-16)) return;
-    const double H = (double)job.height;
-    const double lo = fmin(y0, y1), hi = fmax(y0, y1);
-    if (!(hi > 0.0) || !(lo < H)) return;
-    const double first = floor(fmax(lo, 0.0));
-    const double end = fmin(H, ceil(hi));
-    if (!(first < end)) return;
-    const int oy = job.oy, ox = job.ox;
-    const int b0 = ((int)first + oy) >> band_shift, b1 = ((int)end - 1 + oy) >> band_shift;
-    const int n_chunks = (int)job.n_chunks;
-    if (n_chunks == 1) {
-        for (int b = b0; b <= b1; b++) f(job.tile_begin + (uint32_t)b);
-        return;
-    }
-    const float fx0 = (float)x0, fy0 = (float)y0, fdxdy = (float)((x1 - x0) / (y1 - y0));
-    const float fylo = (float)lo, fyhi = (float)hi, fwc = (float)job.clamp_w;
-    for (int b = b0; b <= b1; b++) {
-        const float ya = fmaxf((float)((b << band_shift) - oy), fylo);
-        const float yb = fminf((float)(((b + 1) << band_shift) - oy), fyhi);
-        const float xa = fx0 + (ya - fy0) * fdxdy, xb = fx0 + (yb - fy0) * fdxdy;
-        const float xl = fminf(fmaxf(fminf(xa, xb), 0.0f), fwc), xh = fminf(fmaxf(fmaxf(xa, xb), 0.0f), fwc);
-        int c0 = max(0, (__float2int_rd(xl - 1.5f) + ox) >> chunk_shift);
-        int c1 = min(n_chunks - 1, ((int)(xh + 2.5f) + ox) >> chunk_shift);
-        if (!(xl == xl) || !(xh == xh)) { c0 = 0; c1 = n_chunks - 1; }  // NaN from degenerate input: be conservative
-        for (int c = c0; c <= c1; c++) f(job.tile_begin + (uint32_t)b * (uint32_t)n_chunks + (uint32_t)c);
-    }
+    int b0;
+    const int span = band_range(job, y0, y1, band_shift, b0);
+    for (int b = b0; b < b0 + span; b++) for_band_tiles(job, x0, y0, x1, y1, b, band_shift, chunk_shift, f);
 }
 
 // upper_bound-style search: largest j with begin[j] <= v, over a strided member of JobDev

@@ -1,183 +1,781 @@
 // Fused fill path for small canvases (at most 64 x 64 visible pixels, e.g. glyph batches — BASELINE config 4):
-// ONE CTA per job runs K1..K4 end to end.  The path's curves are flattened straight into shared memory, the
-// lines are accumulated into a shared-memory canvas, scanned, and the coverage (or the composited colour) is
-// written once.  No line buffer, no bins and no carries ever touch HBM: traffic is the algorithmic minimum
-// (control points in, pixels out), and a whole batch is a single launch.
+// ONE 160-thread CTA per job runs K1..K4 end to end.  No line buffer, no bins and no carries ever touch HBM: traffic
+// is the algorithmic minimum (control points in, pixels out), and a whole batch is one launch.
 //
-// Same arithmetic as the tiled pipeline: flatten primitives from flatten_device.cuh (bit-exact f64, reference
-// order inside a slot; order between slots is irrelevant for accumulation), span body / clipping / fixed-point
-// rounding / paints from raster_device.cuh.  Reference citations live in those files.
+// Round-2 design (the round-1 kernel is kept in small_v1.cu for A/B, RGPU_SMALL_V1=1).  The kernel is bound by
+// instruction issue, not by HBM, so everything below is about executing few warp-instructions with full warps:
+//   * curves are transformed ONCE into shared memory (chunks of 20 curves); a curve's subdivision tree is cut at
+//     depth 3 (8 slot threads per curve, 20 curves = 160 threads).  A slot thread descends to its subtree root and
+//     walks the two levels below it with straight-line code in registers — no stack, no loop, every lane of the warp
+//     on the same instruction — testing each child's flatness as soon as it exists;
+//   * leaves are parked in a per-warp shared-memory line queue through warp-collective "emit sites" (ballot +
+//     popc), nodes that are still not flat two levels below the slot root (a tenth of a glyph's level-5 nodes) go to
+//     a small per-warp node queue and are expanded later with one lane per child; anything deeper takes a stack-free
+//     walk by path bits (the next node of the depth-first order is recomputed from its subtree root);
+//   * a warp's line queue is drained once per round (about 120 lines of a glyph) in converged stages: lane = line
+//     (orientation, slope, row range, a warp prefix sum over the row counts), then lane = (line, row) span.  A span
+//     over at most two columns (93 % of a glyph's spans) is three shared-memory integer reductions computed without a
+//     branch; the few wider ones are set aside and done together at the end of the pass, so the rare path does not
+//     run in every round with two lanes;
+//   * there are two block barriers per job (after staging, before the row scan);
+//   * end points of a small canvas are below 128, where f32 resolves 7.6e-6: a queued line's spans are evaluated in
+//     f32 (lines that leave the canvas columns or lie far outside its rows take the f64 path of the tiled kernels,
+//     one lane each — rare).  Consecutive lines share their (identically rounded) end points, so contours stay
+//     closed and the winding stays exact; the coverage error is bounded by the 4e-6 shift of an end point.
+//
+// Same arithmetic as the tiled pipeline otherwise: subdivision decisions are bit-exact f64 in the reference's
+// expression order (products by powers of two are exact, so `fma(0.5, a, b)` is `0.5 * a + b` with one rounding —
+// only the inexact products are rounded separately), Q7.24 telescoping coverage differences, integer atomics (the
+// result does not depend on the order in which lines are accumulated).
+// Reference citations: flatten src/path.rs:744-795, src/curve.rs:413-417, 449-456, 692-697, 731-747; raster
+// src/rasterize.rs:365-507; fill src/rasterize.rs:70-115.
 #include "flatten_device.cuh"
 #include "raster_device.cuh"
 
+#include <type_traits>
+
 namespace rgpu {
+
+void launch_small_canvas_v1(const JobDev* jobs, uint32_t job_first, uint32_t n_jobs, const PaintDev* paints, double thr, Status* status,
+                            cudaStream_t s);
 
 namespace {
 
 using namespace fl;
 using namespace rs;
 
-constexpr int kSmThreads = 256;
-constexpr int kSmWarps = kSmThreads / 32;
+constexpr int kGThreads = 160;
+constexpr int kGWarps = kGThreads / 32;
+constexpr int kGDepth = 3;                                      // slot cut: 8 slot threads per curve
+constexpr int kGSlots = 1 << kGDepth;
+constexpr int kGCurves = kGThreads / kGSlots;                   // curves staged in shared memory at a time
+constexpr int kGQueue = 160;                                    // per-warp line queue: a round of 32 slots leaves ~120 lines of a glyph
+constexpr int kGSpanRows = 8;                                   // lines over more rows are done by their own lane
+constexpr int kGIds = 512;                                      // span ids of one accumulation pass (>= 2 batches of 32 lines x 8 rows)
+constexpr int kGWide = 64;                                      // spans over three or more columns, deferred to the end of a pass
+constexpr int kGDeep = 16;                                      // per-warp queue of nodes not flat at level kGDepth + 2
+constexpr int kGMaxBelow = kSlotDepth + kMaxStack - kGDepth - 3;  // walk_deep starts three levels below a slot root
 constexpr int kSmMaxW = 64, kSmMaxH = 64;
-constexpr int kSmPitch = 68;        // 64 columns + overflow column, padded to a multiple of 4 ints
-constexpr int kSmLineCap = 768;     // lines kept in shared memory per window (24 KB)
-constexpr int kSmRowBits = 6;
-constexpr int kSmSpanCap = 256;     // per-warp span list (lanes that do not fit do their rows serially)
+constexpr int kSmPitch = 68;                                    // 64 columns + overflow column, padded to a multiple of 4 ints
+constexpr unsigned kFull = 0xffffffffu;
 
-__global__ void __launch_bounds__(kSmThreads, 4)
+// A curve node in registers (quads use points 0..2)
+struct Nd {
+    double x0, x1, x2, x3, y0, y1, y2, y3;
+};
+
+__device__ __forceinline__ bool nd_has_nan(const Nd& n, int kind) {
+    bool b = isnan(n.x0) || isnan(n.y0) || isnan(n.x1) || isnan(n.y1) || isnan(n.x2) || isnan(n.y2);
+    if (kind == 4) b = b || isnan(n.x3) || isnan(n.y3);
+    return b;
+}
+
+// Curve::flatness, src/curve.rs:413-417 (quad), 692-697 (cubic).  2 * p is exact, so `3 p1 - 2 p0` is one fma.
+__device__ __forceinline__ double nd_flatness(const Nd& n, int kind) {
+    if (kind == 4) {
+        const double ux = dsub(fma(-2.0, n.x0, dmul(3.0, n.x1)), n.x3);
+        const double uy = dsub(fma(-2.0, n.y0, dmul(3.0, n.y1)), n.y3);
+        const double vx = fma(-2.0, n.x3, dsub(dmul(3.0, n.x2), n.x0));
+        const double vy = fma(-2.0, n.y3, dsub(dmul(3.0, n.y2), n.y0));
+        return dadd(dmax(dmul(ux, ux), dmul(vx, vx)), dmax(dmul(uy, uy), dmul(vy, vy)));
+    }
+    // 2.0 * p1 - p0 - p2
+    const double dx = dsub(fma(2.0, n.x1, -n.x0), n.x2);
+    const double dy = dsub(fma(2.0, n.y1, -n.y0), n.y2);
+    return dadd(dmul(dx, dx), dmul(dy, dy));
+}
+
+// split() of one coordinate (src/curve.rs:449-456, 731-747): both halves.
+//   mid = 0.125 p0 + 0.375 p1 + 0.375 p2 + 0.125 p3 (left to right)
+//   left  = (p0, 0.5 p0 + 0.5 p1, 0.25 p0 + 0.5 p1 + 0.25 p2, mid)
+//   right = (mid, 0.25 p1 + 0.5 p2 + 0.25 p3, 0.5 p2 + 0.5 p3, p3)
+__device__ __forceinline__ void split_cubic(double p0, double p1, double p2, double p3, double& a1, double& a2, double& mid, double& b1,
+                                            double& b2) {
+    mid = fma(0.125, p3, dadd(fma(0.125, p0, dmul(0.375, p1)), dmul(0.375, p2)));
+    const double h1 = dmul(0.5, p1), h2 = dmul(0.5, p2);
+    a1 = fma(0.5, p0, h1);
+    a2 = fma(0.25, p2, fma(0.25, p0, h1));
+    b1 = fma(0.25, p3, fma(0.25, p1, h2));
+    b2 = fma(0.5, p3, h2);
+}
+// quad: mid = 0.25 * (p0 + 2 p1 + p2); left = (p0, 0.5 (p0 + p1), mid); right = (mid, 0.5 (p1 + p2), p2)
+__device__ __forceinline__ void split_quad(double p0, double p1, double p2, double& a1, double& mid, double& b1) {
+    mid = dmul(0.25, dadd(fma(2.0, p1, p0), p2));
+    a1 = dmul(0.5, dadd(p0, p1));
+    b1 = dmul(0.5, dadd(p1, p2));
+}
+__device__ __forceinline__ void nd_split(const Nd& n, int kind, Nd& a, Nd& b) {
+    if (kind == 4) {
+        double mx, my;
+        split_cubic(n.x0, n.x1, n.x2, n.x3, a.x1, a.x2, mx, b.x1, b.x2);
+        split_cubic(n.y0, n.y1, n.y2, n.y3, a.y1, a.y2, my, b.y1, b.y2);
+        a.x0 = n.x0; a.y0 = n.y0; a.x3 = mx; a.y3 = my;
+        b.x0 = mx; b.y0 = my; b.x3 = n.x3; b.y3 = n.y3;
+    } else {
+        double mx, my;
+        split_quad(n.x0, n.x1, n.x2, a.x1, mx, b.x1);
+        split_quad(n.y0, n.y1, n.y2, a.y1, my, b.y1);
+        a.x0 = n.x0; a.y0 = n.y0; a.x2 = mx; a.y2 = my;
+        b.x0 = mx; b.y0 = my; b.x2 = n.x2; b.y2 = n.y2;
+        a.x3 = a.y3 = b.x3 = b.y3 = 0.0;
+    }
+}
+__device__ __forceinline__ void nd_child(Nd& n, int kind, bool r) {
+    Nd a, b;
+    nd_split(n, kind, a, b);
+    n.x0 = r ? b.x0 : a.x0; n.x1 = r ? b.x1 : a.x1; n.x2 = r ? b.x2 : a.x2; n.x3 = r ? b.x3 : a.x3;
+    n.y0 = r ? b.y0 : a.y0; n.y1 = r ? b.y1 : a.y1; n.y2 = r ? b.y2 : a.y2; n.y3 = r ? b.y3 : a.y3;
+}
+// One half of split() with the side known at compile time (the straight-line walk): 10 f64 operations per coordinate.
+template <bool R>
+__device__ __forceinline__ void half_cubic(double p0, double p1, double p2, double p3, double& o0, double& o1, double& o2, double& o3) {
+    const double mid = fma(0.125, p3, dadd(fma(0.125, p0, dmul(0.375, p1)), dmul(0.375, p2)));
+    if (R) {
+        const double h2 = dmul(0.5, p2);
+        o0 = mid; o1 = fma(0.25, p3, fma(0.25, p1, h2)); o2 = fma(0.5, p3, h2); o3 = p3;
+    } else {
+        const double h1 = dmul(0.5, p1);
+        o0 = p0; o1 = fma(0.5, p0, h1); o2 = fma(0.25, p2, fma(0.25, p0, h1)); o3 = mid;
+    }
+}
+template <bool R>
+__device__ __forceinline__ Nd nd_half(const Nd& n, int kind) {
+    Nd o;
+    if (kind == 4) {
+        half_cubic<R>(n.x0, n.x1, n.x2, n.x3, o.x0, o.x1, o.x2, o.x3);
+        half_cubic<R>(n.y0, n.y1, n.y2, n.y3, o.y0, o.y1, o.y2, o.y3);
+    } else {
+        double ax, mx, bx, ay, my, by;
+        split_quad(n.x0, n.x1, n.x2, ax, mx, bx);
+        split_quad(n.y0, n.y1, n.y2, ay, my, by);
+        o.x0 = R ? mx : n.x0; o.x1 = R ? bx : ax; o.x2 = R ? n.x2 : mx; o.x3 = 0.0;
+        o.y0 = R ? my : n.y0; o.y1 = R ? by : ay; o.y2 = R ? n.y2 : my; o.y3 = 0.0;
+    }
+    return o;
+}
+__device__ __forceinline__ double nd_endx(const Nd& n, int kind) { return kind == 4 ? n.x3 : n.x2; }
+__device__ __forceinline__ double nd_endy(const Nd& n, int kind) { return kind == 4 ? n.y3 : n.y2; }
+
+__device__ __forceinline__ int fix_f(float v) { return __float2int_rn(v * 16777216.0f); }
+
+// ---- shared memory of a CTA (file scope, so that the out-of-line helpers address it as shared memory) ------------
+__shared__ __align__(16) int s_cells[kSmMaxH * kSmPitch];
+// phase 1: per-warp line queues; phase 2: a gradient paint's table
+__shared__ __align__(16) float4 s_lineq[kGWarps][kGQueue];
+__shared__ __align__(16) double s_dq[kGWarps][kGDeep * 8];
+__shared__ __align__(16) double s_x[kGCurves][4];
+__shared__ __align__(16) double s_y[kGCurves][4];
+__shared__ unsigned short s_ids[kGWarps][kGIds];
+__shared__ unsigned short s_wide[kGWarps][kGWide];
+__shared__ unsigned char s_dkind[kGWarps][kGDeep];
+__shared__ unsigned char s_meta[kGCurves];  // kind | 8 = f64 path (control points not finite, outside the canvas columns or far from its rows)
+__shared__ int s_rowtot[kSmMaxH], s_row_touched[kSmMaxH];  // written by the f64 path only (the tiled kernels' carry state; unused here)
+__shared__ JobDev s_job;
+__shared__ uint32_t s_nlines;
+static_assert(sizeof(PaintDev) <= sizeof(s_lineq), "paint overlay");
+
+// Per-job constants of the accumulation
+struct Canvas {
+    int H, wci, tile_end;
+    float wcf;
+    double wc;
+};
+
+__device__ __forceinline__ void cell_add(int idx, int v) {
+    // result unused: a shared-memory reduction
+    atomicAdd(&s_cells[idx], v);
+}
+
+// A (line, row) span of a prepared line p = (ax, ay, +-by, dxdy) (ay < by, the sign of the third field is the line's
+// direction): the body of the reference's row loop (src/rasterize.rs:421-469) in f32.
+struct Span {
+    float xt, xn, xa, xb, d;
+    int x0i, x1i, n, fd, at;
+};
+__device__ __forceinline__ Span span_head(const float4 p, const int y, const Canvas& cv) {
+    Span s;
+    const float ax = p.x, ay = p.y, by = fabsf(p.z), dxdy = p.w;
+    const float fy = (float)y;
+    const float yt = fmaxf(fy, ay), yb = fminf(fy + 1.0f, by);
+    s.d = copysignf(yb - yt, p.z);
+    s.xt = fminf(fmaxf(fmaf(yt - ay, dxdy, ax), 0.0f), cv.wcf);
+    s.xn = fminf(fmaxf(fmaf(yb - ay, dxdy, ax), 0.0f), cv.wcf);
+    s.xa = fminf(s.xt, s.xn);
+    s.xb = fmaxf(s.xt, s.xn);
+    s.x0i = (int)s.xa;
+    s.x1i = min((int)ceilf(s.xb), cv.wci);
+    s.n = s.x1i - s.x0i;
+    s.fd = fix_f(s.d);
+    s.at = y * kSmPitch + s.x0i;
+    return s;
+}
+// one column (src/rasterize.rs:437-444) or two (:445-459), without a branch between them
+__device__ __forceinline__ void span_narrow(const Span& s, const Canvas& cv) {
+    const float fx0 = (float)s.x0i;
+    const float sf = __fdividef(1.0f, fmaxf(s.xb - s.xa, 1e-20f));
+    const float x1f = s.xb - (float)s.x1i + 1.0f;
+    const float c_narrow = 1.0f - (0.5f * (s.xt + s.xn) - fx0);
+    const float u = 1.0f - (s.xa - fx0);
+    const float c_wide = 0.5f * sf * u * u;
+    const bool two = s.n == 2;
+    const int qa = fix_f(s.d * (two ? c_wide : c_narrow));
+    const int qb = two ? fix_f(s.d * (1.0f - 0.5f * sf * x1f * x1f)) : s.fd;
+    cell_add(s.at, qa);
+    if (s.x0i + 1 < cv.tile_end) cell_add(s.at + 1, qb - qa);
+    if (two) cell_add(s.at + 2, s.fd - qb);  // x0i + 2 == x1i <= wci < tile_end
+}
+// three or more columns (src/rasterize.rs:445-468)
+__device__ __forceinline__ void span_wide(const Span& s) {
+    const float x0f = s.xa - (float)s.x0i;
+    const float sf = __fdividef(1.0f, s.xb - s.xa);
+    const float x1f = s.xb - (float)s.x1i + 1.0f;
+    const float c0 = 0.5f * sf * (1.0f - x0f) * (1.0f - x0f);
+    const float cl = 1.0f - 0.5f * sf * x1f * x1f;
+    const float a1 = sf * (1.5f - x0f);
+    int prev = fix_f(s.d * c0);
+    cell_add(s.at, prev);
+    for (int j = 1; j < s.n; j++) {
+        const float c = (j == s.n - 1) ? cl : a1 + (float)(j - 1) * sf;
+        const int cur = fix_f(s.d * c);
+        cell_add(s.at + j, cur - prev);
+        prev = cur;
+    }
+    cell_add(s.at + s.n, s.fd - prev);  // x1i <= wci < tile_end
+}
+
+// Accumulate the first `count` lines of this warp's queue.  Every end point lies inside the canvas columns [0, wc] and
+// within (-64, 128) of its rows, so the clipping branches of signed_difference_line (x > width, x < 0) cannot trigger.
+// Stage 1, lane = line (batches of 32): orientation, slope and row range (src/rasterize.rs:400-421); the prepared line
+// replaces its queue entry and its (line, row) spans are listed through a warp prefix sum.  Stage 2, lane = span.
+// Spans over three or more columns are set aside and done at the end.
+__device__ __noinline__ void accumulate_warp(const int count, const Canvas cv) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4* __restrict__ q = s_lineq[warp];
+    unsigned short* __restrict__ ids = s_ids[warp];
+    unsigned short* __restrict__ wide = s_wide[warp];
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int n_wide = 0;
+    auto do_wide = [&]() {
+        __syncwarp();
+        if (lane < n_wide) {
+            const int id = wide[lane];
+            span_wide(span_head(q[id >> 6], id & 63, cv));
+        }
+        if (lane + 32 < n_wide) {
+            const int id = wide[lane + 32];
+            span_wide(span_head(q[id >> 6], id & 63, cv));
+        }
+        n_wide = 0;
+        __syncwarp();
+    };
+    int b0 = 0;
+    while (b0 < count) {
+        int total = 0;
+        while (b0 < count && total + 32 * kGSpanRows <= kGIds) {
+            const int i = b0 + lane;
+            int n = 0, rb = 0;
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < count) {
+                const float4 l = q[i];
+                float ax = l.x, ay = l.y, bx = l.z, by = l.w;
+                float dirf = 1.0f;
+                if (ay > by) {
+                    float t;
+                    t = ax; ax = bx; bx = t;
+                    t = ay; ay = by; by = t;
+                    dirf = -1.0f;
+                }
+                if (ay != by) {
+                    p = make_float4(ax, ay, copysignf(by, dirf), __fdividef(bx - ax, by - ay));
+                    rb = (int)fmaxf(ay, 0.0f);
+                    n = max(min(cv.H, (int)ceilf(by)) - rb, 0);  // lines above or below the canvas: no rows
+                }
+                q[i] = p;
+            }
+            const bool listed = n <= kGSpanRows;
+            int incl = listed ? n : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int nb = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += nb;
+            }
+            if (listed) {
+                int at = total + incl - n;
+                for (int k = 0; k < n; k++) ids[at++] = (unsigned short)((i << 6) | (rb + k));
+            } else {  // a line over many rows (not in a glyph): its own lane walks them
+                for (int k = 0; k < n; k++) {
+                    const Span s = span_head(p, rb + k, cv);
+                    if (s.n <= 2) span_narrow(s, cv); else span_wide(s);
+                }
+            }
+            total += __shfl_sync(kFull, incl, 31);
+            b0 += 32;
+        }
+        __syncwarp();
+        for (int s0 = 0; s0 < total; s0 += 32) {
+            const int si = s0 + lane;
+            bool is_wide = false;
+            int id = 0;
+            if (si < total) {
+                id = ids[si];
+                const Span s = span_head(q[id >> 6], id & 63, cv);
+                is_wide = s.n > 2;
+                if (!is_wide) span_narrow(s, cv);
+            }
+            const unsigned mw = __ballot_sync(kFull, is_wide);
+            if (mw) {
+                if (is_wide) wide[n_wide + __popc(mw & lt_mask)] = (unsigned short)id;
+                n_wide += __popc(mw);
+                if (n_wide > kGWide - 32) do_wide();
+            }
+        }
+        __syncwarp();
+    }
+    if (n_wide) do_wide();
+    __syncwarp();
+}
+
+// rare paths, kept out of line so that their registers do not count against the flatten walk
+__device__ __noinline__ void line_slow(double x0, double y0, double x1, double y1, const Canvas cv) {
+    if (fmax(y0, y1) <= 0.0 || fmin(y0, y1) >= (double)cv.H) return;  // misses every row: the reference's row loop is empty
+    TileGeom g;
+    g.row0 = 0;
+    g.row1 = cv.H;
+    g.cx0 = 0;
+    g.wc = cv.wc;
+    g.wci = cv.wci;
+    g.tile_end = cv.tile_end;
+    g.pitch = kSmPitch;
+    line_serial<false>(make_double4(x0, y0, x1, y1), g, s_cells, s_rowtot, s_row_touched);
+}
+
+// All coordinates inside the canvas columns and near its rows: the f32 spans apply (see accumulate_warp).  A curve whose
+// control points pass this test has all its leaves pass it (they lie in the convex hull).
+__device__ __forceinline__ bool point_safe(double x, double y, const Canvas& cv) {
+    return x >= 0.0 && x <= cv.wc && y > -64.0 && y < 128.0;
+}
+
+// Per-warp state of the flatten walk
+struct Warp {
+    int qn, dn;            // warp-uniform fill levels of the line queue / the deep-node queue
+    uint32_t lines;        // leaves found by this lane
+    unsigned lt_mask;
+    int warp;
+};
+
+// Warp-collective emit site: lanes with `pred` hold a leaf (x0, y0) -> (x1, y1) of a "safe" curve.  No call, no drain:
+// the callers drain at points where little is live and size the queue for what can arrive in between.
+__device__ __forceinline__ void emit_site(bool pred, double x0, double y0, double x1, double y1, Warp& w) {
+    const unsigned mf = __ballot_sync(kFull, pred);
+    if (pred) {
+        w.lines++;
+        s_lineq[w.warp][w.qn + __popc(mf & w.lt_mask)] = make_float4((float)x0, (float)y0, (float)x1, (float)y1);
+    }
+    w.qn += __popc(mf);
+}
+// make room for `room` more lines
+__device__ __forceinline__ void ensure_room(Warp& w, int room, const Canvas& cv) {
+    if (w.qn > kGQueue - room) {
+        __syncwarp();
+        accumulate_warp(w.qn, cv);
+        w.qn = 0;
+    }
+}
+
+// Stack-free depth-first walk below `root` in the reference's order (left half first): the next node is recomputed
+// from the root along its path bits.  Curves on the f64 path and nodes still not flat three levels below a slot root get
+// here; their leaves are rasterized by this lane.  `chk`: test every node for NaN like the reference (src/path.rs:765).
+__device__ __noinline__ uint32_t walk_deep(const Nd root, const int kind, const bool chk, const double thr, const Canvas cv,
+                                           Status* __restrict__ status) {
+    Nd cur = root;
+    int depth = 0;
+    uint32_t path = 0, count = 0;
+    while (true) {
+        if (chk && nd_has_nan(cur, kind)) { atomicExch(&status->nan_flag, 1u); break; }
+        if (nd_flatness(cur, kind) < thr) {
+            count++;
+            line_slow(cur.x0, cur.y0, nd_endx(cur, kind), nd_endy(cur, kind), cv);
+            while (depth > 0 && (path & 1u)) { path >>= 1; depth--; }
+            if (depth == 0) break;
+            path |= 1u;
+            cur = root;
+#pragma unroll 1
+            for (int lv = depth - 1; lv >= 0; lv--) nd_child(cur, kind, ((path >> lv) & 1u) != 0);
+        } else if (depth >= kGMaxBelow) {
+            atomicExch(&status->depth_flag, 1u);
+            break;
+        } else {
+            nd_child(cur, kind, false);
+            depth++;
+            path <<= 1;
+        }
+    }
+    return count;
+}
+
+// Expand the queued deep nodes, one lane per child (batches of 16 nodes) while more than `keep` are queued.  All of
+// them belong to safe curves.  Returns the new fill level of the line queue; *lines_add: leaves found by this lane.
+__device__ __noinline__ int drain_deep(int qn, int dn, const int keep, uint32_t* lines_add, const double thr, const Canvas cv,
+                                       Status* __restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    Warp w;
+    w.qn = qn;
+    w.dn = 0;
+    w.lines = 0;
+    w.lt_mask = (1u << lane) - 1u;
+    w.warp = threadIdx.x >> 5;
+    const double* dq = s_dq[w.warp];
+    __syncwarp();
+    while (dn > keep) {
+        const int take = min(dn, 16);
+        dn -= take;
+        const bool valid = lane < 2 * take;
+        Nd c;
+        int kind = 4;
+        c.x0 = c.x1 = c.x2 = c.x3 = c.y0 = c.y1 = c.y2 = c.y3 = 0.0;
+        if (valid) {
+            const int e = dn + (lane >> 1);
+            const double2* src = reinterpret_cast<const double2*>(dq + 8 * e);
+            const double2 a = src[0], b = src[1], cc = src[2], dd = src[3];
+            c.x0 = a.x; c.x1 = a.y; c.x2 = b.x; c.x3 = b.y; c.y0 = cc.x; c.y1 = cc.y; c.y2 = dd.x; c.y3 = dd.y;
+            kind = s_dkind[w.warp][e];
+            nd_child(c, kind, (lane & 1) != 0);
+        }
+        const bool flat = valid && nd_flatness(c, kind) < thr;
+        ensure_room(w, 32, cv);
+        emit_site(flat, c.x0, c.y0, nd_endx(c, kind), nd_endy(c, kind), w);
+        if (valid && !flat) w.lines += walk_deep(c, kind, false, thr, cv, status);
+    }
+    *lines_add = w.lines;
+    return w.qn;
+}
+// nodes left in the deep queue after drain_deep(.., dn, keep, ..)
+__device__ __forceinline__ int deep_left(int dn, int keep) {
+    while (dn > keep) dn -= min(dn, 16);
+    return dn;
+}
+
+// Warp-collective: lanes with `pred` hold a node that is not flat two levels below its slot root.  No call in here: when
+// the queue cannot take the site's nodes (it is drained at the drain points, so this needs half the lanes to overflow at
+// once), the lanes note the site in `ovf` and redo those nodes after the walk.
+template <int SITE>
+__device__ __forceinline__ void deep_site(bool pred, const Nd& n, int kind, Warp& w, unsigned& ovf) {
+    const unsigned m = __ballot_sync(kFull, pred);
+    if (m == 0) return;
+    if (w.dn + __popc(m) > kGDeep) {
+        if (pred) ovf |= 1u << SITE;
+        return;
+    }
+    if (pred) {
+        const int e = w.dn + __popc(m & w.lt_mask);
+        double2* dst = reinterpret_cast<double2*>(s_dq[w.warp] + 8 * e);
+        dst[0] = make_double2(n.x0, n.x1);
+        dst[1] = make_double2(n.x2, n.x3);
+        dst[2] = make_double2(n.y0, n.y1);
+        dst[3] = make_double2(n.y2, n.y3);
+        s_dkind[w.warp][e] = (unsigned char)kind;
+    }
+    w.dn += __popc(m);
+}
+
+// PLAIN: no gradient paint in the batch (masks, coverage, solid fills) — the paint evaluation is compiled out
+template <int MINB, bool PLAIN>
+__global__ void __launch_bounds__(kGThreads, MINB)
 small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const PaintDev* __restrict__ paints, double thr,
                     Status* __restrict__ status) {
-    // dynamic shared memory (> 48 KB): line window | cells (plain row-major) | piece constants | per-warp span lists
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double4* lines_s = reinterpret_cast<double4*>(smem_raw);
-    int* cells = reinterpret_cast<int*>(lines_s + kSmLineCap);
-    double* p_ax = reinterpret_cast<double*>(cells + kSmMaxH * kSmPitch);
-    double* p_ay = p_ax + kSmThreads;
-    double* p_by = p_ay + kSmThreads;
-    double* p_dxdy = p_by + kSmThreads;
-    unsigned short* spans_all = reinterpret_cast<unsigned short*>(p_dxdy + kSmThreads);
-    __shared__ int rowtot[kSmMaxH];
-    __shared__ int row_touched[kSmMaxH];
-    __shared__ uint32_t n_lines_s;
-    __shared__ PaintDev s_paint;
-
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    // the job descriptor is read all through the kernel: one cooperative copy into shared memory instead of repeated
-    // (L1-latency, alias-constrained) global loads
-    __shared__ JobDev s_job;
     {
         const int* src = reinterpret_cast<const int*>(&jobs[job_first + blockIdx.x]);
         int* dst = reinterpret_cast<int*>(&s_job);
         if (tid < (int)(sizeof(JobDev) / 4)) dst[tid] = src[tid];
+        const int4 z = make_int4(0, 0, 0, 0);
+        int4* c4 = reinterpret_cast<int4*>(s_cells);
+        for (int i = tid; i < kSmMaxH * kSmPitch / 4; i += kGThreads) c4[i] = z;
+        if (tid == 0) s_nlines = 0;
     }
     __syncthreads();
     const JobDev& job = s_job;
-    const int mode = job.mode;
+    Canvas cv;
+    cv.H = job.height;
+    cv.wc = job.clamp_w;
+    cv.wci = (int)cv.wc;
+    cv.wcf = (float)cv.wc;
+    cv.tile_end = min(kSmPitch, cv.wci + 1);  // reference columns incl. the overflow column
+    Warp w;
+    w.qn = 0;
+    w.dn = 0;
+    w.lines = 0;
+    w.lt_mask = (1u << lane) - 1u;
+    w.warp = warp;
+    auto drain_deep_keep = [&](int keep) {
+        uint32_t add = 0;
+        w.qn = drain_deep(w.qn, w.dn, keep, &add, thr, cv, status);
+        w.dn = deep_left(w.dn, keep);
+        w.lines += add;
+    };
 
-    {
-        const int4 z = make_int4(0, 0, 0, 0);
-        int4* c4 = reinterpret_cast<int4*>(cells);
-        for (int i = tid; i < kSmMaxH * kSmPitch / 4; i += kSmThreads) c4[i] = z;
-    }
-    if (tid < kSmMaxH) { rowtot[tid] = 0; row_touched[tid] = 0; }
-    const bool render = mode == kModeRender;  // fill onto a canvas created here: every pixel is written, none is read
-    if (mode >= kModeFill && job.paint_index >= 0) {
-        const int* src = reinterpret_cast<const int*>(&paints[job.paint_index]);
-        int* dst = reinterpret_cast<int*>(&s_paint);
-        for (int i = tid; i < (int)(sizeof(PaintDev) / 4); i += kSmThreads) dst[i] = src[i];
-    }
-
-    TileGeom g;
-    g.row0 = 0;
-    g.row1 = job.height;
-    g.cx0 = 0;
-    g.wc = job.clamp_w;
-    g.wci = (int)g.wc;
-    g.tile_end = min(kSmPitch, g.wci + 1);  // reference columns incl. the overflow column
-    g.pitch = kSmPitch;
-    unsigned short* spans = spans_all + warp * kSmSpanCap;
-    __syncthreads();
-
-    // ---- K1 into shared memory, K3 phase 1 from shared memory -----------------------------------------------
-    // One depth-first walk per slot: every leaf claims a place in the shared line window with a shared-memory
-    // atomic (the order of lines is irrelevant to the fixed-point accumulation).  If the window is full the
-    // emitting thread rasterizes that line itself, so any path size works; ordinary glyphs fit in one window.
-    const uint32_t total_slots = job.n_items * kSlotsPerItem;
-    uint32_t my_lines = 0;
-    for (uint32_t s0 = 0; s0 < total_slots; s0 += kSmThreads) {
-        if (tid == 0) n_lines_s = 0;
+    const uint32_t n_items = job.n_items, n_curves = job.n_curves;
+    // ---- curves (first in the packed order): chunks of 20, 8 slot threads each --------------------------------
+    for (uint32_t c0 = 0; c0 < n_curves; c0 += kGCurves) {
+        const uint32_t cn = min((uint32_t)kGCurves, n_curves - c0);
+        if (c0) __syncthreads();  // the previous chunk's slots are done with s_x / s_y
+        if (tid < kGCurves * 4) {
+            // stage: thread = (curve, point); Transform::apply once per control point
+            const uint32_t i = (uint32_t)tid >> 2, j = (uint32_t)tid & 3u;
+            bool slow = false;
+            int kind = 0;
+            if (i < cn) {
+                const uint2 it = job.items_packed[c0 + i];
+                kind = (int)it.y;
+                if (j < (uint32_t)kind) {
+                    const P2 p = tr_apply(job.tr, job.pts[it.x + j]);
+                    s_x[i][j] = p.x;
+                    s_y[i][j] = p.y;
+                    slow = !point_safe(p.x, p.y, cv);  // also true for NaN / infinite coordinates
+                } else {
+                    s_x[i][j] = 0.0;
+                    s_y[i][j] = 0.0;
+                }
+            }
+            // kGCurves * 4 = 80 threads: warps 0, 1 and the lower half of warp 2 — the four lanes of a curve are in one warp.
+            // (no short-circuit around the shuffles: every lane of the group must execute them)
+            const unsigned grp = __activemask();
+            const bool s1 = __shfl_xor_sync(grp, slow, 1);
+            slow = slow | s1;
+            const bool s2 = __shfl_xor_sync(grp, slow, 2);
+            slow = slow | s2;
+            if (i < cn && j == 0) s_meta[i] = (unsigned char)(kind | (slow ? 8 : 0));
+        }
         __syncthreads();
-        // the job table entry doubles as a one-job table for slot_setup: slot t of this job is global slot
-        // item_begin*8 + t of a table whose only entry starts at item_begin
-        const uint32_t t = s0 + tid;
-        SlotCtx c;
-        if (t < total_slots && slot_setup(&job, 1, job.item_begin * kSlotsPerItem + t, thr, c, status)) {
-            auto emit = [&](double x0, double y0, double x1, double y1) {
-                const uint32_t k = atomicAdd(&n_lines_s, 1u);
-                if (k < (uint32_t)kSmLineCap) {
-                    lines_s[k] = make_double4(x0, y0, x1, y1);
-                } else {  // window full: rasterize here (serial in this thread)
-                    line_serial<false>(make_double4(x0, y0, x1, y1), g, cells, rowtot, row_touched);
+
+        // one round: thread = (curve, slot)
+        const uint32_t ci = (uint32_t)tid >> kGDepth, slot = (uint32_t)tid & (kGSlots - 1);
+        bool act = false, leaf = false, slow = false;
+        int kind = 4;
+        Nd nd;
+        nd.x0 = nd.x1 = nd.x2 = nd.x3 = nd.y0 = nd.y1 = nd.y2 = nd.y3 = 0.0;
+        if (ci < cn) {
+            const int meta = s_meta[ci];
+            kind = meta & 7;
+            slow = (meta & 8) != 0;
+            const double2 xa = *reinterpret_cast<const double2*>(&s_x[ci][0]);
+            const double2 xb = *reinterpret_cast<const double2*>(&s_x[ci][2]);
+            const double2 ya = *reinterpret_cast<const double2*>(&s_y[ci][0]);
+            const double2 yb = *reinterpret_cast<const double2*>(&s_y[ci][2]);
+            nd.x0 = xa.x; nd.x1 = xa.y; nd.x2 = xb.x; nd.x3 = xb.y;
+            nd.y0 = ya.x; nd.y1 = ya.y; nd.y2 = yb.x; nd.y3 = yb.y;
+            act = true;
+            // descend to this slot's subtree root (bits of `slot`, most significant first).  A NaN control point makes every
+            // flatness NaN (never < thr): such a curve descends to the cut and is reported by walk_deep below.
+#pragma unroll 1
+            for (int level = 0; level < kGDepth; level++) {
+                if (nd_flatness(nd, kind) < thr) {
+                    // a leaf above the cut: owned by the slot whose remaining bits are all zero
+                    if (slot & ((1u << (kGDepth - level)) - 1u)) act = false;
+                    else leaf = true;
+                    break;
+                }
+                nd_child(nd, kind, ((slot >> (kGDepth - 1 - level)) & 1u) != 0);
+            }
+        }
+        slow = slow && act;  // this slot's whole subtree on the f64 path, after the walk
+        act = act && !slow;
+        if (act && !leaf) leaf = nd_flatness(nd, kind) < thr;
+        // The two levels below the slot root in straight-line code without a call: every child's flatness is tested as
+        // soon as it exists.  Queue budget: the queue is empty at the start of a round and a lane emits at most two lines
+        // in each half of the walk (slot root or first child, then that child's two children).
+        emit_site(act && leaf, nd.x0, nd.y0, nd_endx(nd, kind), nd_endy(nd, kind), w);
+        const bool go = act && !leaf;
+        unsigned ovf = 0;
+        if (__any_sync(kFull, go)) {
+            // one child at a time (the sibling is recomputed from its parent: 14 more f64 operations per split than
+            // splitting once, but only three nodes are ever live)
+            auto leaf2 = [&](const Nd& b, const bool ga, auto site) {
+                const bool fb = ga && nd_flatness(b, kind) < thr;
+                emit_site(fb, b.x0, b.y0, nd_endx(b, kind), nd_endy(b, kind), w);
+                deep_site<decltype(site)::value>(ga && !fb, b, kind, w, ovf);
+            };
+            auto level1 = [&](const Nd& a, auto side) {
+                const bool fa = go && nd_flatness(a, kind) < thr;
+                emit_site(fa, a.x0, a.y0, nd_endx(a, kind), nd_endy(a, kind), w);
+                const bool ga = go && !fa;
+                if (__any_sync(kFull, ga)) {
+                    leaf2(nd_half<false>(a, kind), ga, std::integral_constant<int, decltype(side)::value * 2>{});
+                    leaf2(nd_half<true>(a, kind), ga, std::integral_constant<int, decltype(side)::value * 2 + 1>{});
                 }
             };
-            if (seg_all_finite(c.seg, c.kind)) my_lines += slot_walk<false>(c, thr, status, emit);
-            else my_lines += slot_walk<true>(c, thr, status, emit);
+            level1(nd_half<false>(nd, kind), std::integral_constant<int, 0>{});
+            // drain point: only the slot root is live
+            if (w.dn >= 16) drain_deep_keep(15);
+            ensure_room(w, 64, cv);
+            level1(nd_half<true>(nd, kind), std::integral_constant<int, 1>{});
         }
-        __syncthreads();
-        const uint32_t n = min(n_lines_s, (uint32_t)kSmLineCap);
-        for (uint32_t i0 = warp * 32; i0 < n; i0 += kSmThreads) {
-            const uint32_t i = i0 + lane;
-            const bool valid = i < n;
-            const double4 l = valid ? lines_s[i] : make_double4(0, 0, 0, 0);
-            warp_accumulate_round<false, kSmRowBits, kSmSpanCap, unsigned short>(l, valid, g, cells, rowtot, row_touched, p_ax, p_ay, p_by, p_dxdy, spans, tid);
+        if (w.dn >= 16) drain_deep_keep(15);
+        // the round's lines in one pass
+        if (w.qn) {
+            __syncwarp();
+            accumulate_warp(w.qn, cv);
+            w.qn = 0;
         }
-        __syncthreads();
+        // rare: nodes the deep queue could not take, and slots of curves on the f64 path
+        if (ovf) {
+            for (int site = 0; site < 4; site++)
+                if ((ovf >> site) & 1u) {
+                    Nd b = nd;
+                    nd_child(b, kind, (site >> 1) != 0);
+                    nd_child(b, kind, (site & 1) != 0);
+                    w.lines += walk_deep(b, kind, false, thr, cv, status);
+                }
+        }
+        if (slow) {
+            if (leaf) {
+                w.lines++;
+                if (nd_has_nan(nd, kind)) atomicExch(&status->nan_flag, 1u);
+                else line_slow(nd.x0, nd.y0, nd_endx(nd, kind), nd_endy(nd, kind), cv);
+            } else {
+                w.lines += walk_deep(nd, kind, true, thr, cv, status);
+            }
+        }
     }
-    // line count of the batch (statistics only): one atomic per warp
+    // ---- lines and closing lines: one thread each, straight from the path -------------------------------------
+    for (uint32_t i0 = n_curves; i0 < n_items; i0 += kGThreads) {
+        const uint32_t i = i0 + tid;
+        bool pred = false;
+        double x0 = 0.0, y0 = 0.0, x1 = 0.0, y1 = 0.0;
+        if (i < n_items) {
+            const uint2 it = job.items_packed[i];
+            uint32_t ia, ib;
+            if (it.y & kItemClosing) {
+                // Line::new(subpath.end(), subpath.start()).transform(tr), src/path.rs:781-785: emitted when the subpath
+                // is closed or `close` is set, even if zero length
+                pred = (it.y & kItemExplicitClosed) || job.close;
+                ia = it.x;
+                ib = it.y & kItemIndexMask;
+            } else {
+                pred = true;
+                ia = it.x;
+                ib = it.x + 1;
+            }
+            if (pred) {
+                const P2 a = tr_apply(job.tr, job.pts[ia]);
+                const P2 b = tr_apply(job.tr, job.pts[ib]);
+                x0 = a.x; y0 = a.y; x1 = b.x; y1 = b.y;
+                // Line: flatness 0 < thr (src/curve.rs:233-235); NaN end points panic in the reference (src/path.rs:765-767)
+                if (isnan(x0) || isnan(y0) || isnan(x1) || isnan(y1)) {
+                    atomicExch(&status->nan_flag, 1u);
+                    pred = false;
+                } else if (!(point_safe(x0, y0, cv) && point_safe(x1, y1, cv))) {
+                    w.lines++;
+                    line_slow(x0, y0, x1, y1, cv);
+                    pred = false;
+                }
+            }
+        }
+        ensure_room(w, 32, cv);
+        emit_site(pred, x0, y0, x1, y1, w);
+    }
+    if (w.dn) drain_deep_keep(0);
+    if (w.qn) {
+        __syncwarp();
+        accumulate_warp(w.qn, cv);
+        w.qn = 0;
+    }
     {
-        uint32_t v = my_lines;
+        uint32_t v = w.lines;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0 && v) atomicAdd(&status->n_lines, v);
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        if (lane == 0 && v) atomicAdd(&s_nlines, v);
     }
     __syncthreads();
+    if (tid == 0 && s_nlines) atomicAdd(&status->n_lines, s_nlines);  // statistics only
 
     // ---- K3 phase 2 + K4: two rows per warp iteration (16 lanes x 4 columns each) ----------------------------
+    int* const cells = s_cells;
+    const int mode = job.mode;
+    const bool render = mode == kModeRender;  // fill onto a canvas created here: every pixel is written, none is read
     const int wout = job.width_out, hout = job.height;
     const int half = lane >> 4, hl = lane & 15;
     const bool evenodd = job.rule == 1;
-    // per-thread constants of the composite loop: a solid paint is its colour (glyph batches), the canvas window's base
-    const bool solid = mode >= kModeFill && (job.paint_index < 0 || s_paint.kind == 0);
-    const float4 solid_c = (mode >= kModeFill && job.paint_index >= 0) ? make_float4(s_paint.solid[0], s_paint.solid[1], s_paint.solid[2], s_paint.solid[3])
-                                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool has_paint = mode >= kModeFill && job.paint_index >= 0;
+    const PaintDev& s_paint = *reinterpret_cast<const PaintDev*>(&s_lineq[0][0]);
+    bool solid = true;
+    float4 solid_c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_paint) {
+        const PaintDev* gp = &paints[job.paint_index];
+        solid = PLAIN || gp->kind == 0;
+        if (solid) {
+            solid_c = *reinterpret_cast<const float4*>(gp->solid);
+        } else {  // gradient: its table replaces the line queues
+            const int* src = reinterpret_cast<const int*>(gp);
+            int* dst = reinterpret_cast<int*>(&s_lineq[0][0]);
+            for (int i = tid; i < (int)(sizeof(PaintDev) / 4); i += kGThreads) dst[i] = src[i];
+            __syncthreads();
+        }
+    }
+    // RENDER with a solid colour whose components are finite and not negative (the glyph batch): the composite
+    // `0.blend_over(colour * alpha)` is colour * alpha exactly — colour * alpha + 0 * (1 - colour.a * alpha) adds +0 to a
+    // value that is never -0 — so a pixel is four multiplications and one store
+    const bool plain = render && solid && solid_c.x >= 0.f && solid_c.y >= 0.f && solid_c.z >= 0.f && solid_c.w >= 0.f &&
+                       !signbit(solid_c.x) && !signbit(solid_c.y) && !signbit(solid_c.z) && !signbit(solid_c.w) && solid_c.x < 3e38f &&
+                       solid_c.y < 3e38f && solid_c.z < 3e38f && solid_c.w < 3e38f;
     float4* const out_base = reinterpret_cast<float4*>(job.canvas) + job.origin;
     const unsigned long long row_stride = job.row_stride;
-    for (int r2 = warp * 2; r2 < hout; r2 += kSmWarps * 2) {
+    for (int r2 = warp * 2; r2 < hout; r2 += kGWarps * 2) {
         const int r = r2 + half;
         const bool rvalid = r < hout;
         int* rowc = cells + (rvalid ? r : 0) * kSmPitch;
-        int4 q = make_int4(0, 0, 0, 0);
-        if (rvalid) q = *reinterpret_cast<const int4*>(rowc + hl * 4);
-        const int p0 = q.x, p1 = p0 + q.y, p2 = p1 + q.z, p3 = p2 + q.w;
+        int4 qv = make_int4(0, 0, 0, 0);
+        if (rvalid) qv = *reinterpret_cast<const int4*>(rowc + hl * 4);
+        const int p0 = qv.x, p1 = p0 + qv.y, p2 = p1 + qv.z, p3 = p2 + qv.w;
         int incl = p3;
 #pragma unroll
         for (int o = 1; o < 16; o <<= 1) {
-            const int nb = __shfl_up_sync(0xffffffffu, incl, o, 16);
+            const int nb = __shfl_up_sync(kFull, incl, o, 16);
             if (hl >= o) incl += nb;
         }
         const int base = incl - p3;
-        float4 cv;
+        float4 c;
         if (evenodd)
-            cv = make_float4(coverage_from_fixed<true>(base + p0), coverage_from_fixed<true>(base + p1), coverage_from_fixed<true>(base + p2),
-                             coverage_from_fixed<true>(base + p3));
+            c = make_float4(coverage_from_fixed<true>(base + p0), coverage_from_fixed<true>(base + p1), coverage_from_fixed<true>(base + p2),
+                            coverage_from_fixed<true>(base + p3));
         else
-            cv = make_float4(coverage_from_fixed<false>(base + p0), coverage_from_fixed<false>(base + p1),
-                             coverage_from_fixed<false>(base + p2), coverage_from_fixed<false>(base + p3));
+            c = make_float4(coverage_from_fixed<false>(base + p0), coverage_from_fixed<false>(base + p1),
+                            coverage_from_fixed<false>(base + p2), coverage_from_fixed<false>(base + p3));
         const int col = hl * 4;
+        if (mode != kModeMask) {  // mask_iter drops abs(alpha) < 1e-6 (src/rasterize.rs:348); fill_impl sees that iterator
+            if (c.x < 1e-6f) c.x = 0.f;
+            if (c.y < 1e-6f) c.y = 0.f;
+            if (c.z < 1e-6f) c.z = 0.f;
+            if (c.w < 1e-6f) c.w = 0.f;
+        }
         if (mode < kModeFill) {
             if (rvalid) {
-                if (mode == kModeCoverage) {  // mask_iter drops abs(alpha) < 1e-6 (src/rasterize.rs:348)
-                    if (cv.x < 1e-6f) cv.x = 0.f;
-                    if (cv.y < 1e-6f) cv.y = 0.f;
-                    if (cv.z < 1e-6f) cv.z = 0.f;
-                    if (cv.w < 1e-6f) cv.w = 0.f;
-                }
                 float* out = reinterpret_cast<float*>(job.canvas) + job.origin + (unsigned long long)r * job.row_stride;
                 if (col + 3 < wout && ((reinterpret_cast<uintptr_t>(out + col) & 15) == 0)) {
-                    __stcs(reinterpret_cast<float4*>(out + col), cv);
+                    __stcs(reinterpret_cast<float4*>(out + col), c);
                 } else {
-                    if (col < wout) out[col] = cv.x;
-                    if (col + 1 < wout) out[col + 1] = cv.y;
-                    if (col + 2 < wout) out[col + 2] = cv.z;
-                    if (col + 3 < wout) out[col + 3] = cv.w;
+                    if (col < wout) out[col] = c.x;
+                    if (col + 1 < wout) out[col + 1] = c.y;
+                    if (col + 2 < wout) out[col + 2] = c.z;
+                    if (col + 3 < wout) out[col + 3] = c.w;
                 }
             }
+            continue;
+        }
+        // stage the two rows' coverage so that consecutive lanes composite consecutive pixels (16 B each)
+        if (rvalid) *reinterpret_cast<float4*>(rowc + col) = c;
+        __syncwarp();
+        if (plain && wout == 64 && r2 + 1 < hout) {
+            const float* al = reinterpret_cast<const float*>(cells + r2 * kSmPitch);
+            float4* o0 = out_base + (unsigned long long)r2 * row_stride;
+            float4* o1 = o0 + row_stride;
+            const float a0 = al[lane], a1 = al[lane + 32], a2 = al[kSmPitch + lane], a3 = al[kSmPitch + lane + 32];
+            __stcs(o0 + lane, make_float4(fmul(solid_c.x, a0), fmul(solid_c.y, a0), fmul(solid_c.z, a0), fmul(solid_c.w, a0)));
+            __stcs(o0 + lane + 32, make_float4(fmul(solid_c.x, a1), fmul(solid_c.y, a1), fmul(solid_c.z, a1), fmul(solid_c.w, a1)));
+            __stcs(o1 + lane, make_float4(fmul(solid_c.x, a2), fmul(solid_c.y, a2), fmul(solid_c.z, a2), fmul(solid_c.w, a2)));
+            __stcs(o1 + lane + 32, make_float4(fmul(solid_c.x, a3), fmul(solid_c.y, a3), fmul(solid_c.z, a3), fmul(solid_c.w, a3)));
         } else {
-            // stage the two rows' coverage so that consecutive lanes composite consecutive pixels (16 B each)
-            if (rvalid) *reinterpret_cast<float4*>(rowc + col) = cv;
-            __syncwarp();
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int pidx = i * 32 + lane;  // 0..127 over the two rows
@@ -185,8 +783,9 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
                 if (rr < hout && px < wout) {
                     const float alpha = reinterpret_cast<const float*>(cells + rr * kSmPitch)[px];
                     float4* out = out_base + (unsigned long long)rr * row_stride;
-                    if (alpha >= 1e-6f) {
-                        float4 color = solid ? solid_c : paint_at(s_paint, px, rr);
+                    if (alpha != 0.0f) {
+                        float4 color = solid_c;
+                        if (!PLAIN && !solid) color = paint_at(s_paint, px, rr);
                         color = make_float4(fmul(color.x, alpha), fmul(color.y, alpha), fmul(color.z, alpha), fmul(color.w, alpha));
                         float4 dstc = render ? make_float4(0.f, 0.f, 0.f, 0.f) : out[px];  // `Layer::new`: transparent
                         const float k = fsub(1.0f, color.w);
@@ -198,8 +797,8 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
                     }
                 }
             }
-            __syncwarp();
         }
+        __syncwarp();
     }
 }
 
@@ -212,18 +811,22 @@ bool small_canvas_eligible(uint32_t width, uint32_t height, int mode) {
 }
 
 void launch_small_canvas(const JobDev* jobs, uint32_t job_first, uint32_t n_jobs, const PaintDev* paints, double thr, Status* status,
-                         cudaStream_t s) {
+                         bool gradients, cudaStream_t s) {
     if (n_jobs == 0) return;
-    constexpr size_t smem = sizeof(double4) * kSmLineCap + sizeof(int) * kSmMaxH * kSmPitch + sizeof(double) * 4 * kSmThreads +
-                            sizeof(unsigned short) * kSmSpanCap * kSmWarps;
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaFuncSetAttribute(small_canvas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured[dev] = true;
+    static const bool use_v1 = getenv("RGPU_SMALL_V1") != nullptr;  // A/B switch: the round-1 kernel
+    if (use_v1) {
+        launch_small_canvas_v1(jobs, job_first, n_jobs, paints, thr, status, s);
+        return;
     }
-    small_canvas_kernel<<<n_jobs, kSmThreads, smem, s>>>(jobs, job_first, paints, thr, status);
+    // CTAs per SM (register budget): 4 -> 96, 5 -> 80
+    static const int minb = getenv("RGPU_SMALL_MINB") ? atoi(getenv("RGPU_SMALL_MINB")) : 5;
+    if (gradients) {
+        small_canvas_kernel<4, false><<<n_jobs, kGThreads, 0, s>>>(jobs, job_first, paints, thr, status);
+    } else if (minb <= 4) {
+        small_canvas_kernel<4, true><<<n_jobs, kGThreads, 0, s>>>(jobs, job_first, paints, thr, status);
+    } else {
+        small_canvas_kernel<5, true><<<n_jobs, kGThreads, 0, s>>>(jobs, job_first, paints, thr, status);
+    }
 }
 
 }  // namespace rgpu

@@ -13,6 +13,7 @@ LIB_PATH = PKG / "librasterize_b200.so"
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NAN, ERR_DEPTH, ERR_CAPACITY = 0, -1, -2, -3, -4, -5
 JOB_MASK, JOB_COVERAGE, JOB_FILL, JOB_RENDER = 0, 1, 2, 3
+OUT_LINCOLOR, OUT_RGBA8, OUT_COVERAGE = 0, 1, 2
 BATCH_ORDERED, BATCH_INDEPENDENT = 0, 1
 MAX_STOPS = 32
 
@@ -67,6 +68,9 @@ SYMBOLS = [
     "rgpu_last_stage_ms", "rgpu_to_rgba8_dev", "rgpu_layer_scale_by_mask_dev", "rgpu_layer_blend_over_dev", "rgpu_download_rgba8",
     "rgpu_fill_color_dev", "rgpu_stream", "rgpu_sync", "rgpu_device_alloc", "rgpu_device_free", "rgpu_device_zero",
     "rgpu_memcpy_h2d", "rgpu_memcpy_d2h", "rgpu_host_alloc", "rgpu_host_free",
+    "rgpu_path_upload_batch", "rgpu_path_batch_get", "rgpu_path_batch_free", "rgpu_batch_create", "rgpu_batch_render", "rgpu_batch_free",
+    "rgpu_fill_batch_host", "rgpu_mask_banded_host", "rgpu_multi_create", "rgpu_multi_destroy", "rgpu_multi_device_count",
+    "rgpu_multi_last_error", "rgpu_multi_fill_batch_host", "rgpu_multi_mask_banded_host",
 ]
 
 
@@ -124,5 +128,20 @@ def lib():
     sig("rgpu_memcpy_d2h", i32, vp, vp, vp, sz)
     sig("rgpu_host_alloc", i32, vp, sz, C.POINTER(vp))
     sig("rgpu_host_free", i32, vp, vp)
+    pu32 = C.POINTER(C.c_uint32)
+    sig("rgpu_path_upload_batch", i32, vp, C.POINTER(CPath), pu32, sz, C.POINTER(vp))
+    sig("rgpu_path_batch_get", vp, vp, sz)
+    sig("rgpu_path_batch_free", None, vp, vp)
+    sig("rgpu_batch_create", i32, vp, vp, sz, u32, C.POINTER(vp))
+    sig("rgpu_batch_render", i32, vp, vp)
+    sig("rgpu_batch_free", None, vp, vp)
+    sig("rgpu_fill_batch_host", i32, vp, C.POINTER(CPath), pu32, sz, pd, i32, C.POINTER(CPaint), u32, u32, i32, vp)
+    sig("rgpu_mask_banded_host", i32, vp, C.POINTER(CPath), pd, i32, vp, sz, sz, sz, u32, u32, u32)
+    sig("rgpu_multi_create", i32, C.POINTER(C.c_int), i32, dbl, C.POINTER(vp))
+    sig("rgpu_multi_destroy", None, vp)
+    sig("rgpu_multi_device_count", i32, vp)
+    sig("rgpu_multi_last_error", C.c_char_p, vp)
+    sig("rgpu_multi_fill_batch_host", i32, vp, C.POINTER(CPath), pu32, sz, pd, i32, C.POINTER(CPaint), u32, u32, i32, vp)
+    sig("rgpu_multi_mask_banded_host", i32, vp, C.POINTER(CPath), pd, i32, vp, sz, sz, sz, u32)
     _lib = L
     return L

@@ -35,6 +35,23 @@ def _as_i32(v: float) -> int:
     return int(max(-2 ** 31, min(2 ** 31 - 1, math.trunc(v))))
 
 
+def fill_window(bbox, lx: int, ly: int, W: int, H: int):
+    """Window of a W x H layer at (lx, ly) that the Fill arm of `Pipeline::render_rec` draws a node with bounding box `bbox`
+    into (src/scene.rs:412-423 + `view_shape`, src/image.rs:588-605): columns [floor(min x) - lx, ceil(max x) - lx + 1),
+    rows alike, clamped to the layer.  The reference casts the i32 bounds `as usize`: a NEGATIVE bound (a node that
+    starts left of or above the layer — impossible through `Scene::render`, which restricts every bbox to the view, but
+    possible for a hand-built node table) wraps to a huge value that `view_shape` clamps to the layer's width / height,
+    so such a node gets an EMPTY window and draws nothing.  Reproduced here.  Returns (col_min, row_min, width, height)."""
+    def as_usize(v: int) -> int:
+        return v if v >= 0 else v + (1 << 64)
+
+    col_min = min(as_usize(_as_i32(math.floor(bbox[0])) - lx), W)
+    col_max = min(max(as_usize(_as_i32(math.ceil(bbox[2])) - lx + 1), col_min), W)
+    row_min = min(as_usize(_as_i32(math.floor(bbox[1])) - ly), H)
+    row_max = min(max(as_usize(_as_i32(math.ceil(bbox[3])) - ly + 1), row_min), H)
+    return col_min, row_min, col_max - col_min, row_max - row_min
+
+
 @dataclass
 class PipelineNode:
     """One node of `Pipeline` (src/scene.rs:225-262)."""
@@ -133,16 +150,15 @@ def _render_rec(rast: GpuRasterizer, nodes, node_id: int, layer: DeviceLayer, tr
     node = nodes[node_id]
     if node.kind == FILL:
         # window of the layer covered by the node: `view_shape` clamps like src/image.rs:588-605
-        W, H = layer.width, layer.height
-        col_min = max(0, min(_as_i32(math.floor(node.bbox[0])) - layer.x, W))
-        col_max = max(col_min, min(_as_i32(math.ceil(node.bbox[2])) - layer.x + 1, W))
-        row_min = max(0, min(_as_i32(math.floor(node.bbox[1])) - layer.y, H))
-        row_max = max(row_min, min(_as_i32(math.ceil(node.bbox[3])) - layer.y + 1, H))
+        W = layer.width
+        col_min, row_min, ww, wh = fill_window(node.bbox, layer.x, layer.y, W, layer.height)
+        if ww == 0 or wh == 0:
+            return
         align = Transform.new_translate(-math.floor(node.bbox[0]), -math.floor(node.bbox[1]))
         dp = rast.upload(node.path)
         layer.keep.append(dp)
-        layer.pending.append(Job(dp, align * Transform.from_array(node.tr), node.fill_rule, ffi.JOB_FILL, layer.ptr, col_max - col_min,
-                                 row_max - row_min, W, origin=row_min * W + col_min, paint=node.paint, path_bbox=node.path_bbox))
+        layer.pending.append(Job(dp, align * Transform.from_array(node.tr), node.fill_rule, ffi.JOB_FILL, layer.ptr, ww, wh, W,
+                                 origin=row_min * W + col_min, paint=node.paint, path_bbox=node.path_bbox))
     elif node.kind == GROUP:
         for c in node.children:
             _render_rec(rast, nodes, c, layer, trash)
@@ -223,17 +239,14 @@ def fixture_jobs(rast: GpuRasterizer, sc, layer_ptr: int):
     W, H = math.ceil(x1) - lx, math.ceil(y1) - ly
     jobs, keep, in_bytes = [], [], 0
     for f in sc.fills:
-        bx0, by0, bx1, by1 = f.bbox
-        col_min = max(0, min(math.floor(bx0) - lx, W))
-        col_max = max(col_min, min(math.ceil(bx1) - lx + 1, W))
-        row_min = max(0, min(math.floor(by0) - ly, H))
-        row_max = max(row_min, min(math.ceil(by1) - ly + 1, H))
+        bx0, by0 = f.bbox[0], f.bbox[1]
+        col_min, row_min, ww, wh = fill_window(f.bbox, lx, ly, W, H)
         tr = Transform.new_translate(-math.floor(bx0), -math.floor(by0)) * Transform.from_array(f.tr)
         dp = rast.upload(f.path)
         keep.append(dp)
         in_bytes += f.path.input_bytes()
-        jobs.append(Job(dp, tr, f.fill_rule, ffi.JOB_FILL, layer_ptr, col_max - col_min, row_max - row_min, W,
-                        origin=row_min * W + col_min, paint=f.paint, path_bbox=f.path_bbox))
+        jobs.append(Job(dp, tr, f.fill_rule, ffi.JOB_FILL, layer_ptr, ww, wh, W, origin=row_min * W + col_min, paint=f.paint,
+                        path_bbox=f.path_bbox))
     return jobs, keep, W, H, in_bytes
 
 
@@ -245,11 +258,8 @@ def fixture_fills_host(sc):
     W, H = math.ceil(x1) - lx, math.ceil(y1) - ly
     fills = []
     for f in sc.fills:
-        bx0, by0, bx1, by1 = f.bbox
-        col_min = max(0, min(math.floor(bx0) - lx, W))
-        col_max = max(col_min, min(math.ceil(bx1) - lx + 1, W))
-        row_min = max(0, min(math.floor(by0) - ly, H))
-        row_max = max(row_min, min(math.ceil(by1) - ly + 1, H))
+        bx0, by0 = f.bbox[0], f.bbox[1]
+        col_min, row_min, ww, wh = fill_window(f.bbox, lx, ly, W, H)
         tr = Transform.new_translate(-math.floor(bx0), -math.floor(by0)) * Transform.from_array(f.tr)
-        fills.append((f.path, tr, f.fill_rule, f.paint, f.path_bbox, col_min, row_min, col_max - col_min, row_max - row_min))
+        fills.append((f.path, tr, f.fill_rule, f.paint, f.path_bbox, col_min, row_min, ww, wh))
     return fills, W, H

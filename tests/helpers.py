@@ -6,6 +6,7 @@ import numpy as np
 import oracle as O
 import rasterize_b200 as rb
 from rasterize_b200 import ffi
+from rasterize_b200.scene import fill_window
 
 
 def opath(p):
@@ -24,17 +25,14 @@ def render_scene_gpu(rast, sc, to_rgba=True):
         rast.device_zero(layer, W * H * 16)
     jobs, keep = [], []
     for f in sc.fills:
-        bx0, by0, bx1, by1 = f.bbox
-        col_min = max(0, min(math.floor(bx0) - lx, W))
-        col_max = max(col_min, min(math.ceil(bx1) - lx + 1, W))
-        row_min = max(0, min(math.floor(by0) - ly, H))
-        row_max = max(row_min, min(math.ceil(by1) - ly + 1, H))
+        bx0, by0 = f.bbox[0], f.bbox[1]
+        col_min, row_min, ww, wh = fill_window(f.bbox, lx, ly, W, H)  # the reference's window, incl. its `as usize` wrap
         align = rb.Transform.new_translate(-math.floor(bx0), -math.floor(by0))
         tr = align * rb.Transform.from_array(f.tr)
         dp = rast.upload(f.path)
         keep.append(dp)
-        jobs.append(rb.Job(dp, tr, f.fill_rule, ffi.JOB_FILL, layer, col_max - col_min, row_max - row_min, W,
-                           origin=row_min * W + col_min, paint=f.paint, path_bbox=f.path_bbox))
+        jobs.append(rb.Job(dp, tr, f.fill_rule, ffi.JOB_FILL, layer, ww, wh, W, origin=row_min * W + col_min, paint=f.paint,
+                           path_bbox=f.path_bbox))
     rast.render_batch(jobs, independent=False)
     lin = rast.to_host(layer, (H, W, 4), np.float32)
     rgba = None
@@ -56,15 +54,13 @@ def render_scene_oracle(sc):
     if sc.bg is not None:
         img[:] = sc.bg
     for f in sc.fills:
-        bx0, by0, bx1, by1 = f.bbox
-        col_min = max(0, min(math.floor(bx0) - lx, W))
-        col_max = max(col_min, min(math.ceil(bx1) - lx + 1, W))
-        row_min = max(0, min(math.floor(by0) - ly, H))
-        row_max = max(row_min, min(math.ceil(by1) - ly + 1, H))
+        bx0, by0 = f.bbox[0], f.bbox[1]
+        col_min, row_min, ww, wh = fill_window(f.bbox, lx, ly, W, H)
         align = O.translate(-math.floor(bx0), -math.floor(by0))
         tr = O.transform_mul(align, f.tr)
-        shape = O.Shape(row_min * W + col_min, col_max - col_min, row_max - row_min, W, 1)
-        opath(f.path).fill(tr, int(f.fill_rule), oracle_paint(f.paint_desc), img, shape=shape)
+        shape = O.Shape(row_min * W + col_min, ww, wh, W, 1)
+        if ww and wh:
+            opath(f.path).fill(tr, int(f.fill_rule), oracle_paint(f.paint_desc), img, shape=shape)
     return img
 
 
@@ -129,12 +125,9 @@ def render_pipeline_oracle(pl):
         n = nodes[node_id]
         lx, ly, W, H = geom
         if n.kind == 0:
-            col_min = max(0, min(math.floor(n.bbox[0]) - lx, W))
-            col_max = max(col_min, min(math.ceil(n.bbox[2]) - lx + 1, W))
-            row_min = max(0, min(math.floor(n.bbox[1]) - ly, H))
-            row_max = max(row_min, min(math.ceil(n.bbox[3]) - ly + 1, H))
+            col_min, row_min, ww, wh = fill_window(n.bbox, lx, ly, W, H)
             tr = O.transform_mul(O.translate(-math.floor(n.bbox[0]), -math.floor(n.bbox[1])), n.tr)
-            shape = O.Shape(row_min * W + col_min, col_max - col_min, row_max - row_min, W, 1)
+            shape = O.Shape(row_min * W + col_min, ww, wh, W, 1)
             if shape.width and shape.height:
                 opath(n.path).fill(tr, int(n.fill_rule), oracle_paint(n.paint_desc), img, shape=shape)
         elif n.kind == 1:

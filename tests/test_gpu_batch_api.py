@@ -1,0 +1,213 @@
+"""Batches of independent paths through the round-2 entry points (rgpu_path_upload_batch, rgpu_batch_*,
+rgpu_fill_batch_host, rgpu_mask_banded_host, rgpu_multi_*) and the rare paths of the fused small-canvas kernel, against
+the CPU oracle and against the single-call results.  Run: pytest -m gpu."""
+import numpy as np
+import pytest
+
+import oracle as O
+import rasterize_b200 as rb
+from rasterize_b200 import assets, ffi, synth
+
+pytestmark = pytest.mark.gpu
+COV_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def rast():
+    r = rb.GpuRasterizer()
+    yield r
+    r.close()
+
+
+def opath(p):
+    return O.OraclePath.from_flat(p.points, p.kinds, p.subpath_offsets, p.closed)
+
+
+def job_table(handles, canvas, mode, rule, n, w, h, paint_ptr=0):
+    t = np.zeros(n, dtype=rb.JOB_DTYPE)
+    t["path"] = handles
+    t["tr"] = np.array([1.0, 0, 0, 0, 1.0, 0])
+    t["fill_rule"] = int(rule)
+    t["mode"] = mode
+    t["paint"] = paint_ptr
+    t["canvas"] = canvas
+    t["origin"] = np.arange(n, dtype=np.uint64) * np.uint64(w * h)
+    t["row_stride"] = w
+    t["width"] = w
+    t["height"] = h
+    return t
+
+
+def test_upload_batch_and_prepared_batch_match_per_path_jobs(rast):
+    """One upload + a device-resident job table give the same bits as per-path uploads through rgpu_render_batch."""
+    n = 300
+    pb = synth.glyph_batch(1, n)
+    dpb = rast.upload_batch(pb)
+    slab = rast.device_alloc(n * 4096 * 4)
+    prepared = rast.prepare_job_table(job_table(dpb.handles(), slab, ffi.JOB_MASK, rb.FillRule.NonZero, n, 64, 64))
+    prepared.render()
+    rast.batch_status()
+    got = rast.to_host(slab, (n, 64, 64), np.float32)
+    lines = rast.last_counts()["lines"]
+    prepared.render()  # a second submission of the same handle
+    rast.batch_status()
+    assert np.array_equal(got, rast.to_host(slab, (n, 64, 64), np.float32))
+    dps = [rast.upload(pb.path(i)) for i in range(n)]
+    rast.device_zero(slab, n * 4096 * 4)
+    rast.render_batch([rb.Job(dps[i], rb.Transform.identity(), rb.FillRule.NonZero, ffi.JOB_MASK, slab, 64, 64, 64, origin=i * 4096)
+                       for i in range(n)], independent=True)
+    assert np.array_equal(got, rast.to_host(slab, (n, 64, 64), np.float32))
+    assert rast.last_counts()["lines"] == lines
+    for i in range(0, n, 13):
+        ref = np.zeros((64, 64))
+        opath(pb.path(i)).mask(O.IDENTITY, O.NONZERO, ref)
+        assert np.abs(got[i] - ref).max() <= COV_TOL, i
+    prepared.free()
+    rast.device_free(slab)
+
+
+@pytest.mark.parametrize("n", [1, 37, 5000])
+def test_fill_batch_host_lincolor_rgba_coverage(rast, n):
+    """rgpu_fill_batch_host (chunked, downloads overlapped): LinColor == per-glyph Path::fill of the oracle, RGBA8 ==
+    conversion of that image, coverage == dense mask_iter.  5000 glyphs span several chunks of the slab ring."""
+    pb = synth.glyph_batch(11, n)
+    black = rb.LinColor(0.0, 0.0, 0.0, 1.0)
+    lin = np.full((n, 64, 64, 4), 7.0, dtype=np.float32)
+    rast.fill_batch_host(pb, rb.FillRule.NonZero, black, 64, 64, lin)
+    rgba = np.zeros((n, 64, 64, 4), dtype=np.uint8)
+    rast.fill_batch_host(pb, rb.FillRule.NonZero, black, 64, 64, rgba)
+    cov = np.zeros((n, 64, 64), dtype=np.float32)
+    rast.fill_batch_host(pb, rb.FillRule.NonZero, None, 64, 64, cov)
+    paint = O.OraclePaint.solid([0, 0, 0, 1])
+    for i in sorted(set([0, n - 1] + list(range(0, n, max(1, n // 23))))):
+        g = opath(pb.path(i))
+        ref = np.zeros((64, 64, 4), dtype=np.float32)
+        g.fill(O.IDENTITY, O.NONZERO, paint, ref)
+        assert np.abs(lin[i] - ref).max() <= 2e-4, i
+        assert np.abs(rgba[i].astype(int) - O.lin_to_rgba(lin[i]).astype(int)).max() == 0, i
+        assert np.abs(cov[i] - lin[i][:, :, 3]).max() == 0.0, i
+    # every image of the batch was written (no stale 7.0 left) and identical glyph data gives identical bits per call
+    assert lin.max() <= 1.0 + 1e-6
+    lin2 = np.empty_like(lin)
+    rast.fill_batch_host(pb, rb.FillRule.NonZero, black, 64, 64, lin2)
+    assert np.array_equal(lin, lin2)
+
+
+def test_fill_batch_host_transforms_gradient_and_large_canvas(rast):
+    """Per-path transforms, a gradient paint, even-odd, and canvases beyond the fused kernel (tiled path, 200 x 150)."""
+    n = 9
+    pb = synth.glyph_batch(3, n)
+    trs = np.array([[1.5 + 0.1 * i, 0.2, 3.0 * i, -0.1, 2.0, 5.0] for i in range(n)])
+    stops = [(0.0, [1.0, 0.0, 0.0, 1.0]), (1.0, [0.0, 0.0, 0.5, 0.5])]
+    grad = rb.GradLinear(stops, rb.Units.UserSpaceOnUse, True, rb.GradSpread.Reflect, rb.Transform.identity(), (0, 0), (40, 30))
+    out = np.zeros((n, 150, 200, 4), dtype=np.float32)
+    rast.fill_batch_host(pb, rb.FillRule.EvenOdd, grad, 200, 150, out, trs=trs)
+    og = O.OraclePaint.linear(stops, (0, 0), (40, 30), units=0, linear_colors=True, spread=2)
+    for i in range(n):
+        ref = np.zeros((150, 200, 4), dtype=np.float32)
+        opath(pb.path(i)).fill(trs[i], O.EVENODD, og, ref)
+        assert np.abs(out[i] - ref).max() <= 3e-4, i
+
+
+def test_small_canvas_rare_paths(rast):
+    """The fused kernel's f64 / deep / overflow paths: glyphs scaled far beyond the canvas (curves leave the columns and
+    subdivide 8+ levels), shifted off every edge, quads, open subpaths, line-only paths, tiny canvases."""
+    pb = synth.glyph_batch(101, 12)
+    cases = []
+    for i in range(12):
+        p = pb.path(i)
+        cases.append((p, [9.0, 0, -200.0 - 10 * i, 0, 9.0, -150.0], 64, 64))      # deep curves, mostly outside
+        cases.append((p, [1.0, 0, -30.0, 0, 1.0, 17.5], 64, 64))                  # crosses x < 0 and the bottom
+        cases.append((p, [1.0, 0, 25.0, 0, 1.0, -40.25], 64, 64))                 # crosses x > width and the top
+        cases.append((p, [0.45, 0, 1.0, 0, 0.3, 2.0], 33, 21))                    # odd small canvas
+        cases.append((p, [40.0, 0, -900.0, 0, 40.0, -1200.0], 64, 64))            # a few huge pieces, far coordinates
+    b = rb.Path.builder()
+    b.move_to((5, 5)).quad_to((60, 0), (58, 40)).quad_to((30, 70), (8, 50)).line_to((2, 30))   # open: closed by the rasterizer
+    b.move_to((20, 20)).line_to((40, 22)).line_to((38, 44)).line_to((18, 40)).close()
+    quads = b.build()
+    cases += [(quads, [1.0, 0, 0, 0, 1.0, 0], 64, 64), (quads, [3.0, 0, -50.0, 0, 3.0, -40.0], 64, 64), (quads, [1.0, 0, 0, 0, 1.0, 0], 17, 64)]
+    for rule, orule in ((rb.FillRule.NonZero, O.NONZERO), (rb.FillRule.EvenOdd, O.EVENODD)):
+        dps = [rast.upload(c[0]) for c in cases]
+        slab = rast.device_alloc(len(cases) * 4096 * 4)
+        rast.device_zero(slab, len(cases) * 4096 * 4)
+        jobs = [rb.Job(dps[k], c[1], rule, ffi.JOB_MASK, slab, c[2], c[3], c[2], origin=k * 4096) for k, c in enumerate(cases)]
+        rast.render_batch(jobs, independent=True)
+        got = rast.to_host(slab, (len(cases), 4096), np.float32)
+        lines = 0
+        for k, (p, tr, w, h) in enumerate(cases):
+            ref = np.zeros((h, w))
+            og = opath(p)
+            og.mask(np.array(tr), orule, ref)
+            lines += len(og.flatten(np.array(tr)))
+            err = np.abs(got[k][: w * h].reshape(h, w) - ref).max()
+            assert err <= COV_TOL, (k, tr, w, h, err)
+        assert rast.last_counts()["lines"] == lines
+        rast.device_free(slab)
+
+
+def test_small_canvas_errors(rast):
+    """NaN control points and unbounded subdivision are reported by the fused kernel like by the tiled path."""
+    b = rb.Path.builder()
+    b.move_to((1, 1)).cubic_to((float("nan"), 3), (5, 6), (7, 8)).close()
+    img = np.zeros((32, 32), dtype=np.float32)
+    with pytest.raises(rb.RgpuError) as e:
+        rast.mask(b.build(), rb.Transform.identity(), img, rb.FillRule.NonZero)
+    assert e.value.code == ffi.ERR_NAN
+    b = rb.Path.builder()
+    b.move_to((1, 1)).cubic_to((1e40, 3), (-1e40, 6), (7, 8)).close()
+    with pytest.raises(rb.RgpuError) as e:
+        rast.mask(b.build(), rb.Transform.identity(), img, rb.FillRule.NonZero)
+    assert e.value.code == ffi.ERR_DEPTH
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_mask_banded_is_bit_identical_to_single_mask(rast, dtype):
+    """rgpu_mask_banded_host: any band decomposition stitches to the bits of the unsharded mask (rows are independent,
+    reference src/rasterize.rs:421-469), for the stroked tv outline of config 5 at 4096 x 4096 and material at 1500 x 1100."""
+    ex = assets.expected()["paths"]
+    for name, (w, h) in (("tv_stroked", (4096, 4096)), ("material", (1500, 1100))):
+        p = assets.load_path(name)
+        c = ex[name]["c5" if name == "tv_stroked" else "c2"]
+        tr = np.array(c["tr"]) * np.array([w / c["size"][0]] * 3 + [h / c["size"][1]] * 3)
+        whole = np.zeros((h, w), dtype=dtype)
+        rast.mask(p, tr, whole, rb.FillRule.NonZero)
+        for n_bands in (1, 5, 64):
+            img = np.full((h, w), -3.0, dtype=dtype)
+            rast.mask_banded(p, tr, img, rb.FillRule.NonZero, n_bands=n_bands)
+            assert np.array_equal(img, whole), (name, n_bands)
+        # two "devices" dealing 16 bands round-robin into one image
+        img = np.full((h, w), -3.0, dtype=dtype)
+        rast.mask_banded(p, tr, img, rb.FillRule.NonZero, n_bands=16, band_first=0, band_step=2)
+        assert (img == -3.0).any()
+        rast.mask_banded(p, tr, img, rb.FillRule.NonZero, n_bands=16, band_first=1, band_step=2)
+        assert np.array_equal(img, whole), name
+
+
+def test_multi_gpu_matches_single_gpu():
+    """rgpu_multi_*: shards by path / by scanline band over every device of the box (also exercised with one device, and
+    with the same device listed twice when only one exists: two contexts, two host threads, disjoint output regions)."""
+    n_dev = ffi.lib().rgpu_device_count()
+    devices = list(range(n_dev)) if n_dev > 1 else [0, 0]
+    single = rb.GpuRasterizer()
+    multi = rb.MultiGpuRasterizer(devices)
+    try:
+        n = 1000
+        pb = synth.glyph_batch(5, n)
+        black = rb.LinColor(0.0, 0.0, 0.0, 1.0)
+        a = np.zeros((n, 64, 64, 4), dtype=np.float32)
+        b = np.ones((n, 64, 64, 4), dtype=np.float32)
+        single.fill_batch_host(pb, rb.FillRule.NonZero, black, 64, 64, a)
+        multi.fill_batch_host(pb, rb.FillRule.NonZero, black, 64, 64, b)
+        assert np.array_equal(a, b)
+        p = assets.load_path("tv_stroked")
+        c = assets.expected()["paths"]["tv_stroked"]["c5"]
+        w = h = 8192
+        tr = np.array(c["tr"]) * (w / c["size"][0])
+        whole = np.zeros((h, w), dtype=np.float32)
+        single.mask(p, tr, whole, rb.FillRule.NonZero)
+        img = np.full((h, w), -1.0, dtype=np.float32)
+        multi.mask_banded(p, tr, img, rb.FillRule.NonZero)
+        assert np.array_equal(img, whole)
+    finally:
+        multi.close()
+        single.close()

@@ -18,21 +18,12 @@ workload = sys.argv[1] if len(sys.argv) > 1 else "c2"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 torch.cuda.set_device(0)
 rast = rb.GpuRasterizer(device=0)
-jobs, independent, info = bench.build_workload(workload, rb, rast, 0, 1, torch)
-prepared = rast.prepare_batch(jobs)
+step_fn, info = bench.build_workload(workload, rb, rast, 0, 1, torch)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-scn = info.get("scene")
 
 
 def step():
-    if scn:  # c1 / c3: the scene compositor
-        rast.submit_scene_prepared(prepared, scn["layer"], scn["W"], scn["H"], fresh=True, bg=scn["bg"], rgba_ptr=scn["rgba"], sync=True)
-        return
-    if info.get("pre_step"):
-        info["pre_step"]()
-    rast.submit_prepared(prepared, independent=independent, sync=True)
-    if info.get("post_step"):
-        info["post_step"]()
+    step_fn(sync=True)
 
 
 step()
