@@ -233,8 +233,14 @@ def build_workload(name: str, rb, rast, rank: int, world: int, torch):
         mine = [b for b in range(bands) if b % world == rank]
         dp = rast.upload(path)
         jobs, canvases, rows = [], [], 0
+        runs = []  # consecutive bands of this rank are one job (flattened once): at N = 1 the whole canvas
         for b in mine:
             y0, y1 = sharding.band_rows(hfull, b, bands)
+            if runs and runs[-1][1] == y0:
+                runs[-1][1] = y1
+            elif y1 > y0:
+                runs.append([y0, y1])
+        for y0, y1 in runs:
             canvas = torch.empty((y1 - y0, w), dtype=torch.float32, device=dev)
             canvases.append(canvas)
             rows += y1 - y0

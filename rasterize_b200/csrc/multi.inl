@@ -353,7 +353,9 @@ int rgpu_mask_banded_host(rgpu_ctx* ctx, const rgpu_path* path, const double tr[
     for (uint32_t b = band_first; b < n_bands; b += band_step) {
         const size_t y0 = cut(b), y1 = std::max(cut(b), cut(b + 1));
         if (y1 > y0) {
-            bands.push_back({y0, y1 - y0, rows_total});
+            // consecutive bands of this context are one job (flattened once): with band_step == 1 the whole canvas
+            if (!bands.empty() && bands.back().y0 + bands.back().rows == y0) bands.back().rows += y1 - y0;
+            else bands.push_back({y0, y1 - y0, rows_total});
             rows_total += y1 - y0;
         }
     }

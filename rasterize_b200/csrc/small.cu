@@ -157,6 +157,12 @@ __device__ __forceinline__ double nd_endx(const Nd& n, int kind) { return kind =
 __device__ __forceinline__ double nd_endy(const Nd& n, int kind) { return kind == 4 ? n.y3 : n.y2; }
 
 __device__ __forceinline__ int fix_f(float v) { return __float2int_rn(v * 16777216.0f); }
+// 1 / x for x in (1e-20, 1e3): the bare MUFU.RCP (1 ulp), without the range fix-up of __fdividef
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 // ---- shared memory of a CTA (file scope, so that the out-of-line helpers address it as shared memory) ------------
 __shared__ __align__(16) int s_cells[kSmMaxH * kSmPitch];
@@ -212,7 +218,7 @@ __device__ __forceinline__ Span span_head(const float4 p, const int y, const Can
 // one column (src/rasterize.rs:437-444) or two (:445-459), without a branch between them
 __device__ __forceinline__ void span_narrow(const Span& s, const Canvas& cv) {
     const float fx0 = (float)s.x0i;
-    const float sf = __fdividef(1.0f, fmaxf(s.xb - s.xa, 1e-20f));
+    const float sf = rcp_fast(fmaxf(s.xb - s.xa, 1e-20f));
     const float x1f = s.xb - (float)s.x1i + 1.0f;
     const float c_narrow = 1.0f - (0.5f * (s.xt + s.xn) - fx0);
     const float u = 1.0f - (s.xa - fx0);
@@ -227,7 +233,7 @@ __device__ __forceinline__ void span_narrow(const Span& s, const Canvas& cv) {
 // three or more columns (src/rasterize.rs:445-468)
 __device__ __forceinline__ void span_wide(const Span& s) {
     const float x0f = s.xa - (float)s.x0i;
-    const float sf = __fdividef(1.0f, s.xb - s.xa);
+    const float sf = rcp_fast(s.xb - s.xa);
     const float x1f = s.xb - (float)s.x1i + 1.0f;
     const float c0 = 0.5f * sf * (1.0f - x0f) * (1.0f - x0f);
     const float cl = 1.0f - 0.5f * sf * x1f * x1f;
@@ -549,8 +555,13 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
         }
         __syncthreads();
 
-        // one round: thread = (curve, slot)
-        const uint32_t ci = (uint32_t)tid >> kGDepth, slot = (uint32_t)tid & (kGSlots - 1);
+        // one round: thread = (curve, slot).  The chunk's slots are dealt out evenly over the warps (a glyph's 18 curves are
+        // 144 slots: 29 per warp instead of 32, 32, 32, 32, 16), so that the warps reach the barrier before the row scan together
+        const uint32_t n_slots = cn << kGDepth;
+        const uint32_t per_warp = (n_slots + kGWarps - 1) / kGWarps;
+        const uint32_t sidx = (uint32_t)warp * per_warp + (uint32_t)lane;
+        const bool has_slot = (uint32_t)lane < per_warp && sidx < n_slots;
+        const uint32_t ci = has_slot ? (sidx >> kGDepth) : cn, slot = sidx & (kGSlots - 1);
         bool act = false, leaf = false, slow = false;
         int kind = 4;
         Nd nd;
@@ -818,8 +829,8 @@ void launch_small_canvas(const JobDev* jobs, uint32_t job_first, uint32_t n_jobs
         launch_small_canvas_v1(jobs, job_first, n_jobs, paints, thr, status, s);
         return;
     }
-    // CTAs per SM (register budget): 4 -> 96, 5 -> 80
-    static const int minb = getenv("RGPU_SMALL_MINB") ? atoi(getenv("RGPU_SMALL_MINB")) : 5;
+    // CTAs per SM (register budget): 4 -> 96 registers, 5 -> 72 with spills in the walk (measured: 0.94 vs 1.02 ms per 20 000 glyphs)
+    static const int minb = getenv("RGPU_SMALL_MINB") ? atoi(getenv("RGPU_SMALL_MINB")) : 4;
     if (gradients) {
         small_canvas_kernel<4, false><<<n_jobs, kGThreads, 0, s>>>(jobs, job_first, paints, thr, status);
     } else if (minb <= 4) {
