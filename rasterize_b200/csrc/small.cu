@@ -32,6 +32,7 @@
 #include "flatten_device.cuh"
 #include "raster_device.cuh"
 
+#include <algorithm>
 #include <type_traits>
 
 namespace rgpu {
@@ -164,21 +165,37 @@ __device__ __forceinline__ float rcp_fast(float x) {
     return r;
 }
 
-// ---- shared memory of a CTA (file scope, so that the out-of-line helpers address it as shared memory) ------------
-__shared__ __align__(16) int s_cells[kSmMaxH * kSmPitch];
-// phase 1: per-warp line queues; phase 2: a gradient paint's table
-__shared__ __align__(16) float4 s_lineq[kGWarps][kGQueue];
-__shared__ __align__(16) double s_dq[kGWarps][kGDeep * 8];
-__shared__ __align__(16) double s_x[kGCurves][4];
-__shared__ __align__(16) double s_y[kGCurves][4];
-__shared__ unsigned short s_ids[kGWarps][kGIds];
-__shared__ unsigned short s_wide[kGWarps][kGWide];
-__shared__ unsigned char s_dkind[kGWarps][kGDeep];
-__shared__ unsigned char s_meta[kGCurves];  // kind | 8 = f64 path (control points not finite, outside the canvas columns or far from its rows)
-__shared__ int s_rowtot[kSmMaxH], s_row_touched[kSmMaxH];  // written by the f64 path only (the tiled kernels' carry state; unused here)
-__shared__ JobDev s_job;
-__shared__ uint32_t s_nlines;
-static_assert(sizeof(PaintDev) <= sizeof(s_lineq), "paint overlay");
+// ---- shared memory of a CTA: one dynamic block, addressed through these views so that the out-of-line helpers see
+// shared-memory addresses ---------------------------------------------------------------------------------
+constexpr int kCells = kSmMaxH * kSmPitch;
+constexpr size_t kOffCells = 0;
+constexpr size_t kOffLineq = kOffCells + sizeof(int) * kCells;          // per-warp line queues (phase 2 of the one-glyph kernel: a gradient's table)
+constexpr size_t kOffDq = kOffLineq + sizeof(float4) * kGWarps * kGQueue;   // per-warp deep-node queues
+constexpr size_t kOffRoots = kOffDq + sizeof(double) * kGWarps * kGDeep * 8;  // transformed control points: [20][4] x, then y
+constexpr size_t kOffIds = kOffRoots + sizeof(double) * kGCurves * 4 * 2;
+constexpr size_t kOffWide = kOffIds + sizeof(unsigned short) * kGWarps * kGIds;
+constexpr size_t kOffDkind = kOffWide + sizeof(unsigned short) * kGWarps * kGWide;
+constexpr size_t kOffMeta = kOffDkind + 16 * ((kGWarps * kGDeep + 15) / 16);
+constexpr size_t kOffRowtot = kOffMeta + 48;
+constexpr size_t kOffJob = kOffRowtot + sizeof(int) * 2 * kSmMaxH;
+constexpr size_t kJobPitch = (sizeof(JobDev) + 15) / 16 * 16;
+constexpr size_t kOffBars = kOffJob + kJobPitch;
+constexpr size_t kSmemBytes = kOffBars + 64;
+static_assert(sizeof(PaintDev) <= sizeof(float4) * kGWarps * kGQueue, "paint overlay");
+extern __shared__ __align__(16) unsigned char sm_raw[];
+#define s_cells (reinterpret_cast<int*>(sm_raw + kOffCells))
+#define s_lineq (reinterpret_cast<float4(*)[kGQueue]>(sm_raw + kOffLineq))
+#define s_dq (reinterpret_cast<double(*)[kGDeep * 8]>(sm_raw + kOffDq))
+#define s_x (reinterpret_cast<double(*)[4]>(sm_raw + kOffRoots))
+#define s_y (reinterpret_cast<double(*)[4]>(sm_raw + kOffRoots + sizeof(double) * kGCurves * 4))
+#define s_ids (reinterpret_cast<unsigned short(*)[kGIds]>(sm_raw + kOffIds))
+#define s_wide (reinterpret_cast<unsigned short(*)[kGWide]>(sm_raw + kOffWide))
+#define s_dkind (reinterpret_cast<unsigned char(*)[kGDeep]>(sm_raw + kOffDkind))
+#define s_meta (reinterpret_cast<unsigned char*>(sm_raw + kOffMeta))
+#define s_rowtot (reinterpret_cast<int*>(sm_raw + kOffRowtot))
+#define s_row_touched (reinterpret_cast<int*>(sm_raw + kOffRowtot) + kSmMaxH)
+#define s_job (*reinterpret_cast<JobDev*>(sm_raw + kOffJob))
+#define s_nlines (*reinterpret_cast<uint32_t*>(sm_raw + kOffBars + 32))
 
 // Per-job constants of the accumulation
 struct Canvas {
@@ -484,96 +501,28 @@ __device__ __forceinline__ void deep_site(bool pred, const Nd& n, int kind, Warp
     w.dn += __popc(m);
 }
 
-// PLAIN: no gradient paint in the batch (masks, coverage, solid fills) — the paint evaluation is compiled out
-template <int MINB, bool PLAIN>
-__global__ void __launch_bounds__(kGThreads, MINB)
-small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const PaintDev* __restrict__ paints, double thr,
-                    Status* __restrict__ status) {
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    {
-        const int* src = reinterpret_cast<const int*>(&jobs[job_first + blockIdx.x]);
-        int* dst = reinterpret_cast<int*>(&s_job);
-        if (tid < (int)(sizeof(JobDev) / 4)) dst[tid] = src[tid];
-        const int4 z = make_int4(0, 0, 0, 0);
-        int4* c4 = reinterpret_cast<int4*>(s_cells);
-        for (int i = tid; i < kSmMaxH * kSmPitch / 4; i += kGThreads) c4[i] = z;
-        if (tid == 0) s_nlines = 0;
-    }
-    __syncthreads();
-    const JobDev& job = s_job;
-    Canvas cv;
-    cv.H = job.height;
-    cv.wc = job.clamp_w;
-    cv.wci = (int)cv.wc;
-    cv.wcf = (float)cv.wc;
-    cv.tile_end = min(kSmPitch, cv.wci + 1);  // reference columns incl. the overflow column
-    Warp w;
-    w.qn = 0;
-    w.dn = 0;
-    w.lines = 0;
-    w.lt_mask = (1u << lane) - 1u;
-    w.warp = warp;
-    auto drain_deep_keep = [&](int keep) {
-        uint32_t add = 0;
-        w.qn = drain_deep(w.qn, w.dn, keep, &add, thr, cv, status);
-        w.dn = deep_left(w.dn, keep);
-        w.lines += add;
-    };
+__device__ __forceinline__ void drain_deep_keep(Warp& w, int keep, const double thr, const Canvas& cv, Status* __restrict__ status) {
+    uint32_t add = 0;
+    w.qn = drain_deep(w.qn, w.dn, keep, &add, thr, cv, status);
+    w.dn = deep_left(w.dn, keep);
+    w.lines += add;
+}
 
-    const uint32_t n_items = job.n_items, n_curves = job.n_curves;
-    // ---- curves (first in the packed order): chunks of 20, 8 slot threads each --------------------------------
-    for (uint32_t c0 = 0; c0 < n_curves; c0 += kGCurves) {
-        const uint32_t cn = min((uint32_t)kGCurves, n_curves - c0);
-        if (c0) __syncthreads();  // the previous chunk's slots are done with s_x / s_y
-        if (tid < kGCurves * 4) {
-            // stage: thread = (curve, point); Transform::apply once per control point
-            const uint32_t i = (uint32_t)tid >> 2, j = (uint32_t)tid & 3u;
-            bool slow = false;
-            int kind = 0;
-            if (i < cn) {
-                const uint2 it = job.items_packed[c0 + i];
-                kind = (int)it.y;
-                if (j < (uint32_t)kind) {
-                    const P2 p = tr_apply(job.tr, job.pts[it.x + j]);
-                    s_x[i][j] = p.x;
-                    s_y[i][j] = p.y;
-                    slow = !point_safe(p.x, p.y, cv);  // also true for NaN / infinite coordinates
-                } else {
-                    s_x[i][j] = 0.0;
-                    s_y[i][j] = 0.0;
-                }
-            }
-            // kGCurves * 4 = 80 threads: warps 0, 1 and the lower half of warp 2 — the four lanes of a curve are in one warp.
-            // (no short-circuit around the shuffles: every lane of the group must execute them)
-            const unsigned grp = __activemask();
-            const bool s1 = __shfl_xor_sync(grp, slow, 1);
-            slow = slow | s1;
-            const bool s2 = __shfl_xor_sync(grp, slow, 2);
-            slow = slow | s2;
-            if (i < cn && j == 0) s_meta[i] = (unsigned char)(kind | (slow ? 8 : 0));
-        }
-        __syncthreads();
-
-        // one round: thread = (curve, slot).  The chunk's slots are dealt out evenly over the warps (a glyph's 18 curves are
-        // 144 slots: 29 per warp instead of 32, 32, 32, 32, 16), so that the warps reach the barrier before the row scan together
-        const uint32_t n_slots = cn << kGDepth;
-        const uint32_t per_warp = (n_slots + kGWarps - 1) / kGWarps;
-        const uint32_t sidx = (uint32_t)warp * per_warp + (uint32_t)lane;
-        const bool has_slot = (uint32_t)lane < per_warp && sidx < n_slots;
-        const uint32_t ci = has_slot ? (sidx >> kGDepth) : cn, slot = sidx & (kGSlots - 1);
+// One round of a warp: lane = (curve, slot).  `has`: this lane owns a slot; (rx, ry): the curve's transformed control
+// points in shared memory (4 doubles each); meta = kind | 8 (f64 path).  Warp-collective.
+__device__ __forceinline__ void walk_slot(const bool has, const double* rx, const double* ry, const int meta, const uint32_t slot, Warp& w,
+                                          const Canvas& cv, const double thr, Status* __restrict__ status) {
         bool act = false, leaf = false, slow = false;
         int kind = 4;
         Nd nd;
         nd.x0 = nd.x1 = nd.x2 = nd.x3 = nd.y0 = nd.y1 = nd.y2 = nd.y3 = 0.0;
-        if (ci < cn) {
-            const int meta = s_meta[ci];
+        if (has) {
             kind = meta & 7;
             slow = (meta & 8) != 0;
-            const double2 xa = *reinterpret_cast<const double2*>(&s_x[ci][0]);
-            const double2 xb = *reinterpret_cast<const double2*>(&s_x[ci][2]);
-            const double2 ya = *reinterpret_cast<const double2*>(&s_y[ci][0]);
-            const double2 yb = *reinterpret_cast<const double2*>(&s_y[ci][2]);
+            const double2 xa = *reinterpret_cast<const double2*>(rx);
+            const double2 xb = *reinterpret_cast<const double2*>(rx + 2);
+            const double2 ya = *reinterpret_cast<const double2*>(ry);
+            const double2 yb = *reinterpret_cast<const double2*>(ry + 2);
             nd.x0 = xa.x; nd.x1 = xa.y; nd.x2 = xb.x; nd.x3 = xb.y;
             nd.y0 = ya.x; nd.y1 = ya.y; nd.y2 = yb.x; nd.y3 = yb.y;
             act = true;
@@ -618,11 +567,11 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
             };
             level1(nd_half<false>(nd, kind), std::integral_constant<int, 0>{});
             // drain point: only the slot root is live
-            if (w.dn >= 16) drain_deep_keep(15);
+            if (w.dn >= 16) drain_deep_keep(w, 15, thr, cv, status);
             ensure_room(w, 64, cv);
             level1(nd_half<true>(nd, kind), std::integral_constant<int, 1>{});
         }
-        if (w.dn >= 16) drain_deep_keep(15);
+        if (w.dn >= 16) drain_deep_keep(w, 15, thr, cv, status);
         // the round's lines in one pass
         if (w.qn) {
             __syncwarp();
@@ -649,9 +598,10 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
             }
         }
     }
-    // ---- lines and closing lines: one thread each, straight from the path -------------------------------------
-    for (uint32_t i0 = n_curves; i0 < n_items; i0 += kGThreads) {
-        const uint32_t i = i0 + tid;
+
+// One line / closing item per lane (items beyond the curves in the packed order).  Warp-collective.
+__device__ __forceinline__ void emit_line_item(const uint32_t i, const uint32_t n_items, const JobDev& job, Warp& w, const Canvas& cv,
+                                               Status* __restrict__ status) {
         bool pred = false;
         double x0 = 0.0, y0 = 0.0, x1 = 0.0, y1 = 0.0;
         if (i < n_items) {
@@ -685,31 +635,21 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
         }
         ensure_room(w, 32, cv);
         emit_site(pred, x0, y0, x1, y1, w);
-    }
-    if (w.dn) drain_deep_keep(0);
-    if (w.qn) {
-        __syncwarp();
-        accumulate_warp(w.qn, cv);
-        w.qn = 0;
-    }
-    {
-        uint32_t v = w.lines;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-        if (lane == 0 && v) atomicAdd(&s_nlines, v);
-    }
-    __syncthreads();
-    if (tid == 0 && s_nlines) atomicAdd(&status->n_lines, s_nlines);  // statistics only
+}
 
+// K3 phase 2 + K4 for the rows of NWARPS warps (warp = 0 .. NWARPS - 1, tid = thread index among them): row scan, fill
+// rule, composite, store.  `cells`: the canvas' cell buffer; `paint_buf`: shared memory for a gradient paint's table.
+template <bool PLAIN, int NWARPS>
+__device__ __forceinline__ void finish_rows(const JobDev& job, const PaintDev* __restrict__ paints, int* const cells, void* paint_buf, const int warp,
+                                            const int lane, const int tid) {
     // ---- K3 phase 2 + K4: two rows per warp iteration (16 lanes x 4 columns each) ----------------------------
-    int* const cells = s_cells;
     const int mode = job.mode;
     const bool render = mode == kModeRender;  // fill onto a canvas created here: every pixel is written, none is read
     const int wout = job.width_out, hout = job.height;
     const int half = lane >> 4, hl = lane & 15;
     const bool evenodd = job.rule == 1;
     const bool has_paint = mode >= kModeFill && job.paint_index >= 0;
-    const PaintDev& s_paint = *reinterpret_cast<const PaintDev*>(&s_lineq[0][0]);
+    const PaintDev& s_paint = *reinterpret_cast<const PaintDev*>(paint_buf);
     bool solid = true;
     float4 solid_c = make_float4(0.f, 0.f, 0.f, 0.f);
     if (has_paint) {
@@ -719,9 +659,9 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
             solid_c = *reinterpret_cast<const float4*>(gp->solid);
         } else {  // gradient: its table replaces the line queues
             const int* src = reinterpret_cast<const int*>(gp);
-            int* dst = reinterpret_cast<int*>(&s_lineq[0][0]);
-            for (int i = tid; i < (int)(sizeof(PaintDev) / 4); i += kGThreads) dst[i] = src[i];
-            __syncthreads();
+            int* dst = reinterpret_cast<int*>(paint_buf);
+            for (int i = tid; i < (int)(sizeof(PaintDev) / 4); i += NWARPS * 32) dst[i] = src[i];
+            if (NWARPS == 1) __syncwarp(); else __syncthreads();
         }
     }
     // RENDER with a solid colour whose components are finite and not negative (the glyph batch): the composite
@@ -732,7 +672,7 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
                        solid_c.y < 3e38f && solid_c.z < 3e38f && solid_c.w < 3e38f;
     float4* const out_base = reinterpret_cast<float4*>(job.canvas) + job.origin;
     const unsigned long long row_stride = job.row_stride;
-    for (int r2 = warp * 2; r2 < hout; r2 += kGWarps * 2) {
+    for (int r2 = warp * 2; r2 < hout; r2 += NWARPS * 2) {
         const int r = r2 + half;
         const bool rvalid = r < hout;
         int* rowc = cells + (rvalid ? r : 0) * kSmPitch;
@@ -813,6 +753,103 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
     }
 }
 
+// PLAIN: no gradient paint in the batch (masks, coverage, solid fills) — the paint evaluation is compiled out
+template <int MINB, bool PLAIN>
+__global__ void __launch_bounds__(kGThreads, MINB)
+small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const PaintDev* __restrict__ paints, double thr,
+                    Status* __restrict__ status) {
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    {
+        const int* src = reinterpret_cast<const int*>(&jobs[job_first + blockIdx.x]);
+        int* dst = reinterpret_cast<int*>(&s_job);
+        if (tid < (int)(sizeof(JobDev) / 4)) dst[tid] = src[tid];
+        const int4 z = make_int4(0, 0, 0, 0);
+        int4* c4 = reinterpret_cast<int4*>(s_cells);
+        for (int i = tid; i < kCells / 4; i += kGThreads) c4[i] = z;
+        if (tid == 0) s_nlines = 0;
+    }
+    __syncthreads();
+    const JobDev& job = s_job;
+    Canvas cv;
+    cv.H = job.height;
+    cv.wc = job.clamp_w;
+    cv.wci = (int)cv.wc;
+    cv.wcf = (float)cv.wc;
+    cv.tile_end = min(kSmPitch, cv.wci + 1);  // reference columns incl. the overflow column
+    Warp w;
+    w.qn = 0;
+    w.dn = 0;
+    w.lines = 0;
+    w.lt_mask = (1u << lane) - 1u;
+    w.warp = warp;
+    const uint32_t n_items = job.n_items, n_curves = job.n_curves;
+    // ---- curves (first in the packed order): chunks of 20, 8 slot threads each --------------------------------
+    for (uint32_t c0 = 0; c0 < n_curves; c0 += kGCurves) {
+        const uint32_t cn = min((uint32_t)kGCurves, n_curves - c0);
+        if (c0) __syncthreads();  // the previous chunk's slots are done with s_x / s_y
+        if (tid < kGCurves * 4) {
+            // stage: thread = (curve, point); Transform::apply once per control point
+            const uint32_t i = (uint32_t)tid >> 2, j = (uint32_t)tid & 3u;
+            bool slow = false;
+            int kind = 0;
+            if (i < cn) {
+                const uint2 it = job.items_packed[c0 + i];
+                kind = (int)it.y;
+                if (j < (uint32_t)kind) {
+                    const P2 p = tr_apply(job.tr, job.pts[it.x + j]);
+                    s_x[i][j] = p.x;
+                    s_y[i][j] = p.y;
+                    slow = !point_safe(p.x, p.y, cv);  // also true for NaN / infinite coordinates
+                } else {
+                    s_x[i][j] = 0.0;
+                    s_y[i][j] = 0.0;
+                }
+            }
+            // kGCurves * 4 = 80 threads: warps 0, 1 and the lower half of warp 2 — the four lanes of a curve are in one warp.
+            // (no short-circuit around the shuffles: every lane of the group must execute them)
+            const unsigned grp = __activemask();
+            const bool s1 = __shfl_xor_sync(grp, slow, 1);
+            slow = slow | s1;
+            const bool s2 = __shfl_xor_sync(grp, slow, 2);
+            slow = slow | s2;
+            if (i < cn && j == 0) s_meta[i] = (unsigned char)(kind | (slow ? 8 : 0));
+        }
+        __syncthreads();
+
+        // one round: thread = (curve, slot).  The chunk's slots are dealt out evenly over the warps (a glyph's 18 curves are
+        // 144 slots: 29 per warp instead of 32, 32, 32, 32, 16), so that the warps reach the barrier before the row scan together
+        const uint32_t n_slots = cn << kGDepth;
+        const uint32_t per_warp = (n_slots + kGWarps - 1) / kGWarps;
+        const uint32_t sidx = (uint32_t)warp * per_warp + (uint32_t)lane;
+        const bool has_slot = (uint32_t)lane < per_warp && sidx < n_slots;
+        const uint32_t ci = has_slot ? (sidx >> kGDepth) : cn, slot = sidx & (kGSlots - 1);
+        walk_slot(ci < cn, &s_x[min(ci, (uint32_t)kGCurves - 1)][0], &s_y[min(ci, (uint32_t)kGCurves - 1)][0], ci < cn ? s_meta[ci] : 0, slot, w, cv, thr, status);
+    }
+    // ---- lines and closing lines: one thread each, straight from the path -------------------------------------
+    for (uint32_t i0 = n_curves; i0 < n_items; i0 += kGThreads) {
+        const uint32_t i = i0 + tid;
+        emit_line_item(i, n_items, job, w, cv, status);
+    }
+    if (w.dn) drain_deep_keep(w, 0, thr, cv, status);
+    if (w.qn) {
+        __syncwarp();
+        accumulate_warp(w.qn, cv);
+        w.qn = 0;
+    }
+    {
+        uint32_t v = w.lines;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        if (lane == 0 && v) atomicAdd(&s_nlines, v);
+    }
+    __syncthreads();
+    if (tid == 0 && s_nlines) atomicAdd(&status->n_lines, s_nlines);  // statistics only
+
+    finish_rows<PLAIN, kGWarps>(job, paints, s_cells, &s_lineq[0][0], warp, lane, tid);
+}
+
+
 }  // namespace
 
 bool small_canvas_eligible(uint32_t width, uint32_t height, int mode) {
@@ -831,12 +868,21 @@ void launch_small_canvas(const JobDev* jobs, uint32_t job_first, uint32_t n_jobs
     }
     // CTAs per SM (register budget): 4 -> 96 registers, 5 -> 72 with spills in the walk (measured: 0.94 vs 1.02 ms per 20 000 glyphs)
     static const int minb = getenv("RGPU_SMALL_MINB") ? atoi(getenv("RGPU_SMALL_MINB")) : 4;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaFuncSetAttribute(small_canvas_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        cudaFuncSetAttribute(small_canvas_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        cudaFuncSetAttribute(small_canvas_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        configured[dev] = true;
+    }
     if (gradients) {
-        small_canvas_kernel<4, false><<<n_jobs, kGThreads, 0, s>>>(jobs, job_first, paints, thr, status);
+        small_canvas_kernel<4, false><<<n_jobs, kGThreads, kSmemBytes, s>>>(jobs, job_first, paints, thr, status);
     } else if (minb <= 4) {
-        small_canvas_kernel<4, true><<<n_jobs, kGThreads, 0, s>>>(jobs, job_first, paints, thr, status);
+        small_canvas_kernel<4, true><<<n_jobs, kGThreads, kSmemBytes, s>>>(jobs, job_first, paints, thr, status);
     } else {
-        small_canvas_kernel<5, true><<<n_jobs, kGThreads, 0, s>>>(jobs, job_first, paints, thr, status);
+        small_canvas_kernel<5, true><<<n_jobs, kGThreads, kSmemBytes, s>>>(jobs, job_first, paints, thr, status);
     }
 }
 
