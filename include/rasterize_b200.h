@@ -28,6 +28,8 @@ extern "C" {
 #define RGPU_ERR_NAN (-3)       /* a control point is NaN: reference panics "cannot flatten segment with NaN" */
 #define RGPU_ERR_DEPTH (-4)     /* subdivision deeper than the device stack (reference would recurse without bound) */
 #define RGPU_ERR_CAPACITY (-5)  /* output buffer supplied by the caller is too small */
+#define RGPU_ERR_WINDING (-6)   /* a non-zero winding number reached the guard of the 32-bit fixed-point cells (asynchronous
+                                   submissions only: the *_sync and host-buffer entry points re-run such a batch themselves) */
 
 typedef struct rgpu_ctx rgpu_ctx;
 typedef struct rgpu_dpath rgpu_dpath; /* device-resident path */
@@ -185,6 +187,14 @@ int rgpu_render_scene(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, float*
 /* rgpu_render_scene + rgpu_batch_status with transparent scratch growth and re-run on internal overflow. */
 int rgpu_render_scene_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, float* layer_dev, size_t width, size_t height, int fresh,
                            const float* bg, uint8_t* rgba_dev);
+/* Winding cells are 32-bit fixed point.  integer_bits = 8 (default): Q7.24, 6e-8 of a pixel; the integer part wraps modulo 256
+ * windings, which the even-odd rule cannot see and the non-zero rule sees only for a winding within 1 of a non-zero multiple of
+ * 256 (the reference accumulates f64, src/rasterize.rs:478-493).  The row scans report a non-zero winding of 120 or more
+ * (RGPU_ERR_WINDING from rgpu_batch_status); every *_sync / host-buffer entry point then re-runs the batch with
+ * integer_bits = 14 (Q13.18, 4e-6 of a pixel, windings up to 8191).  This call selects the format up front for the
+ * asynchronous entry points.  Not covered: 128 or more coincident same-direction edges through ONE pixel cell (identical
+ * stacked copies) can wrap that cell before any winding is seen. */
+int rgpu_set_winding_bits(rgpu_ctx* ctx, int integer_bits);
 /* Lines produced by the flatten stage of the last completed batch, and kernels launched since create. */
 int rgpu_last_counts(rgpu_ctx* ctx, uint64_t* n_lines, uint64_t* n_line_refs, uint64_t* n_launches);
 

@@ -712,6 +712,10 @@ class GpuRasterizer:
     def batch_status(self) -> None:
         self._check(ffi.lib().rgpu_batch_status(self.ctx))
 
+    def set_winding_bits(self, integer_bits: int) -> None:
+        """8 = Q7.24 winding cells (default), 14 = Q13.18 (`rgpu_set_winding_bits`)."""
+        self._check(ffi.lib().rgpu_set_winding_bits(self.ctx, integer_bits))
+
     # -- batches of independent paths (BASELINE config 4) / band-sharded masks (config 5) ---------------------------
     def upload_batch(self, batch: PathBatch) -> DevicePathBatch:
         return DevicePathBatch(self, batch)

@@ -9,7 +9,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "librasterize_b200.so"
-SOURCES = ["flatten.cu", "scan.cu", "raster.cu", "scene.cu", "small.cu", "small_v1.cu", "compose.cu", "context.cu"]
+SOURCES = ["flatten.cu", "scan.cu", "raster.cu", "scene.cu", "small.cu", "compose.cu", "context.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -72,6 +72,7 @@ struct rgpu_ctx {
     // device scratch (grow-only)
     DevBuf jobs, paints, slot_counts, slot_offs, lines, line_job, zero_block, tile_offs, refs, scan_temp, status, tile_state;
     uint32_t epoch = 0;
+    int fix_shift = kFixShift;  // fraction bits of the winding cells of the batch being submitted (see rgpu_internal.cuh)
     DevBuf img_f32, img_f64, img_lin;  // staging canvases of the host-buffer entry points
     DevBuf tmp_pts, tmp_items;         // device copy of the path of the current host-buffer call (grow-only, no per-call cudaMalloc)
     uint2* h_items = nullptr;          // pinned staging of the item list
@@ -502,6 +503,7 @@ int build_tables(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, int close_f
         d.rule = in.fill_rule;
         d.mode = in.mode;
         d.close = close_flag;
+        d.fix_shift = ctx->fix_shift;
         d.canvas = in.canvas;
         d.origin = in.origin;
         d.row_stride = in.row_stride;
@@ -834,6 +836,9 @@ int check_status(rgpu_ctx* ctx) {
     ctx->need_lines = st.n_lines;
     ctx->need_refs = st.n_refs;
     if (st.lines_overflow || st.refs_overflow) return fail(ctx, RGPU_ERR_CAPACITY, "internal scratch overflow (retry grows it)");
+    if (st.winding_flag)
+        return fail(ctx, RGPU_ERR_WINDING, "non-zero winding number beyond the guard of the 32-bit cells (the *_sync entry points re-run such a batch with "
+                                           "a wider integer part; rgpu_set_winding_bits selects it up front)");
     ctx->last_lines = st.n_lines;
     ctx->last_refs = st.n_refs;
     return RGPU_OK;
@@ -845,6 +850,20 @@ int submit_sync(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32_t fla
         int rc = submit(ctx, jobs, n_jobs, flags, close_flag, ordered_lines, scene);
         if (rc) return rc;
         rc = check_status(ctx);
+        if (rc == RGPU_ERR_WINDING && ctx->fix_shift > kFixShiftWide) {
+            // a NonZero winding reached the guard of the Q7.24 cells: once more in Q13.18 (windings up to +-8192).  Only batches
+            // that overwrite their output can be repeated: a FILL has already blended into its canvas (the caller re-renders
+            // with rgpu_set_winding_bits(ctx, 14); rgpu_fill restores the image from the host copy and repeats itself).
+            bool repeatable = !(scene && !scene->fresh);
+            for (size_t j = 0; j < n_jobs && repeatable; j++) repeatable = scene || jobs[j].mode != RGPU_JOB_FILL;
+            if (!repeatable) return rc;
+            const int keep = ctx->fix_shift;
+            ctx->fix_shift = kFixShiftWide;
+            rc = submit(ctx, jobs, n_jobs, flags, close_flag, ordered_lines, scene);
+            if (rc == RGPU_OK) rc = check_status(ctx);
+            ctx->fix_shift = keep;
+            if (rc != RGPU_ERR_CAPACITY) return rc;
+        }
         if (rc != RGPU_ERR_CAPACITY) return rc;
         // grow: line count is exact once the emit pass overflowed (it comes from the scan); the reference
         // count is only known when the lines fitted, so over-provision it from the line count.
@@ -1038,6 +1057,13 @@ int rgpu_render_batch(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, uint32
     if (!ctx) return RGPU_ERR_INVALID;
     CK(ctx, cudaSetDevice(ctx->device));
     return submit(ctx, jobs, n_jobs, flags, 1);
+}
+
+int rgpu_set_winding_bits(rgpu_ctx* ctx, int integer_bits) {
+    if (!ctx) return RGPU_ERR_INVALID;
+    if (integer_bits != 8 && integer_bits != 14) return fail(ctx, RGPU_ERR_INVALID, "winding bits: 8 (Q7.24 cells, the default) or 14 (Q13.18)");
+    ctx->fix_shift = integer_bits == 8 ? kFixShift : kFixShiftWide;
+    return RGPU_OK;
 }
 
 int rgpu_batch_status(rgpu_ctx* ctx) {
@@ -1586,6 +1612,20 @@ int rgpu_fill(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill
     job.width = (uint32_t)w;
     job.height = (uint32_t)h;
     rc = submit_sync(ctx, &job, 1, RGPU_BATCH_ORDERED, 1);
+    if (rc == RGPU_ERR_WINDING && ctx->fix_shift > kFixShiftWide) {
+        // the fill has blended into the device copy with wrapped windings: restore it from the caller's image and repeat in Q13.18
+        if (dense_rows) {
+            if (rw && rh)
+                CK(ctx, cudaMemcpy2DAsync(d_img + ry0 * w + rx0, w * sizeof(float4), dst + 4 * (ry0 * shape.row_stride + rx0),
+                                          shape.row_stride * sizeof(float4), rw * sizeof(float4), rh, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            CK(ctx, cudaMemcpyAsync(d_img, ctx->h_stage, sizeof(float4) * w * h, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        const int keep = ctx->fix_shift;
+        ctx->fix_shift = kFixShiftWide;
+        rc = submit_sync(ctx, &job, 1, RGPU_BATCH_ORDERED, 1);
+        ctx->fix_shift = keep;
+    }
     if (rc) return rc;
     if (dense_rows) {
         if (rw && rh)

@@ -47,7 +47,8 @@ struct TileCfg {
 // stores are full 512 B coalesced 128-bit accesses.  Rows no line touched are written straight from registers.
 template <int CW, int TH, int THREADS, bool EVENODD, bool FILL, class Cfg>
 __device__ __forceinline__ void scan_rows(const JobDev& job, const PaintDev& s_paint, int* cells, const int* carry, const int* row_touched,
-                                          int* row_live, int row0, int row1, int cx0, int mode_in, int tid) {
+                                          int* row_live, int row0, int row1, int cx0, int mode_in, int tid, const Fix fix, const uint32_t n_lines,
+                                          Status* __restrict__ status) {
     // FILL = false: the launch holds no FILL job and the paint / composite code is not even compiled in
     const int mode = (!FILL && mode_in == kModeFill) ? kModeMask : mode_in;
     constexpr int L = Cfg::kL;
@@ -58,6 +59,10 @@ __device__ __forceinline__ void scan_rows(const JobDev& job, const PaintDev& s_p
         const int acc = carry[r];
         int* bc = cells + r * CW;
         const int y = row0 + r;
+        // winding guard (NonZero): inside the tile a row's winding moves away from its carry-in by at most one per line of
+        // the tile, so only dense tiles or large carries look at their pixels
+        const bool wcheck = !EVENODD && (abs(acc) >> job.fix_shift) + (int)n_lines >= (fix.guard >> job.fix_shift);
+        if (wcheck && lane == 0 && abs(acc) >= fix.guard) status->winding_flag = 1u;
         if (row_touched[r]) {
             int v[L];
 #pragma unroll
@@ -74,14 +79,20 @@ __device__ __forceinline__ void scan_rows(const JobDev& job, const PaintDev& s_p
                 if (lane >= o) incl += nb;
             }
             const int base = acc + incl - v[L - 1];
+            if (wcheck) {
+                bool risk = false;
+#pragma unroll
+                for (int i = 0; i < NQ; i++) risk = risk || winding_risk(base + v[4 * i], base + v[4 * i + 1], base + v[4 * i + 2], base + v[4 * i + 3], fix);
+                if (risk) status->winding_flag = 1u;
+            }
 #pragma unroll
             for (int i = 0; i < NQ; i++) {
-                const float4 cv = make_float4(coverage_from_fixed<EVENODD>(base + v[4 * i]), coverage_from_fixed<EVENODD>(base + v[4 * i + 1]),
-                                              coverage_from_fixed<EVENODD>(base + v[4 * i + 2]), coverage_from_fixed<EVENODD>(base + v[4 * i + 3]));
+                const float4 cv = make_float4(coverage_from_fixed<EVENODD>(base + v[4 * i], fix), coverage_from_fixed<EVENODD>(base + v[4 * i + 1], fix),
+                                              coverage_from_fixed<EVENODD>(base + v[4 * i + 2], fix), coverage_from_fixed<EVENODD>(base + v[4 * i + 3], fix));
                 *reinterpret_cast<float4*>(bc + swz<true>(lane * L + i * 4)) = cv;
             }
         } else {
-            float c = coverage_from_fixed<EVENODD>(acc);  // no line touched this row of the tile: constant coverage
+            float c = coverage_from_fixed<EVENODD>(acc, fix);  // no line touched this row of the tile: constant coverage
             if (!FILL || mode != kModeFill) {
                 // straight from registers: no shared-memory round trip for empty rows (most of a sparse canvas)
                 if (mode == kModeCoverage && c < 1e-6f) c = 0.f;
@@ -169,7 +180,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : (THREADS >= 512
 raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first, const JobDev one_job,
               const PaintDev* __restrict__ paints, uint32_t* __restrict__ tile_offs, uint32_t bin_cap,
               const double4* __restrict__ bin_lines, unsigned long long* __restrict__ tile_state, uint32_t epoch,
-              uint32_t* __restrict__ ticket, const Status* status, uint32_t zero_early, uint32_t n_tiles, uint32_t late_wait) {
+              uint32_t* __restrict__ ticket, Status* status, uint32_t zero_early, uint32_t n_tiles, uint32_t late_wait) {
     using Cfg = TileCfg<CW, TH, THREADS>;
     using SpanT = typename Cfg::SpanT;
     static_assert(TH <= 64 && CW % 128 == 0 && Cfg::kL % 4 == 0, "tile shape");
@@ -265,6 +276,8 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
     g.wci = (int)g.wc;
     g.tile_end = g.cx0 + min(CW, g.wci + 1 - g.cx0);  // columns that exist in the reference image (incl. overflow column)
     g.pitch = CW;
+    const Fix fix = make_fix(job.fix_shift);
+    g.fix_scale = fix.scale;
     const int row0 = g.row0, row1 = g.row1, cx0 = g.cx0;
     const int mode = job.mode;
     constexpr int LPR = (THREADS / TH >= 32) ? 32 : (THREADS / TH);  // lanes per row in the look-back (16 for 1024 x 8 / 128)
@@ -356,8 +369,8 @@ raster_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, uint32_t job_fir
 
     // ---- phase 2: per-row scan, fill rule, store / composite (rowtot is dead: FILL reuses it as a per-row live flag) ----
     if (late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous fill of this canvas is complete
-    if (job.rule == 1) scan_rows<CW, TH, THREADS, true, FILL, Cfg>(job, s_paint, cells, carry, row_touched, rowtot, row0, row1, cx0, mode, tid);
-    else scan_rows<CW, TH, THREADS, false, FILL, Cfg>(job, s_paint, cells, carry, row_touched, rowtot, row0, row1, cx0, mode, tid);
+    if (job.rule == 1) scan_rows<CW, TH, THREADS, true, FILL, Cfg>(job, s_paint, cells, carry, row_touched, rowtot, row0, row1, cx0, mode, tid, fix, rend - rbeg, status);
+    else scan_rows<CW, TH, THREADS, false, FILL, Cfg>(job, s_paint, cells, carry, row_touched, rowtot, row0, row1, cx0, mode, tid, fix, rend - rbeg, status);
 }
 
 __global__ void to_rgba8_kernel(const float4* __restrict__ lin, uchar4* __restrict__ out, size_t n) {
@@ -378,7 +391,7 @@ __global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restri
 template <int CW, int TH, int THREADS, bool FILL>
 static void launch_raster_t(const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
                             uint32_t n_tiles, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
-                            unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, int pdl, cudaStream_t s) {
+                            unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, Status* status, bool zero_early, int pdl, cudaStream_t s) {
     constexpr size_t smem = TileCfg<CW, TH, THREADS>::smem_bytes();
     static bool configured[64] = {};  // per template instance and per device: the attribute belongs to the device's function
     int dev = 0;
@@ -414,7 +427,7 @@ TileShape raster_tile_shape(int variant) {
 
 void launch_raster(int variant, const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
                    uint32_t n_tiles, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
-                   unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, int pdl, cudaStream_t s) {
+                   unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, Status* status, bool zero_early, int pdl, cudaStream_t s) {
     if (n_tiles == 0) return;
     // launches without a FILL job run the instantiation that carries no paint / composite code (fewer registers)
     bool fill = false;

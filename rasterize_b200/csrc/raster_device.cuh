@@ -152,15 +152,32 @@ static __device__ float4 paint_at(const PaintDev& P, int x, int y) {
 // ---- coverage from the fixed-point winding ---------------------------------------------------------------
 // NonZero: min(|w|, 1) (the reference's `value < 1e-6 -> 0` only matters to mask_iter's pixel dropping, which
 // the COVERAGE / FILL paths apply themselves; below 1e-6 the two differ by < 1e-6).  EvenOdd is exact in integers.
+// Fixed-point format of a batch's winding cells (JobDev::fix_shift fraction bits)
+struct Fix {
+    float scale, inv;  // 2^shift, 2^-shift
+    int one;           // 1 << shift
+    int guard;         // a NonZero winding this large (eight short of the format's range) is reported (Status::winding_flag)
+};
+__device__ __forceinline__ Fix make_fix(int shift) {
+    Fix f;
+    f.scale = __int_as_float((127 + shift) << 23);
+    f.inv = __int_as_float((127 - shift) << 23);
+    f.one = 1 << shift;
+    f.guard = ((1 << (31 - shift)) - 8) << shift;  // 120 windings in Q7.24 (kWindingGuard), 8184 in Q13.18
+    return f;
+}
 template <bool EVENODD>
-__device__ __forceinline__ float coverage_from_fixed(int acc) {
-    constexpr float kInv = 1.0f / 16777216.0f;
+__device__ __forceinline__ float coverage_from_fixed(int acc, const Fix& f) {
     if (EVENODD) {
         // abs(((w + 1) rem_euclid 2) - 1)
-        const int t = (acc + kFixOne) & (2 * kFixOne - 1);
-        return fabsf((float)(t - kFixOne)) * kInv;
+        const int t = (acc + f.one) & (2 * f.one - 1);
+        return fabsf((float)(t - f.one)) * f.inv;
     }
-    return fminf(fabsf((float)acc) * kInv, 1.0f);
+    return fminf(fabsf((float)acc) * f.inv, 1.0f);
+}
+// NonZero only: true when one of four windings has reached the guard
+__device__ __forceinline__ bool winding_risk(int a, int b, int c, int d, const Fix& f) {
+    return max(max(abs(a), abs(b)), max(abs(c), abs(d))) >= f.guard;
 }
 
 // ---- shared-memory cell layout --------------------------------------------------------------------------
@@ -174,7 +191,7 @@ __device__ __forceinline__ int swz(int x) {
     return SWZ ? (x ^ (((x >> 5) & 7) << 2)) : x;
 }
 
-__device__ __forceinline__ int to_fixed_f(float v) { return __float2int_rn(v * 16777216.0f); }
+__device__ __forceinline__ int to_fixed_f(float v, float scale) { return __float2int_rn(v * scale); }
 
 struct TileGeom {
     int row0, row1;   // canvas rows [row0, row1) of this band
@@ -183,6 +200,7 @@ struct TileGeom {
     int pitch;
     double wc;        // reference `width` (= img.width - 1)
     int wci;
+    float fix_scale;  // 2^fix_shift of the batch (see Fix)
 };
 
 // One (piece, row) span: the body of the reference's row loop (src/rasterize.rs:421-469) for canvas row y.
@@ -216,7 +234,7 @@ __device__ __forceinline__ SpanHead span_head(double ax, double ay, double by, d
     h.x1i = min(max(__double2int_ru(h.x1), 0), g.wci);
     h.r = y - g.row0;
     h.d = dirf * (float)dy;
-    h.fd = to_fixed_f(h.d);
+    h.fd = to_fixed_f(h.d, g.fix_scale);
     h.narrow = h.x1i <= h.x0i + 1;
     const int last = h.narrow ? h.x0i + 1 : h.x1i;  // last column that receives a delta
     // right of the tile: nothing here; left of it: the span arrives through the look-back
@@ -231,7 +249,7 @@ __device__ __forceinline__ void span_narrow(const SpanHead& h, const TileGeom& g
                                             int* __restrict__ row_touched) {
     int* rowp = cells + h.r * g.pitch;
     const float c0 = 1.0f - (float)(0.5 * (h.x + h.xn) - (double)h.x0i);  // 1 - xmf
-    const int ca = to_fixed_f(h.d * c0);
+    const int ca = to_fixed_f(h.d * c0, g.fix_scale);
     int tot = 0;
     if (h.x0i >= g.cx0) {  // x0i < tile_end holds (live)
         atomicAdd(&rowp[swz<SWZ>(h.x0i - g.cx0)], ca);
@@ -268,10 +286,10 @@ __device__ __forceinline__ void span_wide(const SpanHead& h, const TileGeom& g, 
     };
     const int kb = max(h.x0i, g.cx0);
     const int ke = min(h.x1i, g.tile_end - 1);
-    const int first = (kb > h.x0i) ? to_fixed_f(h.d * cov(kb - 1 - h.x0i)) : 0;  // rounded coverage just left of the tile
+    const int first = (kb > h.x0i) ? to_fixed_f(h.d * cov(kb - 1 - h.x0i), g.fix_scale) : 0;  // rounded coverage just left of the tile
     int prev = first;
     for (int k = kb; k <= ke; k++) {
-        const int cur = (k == h.x1i) ? h.fd : to_fixed_f(h.d * cov(k - h.x0i));
+        const int cur = (k == h.x1i) ? h.fd : to_fixed_f(h.d * cov(k - h.x0i), g.fix_scale);
         atomicAdd(&rowp[swz<SWZ>(k - g.cx0)], cur - prev);
         prev = cur;
     }

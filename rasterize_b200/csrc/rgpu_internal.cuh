@@ -24,9 +24,13 @@ constexpr uint32_t kItemClosing = 0x80000000u;
 constexpr uint32_t kItemExplicitClosed = 0x40000000u;
 constexpr uint32_t kItemIndexMask = 0x3fffffffu;
 
-constexpr int kFixShift = 24;           // Q7.24 fixed-point winding cells
-constexpr int kFixOne = 1 << kFixShift;
-constexpr double kFixScale = 16777216.0;
+// Winding cells are 32-bit fixed point, Q7.24 by default: 6e-8 of a pixel, windings in [-128, 128).  The integer
+// arithmetic wraps modulo 256 windings, which EvenOdd cannot see (256 is even) and NonZero sees only for a true winding
+// within 1 of a non-zero multiple of 256.  The row scans watch for |winding| >= kWindingGuard under NonZero; a batch that
+// trips the guard is re-run by the *_sync entry points in Q13.18 (4e-6 of a pixel, windings in [-8192, 8192)).
+constexpr int kFixShift = 24;
+constexpr int kFixShiftWide = 18;
+constexpr int kWindingGuard = 120;
 
 constexpr int kMaxStops = 32;
 constexpr int kStateRows = 16;            // rows per tile in the carry look-back state (chunked tiles have 8 rows)
@@ -71,6 +75,8 @@ struct JobDev {
     // scene batches (scene.cu): the job's tile grid is aligned with the LAYER's tiles.  (ox, oy) = position of the job's
     // window inside its first layer tile, (sc0, sb0) = that tile's chunk / band index in the layer.  All zero otherwise.
     int32_t ox, oy, sc0, sb0;
+    int32_t fix_shift;     // fixed-point fraction bits of this batch's winding cells (kFixShift or kFixShiftWide)
+    int32_t pad_;
 };
 
 struct Status {
@@ -81,7 +87,7 @@ struct Status {
     uint32_t n_lines;
     uint32_t n_refs;
     uint32_t bin_max;   // fixed-capacity bins: largest per-tile line count seen (> capacity => refs_overflow)
-    uint32_t pad[1];
+    uint32_t winding_flag;  // a NonZero winding reached kWindingGuard: the 32-bit cells may wrap (see kFixShift)
 };
 
 // tile geometry of the raster kernel variants
@@ -130,7 +136,7 @@ TileShape raster_tile_shape(int variant);
 // the next batch finds them zero without a memset.
 void launch_raster(int variant, const JobDev* jobs, const JobDev* h_jobs, uint32_t n_jobs, uint32_t job_first, uint32_t tile_first,
                    uint32_t n_tiles, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
-                   unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, bool zero_early, int pdl, cudaStream_t s);
+                   unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, Status* status, bool zero_early, int pdl, cudaStream_t s);
 // Scene compositor (scene.cu): every FILL job of a layer in one launch, one CTA per 256 x 8 LAYER tile, fills blended in
 // submission order inside the CTA.  Jobs carry layer-aligned tile grids (JobDev::ox/oy/sc0/sb0); fixed bins only.
 struct SceneArgs {
@@ -150,7 +156,7 @@ struct SceneArgs {
 };
 TileShape scene_tile_shape();
 void launch_scene(const JobDev* jobs, uint32_t n_jobs, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
-                  unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, const SceneArgs& sc, bool pdl,
+                  unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, Status* status, const SceneArgs& sc, bool pdl,
                   cudaStream_t s);
 // Fused one-CTA-per-job pipeline for canvases of at most 64 x 64 visible pixels (small.cu)
 bool small_canvas_eligible(uint32_t width, uint32_t height, int mode);

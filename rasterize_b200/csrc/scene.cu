@@ -49,7 +49,7 @@ struct ScCfg {
 };
 
 template <bool EVENODD, int kScL>
-__device__ __forceinline__ void scan_row_inplace(int* bc, int acc, int lane) {
+__device__ __forceinline__ void scan_row_inplace(int* bc, int acc, int lane, const Fix fix, const bool wcheck, Status* __restrict__ status) {
     int v[kScL];
 #pragma unroll
     for (int i = 0; i < kScL / 4; i++) {
@@ -65,10 +65,16 @@ __device__ __forceinline__ void scan_row_inplace(int* bc, int acc, int lane) {
         if (lane >= o) incl += nb;
     }
     const int base = acc + incl - v[kScL - 1];
+    if (!EVENODD && wcheck) {  // winding guard, see raster.cu scan_rows
+        bool risk = false;
+#pragma unroll
+        for (int i = 0; i < kScL / 4; i++) risk = risk || winding_risk(base + v[4 * i], base + v[4 * i + 1], base + v[4 * i + 2], base + v[4 * i + 3], fix);
+        if (risk) status->winding_flag = 1u;
+    }
 #pragma unroll
     for (int i = 0; i < kScL / 4; i++) {
-        const float4 cv = make_float4(coverage_from_fixed<EVENODD>(base + v[4 * i]), coverage_from_fixed<EVENODD>(base + v[4 * i + 1]),
-                                      coverage_from_fixed<EVENODD>(base + v[4 * i + 2]), coverage_from_fixed<EVENODD>(base + v[4 * i + 3]));
+        const float4 cv = make_float4(coverage_from_fixed<EVENODD>(base + v[4 * i], fix), coverage_from_fixed<EVENODD>(base + v[4 * i + 1], fix),
+                                      coverage_from_fixed<EVENODD>(base + v[4 * i + 2], fix), coverage_from_fixed<EVENODD>(base + v[4 * i + 3], fix));
         *reinterpret_cast<float4*>(bc + swz<true>(lane * kScL + i * 4)) = cv;
     }
 }
@@ -77,7 +83,7 @@ template <int kScW, int kScThreads>
 __global__ void __launch_bounds__(kScThreads, (ScCfg<kScW, kScThreads>::kMinBlocks))
 scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* __restrict__ paints, uint32_t* __restrict__ tile_offs,
              uint32_t bin_cap, const double4* __restrict__ bin_lines, unsigned long long* __restrict__ tile_state, uint32_t epoch,
-             uint32_t* __restrict__ ticket, const Status* status, const SceneArgs sc) {
+             uint32_t* __restrict__ ticket, Status* status, const SceneArgs sc) {
     using Cfg = ScCfg<kScW, kScThreads>;
     constexpr int kScL = Cfg::kL, kScWarps = Cfg::kWarps;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -216,6 +222,8 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
         g.wci = (int)g.wc;
         g.tile_end = min(g.cx0 + kScW, g.wci + 1);
         g.pitch = kScW;
+        const Fix fix = make_fix(job.fix_shift);
+        g.fix_scale = fix.scale;
         if (cnt) {
             {
                 const int4 z = make_int4(0, 0, 0, 0);
@@ -247,12 +255,14 @@ scene_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, const PaintDev* _
         if (warp < kScH) {
             const int r = warp;
             const int acc = carry[r];
+            const bool wcheck = !job_evenodd && (abs(acc) >> job.fix_shift) + (int)cnt >= (fix.guard >> job.fix_shift);
+            if (wcheck && lane == 0 && abs(acc) >= fix.guard) status->winding_flag = 1u;
             if (row_touched[r]) {
-                if (job_evenodd) scan_row_inplace<true, kScL>(cells + r * kScW, acc, lane);
-                else scan_row_inplace<false, kScL>(cells + r * kScW, acc, lane);
+                if (job_evenodd) scan_row_inplace<true, kScL>(cells + r * kScW, acc, lane, fix, false, status);
+                else scan_row_inplace<false, kScL>(cells + r * kScW, acc, lane, fix, wcheck, status);
                 if (lane == 0) row_live[r] = 1;
             } else if (lane == 0) {  // no line touched this row of the tile: constant coverage
-                const float cv = job_evenodd ? coverage_from_fixed<true>(acc) : coverage_from_fixed<false>(acc);
+                const float cv = job_evenodd ? coverage_from_fixed<true>(acc, fix) : coverage_from_fixed<false>(acc, fix);
                 row_const[r] = cv;
                 row_live[r] = cv >= 1e-6f;
             }
@@ -341,7 +351,7 @@ TileShape scene_tile_shape() { return TileShape{scene_cw(), kScH}; }
 
 template <int CW, int THREADS>
 static void launch_scene_t(const JobDev* jobs, uint32_t n_jobs, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap,
-                           const double4* bin_lines, unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status,
+                           const double4* bin_lines, unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, Status* status,
                            const SceneArgs& sc, bool pdl, cudaStream_t s) {
     const uint32_t n_tiles = sc.n_bands * sc.n_chunks;
     constexpr size_t smem = ScCfg<CW, THREADS>::kSmem;
@@ -367,7 +377,7 @@ static void launch_scene_t(const JobDev* jobs, uint32_t n_jobs, const PaintDev* 
 }
 
 void launch_scene(const JobDev* jobs, uint32_t n_jobs, const PaintDev* paints, uint32_t* tile_offs, uint32_t bin_cap, const double4* bin_lines,
-                  unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, const Status* status, const SceneArgs& sc, bool pdl,
+                  unsigned long long* tile_state, uint32_t epoch, uint32_t* ticket, Status* status, const SceneArgs& sc, bool pdl,
                   cudaStream_t s) {
     if (sc.n_bands * sc.n_chunks == 0) return;
 #define RGPU_SCENE(CW, T) launch_scene_t<CW, T>(jobs, n_jobs, paints, tile_offs, bin_cap, bin_lines, tile_state, epoch, ticket, status, sc, pdl, s)

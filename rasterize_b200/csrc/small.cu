@@ -2,7 +2,8 @@
 // ONE 160-thread CTA per job runs K1..K4 end to end.  No line buffer, no bins and no carries ever touch HBM: traffic
 // is the algorithmic minimum (control points in, pixels out), and a whole batch is one launch.
 //
-// Round-2 design (the round-1 kernel is kept in small_v1.cu for A/B, RGPU_SMALL_V1=1).  The kernel is bound by
+// Round-2 design (round 1: one 256-thread CTA, a depth-first walk with a 1.5 KB local-memory stack per slot thread, block
+// barriers between flattening, accumulation and the scan: 1.40 ms per 20 000 glyphs against 0.94 ms now).  The kernel is bound by
 // instruction issue, not by HBM, so everything below is about executing few warp-instructions with full warps:
 //   * curves are transformed ONCE into shared memory (chunks of 20 curves); a curve's subdivision tree is cut at
 //     depth 3 (8 slot threads per curve, 20 curves = 160 threads).  A slot thread descends to its subtree root and
@@ -36,9 +37,6 @@
 #include <type_traits>
 
 namespace rgpu {
-
-void launch_small_canvas_v1(const JobDev* jobs, uint32_t job_first, uint32_t n_jobs, const PaintDev* paints, double thr, Status* status,
-                            cudaStream_t s);
 
 namespace {
 
@@ -157,7 +155,7 @@ __device__ __forceinline__ Nd nd_half(const Nd& n, int kind) {
 __device__ __forceinline__ double nd_endx(const Nd& n, int kind) { return kind == 4 ? n.x3 : n.x2; }
 __device__ __forceinline__ double nd_endy(const Nd& n, int kind) { return kind == 4 ? n.y3 : n.y2; }
 
-__device__ __forceinline__ int fix_f(float v) { return __float2int_rn(v * 16777216.0f); }
+__device__ __forceinline__ int fix_f(float v, float scale) { return __float2int_rn(v * scale); }
 // 1 / x for x in (1e-20, 1e3): the bare MUFU.RCP (1 ulp), without the range fix-up of __fdividef
 __device__ __forceinline__ float rcp_fast(float x) {
     float r;
@@ -201,6 +199,7 @@ extern __shared__ __align__(16) unsigned char sm_raw[];
 struct Canvas {
     int H, wci, tile_end;
     float wcf;
+    float fix_scale;  // 2^fix_shift of the batch (raster_device.cuh: Fix)
     double wc;
 };
 
@@ -228,7 +227,7 @@ __device__ __forceinline__ Span span_head(const float4 p, const int y, const Can
     s.x0i = (int)s.xa;
     s.x1i = min((int)ceilf(s.xb), cv.wci);
     s.n = s.x1i - s.x0i;
-    s.fd = fix_f(s.d);
+    s.fd = fix_f(s.d, cv.fix_scale);
     s.at = y * kSmPitch + s.x0i;
     return s;
 }
@@ -241,25 +240,25 @@ __device__ __forceinline__ void span_narrow(const Span& s, const Canvas& cv) {
     const float u = 1.0f - (s.xa - fx0);
     const float c_wide = 0.5f * sf * u * u;
     const bool two = s.n == 2;
-    const int qa = fix_f(s.d * (two ? c_wide : c_narrow));
-    const int qb = two ? fix_f(s.d * (1.0f - 0.5f * sf * x1f * x1f)) : s.fd;
+    const int qa = fix_f(s.d * (two ? c_wide : c_narrow), cv.fix_scale);
+    const int qb = two ? fix_f(s.d * (1.0f - 0.5f * sf * x1f * x1f), cv.fix_scale) : s.fd;
     cell_add(s.at, qa);
     if (s.x0i + 1 < cv.tile_end) cell_add(s.at + 1, qb - qa);
     if (two) cell_add(s.at + 2, s.fd - qb);  // x0i + 2 == x1i <= wci < tile_end
 }
 // three or more columns (src/rasterize.rs:445-468)
-__device__ __forceinline__ void span_wide(const Span& s) {
+__device__ __forceinline__ void span_wide(const Span& s, const Canvas& cv) {
     const float x0f = s.xa - (float)s.x0i;
     const float sf = rcp_fast(s.xb - s.xa);
     const float x1f = s.xb - (float)s.x1i + 1.0f;
     const float c0 = 0.5f * sf * (1.0f - x0f) * (1.0f - x0f);
     const float cl = 1.0f - 0.5f * sf * x1f * x1f;
     const float a1 = sf * (1.5f - x0f);
-    int prev = fix_f(s.d * c0);
+    int prev = fix_f(s.d * c0, cv.fix_scale);
     cell_add(s.at, prev);
     for (int j = 1; j < s.n; j++) {
         const float c = (j == s.n - 1) ? cl : a1 + (float)(j - 1) * sf;
-        const int cur = fix_f(s.d * c);
+        const int cur = fix_f(s.d * c, cv.fix_scale);
         cell_add(s.at + j, cur - prev);
         prev = cur;
     }
@@ -282,11 +281,11 @@ __device__ __noinline__ void accumulate_warp(const int count, const Canvas cv) {
         __syncwarp();
         if (lane < n_wide) {
             const int id = wide[lane];
-            span_wide(span_head(q[id >> 6], id & 63, cv));
+            span_wide(span_head(q[id >> 6], id & 63, cv), cv);
         }
         if (lane + 32 < n_wide) {
             const int id = wide[lane + 32];
-            span_wide(span_head(q[id >> 6], id & 63, cv));
+            span_wide(span_head(q[id >> 6], id & 63, cv), cv);
         }
         n_wide = 0;
         __syncwarp();
@@ -328,7 +327,7 @@ __device__ __noinline__ void accumulate_warp(const int count, const Canvas cv) {
             } else {  // a line over many rows (not in a glyph): its own lane walks them
                 for (int k = 0; k < n; k++) {
                     const Span s = span_head(p, rb + k, cv);
-                    if (s.n <= 2) span_narrow(s, cv); else span_wide(s);
+                    if (s.n <= 2) span_narrow(s, cv); else span_wide(s, cv);
                 }
             }
             total += __shfl_sync(kFull, incl, 31);
@@ -369,6 +368,7 @@ __device__ __noinline__ void line_slow(double x0, double y0, double x1, double y
     g.wci = cv.wci;
     g.tile_end = cv.tile_end;
     g.pitch = kSmPitch;
+    g.fix_scale = cv.fix_scale;
     line_serial<false>(make_double4(x0, y0, x1, y1), g, s_cells, s_rowtot, s_row_touched);
 }
 
@@ -641,7 +641,8 @@ __device__ __forceinline__ void emit_line_item(const uint32_t i, const uint32_t 
 // rule, composite, store.  `cells`: the canvas' cell buffer; `paint_buf`: shared memory for a gradient paint's table.
 template <bool PLAIN, int NWARPS>
 __device__ __forceinline__ void finish_rows(const JobDev& job, const PaintDev* __restrict__ paints, int* const cells, void* paint_buf, const int warp,
-                                            const int lane, const int tid) {
+                                            const int lane, const int tid, Status* __restrict__ status) {
+    const Fix fix = make_fix(job.fix_shift);
     // ---- K3 phase 2 + K4: two rows per warp iteration (16 lanes x 4 columns each) ----------------------------
     const int mode = job.mode;
     const bool render = mode == kModeRender;  // fill onto a canvas created here: every pixel is written, none is read
@@ -687,12 +688,14 @@ __device__ __forceinline__ void finish_rows(const JobDev& job, const PaintDev* _
         }
         const int base = incl - p3;
         float4 c;
-        if (evenodd)
-            c = make_float4(coverage_from_fixed<true>(base + p0), coverage_from_fixed<true>(base + p1), coverage_from_fixed<true>(base + p2),
-                            coverage_from_fixed<true>(base + p3));
-        else
-            c = make_float4(coverage_from_fixed<false>(base + p0), coverage_from_fixed<false>(base + p1),
-                            coverage_from_fixed<false>(base + p2), coverage_from_fixed<false>(base + p3));
+        if (evenodd) {
+            c = make_float4(coverage_from_fixed<true>(base + p0, fix), coverage_from_fixed<true>(base + p1, fix), coverage_from_fixed<true>(base + p2, fix),
+                            coverage_from_fixed<true>(base + p3, fix));
+        } else {
+            if (winding_risk(base + p0, base + p1, base + p2, base + p3, fix)) status->winding_flag = 1u;  // see rgpu_internal.cuh: kFixShift
+            c = make_float4(coverage_from_fixed<false>(base + p0, fix), coverage_from_fixed<false>(base + p1, fix),
+                            coverage_from_fixed<false>(base + p2, fix), coverage_from_fixed<false>(base + p3, fix));
+        }
         const int col = hl * 4;
         if (mode != kModeMask) {  // mask_iter drops abs(alpha) < 1e-6 (src/rasterize.rs:348); fill_impl sees that iterator
             if (c.x < 1e-6f) c.x = 0.f;
@@ -777,6 +780,7 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
     cv.wci = (int)cv.wc;
     cv.wcf = (float)cv.wc;
     cv.tile_end = min(kSmPitch, cv.wci + 1);  // reference columns incl. the overflow column
+    cv.fix_scale = make_fix(job.fix_shift).scale;
     Warp w;
     w.qn = 0;
     w.dn = 0;
@@ -846,7 +850,7 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
     __syncthreads();
     if (tid == 0 && s_nlines) atomicAdd(&status->n_lines, s_nlines);  // statistics only
 
-    finish_rows<PLAIN, kGWarps>(job, paints, s_cells, &s_lineq[0][0], warp, lane, tid);
+    finish_rows<PLAIN, kGWarps>(job, paints, s_cells, &s_lineq[0][0], warp, lane, tid, status);
 }
 
 
@@ -861,11 +865,6 @@ bool small_canvas_eligible(uint32_t width, uint32_t height, int mode) {
 void launch_small_canvas(const JobDev* jobs, uint32_t job_first, uint32_t n_jobs, const PaintDev* paints, double thr, Status* status,
                          bool gradients, cudaStream_t s) {
     if (n_jobs == 0) return;
-    static const bool use_v1 = getenv("RGPU_SMALL_V1") != nullptr;  // A/B switch: the round-1 kernel
-    if (use_v1) {
-        launch_small_canvas_v1(jobs, job_first, n_jobs, paints, thr, status, s);
-        return;
-    }
     // CTAs per SM (register budget): 4 -> 96 registers, 5 -> 72 with spills in the walk (measured: 0.94 vs 1.02 ms per 20 000 glyphs)
     static const int minb = getenv("RGPU_SMALL_MINB") ? atoi(getenv("RGPU_SMALL_MINB")) : 4;
     static bool configured[64] = {};

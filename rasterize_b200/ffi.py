@@ -11,7 +11,7 @@ from pathlib import Path as _P
 PKG = _P(__file__).resolve().parent
 LIB_PATH = PKG / "librasterize_b200.so"
 
-OK, ERR_INVALID, ERR_CUDA, ERR_NAN, ERR_DEPTH, ERR_CAPACITY = 0, -1, -2, -3, -4, -5
+OK, ERR_INVALID, ERR_CUDA, ERR_NAN, ERR_DEPTH, ERR_CAPACITY, ERR_WINDING = 0, -1, -2, -3, -4, -5, -6
 JOB_MASK, JOB_COVERAGE, JOB_FILL, JOB_RENDER = 0, 1, 2, 3
 OUT_LINCOLOR, OUT_RGBA8, OUT_COVERAGE = 0, 1, 2
 BATCH_ORDERED, BATCH_INDEPENDENT = 0, 1
@@ -70,7 +70,7 @@ SYMBOLS = [
     "rgpu_memcpy_h2d", "rgpu_memcpy_d2h", "rgpu_host_alloc", "rgpu_host_free",
     "rgpu_path_upload_batch", "rgpu_path_batch_get", "rgpu_path_batch_free", "rgpu_batch_create", "rgpu_batch_render", "rgpu_batch_free",
     "rgpu_fill_batch_host", "rgpu_mask_banded_host", "rgpu_multi_create", "rgpu_multi_destroy", "rgpu_multi_device_count",
-    "rgpu_multi_last_error", "rgpu_multi_fill_batch_host", "rgpu_multi_mask_banded_host",
+    "rgpu_multi_last_error", "rgpu_multi_fill_batch_host", "rgpu_multi_mask_banded_host", "rgpu_set_winding_bits",
 ]
 
 
@@ -106,6 +106,7 @@ def lib():
     sig("rgpu_path_free", None, vp, vp)
     sig("rgpu_render_batch", i32, vp, C.POINTER(CJob), sz, u32)
     sig("rgpu_batch_status", i32, vp)
+    sig("rgpu_set_winding_bits", i32, vp, i32)
     sig("rgpu_render_batch_sync", i32, vp, C.POINTER(CJob), sz, u32)
     sig("rgpu_render_scene", i32, vp, C.POINTER(CJob), sz, vp, sz, sz, i32, pf, vp)
     sig("rgpu_render_scene_sync", i32, vp, C.POINTER(CJob), sz, vp, sz, sz, i32, pf, vp)

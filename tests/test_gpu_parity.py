@@ -272,3 +272,39 @@ def test_staged_item_lists_follow_the_path_structure(rast):
         ref = np.zeros((48, 52))
         opath(p).mask(O.IDENTITY, O.NONZERO, ref)
         assert np.abs(img - ref).max() <= COV_TOL
+
+
+def test_shallow_lines_next_to_a_chunk_boundary_at_large_y(rast):
+    """the binning used to estimate a line's columns per band in f32 with 1.5 px of slack; at y ~ 32000 an f32 row
+    coordinate is 2e-3 off, which a shallow slope turns into many pixels, so a chunk the line reaches could miss it.  Long,
+    nearly horizontal edges that end a fraction of a pixel before / after the 1024-column boundary, far down a tall canvas."""
+    w, h = 1100, 32768
+    b = rb.Path.builder()
+    rng = np.random.default_rng(5)
+    for k in range(40):
+        y = 31000.0 + 40.0 * k + float(rng.uniform(0, 1))
+        xe = 1024.0 + float(rng.uniform(-1.6, 1.6))       # the shallow edge ends next to the chunk boundary
+        x0 = float(rng.uniform(3.0, 200.0))
+        dy = float(rng.uniform(0.002, 0.9))               # slopes dx/dy between ~1e3 and ~5e5
+        b.move_to((x0, y)).line_to((xe, y + dy)).line_to((x0 + 5.0, y + 12.0)).close()
+        b.move_to((xe + 30.0, y + 20.0)).line_to((1024.0 - float(rng.uniform(0.0, 3.0)), y + 20.0 + dy)).line_to((1090.0, y + 31.0)).close()
+    p = b.build()
+    img = np.zeros((h, w), dtype=np.float32)
+    rast.mask(p, rb.Transform.identity(), img, rb.FillRule.NonZero)
+    ref = np.zeros((h, w))
+    opath(p).mask_threads(O.IDENTITY, O.NONZERO, ref, threads=8)
+    assert np.abs(img[30900:] - ref[30900:]).max() <= COV_TOL
+    assert not img[:30900].any()
+
+
+def test_too_many_gradient_stops_is_an_error_everywhere(rast):
+    """rgpu_render_batch used to truncate a gradient to RGPU_MAX_STOPS silently; every entry point now rejects it."""
+    stops = [(i / 40.0, [1.0, 0.0, 0.0, 1.0]) for i in range(41)]
+    grad = rb.GradLinear(stops, rb.Units.UserSpaceOnUse, True, rb.GradSpread.Pad, rb.Transform.identity(), (0, 0), (10, 10))
+    p = assets.load_path("squirrel")
+    dp = rast.upload(p)
+    canvas = rast.device_alloc(100 * 100 * 16)
+    with pytest.raises(rb.RgpuError) as e:
+        rast.render_batch([rb.Job(dp, rb.Transform.identity(), rb.FillRule.NonZero, ffi.JOB_FILL, canvas, 100, 100, 100, paint=grad)])
+    assert e.value.code == ffi.ERR_INVALID
+    rast.device_free(canvas)

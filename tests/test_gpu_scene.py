@@ -60,3 +60,34 @@ def test_compose_primitives(rast):
         assert np.array_equal(rast.to_host(d_dst, dst.shape, np.float32), dst)
     for p in (d_dst, d_src, d_mask):
         rast.device_free(p)
+
+
+def test_nodes_starting_left_of_or_above_the_layer_draw_nothing(rast):
+    """the Fill arm casts `floor(bbox.min) - layer.xy` `as usize`; a negative value wraps and `view_shape`
+    clamps it to the layer's size, so a node whose bbox starts left of or above the layer gets an EMPTY window
+    (src/scene.rs:412-423, src/image.rs:588-605) — it is not drawn shifted, which round 1 did.  `Scene::render` never produces
+    such a node (bboxes are restricted to the view at build time); a hand-made node table with a view that cuts into the nodes
+    does.  Expected image = the same pipeline without the nodes that start outside, rendered over the same view."""
+    import copy
+    pl = assets.load_pipeline("firefox_512")
+    fills = [n for n in pl.nodes if n.kind == scene.FILL]
+    xs = sorted(float(n.bbox[0]) for n in fills)
+    ys = sorted(float(n.bbox[1]) for n in fills)
+    cut = copy.copy(pl)
+    # a view whose origin lies right of / below some nodes' bbox origins
+    vx, vy = np.floor(xs[len(xs) // 2]) + 3.0, np.floor(ys[len(ys) // 3]) + 2.0
+    cut.view = np.array([vx, vy, vx + 300.0, vy + 260.0])
+    outside = [i for i, n in enumerate(pl.nodes) if n.kind == scene.FILL and (np.floor(n.bbox[0]) < np.floor(vx) or np.floor(n.bbox[1]) < np.floor(vy))]
+    inside = [i for i, n in enumerate(pl.nodes) if n.kind == scene.FILL and i not in outside]
+    assert outside and inside
+    x, y, lin = scene.render(rast, cut)
+    # reference: drop the outside nodes (give them an empty bbox far away), keep everything else
+    kept = copy.copy(cut)
+    kept.nodes = [copy.copy(n) for n in cut.nodes]
+    for i in outside:
+        kept.nodes[i].bbox = np.array([1e7, 1e7, 1e7 + 1.0, 1e7 + 1.0])
+    x2, y2, lin2 = scene.render(rast, kept)
+    assert (x, y) == (x2, y2) and np.array_equal(lin, lin2)
+    ox, oy, ref = render_pipeline_oracle(cut)
+    assert (x, y) == (ox, oy) and np.abs(lin - ref).max() <= LIN_TOL
+    assert np.abs(lin).max() > 0.05  # the inside nodes were drawn
