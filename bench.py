@@ -144,7 +144,7 @@ def glyph_path(rb, seed: int):
 
 
 C4_TOTAL_GLYPHS = 100_000  # BASELINE configs[3]
-C5_BANDS = 64              # fine scanline bands dealt round-robin over the ranks (work and output bytes both balance)
+C5_BANDS = 64              # scanline bands of the canvas; rank r takes the contiguous block [r * 64 / N, (r + 1) * 64 / N) as one job
 
 
 def c4_total() -> int:
@@ -161,7 +161,7 @@ def workload_label(name: str) -> str:
         return "c2: data/material.path (21106 segments) fitted to 4096x4096, Rasterizer::mask, nonzero"
     if name == "c5":
         return ("c5: data/tv.path stroked (w=0.5 round/round) on a 32768x32768 canvas, Rasterizer::mask, nonzero, split into "
-                f"{int(os.environ.get('RB_BANDS', C5_BANDS))} scanline bands dealt round-robin over the GPUs")
+                f"{int(os.environ.get('RB_BANDS', C5_BANDS))} scanline bands, a contiguous block of bands per GPU")
     if name == "c1":
         return "c1: examples/rasterize scene of data/squirrel.path at 512 px (checkerboard + fill over #f0f0f0), Scene::render + RGBA8 export"
     return "c3: data/firefox.scene Scene::render at 2048x2048, 14 linear/radial gradient fills, + RGBA8 export"
@@ -224,13 +224,13 @@ def build_workload(name: str, rb, rast, rank: int, world: int, torch):
                     parallelism=f"glyphs [{a}, {b}) of {total} on this rank, {world} ranks, no collective")
         return (lambda sync=False: (prepared.render(), rast.batch_status() if sync else None)), info
     if name == "c5":
-        # strong scaling: the whole 32768 x 32768 canvas as fine scanline bands, rank r renders bands r, r + N, ...
-        # as independent jobs of one batch (band-local translate(0, -y0): the reference's own y clipping crops exactly)
+        # strong scaling: the whole 32768 x 32768 canvas as scanline bands, rank r renders a contiguous block of them
+        # as one job (band-local translate(0, -y0): the reference's own y clipping crops exactly)
         path = assets.load_path("tv_stroked")
         c5 = ex["tv_stroked"]["c5"]
         w, hfull = c5["size"]
         bands = int(os.environ.get("RB_BANDS", C5_BANDS))
-        mine = [b for b in range(bands) if b % world == rank]
+        mine = list(range(bands * rank // world, bands * (rank + 1) // world))  # equal rows = equal output bytes, which bound the raster kernel
         dp = rast.upload(path)
         jobs, canvases, rows = [], [], 0
         runs = []  # consecutive bands of this rank are one job (flattened once): at N = 1 the whole canvas
@@ -447,13 +447,14 @@ def measure(hx: Harness, name: str, steps: int, warmup: int, with_cpu: bool, sam
     elif name == "c5":
         path, tr, (w, h) = info["host_path"], info["host_tr"], info["host_size"]
         img = rast.host_alloc((h, w), np.float32)  # the whole canvas, pinned; this rank fills the rows of its bands
-        call = lambda: rast.mask_banded(path, tr, img, rb.FillRule.NonZero, n_bands=info["bands"], band_first=hx.rank, band_step=hx.world)  # noqa: E731
+        b0, b1 = info["bands"] * hx.rank // hx.world, info["bands"] * (hx.rank + 1) // hx.world
+        call = lambda: rast.mask_banded(path, tr, img, rb.FillRule.NonZero, n_bands=info["bands"], band_first=b0, band_count=b1 - b0)  # noqa: E731
         dt = time_calls(hx, call, max(2, min(4, steps)), 1)
         h2d, d2h = rast.last_transfer_bytes()
         e2e = {"value": round(info["total_pixels"] / dt / 1e6, 1), "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_call": round(dt * 1e3, 3),
-               "call": "rgpu_mask_banded_host(band_first = rank, band_step = ranks): host path in, this rank's bands rendered as one batch and copied "
-                       "into their rows of a pinned f32 host image of the whole canvas"}
+               "call": "rgpu_mask_banded_host on this rank's block of bands: host path in, the block rendered as one job and copied into its rows of a "
+                       "pinned f32 host image of the whole canvas"}
     elif name in ("c1", "c3"):
         # Scene::render + RGBA8 export through the host-buffer entry point: host paths in (H2D), pinned RGBA8 image out (D2H)
         from rasterize_b200 import assets as _assets, scene as rscene

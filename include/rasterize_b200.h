@@ -277,20 +277,20 @@ int rgpu_multi_fill_batch_host(rgpu_multi* m, const rgpu_path* all, const uint32
                                const double* trs, int fill_rule, const rgpu_paint* paint, uint32_t width, uint32_t height,
                                int out_format, void* out_host);
 /* `Rasterizer::mask` (src/rasterize.rs:299-311) of ONE path on a huge canvas, sharded by scanline bands: rows are
- * independent in the signed-difference rasterizer (src/rasterize.rs:421-469, 478-503), so the canvas is cut into
- * n_bands bands of rows (0 = 8 per device; cut points are multiples of 8 rows), band b goes to device b mod n_devices
- * (fine bands dealt round-robin balance both the raster work and the output bytes), every device flattens the path
- * with a band-local translate(0, -y0) — the reference's own y clipping then crops exactly — and copies its bands into
- * their rows of the host image.  `img` is a dense width x height image of f32 (elem_size 4, the device-native format)
- * or f64 (elem_size 8, the trait's `Scalar`); it does not have to be zero on entry (every pixel is written).
- * The result is bit-identical to the single-device rgpu_mask_f32 / rgpu_mask. */
+ * independent in the signed-difference rasterizer (src/rasterize.rs:421-469, 478-503), so the canvas is cut into n_bands
+ * bands of rows (0 = one per device; cut points are multiples of 8 rows), device d takes the contiguous block of bands
+ * [d * n_bands / n_devices, (d + 1) * n_bands / n_devices) as ONE job — equal rows are equal output bytes, which is what
+ * bounds the raster kernel — flattens the path with a band-local translate(0, -y0) (the reference's own y clipping then
+ * crops exactly) and copies its rows into the host image.  `img` is a dense width x height image of f32 (elem_size 4, the
+ * device-native format) or f64 (elem_size 8, the trait's `Scalar`); it does not have to be zero on entry (every pixel is
+ * written).  The result is bit-identical to the single-device rgpu_mask_f32 / rgpu_mask. */
 int rgpu_multi_mask_banded_host(rgpu_multi* m, const rgpu_path* path, const double tr[6], int fill_rule, void* img, size_t elem_size,
                                 size_t width, size_t height, uint32_t n_bands);
-/* The same band decomposition on ONE context (bands rendered as independent jobs of one batch); also what every worker
- * of rgpu_multi_mask_banded_host runs for its bands.  band_first / band_step select bands band_first, band_first +
- * band_step, ... of n_bands. */
+/* The same band decomposition on ONE context; also what every worker of rgpu_multi_mask_banded_host runs for its block.
+ * Renders bands [band_first, band_first + band_count) of n_bands (consecutive bands are one job, flattened once) into their
+ * rows of `img`; the other rows are not touched. */
 int rgpu_mask_banded_host(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill_rule, void* img, size_t elem_size,
-                          size_t width, size_t height, uint32_t n_bands, uint32_t band_first, uint32_t band_step);
+                          size_t width, size_t height, uint32_t n_bands, uint32_t band_first, uint32_t band_count);
 
 /* ---- plumbing ----------------------------------------------------------------------------------- */
 void* rgpu_stream(rgpu_ctx* ctx);  /* cudaStream_t the context launches on */

@@ -728,14 +728,15 @@ class GpuRasterizer:
         (`rgpu_fill_batch_host`).  `out` selects the format: f32 [n,H,W,4] LinColor, u8 [n,H,W,4] RGBA8, f32 [n,H,W] coverage."""
         return _fill_batch_host(ffi.lib().rgpu_fill_batch_host, self.ctx, self._check, batch, fill_rule, paint, width, height, out, trs)
 
-    def mask_banded(self, path: Path, tr, img: np.ndarray, fill_rule: FillRule, n_bands: int = 8, band_first: int = 0, band_step: int = 1) -> None:
-        """`Rasterizer::mask` as independent scanline bands (`rgpu_mask_banded_host`); img is dense f32 or f64 [H, W]."""
+    def mask_banded(self, path: Path, tr, img: np.ndarray, fill_rule: FillRule, n_bands: int = 8, band_first: int = 0, band_count: int | None = None) -> None:
+        """`Rasterizer::mask` of bands [band_first, band_first + band_count) of n_bands scanline bands (`rgpu_mask_banded_host`);
+        img is the dense f32 or f64 [H, W] image of the whole canvas."""
         if img.dtype not in (np.float32, np.float64) or not img.flags.c_contiguous or img.ndim != 2:
             raise TypeError("banded mask image must be dense float32 / float64 [H, W]")
         c = path._c()
         t = _as_tr(tr)
         self._check(ffi.lib().rgpu_mask_banded_host(self.ctx, C.byref(c), t.ctypes.data_as(C.POINTER(C.c_double)), int(fill_rule), img.ctypes.data,
-                                                    img.itemsize, img.shape[1], img.shape[0], n_bands, band_first, band_step))
+                                                    img.itemsize, img.shape[1], img.shape[0], n_bands, band_first, n_bands if band_count is None else band_count))
 
     def last_counts(self):
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()

@@ -328,7 +328,7 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
 }
 
 int rgpu_mask_banded_host(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill_rule, void* img, size_t elem_size, size_t width,
-                          size_t height, uint32_t n_bands, uint32_t band_first, uint32_t band_step) {
+                          size_t height, uint32_t n_bands, uint32_t band_first, uint32_t band_count) {
     if (!ctx || !tr) return RGPU_ERR_INVALID;
     CK(ctx, cudaSetDevice(ctx->device));
     if (elem_size != 4 && elem_size != 8) return fail(ctx, RGPU_ERR_INVALID, "elem_size must be 4 (f32) or 8 (f64)");
@@ -339,8 +339,7 @@ int rgpu_mask_banded_host(rgpu_ctx* ctx, const rgpu_path* path, const double tr[
     if (!img) return RGPU_ERR_INVALID;
     int rc = validate_path(ctx, path);
     if (rc) return rc;
-    if (n_bands == 0) n_bands = 8;
-    if (band_step == 0) band_step = 1;
+    if (n_bands == 0) n_bands = 1;
     n_bands = (uint32_t)std::min<size_t>(n_bands, (height + 7) / 8);
     auto cut = [&](uint32_t k) -> size_t {  // multiples of the raster tile height, like sharding.band_rows
         if (k >= n_bands) return height;
@@ -350,10 +349,10 @@ int rgpu_mask_banded_host(rgpu_ctx* ctx, const rgpu_path* path, const double tr[
     struct Band { size_t y0, rows, off; };
     std::vector<Band> bands;
     size_t rows_total = 0;
-    for (uint32_t b = band_first; b < n_bands; b += band_step) {
+    for (uint32_t b = band_first; b < n_bands && b - band_first < band_count; b++) {
         const size_t y0 = cut(b), y1 = std::max(cut(b), cut(b + 1));
         if (y1 > y0) {
-            // consecutive bands of this context are one job (flattened once): with band_step == 1 the whole canvas
+            // consecutive bands are one job (flattened once)
             if (!bands.empty() && bands.back().y0 + bands.back().rows == y0) bands.back().rows += y1 - y0;
             else bands.push_back({y0, y1 - y0, rows_total});
             rows_total += y1 - y0;
@@ -538,9 +537,11 @@ int rgpu_multi_mask_banded_host(rgpu_multi* m, const rgpu_path* path, const doub
                                 size_t height, uint32_t n_bands) {
     if (!m || m->ctxs.empty() || !tr) return RGPU_ERR_INVALID;
     const uint32_t nd = (uint32_t)m->ctxs.size();
-    if (n_bands == 0) n_bands = 8 * nd;
+    if (n_bands == 0) n_bands = nd;
+    n_bands = (uint32_t)std::min<size_t>(n_bands, std::max<size_t>((height + 7) / 8, 1));  // the clamp rgpu_mask_banded_host applies
     return multi_run(m, [&](size_t d) -> int {
-        return rgpu_mask_banded_host(m->ctxs[d], path, tr, fill_rule, img, elem_size, width, height, n_bands, (uint32_t)d, nd);
+        const uint32_t b0 = (uint32_t)((uint64_t)n_bands * d / nd), b1 = (uint32_t)((uint64_t)n_bands * (d + 1) / nd);
+        return rgpu_mask_banded_host(m->ctxs[d], path, tr, fill_rule, img, elem_size, width, height, n_bands, b0, b1 - b0);
     });
 }
 

@@ -175,11 +175,12 @@ def test_mask_banded_is_bit_identical_to_single_mask(rast, dtype):
             img = np.full((h, w), -3.0, dtype=dtype)
             rast.mask_banded(p, tr, img, rb.FillRule.NonZero, n_bands=n_bands)
             assert np.array_equal(img, whole), (name, n_bands)
-        # two "devices" dealing 16 bands round-robin into one image
+        # three "devices" with blocks of the 16 bands, into one image
         img = np.full((h, w), -3.0, dtype=dtype)
-        rast.mask_banded(p, tr, img, rb.FillRule.NonZero, n_bands=16, band_first=0, band_step=2)
+        rast.mask_banded(p, tr, img, rb.FillRule.NonZero, n_bands=16, band_first=5, band_count=6)
         assert (img == -3.0).any()
-        rast.mask_banded(p, tr, img, rb.FillRule.NonZero, n_bands=16, band_first=1, band_step=2)
+        rast.mask_banded(p, tr, img, rb.FillRule.NonZero, n_bands=16, band_first=0, band_count=5)
+        rast.mask_banded(p, tr, img, rb.FillRule.NonZero, n_bands=16, band_first=11, band_count=5)
         assert np.array_equal(img, whole), name
 
 
