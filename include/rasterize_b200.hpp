@@ -114,10 +114,105 @@ public:
     }
 };
 
-// `PathBuilder` (move_to / line_to / quad_to / cubic_to / close / build), src/path.rs:813-943.
-// arc_to is a host-side arc -> cubic conversion in the reference (src/path.rs:945-972) and stays there.
+// Elliptic arc in centre form and its conversion into cubics of at most a quarter turn: `EllipArc::new_param`
+// (src/ellipse.rs:40-96), `EllipArcCubicIter` (src/ellipse.rs:167-214), `Point::angle_between` (src/geometry.rs:186-203).
+// A `Path` only ever stores lines, quads and cubics (src/curve.rs:905-909): arcs are converted here, on the host, when the
+// path is built — the flatten kernel never sees one.  IEEE semantics are kept as in Rust: a zero sweep gives a
+// NaN step and no cubic at all.
+struct EllipArc {
+    Point center;
+    Scalar rx, ry, phi, eta, eta_delta;
+    static bool angle_between(Point a, Point b, Scalar& out) {
+        const Scalar lengths = std::hypot(a.x, a.y) * std::hypot(b.x, b.y);
+        if (lengths < EPSILON) return false;
+        Scalar c = (a.x * b.x + a.y * b.y) / lengths;
+        c = c < -1.0 ? -1.0 : (c > 1.0 ? 1.0 : c);
+        const Scalar angle = std::acos(c);
+        out = (a.x * b.y - a.y * b.x < 0.0) ? -angle : angle;
+        return true;
+    }
+    static Scalar rem_euclid(Scalar x, Scalar rhs) {
+        const Scalar r = std::fmod(x, rhs);
+        return r < 0.0 ? r + std::fabs(rhs) : r;
+    }
+    static bool new_param(Point src, Point dst, Scalar rx, Scalar ry, Scalar x_axis_rot, bool large_flag, bool sweep_flag, EllipArc& out) {
+        constexpr Scalar PI = 3.14159265358979323846264338327950288;
+        rx = std::fabs(rx);
+        ry = std::fabs(ry);
+        const Scalar phi = x_axis_rot * PI / 180.0;
+        const Point p1 = Transform::new_rotate(-phi).apply({0.5 * (src.x - dst.x), 0.5 * (src.y - dst.y)});
+        const Scalar x1 = p1.x, y1 = p1.y;
+        const Scalar ax = x1 / rx, ay = y1 / ry;
+        const Scalar s = ax * ax + ay * ay;
+        if (s > 1.0) {
+            const Scalar sq = std::sqrt(s);
+            rx = rx * sq;
+            ry = ry * sq;
+        }
+        const Scalar rxry = rx * ry, rxy1 = rx * y1, ryx1 = ry * x1;
+        Scalar q = rxry * rxry / (rxy1 * rxy1 + ryx1 * ryx1) - 1.0;
+        q = (q > 0.0 || q != q) ? q : 0.0;  // f64::max(0.0): NaN.max(0.0) is 0.0 in Rust
+        if (q != q) q = 0.0;
+        Scalar sq = std::sqrt(q);
+        sq = (large_flag == sweep_flag) ? -sq : sq;
+        const Scalar cx = sq * (rx * y1 / ry), cy = sq * (-ry * x1 / rx);
+        const Point rc = Transform::new_rotate(phi).apply({cx, cy});
+        const Point center{rc.x + 0.5 * (dst.x + src.x), rc.y + 0.5 * (dst.y + src.y)};
+        Scalar eta, ed;
+        if (!angle_between({1.0, 0.0}, {(x1 - cx) / rx, (y1 - cy) / ry}, eta)) return false;
+        if (!angle_between({(x1 - cx) / rx, (y1 - cy) / ry}, {(-x1 - cx) / rx, (-y1 - cy) / ry}, ed)) return false;
+        // NaN angles (coincident end points, a zero radius): the reference's cubic iterator then never terminates
+        // (`segment_index > NaN` is false for ever, src/ellipse.rs:198-201); treated like the degenerate arcs it does detect
+        if (eta != eta || ed != ed) return false;
+        Scalar eta_delta = rem_euclid(ed, 2.0 * PI);
+        if (!sweep_flag && eta_delta > 0.0) eta_delta = eta_delta - 2.0 * PI;
+        else if (sweep_flag && eta_delta < 0.0) eta_delta = eta_delta + 2.0 * PI;
+        out = EllipArc{center, rx, ry, phi, eta, eta_delta};
+        return true;
+    }
+    template <class F>  // f(p0, p1, p2, p3) for every cubic
+    void to_cubics(F f) const {
+        constexpr Scalar PI = 3.14159265358979323846264338327950288;
+        const Transform phi_tr = Transform::new_rotate(phi);
+        Scalar segment_count = std::ceil(std::fabs(eta_delta) / (PI / 2.0));
+        const Scalar segment_delta = eta_delta / segment_count;
+        Scalar segment_index = 0.0;
+        segment_count = segment_count - 1.0;
+        auto at = [&](Scalar alpha, Point& a, Point& d) {
+            const Scalar sn = std::sin(alpha), cs = std::cos(alpha);
+            const Point t = phi_tr.apply({rx * cs, ry * sn});
+            a = {t.x + center.x, t.y + center.y};
+            d = phi_tr.apply({-rx * sn, ry * cs});
+        };
+        while (!(segment_index > segment_count)) {
+            const Scalar eta_1 = eta + segment_delta * segment_index;
+            const Scalar eta_2 = eta_1 + segment_delta;
+            segment_index += 1.0;
+            const Scalar tn = std::tan((eta_2 - eta_1) / 2.0);
+            const Scalar sq = std::sqrt(4.0 + 3.0 * (tn * tn));
+            const Scalar alpha = std::sin(eta_2 - eta_1) * (sq - 1.0) / 3.0;
+            Point p0, d0, p3, d3;
+            at(eta_1, p0, d0);
+            at(eta_2, p3, d3);
+            f(p0, Point{p0.x + alpha * d0.x, p0.y + alpha * d0.y}, Point{p3.x - alpha * d3.x, p3.y - alpha * d3.y}, p3);
+        }
+    }
+};
+
+// `PathBuilder` (move_to / line_to / quad_to / cubic_to / arc_to / close / build), src/path.rs:813-972.
 class PathBuilder {
 public:
+    // `PathBuilder::arc_to` (src/path.rs:945-972): SVG endpoint arc -> cubics stored in the path; a degenerate arc is a line
+    PathBuilder& arc_to(Point radii, Scalar x_axis_rot, bool large, bool sweep, Point p) {
+        EllipArc arc;
+        if (!EllipArc::new_param(pos_, p, radii.x, radii.y, x_axis_rot, large, sweep, arc)) return line_to(p);
+        arc.to_cubics([&](Point p0, Point p1, Point p2, Point p3) {
+            push(p0); push(p1); push(p2); push(p3);
+            path_.kinds.push_back(4);
+        });
+        pos_ = p;
+        return *this;
+    }
     PathBuilder& move_to(Point p) { finish(false); pos_ = p; return *this; }
     PathBuilder& close() { finish(true); return *this; }
     PathBuilder& line_to(Point p) {

@@ -233,8 +233,95 @@ class PathBatch:
         return self.flat.input_bytes()
 
 
+def _angle_between(a, b):
+    """`Point::angle_between` (src/geometry.rs:186-203); None when a vector has (almost) no length."""
+    lengths = math.hypot(a[0], a[1]) * math.hypot(b[0], b[1])
+    if lengths < EPSILON:
+        return None
+    c = np.float64(a[0] * b[0] + a[1] * b[1]) / np.float64(lengths)
+    if c != c:
+        return float("nan")
+    angle = math.acos(min(max(float(c), -1.0), 1.0))
+    return -angle if (a[0] * b[1] - a[1] * b[0]) < 0.0 else angle
+
+
+def _rotate(phi, p):
+    """`Transform::new_rotate(phi).apply(p)` (src/geometry.rs:363-367, 409-412)"""
+    s, c = math.sin(phi), math.cos(phi)
+    return (p[0] * c + p[1] * -s + 0.0, p[0] * s + p[1] * c + 0.0)
+
+
+def ellip_arc_cubics(src, dst, rx, ry, x_axis_rot, large_flag, sweep_flag):
+    """`EllipArc::new_param(..).to_cubics()` (src/ellipse.rs:40-96, 167-214): the cubics (4 points each) of an SVG endpoint arc,
+    or None when the arc is degenerate (`arc_to` then draws a line).  IEEE semantics as in Rust (numpy scalars: x / 0 = inf,
+    0 / 0 = NaN): a zero sweep gives a NaN step and NO cubic."""
+    f = np.float64
+    with np.errstate(all="ignore"):
+        rx, ry = f(abs(rx)), f(abs(ry))
+        phi = x_axis_rot * math.pi / 180.0
+        x1, y1 = _rotate(-phi, (0.5 * (src[0] - dst[0]), 0.5 * (src[1] - dst[1])))
+        x1, y1 = f(x1), f(y1)
+        ax, ay = x1 / rx, y1 / ry
+        s = ax * ax + ay * ay
+        if s > 1.0:
+            sq = np.sqrt(s)
+            rx, ry = rx * sq, ry * sq
+        rxry, rxy1, ryx1 = rx * ry, rx * y1, ry * x1
+        q = rxry * rxry / (rxy1 * rxy1 + ryx1 * ryx1) - 1.0
+        q = q if q > 0.0 else f(0.0)  # f64::max(0.0); NaN.max(0.0) == 0.0
+        sq = np.sqrt(q)
+        sq = -sq if large_flag == sweep_flag else sq
+        cx, cy = sq * (rx * y1 / ry), sq * (-ry * x1 / rx)
+        rc = _rotate(phi, (float(cx), float(cy)))
+        center = (rc[0] + 0.5 * (dst[0] + src[0]), rc[1] + 0.5 * (dst[1] + src[1]))
+        v1 = (float((x1 - cx) / rx), float((y1 - cy) / ry))
+        v2 = (float((-x1 - cx) / rx), float((-y1 - cy) / ry))
+        eta = _angle_between((1.0, 0.0), v1)
+        if eta is None:
+            return None
+        ed = _angle_between(v1, v2)
+        if ed is None:
+            return None
+        if eta != eta or ed != ed:
+            # NaN angles (coincident end points, a zero radius): the reference's cubic iterator then never terminates
+            # (`segment_index > NaN` is false for ever, src/ellipse.rs:198-201).  Treated like the degenerate arcs it does detect.
+            return None
+        two_pi = 2.0 * math.pi
+        eta_delta = math.fmod(ed, two_pi)
+        if eta_delta < 0.0:
+            eta_delta += two_pi
+        if not sweep_flag and eta_delta > 0.0:
+            eta_delta -= two_pi
+        elif sweep_flag and eta_delta < 0.0:
+            eta_delta += two_pi
+        rx, ry = float(rx), float(ry)
+        count = f(math.ceil(abs(eta_delta) / (math.pi / 2.0)))
+        delta = f(eta_delta) / count
+        index, count = 0.0, float(count) - 1.0
+
+        def at(alpha):
+            sn, cs = math.sin(alpha), math.cos(alpha)
+            a = _rotate(phi, (rx * cs, ry * sn))
+            return (a[0] + center[0], a[1] + center[1]), _rotate(phi, (-rx * sn, ry * cs))
+
+        out = []
+        delta = float(delta)
+        while not (index > count):
+            eta_1 = eta + delta * index
+            eta_2 = eta_1 + delta
+            index += 1.0
+            tn = math.tan((eta_2 - eta_1) / 2.0)
+            sq = math.sqrt(4.0 + 3.0 * (tn * tn))
+            alpha = math.sin(eta_2 - eta_1) * (sq - 1.0) / 3.0
+            p0, d0 = at(eta_1)
+            p3, d3 = at(eta_2)
+            out.append((p0, (p0[0] + alpha * d0[0], p0[1] + alpha * d0[1]), (p3[0] - alpha * d3[0], p3[1] - alpha * d3[1]), p3))
+        return out
+
+
 class PathBuilder:
-    """`PathBuilder` (src/path.rs:800-1056) without arcs (arc -> cubic conversion stays on the Rust host side)."""
+    """`PathBuilder` (src/path.rs:800-1056).  Arcs are converted to cubics here, on the host, exactly as the reference's
+    `arc_to` does (a `Path` stores only lines, quads and cubics): the device never sees an arc."""
 
     def __init__(self):
         self.position = (0.0, 0.0)
@@ -285,6 +372,17 @@ class PathBuilder:
         self._pts += [self.position, p1, p2, p3]
         self._kinds.append(4)
         self.position = p3
+        return self
+
+    def arc_to(self, radii, x_axis_rot: float, large: bool, sweep: bool, p) -> "PathBuilder":  # src/path.rs:945-972
+        p = (float(p[0]), float(p[1]))
+        cubics = ellip_arc_cubics(self.position, p, float(radii[0]), float(radii[1]), float(x_axis_rot), bool(large), bool(sweep))
+        if cubics is None:
+            return self.line_to(p)
+        for c in cubics:
+            self._pts += list(c)
+            self._kinds.append(4)
+        self.position = p
         return self
 
     def build(self) -> Path:
