@@ -13,11 +13,13 @@
 //     popc), nodes that are still not flat two levels below the slot root (a tenth of a glyph's level-5 nodes) go to
 //     a small per-warp node queue and are expanded later with one lane per child; anything deeper takes a stack-free
 //     walk by path bits (the next node of the depth-first order is recomputed from its subtree root);
-//   * a warp's line queue is drained once per round (about 120 lines of a glyph) in converged stages: lane = line
-//     (orientation, slope, row range, a warp prefix sum over the row counts), then lane = (line, row) span.  A span
-//     over at most two columns (93 % of a glyph's spans) is three shared-memory integer reductions computed without a
-//     branch; the few wider ones are set aside and done together at the end of the pass, so the rare path does not
-//     run in every round with two lanes;
+//   * a warp's line queue is drained once per round (about 120 lines of a glyph), lane = line: orientation, slope and
+//     row range, then the line's rows in a loop whose trip count is the warp's longest line (a glyph's lines cover 2.0
+//     rows on average, at most 4 for 99 %).  A span over at most two columns (93 % of a glyph's spans) is three
+//     shared-memory integer reductions computed without a branch; the few wider ones are set aside and done together
+//     at the end of the pass, so the rare path does not run in every iteration with two lanes.  (A span list built by
+//     a warp prefix sum and processed with lane = span keeps more lanes busy but costs as many instructions again for
+//     its bookkeeping: 0.96 vs 0.87 ms per 20 000 glyphs.);
 //   * there are two block barriers per job (after staging, before the row scan);
 //   * end points of a small canvas are below 128, where f32 resolves 7.6e-6: a queued line's spans are evaluated in
 //     f32 (lines that leave the canvas columns or lie far outside its rows take the f64 path of the tiled kernels,
@@ -49,8 +51,7 @@ constexpr int kGDepth = 3;                                      // slot cut: 8 s
 constexpr int kGSlots = 1 << kGDepth;
 constexpr int kGCurves = kGThreads / kGSlots;                   // curves staged in shared memory at a time
 constexpr int kGQueue = 160;                                    // per-warp line queue: a round of 32 slots leaves ~120 lines of a glyph
-constexpr int kGSpanRows = 8;                                   // lines over more rows are done by their own lane
-constexpr int kGIds = 512;                                      // span ids of one accumulation pass (>= 2 batches of 32 lines x 8 rows)
+constexpr int kGIds = 8;                                        // per-warp scratch words (the count of deferred wide spans)
 constexpr int kGWide = 64;                                      // spans over three or more columns, deferred to the end of a pass
 constexpr int kGDeep = 16;                                      // per-warp queue of nodes not flat at level kGDepth + 2
 constexpr int kGMaxBelow = kSlotDepth + kMaxStack - kGDepth - 3;  // walk_deep starts three levels below a slot root
@@ -172,7 +173,8 @@ constexpr size_t kOffDq = kOffLineq + sizeof(float4) * kGWarps * kGQueue;   // p
 constexpr size_t kOffRoots = kOffDq + sizeof(double) * kGWarps * kGDeep * 8;  // transformed control points: [20][4] x, then y
 constexpr size_t kOffIds = kOffRoots + sizeof(double) * kGCurves * 4 * 2;
 constexpr size_t kOffWide = kOffIds + sizeof(unsigned short) * kGWarps * kGIds;
-constexpr size_t kOffDkind = kOffWide + sizeof(unsigned short) * kGWarps * kGWide;
+constexpr size_t kOffWideY = kOffWide + sizeof(float4) * kGWarps * kGWide;
+constexpr size_t kOffDkind = kOffWideY + kGWarps * kGWide;
 constexpr size_t kOffMeta = kOffDkind + 16 * ((kGWarps * kGDeep + 15) / 16);
 constexpr size_t kOffRowtot = kOffMeta + 48;
 constexpr size_t kOffJob = kOffRowtot + sizeof(int) * 2 * kSmMaxH;
@@ -187,7 +189,8 @@ extern __shared__ __align__(16) unsigned char sm_raw[];
 #define s_x (reinterpret_cast<double(*)[4]>(sm_raw + kOffRoots))
 #define s_y (reinterpret_cast<double(*)[4]>(sm_raw + kOffRoots + sizeof(double) * kGCurves * 4))
 #define s_ids (reinterpret_cast<unsigned short(*)[kGIds]>(sm_raw + kOffIds))
-#define s_wide (reinterpret_cast<unsigned short(*)[kGWide]>(sm_raw + kOffWide))
+#define s_wide_p (reinterpret_cast<float4(*)[kGWide]>(sm_raw + kOffWide))
+#define s_wide_y (reinterpret_cast<unsigned char(*)[kGWide]>(sm_raw + kOffWideY))
 #define s_dkind (reinterpret_cast<unsigned char(*)[kGDeep]>(sm_raw + kOffDkind))
 #define s_meta (reinterpret_cast<unsigned char*>(sm_raw + kOffMeta))
 #define s_rowtot (reinterpret_cast<int*>(sm_raw + kOffRowtot))
@@ -267,94 +270,69 @@ __device__ __forceinline__ void span_wide(const Span& s, const Canvas& cv) {
 
 // Accumulate the first `count` lines of this warp's queue.  Every end point lies inside the canvas columns [0, wc] and
 // within (-64, 128) of its rows, so the clipping branches of signed_difference_line (x > width, x < 0) cannot trigger.
-// Stage 1, lane = line (batches of 32): orientation, slope and row range (src/rasterize.rs:400-421); the prepared line
-// replaces its queue entry and its (line, row) spans are listed through a warp prefix sum.  Stage 2, lane = span.
-// Spans over three or more columns are set aside and done at the end.
+// Lane = line, 32 at a time: orientation, slope and row range (src/rasterize.rs:400-421), then the rows of the line in a loop
+// whose trip count is the warp's longest line (a glyph's lines cover 2.0 rows on average, 4 or fewer for 99 %: the loop runs
+// about four times per round with predicated lanes, and there is no span list to build and read back).  Spans over three or
+// more columns (7 %) are set aside with their prepared line and done together at the end of the pass.
+// Measured and not kept: lines over one or two rows done in two predicated steps and the longer ones compacted for a second
+// pass (more code, same instruction count: 0.93 vs 0.87 ms per 20 000 glyphs).
 __device__ __noinline__ void accumulate_warp(const int count, const Canvas cv) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float4* __restrict__ q = s_lineq[warp];
-    unsigned short* __restrict__ ids = s_ids[warp];
-    unsigned short* __restrict__ wide = s_wide[warp];
-    const unsigned lt_mask = (1u << lane) - 1u;
-    int n_wide = 0;
+    const float4* __restrict__ q = s_lineq[warp];
+    float4* __restrict__ wide_p = s_wide_p[warp];
+    unsigned char* __restrict__ wide_y = s_wide_y[warp];
+    int* const n_wide = reinterpret_cast<int*>(s_ids[warp]);  // count of deferred wide spans
+    if (lane == 0) *n_wide = 0;
+    __syncwarp();
     auto do_wide = [&]() {
         __syncwarp();
-        if (lane < n_wide) {
-            const int id = wide[lane];
-            span_wide(span_head(q[id >> 6], id & 63, cv), cv);
-        }
-        if (lane + 32 < n_wide) {
-            const int id = wide[lane + 32];
-            span_wide(span_head(q[id >> 6], id & 63, cv), cv);
-        }
-        n_wide = 0;
+        const int nw = min(*n_wide, kGWide);
+        __syncwarp();
+        for (int k = lane; k < nw; k += 32) span_wide(span_head(wide_p[k], wide_y[k], cv), cv);
+        if (lane == 0) *n_wide = 0;
         __syncwarp();
     };
-    int b0 = 0;
-    while (b0 < count) {
-        int total = 0;
-        while (b0 < count && total + 32 * kGSpanRows <= kGIds) {
-            const int i = b0 + lane;
-            int n = 0, rb = 0;
-            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < count) {
-                const float4 l = q[i];
-                float ax = l.x, ay = l.y, bx = l.z, by = l.w;
-                float dirf = 1.0f;
-                if (ay > by) {
-                    float t;
-                    t = ax; ax = bx; bx = t;
-                    t = ay; ay = by; by = t;
-                    dirf = -1.0f;
-                }
-                if (ay != by) {
-                    p = make_float4(ax, ay, copysignf(by, dirf), __fdividef(bx - ax, by - ay));
-                    rb = (int)fmaxf(ay, 0.0f);
-                    n = max(min(cv.H, (int)ceilf(by)) - rb, 0);  // lines above or below the canvas: no rows
-                }
-                q[i] = p;
+    for (int b0 = 0; b0 < count; b0 += 32) {
+        const int i = b0 + lane;
+        int n = 0, rb = 0;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < count) {
+            const float4 l = q[i];
+            float ax = l.x, ay = l.y, bx = l.z, by = l.w;
+            float dirf = 1.0f;
+            if (ay > by) {
+                float t;
+                t = ax; ax = bx; bx = t;
+                t = ay; ay = by; by = t;
+                dirf = -1.0f;
             }
-            const bool listed = n <= kGSpanRows;
-            int incl = listed ? n : 0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int nb = __shfl_up_sync(kFull, incl, o);
-                if (lane >= o) incl += nb;
+            if (ay != by) {
+                p = make_float4(ax, ay, copysignf(by, dirf), __fdividef(bx - ax, by - ay));
+                rb = (int)fmaxf(ay, 0.0f);
+                n = max(min(cv.H, (int)ceilf(by)) - rb, 0);  // lines above or below the canvas: no rows
             }
-            if (listed) {
-                int at = total + incl - n;
-                for (int k = 0; k < n; k++) ids[at++] = (unsigned short)((i << 6) | (rb + k));
-            } else {  // a line over many rows (not in a glyph): its own lane walks them
-                for (int k = 0; k < n; k++) {
-                    const Span s = span_head(p, rb + k, cv);
-                    if (s.n <= 2) span_narrow(s, cv); else span_wide(s, cv);
-                }
-            }
-            total += __shfl_sync(kFull, incl, 31);
-            b0 += 32;
         }
-        __syncwarp();
-        for (int s0 = 0; s0 < total; s0 += 32) {
-            const int si = s0 + lane;
-            bool is_wide = false;
-            int id = 0;
-            if (si < total) {
-                id = ids[si];
-                const Span s = span_head(q[id >> 6], id & 63, cv);
-                is_wide = s.n > 2;
-                if (!is_wide) span_narrow(s, cv);
-            }
-            const unsigned mw = __ballot_sync(kFull, is_wide);
-            if (mw) {
-                if (is_wide) wide[n_wide + __popc(mw & lt_mask)] = (unsigned short)id;
-                n_wide += __popc(mw);
-                if (n_wide > kGWide - 32) do_wide();
+        const int n_max = __reduce_max_sync(kFull, n);
+        for (int k = 0; k < n_max; k++) {
+            if (k < n) {
+                const Span s = span_head(p, rb + k, cv);
+                if (s.n <= 2) {
+                    span_narrow(s, cv);
+                } else {
+                    const int slot = atomicAdd(n_wide, 1);
+                    if (slot < kGWide) {
+                        wide_p[slot] = p;
+                        wide_y[slot] = (unsigned char)(rb + k);
+                    } else {
+                        span_wide(s, cv);  // list full: here and now
+                    }
+                }
             }
         }
         __syncwarp();
+        if (*n_wide > kGWide - 32) do_wide();  // warp-uniform: every lane reads the same word after the loop
     }
-    if (n_wide) do_wide();
-    __syncwarp();
+    do_wide();
 }
 
 // rare paths, kept out of line so that their registers do not count against the flatten walk
