@@ -46,11 +46,16 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(workload: str):
-    """dram bytes per raster launch from the committed ncu --set full capture, if one exists for this workload."""
+def recorded_traffic(workload: str, out_bytes=None):
+    """dram bytes per raster launch from the committed ncu --set full capture, if one exists for this workload.  The capture is of
+    the one-GPU launch; a rank that renders a shard of it (N > 1) gets the capture scaled by its share of the output bytes."""
     p = os.path.join(ROOT, "profiles", "raster_traffic.json")
     try:
-        return float(json.load(open(p))[workload]["dram_bytes_per_launch"])
+        e = json.load(open(p))[workload]
+        t = float(e["dram_bytes_per_launch"])
+        if out_bytes and e.get("out_bytes_per_launch"):
+            t *= out_bytes / float(e["out_bytes_per_launch"])
+        return t
     except Exception:
         return None
 
@@ -404,7 +409,7 @@ def measure(hx: Harness, name: str, steps: int, warmup: int, with_cpu: bool, sam
                   name, "raster_kernel (K3: accumulate + row scan + fill rule + store)")
     roofline = {
         "bound": "hbm", "kernel": kernel, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-        "peak_source": peak_src, "traffic": recorded_traffic(name + ("_mask" if name == "c4" and os.environ.get("RB_C4_MASK") else "")),
+        "peak_source": peak_src, "traffic": recorded_traffic(name + ("_mask" if name == "c4" and os.environ.get("RB_C4_MASK") else ""), info["out_bytes"]),
         "algorithmic_bytes_per_launch": info["out_bytes"], "kernel_ms": round(float(stage_ms[2]), 5),
         "stage_ms": {"flatten_and_bin": round(float(stage_ms[0]), 5), "two_pass_only_scan_and_emit": round(float(stage_ms[1]), 5),
                      "raster": round(float(stage_ms[2]), 5)},
