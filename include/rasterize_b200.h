@@ -135,6 +135,30 @@ int rgpu_render_scene_host(rgpu_ctx* ctx, const rgpu_scene_fill* fills, size_t n
 int rgpu_path_upload(rgpu_ctx* ctx, const rgpu_path* path, rgpu_dpath** out);
 void rgpu_path_free(rgpu_ctx* ctx, rgpu_dpath* p);
 
+/* `StrokeStyle` (src/path.rs:121-136), `LineJoin` (:78-93, the miter limit lives in `Miter(limit)`, default 4.0) and
+ * `LineCap` (:103-110). */
+enum { RGPU_JOIN_MITER = 0, RGPU_JOIN_BEVEL = 1, RGPU_JOIN_ROUND = 2 };
+enum { RGPU_CAP_BUTT = 0, RGPU_CAP_SQUARE = 1, RGPU_CAP_ROUND = 2 };
+typedef struct {
+    double width;
+    double miter_limit; /* used by RGPU_JOIN_MITER only */
+    int32_t line_join, line_cap;
+} rgpu_stroke_style;
+/* `Path::stroke` (src/path.rs:374-415; `stroke_segment` :692-706, `stroke_close` :708-732; curve offsets, joins and caps
+ * src/curve.rs:978-1078, 1283-1433) computed on the device: the host path goes up once, the outline of the stroke comes
+ * back as a device-resident path that every entry point taking an `rgpu_dpath` accepts (config 5's pre-step without a
+ * round trip).  One thread per (segment, direction) unit of the reference's walk, three passes (pieces, joins, emit), the
+ * segments in the reference's order.  With Miter / Bevel joins and Butt / Square caps the segment list is bit-identical to
+ * the reference's; round joins and caps go through sin / cos / tan / acos and agree to a few ulp.
+ * Deviations: a cubic whose four control points coincide makes the reference panic (`ends`, src/curve.rs:660-666) and is
+ * treated here as having the tangent of its first two points; NaN input that would spin the reference's arc iterator for
+ * ever yields no arc. */
+int rgpu_path_stroke(rgpu_ctx* ctx, const rgpu_path* path, const rgpu_stroke_style* style, rgpu_dpath** out);
+/* Size of a device path made by rgpu_path_upload / rgpu_path_stroke, and its download in the `rgpu_path` encoding:
+ * points[2 * n_points], kinds[n_segments], subpath_offsets[n_subpaths + 1], closed[n_subpaths]. */
+int rgpu_dpath_info(const rgpu_dpath* p, uint32_t* n_points, uint32_t* n_segments, uint32_t* n_subpaths);
+int rgpu_dpath_download(rgpu_ctx* ctx, const rgpu_dpath* p, double* points, uint8_t* kinds, uint32_t* subpath_offsets, uint8_t* closed);
+
 /* One fill job of a batch.  `canvas` is a DEVICE pointer; the job covers the `width` x `height` window whose
  * top-left element is canvas[origin] with `row_stride` elements between rows (elements = f32 for masks,
  * 4 x f32 for colour).  This is the device form of `Path::fill` on a `view_mut` sub-image

@@ -114,6 +114,24 @@ public:
     }
 };
 
+// `LineJoin` (src/path.rs:78-93), `LineCap` (:103-110), `StrokeStyle` (:121-136)
+enum class LineJoin : int { Miter = RGPU_JOIN_MITER, Bevel = RGPU_JOIN_BEVEL, Round = RGPU_JOIN_ROUND };
+enum class LineCap : int { Butt = RGPU_CAP_BUTT, Square = RGPU_CAP_SQUARE, Round = RGPU_CAP_ROUND };
+struct StrokeStyle {
+    Scalar width = 1.0;
+    LineJoin line_join = LineJoin::Miter;
+    Scalar miter_limit = 4.0;  // `LineJoin::Miter(limit)`, default 4.0
+    LineCap line_cap = LineCap::Butt;
+    rgpu_stroke_style ffi() const {
+        rgpu_stroke_style s;
+        s.width = width;
+        s.miter_limit = miter_limit;
+        s.line_join = (int32_t)line_join;
+        s.line_cap = (int32_t)line_cap;
+        return s;
+    }
+};
+
 // Elliptic arc in centre form and its conversion into cubics of at most a quarter turn: `EllipArc::new_param`
 // (src/ellipse.rs:40-96), `EllipArcCubicIter` (src/ellipse.rs:167-214), `Point::angle_between` (src/geometry.rs:186-203).
 // A `Path` only ever stores lines, quads and cubics (src/curve.rs:905-909): arcs are converted here, on the host, when the
@@ -328,6 +346,25 @@ public:
         check(rc);
         lines.resize(4 * n);
         return lines;
+    }
+    // `Path::stroke(style)` (src/path.rs:374-415), computed on the device and returned as a host `Path`.  Callers that go
+    // on to rasterize the outline keep it on the device instead: rgpu_path_stroke hands back an `rgpu_dpath`.
+    Path stroke(const Path& path, const StrokeStyle& style) {
+        const rgpu_path p = path.ffi();
+        const rgpu_stroke_style st = style.ffi();
+        rgpu_dpath* dp = nullptr;
+        check(rgpu_path_stroke(ctx_, &p, &st, &dp));
+        uint32_t n_pts = 0, n_seg = 0, n_sub = 0;
+        rgpu_dpath_info(dp, &n_pts, &n_seg, &n_sub);
+        Path out;
+        out.points.resize(2 * (size_t)n_pts);
+        out.kinds.resize(n_seg);
+        out.subpath_offsets.resize((size_t)n_sub + 1);
+        out.closed.resize(n_sub);
+        const int rc = rgpu_dpath_download(ctx_, dp, out.points.data(), out.kinds.data(), out.subpath_offsets.data(), out.closed.data());
+        rgpu_path_free(ctx_, dp);
+        check(rc);
+        return out;
     }
     // One Fill node as the Fill arm of `Pipeline::render_rec` sets it up (src/scene.rs:407-430): `tr` = align * node
     // transform, (x, y, width, height) = the `view_mut` window of the layer.

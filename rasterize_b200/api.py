@@ -29,6 +29,32 @@ class FillRule(enum.IntEnum):
     EvenOdd = 1
 
 
+class LineJoin(enum.IntEnum):
+    """`LineJoin` (src/path.rs:78-93); the miter limit of `Miter(limit)` lives in `StrokeStyle.miter_limit`."""
+    Miter = 0
+    Bevel = 1
+    Round = 2
+
+
+class LineCap(enum.IntEnum):
+    """`LineCap` (src/path.rs:103-110)"""
+    Butt = 0
+    Square = 1
+    Round = 2
+
+
+@dataclass
+class StrokeStyle:
+    """`StrokeStyle` (src/path.rs:121-136); defaults as `LineJoin::default()` = `Miter(4.0)` and `LineCap::default()` = `Butt`."""
+    width: float
+    line_join: LineJoin = LineJoin.Miter
+    miter_limit: float = 4.0
+    line_cap: LineCap = LineCap.Butt
+
+    def _c(self) -> "ffi.CStrokeStyle":
+        return ffi.CStrokeStyle(float(self.width), float(self.miter_limit), int(self.line_join), int(self.line_cap))
+
+
 class Units(enum.IntEnum):
     UserSpaceOnUse = 0
     BoundingBox = 1
@@ -488,15 +514,38 @@ def paint_from_desc(d: dict):
 
 # ---- device objects -------------------------------------------------------------------------------------
 class DevicePath:
-    """Device-resident path (`rgpu_dpath`)."""
+    """Device-resident path (`rgpu_dpath`): an uploaded host path, or (`stroke=`) the outline of its stroke computed on the
+    device (`Path::stroke`, src/path.rs:374-415), which never visits the host unless `download()` is called."""
 
-    def __init__(self, rast: "GpuRasterizer", path: Path):
+    def __init__(self, rast: "GpuRasterizer", path: Path, stroke: "StrokeStyle | None" = None):
         self.rast = rast
-        self.path = path
+        self.path = path if stroke is None else None
         h = C.c_void_p()
         c = path._c()
-        rast._check(ffi.lib().rgpu_path_upload(rast.ctx, C.byref(c), C.byref(h)))
+        if stroke is None:
+            rast._check(ffi.lib().rgpu_path_upload(rast.ctx, C.byref(c), C.byref(h)))
+        else:
+            st = stroke._c()
+            rast._check(ffi.lib().rgpu_path_stroke(rast.ctx, C.byref(c), C.byref(st), C.byref(h)))
         self.h = h
+
+    def counts(self) -> tuple[int, int, int]:
+        """(n_points, n_segments, n_subpaths)"""
+        n = [C.c_uint32() for _ in range(3)]
+        self.rast._check(ffi.lib().rgpu_dpath_info(self.h, *[C.byref(v) for v in n]))
+        return tuple(v.value for v in n)
+
+    def download(self) -> Path:
+        """The device path as a host `Path` (for a stroked path: what `Path::stroke` returns)."""
+        n_pts, n_seg, n_sub = self.counts()
+        pts = np.zeros((n_pts, 2), dtype=np.float64)
+        kinds = np.zeros(n_seg, dtype=np.uint8)
+        sp = np.zeros(n_sub + 1, dtype=np.uint32)
+        closed = np.zeros(n_sub, dtype=np.uint8)
+        self.rast._check(ffi.lib().rgpu_dpath_download(self.rast.ctx, self.h, pts.ctypes.data_as(C.POINTER(C.c_double)),
+                                                       kinds.ctypes.data_as(C.POINTER(C.c_uint8)), sp.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                       closed.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return Path(pts, kinds, sp, closed)
 
     def free(self):
         if self.h:
@@ -717,6 +766,11 @@ class GpuRasterizer:
     # -- device-resident API ---------------------------------------------------------------------------
     def upload(self, path: Path) -> DevicePath:
         return DevicePath(self, path)
+
+    def stroke(self, path: Path, style: StrokeStyle) -> DevicePath:
+        """`Path::stroke` (src/path.rs:374-415) on the device: the outline as a device-resident path, usable wherever an
+        uploaded path is (`Job.path`); `.download()` gives the host `Path` the reference returns."""
+        return DevicePath(self, path, stroke=style)
 
     def _cjobs(self, jobs: Iterable[Job]):
         jobs = list(jobs)

@@ -9,7 +9,9 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "librasterize_b200.so"
-SOURCES = ["flatten.cu", "scan.cu", "raster.cu", "scene.cu", "small.cu", "compose.cu", "context.cu"]
+SOURCES = ["flatten.cu", "scan.cu", "raster.cu", "scene.cu", "small.cu", "compose.cu", "stroke.cu", "context.cu"]
+# stroke.cu restates f64 expressions of the reference with plain operators: no multiply-add contraction there
+SOURCE_FLAGS = {"stroke.cu": ["--fmad=false"]}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
@@ -41,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     extra = os.environ.get("RGPU_NVCC_EXTRA", "").split()  # tuning builds, e.g. -DRGPU_FLAT_MINB=9
     for src in SOURCES:
         obj = objdir / (src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *SOURCE_FLAGS.get(src, []), *extra, "-c", str(CSRC / src), "-o", str(obj)]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

@@ -26,6 +26,7 @@ struct rgpu_dpath {
     uint2* items = nullptr;         // reference order (ordered flatten, two-pass binning)
     uint2* items_packed = nullptr;  // curves first, then lines / closing items (single-pass binning)
     uint32_t n_points = 0, n_items = 0, n_curves = 0;
+    uint32_t n_segments = 0, n_subpaths = 0;  // n_items = n_segments + n_subpaths
 };
 
 namespace {
@@ -74,6 +75,7 @@ struct rgpu_ctx {
     uint32_t epoch = 0;
     int fix_shift = kFixShift;  // fraction bits of the winding cells of the batch being submitted (see rgpu_internal.cuh)
     DevBuf img_f32, img_f64, img_lin;  // staging canvases of the host-buffer entry points
+    DevBuf stroke_buf;                 // scratch of rgpu_path_stroke (unit table, counts, offsets, first / last pieces)
     DevBuf tmp_pts, tmp_items;         // device copy of the path of the current host-buffer call (grow-only, no per-call cudaMalloc)
     uint2* h_items = nullptr;          // pinned staging of the item list
     size_t h_items_cap = 0;
@@ -259,6 +261,8 @@ int upload_path(rgpu_ctx* ctx, const rgpu_path* path, rgpu_dpath* dp) {
     pack_items(items, packed);
     dp->n_points = path->n_points;
     dp->n_items = (uint32_t)items.size();
+    dp->n_segments = path->n_segments;
+    dp->n_subpaths = path->n_subpaths;
     items.insert(items.end(), packed.begin(), packed.end());  // one allocation: [reference order | curves first]
     if (dp->n_points) {
         CK(ctx, cudaMalloc(reinterpret_cast<void**>(&dp->pts), sizeof(double2) * dp->n_points));
@@ -947,7 +951,7 @@ void rgpu_destroy(rgpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->jobs, &ctx->paints, &ctx->slot_counts, &ctx->slot_offs, &ctx->lines, &ctx->line_job, &ctx->zero_block, &ctx->tile_offs,
-                      &ctx->tile_state, &ctx->fixed_block, &ctx->refs, &ctx->scan_temp, &ctx->status, &ctx->img_f32, &ctx->img_f64, &ctx->img_lin, &ctx->tmp_pts, &ctx->tmp_items, &ctx->scene_lists};
+                      &ctx->tile_state, &ctx->fixed_block, &ctx->refs, &ctx->scan_temp, &ctx->status, &ctx->img_f32, &ctx->img_f64, &ctx->img_lin, &ctx->tmp_pts, &ctx->tmp_items, &ctx->scene_lists, &ctx->stroke_buf};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
@@ -1645,3 +1649,4 @@ int rgpu_fill(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill
 }  // extern "C"
 
 #include "multi.inl"
+#include "stroke_host.inl"

@@ -12,6 +12,7 @@
 //   tile_state  u64[tiles*16]                per-row tile totals / inclusive prefixes for the carry look-back
 //   canvases    caller-owned                 f32 coverage or f32x4 LinColor
 #pragma once
+#include "stroke_units.hpp"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -123,6 +124,19 @@ void launch_flatten_bin_fixed(const JobDev* jobs, const JobDev* h_jobs, uint32_t
                               uint32_t* tile_counts, double4* bin_lines, uint32_t bin_cap, int band_rows, int chunk_cols, Status* status,
                               Status* next_status, cudaStream_t s);
 TileShape raster_tile_shape(int variant);
+// ---- stroke (stroke.cu; the unit table is described in stroke_units.hpp) ----
+struct StrokeStyleDev {
+    double width, miter_limit;
+    int join, cap;
+};
+// cnt / off: four arrays of stroke_count_stride(n_units) words each (segments, points, curves, closed contours)
+void launch_stroke_pieces(const StrokeUnit* units, uint32_t n_units, const double2* pts, const StrokeStyleDev& st, uint32_t* cnt,
+                          void* first, void* last, cudaStream_t s);
+void launch_stroke_units(bool emit, const StrokeUnit* units, uint32_t n_units, const double2* pts, const StrokeStyleDev& st, uint32_t* cnt,
+                         const void* first, const void* last, const uint32_t* off, double2* out_pts, uint2* out_items, uint2* out_packed,
+                         cudaStream_t s);
+size_t stroke_piece_bytes();
+
 // `ticket` is a zeroed device counter private to this launch (dynamic tile ids for the carry look-back);
 // `tile_state` holds kMaxBandRows u64 words per tile, validated by `epoch` (no clearing between batches).
 // `h_jobs` is the host copy of the job table: single-job launches pass their descriptor by value.

@@ -5,7 +5,8 @@
 //! Uncompiled in the repository that ships this file (no Rust toolchain there); `tests/test_rust_ffi.py` checks the
 //! `extern "C"` block against the header.
 use crate::{
-    rasterize::fill_with_paint, FillRule, ImageMut, LinColor, Paint, Path, Pixel, Point, Rasterizer, Scalar, Segment, Size, Transform,
+    rasterize::fill_with_paint, FillRule, ImageMut, LinColor, LineCap, LineJoin, Paint, Path, Pixel, Point, Rasterizer, Scalar, Segment, Size,
+    StrokeStyle, Transform,
 };
 use std::{
     ffi::CStr,
@@ -81,6 +82,13 @@ pub struct RgpuSceneFill {
     width: u32,
     height: u32,
 }
+#[repr(C)]
+pub struct RgpuStrokeStyle {
+    width: f64,
+    miter_limit: f64,
+    line_join: i32,
+    line_cap: i32,
+}
 pub enum RgpuCtx {}
 pub enum RgpuDpath {}
 pub enum RgpuMulti {}
@@ -98,6 +106,10 @@ extern "C" {
     fn rgpu_mask(ctx: *mut RgpuCtx, path: *const RgpuPath, tr: *const f64, fill_rule: c_int, img: *mut f64, shape: RgpuShape) -> c_int;
     fn rgpu_mask_iter(ctx: *mut RgpuCtx, path: *const RgpuPath, tr: *const f64, width: usize, height: usize, fill_rule: c_int, out: *mut RgpuPixel, cap: usize, n_out: *mut usize) -> c_int;
     fn rgpu_fill(ctx: *mut RgpuCtx, path: *const RgpuPath, tr: *const f64, fill_rule: c_int, paint: *const RgpuPaint, path_bbox: *const f64, img: *mut f32, shape: RgpuShape) -> c_int;
+    fn rgpu_path_free(ctx: *mut RgpuCtx, p: *mut RgpuDpath);
+    fn rgpu_path_stroke(ctx: *mut RgpuCtx, path: *const RgpuPath, style: *const RgpuStrokeStyle, out: *mut *mut RgpuDpath) -> c_int;
+    fn rgpu_dpath_info(p: *const RgpuDpath, n_points: *mut u32, n_segments: *mut u32, n_subpaths: *mut u32) -> c_int;
+    fn rgpu_dpath_download(ctx: *mut RgpuCtx, p: *const RgpuDpath, points: *mut f64, kinds: *mut u8, subpath_offsets: *mut u32, closed: *mut u8) -> c_int;
     fn rgpu_render_scene_host(ctx: *mut RgpuCtx, fills: *const RgpuSceneFill, n_fills: usize, width: usize, height: usize, bg: *const f32, lin_out: *mut f32, rgba_out: *mut u8) -> c_int;
     fn rgpu_fill_batch_host(ctx: *mut RgpuCtx, all: *const RgpuPath, path_subpath_offsets: *const u32, n_paths: usize, trs: *const f64, fill_rule: c_int, paint: *const RgpuPaint, width: u32, height: u32, out_format: c_int, out_host: *mut c_void) -> c_int;
     fn rgpu_multi_create(devices: *const c_int, n_devices: c_int, flatness: f64, out: *mut *mut RgpuMulti) -> c_int;
@@ -251,6 +263,51 @@ impl GpuRasterizer {
         }
         unsafe { buf.set_len(4 * n) };
         buf.chunks_exact(4).map(|l| crate::Line::new((l[0], l[1]), (l[2], l[3]))).collect()
+    }
+
+    /// `Path::stroke(style)` (src/path.rs:374-415) on the device.  The C ABI hands the outline back device-resident
+    /// (`rgpu_dpath`, for callers that rasterize it next); this method downloads it into an ordinary `Path`.
+    pub fn stroke(&self, path: &Path, style: StrokeStyle) -> Path {
+        let flat = FlatPath::new(path);
+        let (line_join, miter_limit) = match style.line_join {
+            LineJoin::Miter(limit) => (0, limit),
+            LineJoin::Bevel => (1, 4.0),
+            LineJoin::Round => (2, 4.0),
+        };
+        let line_cap = match style.line_cap {
+            LineCap::Butt => 0,
+            LineCap::Square => 1,
+            LineCap::Round => 2,
+        };
+        let st = RgpuStrokeStyle { width: style.width, miter_limit, line_join, line_cap };
+        let ctx = self.ctx.lock().unwrap();
+        let mut dp = std::ptr::null_mut();
+        Self::check(*ctx, unsafe { rgpu_path_stroke(*ctx, &flat.ffi(), &st, &mut dp) });
+        let (mut n_pts, mut n_seg, mut n_sub) = (0u32, 0u32, 0u32);
+        unsafe { rgpu_dpath_info(dp, &mut n_pts, &mut n_seg, &mut n_sub) };
+        let mut points = vec![0.0f64; 2 * n_pts as usize];
+        let mut kinds = vec![0u8; n_seg as usize];
+        let mut offsets = vec![0u32; n_sub as usize + 1];
+        let mut closed = vec![0u8; n_sub as usize];
+        let rc = unsafe { rgpu_dpath_download(*ctx, dp, points.as_mut_ptr(), kinds.as_mut_ptr(), offsets.as_mut_ptr(), closed.as_mut_ptr()) };
+        unsafe { rgpu_path_free(*ctx, dp) };
+        Self::check(*ctx, rc);
+        // back into `Path { segments, subpaths, closed }` (src/path.rs:227-240)
+        let mut segments = Vec::with_capacity(kinds.len());
+        let mut at = 0usize;
+        let pt = |i: usize| Point::new(points[2 * i], points[2 * i + 1]);
+        for k in &kinds {
+            segments.push(match k {
+                2 => Segment::Line(crate::Line::new(pt(at), pt(at + 1))),
+                3 => Segment::Quad(crate::Quad::new(pt(at), pt(at + 1), pt(at + 2))),
+                _ => Segment::Cubic(crate::Cubic::new(pt(at), pt(at + 1), pt(at + 2), pt(at + 3))),
+            });
+            at += *k as usize;
+        }
+        if segments.is_empty() {
+            return Path::empty();
+        }
+        Path::new(segments, offsets.iter().map(|o| *o as usize).collect(), closed.iter().map(|c| *c != 0).collect())
     }
 
     /// `ImageOwned::new_default(size)` + `Path::fill` for a batch of independent paths (glyph batches): the images come back

@@ -139,6 +139,23 @@ static void test_scene(GpuRasterizer& r) {
     CHECK(rgba[3] == 255 && rgba.size() == W * H * 4);
 }
 
+// src/path.rs:1225-1269 test_stroke, first case: "M2,2L8,2C11,2 11,8 8,8L5,4" stroked with width 1 (miter / butt)
+static void test_stroke(GpuRasterizer& r) {
+    Path path = Path::builder().move_to({2, 2}).line_to({8, 2}).cubic_to({11, 2}, {11, 8}, {8, 8}).line_to({5, 4}).build();
+    StrokeStyle style;
+    style.width = 1.0;
+    Path s = r.stroke(path, style);
+    const uint8_t kinds[] = {2, 4, 4, 2, 2, 2, 2, 2, 2, 4, 4, 2, 2};
+    const double pts[] = {2, 1.5, 8, 1.5, 8, 1.5, 9.80902, 1.5, 10.75, 3.38197, 10.75, 5, 10.75, 5, 10.75, 6.61803, 9.80902, 8.5, 8, 8.5,
+                          8, 8.5, 7.75, 8.5, 7.75, 8.5, 7.6, 8.3, 7.6, 8.3, 4.6, 4.3, 4.6, 4.3, 5.4, 3.7, 5.4, 3.7, 8.4, 7.7, 8.4, 7.7, 8, 7.5,
+                          8, 7.5, 9.19098, 7.5, 9.75, 6.38197, 9.75, 5, 9.75, 5, 9.75, 3.61803, 9.19098, 2.5, 8, 2.5, 8, 2.5, 2, 2.5, 2, 2.5, 2, 1.5};
+    CHECK(s.kinds.size() == sizeof(kinds));
+    for (size_t i = 0; i < sizeof(kinds); i++) CHECK(s.kinds[i] == kinds[i]);
+    CHECK(s.closed.size() == 1 && s.closed[0] == 1 && s.subpath_offsets[1] == sizeof(kinds));
+    CHECK(s.points.size() == sizeof(pts) / sizeof(double));
+    for (size_t i = 0; i < s.points.size(); i++) CHECK(std::fabs(s.points[i] - pts[i]) < 1e-4);
+}
+
 int main() {
     GpuRasterizer r;
     CHECK(std::string(r.name()) == "gpu-signed-difference");
@@ -146,6 +163,7 @@ int main() {
     test_fill_rule(r);
     test_layers(r);
     test_scene(r);
+    test_stroke(r);
     // NaN control point -> error (reference panics, src/path.rs:765-767)
     Path bad = Path::builder().move_to({0, 0}).quad_to({std::nan(""), 1}, {2, 2}).build();
     bool threw = false;
