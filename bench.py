@@ -501,6 +501,105 @@ def measure(hx: Harness, name: str, steps: int, warmup: int, with_cpu: bool, sam
     return out
 
 
+def measure_pre_stages():
+    """The steps in front of the path that SURVEY §8f ranks next, on the device (N = 1): `Path::stroke` of config 5's / config 2's
+    outline and the batch SVG parse + bbox + fit_size of a glyph batch.  Wall clock of the reference-facing call (host data in,
+    device-resident path(s) out) with the kernels' CUDA-event time beside it, and the oracle on one host thread as baseline."""
+    import oracle as O
+    import rasterize_b200 as rb
+    from rasterize_b200 import Align, LineCap, LineJoin, StrokeStyle, assets, synth
+    rast = rb.GpuRasterizer()
+    rast.set_profiling(True)
+    out = {}
+
+    def timed(call, n, warm=2):
+        for _ in range(warm):
+            call()
+        ts, st = [], None
+        for _ in range(n):
+            t0 = time.perf_counter()
+            r = call(keep=True)
+            ts.append(time.perf_counter() - t0)
+            st = rast.last_stage_ms()
+            r.free()
+        return statistics.median(ts), st
+
+    style = StrokeStyle(0.5, LineJoin.Round, 4.0, LineCap.Round)
+    for name in ("tv", "material"):
+        p = assets.load_path(name)
+
+        def call(keep=False):
+            dp = rast.stroke(p, style)
+            if keep:
+                return dp
+            dp.free()
+
+        t, st = timed(call, 10)
+        op = O.OraclePath.from_flat(p.points, p.kinds, p.subpath_offsets, p.closed)
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 0.3:
+            op.stroke(0.5, "round", 4.0, "round")
+            reps += 1
+        tc = (time.perf_counter() - t0) / reps
+        out[f"stroke_{name}"] = {"call": "rgpu_path_stroke (w = 0.5, round / round): host path in, device-resident outline out",
+                                 "segments_in": p.segments_count(), "ms_per_call": round(t * 1e3, 4),
+                                 "kernel_ms": {"pieces_count_scan": round(st[0], 4), "emit": round(st[2], 4)},
+                                 "cpu_baseline": {"value": round(tc * 1e3, 4), "unit": "ms", "cores": 1, "kind": "port", "sample": f"{reps} x Path::stroke"}}
+    n = 100000
+    pb = synth.glyph_batch(1, 2000)
+    strings = [pb.path(i).to_svg_path().encode() for i in range(2000)]
+    strings = (strings * (n // len(strings)))[:n]  # 2 000 distinct outlines, repeated: the parser's work is the same
+    off = np.zeros(n + 1, dtype=np.uint32)
+    off[1:] = np.cumsum([len(s) for s in strings])
+    text_bytes = b"".join(strings)
+    text = rast.host_alloc((len(text_bytes),), np.uint8)  # pinned, as the contract asks of a step's inputs
+    text[:] = np.frombuffer(text_bytes, dtype=np.uint8)
+    info_box = {}
+
+    def call(keep=False):
+        dpb, info = rast.parse_svg_batch((text, off), fit=(64, 64, Align.Mid))
+        info_box["info"] = info
+        if keep:
+            return dpb
+        dpb.free()
+
+    t, st = timed(call, 5, warm=1)
+    t0 = time.perf_counter()
+    m = 300
+    for s in strings[:m]:
+        op = O.OraclePath.parse(s)
+        O.fit_size(op.bbox(), 64, 64, 1)
+    tc = (time.perf_counter() - t0) / m
+    out["parse_glyph_batch"] = {"call": "rgpu_parse_svg_batch + fit_size(64 x 64, Mid): host text in, device path batch + bbox + fit transforms out",
+                                "paths": n, "text_mb": round(len(text) / 1e6, 2), "segments": int(info_box["info"]["n_segments"].sum()),
+                                "ms_per_call": round(t * 1e3, 3), "value": round(n / t / 1e6, 3), "unit": "Mpaths/s",
+                                "kernel_ms": {"count": round(st[0], 4), "emit": round(st[2], 4)},
+                                "cpu_baseline": {"value": round(1e-6 / tc, 4), "unit": "Mpaths/s", "cores": 1, "kind": "port",
+                                                 "sample": f"{m} x (parse + bbox + fit_size), {tc * 1e6:.1f} us per path"}}
+    s = assets.load_path("material").to_svg_path().encode()
+
+    def call1(keep=False):
+        dpb, _ = rast.parse_svg_batch([s])
+        if keep:
+            return dpb
+        dpb.free()
+
+    t, st = timed(call1, 10)
+    t0 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t0 < 0.3:
+        O.OraclePath.parse(s).bbox()
+        reps += 1
+    tc = (time.perf_counter() - t0) / reps
+    out["parse_material"] = {"call": "rgpu_parse_svg_batch of ONE string (the reference's material-big `parse` + `bbox` bench ids), cut at absolute movetos",
+                             "text_mb": round(len(s) / 1e6, 3), "ms_per_call": round(t * 1e3, 4),
+                             "kernel_ms": {"count": round(st[0], 4), "emit": round(st[2], 4)},
+                             "cpu_baseline": {"value": round(tc * 1e3, 4), "unit": "ms", "cores": 1, "kind": "port", "sample": f"{reps} x (parse + bbox)"}}
+    rast.close()
+    return out
+
+
 def run_ours(args):
     hx = Harness()
     main = measure(hx, args.workload, args.steps, args.warmup, with_cpu=True, sample_clocks=True)
@@ -517,6 +616,11 @@ def run_ours(args):
                 others[n]["roofline"] = {k: r["roofline"][k] for k in ("kernel", "achieved", "frac", "kernel_ms", "stage_ms", "step_frac")}
             except Exception as e:  # a side measurement must not take the headline line down with it
                 others[n] = {"error": f"{type(e).__name__}: {e}"}
+        if hx.world == 1:
+            try:
+                others["pre_stages"] = measure_pre_stages()
+            except Exception as e:
+                others["pre_stages"] = {"error": f"{type(e).__name__}: {e}"}
     if hx.rank == 0:
         if others:
             main["other_configs"] = others

@@ -264,6 +264,43 @@ int rgpu_path_upload_batch(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* 
 const rgpu_dpath* rgpu_path_batch_get(const rgpu_dpath_batch* batch, size_t i);
 void rgpu_path_batch_free(rgpu_ctx* ctx, rgpu_dpath_batch* batch);
 
+/* Batch SVG path parse + `Path::bbox` + `fit_size` on the device: `text` holds n_paths SVG path strings back to
+ * back (`d` attribute syntax), string i = bytes [text_offsets[i], text_offsets[i + 1]).  Every string is parsed by the
+ * reference's grammar and number scanner (`SvgPathParser` src/svg.rs:241-421; scalars src/svg.rs:165-235: value =
+ * (i64 mantissa as f64) * powi(10, exponent), not strtod) into `PathBuilder` semantics (src/path.rs:832-972: `line_to` drops
+ * a line shorter than EPSILON, `close` returns to the subpath's first point, arcs become cubics), one thread per string, and
+ * the result is an ordinary device path batch (rgpu_path_batch_get, rgpu_job::path).  Per path, `info[i]` (HOST array of
+ * n_paths entries, may be NULL) receives `Path::bbox(identity)` (src/path.rs:428-431), the segment counts, the parse status
+ * (`SvgParserError`, src/svg.rs:604-640; a failed path is empty) and — when `opt->fit_align >= 0` — `fit_size(bbox,
+ * Size {fit_width, fit_height}, align)` (src/geometry.rs:490-516: the canvas size and the transform that fits the path
+ * into it).  With info == NULL a parse error in any path fails the call (RGPU_ERR_INVALID, rgpu_last_error names the path,
+ * the error kind and the byte offset).  Control points are bit-identical to the reference's except inside arcs (`A` / `a`:
+ * sin / cos / tan / acos, a few ulp). */
+enum { RGPU_PARSE_OK = 0, RGPU_PARSE_INVALID_CMD = 1, RGPU_PARSE_INVALID_SCALAR = 2, RGPU_PARSE_INVALID_FLAG = 3 };
+enum { RGPU_ALIGN_MIN = 0, RGPU_ALIGN_MID = 1, RGPU_ALIGN_MAX = 2 }; /* `Align`, src/geometry.rs:298-305 */
+typedef struct {
+    double bbox[4];   /* min x, min y, max x, max y; valid when has_bbox */
+    double fit_tr[6]; /* identity unless a fit was requested and has_bbox */
+    uint32_t fit_width, fit_height;
+    uint32_t n_points, n_segments, n_subpaths;
+    int32_t status;        /* RGPU_PARSE_* */
+    uint32_t error_offset; /* byte offset inside the path's string */
+    int32_t has_bbox;      /* 0 for an empty path (`Path::bbox` returns None) */
+    uint32_t n_curves, reserved;
+} rgpu_parse_info;
+typedef struct {
+    uint32_t fit_width, fit_height; /* 0 = derive from the other side and the bbox's aspect ratio, as `fit_size` does */
+    int32_t fit_align;              /* RGPU_ALIGN_*, or < 0: no fit */
+} rgpu_parse_options;
+int rgpu_parse_svg_batch(rgpu_ctx* ctx, const char* text, const uint32_t* text_offsets, size_t n_paths, const rgpu_parse_options* opt,
+                         rgpu_dpath_batch** out, rgpu_parse_info* info);
+/* Totals of a device path batch and its download in the flat batch encoding of rgpu_path_upload_batch:
+ * points[2 * n_points], kinds[n_segments], subpath_offsets[n_subpaths + 1], closed[n_subpaths],
+ * path_subpath_offsets[n_paths + 1]. */
+int rgpu_path_batch_info(const rgpu_dpath_batch* batch, size_t* n_paths, uint32_t* n_points, uint32_t* n_segments, uint32_t* n_subpaths);
+int rgpu_path_batch_download(rgpu_ctx* ctx, const rgpu_dpath_batch* batch, double* points, uint8_t* kinds, uint32_t* subpath_offsets,
+                             uint8_t* closed, uint32_t* path_subpath_offsets);
+
 /* A job list marshalled once and kept on the device: the steady state of a render loop that re-submits the same
  * batch (rgpu_render_batch re-derives and compares its tables on every call, which for 10^5 glyph jobs costs more
  * host time than the kernel takes).  `jobs` (and the paints they point to) must stay valid until rgpu_batch_free.

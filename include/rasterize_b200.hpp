@@ -366,6 +366,51 @@ public:
         check(rc);
         return out;
     }
+    // Batch `str::parse::<Path>()` + `Path::bbox` + `fit_size` on the device (src/svg.rs:241-421, src/path.rs:428-451,
+    // src/geometry.rs:490-516): one host call for n strings.  `info[i]` carries the bbox, the parse status and, when
+    // fit_align >= 0, the fitted size and transform; a string that does not parse gives an empty path.
+    struct ParsedBatch {
+        std::vector<Path> paths;
+        std::vector<rgpu_parse_info> info;
+    };
+    ParsedBatch parse_svg_batch(const std::vector<std::string>& strings, uint32_t fit_width = 0, uint32_t fit_height = 0, int fit_align = -1) {
+        std::string text;
+        std::vector<uint32_t> off(1, 0u);
+        for (const std::string& s : strings) {
+            text += s;
+            off.push_back((uint32_t)text.size());
+        }
+        ParsedBatch out;
+        out.info.resize(strings.size());
+        rgpu_parse_options opt{fit_width, fit_height, fit_align};
+        rgpu_dpath_batch* b = nullptr;
+        check(rgpu_parse_svg_batch(ctx_, text.data(), off.data(), strings.size(), &opt, &b, out.info.data()));
+        size_t n = 0;
+        uint32_t n_pts = 0, n_seg = 0, n_sub = 0;
+        rgpu_path_batch_info(b, &n, &n_pts, &n_seg, &n_sub);
+        std::vector<double> pts(2 * (size_t)n_pts);
+        std::vector<uint8_t> kinds(n_seg), closed(n_sub);
+        std::vector<uint32_t> sp((size_t)n_sub + 1), psp(n + 1);
+        const int rc = rgpu_path_batch_download(ctx_, b, pts.data(), kinds.data(), sp.data(), closed.data(), psp.data());
+        rgpu_path_batch_free(ctx_, b);
+        check(rc);
+        size_t pt = 0;
+        out.paths.resize(n);
+        for (size_t i = 0; i < n; i++) {
+            Path& p = out.paths[i];
+            const uint32_t s0 = psp[i], s1 = psp[i + 1];
+            if (s1 == s0) continue;
+            const uint32_t k0 = sp[s0], k1 = sp[s1];
+            size_t np = 0;
+            for (uint32_t k = k0; k < k1; k++) np += kinds[k];
+            p.points.assign(pts.begin() + 2 * pt, pts.begin() + 2 * (pt + np));
+            p.kinds.assign(kinds.begin() + k0, kinds.begin() + k1);
+            for (uint32_t s = s0; s <= s1; s++) p.subpath_offsets.push_back(sp[s] - k0);
+            p.closed.assign(closed.begin() + s0, closed.begin() + s1);
+            pt += np;
+        }
+        return out;
+    }
     // One Fill node as the Fill arm of `Pipeline::render_rec` sets it up (src/scene.rs:407-430): `tr` = align * node
     // transform, (x, y, width, height) = the `view_mut` window of the layer.
     struct SceneFill {

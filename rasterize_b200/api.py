@@ -174,6 +174,23 @@ class Path:
         pts = np.stack([x * m[0] + y * m[1] + m[2], x * m[3] + y * m[4] + m[5]], axis=1)
         return Path(pts, self.kinds, self.subpath_offsets, self.closed)
 
+    def to_svg_path(self) -> str:
+        """The path as an SVG path string (absolute M / L / Q / C / Z, shortest round-trip decimals).  `Path::write_svg_path`
+        (src/path.rs:537-541) prints 4 significant digits; this one keeps every digit.  NOTE: the reference's scanner is not
+        correctly rounded ((i64 mantissa) * powi(10, e)), so parsing the text again may differ from `self` in the last bit."""
+        pts = self.points
+        out, at = [], 0
+        for s in range(len(self.closed)):
+            for k in range(int(self.subpath_offsets[s]), int(self.subpath_offsets[s + 1])):
+                n = int(self.kinds[k])
+                if k == self.subpath_offsets[s]:
+                    out.append(f"M{float(pts[at][0])!r},{float(pts[at][1])!r}")
+                out.append("LQC"[n - 2] + " ".join(f"{float(x)!r},{float(y)!r}" for x, y in pts[at + 1:at + n]))
+                at += n
+            if self.closed[s]:
+                out.append("Z")
+        return "".join(out)
+
     def input_bytes(self) -> int:
         """Algorithmic input bytes: 16 B per control point."""
         return int(self.points.shape[0]) * 16
@@ -559,24 +576,66 @@ class DevicePath:
             pass
 
 
-class DevicePathBatch:
-    """Device-resident `PathBatch` (`rgpu_dpath_batch`): element i is an ordinary device path."""
+#: numpy view of `rgpu_parse_info` (include/rasterize_b200.h)
+PARSE_INFO_DTYPE = np.dtype([("bbox", "<f8", 4), ("fit_tr", "<f8", 6), ("fit_width", "<u4"), ("fit_height", "<u4"), ("n_points", "<u4"),
+                             ("n_segments", "<u4"), ("n_subpaths", "<u4"), ("status", "<i4"), ("error_offset", "<u4"), ("has_bbox", "<i4"),
+                             ("n_curves", "<u4"), ("reserved", "<u4")])
 
-    def __init__(self, rast: "GpuRasterizer", batch: PathBatch):
+
+class Align(enum.IntEnum):
+    """`Align` (src/geometry.rs:298-305)"""
+    Min = 0
+    Mid = 1
+    Max = 2
+
+
+class DevicePathBatch:
+    """Device-resident `PathBatch` (`rgpu_dpath_batch`): element i is an ordinary device path.  Made from a host batch
+    (upload) or, with `handle=`, wrapped around a batch the library built itself (`GpuRasterizer.parse_svg_batch`)."""
+
+    def __init__(self, rast: "GpuRasterizer", batch: PathBatch | None, handle=None, n_paths: int | None = None):
         self.rast = rast
         self.batch = batch
+        if handle is not None:
+            self.h = handle
+            self.n_paths = int(n_paths)
+            return
         h = C.c_void_p()
         c = batch.flat._c()
         rast._check(ffi.lib().rgpu_path_upload_batch(rast.ctx, C.byref(c), batch.path_subpath_offsets.ctypes.data_as(C.POINTER(C.c_uint32)),
                                                      len(batch), C.byref(h)))
         self.h = h
+        self.n_paths = len(batch)
+
+    def __len__(self) -> int:
+        return self.n_paths
+
+    def counts(self) -> tuple[int, int, int, int]:
+        """(n_paths, n_points, n_segments, n_subpaths)"""
+        n = C.c_size_t()
+        c = [C.c_uint32() for _ in range(3)]
+        self.rast._check(ffi.lib().rgpu_path_batch_info(self.h, C.byref(n), *[C.byref(v) for v in c]))
+        return (int(n.value),) + tuple(v.value for v in c)
+
+    def download(self) -> PathBatch:
+        """The batch as a host `PathBatch` (for a parsed batch: what `str::parse::<Path>` gives, path by path)."""
+        n, n_pts, n_seg, n_sub = self.counts()
+        pts = np.zeros((n_pts, 2), dtype=np.float64)
+        kinds = np.zeros(n_seg, dtype=np.uint8)
+        sp = np.zeros(n_sub + 1, dtype=np.uint32)
+        closed = np.zeros(n_sub, dtype=np.uint8)
+        psp = np.zeros(n + 1, dtype=np.uint32)
+        u32p, u8p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
+        self.rast._check(ffi.lib().rgpu_path_batch_download(self.rast.ctx, self.h, pts.ctypes.data_as(C.POINTER(C.c_double)), kinds.ctypes.data_as(u8p),
+                                                            sp.ctypes.data_as(u32p), closed.ctypes.data_as(u8p), psp.ctypes.data_as(u32p)))
+        return PathBatch(pts, kinds, sp, closed, psp)
 
     def handle(self, i: int) -> int:
         return int(ffi.lib().rgpu_path_batch_get(self.h, i) or 0)
 
     def handles(self) -> np.ndarray:
         """Device-path handles of all elements as u64 (they are elements of one array)."""
-        n = len(self.batch)
+        n = self.n_paths
         if n == 0:
             return np.zeros(0, dtype=np.uint64)
         h0 = self.handle(0)
@@ -871,6 +930,32 @@ class GpuRasterizer:
     # -- batches of independent paths (BASELINE config 4) / band-sharded masks (config 5) ---------------------------
     def upload_batch(self, batch: PathBatch) -> DevicePathBatch:
         return DevicePathBatch(self, batch)
+
+    def parse_svg_batch(self, strings, fit: tuple[int, int, Align] | None = None, strict: bool = False):
+        """Batch `str::parse::<Path>` + `Path::bbox` (+ `fit_size`) on the device (SURVEY §8f-4; src/svg.rs:241-421,
+        src/path.rs:428-451, src/geometry.rs:490-516).  `strings` = a sequence of str / bytes, or (text, offsets u32[n + 1]) with
+        `text` = bytes or a uint8 array (e.g. pinned, from `host_alloc`).
+        -> (DevicePathBatch, info: ndarray of PARSE_INFO_DTYPE).  A string that does not parse gives an empty path and its
+        `status` / `error_offset`; with `strict` the call raises instead."""
+        if isinstance(strings, tuple):
+            text, off = strings
+            off = np.ascontiguousarray(off, dtype=np.uint32)
+        else:
+            enc = [s.encode() if isinstance(s, str) else bytes(s) for s in strings]
+            off = np.zeros(len(enc) + 1, dtype=np.uint32)
+            off[1:] = np.cumsum([len(e) for e in enc])
+            text = b"".join(enc)
+        n = len(off) - 1
+        info = np.zeros(max(n, 1), dtype=PARSE_INFO_DTYPE)
+        opt = ffi.CParseOptions(int(fit[0]), int(fit[1]), int(fit[2])) if fit is not None else ffi.CParseOptions(0, 0, -1)
+        h = C.c_void_p()
+        if isinstance(text, np.ndarray):
+            assert text.dtype == np.uint8 and text.flags.c_contiguous
+            text = C.cast(text.ctypes.data, C.c_char_p)
+        self._check(ffi.lib().rgpu_parse_svg_batch(self.ctx, text, off.ctypes.data_as(C.POINTER(C.c_uint32)), n, C.byref(opt), C.byref(h),
+                                                   None if strict else info.ctypes.data))
+        batch = DevicePathBatch(self, None, handle=h, n_paths=n)
+        return batch, (None if strict else info[:n])
 
     def prepare_job_table(self, table: np.ndarray, independent: bool = True, keep=None) -> PreparedBatch:
         return PreparedBatch(self, table, independent, keep)

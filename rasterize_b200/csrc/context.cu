@@ -1650,3 +1650,4 @@ int rgpu_fill(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill
 
 #include "multi.inl"
 #include "stroke_host.inl"
+#include "parse_host.inl"

@@ -8,6 +8,7 @@ struct rgpu_dpath_batch {
     std::vector<rgpu_dpath> paths;  // views into the two allocations below
     double2* pts = nullptr;
     uint2* items = nullptr;         // [reference order of every path | curves-first order of every path]
+    uint32_t n_points = 0, n_items = 0, n_segments = 0, n_subpaths = 0;  // totals (rgpu_path_batch_info / _download)
 };
 
 struct rgpu_batch {
@@ -108,6 +109,10 @@ int rgpu_path_upload_batch(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* 
         delete b;
         return RGPU_ERR_CUDA;
     }
+    b->n_points = all->n_points;
+    b->n_items = (uint32_t)n_items;
+    b->n_segments = all->n_segments;
+    b->n_subpaths = all->n_subpaths;
     b->paths.resize(n_paths);
     for (size_t i = 0; i < n_paths; i++) {
         rgpu_dpath& d = b->paths[i];

@@ -13,6 +13,8 @@
 //   canvases    caller-owned                 f32 coverage or f32x4 LinColor
 #pragma once
 #include "stroke_units.hpp"
+#include "parse_tables.hpp"
+#include <vector>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -136,6 +138,16 @@ void launch_stroke_units(bool emit, const StrokeUnit* units, uint32_t n_units, c
                          const void* first, const void* last, const uint32_t* off, double2* out_pts, uint2* out_items, uint2* out_packed,
                          cudaStream_t s);
 size_t stroke_piece_bytes();
+// ---- batch SVG parse (parse.cu; tables and the host-side plan are in parse_plan.hpp) ----
+void launch_parse_count(const uint8_t* text, const uint32_t* chunk_off, uint32_t n_chunks, const ParseFit& fit, ParseInfoDev* info,
+                        cudaStream_t s);
+void launch_parse_emit(const uint8_t* text, const uint32_t* chunk_off, uint32_t n_chunks, const ParseEmitBase* bases, double2* out_pts,
+                       uint2* out_items, uint2* out_packed, cudaStream_t s);
+void parse_plan_chunks_host(const char* text, const uint32_t* text_off, uint32_t n_paths, std::vector<uint32_t>& chunk_off,
+                            std::vector<uint32_t>& chunk_first);
+void parse_merge_chunks_host(const ParseInfoDev* info, const std::vector<uint32_t>& chunk_off, const std::vector<uint32_t>& chunk_first,
+                             const uint32_t* text_off, uint32_t n_paths, const ParseFit& fit, ParseInfoDev* path_info,
+                             std::vector<ParseEmitBase>& bases, std::vector<uint32_t>& item_off, uint32_t& total_pts);
 
 // `ticket` is a zeroed device counter private to this launch (dynamic tile ids for the carry look-back);
 // `tile_state` holds kMaxBandRows u64 words per tile, validated by `epoch` (no clearing between batches).

@@ -293,9 +293,11 @@ SD_FN inline int quadratic_solve(double a, double b, double c, double* r) {
     }
     return n;
 }
-// `Curve::bbox(None)`: src/curve.rs:505-513 + extremities :535-555 (Quad), :810-818 + :853-864 (Cubic)
-SD_FN inline Box seg_bbox(const Seg& s) {
+// `Curve::bbox(init)`: src/curve.rs:270-273 (Line), :505-513 + extremities :535-555 (Quad), :810-818 + :853-864 (Cubic);
+// `BBox::union_opt` src/geometry.rs:636-645
+SD_FN inline Box seg_bbox_acc(const Seg& s, bool has_init, const Box& init) {
     Box bb = box_new(seg_start(s), seg_end(s));
+    if (has_init) bb = box_extend(box_extend(bb, init.lo), init.hi);
     if (s.kind == 2) return bb;
     if (s.kind == 3) {
         if (box_contains(bb, s.p[1])) return bb;
@@ -324,6 +326,7 @@ SD_FN inline Box seg_bbox(const Seg& s) {
         if (ry[i] >= 0.0 && ry[i] <= 1.0) bb = box_extend(bb, seg_at(s, ry[i]));
     return bb;
 }
+SD_FN inline Box seg_bbox(const Seg& s) { return seg_bbox_acc(s, false, Box()); }
 
 // ---- polyline offset, src/curve.rs:1294-1346 ----
 SD_FN inline bool polyline_offset(P2* ps, int len, double dist) {
@@ -373,8 +376,9 @@ SD_FN inline double rem_euclid(double x, double rhs) {
 }
 
 // The arc from `src` to `dst` with radii (rx, ry), as cubics into `sink`; false when the parametrisation fails
-// (the caller then falls back to the bevel).  A NaN sweep makes the reference's iterator spin for ever; here it
-// yields nothing.
+// (the caller then falls back to a line).  NaN angles (e.g. an arc whose end points coincide: 0 / 0 in the centre) make the
+// reference's iterator spin for ever; here, as in the host builders (api.py / .hpp `arc_to`), they count as a failed
+// parametrisation.
 template <class Sink>
 SD_FN inline bool arc_cubics(P2 src, P2 dst, double rx, double ry, double x_axis_rot, bool large_flag, bool sweep_flag, Sink& sink) {
     rx = fabs(rx);
@@ -402,6 +406,7 @@ SD_FN inline bool arc_cubics(P2 src, P2 dst, double rx, double ry, double x_axis
     double eta, eta_delta;
     if (!angle_between(v0, v1, eta)) return false;
     if (!angle_between(v1, v2, eta_delta)) return false;
+    if (eta != eta || eta_delta != eta_delta) return false;
     eta_delta = rem_euclid(eta_delta, 2.0 * kPi);
     if (!sweep_flag && eta_delta > 0.0) eta_delta = eta_delta - 2.0 * kPi;
     else if (sweep_flag && eta_delta < 0.0) eta_delta = eta_delta + 2.0 * kPi;
@@ -411,7 +416,6 @@ SD_FN inline bool arc_cubics(P2 src, P2 dst, double rx, double ry, double x_axis
     const double segment_delta = eta_delta / segment_count;
     double segment_index = 0.0;
     segment_count = segment_count - 1.0;
-    if (segment_count != segment_count) return true;
     while (!(segment_index > segment_count)) {
         const double eta_1 = eta + segment_delta * segment_index;
         const double eta_2 = eta_1 + segment_delta;

@@ -54,6 +54,10 @@ int rgpu_path_stroke(rgpu_ctx* ctx, const rgpu_path* path, const rgpu_stroke_sty
     CKB(cudaMemcpyAsync(d_pts, path->points, sizeof(double2) * path->n_points, cudaMemcpyHostToDevice, st));
     CKB(cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t) * 4 * stride, st));
     StrokeStyleDev sd{style->width, style->miter_limit, style->line_join, style->line_cap};
+    // rgpu_set_profiling: stage 0 = pieces + count + scans, stage 1 = the host's turn (sizes, allocation), stage 2 = emit
+    const bool prof = ctx->profiling && ctx->ev[0];
+    ctx->ev_valid = false;
+    if (prof) CKB(cudaEventRecord(ctx->ev[0], st));
     launch_stroke_pieces(d_units, n, d_pts, sd, d_cnt, base + o_first, base + o_last, st);
     launch_stroke_units(false, d_units, n, d_pts, sd, d_cnt, base + o_first, base + o_last, nullptr, nullptr, nullptr, nullptr, st);
     for (int k = 0; k < 4; k++) {
@@ -61,6 +65,7 @@ int rgpu_path_stroke(rgpu_ctx* ctx, const rgpu_path* path, const rgpu_stroke_sty
         launch_exclusive_scan(d_cnt + k * stride, d_off + k * stride, n + 1, base + o_scan, scan_bytes, st, true);
     }
     ctx->n_launches += 6;
+    if (prof) CKB(cudaEventRecord(ctx->ev[1], st));
     uint32_t totals[4];
     for (int k = 0; k < 4; k++) CKB(cudaMemcpyAsync(&totals[k], d_off + k * stride + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CKB(cudaStreamSynchronize(st));
@@ -79,8 +84,13 @@ int rgpu_path_stroke(rgpu_ctx* ctx, const rgpu_path* path, const rgpu_stroke_sty
         CKB(cudaMalloc(reinterpret_cast<void**>(&dp->pts), sizeof(double2) * std::max<uint32_t>(n_pts, 1)));
         CKB(cudaMalloc(reinterpret_cast<void**>(&dp->items), sizeof(uint2) * 2 * dp->n_items));
         dp->items_packed = dp->items + dp->n_items;
+        if (prof) CKB(cudaEventRecord(ctx->ev[2], st));
         launch_stroke_units(true, d_units, n, d_pts, sd, d_cnt, base + o_first, base + o_last, d_off, dp->pts, dp->items, dp->items_packed, st);
         ctx->n_launches += 1;
+        if (prof) {
+            CKB(cudaEventRecord(ctx->ev[3], st));
+            ctx->ev_valid = true;
+        }
         CKB(cudaStreamSynchronize(st));
         CKB(cudaGetLastError());
     }

@@ -57,6 +57,10 @@ class CStrokeStyle(C.Structure):
     _fields_ = [("width", C.c_double), ("miter_limit", C.c_double), ("line_join", C.c_int32), ("line_cap", C.c_int32)]
 
 
+class CParseOptions(C.Structure):
+    _fields_ = [("fit_width", C.c_uint32), ("fit_height", C.c_uint32), ("fit_align", C.c_int32)]
+
+
 class CSceneFill(C.Structure):
     _fields_ = [("path", C.POINTER(CPath)), ("tr", C.c_double * 6), ("fill_rule", C.c_int32), ("paint", C.POINTER(CPaint)),
                 ("path_bbox", C.POINTER(C.c_double)), ("x", C.c_uint32), ("y", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32)]
@@ -75,7 +79,7 @@ SYMBOLS = [
     "rgpu_path_upload_batch", "rgpu_path_batch_get", "rgpu_path_batch_free", "rgpu_batch_create", "rgpu_batch_render", "rgpu_batch_free",
     "rgpu_fill_batch_host", "rgpu_mask_banded_host", "rgpu_multi_create", "rgpu_multi_destroy", "rgpu_multi_device_count",
     "rgpu_multi_last_error", "rgpu_multi_fill_batch_host", "rgpu_multi_mask_banded_host", "rgpu_set_winding_bits",
-    "rgpu_path_stroke", "rgpu_dpath_info", "rgpu_dpath_download",
+    "rgpu_path_stroke", "rgpu_dpath_info", "rgpu_dpath_download", "rgpu_parse_svg_batch", "rgpu_path_batch_info", "rgpu_path_batch_download",
 ]
 
 
@@ -113,6 +117,9 @@ def lib():
     pu32_ = C.POINTER(C.c_uint32)
     sig("rgpu_dpath_info", i32, vp, pu32_, pu32_, pu32_)
     sig("rgpu_dpath_download", i32, vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_uint8), pu32_, C.POINTER(C.c_uint8))
+    sig("rgpu_parse_svg_batch", i32, vp, C.c_char_p, pu32_, sz, C.POINTER(CParseOptions), C.POINTER(vp), vp)
+    sig("rgpu_path_batch_info", i32, vp, C.POINTER(sz), pu32_, pu32_, pu32_)
+    sig("rgpu_path_batch_download", i32, vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_uint8), pu32_, C.POINTER(C.c_uint8), pu32_)
     sig("rgpu_render_batch", i32, vp, C.POINTER(CJob), sz, u32)
     sig("rgpu_batch_status", i32, vp)
     sig("rgpu_set_winding_bits", i32, vp, i32)

@@ -2,7 +2,7 @@
 // fails without nvcc).  Sources: rasterize_b200/csrc (copied or vendored next to Cargo.toml).
 use std::{env, path::PathBuf, process::Command};
 
-const SOURCES: &[&str] = &["flatten.cu", "scan.cu", "raster.cu", "scene.cu", "small.cu", "compose.cu", "stroke.cu", "context.cu"];
+const SOURCES: &[&str] = &["flatten.cu", "scan.cu", "raster.cu", "scene.cu", "small.cu", "compose.cu", "stroke.cu", "parse.cu", "context.cu"];
 
 fn main() {
     if env::var_os("CARGO_FEATURE_GPU").is_none() {
@@ -17,8 +17,8 @@ fn main() {
         let ok = Command::new(&nvcc)
             .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr",
                    "-Xcompiler", "-fPIC", "-c"])
-            // stroke.cu restates f64 expressions of the reference with plain operators: no multiply-add contraction there
-            .args(if *f == "stroke.cu" { &["--fmad=false"][..] } else { &[][..] })
+            // stroke.cu / parse.cu restate f64 expressions of the reference with plain operators: no multiply-add contraction there
+            .args(if *f == "stroke.cu" || *f == "parse.cu" { &["--fmad=false"][..] } else { &[][..] })
             .arg(csrc.join(f))
             .arg("-o")
             .arg(&obj)

@@ -5,7 +5,7 @@
 //! Uncompiled in the repository that ships this file (no Rust toolchain there); `tests/test_rust_ffi.py` checks the
 //! `extern "C"` block against the header.
 use crate::{
-    rasterize::fill_with_paint, FillRule, ImageMut, LinColor, LineCap, LineJoin, Paint, Path, Pixel, Point, Rasterizer, Scalar, Segment, Size,
+    rasterize::fill_with_paint, Align, FillRule, ImageMut, LinColor, LineCap, LineJoin, Paint, Path, Pixel, Point, Rasterizer, Scalar, Segment, Size,
     StrokeStyle, Transform,
 };
 use std::{
@@ -89,6 +89,30 @@ pub struct RgpuStrokeStyle {
     line_join: i32,
     line_cap: i32,
 }
+/// `rgpu_parse_info`: per-path result of the batch parser
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct RgpuParseInfo {
+    pub bbox: [f64; 4],
+    pub fit_tr: [f64; 6],
+    pub fit_width: u32,
+    pub fit_height: u32,
+    pub n_points: u32,
+    pub n_segments: u32,
+    pub n_subpaths: u32,
+    pub status: i32,
+    pub error_offset: u32,
+    pub has_bbox: i32,
+    pub n_curves: u32,
+    pub reserved: u32,
+}
+#[repr(C)]
+pub struct RgpuParseOptions {
+    fit_width: u32,
+    fit_height: u32,
+    fit_align: i32,
+}
+pub enum RgpuDpathBatch {}
 pub enum RgpuCtx {}
 pub enum RgpuDpath {}
 pub enum RgpuMulti {}
@@ -110,6 +134,10 @@ extern "C" {
     fn rgpu_path_stroke(ctx: *mut RgpuCtx, path: *const RgpuPath, style: *const RgpuStrokeStyle, out: *mut *mut RgpuDpath) -> c_int;
     fn rgpu_dpath_info(p: *const RgpuDpath, n_points: *mut u32, n_segments: *mut u32, n_subpaths: *mut u32) -> c_int;
     fn rgpu_dpath_download(ctx: *mut RgpuCtx, p: *const RgpuDpath, points: *mut f64, kinds: *mut u8, subpath_offsets: *mut u32, closed: *mut u8) -> c_int;
+    fn rgpu_parse_svg_batch(ctx: *mut RgpuCtx, text: *const c_char, text_offsets: *const u32, n_paths: usize, opt: *const RgpuParseOptions, out: *mut *mut RgpuDpathBatch, info: *mut RgpuParseInfo) -> c_int;
+    fn rgpu_path_batch_info(batch: *const RgpuDpathBatch, n_paths: *mut usize, n_points: *mut u32, n_segments: *mut u32, n_subpaths: *mut u32) -> c_int;
+    fn rgpu_path_batch_download(ctx: *mut RgpuCtx, batch: *const RgpuDpathBatch, points: *mut f64, kinds: *mut u8, subpath_offsets: *mut u32, closed: *mut u8, path_subpath_offsets: *mut u32) -> c_int;
+    fn rgpu_path_batch_free(ctx: *mut RgpuCtx, batch: *mut RgpuDpathBatch);
     fn rgpu_render_scene_host(ctx: *mut RgpuCtx, fills: *const RgpuSceneFill, n_fills: usize, width: usize, height: usize, bg: *const f32, lin_out: *mut f32, rgba_out: *mut u8) -> c_int;
     fn rgpu_fill_batch_host(ctx: *mut RgpuCtx, all: *const RgpuPath, path_subpath_offsets: *const u32, n_paths: usize, trs: *const f64, fill_rule: c_int, paint: *const RgpuPaint, width: u32, height: u32, out_format: c_int, out_host: *mut c_void) -> c_int;
     fn rgpu_multi_create(devices: *const c_int, n_devices: c_int, flatness: f64, out: *mut *mut RgpuMulti) -> c_int;
@@ -308,6 +336,63 @@ impl GpuRasterizer {
             return Path::empty();
         }
         Path::new(segments, offsets.iter().map(|o| *o as usize).collect(), closed.iter().map(|c| *c != 0).collect())
+    }
+
+    /// `str::parse::<Path>()` for a batch of SVG path strings, with `Path::bbox(identity)` and (when `fit` is given)
+    /// `fit_size(bbox, size, align)` per path, in one device call (src/svg.rs:241-421, src/path.rs:428-451,
+    /// src/geometry.rs:490-516).  A string that does not parse comes back as `Err((kind, byte offset))`.
+    pub fn parse_svg_batch(&self, strings: &[&str], fit: Option<(Size, Align)>) -> Vec<Result<(Path, RgpuParseInfo), (i32, u32)>> {
+        let mut text = String::new();
+        let mut off = vec![0u32];
+        for s in strings {
+            text.push_str(s);
+            off.push(text.len() as u32);
+        }
+        let opt = match fit {
+            Some((size, align)) => RgpuParseOptions { fit_width: size.width as u32, fit_height: size.height as u32,
+                                                      fit_align: match align { Align::Min => 0, Align::Mid => 1, Align::Max => 2 } },
+            None => RgpuParseOptions { fit_width: 0, fit_height: 0, fit_align: -1 },
+        };
+        let mut info = vec![RgpuParseInfo::default(); strings.len()];
+        let ctx = self.ctx.lock().unwrap();
+        let mut b = std::ptr::null_mut();
+        Self::check(*ctx, unsafe { rgpu_parse_svg_batch(*ctx, text.as_ptr() as *const c_char, off.as_ptr(), strings.len(), &opt, &mut b, info.as_mut_ptr()) });
+        let (mut n, mut n_pts, mut n_seg, mut n_sub) = (0usize, 0u32, 0u32, 0u32);
+        unsafe { rgpu_path_batch_info(b, &mut n, &mut n_pts, &mut n_seg, &mut n_sub) };
+        let mut points = vec![0.0f64; 2 * n_pts as usize];
+        let mut kinds = vec![0u8; n_seg as usize];
+        let mut sp = vec![0u32; n_sub as usize + 1];
+        let mut closed = vec![0u8; n_sub as usize];
+        let mut psp = vec![0u32; n + 1];
+        let rc = unsafe { rgpu_path_batch_download(*ctx, b, points.as_mut_ptr(), kinds.as_mut_ptr(), sp.as_mut_ptr(), closed.as_mut_ptr(), psp.as_mut_ptr()) };
+        unsafe { rgpu_path_batch_free(*ctx, b) };
+        Self::check(*ctx, rc);
+        let pt = |i: usize| Point::new(points[2 * i], points[2 * i + 1]);
+        let mut at = 0usize;
+        (0..n)
+            .map(|i| {
+                if info[i].status != 0 {
+                    return Err((info[i].status, info[i].error_offset));
+                }
+                let (s0, s1) = (psp[i] as usize, psp[i + 1] as usize);
+                if s0 == s1 {
+                    return Ok((Path::empty(), info[i]));
+                }
+                let (k0, k1) = (sp[s0] as usize, sp[s1] as usize);
+                let mut segments = Vec::with_capacity(k1 - k0);
+                for k in &kinds[k0..k1] {
+                    segments.push(match k {
+                        2 => Segment::Line(crate::Line::new(pt(at), pt(at + 1))),
+                        3 => Segment::Quad(crate::Quad::new(pt(at), pt(at + 1), pt(at + 2))),
+                        _ => Segment::Cubic(crate::Cubic::new(pt(at), pt(at + 1), pt(at + 2), pt(at + 3))),
+                    });
+                    at += *k as usize;
+                }
+                let subpaths = sp[s0..=s1].iter().map(|o| *o as usize - k0).collect();
+                let closed = closed[s0..s1].iter().map(|c| *c != 0).collect();
+                Ok((Path::new(segments, subpaths, closed), info[i]))
+            })
+            .collect()
     }
 
     /// `ImageOwned::new_default(size)` + `Path::fill` for a batch of independent paths (glyph batches): the images come back

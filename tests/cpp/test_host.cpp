@@ -156,6 +156,25 @@ static void test_stroke(GpuRasterizer& r) {
     for (size_t i = 0; i < s.points.size(); i++) CHECK(std::fabs(s.points[i] - pts[i]) < 1e-4);
 }
 
+// src/path.rs:1155-1176 (test_path_parse, the small cases) and :1098-1105 (test_bbox) through the batch parser
+static void test_parse(GpuRasterizer& r) {
+    auto b = r.parse_svg_batch({" M0,0L1-1L1,0ZL0,1 L1,1Z ", "M.5-3-11-.11", " m.5,-3 -11.5\n2.89 ", "M0,0 L", "M12 1C9.79 1 8 2.31 8 3.92"}, 64, 64, RGPU_ALIGN_MID);
+    CHECK(b.paths.size() == 5);
+    const Path& p0 = b.paths[0];
+    CHECK(p0.kinds.size() == 4 && p0.closed.size() == 2 && p0.closed[0] == 1 && p0.closed[1] == 1);
+    const double want0[] = {0, 0, 1, -1, 1, -1, 1, 0, 0, 0, 0, 1, 0, 1, 1, 1};
+    CHECK(p0.points.size() == 16);
+    for (int i = 0; i < 16; i++) CHECK(p0.points[i] == want0[i]);
+    for (int k = 1; k <= 2; k++) {
+        const Path& p = b.paths[k];
+        CHECK(p.kinds.size() == 1 && p.kinds[0] == 2 && p.closed.size() == 1 && p.closed[0] == 0);
+        const double want[] = {0.5, -3.0, -11.0, -0.11};
+        for (int i = 0; i < 4; i++) CHECK(std::fabs(p.points[i] - want[i]) < 1e-12);
+    }
+    CHECK(b.info[3].status == RGPU_PARSE_INVALID_SCALAR && b.info[3].error_offset == 6 && b.paths[3].is_empty());
+    CHECK(b.info[4].has_bbox && b.info[4].bbox[0] == 8.0 && b.info[4].bbox[2] == 12.0 && b.info[4].fit_width == 64);
+}
+
 int main() {
     GpuRasterizer r;
     CHECK(std::string(r.name()) == "gpu-signed-difference");
@@ -164,6 +183,7 @@ int main() {
     test_layers(r);
     test_scene(r);
     test_stroke(r);
+    test_parse(r);
     // NaN control point -> error (reference panics, src/path.rs:765-767)
     Path bad = Path::builder().move_to({0, 0}).quad_to({std::nan(""), 1}, {2, 2}).build();
     bool threw = false;

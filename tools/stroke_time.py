@@ -14,6 +14,7 @@ from rasterize_b200 import LineCap, LineJoin, StrokeStyle, assets
 import oracle as O
 
 rast = rb.GpuRasterizer()
+rast.set_profiling(True)
 for name in ("tv", "squirrel", "material"):
     p = assets.load_path(name)
     for style, label in ((StrokeStyle(0.5, LineJoin.Round, 4.0, LineCap.Round), "round/round"), (StrokeStyle(1.0), "miter/butt")):
@@ -24,6 +25,7 @@ for name in ("tv", "squirrel", "material"):
             t0 = time.perf_counter()
             dp = rast.stroke(p, style)
             ts.append(time.perf_counter() - t0)
+            st = rast.last_stage_ms()
             n = dp.counts()
             dp.free()
         op = O.OraclePath.from_flat(p.points, p.kinds, p.subpath_offsets, p.closed)
@@ -35,4 +37,4 @@ for name in ("tv", "squirrel", "material"):
             op.stroke(style.width, j, style.miter_limit, c)
             tc.append(time.perf_counter() - t0)
         print(f"{name:9s} {label:12s} segments {p.segments_count():7d} -> {n[1]:8d}  device call {np.median(ts) * 1e3:8.3f} ms (min {min(ts) * 1e3:.3f})"
-              f"  oracle {np.median(tc) * 1e3:8.3f} ms")
+              f"  kernels: pieces+count+scan {st[0]:.3f} ms, emit {st[2]:.3f} ms;  oracle {np.median(tc) * 1e3:8.3f} ms")
