@@ -30,62 +30,18 @@ SD_FN inline double powi(double a, int b) {
 struct Bytes {  // src/svg.rs:62-162
     const uint8_t* data;
     uint32_t len, pos;
-    // The text is read through a 16-byte window held in registers: with one thread per string, a byte load puts the 32
-    // lanes of a warp on 32 different cache lines — 32 L1 wavefronts for 32 bytes.  An aligned 16-byte load costs the same
-    // wavefronts and feeds the next 16 bytes from registers.  Windows that stick out of [0, len) are filled byte by byte.
-    uint64_t w0, w1;
-    int64_t wbase;  // index (relative to data) of the window's first byte; the window is empty when pos - wbase is not in [0, 16)
     SD_FN void init(const uint8_t* d, uint32_t n) {
         data = d;
         len = n;
         pos = 0;
-        w0 = w1 = 0;
-        wbase = -1000;
     }
-    SD_FN void load_window(uint32_t p) {
-        const uintptr_t addr = reinterpret_cast<uintptr_t>(data + p) & ~static_cast<uintptr_t>(15);
-        const int64_t base = static_cast<int64_t>(addr) - static_cast<int64_t>(reinterpret_cast<uintptr_t>(data));
-        wbase = base;
-        if (base >= 0 && base + 16 <= static_cast<int64_t>(len)) {
-            const uint64_t* q = reinterpret_cast<const uint64_t*>(addr);
-#if defined(__CUDA_ARCH__)
-            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(addr);
-            w0 = v.x;
-            w1 = v.y;
-            (void)q;
-#else
-            w0 = q[0];
-            w1 = q[1];
-#endif
-        } else {
-            w0 = w1 = 0;
-            for (int k = 0; k < 16; k++) {
-                const int64_t i = base + k;
-                if (i >= 0 && i < static_cast<int64_t>(len)) {
-                    const uint64_t byte = data[i];
-                    if (k < 8) w0 |= byte << (8 * k);
-                    else w1 |= byte << (8 * (k - 8));
-                }
-            }
-        }
-    }
-    SD_FN uint8_t at(uint32_t p) {  // p < len
-        uint64_t off = static_cast<uint64_t>(static_cast<int64_t>(p) - wbase);
-        if (off >= 16) {
-            load_window(p);
-            off = static_cast<uint64_t>(static_cast<int64_t>(p) - wbase);
-        }
-        const uint64_t w = (off & 8) ? w1 : w0;
-        return static_cast<uint8_t>(w >> (8 * (off & 7)));
-    }
-    SD_FN int peek() { return pos < len ? (int)at(pos) : -1; }
-    SD_FN int next() {
-        if (pos >= len) return -1;
-        return (int)at(pos++);
-    }
+    // Plain byte loads.  (Reading through an aligned 16-byte register window was measured: slower, see DESIGN.md.)
+    SD_FN uint8_t at(uint32_t p) const { return data[p]; }
+    SD_FN int peek() const { return pos < len ? (int)data[pos] : -1; }
+    SD_FN int next() { return pos < len ? (int)data[pos++] : -1; }
     SD_FN void separators() {
         while (pos < len) {
-            const uint8_t b = at(pos);
+            const uint8_t b = data[pos];
             if (b == ' ' || b == '\t' || b == '\r' || b == '\n' || b == ',') pos++;
             else break;
         }
