@@ -329,6 +329,14 @@ class Harness:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def gather_over_ranks(self, v: float) -> list:
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        if self.dist is None:
+            return [float(t.item())]
+        out = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
     def sum_over_ranks(self, v: float) -> float:
         t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
         if self.dist is not None:
@@ -381,7 +389,8 @@ def measure(hx: Harness, name: str, steps: int, warmup: int, with_cpu: bool, sam
     clocks = sampler.stop() if sampler else None
     launches = rast.last_counts()["launches"] - l0
     per_step = np.array([a.elapsed_time(b) for a, b in zip(starts, stops)])
-    ms_per_step = hx.max_over_ranks(float(per_step.sum())) / steps
+    rank_ms = [v / steps for v in hx.gather_over_ranks(float(per_step.sum()))]  # device time of every rank's steps
+    ms_per_step = max(rank_ms)
     counts = rast.last_counts() if has_work else dict(lines=0, line_refs=0, launches=0)
     # per-stage split (flatten / bin / raster) from the library's own events, sampled on a few extra steps
     stage_ms = np.zeros(3)
@@ -487,6 +496,7 @@ def measure(hx: Harness, name: str, steps: int, warmup: int, with_cpu: bool, sam
                    "flatness": 0.05, "l2": "flushed between timed steps (256 MiB memset outside the event pairs)", "parallelism": info["parallelism"]},
         "lines_per_s": round(total_lines / (ms_per_step * 1e-3), 1),
         "lines_per_step": int(total_lines), "gpu_launches": int(launches), "launches_per_step": launches / steps, "roofline": roofline,
+        "rank_ms_per_step": [round(v, 5) for v in rank_ms],
         "step_ms_min_med_max": [round(float(per_step.min()), 5), round(float(np.median(per_step)), 5), round(float(per_step.max()), 5)],
     }
     if "variant" in info:
@@ -611,7 +621,7 @@ def run_ours(args):
         for n in names:
             try:
                 r = measure(hx, n, max(5, min(args.steps, 30)), min(args.warmup, 5), with_cpu=(hx.world == 1), sample_clocks=False)
-                others[n] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "lines_per_s", "gpu_launches", "e2e", "cpu_baseline")
+                others[n] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "rank_ms_per_step", "scaling", "config", "lines_per_s", "gpu_launches", "e2e", "cpu_baseline")
                              if k in r}
                 others[n]["roofline"] = {k: r["roofline"][k] for k in ("kernel", "achieved", "frac", "kernel_ms", "stage_ms", "step_frac")}
             except Exception as e:  # a side measurement must not take the headline line down with it

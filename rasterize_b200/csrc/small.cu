@@ -52,6 +52,10 @@ constexpr int kGSlots = 1 << kGDepth;
 constexpr int kGCurves = kGThreads / kGSlots;                   // curves staged in shared memory at a time
 constexpr int kGQueue = 160;                                    // per-warp line queue: a round of 32 slots leaves ~120 lines of a glyph
 constexpr int kGIds = 8;                                        // per-warp scratch words (the count of deferred wide spans)
+#ifndef RGPU_GTALL
+#define RGPU_GTALL 6
+#endif
+constexpr int kGTall = RGPU_GTALL;                              // a line over more rows than this is spread over the lanes (deferred list)
 constexpr int kGWide = 64;                                      // spans over three or more columns, deferred to the end of a pass
 constexpr int kGDeep = 16;                                      // per-warp queue of nodes not flat at level kGDepth + 2
 constexpr int kGMaxBelow = kSlotDepth + kMaxStack - kGDepth - 3;  // walk_deep starts three levels below a slot root
@@ -273,7 +277,8 @@ __device__ __forceinline__ void span_wide(const Span& s, const Canvas& cv) {
 // Lane = line, 32 at a time: orientation, slope and row range (src/rasterize.rs:400-421), then the rows of the line in a loop
 // whose trip count is the warp's longest line (a glyph's lines cover 2.0 rows on average, 4 or fewer for 99 %: the loop runs
 // about four times per round with predicated lanes, and there is no span list to build and read back).  Spans over three or
-// more columns (7 %) are set aside with their prepared line and done together at the end of the pass.
+// more columns (7 %) are set aside with their prepared line and done together at the end of the pass, and so are all rows of a
+// line taller than kGTall rows (each glyph has one: its closing line), which would otherwise set the trip count for 32 lanes.
 // Measured and not kept: lines over one or two rows done in two predicated steps and the longer ones compacted for a second
 // pass (more code, same instruction count: 0.93 vs 0.87 ms per 20 000 glyphs).
 __device__ __noinline__ void accumulate_warp(const int count, const Canvas cv) {
@@ -284,11 +289,17 @@ __device__ __noinline__ void accumulate_warp(const int count, const Canvas cv) {
     int* const n_wide = reinterpret_cast<int*>(s_ids[warp]);  // count of deferred wide spans
     if (lane == 0) *n_wide = 0;
     __syncwarp();
+    // the deferred list: (prepared line, row) spans — those over three or more columns, and every row of a tall line.
+    // (Measured and not kept: spans over more than 8 / 16 columns done by the whole warp with lane = column — no change.)
     auto do_wide = [&]() {
         __syncwarp();
         const int nw = min(*n_wide, kGWide);
         __syncwarp();
-        for (int k = lane; k < nw; k += 32) span_wide(span_head(wide_p[k], wide_y[k], cv), cv);
+        for (int k = lane; k < nw; k += 32) {
+            const Span s = span_head(wide_p[k], wide_y[k], cv);
+            if (s.n <= 2) span_narrow(s, cv);
+            else span_wide(s, cv);
+        }
         if (lane == 0) *n_wide = 0;
         __syncwarp();
     };
@@ -312,9 +323,13 @@ __device__ __noinline__ void accumulate_warp(const int count, const Canvas cv) {
                 n = max(min(cv.H, (int)ceilf(by)) - rb, 0);  // lines above or below the canvas: no rows
             }
         }
-        const int n_max = __reduce_max_sync(kFull, n);
+        // A tall line (a glyph has one or two: the closing line, a long straight side) would hold the whole warp in the row
+        // loop with one active lane: its rows go to the deferred list instead, 32 lanes writing 32 rows at a time.
+        unsigned tall = __ballot_sync(kFull, n > kGTall);
+        const int n_main = n > kGTall ? 0 : n;
+        const int n_max = __reduce_max_sync(kFull, n_main);
         for (int k = 0; k < n_max; k++) {
-            if (k < n) {
+            if (k < n_main) {
                 const Span s = span_head(p, rb + k, cv);
                 if (s.n <= 2) {
                     span_narrow(s, cv);
@@ -330,6 +345,22 @@ __device__ __noinline__ void accumulate_warp(const int count, const Canvas cv) {
             }
         }
         __syncwarp();
+        while (tall) {
+            const int src = __ffs(tall) - 1;
+            tall &= tall - 1;
+            const float4 pl = make_float4(__shfl_sync(kFull, p.x, src), __shfl_sync(kFull, p.y, src), __shfl_sync(kFull, p.z, src),
+                                          __shfl_sync(kFull, p.w, src));
+            const int rbl = __shfl_sync(kFull, rb, src), nl = __shfl_sync(kFull, n, src);  // nl <= 64 = kGWide
+            if (*n_wide + nl > kGWide) do_wide();
+            const int base = min(*n_wide, kGWide);
+            __syncwarp();
+            for (int k = lane; k < nl; k += 32) {
+                wide_p[base + k] = pl;
+                wide_y[base + k] = (unsigned char)(rbl + k);
+            }
+            if (lane == 0) *n_wide = base + nl;
+            __syncwarp();
+        }
         if (*n_wide > kGWide - 32) do_wide();  // warp-uniform: every lane reads the same word after the loop
     }
     do_wide();
@@ -803,7 +834,13 @@ small_canvas_kernel(const JobDev* __restrict__ jobs, uint32_t job_first, const P
         // 144 slots: 29 per warp instead of 32, 32, 32, 32, 16), so that the warps reach the barrier before the row scan together
         const uint32_t n_slots = cn << kGDepth;
         const uint32_t per_warp = (n_slots + kGWarps - 1) / kGWarps;
+#ifdef RGPU_SLOTS_CONTIGUOUS
         const uint32_t sidx = (uint32_t)warp * per_warp + (uint32_t)lane;
+#else
+        // interleaved: warp w takes slots w, w + 5, w + 10, ... — the 8 slots of a curve (and with them its depth and its
+        // lines) are spread over all warps instead of making one warp's share
+        const uint32_t sidx = (uint32_t)lane * kGWarps + (uint32_t)warp;
+#endif
         const bool has_slot = (uint32_t)lane < per_warp && sidx < n_slots;
         const uint32_t ci = has_slot ? (sidx >> kGDepth) : cn, slot = sidx & (kGSlots - 1);
         walk_slot(ci < cn, &s_x[min(ci, (uint32_t)kGCurves - 1)][0], &s_y[min(ci, (uint32_t)kGCurves - 1)][0], ci < cn ? s_meta[ci] : 0, slot, w, cv, thr, status);

@@ -11,6 +11,7 @@ import sys
 rep = sys.argv[1]
 kre = sys.argv[2] if len(sys.argv) > 2 else None
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 50
+by_samples = len(sys.argv) > 4 and sys.argv[4] == "samples"  # order the lines by stall samples instead of instructions
 cmd = ["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]
 if kre:
     cmd += ["--kernel-name", "regex:" + kre]
@@ -40,5 +41,5 @@ print(f"# {rep}: {tot} warp-instructions, {tots} stall samples")
 for f, n in per_file.most_common():
     print(f"{100 * n / tot:5.1f}% instr  {100 * per_file_s[f] / tots:5.1f}% samples  {f}")
 print()
-for (f, ln), (n, s, text) in sorted(lines.items(), key=lambda kv: -kv[1][0])[:top]:
+for (f, ln), (n, s, text) in sorted(lines.items(), key=lambda kv: -kv[1][1 if by_samples else 0])[:top]:
     print(f"{100 * n / tot:5.1f}% instr {100 * s / tots:5.1f}% smp  {f}:{ln:<4d} {text}")
