@@ -297,39 +297,6 @@ __device__ __forceinline__ void span_wide(const SpanHead& h, const TileGeom& g, 
     row_touched[h.r] = 1;
 }
 
-// span_wide by a whole warp, lane = column: the same values as the serial loop — column k gets q(k) - q(k - 1) with
-// q(k) = the rounded running coverage at column k (h.fd at the span's last column), q(kb - 1) = `first` — every lane
-// computing both of its column's terms itself.
-constexpr int kCoopSpan = 24;
-template <bool SWZ>
-__device__ __forceinline__ void span_wide_lanes(const SpanHead& h, const TileGeom& g, int* __restrict__ cells, int* __restrict__ rowtot,
-                                                int* __restrict__ row_touched, const int lane) {
-    int* rowp = cells + h.r * g.pitch;
-    const int n = h.x1i - h.x0i;
-    const float sf = 1.0f / (float)(h.x1 - h.x0);
-    const float x0f = (float)(h.x0 - (double)h.x0i);
-    const float x1f = (float)(h.x1 - (double)h.x1i + 1.0);
-    const float c0 = 0.5f * sf * (1.0f - x0f) * (1.0f - x0f);
-    const float cl = 1.0f - 0.5f * sf * x1f * x1f;
-    const float a1 = sf * (1.5f - x0f);
-    auto cov = [&](int j) -> float {
-        float t = a1 + (float)(j - 1) * sf;
-        t = (j == 0) ? c0 : t;
-        return (j == n - 1) ? cl : t;
-    };
-    const int kb = max(h.x0i, g.cx0);
-    const int ke = min(h.x1i, g.tile_end - 1);
-    auto q = [&](int k) -> int {  // k in [kb - 1, ke]
-        if (k < h.x0i) return 0;
-        return (k == h.x1i) ? h.fd : to_fixed_f(h.d * cov(k - h.x0i), g.fix_scale);
-    };
-    for (int k = kb + lane; k <= ke; k += 32) atomicAdd(&rowp[swz<SWZ>(k - g.cx0)], q(k) - q(k - 1));
-    if (lane == 0) {
-        atomicAdd(&rowtot[h.r], q(ke) - q(kb - 1));
-        row_touched[h.r] = 1;
-    }
-}
-
 template <bool SWZ>
 __device__ __forceinline__ void span_row(double ax, double ay, double by, double dxdy, float dirf, int y, const TileGeom& g,
                                          int* __restrict__ cells, int* __restrict__ rowtot, int* __restrict__ row_touched) {
@@ -520,31 +487,15 @@ __device__ __forceinline__ void warp_accumulate_round(const double4 l, bool vali
         n_wide += __popc(wm);
     }
     __syncwarp();
-    // pass 2: the wide spans.  One lane each up to kCoopSpan columns; a longer one (a flat line crossing the tile: up to
-    // the tile's width in one row) would keep the warp — and, at the barrier before the scan, the CTA — waiting for one lane's
-    // column loop, so those are done by the whole warp, lane = column.
-    for (int i0 = 0; i0 < n_wide; i0 += 32) {
-        const int i = i0 + lane;
-        bool big = false;
-        if (i < n_wide) {
-            const int e = spans[i];
-            const int src = e >> ROWBITS;
-            const int slot = wbase + src;
-            const int y = g.row0 + (e & ((1 << ROWBITS) - 1));
-            const SpanHead h = span_head(p_ax[slot], p_ay[slot], p_by[slot], p_dxdy[slot], ((neg >> src) & 1u) ? -1.0f : 1.0f, y, g);
-            big = min(h.x1i, g.tile_end - 1) - max(h.x0i, g.cx0) > kCoopSpan;
-            if (!big) span_wide<SWZ>(h, g, cells, rowtot, row_touched);
-        }
-        unsigned bm = __ballot_sync(0xffffffffu, big);
-        while (bm) {
-            const int e = spans[i0 + __ffs(bm) - 1];
-            bm &= bm - 1;
-            const int src = e >> ROWBITS;
-            const int slot = wbase + src;
-            const int y = g.row0 + (e & ((1 << ROWBITS) - 1));
-            const SpanHead h = span_head(p_ax[slot], p_ay[slot], p_by[slot], p_dxdy[slot], ((neg >> src) & 1u) ? -1.0f : 1.0f, y, g);
-            span_wide_lanes<SWZ>(h, g, cells, rowtot, row_touched, lane);
-        }
+    // pass 2: the wide spans, one lane each.  (Measured and not kept: spans over more than 24 / 64 columns done by the whole
+    // warp with lane = column — c5, c2 and c3 unchanged to the third digit.)
+    for (int i = lane; i < n_wide; i += 32) {
+        const int e = spans[i];
+        const int src = e >> ROWBITS;
+        const int slot = wbase + src;
+        const int y = g.row0 + (e & ((1 << ROWBITS) - 1));
+        const SpanHead h = span_head(p_ax[slot], p_ay[slot], p_by[slot], p_dxdy[slot], ((neg >> src) & 1u) ? -1.0f : 1.0f, y, g);
+        span_wide<SWZ>(h, g, cells, rowtot, row_touched);
     }
     __syncwarp();
 }
