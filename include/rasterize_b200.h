@@ -154,6 +154,9 @@ typedef struct {
  * treated here as having the tangent of its first two points; NaN input that would spin the reference's arc iterator for
  * ever yields no arc. */
 int rgpu_path_stroke(rgpu_ctx* ctx, const rgpu_path* path, const rgpu_stroke_style* style, rgpu_dpath** out);
+/* The same for a path that is already on the device (an uploaded path, an element of an uploaded or parsed batch): its
+ * control points are read where they lie; only its item list (8 B per segment) visits the host, to lay out the unit table. */
+int rgpu_dpath_stroke(rgpu_ctx* ctx, const rgpu_dpath* src, const rgpu_stroke_style* style, rgpu_dpath** out);
 /* Size of a device path made by rgpu_path_upload / rgpu_path_stroke, and its download in the `rgpu_path` encoding:
  * points[2 * n_points], kinds[n_segments], subpath_offsets[n_subpaths + 1], closed[n_subpaths]. */
 int rgpu_dpath_info(const rgpu_dpath* p, uint32_t* n_points, uint32_t* n_segments, uint32_t* n_subpaths);

@@ -534,10 +534,16 @@ class DevicePath:
     """Device-resident path (`rgpu_dpath`): an uploaded host path, or (`stroke=`) the outline of its stroke computed on the
     device (`Path::stroke`, src/path.rs:374-415), which never visits the host unless `download()` is called."""
 
-    def __init__(self, rast: "GpuRasterizer", path: Path, stroke: "StrokeStyle | None" = None):
+    def __init__(self, rast: "GpuRasterizer", path, stroke: "StrokeStyle | None" = None):
         self.rast = rast
         self.path = path if stroke is None else None
         h = C.c_void_p()
+        if not isinstance(path, Path):  # a device path (DevicePath or a raw rgpu_dpath handle, e.g. an element of a batch): stroke it in place
+            st = stroke._c()
+            src = path.h if isinstance(path, DevicePath) else C.c_void_p(int(path))
+            rast._check(ffi.lib().rgpu_dpath_stroke(rast.ctx, src, C.byref(st), C.byref(h)))
+            self.h = h
+            return
         c = path._c()
         if stroke is None:
             rast._check(ffi.lib().rgpu_path_upload(rast.ctx, C.byref(c), C.byref(h)))
@@ -826,9 +832,10 @@ class GpuRasterizer:
     def upload(self, path: Path) -> DevicePath:
         return DevicePath(self, path)
 
-    def stroke(self, path: Path, style: StrokeStyle) -> DevicePath:
+    def stroke(self, path, style: StrokeStyle) -> DevicePath:
         """`Path::stroke` (src/path.rs:374-415) on the device: the outline as a device-resident path, usable wherever an
-        uploaded path is (`Job.path`); `.download()` gives the host `Path` the reference returns."""
+        uploaded path is (`Job.path`); `.download()` gives the host `Path` the reference returns.  `path` = a host `Path`, or a
+        path that is already on the device (`DevicePath`, or the handle of a batch element: `DevicePathBatch.handle(i)`)."""
         return DevicePath(self, path, stroke=style)
 
     def _cjobs(self, jobs: Iterable[Job]):

@@ -1,16 +1,71 @@
 // Host side of rgpu_path_stroke / rgpu_dpath_info / rgpu_dpath_download (included at the end of context.cu).
 
+namespace {
+
+int check_stroke_style(rgpu_ctx* ctx, const rgpu_stroke_style* style) {
+    if (!style) return fail(ctx, RGPU_ERR_INVALID, "style is NULL");
+    if (style->line_join < RGPU_JOIN_MITER || style->line_join > RGPU_JOIN_ROUND) return fail(ctx, RGPU_ERR_INVALID, "bad line_join");
+    if (style->line_cap < RGPU_CAP_BUTT || style->line_cap > RGPU_CAP_ROUND) return fail(ctx, RGPU_ERR_INVALID, "bad line_cap");
+    return RGPU_OK;
+}
+
+// The three passes over a unit table.  The source control points come from the host (`host_pts`, copied into the scratch
+// block) or are already on the device (`dev_pts`; unit offsets index it directly).
+int stroke_units_to_path(rgpu_ctx* ctx, const std::vector<StrokeUnit>& units, const double* host_pts, const double2* dev_pts, uint32_t n_points,
+                         const rgpu_stroke_style* style, rgpu_dpath** out);
+
+}  // namespace
+
 int rgpu_path_stroke(rgpu_ctx* ctx, const rgpu_path* path, const rgpu_stroke_style* style, rgpu_dpath** out) {
     if (!ctx || !out) return RGPU_ERR_INVALID;
     *out = nullptr;
     CK(ctx, cudaSetDevice(ctx->device));
     int rc = validate_path(ctx, path);
     if (rc) return rc;
-    if (!style) return fail(ctx, RGPU_ERR_INVALID, "style is NULL");
-    if (style->line_join < RGPU_JOIN_MITER || style->line_join > RGPU_JOIN_ROUND) return fail(ctx, RGPU_ERR_INVALID, "bad line_join");
-    if (style->line_cap < RGPU_CAP_BUTT || style->line_cap > RGPU_CAP_ROUND) return fail(ctx, RGPU_ERR_INVALID, "bad line_cap");
+    if ((rc = check_stroke_style(ctx, style))) return rc;
     std::vector<StrokeUnit> units;
     build_stroke_units(path->kinds, path->n_segments, path->subpath_offsets, path->closed, path->n_subpaths, units);
+    return stroke_units_to_path(ctx, units, path->points, nullptr, path->n_points, style, out);
+}
+
+int rgpu_dpath_stroke(rgpu_ctx* ctx, const rgpu_dpath* src, const rgpu_stroke_style* style, rgpu_dpath** out) {
+    if (!ctx || !out || !src) return RGPU_ERR_INVALID;
+    *out = nullptr;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = check_stroke_style(ctx, style))) return rc;
+    // the path's structure comes from its item list (8 B per segment; the control points stay where they are)
+    std::vector<uint2> items(src->n_items);
+    if (src->n_items) CK(ctx, cudaMemcpyAsync(items.data(), src->items, sizeof(uint2) * src->n_items, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<StrokeUnit> units;
+    units.reserve(2 * items.size());
+    size_t first = 0;  // first item of the current subpath
+    for (size_t i = 0; i < items.size(); i++) {
+        if (!(items[i].y & kItemClosing)) continue;
+        const bool closed = (items[i].y & kItemExplicitClosed) != 0;
+        const uint32_t sp_start = items[i].y & kItemIndexMask, sp_end = items[i].x;
+        uint32_t u0 = (uint32_t)units.size();
+        for (size_t k = first; k < i; k++) units.push_back(StrokeUnit{items[k].x, items[k].y, u0, 0u});
+        if (closed) {
+            units.push_back(StrokeUnit{sp_start, kUnitCloser | (kCloserForward << 16), u0, sp_end});
+            u0 = (uint32_t)units.size();
+        }
+        for (size_t k = i; k > first; k--) {
+            const uint32_t cap = (!closed && k == i) ? kUnitCap : 0u;
+            units.push_back(StrokeUnit{items[k - 1].x, items[k - 1].y | kUnitReversed | cap, u0, 0u});
+        }
+        units.push_back(StrokeUnit{sp_start, kUnitCloser | ((closed ? kCloserBackward : kCloserOpen) << 16), u0, sp_end});
+        first = i + 1;
+    }
+    return stroke_units_to_path(ctx, units, nullptr, src->pts, src->n_points, style, out);
+}
+
+namespace {
+
+int stroke_units_to_path(rgpu_ctx* ctx, const std::vector<StrokeUnit>& units, const double* host_pts, const double2* dev_pts, uint32_t n_points,
+                         const rgpu_stroke_style* style, rgpu_dpath** out) {
+    int rc;
     if (units.size() > 0x7fffffffull) return fail(ctx, RGPU_ERR_INVALID, "path too large");
     const uint32_t n = (uint32_t)units.size();
     auto* dp = new rgpu_dpath();
@@ -23,7 +78,7 @@ int rgpu_path_stroke(rgpu_ctx* ctx, const rgpu_path* path, const rgpu_stroke_sty
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t o_units = 0;
     const size_t o_pts = up(o_units + sizeof(StrokeUnit) * n);
-    const size_t o_cnt = up(o_pts + sizeof(double2) * path->n_points);
+    const size_t o_cnt = up(o_pts + (host_pts ? sizeof(double2) * n_points : 0));
     const size_t o_off = up(o_cnt + sizeof(uint32_t) * 4 * stride);
     const size_t o_first = up(o_off + sizeof(uint32_t) * 4 * stride);
     const size_t o_last = up(o_first + stroke_piece_bytes() * n);
@@ -38,7 +93,7 @@ int rgpu_path_stroke(rgpu_ctx* ctx, const rgpu_path* path, const rgpu_stroke_sty
     if ((rc = ensure_dev(ctx, ctx->stroke_buf, total))) return bail(rc);
     char* base = static_cast<char*>(ctx->stroke_buf.p);
     auto* d_units = reinterpret_cast<StrokeUnit*>(base + o_units);
-    auto* d_pts = reinterpret_cast<double2*>(base + o_pts);
+    const double2* d_pts = host_pts ? reinterpret_cast<const double2*>(base + o_pts) : dev_pts;
     auto* d_cnt = reinterpret_cast<uint32_t*>(base + o_cnt);
     auto* d_off = reinterpret_cast<uint32_t*>(base + o_off);
     cudaStream_t st = ctx->stream;
@@ -51,7 +106,7 @@ int rgpu_path_stroke(rgpu_ctx* ctx, const rgpu_path* path, const rgpu_stroke_sty
         }                                                                    \
     } while (0)
     CKB(cudaMemcpyAsync(d_units, units.data(), sizeof(StrokeUnit) * n, cudaMemcpyHostToDevice, st));
-    CKB(cudaMemcpyAsync(d_pts, path->points, sizeof(double2) * path->n_points, cudaMemcpyHostToDevice, st));
+    if (host_pts && n_points) CKB(cudaMemcpyAsync(base + o_pts, host_pts, sizeof(double2) * n_points, cudaMemcpyHostToDevice, st));
     CKB(cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t) * 4 * stride, st));
     StrokeStyleDev sd{style->width, style->miter_limit, style->line_join, style->line_cap};
     // rgpu_set_profiling: stage 0 = pieces + count + scans, stage 1 = the host's turn (sizes, allocation), stage 2 = emit
@@ -98,6 +153,8 @@ int rgpu_path_stroke(rgpu_ctx* ctx, const rgpu_path* path, const rgpu_stroke_sty
     *out = dp;
     return RGPU_OK;
 }
+
+}  // namespace
 
 int rgpu_dpath_info(const rgpu_dpath* p, uint32_t* n_points, uint32_t* n_segments, uint32_t* n_subpaths) {
     if (!p) return RGPU_ERR_INVALID;

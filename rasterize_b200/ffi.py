@@ -79,7 +79,7 @@ SYMBOLS = [
     "rgpu_path_upload_batch", "rgpu_path_batch_get", "rgpu_path_batch_free", "rgpu_batch_create", "rgpu_batch_render", "rgpu_batch_free",
     "rgpu_fill_batch_host", "rgpu_mask_banded_host", "rgpu_multi_create", "rgpu_multi_destroy", "rgpu_multi_device_count",
     "rgpu_multi_last_error", "rgpu_multi_fill_batch_host", "rgpu_multi_mask_banded_host", "rgpu_set_winding_bits",
-    "rgpu_path_stroke", "rgpu_dpath_info", "rgpu_dpath_download", "rgpu_parse_svg_batch", "rgpu_path_batch_info", "rgpu_path_batch_download",
+    "rgpu_path_stroke", "rgpu_dpath_stroke", "rgpu_dpath_info", "rgpu_dpath_download", "rgpu_parse_svg_batch", "rgpu_path_batch_info", "rgpu_path_batch_download",
 ]
 
 
@@ -114,6 +114,7 @@ def lib():
     sig("rgpu_path_upload", i32, vp, C.POINTER(CPath), C.POINTER(vp))
     sig("rgpu_path_free", None, vp, vp)
     sig("rgpu_path_stroke", i32, vp, C.POINTER(CPath), C.POINTER(CStrokeStyle), C.POINTER(vp))
+    sig("rgpu_dpath_stroke", i32, vp, vp, C.POINTER(CStrokeStyle), C.POINTER(vp))
     pu32_ = C.POINTER(C.c_uint32)
     sig("rgpu_dpath_info", i32, vp, pu32_, pu32_, pu32_)
     sig("rgpu_dpath_download", i32, vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_uint8), pu32_, C.POINTER(C.c_uint8))

@@ -132,6 +132,7 @@ extern "C" {
     fn rgpu_fill(ctx: *mut RgpuCtx, path: *const RgpuPath, tr: *const f64, fill_rule: c_int, paint: *const RgpuPaint, path_bbox: *const f64, img: *mut f32, shape: RgpuShape) -> c_int;
     fn rgpu_path_free(ctx: *mut RgpuCtx, p: *mut RgpuDpath);
     fn rgpu_path_stroke(ctx: *mut RgpuCtx, path: *const RgpuPath, style: *const RgpuStrokeStyle, out: *mut *mut RgpuDpath) -> c_int;
+    fn rgpu_dpath_stroke(ctx: *mut RgpuCtx, src: *const RgpuDpath, style: *const RgpuStrokeStyle, out: *mut *mut RgpuDpath) -> c_int;
     fn rgpu_dpath_info(p: *const RgpuDpath, n_points: *mut u32, n_segments: *mut u32, n_subpaths: *mut u32) -> c_int;
     fn rgpu_dpath_download(ctx: *mut RgpuCtx, p: *const RgpuDpath, points: *mut f64, kinds: *mut u8, subpath_offsets: *mut u32, closed: *mut u8) -> c_int;
     fn rgpu_parse_svg_batch(ctx: *mut RgpuCtx, text: *const c_char, text_offsets: *const u32, n_paths: usize, opt: *const RgpuParseOptions, out: *mut *mut RgpuDpathBatch, info: *mut RgpuParseInfo) -> c_int;

@@ -105,6 +105,34 @@ def test_empty_and_errors(rast):
         rast._check(ffi.lib().rgpu_path_stroke(rast.ctx, C.byref(c), C.byref(st), C.byref(h)))
 
 
+def test_stroke_of_device_resident_paths(rast):
+    """rgpu_dpath_stroke: the source is already on the device — an uploaded path, an element of an uploaded batch, an element of
+    a batch parsed from text — and gives the same outline as the host-path entry point, bit for bit."""
+    paths = [assets.load_path(n) for n in ("squirrel", "tv", "rust")]
+    style = StrokeStyle(0.7, LineJoin.Miter, 4.0, LineCap.Square)
+    want = [rast.stroke(p, style).download() for p in paths]
+    up = rast.upload(paths[1])
+    got = rast.stroke(up, style).download()
+    assert np.array_equal(got.points, want[1].points) and np.array_equal(got.kinds, want[1].kinds) and np.array_equal(got.closed, want[1].closed)
+    dpb = rast.upload_batch(rb.PathBatch.from_paths(paths))
+    for i in range(3):
+        g = rast.stroke(dpb.handle(i), style).download()
+        assert np.array_equal(g.points, want[i].points) and np.array_equal(g.subpath_offsets, want[i].subpath_offsets)
+    # text -> parse -> stroke -> mask without the geometry visiting the host, against the oracle's parse + stroke + mask
+    import oracle as O
+    svg = paths[1].to_svg_path()
+    parsed, info = rast.parse_svg_batch([svg], fit=(512, 512, rb.Align.Mid))
+    outline = rast.stroke(parsed.handle(0), StrokeStyle(0.5, LineJoin.Round, 4.0, LineCap.Round))
+    tr = info["fit_tr"][0]
+    canvas = rast.device_alloc(512 * 512 * 4)
+    rast.render_batch([rb.Job(outline, tr, rb.FillRule.NonZero, ffi.JOB_MASK, canvas, 512, 512, 512)], independent=True)
+    img = rast.to_host(canvas, (512, 512), np.float32)
+    rast.device_free(canvas)
+    ref = np.zeros((512, 512))
+    O.OraclePath.parse(svg).stroke(0.5, "round", 4.0, "round").mask(tr, O.NONZERO, ref)
+    assert img.max() > 0.9 and np.abs(img - ref).max() <= 1e-4
+
+
 def test_config5_from_device_stroke(rast):
     """config 5 without the host round trip: tv.path stroked on the device and the outline rasterized as it lies in HBM,
     against the same canvas rendered from the oracle-stroked fixture (4096 rows of the 32768-wide canvas)."""
