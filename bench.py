@@ -149,7 +149,8 @@ def glyph_path(rb, seed: int):
 
 
 C4_TOTAL_GLYPHS = 100_000  # BASELINE configs[3]
-C5_BANDS = 64              # scanline bands of the canvas; rank r takes the contiguous block [r * 64 / N, (r + 1) * 64 / N) as one job
+C5_BANDS = 256             # scanline bands of the canvas (128 rows each): rank r renders a contiguous block of them as one job; the cut
+                           # points balance the blocks' cost (rows + spans), see build_workload
 
 
 def c4_total() -> int:
@@ -166,7 +167,7 @@ def workload_label(name: str) -> str:
         return "c2: data/material.path (21106 segments) fitted to 4096x4096, Rasterizer::mask, nonzero"
     if name == "c5":
         return ("c5: data/tv.path stroked (w=0.5 round/round) on a 32768x32768 canvas, Rasterizer::mask, nonzero, split into "
-                f"{int(os.environ.get('RB_BANDS', C5_BANDS))} scanline bands, a contiguous block of bands per GPU")
+                f"{int(os.environ.get('RB_BANDS', C5_BANDS))} scanline bands, a contiguous cost-balanced block of bands per GPU")
     if name == "c1":
         return "c1: examples/rasterize scene of data/squirrel.path at 512 px (checkerboard + fill over #f0f0f0), Scene::render + RGBA8 export"
     return "c3: data/firefox.scene Scene::render at 2048x2048, 14 linear/radial gradient fills, + RGBA8 export"
@@ -235,7 +236,18 @@ def build_workload(name: str, rb, rast, rank: int, world: int, torch):
         c5 = ex["tv_stroked"]["c5"]
         w, hfull = c5["size"]
         bands = int(os.environ.get("RB_BANDS", C5_BANDS))
-        mine = list(range(bands * rank // world, bands * (rank + 1) // world))  # equal rows = equal output bytes, which bound the raster kernel
+        # Blocks of bands with equal COST, not equal rows: a band costs its rows (empty tiles are bound by the bytes written) plus
+        # its (line, row) spans (tiles with geometry are bound by issue) — with equal rows the 8 ranks took 0.115 .. 0.152 ms, the
+        # glyph sits in the middle of the canvas (sharding.band_costs; RB_C5_EQUAL_ROWS=1 for the A/B).
+        if os.environ.get("RB_C5_EQUAL_ROWS") or world == 1:
+            cuts = [bands * k // world for k in range(world + 1)]
+        else:
+            costs = sharding.band_costs(rast.flatten(path, c5["tr"], True), hfull, bands, w)
+            cuts = [sharding.shard_range(bands, k, world, costs)[0] for k in range(world)] + [bands]
+        if os.environ.get("RB_C5_BLOCK"):  # diagnosis: time one block of bands on one GPU, e.g. RB_C5_BLOCK=24:32
+            a, b = (int(v) for v in os.environ["RB_C5_BLOCK"].split(":"))
+            cuts = [a if k <= rank else b for k in range(world + 1)]
+        mine = list(range(cuts[rank], cuts[rank + 1]))
         dp = rast.upload(path)
         jobs, canvases, rows = [], [], 0
         runs = []  # consecutive bands of this rank are one job (flattened once): at N = 1 the whole canvas
@@ -253,7 +265,7 @@ def build_workload(name: str, rb, rast, rank: int, world: int, torch):
         prepared = rast.prepare_batch(jobs)
         info = dict(canvas=[w, hfull], items=len(mine), total_items=bands, pixels_per_step=w * rows, total_pixels=w * hfull,
                     in_bytes=path.input_bytes() * len(mine), out_bytes=4 * w * rows, host_path=path, host_tr=np.array(c5["tr"]), host_size=(w, hfull),
-                    bands=bands, keep=[dp, canvases, prepared], scaling="strong",
+                    bands=bands, band_block=(cuts[rank], cuts[rank + 1]), keep=[dp, canvases, prepared], scaling="strong",
                     parallelism=f"{len(mine)} of {bands} scanline bands ({rows} rows) on this rank, {world} ranks, no collective")
         return (lambda sync=False: rast.submit_prepared(prepared, independent=True, sync=sync)), info
     if name in ("c1", "c3"):
@@ -461,7 +473,7 @@ def measure(hx: Harness, name: str, steps: int, warmup: int, with_cpu: bool, sam
     elif name == "c5":
         path, tr, (w, h) = info["host_path"], info["host_tr"], info["host_size"]
         img = rast.host_alloc((h, w), np.float32)  # the whole canvas, pinned; this rank fills the rows of its bands
-        b0, b1 = info["bands"] * hx.rank // hx.world, info["bands"] * (hx.rank + 1) // hx.world
+        b0, b1 = info["band_block"]
         call = lambda: rast.mask_banded(path, tr, img, rb.FillRule.NonZero, n_bands=info["bands"], band_first=b0, band_count=b1 - b0)  # noqa: E731
         dt = time_calls(hx, call, max(2, min(4, steps)), 1)
         h2d, d2h = rast.last_transfer_bytes()

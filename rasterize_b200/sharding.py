@@ -34,6 +34,27 @@ def shard_range(n_items: int, rank: int, world: int, weights: Optional[Sequence[
     return cuts[rank], cuts[rank + 1]
 
 
+#: what one (line, row) span costs the tiled raster path, in rows of a 32768-wide f32 canvas: fitted to the eight ranks of config 5
+#: on 8 B200s (profiles/bench/r2v_bench_n8.json: rank time = 0.1156 ms per 4096 rows + 0.465 ns per span, residual < 0.003 ms)
+SPAN_COST_ROWS = 0.0165
+
+
+def band_costs(lines, height: int, n_bands: int, width: int = 32768) -> np.ndarray:
+    """Relative cost of every scanline band of a canvas for the tiled raster path: its rows (the kernel is bound by the bytes it
+    writes where a band is empty) plus its (line, row) spans (tiles that hold geometry are bound by issue, not bytes).  `lines` =
+    the flattened outline in canvas space, (n, 4) as `GpuRasterizer.flatten` returns it.  With equal rows the ranks of config 5
+    took 0.115 .. 0.152 ms on 8 GPUs: the glyph sits in the middle of the canvas."""
+    L = np.asarray(lines, dtype=np.float64).reshape(-1, 4)
+    ylo, yhi = np.minimum(L[:, 1], L[:, 3]), np.maximum(L[:, 1], L[:, 3])
+    out = np.zeros(n_bands)
+    for b in range(n_bands):
+        y0, y1 = band_rows(height, b, n_bands)
+        m = (yhi > y0) & (ylo < y1)
+        spans = float((np.minimum(yhi[m], y1) - np.maximum(ylo[m], y0)).sum())
+        out[b] = (y1 - y0) * (width / 32768.0) + SPAN_COST_ROWS * spans
+    return out
+
+
 def band_rows(height: int, rank: int, world: int, align: int = 8) -> Tuple[int, int]:
     """Rows [y0, y1) of the band rank `rank` renders; cut points are multiples of `align` (the raster tile height)
     except the last one."""

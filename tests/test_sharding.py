@@ -106,3 +106,25 @@ def test_gloo_world2_band_and_batch_sharding():
     assert err_band < 1e-12   # bands stitched == unsharded mask
     assert err_batch == 0.0
     assert tmax == 2.0
+
+
+def test_band_costs_balance_blocks():
+    """Cost-balanced blocks of scanline bands (bench.py config 5 at N > 1): the blocks tile the canvas, and a block in the dense
+    middle of the outline gets fewer rows than an empty one."""
+    import numpy as np
+    from rasterize_b200 import sharding
+    h, nb = 32768, 256
+    rng = np.random.default_rng(0)
+    y0 = rng.uniform(9000, 23000, 5000)
+    lines = np.stack([rng.uniform(0, 32768, 5000), y0, rng.uniform(0, 32768, 5000), y0 + rng.uniform(-900, 900, 5000)], axis=1)
+    costs = sharding.band_costs(lines, h, nb, 32768)
+    assert costs.shape == (nb,) and np.all(costs >= 128 - 1e-9) and costs[0] == 128 and costs[nb // 2] > 2 * 128
+    for world in (1, 2, 3, 8):
+        cuts = [sharding.shard_range(nb, k, world, costs)[0] for k in range(world)] + [nb]
+        assert cuts[0] == 0 and all(a <= b for a, b in zip(cuts, cuts[1:]))
+        assert [sharding.shard_range(nb, k, world, costs) for k in range(world)] == list(zip(cuts[:-1], cuts[1:]))
+        block = [costs[a:b].sum() for a, b in zip(cuts[:-1], cuts[1:])]
+        assert max(block) <= costs.sum() / world + costs.max()  # within one band of the ideal
+    cuts = [sharding.shard_range(nb, k, 8, costs)[0] for k in range(8)] + [nb]
+    sizes = np.diff(cuts)
+    assert sizes[0] > sizes[3] and sizes[7] > sizes[4]
