@@ -942,6 +942,17 @@ int rgpu_create(int device, double flatness, rgpu_ctx** out) {
     }
     ctx->status.cap = 256;
     std::memset(ctx->h_status, 0, sizeof(Status));
+    {
+        // The device paths rgpu_path_stroke / rgpu_parse_svg_batch hand out come from the device's stream-ordered pool
+        // (cudaMallocAsync): keep what is freed in the pool instead of returning it to the driver at every synchronisation,
+        // so that a loop of stroke / parse calls does not pay cudaMalloc each time.
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     *out = ctx;
     return RGPU_OK;
 }

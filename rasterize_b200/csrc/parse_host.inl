@@ -100,8 +100,8 @@ int rgpu_parse_svg_batch(rgpu_ctx* ctx, const char* text, const uint32_t* text_o
             }
     }
     if (n_items) {
-        CKB(cudaMalloc(reinterpret_cast<void**>(&b->pts), sizeof(double2) * std::max<uint32_t>(total_pts, 1)));
-        CKB(cudaMalloc(reinterpret_cast<void**>(&b->items), sizeof(uint2) * 2 * n_items));
+        CKB(cudaMallocAsync(reinterpret_cast<void**>(&b->pts), sizeof(double2) * std::max<uint32_t>(total_pts, 1), st));  // freed with cudaFree
+        CKB(cudaMallocAsync(reinterpret_cast<void**>(&b->items), sizeof(uint2) * 2 * n_items, st));
         CKB(cudaMemcpyAsync(d_base, bases.data(), sizeof(ParseEmitBase) * n_chunks, cudaMemcpyHostToDevice, st));
         if (prof) CKB(cudaEventRecord(ctx->ev[2], st));
         launch_parse_emit(d_text, d_coff, n_chunks, d_base, b->pts, b->items, b->items + n_items, st);

@@ -52,6 +52,9 @@ constexpr int kGSlots = 1 << kGDepth;
 constexpr int kGCurves = kGThreads / kGSlots;                   // curves staged in shared memory at a time
 constexpr int kGQueue = 160;                                    // per-warp line queue: a round of 32 slots leaves ~120 lines of a glyph
 constexpr int kGIds = 8;                                        // per-warp scratch words (the count of deferred wide spans)
+#ifndef RGPU_ROW_UNROLL
+#define RGPU_ROW_UNROLL 1
+#endif
 #ifndef RGPU_GTALL
 #define RGPU_GTALL 6
 #endif
@@ -328,7 +331,7 @@ __device__ __noinline__ void accumulate_warp(const int count, const Canvas cv) {
         unsigned tall = __ballot_sync(kFull, n > kGTall);
         const int n_main = n > kGTall ? 0 : n;
         const int n_max = __reduce_max_sync(kFull, n_main);
-        for (int k = 0; k < n_max; k++) {
+        auto row = [&](const int k) {
             if (k < n_main) {
                 const Span s = span_head(p, rb + k, cv);
                 if (s.n <= 2) {
@@ -343,7 +346,15 @@ __device__ __noinline__ void accumulate_warp(const int count, const Canvas cv) {
                     }
                 }
             }
+        };
+#if RGPU_ROW_UNROLL == 2
+        for (int k = 0; k < n_max; k += 2) {
+            row(k);
+            row(k + 1);
         }
+#else
+        for (int k = 0; k < n_max; k++) row(k);
+#endif
         __syncwarp();
         while (tall) {
             const int src = __ffs(tall) - 1;

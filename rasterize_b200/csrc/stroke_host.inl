@@ -136,8 +136,8 @@ int stroke_units_to_path(rgpu_ctx* ctx, const std::vector<StrokeUnit>& units, co
     dp->n_segments = n_seg;
     dp->n_subpaths = n_sub;
     if (dp->n_items) {
-        CKB(cudaMalloc(reinterpret_cast<void**>(&dp->pts), sizeof(double2) * std::max<uint32_t>(n_pts, 1)));
-        CKB(cudaMalloc(reinterpret_cast<void**>(&dp->items), sizeof(uint2) * 2 * dp->n_items));
+        CKB(cudaMallocAsync(reinterpret_cast<void**>(&dp->pts), sizeof(double2) * std::max<uint32_t>(n_pts, 1), st));  // freed with cudaFree (free_path)
+        CKB(cudaMallocAsync(reinterpret_cast<void**>(&dp->items), sizeof(uint2) * 2 * dp->n_items, st));
         dp->items_packed = dp->items + dp->n_items;
         if (prof) CKB(cudaEventRecord(ctx->ev[2], st));
         launch_stroke_units(true, d_units, n, d_pts, sd, d_cnt, base + o_first, base + o_last, d_off, dp->pts, dp->items, dp->items_packed, st);

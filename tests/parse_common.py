@@ -128,6 +128,18 @@ def random_svg(rng, n_cmds=40, arcs=True) -> str:
     return "".join(parts)
 
 
+def garbage_strings(seed: int, n: int):
+    """Random strings over the grammar's alphabet (no arc commands: degenerate arcs have no reference answer): almost all are
+    malformed, and the kind and byte offset of the first error must be the reference's."""
+    rng = np.random.default_rng(seed)
+    alpha = "MmLlHhVvCcSsQqTtZz0123456789.-+eE ,\n\t"
+    out = []
+    for _ in range(n):
+        s = "".join(alpha[j] for j in rng.integers(0, len(alpha), int(rng.integers(0, 60))))
+        out.append("M" + s if rng.random() < 0.6 else s)
+    return out
+
+
 def oracle_parse(text: str):
     """-> dict(points, kinds, subpath_offsets, closed, bbox | None) or dict(error=(kind, offset))"""
     try:

@@ -27,6 +27,10 @@ def compare(got, want, exact, scale=1.0):
     bit when `exact`, else within a few ulp of the coordinates' magnitude (round joins: libm against CUDA trigonometry)."""
     gp, gk, gs, gc = got
     wp, wk, ws, wc = want
+    if len(ws) == 0:  # the oracle exports an empty path without the leading 0
+        ws = np.zeros(1, dtype=np.uint32)
+    if len(gs) == 0:
+        gs = np.zeros(1, dtype=np.uint32)
     assert np.array_equal(np.asarray(gk, dtype=np.uint8), np.asarray(wk, dtype=np.uint8)), "segment kinds differ"
     assert np.array_equal(np.asarray(gs, dtype=np.uint32), np.asarray(ws, dtype=np.uint32)), "subpath offsets differ"
     assert np.array_equal(np.asarray(gc, dtype=np.uint8), np.asarray(wc, dtype=np.uint8)), "closed flags differ"
@@ -68,4 +72,43 @@ def synthetic_paths():
         if sp % 2:
             b.close()
     out["random_lines_quads"] = b.build()
+    return out
+
+
+def random_paths(seed: int, n: int):
+    """Random paths for the walk's decomposition: mixed kinds, open and closed subpaths, repeated points, zero-length and nearly
+    zero-length segments, cusps, collinear runs, tiny and huge coordinates."""
+    from rasterize_b200 import PathBuilder
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        b = PathBuilder()
+        scale = float(rng.choice([1.0, 1.0, 30.0, 1e-3, 1e4]))
+        for _sp in range(int(rng.integers(1, 4))):
+            cur = rng.uniform(-10, 10, 2) * scale
+            b.move_to(tuple(cur))
+
+            def nxt():
+                mode = rng.integers(0, 10)
+                if mode == 0:
+                    return cur.copy()                      # repeated point
+                if mode == 1:
+                    return cur + rng.uniform(-1, 1, 2) * 1e-17 * scale  # closer than EPSILON at scale 1
+                if mode == 2:
+                    return cur + np.array([rng.uniform(-5, 5) * scale, 0.0])  # collinear runs
+                return cur + rng.uniform(-6, 6, 2) * scale
+
+            for _seg in range(int(rng.integers(1, 9))):
+                k = rng.integers(0, 3)
+                if k == 0:
+                    p = nxt(); b.line_to(tuple(p)); cur = p
+                elif k == 1:
+                    c, p = nxt(), nxt(); b.quad_to(tuple(c), tuple(p)); cur = p
+                else:
+                    c1, c2, p = nxt(), nxt(), nxt(); b.cubic_to(tuple(c1), tuple(c2), tuple(p)); cur = p
+            if rng.random() < 0.5:
+                b.close()
+        p = b.build()
+        if p.segments_count():
+            out.append(p)
     return out

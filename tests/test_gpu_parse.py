@@ -9,7 +9,7 @@ import pytest
 import oracle as O
 import rasterize_b200 as rb
 from rasterize_b200 import Align, assets, ffi, synth
-from parse_common import (CORNER_STRINGS, DEGENERATE_ARCS, ERROR_STRINGS, REFERENCE_STRINGS, check_batch, oracle_parse, random_arcs, random_svg,
+from parse_common import (CORNER_STRINGS, DEGENERATE_ARCS, ERROR_STRINGS, REFERENCE_STRINGS, check_batch, garbage_strings, oracle_parse, random_arcs, random_svg,
                           svg_of)
 
 pytestmark = pytest.mark.gpu
@@ -52,6 +52,13 @@ def test_random_grammar(rast):
     got, info = device_parse(rast, strings, (128, 128, Align.Mid))
     check_batch(strings, got, info, fit=(128, 128, 1))
     assert (info["status"] == 0).mean() > 0.9
+
+
+def test_garbage_input_reports_the_references_errors(rast):
+    strings = garbage_strings(321, 3000)
+    got, info = device_parse(rast, strings, (64, 64, Align.Mid))
+    check_batch(strings, got, info, fit=(64, 64, 1))
+    assert (info["status"] != 0).mean() > 0.9
 
 
 def test_random_arcs(rast):

@@ -9,7 +9,7 @@ import pytest
 
 import rasterize_b200 as rb
 from rasterize_b200 import LineCap, LineJoin, StrokeStyle, assets, ffi, sharding
-from stroke_common import STYLES, compare, exact_case, oracle_stroke, synthetic_paths
+from stroke_common import STYLES, compare, exact_case, oracle_stroke, random_paths, synthetic_paths
 
 pytestmark = pytest.mark.gpu
 
@@ -86,6 +86,20 @@ def test_corner_cases_match_oracle(rast):
                 compare(got, want, exact=exact_case(p.kinds, join, cap))
             except AssertionError as e:
                 raise AssertionError(f"{name} {width} {join} {cap}: {e}") from None
+
+
+def test_random_paths_match_oracle(rast):
+    """300 random paths with degenerate pieces (repeated points, segments shorter than EPSILON, collinear runs, cusps, tiny and
+    huge scales): same structure as the oracle in every style; points bit for bit where no arc is involved."""
+    for i, p in enumerate(random_paths(23, 300)):
+        for width, join, ml, cap in STYLES[:3] if i % 2 else STYLES[3:]:
+            w = width * (1.0 if i % 3 else 0.01)
+            got = device_stroke(rast, p, w, join, ml, cap)
+            want = oracle_stroke(p.points, p.kinds, p.subpath_offsets, p.closed, w, join, ml, cap)
+            try:
+                compare(got, want, exact=exact_case(p.kinds, join, cap), scale=float(np.abs(p.points).max()))
+            except AssertionError as e:
+                raise AssertionError(f"path {i} {w} {join} {cap}: {e}") from None
 
 
 def test_empty_and_errors(rast):

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from rasterize_b200 import assets
-from parse_common import CORNER_STRINGS, DEGENERATE_ARCS, ERROR_STRINGS, INFO_DTYPE, REFERENCE_STRINGS, check_batch, pack, random_arcs, random_svg, svg_of
+from parse_common import CORNER_STRINGS, DEGENERATE_ARCS, ERROR_STRINGS, INFO_DTYPE, REFERENCE_STRINGS, check_batch, garbage_strings, pack, random_arcs, random_svg, svg_of
 
 ROOT = FsPath(__file__).resolve().parent.parent
 
@@ -97,3 +97,10 @@ def test_long_strings_with_errors_and_relative_groups(harness):
     assert run_harness.last_chunks > len(strings) + 20
     check_batch(strings, got, info, fit=(256, 256, 1), exact_arcs=True)
     assert int(info["status"][2]) == 2 and int(info["status"][5]) == 2 and int(info["status"][1]) == 0
+
+
+def test_garbage_input_reports_the_references_errors(harness):
+    strings = garbage_strings(123, 3000)
+    got, info = run_harness(harness, strings, (64, 64, 1))
+    check_batch(strings, got, info, fit=(64, 64, 1), exact_arcs=True)
+    assert (info["status"] != 0).mean() > 0.9

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from rasterize_b200 import assets
-from stroke_common import CAPS, JOINS, STYLES, compare, oracle_stroke, synthetic_paths
+from stroke_common import CAPS, JOINS, STYLES, compare, oracle_stroke, random_paths, synthetic_paths
 
 ROOT = FsPath(__file__).resolve().parent.parent
 
@@ -92,3 +92,16 @@ def test_corner_cases_match_oracle(harness):
                 compare(got, want, exact=True)
             except AssertionError as e:
                 raise AssertionError(f"{name} {width} {join} {cap}: {e}") from None
+
+
+def test_random_paths_match_oracle(harness):
+    """400 random paths with degenerate pieces, every style: the unit decomposition follows the reference's serial walk bit for bit."""
+    for i, p in enumerate(random_paths(17, 400)):
+        for width, join, ml, cap in STYLES[:4] if i % 2 else STYLES[2:]:
+            w = width * (1.0 if i % 3 else 0.01)
+            got = run_harness(harness, p, w, join, ml, cap)
+            want = oracle_stroke(p.points, p.kinds, p.subpath_offsets, p.closed, w, join, ml, cap)
+            try:
+                compare(got, want, exact=True)
+            except AssertionError as e:
+                raise AssertionError(f"path {i} {w} {join} {cap}: {e}") from None
