@@ -52,6 +52,9 @@ constexpr int kGSlots = 1 << kGDepth;
 constexpr int kGCurves = kGThreads / kGSlots;                   // curves staged in shared memory at a time
 constexpr int kGQueue = 160;                                    // per-warp line queue: a round of 32 slots leaves ~120 lines of a glyph
 constexpr int kGIds = 8;                                        // per-warp scratch words (the count of deferred wide spans)
+#ifndef RGPU_TWO_CLASS
+#define RGPU_TWO_CLASS 1
+#endif
 #ifndef RGPU_GTALL
 #define RGPU_GTALL 6
 #endif
@@ -272,7 +275,8 @@ __device__ __forceinline__ void span_wide(const Span& s, const Canvas& cv) {
     cell_add(s.at + s.n, s.fd - prev);  // x1i <= wci < tile_end
 }
 
-// Accumulate the first `count` lines of this warp's queue.  Every end point lies inside the canvas columns [0, wc] and
+// Accumulate this warp's queue: `counts` = short lines (at the front) | other lines (at the back) << 16; a group of 32 never
+// mixes the two.  Every end point lies inside the canvas columns [0, wc] and
 // within (-64, 128) of its rows, so the clipping branches of signed_difference_line (x > width, x < 0) cannot trigger.
 // Lane = line, 32 at a time: orientation, slope and row range (src/rasterize.rs:400-421), then the rows of the line in a loop
 // whose trip count is the warp's longest line (a glyph's lines cover 2.0 rows on average, 4 or fewer for 99 %: the loop runs
@@ -281,7 +285,9 @@ __device__ __forceinline__ void span_wide(const Span& s, const Canvas& cv) {
 // line taller than kGTall rows (each glyph has one: its closing line), which would otherwise set the trip count for 32 lanes.
 // Measured and not kept: lines over one or two rows done in two predicated steps and the longer ones compacted for a second
 // pass (more code, same instruction count: 0.93 vs 0.87 ms per 20 000 glyphs).
-__device__ __noinline__ void accumulate_warp(const int count, const Canvas cv) {
+__device__ __noinline__ void accumulate_warp(const int counts, const Canvas cv) {
+    const int count_a = counts & 0xffff, count_b = counts >> 16;  // short lines from the front, the others from the back
+    const int groups_a = (count_a + 31) >> 5, groups = groups_a + ((count_b + 31) >> 5);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float4* __restrict__ q = s_lineq[warp];
     float4* __restrict__ wide_p = s_wide_p[warp];
@@ -303,12 +309,13 @@ __device__ __noinline__ void accumulate_warp(const int count, const Canvas cv) {
         if (lane == 0) *n_wide = 0;
         __syncwarp();
     };
-    for (int b0 = 0; b0 < count; b0 += 32) {
-        const int i = b0 + lane;
+    for (int g = 0; g < groups; g++) {
+        const bool back = g >= groups_a;
+        const int i = ((back ? g - groups_a : g) << 5) + lane;
         int n = 0, rb = 0;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < count) {
-            const float4 l = q[i];
+        if (i < (back ? count_b : count_a)) {
+            const float4 l = q[back ? kGQueue - 1 - i : i];
             float ax = l.x, ay = l.y, bx = l.z, by = l.w;
             float dirf = 1.0f;
             if (ay > by) {
@@ -390,7 +397,8 @@ __device__ __forceinline__ bool point_safe(double x, double y, const Canvas& cv)
 
 // Per-warp state of the flatten walk
 struct Warp {
-    int qn, dn;            // warp-uniform fill levels of the line queue / the deep-node queue
+    int qn, dn;            // warp-uniform fill levels of the line queue / the deep-node queue.  qn = short | tall << 16: lines over
+                           // at most two rows fill the queue from the front, the others from the back (see emit_site)
     uint32_t lines;        // leaves found by this lane
     unsigned lt_mask;
     int warp;
@@ -399,16 +407,33 @@ struct Warp {
 // Warp-collective emit site: lanes with `pred` hold a leaf (x0, y0) -> (x1, y1) of a "safe" curve.  No call, no drain:
 // the callers drain at points where little is live and size the queue for what can arrive in between.
 __device__ __forceinline__ void emit_site(bool pred, double x0, double y0, double x1, double y1, Warp& w) {
+    const float fx0 = (float)x0, fy0 = (float)y0, fx1 = (float)x1, fy1 = (float)y1;
+#if RGPU_TWO_CLASS
+    // Two classes, kept apart in the queue: the row loop of accumulate_warp runs to the longest line of a group of 32, and
+    // 75 % of a glyph's lines cover one or two rows — mixed with the others they idle through the long ones' iterations
+    // (measured: 12.9 of 32 lanes active).  Sorted into two classes a warp's ~110 lines take 57 instead of 81 loop iterations
+    // per glyph (as many as a full sort by row count would give).  The test is only a hint: any assignment is correct.
+    const bool big = ceilf(fmaxf(fy0, fy1)) - floorf(fminf(fy0, fy1)) > 2.0f;
+    const unsigned ma = __ballot_sync(kFull, pred && !big), mb = __ballot_sync(kFull, pred && big);
+    if (pred) {
+        w.lines++;
+        const int pos = big ? kGQueue - 1 - ((w.qn >> 16) + __popc(mb & w.lt_mask)) : (w.qn & 0xffff) + __popc(ma & w.lt_mask);
+        s_lineq[w.warp][pos] = make_float4(fx0, fy0, fx1, fy1);
+    }
+    w.qn += __popc(ma) + (__popc(mb) << 16);
+#else
     const unsigned mf = __ballot_sync(kFull, pred);
     if (pred) {
         w.lines++;
-        s_lineq[w.warp][w.qn + __popc(mf & w.lt_mask)] = make_float4((float)x0, (float)y0, (float)x1, (float)y1);
+        s_lineq[w.warp][(w.qn & 0xffff) + __popc(mf & w.lt_mask)] = make_float4(fx0, fy0, fx1, fy1);
     }
     w.qn += __popc(mf);
+#endif
 }
+__device__ __forceinline__ int queue_fill(int qn) { return (qn & 0xffff) + (qn >> 16); }
 // make room for `room` more lines
 __device__ __forceinline__ void ensure_room(Warp& w, int room, const Canvas& cv) {
-    if (w.qn > kGQueue - room) {
+    if (queue_fill(w.qn) > kGQueue - room) {
         __syncwarp();
         accumulate_warp(w.qn, cv);
         w.qn = 0;
@@ -551,10 +576,11 @@ __device__ __forceinline__ void walk_slot(const bool has, const double* rx, cons
         }
         slow = slow && act;  // this slot's whole subtree on the f64 path, after the walk
         act = act && !slow;
+        // queue budget of the first half of the walk: the slot root or its first child, then that child's two children
+        ensure_room(w, 96, cv);
         if (act && !leaf) leaf = nd_flatness(nd, kind) < thr;
         // The two levels below the slot root in straight-line code without a call: every child's flatness is tested as
-        // soon as it exists.  Queue budget: the queue is empty at the start of a round and a lane emits at most two lines
-        // in each half of the walk (slot root or first child, then that child's two children).
+        // soon as it exists.  Queue budget: a lane emits at most three lines in the first half of the walk and two in the second.
         emit_site(act && leaf, nd.x0, nd.y0, nd_endx(nd, kind), nd_endy(nd, kind), w);
         const bool go = act && !leaf;
         unsigned ovf = 0;
@@ -582,12 +608,8 @@ __device__ __forceinline__ void walk_slot(const bool has, const double* rx, cons
             level1(nd_half<true>(nd, kind), std::integral_constant<int, 1>{});
         }
         if (w.dn >= 16) drain_deep_keep(w, 15, thr, cv, status);
-        // the round's lines in one pass
-        if (w.qn) {
-            __syncwarp();
-            accumulate_warp(w.qn, cv);
-            w.qn = 0;
-        }
+        // The round's lines stay in the queue: the leaves of the deep nodes and the line items join them, and the kernel drains
+        // everything in one pass at the end (fewer, fuller groups of 32).  The next round makes room first (ensure_room above).
         // rare: nodes the deep queue could not take, and slots of curves on the f64 path
         if (ovf) {
             for (int site = 0; site < 4; site++)
