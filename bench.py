@@ -317,6 +317,18 @@ class Harness:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device (rasterize_b200 has no CPU fallback)")
         torch.cuda.set_device(self.local_rank)
+        # Run this rank (and the pinned buffers and host threads it creates from here on) on the CPUs next to its GPU: the
+        # e2e legs are bound by device writes into host memory, and a pinned buffer on the far socket costs PCIe bandwidth.
+        self.affinity = None
+        if not os.environ.get("RB_NO_AFFINITY"):
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.local_rank)
+                pynvml.nvmlDeviceSetCpuAffinity(h)
+                self.affinity = len(os.sched_getaffinity(0))
+            except Exception as e:  # no NVML, a container without the topology: keep the inherited affinity
+                self.affinity = f"unchanged ({type(e).__name__})"
         self.dist = None
         if self.world > 1:
             import torch.distributed as dist
@@ -509,6 +521,7 @@ def measure(hx: Harness, name: str, steps: int, warmup: int, with_cpu: bool, sam
         "lines_per_s": round(total_lines / (ms_per_step * 1e-3), 1),
         "lines_per_step": int(total_lines), "gpu_launches": int(launches), "launches_per_step": launches / steps, "roofline": roofline,
         "rank_ms_per_step": [round(v, 5) for v in rank_ms],
+        "host_cpus_of_this_rank": hx.affinity,
         "step_ms_min_med_max": [round(float(per_step.min()), 5), round(float(np.median(per_step)), 5), round(float(per_step.max()), 5)],
     }
     if "variant" in info:
