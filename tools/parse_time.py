@@ -50,5 +50,5 @@ for _ in range(5):
 t0 = time.perf_counter()
 O.OraclePath.parse(s).bbox()
 tc = time.perf_counter() - t0
-print(f"material as ONE string ({len(s) / 1e6:.2f} MB, {int(info['n_segments'][0])} segments): device call {np.median(ts) * 1e3:.2f} ms (one thread walks the "
-      f"whole string), oracle {tc * 1e3:.2f} ms")
+print(f"material as ONE string ({len(s) / 1e6:.2f} MB, {int(info['n_segments'][0])} segments): device call {np.median(ts) * 1e3:.2f} ms (cut at its "
+      f"absolute movetos), oracle {tc * 1e3:.2f} ms")
