@@ -250,15 +250,16 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
         if ((rc = ensure_dev(ctx, ctx->ring_slab[i], chunk * px * slab_elem))) return rc;
         if (out_format == RGPU_OUT_RGBA8 && (rc = ensure_dev(ctx, ctx->ring_rgba[i], chunk * px * 4))) return rc;
     }
-    // all control points in one copy, straight from the caller's array
+    // The control points go up chunk by chunk, next to the chunk's items (both are small against the chunk's output): one
+    // copy of all of them up front — 115 MB for 100 000 glyphs, from the caller's pageable array — held the first kernel
+    // back by ~10 ms of the 130 ms call, while a chunk's share overlaps the download of the chunk before it.
     std::vector<uint32_t> pt_off;
     segment_point_offsets(all, pt_off);
-    if ((rc = ensure_dev(ctx, ctx->tmp_pts, std::max<size_t>(sizeof(double2) * all->n_points, 16)))) return rc;
     ctx->staged_items_valid = false;
-    if (all->n_points)
-        CK(ctx, cudaMemcpyAsync(ctx->tmp_pts.p, all->points, sizeof(double2) * all->n_points, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->last_h2d_bytes += sizeof(double2) * all->n_points;
-    double2* const d_pts = static_cast<double2*>(ctx->tmp_pts.p);
+    auto first_point = [&](size_t path) -> uint32_t {
+        const uint32_t sp = pso[path];
+        return pt_off[sp < all->n_subpaths ? all->subpath_offsets[sp] : all->n_segments];
+    };
     static const double ident[6] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0};
     std::vector<uint2> ref, packed;
     std::vector<uint32_t> item_off, n_curves;
@@ -270,8 +271,15 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
         const int slot = (int)(c % ring);
         ref.clear();
         packed.clear();
-        build_range_items(all, pso, pt_off, a, b, 0, ref, packed, item_off, n_curves);
+        const uint32_t pt_a = first_point(a), pt_b = first_point(b);
+        build_range_items(all, pso, pt_off, a, b, pt_a, ref, packed, item_off, n_curves);
         const size_t n_items = ref.size();
+        if ((rc = ensure_dev(ctx, ctx->tmp_pts, std::max<size_t>(sizeof(double2) * (pt_b - pt_a), 16)))) return rc;
+        double2* const d_pts = static_cast<double2*>(ctx->tmp_pts.p);
+        // (the previous chunk's kernel has completed — submit_sync — so its points may be overwritten)
+        if (pt_b > pt_a)
+            CK(ctx, cudaMemcpyAsync(d_pts, all->points + 2 * (size_t)pt_a, sizeof(double2) * (pt_b - pt_a), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->last_h2d_bytes += sizeof(double2) * (pt_b - pt_a);
         if ((rc = ensure_dev(ctx, ctx->tmp_items, sizeof(uint2) * std::max<size_t>(2 * n_items, 1)))) return rc;
         if ((rc = ensure_pinned(ctx, ctx->h_items, ctx->h_items_cap, std::max<size_t>(2 * n_items, 1)))) return rc;
         // (ensure_* and the status check of the previous chunk have synchronised the stream: the staging is free)
@@ -289,7 +297,7 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
             d.items_packed = d_items + n_items + item_off[i];
             d.n_items = item_off[i + 1] - item_off[i];
             d.n_curves = n_curves[i];
-            d.n_points = all->n_points;
+            d.n_points = pt_b - pt_a;
             rgpu_job& j = jobs[i];
             std::memset(&j, 0, sizeof(j));
             j.path = &d;
