@@ -50,7 +50,10 @@ constexpr int kGWarps = kGThreads / 32;
 constexpr int kGDepth = 3;                                      // slot cut: 8 slot threads per curve
 constexpr int kGSlots = 1 << kGDepth;
 constexpr int kGCurves = kGThreads / kGSlots;                   // curves staged in shared memory at a time
-constexpr int kGQueue = 160;                                    // per-warp line queue: a round of 32 slots leaves ~120 lines of a glyph
+#ifndef RGPU_GQUEUE
+#define RGPU_GQUEUE 160
+#endif
+constexpr int kGQueue = RGPU_GQUEUE;                                    // per-warp line queue: a round of 32 slots leaves ~120 lines of a glyph
 constexpr int kGIds = 8;                                        // per-warp scratch words (the count of deferred wide spans)
 #ifndef RGPU_TWO_CLASS
 #define RGPU_TWO_CLASS 1
