@@ -126,6 +126,12 @@ struct rgpu_ctx {
     static constexpr int kRing = 3;
     cudaStream_t copy_stream = nullptr;
     DevBuf ring_slab[kRing], ring_rgba[kRing];
+    unsigned char* h_chunk[2] = {nullptr, nullptr};       // pinned staging of a chunk's control points + item lists (rgpu_fill_batch_host)
+    size_t h_chunk_cap[2] = {0, 0};
+    float* h_alpha[kRing] = {nullptr, nullptr, nullptr};  // pinned staging of the coverage share of a chunk (split download)
+    size_t h_alpha_cap[kRing] = {0, 0, 0};
+    double expand_frac = 0.6;  // share of a chunk's images that crosses PCIe as coverage and is expanded by host threads (adapts)
+    double expand_dir = 1.0, expand_last = 0.0;  // hill climbing on the call's time per pixel
     cudaEvent_t ring_done[kRing] = {nullptr, nullptr, nullptr}, ring_copied[kRing] = {nullptr, nullptr, nullptr};
     // optional stage timing
     bool profiling = false;
@@ -969,6 +975,7 @@ void rgpu_destroy(rgpu_ctx* ctx) {
     for (int i = 0; i < rgpu_ctx::kRing; i++) {
         if (ctx->ring_slab[i].p) cudaFree(ctx->ring_slab[i].p);
         if (ctx->ring_rgba[i].p) cudaFree(ctx->ring_rgba[i].p);
+        if (ctx->h_alpha[i]) cudaFreeHost(ctx->h_alpha[i]);
         if (ctx->ring_done[i]) cudaEventDestroy(ctx->ring_done[i]);
         if (ctx->ring_copied[i]) cudaEventDestroy(ctx->ring_copied[i]);
     }
@@ -978,6 +985,8 @@ void rgpu_destroy(rgpu_ctx* ctx) {
     if (ctx->h_jobs) cudaFreeHost(ctx->h_jobs);
     if (ctx->h_paints) cudaFreeHost(ctx->h_paints);
     if (ctx->h_items) cudaFreeHost(ctx->h_items);
+    for (int i = 0; i < 2; i++)
+        if (ctx->h_chunk[i]) cudaFreeHost(ctx->h_chunk[i]);
     if (ctx->h_pts) cudaFreeHost(ctx->h_pts);
     for (int i = 0; i < 4; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

@@ -75,6 +75,35 @@ void build_range_items(const rgpu_path* all, const uint32_t* pso, const std::vec
     }
 }
 
+// Host side of the split download of rgpu_fill_batch_host: `n_px` pixels of coverage (f32) become premultiplied LinColor
+// pixels colour * alpha — the very multiplication the kernel does for a plain solid paint (small.cu finish_rows), so the
+// bytes are the ones the device would have sent.  Non-temporal stores: the destination is written once and not read here.
+void expand_alpha(const float* alpha, const float colour[4], float* out, size_t n_px) {
+#if defined(__SSE2__)
+    const __m128 c = _mm_loadu_ps(colour);
+    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        for (size_t i = 0; i < n_px; i++) _mm_stream_ps(out + 4 * i, _mm_mul_ps(c, _mm_set1_ps(alpha[i])));
+        _mm_sfence();
+        return;
+    }
+#endif
+    for (size_t i = 0; i < n_px; i++) {
+        const float a = alpha[i];
+        out[4 * i] = colour[0] * a;
+        out[4 * i + 1] = colour[1] * a;
+        out[4 * i + 2] = colour[2] * a;
+        out[4 * i + 3] = colour[3] * a;
+    }
+}
+
+// the condition under which RGPU_JOB_RENDER writes colour * alpha (small.cu: `plain`)
+bool plain_solid(const rgpu_paint* p) {
+    if (!p || p->kind != RGPU_PAINT_SOLID) return false;
+    for (int k = 0; k < 4; k++)
+        if (!(p->solid[k] >= 0.0f) || std::signbit(p->solid[k]) || !(p->solid[k] < 3e38f)) return false;
+    return true;
+}
+
 size_t out_elem_bytes(int fmt) { return fmt == RGPU_OUT_LINCOLOR ? 16 : 4; }
 
 }  // namespace
@@ -237,6 +266,7 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
             CK(ctx, cudaEventCreateWithFlags(&ctx->ring_copied[i], cudaEventDisableTiming));
         }
     }
+    const auto t_call = std::chrono::steady_clock::now();
     const size_t px = (size_t)width * height;
     const size_t slab_elem = coverage ? 4 : 16;                  // what the kernels write
     const size_t out_elem = out_elem_bytes(out_format);          // what crosses PCIe
@@ -246,10 +276,52 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
     chunk = std::min(chunk, n_paths);
     const size_t n_chunks = (n_paths + chunk - 1) / chunk;
     const int ring = (int)std::min<size_t>(rgpu_ctx::kRing, n_chunks);
+    // Split download (LinColor output of a plain solid paint on canvases the fused small-canvas kernel takes): a share of every
+    // chunk is rendered as coverage (4 B per pixel over PCIe instead of 16) and turned into colour * alpha by host threads
+    // while the rest of the chunk arrives as LinColor by DMA — two producers into the caller's buffer instead of one PCIe
+    // link.  The share adapts from call to call (ctx->expand_frac); RGPU_E2E_EXPAND=0 switches it off.
+    static const bool expand_enabled = !(getenv("RGPU_E2E_EXPAND") && atoi(getenv("RGPU_E2E_EXPAND")) == 0);
+    const bool can_expand = expand_enabled && out_format == RGPU_OUT_LINCOLOR && plain_solid(paint) && width <= 64 && height <= 64 && n_paths >= 64;
+    static const char* fixed_share = getenv("RGPU_E2E_EXPAND_FRAC");  // diagnosis: a fixed share instead of the adaptive one
+    if (fixed_share) ctx->expand_frac = std::min(0.95, std::max(0.0, atof(fixed_share)));
     for (int i = 0; i < ring; i++) {
         if ((rc = ensure_dev(ctx, ctx->ring_slab[i], chunk * px * slab_elem))) return rc;
-        if (out_format == RGPU_OUT_RGBA8 && (rc = ensure_dev(ctx, ctx->ring_rgba[i], chunk * px * 4))) return rc;
+        if ((out_format == RGPU_OUT_RGBA8 || can_expand) && (rc = ensure_dev(ctx, ctx->ring_rgba[i], chunk * px * 4))) return rc;
+        if (can_expand && (rc = ensure_pinned(ctx, ctx->h_alpha[i], ctx->h_alpha_cap[i], chunk * px))) return rc;
     }
+    if (can_expand && !ctx->pool) {
+        unsigned nthr = std::thread::hardware_concurrency();
+        if (const char* e = getenv("RGPU_HOST_THREADS")) nthr = (unsigned)std::max(1, atoi(e));
+        ctx->pool.reset(new rgpu::HostPool(std::max(1u, std::min(nthr ? nthr : 4u, 32u))));
+    }
+    float colour[4] = {0.f, 0.f, 0.f, 0.f};
+    if (can_expand) std::memcpy(colour, paint->solid, sizeof(colour));
+    struct Pending { size_t first_path, n; int slot; };  // coverage downloaded (or on its way) and not yet expanded
+    std::vector<Pending> pending;
+    double wait_copy_ms = 0.0, wait_pool_ms = 0.0, prep_ms = 0.0, submit_ms = 0.0;
+    auto ms_since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    // hand the oldest downloaded coverage to the pool (after the expansion before it has finished: its staging buffer is the
+    // next one to be overwritten)
+    auto expand_oldest = [&]() -> int {
+        const Pending pd = pending.front();
+        pending.erase(pending.begin());
+        auto t0 = std::chrono::steady_clock::now();
+        CK(ctx, cudaEventSynchronize(ctx->ring_copied[pd.slot]));
+        wait_copy_ms += ms_since(t0);
+        t0 = std::chrono::steady_clock::now();
+        ctx->pool->wait();
+        wait_pool_ms += ms_since(t0);
+        const float* alpha = ctx->h_alpha[pd.slot];
+        float* dst = static_cast<float*>(out_host) + pd.first_path * px * 4;
+        const size_t total = pd.n * px, parts = std::min<size_t>(ctx->pool->size() * 2, std::max<size_t>(1, total / 4096));
+        for (size_t q = 0; q < parts; q++) {
+            const size_t lo = total * q / parts, hi = total * (q + 1) / parts;
+            ctx->pool->submit([=] { expand_alpha(alpha + lo, colour, dst + 4 * lo, hi - lo); });
+        }
+        return RGPU_OK;
+    };
     // The control points go up chunk by chunk, next to the chunk's items (both are small against the chunk's output): one
     // copy of all of them up front — 115 MB for 100 000 glyphs, from the caller's pageable array — held the first kernel
     // back by ~10 ms of the 130 ms call, while a chunk's share overlaps the download of the chunk before it.
@@ -261,34 +333,107 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
         return pt_off[sp < all->n_subpaths ? all->subpath_offsets[sp] : all->n_segments];
     };
     static const double ident[6] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0};
-    std::vector<uint2> ref, packed;
-    std::vector<uint32_t> item_off, n_curves;
+    // Host preparation of a chunk — its item lists, and its control points moved into pinned staging (an asynchronous DMA
+    // instead of the driver's synchronous bounce of pageable memory) — runs on a helper thread one chunk ahead of the
+    // submissions: ~0.8 ms per chunk of 2048 glyphs, 40 ms of a 100 000-glyph call when it sat between the submissions.
+    // Two staging slots; a slot is released after its chunk's submission has synchronised the stream (its copies are done).
+    size_t max_pts = 1, max_items = 1;
+    for (size_t c = 0; c < n_chunks; c++) {
+        const size_t a = c * chunk, b = std::min(n_paths, a + chunk);
+        max_pts = std::max<size_t>(max_pts, first_point(b) - first_point(a));
+        const uint32_t sa = pso[a], sb = pso[b];
+        max_items = std::max<size_t>(max_items, (size_t)(all->subpath_offsets[sb] - all->subpath_offsets[sa]) + (sb - sa));
+    }
+    const size_t stage_items_at = (sizeof(double2) * max_pts + 255) & ~(size_t)255;
+    for (int i = 0; i < 2; i++)
+        if ((rc = ensure_pinned(ctx, ctx->h_chunk[i], ctx->h_chunk_cap[i], stage_items_at + sizeof(uint2) * 2 * max_items))) return rc;
+    if ((rc = ensure_dev(ctx, ctx->tmp_pts, std::max<size_t>(sizeof(double2) * max_pts, 16)))) return rc;
+    if ((rc = ensure_dev(ctx, ctx->tmp_items, sizeof(uint2) * 2 * max_items))) return rc;
+    struct Prep {
+        std::vector<uint2> ref, packed;
+        std::vector<uint32_t> item_off, n_curves;
+        uint32_t pt_a = 0, pt_b = 0;
+    } preps[2];
+    auto prepare = [&](size_t c) {
+        Prep& pr = preps[c & 1];
+        const size_t a = c * chunk, b = std::min(n_paths, a + chunk);
+        pr.ref.clear();
+        pr.packed.clear();
+        pr.pt_a = first_point(a);
+        pr.pt_b = first_point(b);
+        build_range_items(all, pso, pt_off, a, b, pr.pt_a, pr.ref, pr.packed, pr.item_off, pr.n_curves);
+        unsigned char* const st = ctx->h_chunk[c & 1];
+        if (pr.pt_b > pr.pt_a) std::memcpy(st, all->points + 2 * (size_t)pr.pt_a, sizeof(double2) * (pr.pt_b - pr.pt_a));
+        std::memcpy(st + stage_items_at, pr.ref.data(), sizeof(uint2) * pr.ref.size());
+        std::memcpy(st + stage_items_at + sizeof(uint2) * pr.ref.size(), pr.packed.data(), sizeof(uint2) * pr.packed.size());
+    };
+    struct Ahead {  // the helper thread and its handshake; the destructor stops and joins it on every way out
+        std::mutex m;
+        std::condition_variable cv;
+        size_t produced = 0, consumed = 0;
+        bool stop = false;
+        std::thread th;
+        ~Ahead() {
+            {
+                std::lock_guard<std::mutex> l(m);
+                stop = true;
+            }
+            cv.notify_all();
+            if (th.joinable()) th.join();
+        }
+    } ahead;
+    if (n_chunks > 1)
+        ahead.th = std::thread([&] {
+            for (size_t c = 0; c < n_chunks; c++) {
+                {
+                    std::unique_lock<std::mutex> l(ahead.m);
+                    ahead.cv.wait(l, [&] { return ahead.stop || c < ahead.consumed + 2; });
+                    if (ahead.stop) return;
+                }
+                prepare(c);
+                {
+                    std::lock_guard<std::mutex> l(ahead.m);
+                    ahead.produced = c + 1;
+                }
+                ahead.cv.notify_all();
+            }
+        });
     std::vector<rgpu_dpath> dps(chunk);
     std::vector<rgpu_job> jobs(chunk);
     int status = RGPU_OK;
     for (size_t c = 0; c < n_chunks && status == RGPU_OK; c++) {
         const size_t a = c * chunk, b = std::min(n_paths, a + chunk), n = b - a;
         const int slot = (int)(c % ring);
-        ref.clear();
-        packed.clear();
-        const uint32_t pt_a = first_point(a), pt_b = first_point(b);
-        build_range_items(all, pso, pt_off, a, b, pt_a, ref, packed, item_off, n_curves);
-        const size_t n_items = ref.size();
-        if ((rc = ensure_dev(ctx, ctx->tmp_pts, std::max<size_t>(sizeof(double2) * (pt_b - pt_a), 16)))) return rc;
+        const auto t_prep = std::chrono::steady_clock::now();
+        if (n_chunks > 1) {
+            std::unique_lock<std::mutex> l(ahead.m);
+            ahead.cv.wait(l, [&] { return ahead.produced > c; });
+        } else {
+            prepare(c);
+        }
+        const Prep& pr = preps[c & 1];
+        const std::vector<uint32_t>&item_off = pr.item_off, &n_curves = pr.n_curves;
+        const uint32_t pt_a = pr.pt_a, pt_b = pr.pt_b;
+        const size_t n_items = pr.ref.size();
+        const unsigned char* const st = ctx->h_chunk[c & 1];
         double2* const d_pts = static_cast<double2*>(ctx->tmp_pts.p);
-        // (the previous chunk's kernel has completed — submit_sync — so its points may be overwritten)
-        if (pt_b > pt_a)
-            CK(ctx, cudaMemcpyAsync(d_pts, all->points + 2 * (size_t)pt_a, sizeof(double2) * (pt_b - pt_a), cudaMemcpyHostToDevice, ctx->stream));
-        ctx->last_h2d_bytes += sizeof(double2) * (pt_b - pt_a);
-        if ((rc = ensure_dev(ctx, ctx->tmp_items, sizeof(uint2) * std::max<size_t>(2 * n_items, 1)))) return rc;
-        if ((rc = ensure_pinned(ctx, ctx->h_items, ctx->h_items_cap, std::max<size_t>(2 * n_items, 1)))) return rc;
-        // (ensure_* and the status check of the previous chunk have synchronised the stream: the staging is free)
-        std::memcpy(ctx->h_items, ref.data(), sizeof(uint2) * n_items);
-        std::memcpy(ctx->h_items + n_items, packed.data(), sizeof(uint2) * n_items);
         uint2* const d_items = static_cast<uint2*>(ctx->tmp_items.p);
-        if (n_items) CK(ctx, cudaMemcpyAsync(d_items, ctx->h_items, sizeof(uint2) * 2 * n_items, cudaMemcpyHostToDevice, ctx->stream));
-        ctx->last_h2d_bytes += sizeof(uint2) * 2 * n_items;
+        // (the previous chunk's kernel has completed — submit_sync — so its points and items may be overwritten)
+        if (pt_b > pt_a) CK(ctx, cudaMemcpyAsync(d_pts, st, sizeof(double2) * (pt_b - pt_a), cudaMemcpyHostToDevice, ctx->stream));
+        if (n_items) CK(ctx, cudaMemcpyAsync(d_items, st + stage_items_at, sizeof(uint2) * 2 * n_items, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->last_h2d_bytes += sizeof(double2) * (pt_b - pt_a) + sizeof(uint2) * 2 * n_items;
         char* const slab = static_cast<char*>(ctx->ring_slab[slot].p);
+        // paths [a, a + n_dma) arrive as LinColor by DMA, paths [a + n_dma, b) as coverage, expanded on the host
+        const size_t n_exp = (can_expand && n >= 32) ? std::min(n - 1, (size_t)((double)n * ctx->expand_frac)) : 0;
+        const size_t n_dma = n - n_exp;
+        if (n_exp) {
+            // the coverage staging of this slot was read by the expansion of chunk c - ring: make sure that one is under way
+            // and finished before the copy below is queued
+            // (expand_oldest waits for the expansion submitted before it: with chunk c - 2 handed over, the expansion of
+            // chunk c - ring has finished)
+            while (pending.size() >= (size_t)std::max(1, ring - 1))
+                if ((rc = expand_oldest())) return rc;
+        }
         size_t live = 0;
         for (size_t i = 0; i < n; i++) {
             rgpu_dpath& d = dps[i];
@@ -303,10 +448,11 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
             j.path = &d;
             std::memcpy(j.tr, trs ? trs + 6 * (a + i) : ident, sizeof(j.tr));
             j.fill_rule = fill_rule;
-            j.mode = coverage ? RGPU_JOB_COVERAGE : RGPU_JOB_RENDER;
-            j.paint = coverage ? nullptr : paint;
-            j.canvas = slab;
-            j.origin = i * px;
+            const bool as_cov = coverage || i >= n_dma;
+            j.mode = as_cov ? RGPU_JOB_COVERAGE : RGPU_JOB_RENDER;
+            j.paint = as_cov ? nullptr : paint;
+            j.canvas = (i >= n_dma && !coverage) ? ctx->ring_rgba[slot].p : slab;
+            j.origin = (i >= n_dma && !coverage) ? (i - n_dma) * px : i * px;
             j.row_stride = width;
             j.width = width;
             j.height = height;
@@ -314,9 +460,21 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
         }
         // the slab is free once the download of the chunk that used it last has finished
         if (c >= (size_t)ring) CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ring_copied[slot], 0));
-        if (live != n)  // paths without segments draw nothing: their images are the fresh (zero) canvas
-            CK(ctx, cudaMemsetAsync(slab, 0, n * px * slab_elem, ctx->stream));
+        if (live != n) {  // paths without segments draw nothing: their images are the fresh (zero) canvas
+            CK(ctx, cudaMemsetAsync(slab, 0, n_dma * px * slab_elem, ctx->stream));
+            if (n_exp) CK(ctx, cudaMemsetAsync(ctx->ring_rgba[slot].p, 0, n_exp * px * 4, ctx->stream));
+        }
+        prep_ms += ms_since(t_prep);
+        const auto t_submit = std::chrono::steady_clock::now();
         status = submit_sync(ctx, jobs.data(), n, RGPU_BATCH_INDEPENDENT, 1);
+        submit_ms += ms_since(t_submit);
+        if (n_chunks > 1) {  // the stream is synchronised: the staging slot of this chunk is free for chunk c + 2
+            {
+                std::lock_guard<std::mutex> l(ahead.m);
+                ahead.consumed = c + 1;
+            }
+            ahead.cv.notify_all();
+        }
         if (status != RGPU_OK) break;
         const void* src = slab;
         if (out_format == RGPU_OUT_RGBA8) {
@@ -326,12 +484,37 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
         }
         CK(ctx, cudaEventRecord(ctx->ring_done[slot], ctx->stream));
         CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ring_done[slot], 0));
-        CK(ctx, cudaMemcpyAsync(static_cast<char*>(out_host) + a * px * out_elem, src, n * px * out_elem, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (n_exp)  // the small part first: its expansion can start while the LinColor part is still crossing
+            CK(ctx, cudaMemcpyAsync(ctx->h_alpha[slot], ctx->ring_rgba[slot].p, n_exp * px * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CK(ctx, cudaMemcpyAsync(static_cast<char*>(out_host) + a * px * out_elem, src, n_dma * px * out_elem, cudaMemcpyDeviceToHost, ctx->copy_stream));
         CK(ctx, cudaEventRecord(ctx->ring_copied[slot], ctx->copy_stream));
-        ctx->last_d2h_bytes += n * px * out_elem;
+        ctx->last_d2h_bytes += n_dma * px * out_elem + n_exp * px * 4;
+        if (n_exp) pending.push_back(Pending{a + n_dma, n_exp, slot});
     }
+    if (status == RGPU_OK)
+        while (!pending.empty())
+            if ((rc = expand_oldest())) return rc;
+    if (ctx->pool && can_expand) {
+        const auto t0 = std::chrono::steady_clock::now();
+        ctx->pool->wait();
+        wait_pool_ms += ms_since(t0);
+    }
+    static const bool trace = getenv("RGPU_E2E_TRACE") != nullptr;
+    const auto t_tail = std::chrono::steady_clock::now();
     cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    if (can_expand && !fixed_share && n_chunks >= 4 && status == RGPU_OK) {
+        // The share climbs the hill of the call's own time per pixel: keep moving while calls get faster, turn round when
+        // one got slower (who waits for whom — copy engine, expansion threads, host memory — shows up only in the total).
+        const double per_px = ms_since(t_call) / ((double)n_paths * (double)px);
+        if (ctx->expand_last > 0.0 && per_px > ctx->expand_last * 1.005) ctx->expand_dir = -ctx->expand_dir;
+        ctx->expand_last = per_px;
+        ctx->expand_frac = std::min(0.95, std::max(0.05, ctx->expand_frac + 0.04 * ctx->expand_dir));
+    }
+    if (trace)
+        fprintf(stderr, "rgpu_fill_batch_host: %zu chunks, host prep %.2f ms, submit + status %.2f ms, waited %.2f ms for coverage copies, %.2f ms for the "
+                "expansion threads, %.2f ms for the last copies; next share %.2f\n", n_chunks, prep_ms, submit_ms, wait_copy_ms, wait_pool_ms,
+                ms_since(t_tail), can_expand ? ctx->expand_frac : 0.0);
     if (status != RGPU_OK) return status;
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
         ctx->err = std::string("rgpu_fill_batch_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2);

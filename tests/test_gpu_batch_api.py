@@ -212,3 +212,34 @@ def test_multi_gpu_matches_single_gpu():
     finally:
         multi.close()
         single.close()
+
+
+def test_fill_batch_host_split_download_is_bit_identical(rast):
+    """LinColor output of a plain solid paint: a share of every chunk crosses PCIe as coverage and is expanded to colour * alpha
+    by host threads (rgpu_fill_batch_host, split download).  The share adapts from call to call, so repeated calls route
+    different glyphs through the host expansion: every call must give the same bytes, and they must be the bytes of the
+    device-side RENDER path (a prepared batch rendering into a device slab, downloaded whole)."""
+    n = 6000  # three chunks of 2048 glyphs
+    pb = synth.glyph_batch(77, n)
+    colour = rb.LinColor(0.25, 0.5, 0.125, 0.75)
+    outs = []
+    for _ in range(4):
+        out = np.full((n, 64, 64, 4), 9.0, dtype=np.float32)
+        rast.fill_batch_host(pb, rb.FillRule.NonZero, colour, 64, 64, out)
+        outs.append(out)
+    for o in outs[1:]:
+        assert np.array_equal(outs[0].view(np.uint32), o.view(np.uint32))
+    dpb = rast.upload_batch(pb)
+    slab = rast.device_alloc(n * 4096 * 16)
+    keep = []
+    paint_ptr = colour._c(keep)
+    import ctypes as C
+    t = job_table(dpb.handles(), slab, ffi.JOB_RENDER, rb.FillRule.NonZero, n, 64, 64, C.addressof(paint_ptr))
+    prepared = rast.prepare_job_table(t, keep=[keep, paint_ptr])
+    prepared.render()
+    rast.batch_status()
+    dev = rast.to_host(slab, (n, 64, 64, 4), np.float32)
+    assert np.array_equal(outs[0].view(np.uint32), dev.view(np.uint32))
+    prepared.free()
+    rast.device_free(slab)
+    dpb.free()
