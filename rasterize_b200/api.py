@@ -787,17 +787,31 @@ class GpuRasterizer:
         else:
             raise TypeError("mask image must be float64 or float32")
 
-    def mask_iter(self, path: Path, tr, size: Size, fill_rule: FillRule):
-        """`Rasterizer::mask_iter`: list of (x, y, alpha) with abs(alpha) >= 1e-6, row-major order."""
+    PIXEL_DTYPE = np.dtype([("x", "<u8"), ("y", "<u8"), ("alpha", "<f8")])  # = rgpu_pixel
+
+    def mask_iter_array(self, path: Path, tr, size: Size, fill_rule: FillRule, cap: int | None = None) -> np.ndarray:
+        """`Rasterizer::mask_iter` as a structured array (x, y, alpha) in row-major order.  The list is compacted on the
+        device and only the yielded pixels are downloaded; `cap` is the first guess of their number (the call is repeated
+        with the exact count when it was too small)."""
         L = ffi.lib()
         c = path._c()
         t = _as_tr(tr)
         n = C.c_size_t()
-        cap = max(1, size.width * size.height)
-        buf = (ffi.CPixel * cap)()
-        self._check(L.rgpu_mask_iter(self.ctx, C.byref(c), t.ctypes.data_as(C.POINTER(C.c_double)), size.width, size.height,
-                                     int(fill_rule), buf, cap, C.byref(n)))
-        return [(buf[i].x, buf[i].y, buf[i].alpha) for i in range(n.value)]
+        total = size.width * size.height
+        cap = min(total, 1 << 20) if cap is None else min(total, max(0, int(cap)))
+        while True:
+            buf = np.empty(max(cap, 1), dtype=self.PIXEL_DTYPE)
+            rc = L.rgpu_mask_iter(self.ctx, C.byref(c), t.ctypes.data_as(C.POINTER(C.c_double)), size.width, size.height, int(fill_rule),
+                                  C.cast(buf.ctypes.data, C.POINTER(ffi.CPixel)), cap, C.byref(n))
+            if rc == ffi.ERR_CAPACITY and n.value > cap:
+                cap = n.value
+                continue
+            self._check(rc)
+            return buf[:n.value]
+
+    def mask_iter(self, path: Path, tr, size: Size, fill_rule: FillRule):
+        """`Rasterizer::mask_iter`: list of (x, y, alpha) with abs(alpha) >= 1e-6, row-major order."""
+        return [(int(x), int(y), float(a)) for x, y, a in self.mask_iter_array(path, tr, size, fill_rule).tolist()]
 
     def coverage(self, path: Path, tr, size: Size, fill_rule: FillRule) -> np.ndarray:
         """Dense form of mask_iter: f32 [H,W]."""

@@ -9,7 +9,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "librasterize_b200.so"
-SOURCES = ["flatten.cu", "scan.cu", "raster.cu", "scene.cu", "small.cu", "compose.cu", "stroke.cu", "parse.cu", "context.cu"]
+SOURCES = ["flatten.cu", "scan.cu", "raster.cu", "scene.cu", "small.cu", "compose.cu", "compact.cu", "stroke.cu", "parse.cu", "context.cu"]
 # stroke.cu / parse.cu restate f64 expressions of the reference with plain operators: no multiply-add contraction there
 SOURCE_FLAGS = {"stroke.cu": ["--fmad=false"], "parse.cu": ["--fmad=false"]}
 NVCC_FLAGS = [

@@ -75,6 +75,7 @@ struct rgpu_ctx {
     uint32_t epoch = 0;
     int fix_shift = kFixShift;  // fraction bits of the winding cells of the batch being submitted (see rgpu_internal.cuh)
     DevBuf img_f32, img_f64, img_lin;  // staging canvases of the host-buffer entry points
+    DevBuf px_counts, px_out;          // rgpu_mask_iter: per-block pixel counts | offsets, compacted records
     DevBuf stroke_buf;                 // scratch of rgpu_path_stroke (unit table, counts, offsets, first / last pieces)
     DevBuf tmp_pts, tmp_items;         // device copy of the path of the current host-buffer call (grow-only, no per-call cudaMalloc)
     uint2* h_items = nullptr;          // pinned staging of the item list
@@ -130,8 +131,12 @@ struct rgpu_ctx {
     size_t h_chunk_cap[2] = {0, 0};
     float* h_alpha[kRing] = {nullptr, nullptr, nullptr};  // pinned staging of the coverage share of a chunk (split download)
     size_t h_alpha_cap[kRing] = {0, 0, 0};
-    double expand_frac = 0.6;  // share of a chunk's images that crosses PCIe as coverage and is expanded by host threads (adapts)
-    double expand_dir = 1.0, expand_last = 0.0;  // hill climbing on the call's time per pixel
+    static constexpr int kShares = 11;
+    double expand_frac = 0.85;  // share of a chunk's images that crosses PCIe as coverage and is expanded by host threads (adapts)
+    double share_ms[kShares] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // time per pixel of the calls at share 0.50 + 0.05 i (running mean; 0: not tried)
+    double share_key = 0.0;     // pixels of the workload the table belongs to
+    int share_cur = 7;
+    bool share_cold = true;
     cudaEvent_t ring_done[kRing] = {nullptr, nullptr, nullptr}, ring_copied[kRing] = {nullptr, nullptr, nullptr};
     // optional stage timing
     bool profiling = false;
@@ -968,7 +973,7 @@ void rgpu_destroy(rgpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->jobs, &ctx->paints, &ctx->slot_counts, &ctx->slot_offs, &ctx->lines, &ctx->line_job, &ctx->zero_block, &ctx->tile_offs,
-                      &ctx->tile_state, &ctx->fixed_block, &ctx->refs, &ctx->scan_temp, &ctx->status, &ctx->img_f32, &ctx->img_f64, &ctx->img_lin, &ctx->tmp_pts, &ctx->tmp_items, &ctx->scene_lists, &ctx->stroke_buf};
+                      &ctx->tile_state, &ctx->fixed_block, &ctx->refs, &ctx->scan_temp, &ctx->status, &ctx->img_f32, &ctx->img_f64, &ctx->img_lin, &ctx->tmp_pts, &ctx->tmp_items, &ctx->scene_lists, &ctx->stroke_buf, &ctx->px_counts, &ctx->px_out};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
@@ -1552,19 +1557,34 @@ int rgpu_mask_iter(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], siz
     float* d = nullptr;
     int rc = mask_to_device(ctx, path, tr, fill_rule, RGPU_JOB_COVERAGE, width, height, &d);
     if (rc) return rc;
-    if ((rc = ensure_stage(ctx, sizeof(float) * width * height))) return rc;
-    CK(ctx, cudaMemcpyAsync(ctx->h_stage, d, sizeof(float) * width * height, cudaMemcpyDeviceToHost, ctx->stream));
+    // the yielded pixels are compacted on the device (compact.cu): count per block of pixels, scan, emit in row-major order —
+    // only the records cross PCIe (the dense canvas used to, followed by a scan on one host thread)
+    static_assert(sizeof(rgpu_pixel) == 24, "rgpu_pixel layout (compact.cu PixelRec)");
+    const size_t npx = width * height;
+    if (npx > 0xffffffffull) return fail(ctx, RGPU_ERR_INVALID, "canvas too large for a pixel list (more than 2^32 pixels)");
+    const uint32_t nb = pixel_blocks(npx);
+    const size_t offs_at = ((size_t)nb + 1 + 3) & ~(size_t)3;  // the scan moves whole uint4s: both arrays 16-byte aligned
+    if ((rc = ensure_dev(ctx, ctx->px_counts, sizeof(uint32_t) * (offs_at + (size_t)nb + 1 + 4)))) return rc;
+    if ((rc = ensure_dev(ctx, ctx->scan_temp, scan_temp_bytes(nb + 1)))) return rc;
+    if ((rc = ensure_stage(ctx, 16))) return rc;
+    uint32_t* d_counts = static_cast<uint32_t*>(ctx->px_counts.p);
+    uint32_t* d_offs = d_counts + offs_at;
+    launch_pixel_count(d, npx, d_counts, ctx->stream);
+    launch_exclusive_scan(d_counts, d_offs, nb + 1, ctx->scan_temp.p, ctx->scan_temp.cap, ctx->stream);
+    CK(ctx, cudaMemcpyAsync(ctx->h_stage, d_offs + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
-    const float* cov = static_cast<const float*>(ctx->h_stage);
-    size_t n = 0;
-    for (size_t y = 0; y < height; y++)
-        for (size_t x = 0; x < width; x++) {
-            float a = cov[y * width + x];
-            if (a != 0.0f) {
-                if (n < cap && out) { out[n].x = x; out[n].y = y; out[n].alpha = (double)a; }
-                n++;
-            }
-        }
+    ctx->n_launches += 2;
+    const size_t n = *static_cast<const uint32_t*>(ctx->h_stage);
+    const size_t take = out ? std::min(n, cap) : 0;
+    ctx->last_d2h_bytes = sizeof(uint32_t);
+    if (take) {
+        if ((rc = ensure_dev(ctx, ctx->px_out, sizeof(rgpu_pixel) * take))) return rc;
+        launch_pixel_emit(d, npx, width, d_offs, ctx->px_out.p, take, ctx->stream);
+        ctx->n_launches += 1;
+        CK(ctx, cudaMemcpyAsync(out, ctx->px_out.p, sizeof(rgpu_pixel) * take, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->last_d2h_bytes += sizeof(rgpu_pixel) * take;
+    }
     *n_out = n;
     if (n > cap) return fail(ctx, RGPU_ERR_CAPACITY, "pixel buffer too small");
     return RGPU_OK;
@@ -1614,11 +1634,14 @@ int rgpu_fill(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill
             CK(ctx, cudaMemcpy2DAsync(d_img + ry0 * w + rx0, w * sizeof(float4), dst + 4 * (ry0 * shape.row_stride + rx0),
                                       shape.row_stride * sizeof(float4), rw * sizeof(float4), rh, cudaMemcpyHostToDevice, ctx->stream));
     } else {
-        if ((rc = ensure_stage(ctx, sizeof(float4) * w * h))) return rc;
+        // a view with a column stride: the same rectangle, gathered into (and later scattered from) a packed pinned staging
+        if ((rc = ensure_stage(ctx, std::max<size_t>(sizeof(float4) * rw * rh, 16)))) return rc;
         float4* st = static_cast<float4*>(ctx->h_stage);
-        for (size_t y = 0; y < h; y++)
-            for (size_t x = 0; x < w; x++) std::memcpy(&st[y * w + x], dst + 4 * (y * shape.row_stride + x * shape.col_stride), 16);
-        CK(ctx, cudaMemcpyAsync(d_img, st, sizeof(float4) * w * h, cudaMemcpyHostToDevice, ctx->stream));
+        for (size_t y = 0; y < rh; y++)
+            for (size_t x = 0; x < rw; x++) std::memcpy(&st[y * rw + x], dst + 4 * ((ry0 + y) * shape.row_stride + (rx0 + x) * shape.col_stride), 16);
+        if (rw && rh)
+            CK(ctx, cudaMemcpy2DAsync(d_img + ry0 * w + rx0, w * sizeof(float4), st, rw * sizeof(float4), rw * sizeof(float4), rh, cudaMemcpyHostToDevice,
+                                      ctx->stream));
     }
     rgpu_dpath dp;
     rc = stage_path(ctx, path, &dp);
@@ -1642,8 +1665,9 @@ int rgpu_fill(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill
             if (rw && rh)
                 CK(ctx, cudaMemcpy2DAsync(d_img + ry0 * w + rx0, w * sizeof(float4), dst + 4 * (ry0 * shape.row_stride + rx0),
                                           shape.row_stride * sizeof(float4), rw * sizeof(float4), rh, cudaMemcpyHostToDevice, ctx->stream));
-        } else {
-            CK(ctx, cudaMemcpyAsync(d_img, ctx->h_stage, sizeof(float4) * w * h, cudaMemcpyHostToDevice, ctx->stream));
+        } else if (rw && rh) {
+            CK(ctx, cudaMemcpy2DAsync(d_img + ry0 * w + rx0, w * sizeof(float4), ctx->h_stage, rw * sizeof(float4), rw * sizeof(float4), rh,
+                                      cudaMemcpyHostToDevice, ctx->stream));
         }
         const int keep = ctx->fix_shift;
         ctx->fix_shift = kFixShiftWide;
@@ -1658,10 +1682,12 @@ int rgpu_fill(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill
         CK(ctx, cudaStreamSynchronize(ctx->stream));
     } else {
         float4* st = static_cast<float4*>(ctx->h_stage);
-        CK(ctx, cudaMemcpyAsync(st, d_img, sizeof(float4) * w * h, cudaMemcpyDeviceToHost, ctx->stream));
+        if (rw && rh)
+            CK(ctx, cudaMemcpy2DAsync(st, rw * sizeof(float4), d_img + ry0 * w + rx0, w * sizeof(float4), rw * sizeof(float4), rh, cudaMemcpyDeviceToHost,
+                                      ctx->stream));
         CK(ctx, cudaStreamSynchronize(ctx->stream));
-        for (size_t y = 0; y < h; y++)
-            for (size_t x = 0; x < w; x++) std::memcpy(dst + 4 * (y * shape.row_stride + x * shape.col_stride), &st[y * w + x], 16);
+        for (size_t y = 0; y < rh; y++)
+            for (size_t x = 0; x < rw; x++) std::memcpy(dst + 4 * ((ry0 + y) * shape.row_stride + (rx0 + x) * shape.col_stride), &st[y * rw + x], 16);
     }
     return RGPU_OK;
 }

@@ -504,12 +504,29 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
     cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     if (can_expand && !fixed_share && n_chunks >= 4 && status == RGPU_OK) {
-        // The share climbs the hill of the call's own time per pixel: keep moving while calls get faster, turn round when
-        // one got slower (who waits for whom — copy engine, expansion threads, host memory — shows up only in the total).
-        const double per_px = ms_since(t_call) / ((double)n_paths * (double)px);
-        if (ctx->expand_last > 0.0 && per_px > ctx->expand_last * 1.005) ctx->expand_dir = -ctx->expand_dir;
-        ctx->expand_last = per_px;
-        ctx->expand_frac = std::min(0.95, std::max(0.05, ctx->expand_frac + 0.04 * ctx->expand_dir));
+        // The share is picked from the calls' own times: who waits for whom — copy engine, expansion threads, host memory —
+        // shows up only in the total.  Eleven candidate shares (0.50 .. 1.00); a call's time per pixel goes into its share's
+        // running mean, the next call takes the best share seen so far, or a neighbour of it that has not been tried yet.
+        // (The first call of a context pays for the pinned allocations and is not recorded; another workload starts afresh.)
+        const double key = (double)n_paths * (double)px, per_px = ms_since(t_call) / key;
+        if (!(key > 0.75 * ctx->share_key && key < 1.33 * ctx->share_key)) {
+            std::fill(ctx->share_ms, ctx->share_ms + rgpu_ctx::kShares, 0.0);
+            ctx->share_key = key;
+        }
+        if (ctx->share_cold) ctx->share_cold = false;
+        else {
+            double& m = ctx->share_ms[ctx->share_cur];
+            m = m > 0.0 ? 0.6 * m + 0.4 * per_px : per_px;
+        }
+        int best = ctx->share_cur;
+        for (int i = 0; i < rgpu_ctx::kShares; i++)
+            if (ctx->share_ms[i] > 0.0 && (ctx->share_ms[best] <= 0.0 || ctx->share_ms[i] < ctx->share_ms[best])) best = i;
+        if (ctx->share_ms[best] > 0.0) {
+            if (best + 1 < rgpu_ctx::kShares && ctx->share_ms[best + 1] <= 0.0) best++;
+            else if (best > 0 && ctx->share_ms[best - 1] <= 0.0) best--;
+        }
+        ctx->share_cur = best;
+        ctx->expand_frac = 0.5 + 0.05 * best;
     }
     if (trace)
         fprintf(stderr, "rgpu_fill_batch_host: %zu chunks, host prep %.2f ms, submit + status %.2f ms, waited %.2f ms for coverage copies, %.2f ms for the "

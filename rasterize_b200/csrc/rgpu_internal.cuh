@@ -126,6 +126,10 @@ void launch_flatten_bin_fixed(const JobDev* jobs, const JobDev* h_jobs, uint32_t
                               uint32_t* tile_counts, double4* bin_lines, uint32_t bin_cap, int band_rows, int chunk_cols, Status* status,
                               Status* next_status, cudaStream_t s);
 TileShape raster_tile_shape(int variant);
+// ---- mask_iter (compact.cu): the pixels with coverage != 0 of a dense n_pixels canvas as rgpu_pixel records, row-major ----
+uint32_t pixel_blocks(size_t n_pixels);
+void launch_pixel_count(const float* cov, size_t n_pixels, uint32_t* counts, cudaStream_t s);   // counts[pixel_blocks(n_pixels)]
+void launch_pixel_emit(const float* cov, size_t n_pixels, size_t width, const uint32_t* offs, void* out, size_t cap, cudaStream_t s);
 // ---- stroke (stroke.cu; the unit table is described in stroke_units.hpp) ----
 struct StrokeStyleDev {
     double width, miter_limit;

@@ -56,6 +56,34 @@ def test_fill_solid_host_image(rast):
     assert np.array_equal(got[untouched], bg[untouched])
 
 
+def test_fill_column_strided_view(rast):
+    """rgpu_fill on a view with a column stride (every second pixel of every second row of a larger image): only the bounding
+    rectangle of the path is gathered / scattered; the result matches the oracle's fill through the same Shape and the pixels
+    between the view's pixels stay untouched."""
+    p = assets.load_path("squirrel")
+    e = assets.expected()["paths"]["squirrel"]
+    w, h = e["size"]
+    # the path shrunk into the middle of the view: the moved rectangle is a proper part of it
+    tr = np.array(e["size_tr"]) * 0.5
+    tr[2] += w * 0.25
+    tr[5] += h * 0.25
+    rng = np.random.default_rng(11)
+    bg = rng.random((2 * h + 3, 2 * w + 4, 4), dtype=np.float32) * 0.5
+    got = bg.copy()
+    ref = bg.copy()
+    color = np.float32([0.1, 0.3, 0.2, 0.6])
+    view = got[1:1 + 2 * h:2, 3:3 + 2 * w:2]
+    assert view.shape == (h, w, 4)
+    rast.fill(p, tr, rb.FillRule.EvenOdd, rb.LinColor(*color), view)
+    W = 2 * w + 4
+    opath(p).fill(tr, O.EVENODD, O.OraclePaint.solid(color), ref, shape=O.Shape(W + 3, w, h, 2 * W, 2))
+    assert np.abs(got - ref).max() <= LIN_TOL
+    assert not np.array_equal(got, bg)
+    untouched = np.ones(bg.shape[:2], dtype=bool)
+    untouched[1:1 + 2 * h:2, 3:3 + 2 * w:2] = False
+    assert np.array_equal(got[untouched], bg[untouched])
+
+
 @pytest.mark.parametrize("kind", ["linear", "radial"])
 @pytest.mark.parametrize("spread", [0, 1, 2])
 @pytest.mark.parametrize("linear_colors", [True, False])

@@ -308,3 +308,57 @@ def test_too_many_gradient_stops_is_an_error_everywhere(rast):
         rast.render_batch([rb.Job(dp, rb.Transform.identity(), rb.FillRule.NonZero, ffi.JOB_FILL, canvas, 100, 100, 100, paint=grad)])
     assert e.value.code == ffi.ERR_INVALID
     rast.device_free(canvas)
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (3, 5), (7, 64), (130, 33), (257, 129), (1000, 700), (4099, 53)])
+def test_mask_iter_device_compaction(rast, w, h):
+    """rgpu_mask_iter compacts the yielded pixels on the device (compact.cu): the list must be exactly the non-zero pixels of the
+    dense coverage (same launch path, so bit-identical alphas) in row-major order — for widths on both sides of the float4 /
+    128-pixel / 4096-pixel block boundaries — and must match the oracle's iterator within the coverage tolerance."""
+    p = assets.load_path("squirrel")
+    e = assets.expected()["paths"]["squirrel"]["c1"]
+    w0, h0 = e["size"]
+    tr = np.array(e["tr"]).copy()
+    # scale the asset's own fit transform to this canvas
+    sx, sy = w / w0, h / h0
+    tr = np.array([tr[0] * sx, tr[1] * sx, tr[2] * sx, tr[3] * sy, tr[4] * sy, tr[5] * sy])
+    for rule, orule in ((rb.FillRule.NonZero, O.NONZERO), (rb.FillRule.EvenOdd, O.EVENODD)):
+        got = rast.mask_iter_array(p, tr, rb.Size(w, h), rule)
+        dense = rast.coverage(p, tr, rb.Size(w, h), rule)
+        ys, xs = np.nonzero(dense)
+        assert len(got) == len(xs)
+        assert np.array_equal(got["x"], xs.astype(np.uint64)) and np.array_equal(got["y"], ys.astype(np.uint64))
+        assert np.array_equal(got["alpha"], dense[ys, xs].astype(np.float64))
+        ref = np.zeros((h, w))
+        for x, y, a in opath(p).mask_iter(tr, w, h, orule):
+            ref[y, x] = a
+        mine = np.zeros((h, w))
+        mine[got["y"].astype(np.int64), got["x"].astype(np.int64)] = got["alpha"]
+        assert np.abs(mine - ref).max() <= COV_TOL
+
+
+def test_mask_iter_capacity_and_empty(rast):
+    """A buffer that is too small takes the first `cap` pixels and reports the full count (RGPU_ERR_CAPACITY); an empty path
+    and an off-canvas path yield nothing."""
+    p = assets.load_path("squirrel")
+    e = assets.expected()["paths"]["squirrel"]["c1"]
+    w, h = e["size"]
+    tr = np.array(e["tr"])
+    full = rast.mask_iter_array(p, tr, rb.Size(w, h), rb.FillRule.NonZero)
+    assert len(full) > 100
+    L = ffi.lib()
+    import ctypes as C
+    c = p._c()
+    n = C.c_size_t()
+    cap = 37
+    buf = np.zeros(cap + 3, dtype=rast.PIXEL_DTYPE)
+    rc = L.rgpu_mask_iter(rast.ctx, C.byref(c), tr.ctypes.data_as(C.POINTER(C.c_double)), w, h, int(rb.FillRule.NonZero),
+                          C.cast(buf.ctypes.data, C.POINTER(ffi.CPixel)), cap, C.byref(n))
+    assert rc == ffi.ERR_CAPACITY and n.value == len(full)
+    assert np.array_equal(buf[:cap], full[:cap]) and (buf["alpha"][cap:] == 0).all()
+    rc = L.rgpu_mask_iter(rast.ctx, C.byref(c), tr.ctypes.data_as(C.POINTER(C.c_double)), w, h, int(rb.FillRule.NonZero), None, 0, C.byref(n))
+    assert rc == ffi.ERR_CAPACITY and n.value == len(full)
+    assert len(rast.mask_iter_array(p, tr, rb.Size(w, h), rb.FillRule.NonZero, cap=5)) == len(full)  # retried with the exact count
+    assert len(rast.mask_iter_array(rb.Path.empty(), tr, rb.Size(w, h), rb.FillRule.NonZero)) == 0
+    far = np.array([tr[0], tr[1], tr[2] + 1e6, tr[3], tr[4], tr[5]])
+    assert len(rast.mask_iter_array(p, far, rb.Size(w, h), rb.FillRule.NonZero)) == 0
