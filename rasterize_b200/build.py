@@ -9,7 +9,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "librasterize_b200.so"
-SOURCES = ["flatten.cu", "scan.cu", "raster.cu", "scene.cu", "small.cu", "compose.cu", "compact.cu", "stroke.cu", "parse.cu", "context.cu"]
+SOURCES = ["flatten.cu", "scan.cu", "raster.cu", "scene.cu", "small.cu", "compose.cu", "compact.cu", "stroke.cu", "parse.cu", "context.cu", "host_simd.cpp"]
 # stroke.cu / parse.cu restate f64 expressions of the reference with plain operators: no multiply-add contraction there
 SOURCE_FLAGS = {"stroke.cu": ["--fmad=false"], "parse.cu": ["--fmad=false"]}
 NVCC_FLAGS = [
@@ -29,7 +29,7 @@ def needs_build() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.inl")) + list(CSRC.glob("*.hpp")) + [PKG.parent / "include" / "rasterize_b200.h"]
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.inl")) + list(CSRC.glob("*.hpp")) + list(CSRC.glob("*.cpp")) + [PKG.parent / "include" / "rasterize_b200.h"]
     return any(d.stat().st_mtime > t for d in deps)
 
 

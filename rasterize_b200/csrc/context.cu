@@ -1420,20 +1420,7 @@ int rgpu_coverage_f32(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], 
 
 // f32 -> f64 row with non-temporal stores: a plain store stream would first read every destination line for
 // ownership (134 MB of extra DRAM reads on a 4096^2 mask), which is what bounds the host side of rgpu_mask.
-static inline void widen_row(const float* __restrict__ src, double* __restrict__ dst, size_t n) {
-#if defined(__SSE2__)
-    size_t x = 0;
-    while (x < n && (reinterpret_cast<uintptr_t>(dst + x) & 15)) { dst[x] = (double)src[x]; x++; }
-    for (; x + 4 <= n; x += 4) {
-        const __m128 v = _mm_loadu_ps(src + x);
-        _mm_stream_pd(dst + x, _mm_cvtps_pd(v));
-        _mm_stream_pd(dst + x + 2, _mm_cvtps_pd(_mm_movehl_ps(v, v)));
-    }
-    for (; x < n; x++) dst[x] = (double)src[x];
-#else
-    for (size_t x = 0; x < n; x++) dst[x] = (double)src[x];
-#endif
-}
+static inline void widen_row(const float* __restrict__ src, double* __restrict__ dst, size_t n) { rgpu::widen_row_simd(src, dst, n); }
 
 // f32 device image -> strided f64 host image.  Two producers fill the caller's image at once:
 //   * the BOTTOM rows cross PCIe as f32 in row chunks; as soon as a chunk has landed in pinned staging the pool widens

@@ -64,3 +64,10 @@ private:
 };
 
 }  // namespace rgpu
+
+// host_simd.cpp: streaming loops with the widest vector unit of the CPU (run-time dispatch)
+namespace rgpu {
+const char* host_simd_name();
+void expand_alpha_simd(const float* alpha, const float colour[4], float* out, size_t n_px);  // out[4 i + k] = colour[k] * alpha[i]
+void widen_row_simd(const float* src, double* dst, size_t n);                               // dst[i] = (double)src[i]
+}  // namespace rgpu

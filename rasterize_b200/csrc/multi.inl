@@ -78,23 +78,7 @@ void build_range_items(const rgpu_path* all, const uint32_t* pso, const std::vec
 // Host side of the split download of rgpu_fill_batch_host: `n_px` pixels of coverage (f32) become premultiplied LinColor
 // pixels colour * alpha — the very multiplication the kernel does for a plain solid paint (small.cu finish_rows), so the
 // bytes are the ones the device would have sent.  Non-temporal stores: the destination is written once and not read here.
-void expand_alpha(const float* alpha, const float colour[4], float* out, size_t n_px) {
-#if defined(__SSE2__)
-    const __m128 c = _mm_loadu_ps(colour);
-    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-        for (size_t i = 0; i < n_px; i++) _mm_stream_ps(out + 4 * i, _mm_mul_ps(c, _mm_set1_ps(alpha[i])));
-        _mm_sfence();
-        return;
-    }
-#endif
-    for (size_t i = 0; i < n_px; i++) {
-        const float a = alpha[i];
-        out[4 * i] = colour[0] * a;
-        out[4 * i + 1] = colour[1] * a;
-        out[4 * i + 2] = colour[2] * a;
-        out[4 * i + 3] = colour[3] * a;
-    }
-}
+void expand_alpha(const float* alpha, const float colour[4], float* out, size_t n_px) { rgpu::expand_alpha_simd(alpha, colour, out, n_px); }
 
 // the condition under which RGPU_JOB_RENDER writes colour * alpha (small.cu: `plain`)
 bool plain_solid(const rgpu_paint* p) {
