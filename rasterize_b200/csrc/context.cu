@@ -132,10 +132,10 @@ struct rgpu_ctx {
     float* h_alpha[kRing] = {nullptr, nullptr, nullptr};  // pinned staging of the coverage share of a chunk (split download)
     size_t h_alpha_cap[kRing] = {0, 0, 0};
     static constexpr int kShares = 11;
-    double expand_frac = 0.85;  // share of a chunk's images that crosses PCIe as coverage and is expanded by host threads (adapts)
-    double share_ms[kShares] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // time per pixel of the calls at share 0.50 + 0.05 i (running mean; 0: not tried)
+    double expand_frac = 0.8;   // share of a chunk's images that crosses PCIe as coverage and is expanded by host threads (adapts)
+    double share_ms[kShares] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // time per pixel of the calls at share 0.1 i (running mean; 0: not tried)
     double share_key = 0.0;     // pixels of the workload the table belongs to
-    int share_cur = 7;
+    int share_cur = 8;
     bool share_cold = true;
     cudaEvent_t ring_done[kRing] = {nullptr, nullptr, nullptr}, ring_copied[kRing] = {nullptr, nullptr, nullptr};
     // optional stage timing

@@ -267,7 +267,7 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
     static const bool expand_enabled = !(getenv("RGPU_E2E_EXPAND") && atoi(getenv("RGPU_E2E_EXPAND")) == 0);
     const bool can_expand = expand_enabled && out_format == RGPU_OUT_LINCOLOR && plain_solid(paint) && width <= 64 && height <= 64 && n_paths >= 64;
     static const char* fixed_share = getenv("RGPU_E2E_EXPAND_FRAC");  // diagnosis: a fixed share instead of the adaptive one
-    if (fixed_share) ctx->expand_frac = std::min(0.95, std::max(0.0, atof(fixed_share)));
+    if (fixed_share) ctx->expand_frac = std::min(1.0, std::max(0.0, atof(fixed_share)));
     for (int i = 0; i < ring; i++) {
         if ((rc = ensure_dev(ctx, ctx->ring_slab[i], chunk * px * slab_elem))) return rc;
         if ((out_format == RGPU_OUT_RGBA8 || can_expand) && (rc = ensure_dev(ctx, ctx->ring_rgba[i], chunk * px * 4))) return rc;
@@ -489,7 +489,8 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     if (can_expand && !fixed_share && n_chunks >= 4 && status == RGPU_OK) {
         // The share is picked from the calls' own times: who waits for whom — copy engine, expansion threads, host memory —
-        // shows up only in the total.  Eleven candidate shares (0.50 .. 1.00); a call's time per pixel goes into its share's
+        // shows up only in the total.  Eleven candidate shares (0.0, 0.1 .. 1.0: several GPUs
+        // behind one host's memory are best served by plain DMA, one GPU by expanding nearly everything); a call's time per pixel goes into its share's
         // running mean, the next call takes the best share seen so far, or a neighbour of it that has not been tried yet.
         // (The first call of a context pays for the pinned allocations and is not recorded; another workload starts afresh.)
         const double key = (double)n_paths * (double)px, per_px = ms_since(t_call) / key;
@@ -510,7 +511,7 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
             else if (best > 0 && ctx->share_ms[best - 1] <= 0.0) best--;
         }
         ctx->share_cur = best;
-        ctx->expand_frac = 0.5 + 0.05 * best;
+        ctx->expand_frac = 0.1 * best;
     }
     if (trace)
         fprintf(stderr, "rgpu_fill_batch_host: %zu chunks, host prep %.2f ms, submit + status %.2f ms, waited %.2f ms for coverage copies, %.2f ms for the "
