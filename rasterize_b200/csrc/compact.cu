@@ -101,6 +101,84 @@ __global__ void __launch_bounds__(kPxThreads) pixel_emit_kernel(const float* __r
     }
 }
 
+// ---- run-coded rows: the download format of large masks -------------------------------------------------------------
+// A mask is mostly constant: outside the outline 0, inside 1, fractions only along the edges.  Every row is cut into
+// segments of 64 pixels; a segment whose pixels all carry the bits of +0.0f or all those of 1.0f is a class byte (0 / 1),
+// any other segment (class 2) is a literal: its 64 floats, packed in (row, segment) order.  Class bytes (1/256 of the
+// image), one literal offset per row and the literals cross PCIe; host threads rebuild the rows (host_simd.cpp
+// expand_runs_*) — the very same bytes, but written by the CPUs' streaming stores, which outrun one PCIe link.
+//   seg_classify_kernel  class byte per segment, literal count per row          (block = row)
+//   exclusive scan       first literal of every row, total                      (scan.cu)
+//   seg_emit_kernel      the literals, in order                                 (block = row)
+constexpr int kSegPx = 64;
+constexpr int kSegThreads = 256;
+constexpr int kSegWarps = kSegThreads / 32;
+
+// the two pixels of this lane in segment s of a row; beyond the row's end: the segment's first pixel (so a ragged last
+// segment is classified by its real pixels)
+__device__ __forceinline__ void seg_load(const float* __restrict__ rowp, size_t width, uint32_t s, int lane, uint32_t& b0, uint32_t& b1) {
+    const size_t x0 = (size_t)s * kSegPx, x = x0 + 2 * lane;
+    const uint32_t first = __float_as_uint(rowp[x0]);
+    b0 = x < width ? __float_as_uint(rowp[x]) : first;
+    b1 = x + 1 < width ? __float_as_uint(rowp[x + 1]) : first;
+}
+
+__global__ void __launch_bounds__(kSegThreads) seg_classify_kernel(const float* __restrict__ img, size_t width, uint32_t segs, unsigned char* __restrict__ cls,
+                                                                    uint32_t* __restrict__ row_cnt) {
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* rowp = img + (size_t)blockIdx.x * width;
+    unsigned char* crow = cls + (size_t)blockIdx.x * segs;
+    int cnt = 0;
+    for (uint32_t s = warp; s < segs; s += kSegWarps) {
+        uint32_t b0, b1;
+        seg_load(rowp, width, s, lane, b0, b1);
+        const uint32_t first = __shfl_sync(0xffffffffu, b0, 0);
+        const bool same = __all_sync(0xffffffffu, b0 == first && b1 == first);
+        const int c = (same && first == 0u) ? 0 : (same && first == 0x3f800000u) ? 1 : 2;
+        if (lane == 0) crow[s] = (unsigned char)c;
+        cnt += c == 2;
+    }
+    if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) row_cnt[blockIdx.x] = (uint32_t)s_cnt;
+}
+
+__global__ void __launch_bounds__(kSegThreads) seg_emit_kernel(const float* __restrict__ img, size_t width, uint32_t segs, const unsigned char* __restrict__ cls,
+                                                                const uint32_t* __restrict__ row_off, float* __restrict__ lits) {
+    __shared__ unsigned short s_list[kSegThreads];
+    __shared__ int s_warp[kSegWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* rowp = img + (size_t)blockIdx.x * width;
+    const unsigned char* crow = cls + (size_t)blockIdx.x * segs;
+    size_t at = row_off[blockIdx.x];
+    if (row_off[blockIdx.x + 1] == at) return;  // no literal in this row
+    for (uint32_t base = 0; base < segs; base += kSegThreads) {
+        // the literal segments of this tile of 256 segments, in order
+        const uint32_t s = base + threadIdx.x;
+        const bool lit = s < segs && crow[s] == 2;
+        const unsigned m = __ballot_sync(0xffffffffu, lit);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < kSegWarps; w++) {
+            if (w < warp) before += s_warp[w];
+            total += s_warp[w];
+        }
+        if (lit) s_list[before + __popc(m & ((1u << lane) - 1u))] = (unsigned short)threadIdx.x;
+        __syncthreads();
+        for (int k = warp; k < total; k += kSegWarps) {
+            uint32_t b0, b1;
+            seg_load(rowp, width, base + s_list[k], lane, b0, b1);
+            reinterpret_cast<uint2*>(lits + (at + k) * kSegPx)[lane] = make_uint2(b0, b1);
+        }
+        at += total;
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 uint32_t pixel_blocks(size_t n_pixels) { return (uint32_t)((n_pixels + kPxPerBlock - 1) / kPxPerBlock); }
@@ -113,6 +191,16 @@ void launch_pixel_count(const float* cov, size_t n_pixels, uint32_t* counts, cud
 void launch_pixel_emit(const float* cov, size_t n_pixels, size_t width, const uint32_t* offs, void* out, size_t cap, cudaStream_t s) {
     const uint32_t nb = pixel_blocks(n_pixels);
     if (nb) pixel_emit_kernel<<<nb, kPxThreads, 0, s>>>(cov, n_pixels, width, offs, static_cast<PixelRec*>(out), cap);
+}
+
+uint32_t runcode_segments(size_t width) { return (uint32_t)((width + kSegPx - 1) / kSegPx); }
+
+void launch_seg_classify(const float* img, size_t width, uint32_t rows, unsigned char* cls, uint32_t* row_cnt, cudaStream_t s) {
+    if (rows && width) seg_classify_kernel<<<rows, kSegThreads, 0, s>>>(img, width, runcode_segments(width), cls, row_cnt);
+}
+
+void launch_seg_emit(const float* img, size_t width, uint32_t rows, const unsigned char* cls, const uint32_t* row_off, float* lits, cudaStream_t s) {
+    if (rows && width) seg_emit_kernel<<<rows, kSegThreads, 0, s>>>(img, width, runcode_segments(width), cls, row_off, lits);
 }
 
 }  // namespace rgpu

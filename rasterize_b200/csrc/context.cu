@@ -76,6 +76,11 @@ struct rgpu_ctx {
     int fix_shift = kFixShift;  // fraction bits of the winding cells of the batch being submitted (see rgpu_internal.cuh)
     DevBuf img_f32, img_f64, img_lin;  // staging canvases of the host-buffer entry points
     DevBuf px_counts, px_out;          // rgpu_mask_iter: per-block pixel counts | offsets, compacted records
+    DevBuf rc_buf, rc_lits;            // run-coded download: [row counts | row offsets | class bytes], literals
+    unsigned char* h_rc = nullptr;     // pinned: [row offsets | class bytes]
+    size_t h_rc_cap = 0;
+    float* h_lits = nullptr;           // pinned: literals
+    size_t h_lits_cap = 0;
     DevBuf stroke_buf;                 // scratch of rgpu_path_stroke (unit table, counts, offsets, first / last pieces)
     DevBuf tmp_pts, tmp_items;         // device copy of the path of the current host-buffer call (grow-only, no per-call cudaMalloc)
     uint2* h_items = nullptr;          // pinned staging of the item list
@@ -973,7 +978,7 @@ void rgpu_destroy(rgpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->jobs, &ctx->paints, &ctx->slot_counts, &ctx->slot_offs, &ctx->lines, &ctx->line_job, &ctx->zero_block, &ctx->tile_offs,
-                      &ctx->tile_state, &ctx->fixed_block, &ctx->refs, &ctx->scan_temp, &ctx->status, &ctx->img_f32, &ctx->img_f64, &ctx->img_lin, &ctx->tmp_pts, &ctx->tmp_items, &ctx->scene_lists, &ctx->stroke_buf, &ctx->px_counts, &ctx->px_out};
+                      &ctx->tile_state, &ctx->fixed_block, &ctx->refs, &ctx->scan_temp, &ctx->status, &ctx->img_f32, &ctx->img_f64, &ctx->img_lin, &ctx->tmp_pts, &ctx->tmp_items, &ctx->scene_lists, &ctx->stroke_buf, &ctx->px_counts, &ctx->px_out, &ctx->rc_buf, &ctx->rc_lits};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
@@ -990,6 +995,8 @@ void rgpu_destroy(rgpu_ctx* ctx) {
     if (ctx->h_jobs) cudaFreeHost(ctx->h_jobs);
     if (ctx->h_paints) cudaFreeHost(ctx->h_paints);
     if (ctx->h_items) cudaFreeHost(ctx->h_items);
+    if (ctx->h_rc) cudaFreeHost(ctx->h_rc);
+    if (ctx->h_lits) cudaFreeHost(ctx->h_lits);
     for (int i = 0; i < 2; i++)
         if (ctx->h_chunk[i]) cudaFreeHost(ctx->h_chunk[i]);
     if (ctx->h_pts) cudaFreeHost(ctx->h_pts);
@@ -1393,6 +1400,94 @@ static int mask_to_device(rgpu_ctx* ctx, const rgpu_path* path, const double tr[
     return rc;
 }
 
+// Run-coded download (compact.cu) of `rows` dense f32 rows of `width` pixels at d_img: device row i becomes row img_row[i] of
+// the caller's image (`stride` elements per row, T = float or double).  The class bytes, one literal offset per row and the
+// literal segments cross PCIe; the pool's threads rebuild the rows with streaming stores while later literals still copy.
+// Returns 1 without touching the image when it declines (small image, RGPU_E2E_RUNCODE=0, or more than half of the segments
+// are literals): the caller then copies the dense rows.
+extern "C++" {
+template <class T>
+static int download_runcoded(rgpu_ctx* ctx, const float* d_img, size_t width, size_t rows, const std::vector<size_t>& img_row, T* img, size_t stride) {
+    static const bool enabled = !(getenv("RGPU_E2E_RUNCODE") && atoi(getenv("RGPU_E2E_RUNCODE")) == 0);
+    if (!enabled || rows * width < ((size_t)4 << 20) || rows > 0x7ffffff0u) return 1;
+    static const bool trace = getenv("RGPU_E2E_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    int rc;
+    const uint32_t segs = runcode_segments(width);
+    const size_t n_cls = rows * segs, words = (rows + 1 + 3) & ~(size_t)3;
+    if ((rc = ensure_dev(ctx, ctx->rc_buf, sizeof(uint32_t) * 2 * words + n_cls))) return rc;
+    if ((rc = ensure_dev(ctx, ctx->scan_temp, scan_temp_bytes((uint32_t)rows + 1)))) return rc;
+    if ((rc = ensure_pinned(ctx, ctx->h_rc, ctx->h_rc_cap, sizeof(uint32_t) * words + n_cls))) return rc;
+    uint32_t* d_cnt = static_cast<uint32_t*>(ctx->rc_buf.p);
+    uint32_t* d_off = d_cnt + words;
+    unsigned char* d_cls = reinterpret_cast<unsigned char*>(d_off + words);
+    launch_seg_classify(d_img, width, (uint32_t)rows, d_cls, d_cnt, ctx->stream);
+    launch_exclusive_scan(d_cnt, d_off, (uint32_t)rows + 1, ctx->scan_temp.p, ctx->scan_temp.cap, ctx->stream);
+    ctx->n_launches += 2;
+    // (offsets and class bytes are adjacent on both sides: one copy)
+    CK(ctx, cudaMemcpyAsync(ctx->h_rc, d_off, sizeof(uint32_t) * words + n_cls, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint32_t* row_off = reinterpret_cast<const uint32_t*>(ctx->h_rc);
+    const unsigned char* cls = ctx->h_rc + sizeof(uint32_t) * words;
+    const size_t n_lit = row_off[rows];
+    const double t_classified = since();
+    if (n_lit * 2 > n_cls) return 1;  // an image of edges: dense copies are the shorter way
+    if ((rc = ensure_dev(ctx, ctx->rc_lits, std::max<size_t>(sizeof(float) * 64 * n_lit, 16)))) return rc;
+    if ((rc = ensure_pinned(ctx, ctx->h_lits, ctx->h_lits_cap, std::max<size_t>(64 * n_lit, 16)))) return rc;
+    float* d_lits = static_cast<float*>(ctx->rc_lits.p);
+    if (n_lit) {
+        launch_seg_emit(d_img, width, (uint32_t)rows, d_cls, d_off, d_lits, ctx->stream);
+        ctx->n_launches += 1;
+    }
+    if (!ctx->pool) {
+        unsigned n = std::thread::hardware_concurrency();
+        if (const char* e = getenv("RGPU_HOST_THREADS")) n = (unsigned)std::max(1, atoi(e));
+        ctx->pool.reset(new rgpu::HostPool(std::max(1u, std::min(n ? n : 4u, 32u))));
+    }
+    // the literals come down in pieces of rows, so that the rows of a piece are rebuilt while the next piece is copied
+    const size_t pieces = std::min<size_t>(32, std::max<size_t>(1, rows / 64));
+    while (ctx->chunk_ev.size() < pieces) {
+        cudaEvent_t e;
+        CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->chunk_ev.push_back(e);
+    }
+    for (size_t p = 0; p < pieces; p++) {
+        const size_t ra = rows * p / pieces, rb = rows * (p + 1) / pieces;
+        const size_t la = row_off[ra], lb = row_off[rb];
+        if (lb > la) CK(ctx, cudaMemcpyAsync(ctx->h_lits + 64 * la, d_lits + 64 * la, sizeof(float) * 64 * (lb - la), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaEventRecord(ctx->chunk_ev[p], ctx->stream));
+    }
+    const unsigned workers = ctx->pool->size();
+    const float* lits = ctx->h_lits;
+    const size_t* rowmap = img_row.data();
+    for (size_t p = 0; p < pieces; p++) {
+        const size_t ra = rows * p / pieces, rb = rows * (p + 1) / pieces;
+        CK(ctx, cudaEventSynchronize(ctx->chunk_ev[p]));
+        const size_t parts = std::min<size_t>(workers, rb - ra);
+        for (size_t q = 0; q < parts; q++) {
+            const size_t a = ra + (rb - ra) * q / parts, b = ra + (rb - ra) * (q + 1) / parts;
+            ctx->pool->submit([=] {
+                for (size_t i = a; i < b; i++) {
+                    T* drow = img + rowmap[i] * stride;
+                    if (sizeof(T) == 4) rgpu::expand_runs_f32(cls + i * segs, segs, width, lits + 64 * (size_t)row_off[i], reinterpret_cast<float*>(drow));
+                    else rgpu::expand_runs_f64(cls + i * segs, segs, width, lits + 64 * (size_t)row_off[i], reinterpret_cast<double*>(drow));
+                }
+                rgpu::host_store_fence();
+            });
+        }
+    }
+    const double t_copied = since();
+    ctx->pool->wait();
+    ctx->last_d2h_bytes = sizeof(uint32_t) * words + n_cls + sizeof(float) * 64 * n_lit;
+    if (trace)
+        std::fprintf(stderr, "download_runcoded: %zu x %zu, %zu of %zu segments literal (%.1f MB over PCIe instead of %.1f MB); classified %.3f ms, "
+                     "literals copied %.3f ms, rows rebuilt %.3f ms (%s)\n", width, rows, n_lit, n_cls, ctx->last_d2h_bytes / 1e6,
+                     rows * width * 4 / 1e6, t_classified, t_copied, since(), rgpu::host_simd_name());
+    return RGPU_OK;
+}
+}  // extern "C++"
+
 int rgpu_mask_f32(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill_rule, float* img, size_t width, size_t height) {
     if (!ctx || !tr || (!img && width * height)) return RGPU_ERR_INVALID;
     CK(ctx, cudaSetDevice(ctx->device));
@@ -1400,6 +1495,14 @@ int rgpu_mask_f32(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int 
     float* d = nullptr;
     int rc = mask_to_device(ctx, path, tr, fill_rule, RGPU_JOB_MASK, width, height, &d);
     if (rc) return rc;
+    {   // large masks come down run-coded (constant segments as class bytes, rebuilt by host threads)
+        std::vector<size_t> img_row(height);
+        for (size_t y = 0; y < height; y++) img_row[y] = y;
+        const uint64_t h2d = ctx->last_h2d_bytes;
+        rc = download_runcoded<float>(ctx, d, width, height, img_row, img, width);
+        ctx->last_h2d_bytes = h2d;
+        if (rc <= 0) return rc;
+    }
     CK(ctx, cudaMemcpyAsync(img, d, sizeof(float) * width * height, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->last_d2h_bytes = sizeof(float) * width * height;
@@ -1532,6 +1635,14 @@ int rgpu_mask(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill
     float* d = nullptr;
     int rc = mask_to_device(ctx, path, tr, fill_rule, RGPU_JOB_MASK, w, h, &d);
     if (rc) return rc;
+    if (shape.col_stride == 1) {  // large masks come down run-coded and are rebuilt as f64 by host threads (download_runcoded)
+        std::vector<size_t> img_row(h);
+        for (size_t y = 0; y < h; y++) img_row[y] = y;
+        const uint64_t h2d = ctx->last_h2d_bytes;
+        rc = download_runcoded<double>(ctx, d, w, h, img_row, img + shape.start, shape.row_stride);
+        ctx->last_h2d_bytes = h2d;
+        if (rc <= 0) return rc;
+    }
     return download_widen(ctx, d, w, h, img + shape.start, shape);
 }
 

@@ -70,4 +70,8 @@ namespace rgpu {
 const char* host_simd_name();
 void expand_alpha_simd(const float* alpha, const float colour[4], float* out, size_t n_px);  // out[4 i + k] = colour[k] * alpha[i]
 void widen_row_simd(const float* src, double* dst, size_t n);                               // dst[i] = (double)src[i]
+// one row of a run-coded image (compact.cu) -> pixels; returns the literals consumed; fence afterwards
+size_t expand_runs_f32(const unsigned char* cls, size_t n_segs, size_t width, const float* lits, float* dst);
+size_t expand_runs_f64(const unsigned char* cls, size_t n_segs, size_t width, const float* lits, double* dst);
+void host_store_fence();
 }  // namespace rgpu

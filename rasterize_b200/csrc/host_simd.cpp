@@ -79,6 +79,99 @@ __attribute__((target("avx512f"))) void widen_avx512(const float* src, double* d
     for (; x < n; x++) dst[x] = (double)src[x];
 }
 
+// ---- run-coded rows (compact.cu): one row of class bytes + literals -> pixels ----
+// a segment of n <= 64 pixels: the constant v, or the literal's floats
+template <class T>
+inline void seg_portable(T* d, const float* lit, T v, size_t n) {
+    if (lit) for (size_t i = 0; i < n; i++) d[i] = (T)lit[i];
+    else for (size_t i = 0; i < n; i++) d[i] = v;
+}
+
+__attribute__((target("avx512f"))) size_t runs_f32_avx512(const unsigned char* cls, size_t n_segs, size_t width, const float* lits, float* dst) {
+    const __m512 zero = _mm512_setzero_ps(), one = _mm512_set1_ps(1.0f);
+    size_t lit = 0;
+    for (size_t s = 0; s < n_segs; s++) {
+        float* d = dst + 64 * s;
+        const size_t n = width - 64 * s < 64 ? width - 64 * s : 64;
+        const unsigned c = cls[s];
+        const float* src = c == 2 ? lits + 64 * lit++ : nullptr;
+        if (n == 64 && (reinterpret_cast<uintptr_t>(d) & 63) == 0) {
+            if (src) {
+                _mm512_stream_ps(d, _mm512_loadu_ps(src));
+                _mm512_stream_ps(d + 16, _mm512_loadu_ps(src + 16));
+                _mm512_stream_ps(d + 32, _mm512_loadu_ps(src + 32));
+                _mm512_stream_ps(d + 48, _mm512_loadu_ps(src + 48));
+            } else {
+                const __m512 v = c ? one : zero;
+                _mm512_stream_ps(d, v);
+                _mm512_stream_ps(d + 16, v);
+                _mm512_stream_ps(d + 32, v);
+                _mm512_stream_ps(d + 48, v);
+            }
+        } else {
+            seg_portable<float>(d, src, c ? 1.0f : 0.0f, n);
+        }
+    }
+    return lit;
+}
+
+size_t runs_f32_sse2(const unsigned char* cls, size_t n_segs, size_t width, const float* lits, float* dst) {
+    size_t lit = 0;
+    for (size_t s = 0; s < n_segs; s++) {
+        float* d = dst + 64 * s;
+        const size_t n = width - 64 * s < 64 ? width - 64 * s : 64;
+        const unsigned c = cls[s];
+        const float* src = c == 2 ? lits + 64 * lit++ : nullptr;
+        if (n == 64 && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+            const __m128 v = _mm_set1_ps(c ? 1.0f : 0.0f);
+            for (int i = 0; i < 64; i += 4) _mm_stream_ps(d + i, src ? _mm_loadu_ps(src + i) : v);
+        } else {
+            seg_portable<float>(d, src, c ? 1.0f : 0.0f, n);
+        }
+    }
+    return lit;
+}
+
+__attribute__((target("avx512f"))) size_t runs_f64_avx512(const unsigned char* cls, size_t n_segs, size_t width, const float* lits, double* dst) {
+    const __m512d zero = _mm512_setzero_pd(), one = _mm512_set1_pd(1.0);
+    size_t lit = 0;
+    for (size_t s = 0; s < n_segs; s++) {
+        double* d = dst + 64 * s;
+        const size_t n = width - 64 * s < 64 ? width - 64 * s : 64;
+        const unsigned c = cls[s];
+        const float* src = c == 2 ? lits + 64 * lit++ : nullptr;
+        if (n == 64 && (reinterpret_cast<uintptr_t>(d) & 63) == 0) {
+            if (src) {
+                for (int i = 0; i < 64; i += 8) _mm512_stream_pd(d + i, _mm512_cvtps_pd(_mm256_loadu_ps(src + i)));
+            } else {
+                const __m512d v = c ? one : zero;
+                for (int i = 0; i < 64; i += 8) _mm512_stream_pd(d + i, v);
+            }
+        } else {
+            seg_portable<double>(d, src, c ? 1.0 : 0.0, n);
+        }
+    }
+    return lit;
+}
+
+size_t runs_f64_sse2(const unsigned char* cls, size_t n_segs, size_t width, const float* lits, double* dst) {
+    size_t lit = 0;
+    for (size_t s = 0; s < n_segs; s++) {
+        double* d = dst + 64 * s;
+        const size_t n = width - 64 * s < 64 ? width - 64 * s : 64;
+        const unsigned c = cls[s];
+        const float* src = c == 2 ? lits + 64 * lit++ : nullptr;
+        if (n == 64 && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+            const __m128d v = _mm_set1_pd(c ? 1.0 : 0.0);
+            for (int i = 0; i < 64; i += 2)
+                _mm_stream_pd(d + i, src ? _mm_cvtps_pd(_mm_castsi128_ps(_mm_loadl_epi64(reinterpret_cast<const __m128i*>(src + i)))) : v);
+        } else {
+            seg_portable<double>(d, src, c ? 1.0 : 0.0, n);
+        }
+    }
+    return lit;
+}
+
 int simd_level() {  // 0: SSE2, 1: AVX2, 2: AVX-512F
     static const int level = [] {
         __builtin_cpu_init();
@@ -121,5 +214,15 @@ void widen_row_simd(const float* src, double* dst, size_t n) {
     if (simd_level() == 2) widen_avx512(src + x, dst + x, n - x);
     else widen_sse2(src + x, dst + x, n - x);
 }
+
+// One row of a run-coded image (compact.cu): class byte per 64-pixel segment (0: zeros, 1: ones, 2: the next literal of
+// `lits`, 64 floats each) -> `width` pixels at dst.  Returns the literals consumed.  The caller fences (host_store_fence).
+size_t expand_runs_f32(const unsigned char* cls, size_t n_segs, size_t width, const float* lits, float* dst) {
+    return simd_level() == 2 ? runs_f32_avx512(cls, n_segs, width, lits, dst) : runs_f32_sse2(cls, n_segs, width, lits, dst);
+}
+size_t expand_runs_f64(const unsigned char* cls, size_t n_segs, size_t width, const float* lits, double* dst) {
+    return simd_level() == 2 ? runs_f64_avx512(cls, n_segs, width, lits, dst) : runs_f64_sse2(cls, n_segs, width, lits, dst);
+}
+void host_store_fence() { _mm_sfence(); }
 
 }  // namespace rgpu

@@ -584,6 +584,18 @@ int rgpu_mask_banded_host(rgpu_ctx* ctx, const rgpu_path* path, const double tr[
     }
     const uint64_t h2d = ctx->last_h2d_bytes;
     uint64_t d2h = 0;
+    {   // large masks come down run-coded (constant segments as class bytes, rebuilt by host threads): see download_runcoded
+        std::vector<size_t> img_row(rows_total);
+        for (const Band& b : bands)
+            for (size_t i = 0; i < b.rows; i++) img_row[b.off + i] = b.y0 + i;
+        rc = elem_size == 4 ? download_runcoded<float>(ctx, d_img, width, rows_total, img_row, static_cast<float*>(img), width)
+                            : download_runcoded<double>(ctx, d_img, width, rows_total, img_row, static_cast<double*>(img), width);
+        if (rc < 0) return rc;
+        if (rc == 0) {
+            ctx->last_h2d_bytes = h2d;
+            return RGPU_OK;
+        }
+    }
     for (const Band& b : bands) {
         if (elem_size == 4) {
             CK(ctx, cudaMemcpyAsync(static_cast<float*>(img) + b.y0 * width, d_img + b.off * width, sizeof(float) * width * b.rows, cudaMemcpyDeviceToHost, ctx->stream));

@@ -130,6 +130,11 @@ TileShape raster_tile_shape(int variant);
 uint32_t pixel_blocks(size_t n_pixels);
 void launch_pixel_count(const float* cov, size_t n_pixels, uint32_t* counts, cudaStream_t s);   // counts[pixel_blocks(n_pixels)]
 void launch_pixel_emit(const float* cov, size_t n_pixels, size_t width, const uint32_t* offs, void* out, size_t cap, cudaStream_t s);
+// run-coded rows (compact.cu): class byte per 64-pixel segment of a dense f32 image (0: all +0.0f, 1: all 1.0f, 2: literal),
+// literal count per row, and — after an exclusive scan of the counts — the literals packed in (row, segment) order
+uint32_t runcode_segments(size_t width);
+void launch_seg_classify(const float* img, size_t width, uint32_t rows, unsigned char* cls, uint32_t* row_cnt, cudaStream_t s);
+void launch_seg_emit(const float* img, size_t width, uint32_t rows, const unsigned char* cls, const uint32_t* row_off, float* lits, cudaStream_t s);
 // ---- stroke (stroke.cu; the unit table is described in stroke_units.hpp) ----
 struct StrokeStyleDev {
     double width, miter_limit;

@@ -243,3 +243,35 @@ def test_fill_batch_host_split_download_is_bit_identical(rast):
     prepared.free()
     rast.device_free(slab)
     dpb.free()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_run_coded_download_matches_dense_copies(rast, dtype):
+    """Masks of 4 Mpixel and more come down run-coded (compact.cu: class byte per 64-pixel segment, literals for the edge
+    segments, rows rebuilt by host threads); smaller calls copy the dense rows.  Sixteen small band calls (dense) and one call
+    for the whole canvas (run-coded) must give the same bytes — for rows that are 64-byte aligned (4096), rows with a ragged
+    last segment that are only 16-byte aligned (4100) and rows with no alignment to speak of (5001, 5003 odd) — and the
+    whole-canvas call must move a fraction of the dense bytes."""
+    ex = assets.expected()["paths"]
+    p = assets.load_path("tv_stroked")
+    c = ex["tv_stroked"]["c5"]
+    for (w, h) in ((4096, 2048), (4100, 1500), (5001, 1000), (5003, 999)):
+        tr = np.array(c["tr"]) * np.array([w / c["size"][0]] * 3 + [h / c["size"][1]] * 3)
+        dense = np.full((h, w), -3.0, dtype=dtype)
+        for b in range(16):
+            rast.mask_banded(p, tr, dense, rb.FillRule.NonZero, n_bands=16, band_first=b, band_count=1)
+        whole = np.full((h, w), -5.0, dtype=dtype)
+        rast.mask_banded(p, tr, whole, rb.FillRule.NonZero, n_bands=1)
+        _, d2h = rast.last_transfer_bytes()
+        assert np.array_equal(whole.view(np.uint32 if dtype == np.float32 else np.uint64), dense.view(np.uint32 if dtype == np.float32 else np.uint64)), (w, h)
+        assert 0 < whole.max() <= 1.0 and whole.min() == 0.0
+        assert d2h < 0.5 * w * h * 4, (w, h, d2h)
+    # rgpu_mask_f32 takes the same way
+    w, h = 4096, 1024
+    tr = np.array(c["tr"]) * np.array([w / c["size"][0]] * 3 + [h / c["size"][1]] * 3)
+    a = np.zeros((h, w), dtype=np.float32)
+    rast.mask(p, tr, a, rb.FillRule.EvenOdd)
+    b = np.zeros((h, w), dtype=np.float32)
+    for k in range(8):
+        rast.mask_banded(p, tr, b, rb.FillRule.EvenOdd, n_bands=8, band_first=k, band_count=1)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
