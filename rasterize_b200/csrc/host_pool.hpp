@@ -2,6 +2,7 @@
 // while later chunks are still crossing PCIe.  Host-side plumbing only: no rasterization happens here.
 #pragma once
 #include <condition_variable>
+#include <deque>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -45,8 +46,8 @@ private:
                 std::unique_lock<std::mutex> l(m_);
                 cv_.wait(l, [this] { return stop_ || !q_.empty(); });
                 if (stop_ && q_.empty()) return;
-                f = std::move(q_.back());
-                q_.pop_back();
+                f = std::move(q_.front());  // first in, first out: tasks that wait for a copy are queued in copy order
+                q_.pop_front();
             }
             f();
             {
@@ -56,7 +57,7 @@ private:
         }
     }
     std::vector<std::thread> workers_;
-    std::vector<std::function<void()>> q_;
+    std::deque<std::function<void()>> q_;
     std::mutex m_;
     std::condition_variable cv_, done_;
     size_t pending_ = 0;

@@ -248,6 +248,7 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
         for (int i = 0; i < rgpu_ctx::kRing; i++) {
             CK(ctx, cudaEventCreateWithFlags(&ctx->ring_done[i], cudaEventDisableTiming));
             CK(ctx, cudaEventCreateWithFlags(&ctx->ring_copied[i], cudaEventDisableTiming));
+            CK(ctx, cudaEventCreateWithFlags(&ctx->ring_alpha[i], cudaEventDisableTiming | cudaEventBlockingSync));
         }
     }
     const auto t_call = std::chrono::steady_clock::now();
@@ -256,7 +257,8 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
     const size_t out_elem = out_elem_bytes(out_format);          // what crosses PCIe
     // chunks of about 128 MB of kernel output: large enough to hide launch and copy set-up, small enough that the first
     // download starts early and three slabs stay modest
-    size_t chunk = std::max<size_t>(1, (size_t)(128u << 20) / (px * slab_elem));
+    static const size_t chunk_mb = getenv("RGPU_E2E_CHUNK_MB") ? (size_t)std::max(1, atoi(getenv("RGPU_E2E_CHUNK_MB"))) : 128;  // tuning
+    size_t chunk = std::max<size_t>(1, (chunk_mb << 20) / (px * slab_elem));
     chunk = std::min(chunk, n_paths);
     const size_t n_chunks = (n_paths + chunk - 1) / chunk;
     const int ring = (int)std::min<size_t>(rgpu_ctx::kRing, n_chunks);
@@ -280,31 +282,25 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
     }
     float colour[4] = {0.f, 0.f, 0.f, 0.f};
     if (can_expand) std::memcpy(colour, paint->solid, sizeof(colour));
-    struct Pending { size_t first_path, n; int slot; };  // coverage downloaded (or on its way) and not yet expanded
-    std::vector<Pending> pending;
     double wait_copy_ms = 0.0, wait_pool_ms = 0.0, prep_ms = 0.0, submit_ms = 0.0;
     auto ms_since = [](std::chrono::steady_clock::time_point t0) {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     };
-    // hand the oldest downloaded coverage to the pool (after the expansion before it has finished: its staging buffer is the
-    // next one to be overwritten)
-    auto expand_oldest = [&]() -> int {
-        const Pending pd = pending.front();
-        pending.erase(pending.begin());
-        auto t0 = std::chrono::steady_clock::now();
-        CK(ctx, cudaEventSynchronize(ctx->ring_copied[pd.slot]));
-        wait_copy_ms += ms_since(t0);
-        t0 = std::chrono::steady_clock::now();
-        ctx->pool->wait();
+    // The expansion tasks of a chunk are handed to the pool as soon as its copies are queued; each task first sleeps on the
+    // event behind the coverage copy (the pool is first in, first out, so the threads take the chunks in copy order) — the
+    // submitting thread never waits for the pool except for a staging slot: the coverage staging of a slot may be overwritten
+    // once the tasks of the chunk that used it last (`ring` chunks earlier) are done.
+    std::atomic<int> exp_left[rgpu_ctx::kRing];
+    for (auto& e : exp_left) e.store(0);
+    struct PoolDrain {  // no task may outlive exp_left, whichever way the call ends
+        rgpu::HostPool* p;
+        ~PoolDrain() { if (p) p->wait(); }
+    } pool_drain{can_expand ? ctx->pool.get() : nullptr};
+    auto wait_slot_expanded = [&](int slot) {
+        if (exp_left[slot].load(std::memory_order_acquire) == 0) return;
+        const auto t0 = std::chrono::steady_clock::now();
+        while (exp_left[slot].load(std::memory_order_acquire) > 0) std::this_thread::yield();
         wait_pool_ms += ms_since(t0);
-        const float* alpha = ctx->h_alpha[pd.slot];
-        float* dst = static_cast<float*>(out_host) + pd.first_path * px * 4;
-        const size_t total = pd.n * px, parts = std::min<size_t>(ctx->pool->size() * 2, std::max<size_t>(1, total / 4096));
-        for (size_t q = 0; q < parts; q++) {
-            const size_t lo = total * q / parts, hi = total * (q + 1) / parts;
-            ctx->pool->submit([=] { expand_alpha(alpha + lo, colour, dst + 4 * lo, hi - lo); });
-        }
-        return RGPU_OK;
     };
     // The control points go up chunk by chunk, next to the chunk's items (both are small against the chunk's output): one
     // copy of all of them up front — 115 MB for 100 000 glyphs, from the caller's pageable array — held the first kernel
@@ -410,14 +406,6 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
         // paths [a, a + n_dma) arrive as LinColor by DMA, paths [a + n_dma, b) as coverage, expanded on the host
         const size_t n_exp = (can_expand && n >= 32) ? std::min(n - 1, (size_t)((double)n * ctx->expand_frac)) : 0;
         const size_t n_dma = n - n_exp;
-        if (n_exp) {
-            // the coverage staging of this slot was read by the expansion of chunk c - ring: make sure that one is under way
-            // and finished before the copy below is queued
-            // (expand_oldest waits for the expansion submitted before it: with chunk c - 2 handed over, the expansion of
-            // chunk c - ring has finished)
-            while (pending.size() >= (size_t)std::max(1, ring - 1))
-                if ((rc = expand_oldest())) return rc;
-        }
         size_t live = 0;
         for (size_t i = 0; i < n; i++) {
             rgpu_dpath& d = dps[i];
@@ -468,16 +456,31 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
         }
         CK(ctx, cudaEventRecord(ctx->ring_done[slot], ctx->stream));
         CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ring_done[slot], 0));
-        if (n_exp)  // the small part first: its expansion can start while the LinColor part is still crossing
+        if (n_exp) {  // the small part first: its expansion can start while the LinColor part is still crossing
+            wait_slot_expanded(slot);
             CK(ctx, cudaMemcpyAsync(ctx->h_alpha[slot], ctx->ring_rgba[slot].p, n_exp * px * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CK(ctx, cudaEventRecord(ctx->ring_alpha[slot], ctx->copy_stream));
+        }
         CK(ctx, cudaMemcpyAsync(static_cast<char*>(out_host) + a * px * out_elem, src, n_dma * px * out_elem, cudaMemcpyDeviceToHost, ctx->copy_stream));
         CK(ctx, cudaEventRecord(ctx->ring_copied[slot], ctx->copy_stream));
         ctx->last_d2h_bytes += n_dma * px * out_elem + n_exp * px * 4;
-        if (n_exp) pending.push_back(Pending{a + n_dma, n_exp, slot});
+        if (n_exp) {
+            const float* alpha = ctx->h_alpha[slot];
+            float* dst = static_cast<float*>(out_host) + (a + n_dma) * px * 4;
+            const size_t total = n_exp * px, parts = std::min<size_t>(ctx->pool->size() * 2, std::max<size_t>(1, total / 4096));
+            std::atomic<int>* const left = &exp_left[slot];
+            left->store((int)parts, std::memory_order_release);
+            const cudaEvent_t landed = ctx->ring_alpha[slot];
+            for (size_t q = 0; q < parts; q++) {
+                const size_t lo = total * q / parts, hi = total * (q + 1) / parts;
+                ctx->pool->submit([=] {
+                    cudaEventSynchronize(landed);
+                    expand_alpha(alpha + lo, colour, dst + 4 * lo, hi - lo);
+                    left->fetch_sub(1, std::memory_order_release);
+                });
+            }
+        }
     }
-    if (status == RGPU_OK)
-        while (!pending.empty())
-            if ((rc = expand_oldest())) return rc;
     if (ctx->pool && can_expand) {
         const auto t0 = std::chrono::steady_clock::now();
         ctx->pool->wait();

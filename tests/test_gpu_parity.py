@@ -362,3 +362,24 @@ def test_mask_iter_capacity_and_empty(rast):
     assert len(rast.mask_iter_array(rb.Path.empty(), tr, rb.Size(w, h), rb.FillRule.NonZero)) == 0
     far = np.array([tr[0], tr[1], tr[2] + 1e6, tr[3], tr[4], tr[5]])
     assert len(rast.mask_iter_array(p, far, rb.Size(w, h), rb.FillRule.NonZero)) == 0
+
+
+def test_mask_f64_run_coded_strided_rows(rast):
+    """rgpu_mask on a canvas of 4 Mpixel and more: the f64 rows are rebuilt by host threads from the run-coded download
+    (download_runcoded).  A row-strided view (rows of 2300 + 13 doubles) must get the bits of the f32 device mask widened
+    exactly — the reference point is the dense f32 download assembled from small band calls — the padding stays untouched,
+    and the result is within the coverage tolerance of the oracle."""
+    p = assets.load_path("material")
+    c2 = assets.expected()["paths"]["material"]["c2"]
+    w, h = 2300, 1900
+    tr = np.array(c2["tr"]) * np.array([w / c2["size"][0]] * 3 + [h / c2["size"][1]] * 3)
+    big = np.full((h, w + 13), -2.0)
+    rast.mask(p, tr, big[:, :w], rb.FillRule.NonZero)
+    assert (big[:, w:] == -2.0).all()
+    dense = np.zeros((h, w), dtype=np.float32)
+    for b in range(8):
+        rast.mask_banded(p, tr, dense, rb.FillRule.NonZero, n_bands=8, band_first=b, band_count=1)  # 0.5 Mpixel each: dense copies
+    assert np.array_equal(big[:, :w], dense.astype(np.float64))
+    ref = np.zeros((h, w))
+    opath(p).mask_threads(tr, O.NONZERO, ref, threads=8)
+    assert np.abs(big[:, :w] - ref).max() <= COV_TOL
