@@ -82,6 +82,8 @@ struct rgpu_ctx {
     size_t h_rc_cap = 0;
     float* h_lits = nullptr;           // pinned: literals
     size_t h_lits_cap = 0;
+    int rc_skip = 0;                   // calls of size rc_skip_w x rc_skip_h that skip the run-coded attempt (declined last time)
+    size_t rc_skip_w = 0, rc_skip_h = 0;
     DevBuf stroke_buf;                 // scratch of rgpu_path_stroke (unit table, counts, offsets, first / last pieces)
     DevBuf tmp_pts, tmp_items;         // device copy of the path of the current host-buffer call (grow-only, no per-call cudaMalloc)
     uint2* h_items = nullptr;          // pinned staging of the item list
@@ -1413,6 +1415,11 @@ template <class T>
 static int download_runcoded(rgpu_ctx* ctx, const float* d_img, size_t width, size_t rows, const std::vector<size_t>& img_row, T* img, size_t stride) {
     static const bool enabled = !(getenv("RGPU_E2E_RUNCODE") && atoi(getenv("RGPU_E2E_RUNCODE")) == 0);
     if (!enabled || rows * width < ((size_t)4 << 20) || rows > 0x7ffffff0u) return 1;
+    // an image of edges was declined a moment ago: the next calls of the same size skip the attempt (0.06 ms each), every 16th looks again
+    if (ctx->rc_skip && ctx->rc_skip_w == width && ctx->rc_skip_h == rows) {
+        ctx->rc_skip--;
+        return 1;
+    }
     static const bool trace = getenv("RGPU_E2E_TRACE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
@@ -1435,7 +1442,13 @@ static int download_runcoded(rgpu_ctx* ctx, const float* d_img, size_t width, si
     const unsigned char* cls = ctx->h_rc + sizeof(uint32_t) * words;
     const size_t n_lit = row_off[rows];
     const double t_classified = since();
-    if (n_lit * 2 > n_cls) return 1;  // an image of edges: dense copies are the shorter way
+    if (trace && n_lit * 2 > n_cls) std::fprintf(stderr, "download_runcoded: %zu of %zu segments literal: declined after %.3f ms\n", n_lit, n_cls, t_classified);
+    if (n_lit * 2 > n_cls) {  // an image of edges: dense copies are the shorter way
+        ctx->rc_skip = 15;
+        ctx->rc_skip_w = width;
+        ctx->rc_skip_h = rows;
+        return 1;
+    }
     if ((rc = ensure_dev(ctx, ctx->rc_lits, std::max<size_t>(sizeof(float) * 64 * n_lit, 16)))) return rc;
     if ((rc = ensure_pinned(ctx, ctx->h_lits, ctx->h_lits_cap, std::max<size_t>(64 * n_lit, 16)))) return rc;
     float* d_lits = static_cast<float*>(ctx->rc_lits.p);

@@ -1,5 +1,5 @@
 """Host-side streaming loops (rasterize_b200/csrc/host_simd.cpp): every vector variant the CPU offers gives the bytes of the
-scalar expression — `colour * alpha` per component, `(double)f32` — for unaligned heads, ragged tails and empty ranges, and
+scalar expression — `colour * alpha` per component, `(double)f32`, rows rebuilt from class bytes and literals (run-coded download) — for unaligned heads, ragged tails and empty ranges, and
 writes nothing beyond its range.  CPU-only: the file is compiled on its own with g++ (tests/cpp/test_host_simd.cpp)."""
 import os
 import subprocess
