@@ -2,7 +2,7 @@
 // fails without nvcc).  Sources: rasterize_b200/csrc (copied or vendored next to Cargo.toml).
 use std::{env, path::PathBuf, process::Command};
 
-const SOURCES: &[&str] = &["flatten.cu", "scan.cu", "raster.cu", "scene.cu", "small.cu", "compose.cu", "stroke.cu", "parse.cu", "context.cu"];
+const SOURCES: &[&str] = &["flatten.cu", "scan.cu", "raster.cu", "scene.cu", "small.cu", "compose.cu", "compact.cu", "stroke.cu", "parse.cu", "context.cu", "host_simd.cpp"];
 
 fn main() {
     if env::var_os("CARGO_FEATURE_GPU").is_none() {

@@ -434,13 +434,24 @@ impl Rasterizer for GpuRasterizer {
 
     fn mask_iter(&self, path: &Path, tr: Transform, size: Size, fill_rule: FillRule) -> Box<dyn Iterator<Item = Pixel> + '_> {
         let flat = FlatPath::new(path);
-        let mut buf: Vec<RgpuPixel> = Vec::with_capacity(size.width * size.height);
+        // the list is compacted on the device: only the yielded pixels come down.  First guess: an outline's worth of pixels;
+        // RGPU_ERR_CAPACITY returns the full count and the call is repeated once with room for it
+        let mut buf: Vec<RgpuPixel> = Vec::with_capacity((size.width * size.height).min(1 << 20));
         let mut n = 0usize;
         let trm: [Scalar; 6] = tr.into();
         let ctx = self.ctx.lock().unwrap();
-        Self::check(*ctx, unsafe {
-            rgpu_mask_iter(*ctx, &flat.ffi(), trm.as_ptr(), size.width, size.height, rule(fill_rule), buf.as_mut_ptr(), buf.capacity(), &mut n)
-        });
+        loop {
+            let cap = buf.capacity();
+            let rc = unsafe {
+                rgpu_mask_iter(*ctx, &flat.ffi(), trm.as_ptr(), size.width, size.height, rule(fill_rule), buf.as_mut_ptr(), cap, &mut n)
+            };
+            if rc == -5 && n > cap {
+                buf.reserve(n);
+                continue;
+            }
+            Self::check(*ctx, rc);
+            break;
+        }
         unsafe { buf.set_len(n) };
         Box::new(buf.into_iter().map(|p| Pixel { x: p.x, y: p.y, alpha: p.alpha }))
     }
