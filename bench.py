@@ -183,7 +183,8 @@ def workload_metric(name: str) -> str:
 
 def build_workload(name: str, rb, rast, rank: int, world: int, torch):
     """Device-resident form of a workload for rank `rank` of `world`.  Returns (step(sync) callable, info)."""
-    from rasterize_b200 import assets, ffi, sharding, synth
+    import assets
+    from rasterize_b200 import ffi, sharding, synth
     ex = assets.expected()["paths"]
     dev = torch.device("cuda", torch.cuda.current_device())
     if name == "c2":
@@ -498,7 +499,8 @@ def measure(hx: Harness, name: str, steps: int, warmup: int, with_cpu: bool, sam
                        "pinned f32 host image of the whole canvas"}
     elif name in ("c1", "c3"):
         # Scene::render + RGBA8 export through the host-buffer entry point: host paths in (H2D), pinned RGBA8 image out (D2H)
-        from rasterize_b200 import assets as _assets, scene as rscene
+        import assets as _assets
+        from rasterize_b200 import scene as rscene
         sc = _assets.load_scene(info["scene_name"])
         fills, W, H = rscene.fixture_fills_host(sc)
         prepared_host = rast.prepare_scene_host(fills)
@@ -545,7 +547,8 @@ def measure_pre_stages():
     device-resident path(s) out) with the kernels' CUDA-event time beside it, and the oracle on one host thread as baseline."""
     import oracle as O
     import rasterize_b200 as rb
-    from rasterize_b200 import Align, LineCap, LineJoin, StrokeStyle, assets, synth
+    import assets
+    from rasterize_b200 import Align, LineCap, LineJoin, StrokeStyle, synth
     rast = rb.GpuRasterizer()
     rast.set_profiling(True)
     out = {}
@@ -672,7 +675,7 @@ def cpu_reference_c2(threads: int, budget_s: float):
     """Times the CPU oracle (restatement of SignedDifferenceRasterizer::mask; the Rust reference cannot be built
     here) on config 2: img.clear() + mask per iteration as benches/rasterize_bench.rs:99-108 does."""
     import oracle as O
-    from rasterize_b200 import assets
+    import assets
     p = assets.load_path("material")
     c2 = assets.expected()["paths"]["material"]["c2"]
     w, h = c2["size"]
@@ -698,7 +701,8 @@ def cpu_reference_other(workload: str, budget_s: float):
     import math
 
     import oracle as O
-    from rasterize_b200 import assets, sharding
+    import assets
+    from rasterize_b200 import sharding
     t_end = time.perf_counter() + budget_s
     if workload in ("c1", "c3"):
         from helpers import render_scene_oracle
@@ -767,7 +771,8 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     import oracle as O
-    from rasterize_b200 import assets, sharding
+    import assets
+    from rasterize_b200 import sharding
     world = int(os.environ.get("WORLD_SIZE", "1"))
     wl = args.workload
     lines = None

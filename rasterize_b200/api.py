@@ -518,7 +518,7 @@ class GradRadial(_Grad):
 
 
 def paint_from_desc(d: dict):
-    """Paint from the flat description used by the golden fixtures (kind, units, ..., stop_pos, stop_colors)."""
+    """Paint from a flat description dict (kind, units, ..., stop_pos, stop_colors)."""
     kind = int(d["kind"])
     if kind == 0:
         return LinColor(*[float(v) for v in d["solid"]])

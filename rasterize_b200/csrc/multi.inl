@@ -282,7 +282,7 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
     }
     float colour[4] = {0.f, 0.f, 0.f, 0.f};
     if (can_expand) std::memcpy(colour, paint->solid, sizeof(colour));
-    double wait_copy_ms = 0.0, wait_pool_ms = 0.0, prep_ms = 0.0, submit_ms = 0.0;
+    double wait_pool_ms = 0.0, prep_ms = 0.0, submit_ms = 0.0;
     auto ms_since = [](std::chrono::steady_clock::time_point t0) {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     };
@@ -517,9 +517,9 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
         ctx->expand_frac = 0.1 * best;
     }
     if (trace)
-        fprintf(stderr, "rgpu_fill_batch_host: %zu chunks, host prep %.2f ms, submit + status %.2f ms, waited %.2f ms for coverage copies, %.2f ms for the "
-                "expansion threads, %.2f ms for the last copies; next share %.2f\n", n_chunks, prep_ms, submit_ms, wait_copy_ms, wait_pool_ms,
-                ms_since(t_tail), can_expand ? ctx->expand_frac : 0.0);
+        fprintf(stderr, "rgpu_fill_batch_host: %zu chunks, waited %.2f ms for prepared chunks, %.2f ms in submit + status (kernels, and the slab's "
+                "previous download), %.2f ms for the expansion threads, %.2f ms for the last copies; next share %.2f\n", n_chunks, prep_ms, submit_ms,
+                wait_pool_ms, ms_since(t_tail), can_expand ? ctx->expand_frac : 0.0);
     if (status != RGPU_OK) return status;
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
         ctx->err = std::string("rgpu_fill_batch_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2);

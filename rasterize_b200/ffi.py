@@ -68,7 +68,7 @@ class CSceneFill(C.Structure):
 
 _lib = None
 
-#: every symbol include/rasterize_b200.h declares (checked by tests/test_abi.py)
+#: every symbol include/rasterize_b200.h declares (the ABI test walks this table)
 SYMBOLS = [
     "rgpu_create", "rgpu_destroy", "rgpu_name", "rgpu_last_error", "rgpu_device_count", "rgpu_flatten", "rgpu_mask",
     "rgpu_mask_f32", "rgpu_mask_iter", "rgpu_coverage_f32", "rgpu_fill", "rgpu_path_upload", "rgpu_path_free",

@@ -8,7 +8,7 @@ import pytest
 
 import oracle as O
 from helpers import opath, render_scene_oracle
-from rasterize_b200 import assets
+import assets
 
 
 def digest(a):

@@ -6,7 +6,8 @@ import pytest
 import bench
 import oracle as O
 import rasterize_b200 as rb
-from rasterize_b200 import assets, ffi, sharding
+import assets
+from rasterize_b200 import ffi, sharding
 
 pytestmark = pytest.mark.gpu
 COV_TOL = 1e-4

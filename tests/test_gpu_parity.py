@@ -8,7 +8,8 @@ import pytest
 
 import oracle as O
 import rasterize_b200 as rb
-from rasterize_b200 import assets, ffi
+import assets
+from rasterize_b200 import ffi
 
 pytestmark = pytest.mark.gpu
 

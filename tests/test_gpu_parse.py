@@ -8,7 +8,8 @@ import pytest
 
 import oracle as O
 import rasterize_b200 as rb
-from rasterize_b200 import Align, assets, ffi, synth
+import assets
+from rasterize_b200 import Align, ffi, synth
 from parse_common import (CORNER_STRINGS, DEGENERATE_ARCS, ERROR_STRINGS, REFERENCE_STRINGS, check_batch, garbage_strings, oracle_parse, random_arcs, random_svg,
                           svg_of)
 

@@ -7,7 +7,8 @@ import pytest
 import oracle as O
 import rasterize_b200 as rb
 from helpers import render_pipeline_oracle
-from rasterize_b200 import assets, scene
+import assets
+from rasterize_b200 import scene
 
 pytestmark = pytest.mark.gpu
 

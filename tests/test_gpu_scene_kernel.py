@@ -18,7 +18,8 @@ import bench
 import oracle as O
 import rasterize_b200 as rb
 from helpers import render_scene_oracle
-from rasterize_b200 import assets, ffi, scene
+import assets
+from rasterize_b200 import ffi, scene
 
 pytestmark = pytest.mark.gpu
 
@@ -187,7 +188,8 @@ def test_scene_two_pass_fallback_bit_identical():
     """RGPU_TWO_PASS=1 (exact count -> scan -> emit bins) routes scene batches through the ordered launches: same bits."""
     code = """
 import numpy as np, rasterize_b200 as rb
-from rasterize_b200 import assets, scene
+import assets
+from rasterize_b200 import scene
 r = rb.GpuRasterizer()
 sc = assets.load_scene('firefox_256')
 _, _, W, H, _ = scene.fixture_jobs(r, sc, 1)

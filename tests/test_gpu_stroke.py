@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 
 import rasterize_b200 as rb
-from rasterize_b200 import LineCap, LineJoin, StrokeStyle, assets, ffi, sharding
+import assets
+from rasterize_b200 import LineCap, LineJoin, StrokeStyle, ffi, sharding
 from stroke_common import STYLES, compare, exact_case, oracle_stroke, random_paths, synthetic_paths
 
 pytestmark = pytest.mark.gpu

@@ -10,7 +10,7 @@ from pathlib import Path as FsPath
 import numpy as np
 import pytest
 
-from rasterize_b200 import assets
+import assets
 from parse_common import CORNER_STRINGS, DEGENERATE_ARCS, ERROR_STRINGS, INFO_DTYPE, REFERENCE_STRINGS, check_batch, garbage_strings, pack, random_arcs, random_svg, svg_of
 
 ROOT = FsPath(__file__).resolve().parent.parent

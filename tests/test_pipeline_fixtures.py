@@ -7,7 +7,7 @@ import pytest
 
 import oracle as O
 from helpers import render_pipeline_oracle
-from rasterize_b200 import assets
+import assets
 
 NAMES = ["grad", "grad_1024", "nested", "nested_900", "firefox_512"]
 

@@ -47,7 +47,7 @@ def _worker(rank, world, port, out):
     import torch.distributed as dist
 
     import oracle as O
-    from rasterize_b200 import assets
+    import assets
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)

@@ -10,7 +10,7 @@ from pathlib import Path as FsPath
 import numpy as np
 import pytest
 
-from rasterize_b200 import assets
+import assets
 from stroke_common import CAPS, JOINS, STYLES, compare, oracle_stroke, random_paths, synthetic_paths
 
 ROOT = FsPath(__file__).resolve().parent.parent

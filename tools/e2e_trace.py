@@ -2,8 +2,9 @@
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import rasterize_b200 as rb
-from rasterize_b200 import assets
+import assets
 r = rb.GpuRasterizer()
 p = assets.load_path("material")
 c2 = assets.expected()["paths"]["material"]["c2"]

@@ -11,7 +11,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import rasterize_b200 as rb
-from rasterize_b200 import Align, assets, synth
+import assets
+from rasterize_b200 import Align, synth
 from parse_common import pack, svg_of
 import oracle as O
 

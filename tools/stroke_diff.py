@@ -8,7 +8,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import rasterize_b200 as rb
-from rasterize_b200 import LineCap, LineJoin, StrokeStyle, assets
+import assets
+from rasterize_b200 import LineCap, LineJoin, StrokeStyle
 from stroke_common import STYLES, oracle_stroke
 
 JOIN = {"miter": LineJoin.Miter, "bevel": LineJoin.Bevel, "round": LineJoin.Round}

@@ -10,7 +10,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import rasterize_b200 as rb
-from rasterize_b200 import LineCap, LineJoin, StrokeStyle, assets
+import assets
+from rasterize_b200 import LineCap, LineJoin, StrokeStyle
 import oracle as O
 
 rast = rb.GpuRasterizer()
