@@ -146,7 +146,7 @@ struct rgpu_ctx {
     int share_cur = 8;
     bool share_cold = true;
     cudaEvent_t ring_done[kRing] = {nullptr, nullptr, nullptr}, ring_copied[kRing] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ring_alpha[kRing] = {nullptr, nullptr, nullptr};  // the coverage share of a chunk has landed in h_alpha (blocking sync: pool threads sleep on it)
+    std::vector<cudaEvent_t> ring_alpha[kRing];  // piece q of a chunk's coverage share has landed in h_alpha (blocking sync: pool threads sleep on it)
     // optional stage timing
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -992,7 +992,7 @@ void rgpu_destroy(rgpu_ctx* ctx) {
         if (ctx->h_alpha[i]) cudaFreeHost(ctx->h_alpha[i]);
         if (ctx->ring_done[i]) cudaEventDestroy(ctx->ring_done[i]);
         if (ctx->ring_copied[i]) cudaEventDestroy(ctx->ring_copied[i]);
-        if (ctx->ring_alpha[i]) cudaEventDestroy(ctx->ring_alpha[i]);
+        for (cudaEvent_t e : ctx->ring_alpha[i]) cudaEventDestroy(e);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);

@@ -248,7 +248,6 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
         for (int i = 0; i < rgpu_ctx::kRing; i++) {
             CK(ctx, cudaEventCreateWithFlags(&ctx->ring_done[i], cudaEventDisableTiming));
             CK(ctx, cudaEventCreateWithFlags(&ctx->ring_copied[i], cudaEventDisableTiming));
-            CK(ctx, cudaEventCreateWithFlags(&ctx->ring_alpha[i], cudaEventDisableTiming | cudaEventBlockingSync));
         }
     }
     const auto t_call = std::chrono::steady_clock::now();
@@ -456,10 +455,28 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
         }
         CK(ctx, cudaEventRecord(ctx->ring_done[slot], ctx->stream));
         CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ring_done[slot], 0));
-        if (n_exp) {  // the small part first: its expansion can start while the LinColor part is still crossing
+        // The coverage share first, in pieces (RGPU_E2E_PIECE_MB, default 2 MB; 0: the share in one copy): each piece has its own
+        // event and its own expansion task, so a piece is multiplied out right after it has landed — while it is still in the
+        // last-level cache the DMA wrote it into, instead of coming back from DRAM after the whole share (30 MB) has arrived.
+        size_t n_pieces = 0, piece_px = 0;
+        if (n_exp) {
+            static const size_t piece_mb = getenv("RGPU_E2E_PIECE_MB") ? (size_t)std::max(0, atoi(getenv("RGPU_E2E_PIECE_MB"))) : 2;
+            const size_t total = n_exp * px;
+            piece_px = piece_mb ? std::max<size_t>(4096, (piece_mb << 20) / 4) : total;
+            n_pieces = (total + piece_px - 1) / piece_px;
+            std::vector<cudaEvent_t>& evs = ctx->ring_alpha[slot];
+            while (evs.size() < n_pieces) {
+                cudaEvent_t e;
+                CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+                evs.push_back(e);
+            }
             wait_slot_expanded(slot);
-            CK(ctx, cudaMemcpyAsync(ctx->h_alpha[slot], ctx->ring_rgba[slot].p, n_exp * px * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
-            CK(ctx, cudaEventRecord(ctx->ring_alpha[slot], ctx->copy_stream));
+            const float* d_alpha = static_cast<const float*>(ctx->ring_rgba[slot].p);
+            for (size_t q = 0; q < n_pieces; q++) {
+                const size_t lo = q * piece_px, hi = std::min(total, lo + piece_px);
+                CK(ctx, cudaMemcpyAsync(ctx->h_alpha[slot] + lo, d_alpha + lo, (hi - lo) * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                CK(ctx, cudaEventRecord(evs[q], ctx->copy_stream));
+            }
         }
         CK(ctx, cudaMemcpyAsync(static_cast<char*>(out_host) + a * px * out_elem, src, n_dma * px * out_elem, cudaMemcpyDeviceToHost, ctx->copy_stream));
         CK(ctx, cudaEventRecord(ctx->ring_copied[slot], ctx->copy_stream));
@@ -467,17 +484,22 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
         if (n_exp) {
             const float* alpha = ctx->h_alpha[slot];
             float* dst = static_cast<float*>(out_host) + (a + n_dma) * px * 4;
-            const size_t total = n_exp * px, parts = std::min<size_t>(ctx->pool->size() * 2, std::max<size_t>(1, total / 4096));
+            const size_t total = n_exp * px;
+            // a piece is one task, or — when the share is one or two pieces — enough tasks for the whole pool
+            const size_t per_piece = n_pieces >= ctx->pool->size() ? 1 : (2 * ctx->pool->size() + n_pieces - 1) / n_pieces;
             std::atomic<int>* const left = &exp_left[slot];
-            left->store((int)parts, std::memory_order_release);
-            const cudaEvent_t landed = ctx->ring_alpha[slot];
-            for (size_t q = 0; q < parts; q++) {
-                const size_t lo = total * q / parts, hi = total * (q + 1) / parts;
-                ctx->pool->submit([=] {
-                    cudaEventSynchronize(landed);
-                    expand_alpha(alpha + lo, colour, dst + 4 * lo, hi - lo);
-                    left->fetch_sub(1, std::memory_order_release);
-                });
+            left->store((int)(n_pieces * per_piece), std::memory_order_release);
+            for (size_t q = 0; q < n_pieces; q++) {
+                const size_t plo = q * piece_px, phi = std::min(total, plo + piece_px);
+                const cudaEvent_t landed = ctx->ring_alpha[slot][q];
+                for (size_t t = 0; t < per_piece; t++) {
+                    const size_t lo = plo + (phi - plo) * t / per_piece, hi = plo + (phi - plo) * (t + 1) / per_piece;
+                    ctx->pool->submit([=] {
+                        cudaEventSynchronize(landed);
+                        if (hi > lo) expand_alpha(alpha + lo, colour, dst + 4 * lo, hi - lo);
+                        left->fetch_sub(1, std::memory_order_release);
+                    });
+                }
             }
         }
     }
