@@ -472,6 +472,12 @@ def measure(hx: Harness, name: str, steps: int, warmup: int, with_cpu: bool, sam
                        "pixel) and host threads write colour * coverage into the caller's buffer with streaming stores while the rest arrives "
                        "as LinColor by DMA (bit-identical to the device's own multiplication; d2h_bytes_per_step counts what really crossed)"}
         if not as_mask and n:
+            # the same call with the split download switched off: every byte of the result crosses PCIe as LinColor
+            os.environ["RGPU_E2E_EXPAND"] = "0"
+            try:
+                e2e["dma_only_ms_per_call"] = round(time_calls(hx, call, 3, 1) * 1e3, 3)
+            finally:
+                del os.environ["RGPU_E2E_EXPAND"]
             rgba = rast.host_alloc((n, 64, 64, 4), np.uint8)
             dt8 = time_calls(hx, lambda: rast.fill_batch_host(batch, rb.FillRule.NonZero, black, 64, 64, rgba), n_e2e, 1)
             e2e["rgba8_ms_per_call"] = round(dt8 * 1e3, 3)
@@ -495,8 +501,14 @@ def measure(hx: Harness, name: str, steps: int, warmup: int, with_cpu: bool, sam
         h2d, d2h = rast.last_transfer_bytes()
         e2e = {"value": round(info["total_pixels"] / dt / 1e6, 1), "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_call": round(dt * 1e3, 3),
-               "call": "rgpu_mask_banded_host on this rank's block of bands: host path in, the block rendered as one job and copied into its rows of a "
-                       "pinned f32 host image of the whole canvas"}
+               "call": "rgpu_mask_banded_host on this rank's block of bands: host path in, the block rendered as one job and brought into its rows of a "
+                       "pinned f32 host image of the whole canvas run-coded (class byte per 64-pixel segment + the literal edge segments cross PCIe, "
+                       "host threads rebuild the rows: the same bytes as dense copies; d2h_bytes_per_step counts what really crossed)"}
+        os.environ["RGPU_E2E_RUNCODE"] = "0"  # the same call with dense copies
+        try:
+            e2e["dense_copy_ms_per_call"] = round(time_calls(hx, call, 2, 1) * 1e3, 3)
+        finally:
+            del os.environ["RGPU_E2E_RUNCODE"]
     elif name in ("c1", "c3"):
         # Scene::render + RGBA8 export through the host-buffer entry point: host paths in (H2D), pinned RGBA8 image out (D2H)
         import assets as _assets

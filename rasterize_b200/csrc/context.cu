@@ -82,6 +82,7 @@ struct rgpu_ctx {
     size_t h_rc_cap = 0;
     float* h_lits = nullptr;           // pinned: literals
     size_t h_lits_cap = 0;
+    unsigned pool_share = 1;           // contexts sharing the host's cores (rgpu_multi_create)
     int rc_skip = 0;                   // calls of size rc_skip_w x rc_skip_h that skip the run-coded attempt (declined last time)
     size_t rc_skip_w = 0, rc_skip_h = 0;
     DevBuf stroke_buf;                 // scratch of rgpu_path_stroke (unit table, counts, offsets, first / last pieces)
@@ -207,6 +208,17 @@ int upload_table(rgpu_ctx* ctx, rgpu_ctx::TableShadow& sh, void* dev, const void
     sh.dev = dev;
     uploaded = true;
     return RGPU_OK;
+}
+
+// The context's host thread pool (widening, expansion and rebuilding of downloaded results).  RGPU_HOST_THREADS, else the host's
+// cores divided by the contexts that share them (rgpu_multi_create sets pool_share), capped at 32.
+void ensure_pool(rgpu_ctx* ctx) {
+    if (ctx->pool) return;
+    unsigned n = std::thread::hardware_concurrency();
+    n = n ? n : 4u;
+    if (const char* e = getenv("RGPU_HOST_THREADS")) n = (unsigned)std::max(1, atoi(e));
+    else if (ctx->pool_share > 1) n = std::max(2u, n / ctx->pool_share);
+    ctx->pool.reset(new rgpu::HostPool(std::max(1u, std::min(n, 32u))));
 }
 
 int ensure_stage(rgpu_ctx* ctx, size_t bytes) {
@@ -1413,7 +1425,7 @@ static int mask_to_device(rgpu_ctx* ctx, const rgpu_path* path, const double tr[
 extern "C++" {
 template <class T>
 static int download_runcoded(rgpu_ctx* ctx, const float* d_img, size_t width, size_t rows, const std::vector<size_t>& img_row, T* img, size_t stride) {
-    static const bool enabled = !(getenv("RGPU_E2E_RUNCODE") && atoi(getenv("RGPU_E2E_RUNCODE")) == 0);
+    const bool enabled = !(getenv("RGPU_E2E_RUNCODE") && atoi(getenv("RGPU_E2E_RUNCODE")) == 0);  // read per call: A/B inside one process
     if (!enabled || rows * width < ((size_t)4 << 20) || rows > 0x7ffffff0u) return 1;
     // an image of edges was declined a moment ago: the next calls of the same size skip the attempt (0.06 ms each), every 16th looks again
     if (ctx->rc_skip && ctx->rc_skip_w == width && ctx->rc_skip_h == rows) {
@@ -1456,11 +1468,7 @@ static int download_runcoded(rgpu_ctx* ctx, const float* d_img, size_t width, si
         launch_seg_emit(d_img, width, (uint32_t)rows, d_cls, d_off, d_lits, ctx->stream);
         ctx->n_launches += 1;
     }
-    if (!ctx->pool) {
-        unsigned n = std::thread::hardware_concurrency();
-        if (const char* e = getenv("RGPU_HOST_THREADS")) n = (unsigned)std::max(1, atoi(e));
-        ctx->pool.reset(new rgpu::HostPool(std::max(1u, std::min(n ? n : 4u, 32u))));
-    }
+    ensure_pool(ctx);
     // the literals come down in pieces of rows, so that the rows of a piece are rebuilt while the next piece is copied
     const size_t pieces = std::min<size_t>(32, std::max<size_t>(1, rows / 64));
     while (ctx->chunk_ev.size() < pieces) {
@@ -1554,12 +1562,7 @@ static inline void widen_row(const float* __restrict__ src, double* __restrict__
 static int download_widen(rgpu_ctx* ctx, const float* d_img, size_t w, size_t h, double* dst, rgpu_shape shape) {
     int rc;
     if ((rc = ensure_stage(ctx, sizeof(float) * w * h))) return rc;
-    if (!ctx->pool) {
-        // RGPU_HOST_THREADS: widening threads of this context (one process per GPU shares the host's cores with its peers)
-        unsigned n = std::thread::hardware_concurrency();
-        if (const char* e = getenv("RGPU_HOST_THREADS")) n = (unsigned)std::max(1, atoi(e));
-        ctx->pool.reset(new rgpu::HostPool(std::max(1u, std::min(n ? n : 4u, 32u))));
-    }
+    ensure_pool(ctx);
     // rows [0, h_dev) go the device-widened way
     size_t h_dev = 0;
     if (shape.col_stride == 1 && h >= 64) {

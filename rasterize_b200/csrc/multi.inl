@@ -265,7 +265,7 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
     // chunk is rendered as coverage (4 B per pixel over PCIe instead of 16) and turned into colour * alpha by host threads
     // while the rest of the chunk arrives as LinColor by DMA — two producers into the caller's buffer instead of one PCIe
     // link.  The share adapts from call to call (ctx->expand_frac); RGPU_E2E_EXPAND=0 switches it off.
-    static const bool expand_enabled = !(getenv("RGPU_E2E_EXPAND") && atoi(getenv("RGPU_E2E_EXPAND")) == 0);
+    const bool expand_enabled = !(getenv("RGPU_E2E_EXPAND") && atoi(getenv("RGPU_E2E_EXPAND")) == 0);  // read per call: A/B inside one process
     const bool can_expand = expand_enabled && out_format == RGPU_OUT_LINCOLOR && plain_solid(paint) && width <= 64 && height <= 64 && n_paths >= 64;
     static const char* fixed_share = getenv("RGPU_E2E_EXPAND_FRAC");  // diagnosis: a fixed share instead of the adaptive one
     if (fixed_share) ctx->expand_frac = std::min(1.0, std::max(0.0, atof(fixed_share)));
@@ -274,11 +274,7 @@ int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* ps
         if ((out_format == RGPU_OUT_RGBA8 || can_expand) && (rc = ensure_dev(ctx, ctx->ring_rgba[i], chunk * px * 4))) return rc;
         if (can_expand && (rc = ensure_pinned(ctx, ctx->h_alpha[i], ctx->h_alpha_cap[i], chunk * px))) return rc;
     }
-    if (can_expand && !ctx->pool) {
-        unsigned nthr = std::thread::hardware_concurrency();
-        if (const char* e = getenv("RGPU_HOST_THREADS")) nthr = (unsigned)std::max(1, atoi(e));
-        ctx->pool.reset(new rgpu::HostPool(std::max(1u, std::min(nthr ? nthr : 4u, 32u))));
-    }
+    if (can_expand) ensure_pool(ctx);
     float colour[4] = {0.f, 0.f, 0.f, 0.f};
     if (can_expand) std::memcpy(colour, paint->solid, sizeof(colour));
     double wait_pool_ms = 0.0, prep_ms = 0.0, submit_ms = 0.0;
@@ -693,6 +689,7 @@ int rgpu_multi_create(const int* devices, int n_devices, double flatness, rgpu_m
         m->ctxs.push_back(c);
         m->devices.push_back(dev);
     }
+    for (rgpu_ctx* c : m->ctxs) c->pool_share = (unsigned)n_devices;  // the contexts' host threads share the cores
     *out = m;
     return RGPU_OK;
 }

@@ -205,7 +205,7 @@ np.save('%s', r.to_host(layer, (H, W, 4), np.float32))
         with tempfile.NamedTemporaryFile(suffix=".npy", delete=False) as f:
             name = f.name
         env = dict(os.environ, **env_extra)
-        env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+        env["PYTHONPATH"] = os.path.join(root, "tests") + os.pathsep + root + os.pathsep + env.get("PYTHONPATH", "")
         subprocess.run([sys.executable, "-c", code % name], check=True, env=env, cwd=root, timeout=300)
         outs.append(np.load(name))
         os.unlink(name)
