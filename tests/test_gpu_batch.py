@@ -185,3 +185,45 @@ def test_render_jobs_create_their_canvas(rast):
     rast.render_batch([rb.Job(empty, ident, rb.FillRule.NonZero, ffi.JOB_RENDER, slab, 64, 64, 64, paint=grad)], independent=True)
     assert not rast.to_host(slab, (64, 64, 4), np.float32).any()
     rast.device_free(slab)
+
+
+def test_c5_whole_canvas_properties(rast, monkeypatch):
+    """config 5 at the BASELINE size, the WHOLE 32768 x 32768 canvas through the host-buffer call bench.py times
+    (rgpu_mask_banded_host, 4.29 GB of f32): the run-coded download and dense copies (RGPU_E2E_RUNCODE=0, read per call) give the
+    same bytes for the same jobs; coverage in [0, 1]; rows of the empty top band are exactly zero; sampled rows match the oracle;
+    the run-coded call moves a fraction of the bytes.  Two blocks of bands rendered separately (what two GPUs do) stitch to the
+    whole-canvas image up to one f32 ulp in a handful of pixels: the band-local translate(0, -y0) changes the f64 rounding of the
+    transformed control points (y * tr4 + (tr5 - y0)), which at this size flips the last bit of 6 of 1.07e9 pixels — at 8192^2
+    and below the stitched image is bit-identical (test_mask_banded_is_bit_identical_to_single_mask)."""
+    p = assets.load_path("tv_stroked")
+    c5 = assets.expected()["paths"]["tv_stroked"]["c5"]
+    w, h = c5["size"]
+    tr = np.array(c5["tr"])
+    whole = np.empty((h, w), dtype=np.float32)
+    whole[:] = -1.0
+    rast.mask_banded(p, tr, whole, rb.FillRule.NonZero, n_bands=64)
+    _, d2h = rast.last_transfer_bytes()
+    assert d2h < 0.25 * w * h * 4
+    assert whole.min() == 0.0 and whole.max() == 1.0
+    assert not whole[: h // 8].any()  # band 0 of 8 holds no geometry (SURVEY 8d)
+    other = np.empty((h, w), dtype=np.float32)
+    other[:] = -1.0
+    monkeypatch.setenv("RGPU_E2E_RUNCODE", "0")
+    rast.mask_banded(p, tr, other, rb.FillRule.NonZero, n_bands=64)
+    _, d2h_dense = rast.last_transfer_bytes()
+    monkeypatch.delenv("RGPU_E2E_RUNCODE")
+    assert d2h_dense == w * h * 4
+    assert np.array_equal(whole.view(np.uint32), other.view(np.uint32))
+    # two blocks of bands, the first with dense copies and the second run-coded, into one image
+    other[:] = -1.0
+    monkeypatch.setenv("RGPU_E2E_RUNCODE", "0")
+    rast.mask_banded(p, tr, other, rb.FillRule.NonZero, n_bands=64, band_first=0, band_count=40)
+    monkeypatch.delenv("RGPU_E2E_RUNCODE")
+    rast.mask_banded(p, tr, other, rb.FillRule.NonZero, n_bands=64, band_first=40, band_count=24)
+    ys, xs = np.nonzero(whole.view(np.uint32) != other.view(np.uint32))
+    assert len(ys) <= 64 and (len(ys) == 0 or np.abs(whole[ys, xs] - other[ys, xs]).max() <= 1.2e-7)
+    op = opath(p)
+    for y0 in (h // 2 - 32, 11111, h - 5000):
+        ref = np.zeros((64, w))
+        op.mask(sharding.band_transform(tr, y0), O.NONZERO, ref)
+        assert np.abs(whole[y0:y0 + 64] - ref).max() <= COV_TOL

@@ -276,3 +276,39 @@ def test_run_coded_download_matches_dense_copies(rast, dtype):
     for k in range(8):
         rast.mask_banded(p, tr, b, rb.FillRule.EvenOdd, n_bands=8, band_first=k, band_count=1)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_config4_full_size_properties(rast):
+    """BASELINE config 4 at its full size (100 000 glyphs at 64 x 64, what bench.py times), through size-independent properties:
+    * LinColor output of solid black = (0, 0, 0, coverage): the alpha plane of the whole batch equals the COVERAGE output
+      of the same call bit for bit (two kernel modes, and the LinColor call mixes DMA'd and host-expanded glyphs);
+    * a glyph does not depend on its batch: 61 glyphs picked across the batch and rendered as their own small batch give the
+      bits they have inside the 100 000;
+    * the same 61 glyphs against the oracle's Path::fill (<= 1e-4), and the oracle's coverage sums (a checksum of checksums);
+    * nothing of the output buffer is left unwritten."""
+    n = 100000
+    pb = synth.glyph_batch(1, n)
+    black = rb.LinColor(0.0, 0.0, 0.0, 1.0)
+    lin = np.empty((n, 64, 64, 4), dtype=np.float32)
+    lin[:] = 7.0
+    rast.fill_batch_host(pb, rb.FillRule.NonZero, black, 64, 64, lin)
+    cov = np.empty((n, 64, 64), dtype=np.float32)
+    cov[:] = 7.0
+    rast.fill_batch_host(pb, rb.FillRule.NonZero, None, 64, 64, cov)
+    assert cov.max() <= 1.0 and cov.min() >= 0.0
+    assert np.array_equal(lin[..., 3].view(np.uint32), cov.view(np.uint32))
+    assert not lin[..., :3].any()
+    picks = sorted(set(int(i) for i in np.linspace(0, n - 1, 61)))
+    small = rb.PathBatch.from_paths([pb.path(i) for i in picks])
+    alone = np.empty((len(picks), 64, 64), dtype=np.float32)
+    rast.fill_batch_host(small, rb.FillRule.NonZero, None, 64, 64, alone)
+    assert np.array_equal(alone.view(np.uint32), cov[picks].view(np.uint32))
+    paint = O.OraclePaint.solid([0, 0, 0, 1])
+    sums_gpu, sums_ref = [], []
+    for k, i in enumerate(picks):
+        ref = np.zeros((64, 64, 4), dtype=np.float32)
+        opath(pb.path(i)).fill(O.IDENTITY, O.NONZERO, paint, ref)
+        assert np.abs(lin[i] - ref).max() <= COV_TOL, i
+        sums_gpu.append(float(cov[i].astype(np.float64).sum()))
+        sums_ref.append(float(ref[..., 3].astype(np.float64).sum()))
+    assert abs(sum(sums_gpu) - sum(sums_ref)) <= 1e-2 and max(abs(a - b) for a, b in zip(sums_gpu, sums_ref)) <= 5e-3
