@@ -1485,6 +1485,10 @@ static int download_runcoded(rgpu_ctx* ctx, const float* d_img, size_t width, si
     const unsigned workers = ctx->pool->size();
     const float* lits = ctx->h_lits;
     const size_t* rowmap = img_row.data();
+    struct PoolDrain {  // no task may outlive the row map, whichever way the call ends
+        rgpu::HostPool* p;
+        ~PoolDrain() { p->wait(); }
+    } pool_drain{ctx->pool.get()};
     for (size_t p = 0; p < pieces; p++) {
         const size_t ra = rows * p / pieces, rb = rows * (p + 1) / pieces;
         CK(ctx, cudaEventSynchronize(ctx->chunk_ev[p]));
