@@ -1,3 +1,5 @@
+"""Config 5 at full size: run-coded download against dense copies, and one whole-canvas job against two blocks of bands (where the
+band-local translate shows up: 6 pixels of 1.07e9 differ by one f32 ulp).  python tools/diag_c5.py"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
