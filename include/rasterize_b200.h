@@ -344,10 +344,11 @@ int rgpu_multi_fill_batch_host(rgpu_multi* m, const rgpu_path* all, const uint32
  * independent in the signed-difference rasterizer (src/rasterize.rs:421-469, 478-503), so the canvas is cut into n_bands
  * bands of rows (0 = one per device; cut points are multiples of 8 rows), device d takes the contiguous block of bands
  * [d * n_bands / n_devices, (d + 1) * n_bands / n_devices) as ONE job — equal rows are equal output bytes, which is what
- * bounds the raster kernel — flattens the path with a band-local translate(0, -y0) (the reference's own y clipping then
- * crops exactly) and copies its rows into the host image.  `img` is a dense width x height image of f32 (elem_size 4, the
+ * bounds the raster kernel — flattens the path with the canvas transform, shifts the finished lines by the block's integer
+ * row origin (the reference's own y clipping then crops exactly) and brings its rows into the host image (large blocks
+ * run-coded: class byte per 64-pixel segment + literal edge segments over PCIe, rows rebuilt by host threads).  `img` is a dense width x height image of f32 (elem_size 4, the
  * device-native format) or f64 (elem_size 8, the trait's `Scalar`); it does not have to be zero on entry (every pixel is
- * written).  The result is bit-identical to the single-device rgpu_mask_f32 / rgpu_mask. */
+ * written).  The result is bit-identical to the single-device rgpu_mask_f32 / rgpu_mask at every canvas size. */
 int rgpu_multi_mask_banded_host(rgpu_multi* m, const rgpu_path* path, const double tr[6], int fill_rule, void* img, size_t elem_size,
                                 size_t width, size_t height, uint32_t n_bands);
 /* The same band decomposition on ONE context; also what every worker of rgpu_multi_mask_banded_host runs for its block.

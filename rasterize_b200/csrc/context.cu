@@ -75,6 +75,7 @@ struct rgpu_ctx {
     DevBuf jobs, paints, slot_counts, slot_offs, lines, line_job, zero_block, tile_offs, refs, scan_temp, status, tile_state;
     uint32_t epoch = 0;
     int fix_shift = kFixShift;  // fraction bits of the winding cells of the batch being submitted (see rgpu_internal.cuh)
+    const double* job_row_origin = nullptr;  // per job of the batch being submitted: JobDev::y_org (set by rgpu_mask_banded_host around its submission)
     DevBuf img_f32, img_f64, img_lin;  // staging canvases of the host-buffer entry points
     DevBuf px_counts, px_out;          // rgpu_mask_iter: per-block pixel counts | offsets, compacted records
     DevBuf rc_buf, rc_lits;            // run-coded download: [row counts | row offsets | class bytes], literals
@@ -540,6 +541,7 @@ int build_tables(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, int close_f
         d.mode = in.mode;
         d.close = close_flag;
         d.fix_shift = ctx->fix_shift;
+        d.y_org = ctx->job_row_origin ? ctx->job_row_origin[j] : 0.0;
         d.canvas = in.canvas;
         d.origin = in.origin;
         d.row_stride = in.row_stride;
@@ -562,7 +564,7 @@ int build_tables(rgpu_ctx* ctx, const rgpu_job* jobs, size_t n_jobs, int close_f
         band_acc += d.n_bands;
         tile_acc += d.n_bands * d.n_chunks;
         est_lines += (uint64_t)in.path->n_curves * 24 + (in.path->n_items - in.path->n_curves) + 16;
-        all_small = all_small && !scene && small_canvas_eligible(in.width, in.height, in.mode);
+        all_small = all_small && !scene && d.y_org == 0.0 && small_canvas_eligible(in.width, in.height, in.mode);  // (the fused small-canvas kernel knows no row origin)
         ctx->h_jobs[n_live++] = d;
     }
     tb.item_acc = item_acc;

@@ -136,6 +136,9 @@ flatten_bin_kernel(const JobDev* __restrict__ jobs_in, uint32_t n_jobs, const __
     if (t < total_slots && (PASS == 2 ? slot_setup_packed<DEPTH>(jobs, n_jobs, t, thr, c, status) : slot_setup<DEPTH>(jobs, n_jobs, t, thr, c, status))) {
         const JobDev& job = jobs[c.job];
         auto emit = [&](double x0, double y0, double x1, double y1) {
+            // band jobs: canvas rows -> band rows (JobDev::y_org; exact for every line that reaches the band; y - 0 == y otherwise)
+            y0 = __dsub_rn(y0, job.y_org);
+            y1 = __dsub_rn(y1, job.y_org);
             if (PASS == 2) {
                 const uint32_t k = atomicAdd(&q_n[warp], 1u);
                 if (k < (uint32_t)kWarpQueue) {

@@ -587,12 +587,13 @@ int rgpu_mask_banded_host(rgpu_ctx* ctx, const rgpu_path* path, const double tr[
         rgpu_dpath dp;
         if ((rc = stage_path(ctx, path, &dp))) return rc;
         std::vector<rgpu_job> jobs(bands.size());
+        std::vector<double> origins(bands.size());
         for (size_t i = 0; i < bands.size(); i++) {
             rgpu_job& j = jobs[i];
             std::memset(&j, 0, sizeof(j));
             j.path = &dp;
             std::memcpy(j.tr, tr, sizeof(j.tr));
-            j.tr[5] -= (double)bands[i].y0;  // translate(0, -y0) * tr: the reference's own y clipping crops the band
+            origins[i] = (double)bands[i].y0;  // the band's rows: flattened on the canvas, shifted as lines (JobDev::y_org), cropped by the reference's own y clipping
             j.fill_rule = fill_rule;
             j.mode = RGPU_JOB_MASK;
             j.canvas = d_img;
@@ -601,7 +602,10 @@ int rgpu_mask_banded_host(rgpu_ctx* ctx, const rgpu_path* path, const double tr[
             j.width = (uint32_t)width;
             j.height = (uint32_t)bands[i].rows;
         }
-        if ((rc = submit_sync(ctx, jobs.data(), jobs.size(), RGPU_BATCH_INDEPENDENT, 1))) return rc;
+        ctx->job_row_origin = origins.data();
+        rc = submit_sync(ctx, jobs.data(), jobs.size(), RGPU_BATCH_INDEPENDENT, 1);
+        ctx->job_row_origin = nullptr;
+        if (rc) return rc;
     }
     const uint64_t h2d = ctx->last_h2d_bytes;
     uint64_t d2h = 0;

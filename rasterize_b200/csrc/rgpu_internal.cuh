@@ -80,6 +80,10 @@ struct JobDev {
     int32_t ox, oy, sc0, sb0;
     int32_t fix_shift;     // fixed-point fraction bits of this batch's winding cells (kFixShift or kFixShiftWide)
     int32_t pad_;
+    // Row origin of a band job (rgpu_mask_banded_host): the path is flattened with the canvas transform — the very lines of
+    // the unsharded job — and this (integer-valued) origin is subtracted from the finished lines' y before they are binned,
+    // instead of folding a translate(0, -y0) into `tr`, which would round every transformed control point differently.  0 otherwise.
+    double y_org;
 };
 
 struct Status {

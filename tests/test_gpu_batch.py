@@ -192,9 +192,9 @@ def test_c5_whole_canvas_properties(rast, monkeypatch):
     (rgpu_mask_banded_host, 4.29 GB of f32): the run-coded download and dense copies (RGPU_E2E_RUNCODE=0, read per call) give the
     same bytes for the same jobs; coverage in [0, 1]; rows of the empty top band are exactly zero; sampled rows match the oracle;
     the run-coded call moves a fraction of the bytes.  Two blocks of bands rendered separately (what two GPUs do) stitch to the
-    whole-canvas image up to one f32 ulp in a handful of pixels: the band-local translate(0, -y0) changes the f64 rounding of the
-    transformed control points (y * tr4 + (tr5 - y0)), which at this size flips the last bit of 6 of 1.07e9 pixels — at 8192^2
-    and below the stitched image is bit-identical (test_mask_banded_is_bit_identical_to_single_mask)."""
+    whole-canvas image BIT FOR BIT: a band job flattens the path with the canvas transform and subtracts its integer row origin
+    from the finished lines (JobDev::y_org).  (With a translate(0, -y0) folded into the transform — what a caller of the plain
+    trait call would do — the transformed control points round differently and 6 of the 1.07e9 pixels differ by one f32 ulp.)"""
     p = assets.load_path("tv_stroked")
     c5 = assets.expected()["paths"]["tv_stroked"]["c5"]
     w, h = c5["size"]
@@ -220,8 +220,13 @@ def test_c5_whole_canvas_properties(rast, monkeypatch):
     rast.mask_banded(p, tr, other, rb.FillRule.NonZero, n_bands=64, band_first=0, band_count=40)
     monkeypatch.delenv("RGPU_E2E_RUNCODE")
     rast.mask_banded(p, tr, other, rb.FillRule.NonZero, n_bands=64, band_first=40, band_count=24)
-    ys, xs = np.nonzero(whole.view(np.uint32) != other.view(np.uint32))
-    assert len(ys) <= 64 and (len(ys) == 0 or np.abs(whole[ys, xs] - other[ys, xs]).max() <= 1.2e-7)
+    assert np.array_equal(whole.view(np.uint32), other.view(np.uint32))
+    # the same block through the plain mask call with a translated transform: within one f32 ulp, in a handful of pixels
+    y0, y1 = sharding.band_rows(h, 5, 8)
+    band = np.zeros((y1 - y0, w), dtype=np.float32)
+    rast.mask(p, sharding.band_transform(tr, y0), band, rb.FillRule.NonZero)
+    ys, xs = np.nonzero(band.view(np.uint32) != whole[y0:y1].view(np.uint32))
+    assert len(ys) <= 64 and (len(ys) == 0 or np.abs(band[ys, xs] - whole[y0:y1][ys, xs]).max() <= 1.2e-7)
     op = opath(p)
     for y0 in (h // 2 - 32, 11111, h - 5000):
         ref = np.zeros((64, w))
