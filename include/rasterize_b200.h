@@ -101,7 +101,8 @@ int rgpu_mask(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill
 int rgpu_mask_f32(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], int fill_rule, float* img, size_t width,
                   size_t height);
 /* `Rasterizer::mask_iter` (src/rasterize.rs:61-67, 313-355): pixels with abs(alpha) >= 1e-6 in row-major
- * order; internal (width+1) canvas, overflow column dropped. *n_out is the full count. */
+ * order; internal (width+1) canvas, overflow column dropped.  The list is compacted on the device; the first min(n, cap)
+ * records are written to `out` (NULL: none).  *n_out is the full count; RGPU_ERR_CAPACITY when it exceeds cap. */
 int rgpu_mask_iter(rgpu_ctx* ctx, const rgpu_path* path, const double tr[6], size_t width, size_t height, int fill_rule,
                    rgpu_pixel* out, size_t cap, size_t* n_out);
 /* Dense form of mask_iter: coverage[y*width + x] (0 where the iterator yields nothing). */
@@ -323,8 +324,10 @@ enum {
  * (src/path.rs:492-507, src/rasterize.rs:70-115) for n_paths independent paths with HOST buffers: path i is filled at
  * trs[6 i .. 6 i + 6) (NULL = identity for all) onto its own fresh image, and the images are returned back to back in
  * `out_host` (n_paths x height x width pixels of `out_format`).  The batch runs in chunks: while chunk k renders,
- * chunk k - 1 is on its way to the host on a second stream (cudaMemcpyAsync into `out_host`, which should be pinned),
- * so the call is bound by the PCIe download.  `paint` is ignored for RGPU_OUT_COVERAGE. */
+ * chunk k - 1 is on its way to the host on a second stream (cudaMemcpyAsync into `out_host`, which should be pinned)
+ * and chunk k + 1 is prepared on a helper thread.  RGPU_OUT_LINCOLOR with a plain solid paint: a share of every chunk
+ * crosses PCIe as f32 coverage and host threads write colour * coverage — the multiplication the kernel does last — into
+ * `out_host` (the same bytes; the share adapts to the host).  `paint` is ignored for RGPU_OUT_COVERAGE. */
 int rgpu_fill_batch_host(rgpu_ctx* ctx, const rgpu_path* all, const uint32_t* path_subpath_offsets, size_t n_paths, const double* trs,
                          int fill_rule, const rgpu_paint* paint, uint32_t width, uint32_t height, int out_format, void* out_host);
 
