@@ -75,3 +75,70 @@ def test_random_paths_match_oracle(rast, case):
         for px in op.mask_iter(tr, w, h, O.NONZERO):
             ocov[px[1], px[0]] = px[2]
         assert np.abs(cov - ocov).max() <= COV_TOL, (case, rep)
+
+
+def test_random_paints_deviation_report(rast, record_property):
+    """`Paint::at` + `blend_over` take four documented shortcuts on the device (a rounded reciprocal in unmultiply, the
+    reciprocal of the stop interval and of 2a, one affine form for the linear gradient: DESIGN section 1 / raster_device.cuh) —
+    each far inside the budget, none bit-exact.  This sweep pins how far: 48 random gradients (linear / radial with a focal
+    point, 2-9 random stops with random alpha, every spread, stored linear or sRGB, user-space and bounding-box units, random
+    paint transforms) filled through random paths over a random opaque-ish background, against the oracle's fill.  The
+    largest LinColor deviation is asserted against 1/20 of the budget (measured: 3.6e-7; RGBA8: 2 of 3.2 M components off by one) and both are recorded (junit property / stdout), so a
+    drift towards the 2e-4 / 1 LSB bars shows up long before it fails."""
+    rng = np.random.default_rng(20261018)
+    w, h = 150, 110
+    worst_lin, worst_rgba, n_rgba_off = 0.0, 0, 0
+    for case in range(48):
+        p = random_path(rng, w, h, n_sub=int(rng.integers(1, 4)), n_seg=int(rng.integers(2, 8)))
+        tr = np.array([1.0, float(rng.uniform(-0.2, 0.2)), float(rng.uniform(-5, 5)), float(rng.uniform(-0.2, 0.2)), 1.0, float(rng.uniform(-5, 5))])
+        n_stops = int(rng.integers(2, 10))
+        pos = np.sort(rng.random(n_stops))
+        if case % 5 == 0:
+            pos[1] = pos[0]  # a hard stop
+        stops = []
+        for k in range(n_stops):
+            a = float(rng.choice([1.0, 1.0, rng.uniform(0.05, 1.0)]))
+            rgb = rng.random(3) * a
+            stops.append((float(pos[k]), [float(rgb[0]), float(rgb[1]), float(rgb[2]), a]))
+        units = int(case % 3 == 0)  # every third: objectBoundingBox
+        spread = int(case % 3)
+        linear_colors = bool(case % 2)
+        ptr = O.transform_mul(O.rotate(float(rng.uniform(-1, 1))), O.scale(float(rng.uniform(0.5, 1.5)), float(rng.uniform(0.5, 1.5))))
+        sc = 1.0 if units else float(w)
+        if case % 4 < 2:
+            op = O.OraclePaint.linear(stops, (float(rng.uniform(0, 0.5)) * sc, float(rng.uniform(0, 0.5)) * sc),
+                                      (float(rng.uniform(0.5, 1)) * sc, float(rng.uniform(0.3, 1)) * sc), units=units,
+                                      linear_colors=linear_colors, spread=spread, tr=ptr)
+        else:
+            c = (float(rng.uniform(0.3, 0.7)) * sc, float(rng.uniform(0.3, 0.7)) * sc)
+            r = float(rng.uniform(0.2, 0.6)) * sc
+            f = (c[0] + float(rng.uniform(-0.3, 0.3)) * r, c[1] + float(rng.uniform(-0.3, 0.3)) * r)
+            op = O.OraclePaint.radial(stops, c, r, fcenter=f, fradius=float(rng.uniform(0, 0.1)) * r, units=units,
+                                      linear_colors=linear_colors, spread=spread, tr=ptr)
+        gp = rb.paint_from_desc(op.describe())
+        bg = rng.random((h, w, 4), dtype=np.float32)
+        bg[..., 3] = 0.5 + 0.5 * bg[..., 3]
+        bg[..., :3] *= bg[..., 3:4]
+        ref = bg.copy()
+        got = bg.copy()
+        rule, orule = ((rb.FillRule.NonZero, O.NONZERO), (rb.FillRule.EvenOdd, O.EVENODD))[case % 2]
+        bbox = None
+        if units:
+            bb = opath(p).bbox(O.IDENTITY) if hasattr(opath(p), "bbox") else None
+            if bb is None:
+                continue
+            bbox = np.asarray(bb, dtype=np.float64)
+        opath(p).fill(tr, orule, op, ref)
+        rast.fill(p, tr, rule, gp, got, bbox=bbox)
+        d_lin = float(np.abs(got - ref).max())
+        d_rgba = np.abs(O.lin_to_rgba(got).astype(np.int16) - O.lin_to_rgba(ref).astype(np.int16))
+        worst_lin = max(worst_lin, d_lin)
+        worst_rgba = max(worst_rgba, int(d_rgba.max()))
+        n_rgba_off += int((d_rgba != 0).sum())
+        assert d_lin <= 1e-5, (case, d_lin)  # measured: 3.6e-7
+        assert d_rgba.max() <= 1, (case, int(d_rgba.max()))
+    record_property("max_lincolor_deviation", worst_lin)
+    record_property("max_rgba8_deviation_lsb", worst_rgba)
+    record_property("rgba8_components_off_by_one", n_rgba_off)
+    print(f"random paints: max |LinColor| deviation {worst_lin:.3e} (budget 2e-4), max RGBA8 deviation {worst_rgba} LSB, "
+          f"{n_rgba_off} of {48 * w * h * 4} components off by one")
