@@ -50,7 +50,9 @@ __device__ __forceinline__ float4 unmultiply_rcp(float4 c) {
 __device__ __forceinline__ float4 into_linear(float4 c) {
     float4 u = unmultiply_rcp(c);
     float a = c.w;
-    return make_float4(fmul(s2l_lane(u.x), a), fmul(s2l_lane(u.y), a), fmul(s2l_lane(u.z), a), fmul(s2l_lane(u.w), a));
+    // the unmultiplied alpha is exactly 1 (0 for a transparent colour): its polynomial is a constant (1.0008736)
+    const float sw = (c.w <= 1e-6f) ? 0.0f : s2l_lane(1.0f);
+    return make_float4(fmul(s2l_lane(u.x), a), fmul(s2l_lane(u.y), a), fmul(s2l_lane(u.z), a), fmul(sw, a));
 }
 
 // `From<LinColor> for RGBA`, src/color.rs:164-175 with the x86 l2s polynomial; `as u8` saturates (NaN -> 0)
@@ -81,6 +83,8 @@ __device__ __forceinline__ double rem_euclid(double x, double rhs) {
 static __device__ float4 stops_at(const PaintDev& P, double t) {
     // partition_point(position < t) over the sorted stops == the number of stops left of t: a branch-free count with a
     // warp-uniform trip count instead of a divergent binary search
+    // (Leaving the loop at the first stop that is not left of t — the stops are sorted — was measured on config 3: 233.5 against
+    // 230.2 us; the divergent exit costs more than the skipped compares.)
     int lo = 0;
     for (int i = 0; i < P.n_stops; i++) lo += (P.stop_pos[i] < t) ? 1 : 0;
     int index = lo, size = P.n_stops;
